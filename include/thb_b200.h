@@ -1,0 +1,164 @@
+/* thb_b200.h -- C ABI of libthb_b200.so: the B200 (sm_100a) implementation of THB-Diff's evaluation hot path.
+ *
+ * Conventions (all entry points):
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; sizes are element counts
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*); nothing synchronises, nothing allocates
+ *   - return value: 0 = ok, negative = THB_E_* (thb_last_error() gives the text for the calling thread)
+ *   - no torch / C++ types cross this boundary; the reference-side bindings are shown in INTEGRATION.md
+ *
+ * Each function names the reference interface it replaces (paths relative to the reference repo).
+ */
+#ifndef THB_B200_H
+#define THB_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define THB_API __attribute__((visibility("default")))
+#else
+#define THB_API
+#endif
+
+#define THB_MAX_LEVELS 8
+#define THB_INFO_W 8 /* ints per cellinfo row: level, c0, c1, c2, supp_off, S, tile_off, n_direct */
+
+enum {
+    THB_OK = 0,
+    THB_E_INVALID = -1,     /* bad argument (null pointer, size, unsupported degree combination ...) */
+    THB_E_CUDA = -2,        /* a CUDA runtime call failed; see thb_last_error() */
+    THB_E_UNSUPPORTED = -3, /* valid request the library has no kernel for */
+};
+
+/* Channel bit masks for thb_basis_tiled / thb_eval_fused: bit k set = use the first derivative of the 1-D
+ * basis in dimension k.  0 = values; (1<<k) = d/du_k (true gradient component); all bits = the reference's
+ * return_mode=[False,True] "derivative" (mixed partial, THB/core.py:686-701). */
+#define THB_CH_VALUE 0
+
+/* Packed hierarchy descriptor (see thb_diff_b200/packed.py for the producer). Passed by pointer from the
+ * host; the library copies it into kernel arguments.  Replaces the dict-of-levels inputs
+ * (knotvectors, cells, ac_cells_ac_supp, fn_coeffs, fn_shapes) of THB/core.py:157-189 and :604-701. */
+typedef struct thb_space_desc {
+    int32_t ndim;                           /* 2 or 3 */
+    int32_t nlevels;                        /* <= THB_MAX_LEVELS */
+    int32_t degree[3];                      /* degree[2] = 0 in 2-D */
+    int32_t tile_stride;                    /* floats per tile row: (p+1)^d rounded up to a multiple of 4 */
+    int32_t nslots;                         /* number of active cells */
+    int32_t max_tiled;                      /* max number of tiled supports of any cell */
+    int32_t knot_off[THB_MAX_LEVELS][3];    /* offset of each 1-D knot vector inside `knots` */
+    int32_t knot_len[THB_MAX_LEVELS][3];
+    int32_t ncells[THB_MAX_LEVELS][3];
+    int32_t nfns[THB_MAX_LEVELS][3];
+    int64_t fn_off[THB_MAX_LEVELS + 1];     /* level offsets of the flat function / control-point numbering */
+    int64_t cell_slot_off[THB_MAX_LEVELS];  /* level offsets inside `cell_slot` */
+    const float* knots;                     /* f32, all levels and dims */
+    const int32_t* cell_slot;               /* per cell: slot id of the active cell, or -1 */
+    const int32_t* cellinfo;                /* [nslots][THB_INFO_W] */
+    const uint64_t* dmask;                  /* [nslots] own-level window activity bits */
+    const int32_t* supp_jm;                 /* CSR values: flat ids of each cell's supports, reference order */
+    const float* tiles;                     /* [ntiles][tile_stride] */
+} thb_space_desc;
+
+/* A plan = the points of one batch grouped by active cell. All arrays are caller-allocated device memory:
+ *   slot [N] i32, perm [N] i32, cell_count/cell_start/cell_cursor [nslots+1] i32,
+ *   items [max_items][4] i32 (slot, begin, count, 0), counters [4] i32 (counters[0] = number of items).
+ * max_items >= N / points_per_item + nslots. */
+typedef struct thb_plan_desc {
+    int64_t npoints;
+    int32_t points_per_item;
+    int32_t max_items;
+    int32_t* slot;
+    int32_t* perm;
+    int32_t* cell_count;
+    int32_t* cell_start;
+    int32_t* cell_cursor;
+    int32_t* items;
+    int32_t* counters;
+} thb_plan_desc;
+
+THB_API int thb_version(void);
+THB_API const char* thb_last_error(void);
+
+/* ---- L5 boundary: the torch extension THB_eval ------------------------------------------------------------
+ * thb_eval_forward  replaces THB_eval.forward / cpp_forward
+ *     (THB/THB_extensions/compute_pts_cuda_kernels.cu:3-26,49-71; compute_pts.cpp:4-29)
+ *     out[i, :] = sum_{j in [cumsum[i-1], cumsum[i])} phi[j] * ctrl_pts[jm[j], :]   (cumsum inclusive)
+ * thb_eval_backward replaces THB_eval.backward / cpp_backward
+ *     (compute_pts_cuda_kernels.cu:28-47,73-97; compute_pts.cpp:31-54)
+ *     grad_ctrl_pts[jm[j], :] += phi[j] * grad_out[i, :];  grad_ctrl_pts is zeroed by the callee.
+ * jm / cumsum may be int64 (reference dtype) or int32; cp_dim in 1..4 (reference: 3). */
+THB_API int thb_eval_forward(const float* ctrl_pts, const void* jm, int jm_is_i64, const float* phi, const void* cumsum,
+                     int cumsum_is_i64, float* out, int64_t npoints, int cp_dim, void* stream);
+THB_API int thb_eval_backward(const float* grad_out, const void* jm, int jm_is_i64, const float* phi, const void* cumsum,
+                      int cumsum_is_i64, float* grad_ctrl_pts, int64_t npoints, int64_t nctrl, int cp_dim,
+                      void* stream);
+
+/* ---- 1-D primitives ----------------------------------------------------------------------------------------
+ * thb_find_spans replaces find_span_array_jax (THB/bspline_funcs.py:77-83): searchsorted(U,u,'right')-1,
+ *     >n -> n, u==U[-1] -> n-1, u<U[0] -> -1, n = nknots-degree-1.  params are read with element stride
+ *     `stride` (so a column of an [N,d] array can be passed).
+ * thb_basis_1d replaces basis_fns_vmap / der_basis_fns_vmap (bspline_funcs.py:185-194) using the O(p^2)
+ *     recursion of basisFun (bspline_funcs.py:86-101): values [N, degree+1] and (if non-null) first
+ *     derivatives of the functions span-degree .. span.  Out-of-domain points produce zeros. degree <= 5. */
+THB_API int thb_find_spans(const float* params, int64_t stride, int64_t npoints, const float* knots, int nknots, int degree,
+                   int32_t* spans, void* stream);
+THB_API int thb_basis_1d(const float* params, int64_t stride, int64_t npoints, const float* knots, int nknots, int degree,
+                 float* values, float* derivs, void* stream);
+
+/* ---- active-cell lookup: compute_active_span (THB/core.py:157-189) ----------------------------------------
+ * For every point the finest-level span per dimension, then the finest level whose cell is active.
+ * slot[i] = slot id of that cell (-1 for points outside the domain); num_supp[i] (nullable) = its number of
+ * supports; params is [N, ndim] row-major f32. */
+THB_API int thb_active_span(const thb_space_desc* space, const float* params, int64_t npoints, int32_t* slot,
+                    int32_t* num_supp, void* stream);
+
+/* Expands the per-cell CSR to per-point flat support ids in the reference's pair order
+ * (Jm of THB/core.py:644-650 and THB/torch_funcs.py:72-78). offsets = exclusive prefix sum of num_supp. */
+THB_API int thb_expand_supports(const thb_space_desc* space, const int32_t* slot, const int64_t* offsets, int64_t npoints,
+                        void* jm_out, int jm_is_i64, void* stream);
+
+/* Groups the points of a batch by active cell (counting sort) and cuts the groups into work items.
+ * Computes plan->slot itself (same result as thb_active_span). */
+THB_API int thb_plan_build(const thb_space_desc* space, const float* params, const thb_plan_desc* plan, void* stream);
+
+/* ---- THB_basis_fns (THB/core.py:604-701; float64 statement: compute_THB_fns_tp, core.py:203-268) -----------
+ * phi_out[c][offsets[i] + s] for every channel c < nchannels, point i and support s of the point's cell. */
+THB_API int thb_basis_tiled(const thb_space_desc* space, const thb_plan_desc* plan, const float* params,
+                    const int64_t* offsets, const int32_t* channels, int nchannels, float* const* phi_out_host,
+                    void* stream);
+
+/* Legacy form of THB_basis_fns for callers that hold the reference's dense tables: coeffs is
+ * [nfn_total, prod(nfns_finest)] f32 (THB/core.py:636-643), jm/cumsum as in thb_eval_forward, evaluation at the
+ * finest level exactly as THB/core.py:652-677 (with the SURVEY Q2/Q3 repairs).  The only entry point that
+ * synchronises the stream (it reads nnz = cumsum[npoints-1] back to size its grid). */
+THB_API int thb_basis_dense(const float* params, int64_t npoints, int ndim, const int32_t* degree, const float* knots,
+                    const int32_t* knot_off, const int32_t* knot_len, const int32_t* nfns_finest,
+                    const float* coeffs, const void* jm, int jm_is_i64, const int64_t* cumsum, int channel,
+                    float* phi_out, void* stream);
+
+/* ---- fused basis + evaluation (PHI never leaves the SM) ----------------------------------------------------
+ * out_host[c] is a device buffer [N, cp_dim] per channel.  cellnet != 0 folds the tiles into a per-cell local
+ * control net first (same result, far fewer FLOPs).  Replaces THB_basis_fns followed by THBEval.forward
+ * (THB/torch_funcs.py:22-33). */
+THB_API int thb_eval_fused(const thb_space_desc* space, const thb_plan_desc* plan, const float* params,
+                   const float* ctrl_pts, int cp_dim, const int32_t* channels, int nchannels, float* const* out_host,
+                   int cellnet, void* stream);
+/* grad_ctrl_pts[nctrl, cp_dim] (zeroed by the callee) = A^T grad_out, A = value-channel basis matrix.
+ * Replaces THBEval.backward (THB/torch_funcs.py:35-47) for the fused path. */
+THB_API int thb_eval_fused_backward(const thb_space_desc* space, const thb_plan_desc* plan, const float* params,
+                            const float* grad_out, int cp_dim, float* grad_ctrl_pts, int64_t nctrl, void* stream);
+
+/* ---- measurement helpers -----------------------------------------------------------------------------------
+ * Dependent-chain FP32 FMA micro-kernel used by bench.py to measure the FP32 roofline denominator.
+ * variant 0: scalar FFMA, 1: packed FFMA2.  Enqueues one launch; flops_out_host receives the FLOP count. */
+THB_API int thb_fma_peak(int variant, int iters, float* sink, double* flops_out_host, void* stream);
+/* Number of kernels this library has launched in the calling process (for bench.py's gpu_launches). */
+THB_API int64_t thb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* THB_B200_H */

@@ -31,3 +31,75 @@ def rel_err(a, b, scale=1.0):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     return np.abs(a - b) / np.maximum(np.abs(b), scale)
+
+
+def product_space_from_golden(g):
+    from thb_diff_b200 import multilevel_spline_space as M
+
+    d = int(g["ndim"])
+    nlev = int(g["num_levels"])
+    tp = M.TensorProduct([M.BSpline(g[f"knots0_{k}"], int(g["degrees"][k])) for k in range(d)])
+    h = M.Space(tp, nlev)
+    h.build_hierarchy_from_domain_sequence()
+    for row in g["boxes"]:
+        h.refine_box(tuple(int(x) for x in row[1:1 + d]), tuple(int(x) for x in row[1 + d:1 + 2 * d]), int(row[0]))
+    h.build_hierarchy_from_domain_sequence()
+    return h
+
+
+def emulate_packed_point(P, x, want_grad=False):
+    """NumPy emulation of the tile kernels on the packed tables (tests the host-side builder on CPU):
+    finest-level span -> dyadic walk to the active cell -> cell-level Cox-de Boor -> direct + tiled PHI."""
+    d, L, p, T = P.ndim, P.nlevels, P.degrees, P.T
+    knots = P.knots.cpu().numpy().astype(np.float64)
+    cs = P.cell_slot.cpu().numpy()
+    info = P.cellinfo.cpu().numpy()
+    dmask = P.dmask.cpu().numpy().view(np.uint64)
+    jm = P.supp_jm.cpu().numpy()
+    tiles = P.tiles.cpu().numpy().astype(np.float64)
+
+    def U(l, k):
+        return knots[P.knot_off[l, k]:P.knot_off[l, k] + P.knot_len[l, k]]
+
+    cf = [int(O.find_span_array(np.array([x[k]]), U(L - 1, k), p[k])[0]) - p[k] for k in range(d)]
+    if any(c < 0 or c >= P.sh_cells[L - 1][k] for k, c in enumerate(cf)):
+        return None
+    slot = -1
+    for l in range(L - 1, -1, -1):
+        c = [v >> (L - 1 - l) for v in cf]
+        slot = cs[P.cell_slot_off[l] + np.ravel_multi_index(c, P.sh_cells[l])]
+        if slot >= 0:
+            break
+    if slot < 0:
+        return None
+    lev, c, soff, S, toff, ndir = info[slot, 0], info[slot, 1:1 + d], info[slot, 4], info[slot, 5], info[slot, 6], info[slot, 7]
+    Nd = [O.basis_funs_and_ders(int(c[k]) + p[k], x[k], p[k], U(lev, k)) for k in range(d)]
+
+    def tp(sel):
+        t = Nd[0][sel[0]]
+        for k in range(1, d):
+            t = np.multiply.outer(t, Nd[k][sel[k]])
+        return t.reshape(-1)
+
+    chans = [tp([0] * d)] + ([tp([1 if k == j else 0 for k in range(d)]) for j in range(d)] if want_grad else [])
+    res = []
+    for t in chans:
+        phi = [t[b] for b in range(T) if (int(dmask[slot]) >> b) & 1] if ndir else []
+        assert len(phi) == ndir
+        for s in range(S - ndir):
+            phi.append(float(tiles[toff + s, :T] @ t))
+        res.append(np.array(phi))
+    out = (int(lev), tuple(int(v) for v in c), jm[soff:soff + S].astype(np.int64), res[0])
+    if want_grad:
+        out = out + (np.stack(res[1:], axis=1),)
+    return out
+
+
+def host_tables_from_packed(P):
+    """The packed tables of a (CPU- or GPU-resident) PackedHierarchy as input of the C oracle."""
+    from oracle import c_oracle
+
+    return c_oracle.HostTables(P.ndim, P.nlevels, P.degrees, P.TS, P.knot_off, P.knot_len,
+                               [list(P.sh_cells[l]) for l in range(P.nlevels)], P.cell_slot_off,
+                               P.knots.cpu().numpy(), P.cell_slot.cpu().numpy(), P.cellinfo.cpu().numpy(),
+                               P.dmask.cpu().numpy().view(np.uint64), P.supp_jm.cpu().numpy(), P.tiles.cpu().numpy())

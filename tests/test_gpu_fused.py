@@ -1,0 +1,131 @@
+"""Fused basis+evaluation kernels (forward, derivative channels, backward) vs the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import SPACES, load_golden, product_space_from_golden, rel_err
+from oracle import thb_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+IDENTITY_OK = [s for s in SPACES if s != "twoblock2d"]
+
+
+def _setup(name, onehot=True, cp_dim=3, seed=0):
+    from thb_diff_b200 import engine
+    from thb_diff_b200.packed import PackedHierarchy
+
+    g = load_golden(name)
+    h = product_space_from_golden(g)
+    P = PackedHierarchy.from_space(h, device="cuda", onehot_direct=onehot)
+    plan = engine.Plan(P, g["params"])
+    cp = np.random.default_rng(seed).standard_normal((P.nCP, cp_dim)).astype(np.float32)
+    cs = np.cumsum(g["num_supp"])
+    return g, h, P, plan, cp, cs
+
+
+@pytest.mark.parametrize("cellnet", [False, True])
+@pytest.mark.parametrize("onehot", [True, False])
+@pytest.mark.parametrize("name", IDENTITY_OK)
+def test_fused_forward(name, onehot, cellnet):
+    from thb_diff_b200 import engine
+
+    g, h, P, plan, cp, cs = _setup(name, onehot)
+    ref = O.eval_forward(cp, g["Jm"], g["PHI"], cs)
+    out = engine.eval_fused(P, plan, torch.from_numpy(cp).cuda(), cellnet=cellnet)[0].cpu().numpy()
+    assert rel_err(out, ref, scale=np.abs(ref).max()).max() <= TOL
+
+
+@pytest.mark.parametrize("ppt", ["1", "2"])
+def test_fused_forward_points_per_thread_variants(ppt, monkeypatch):
+    from thb_diff_b200 import engine
+
+    monkeypatch.setenv("THB_FUSED_PPT", ppt)
+    g, h, P, plan, cp, cs = _setup("block3d")
+    ref = O.eval_forward(cp, g["Jm"], g["PHI"], cs)
+    out = engine.eval_fused(P, plan, torch.from_numpy(cp).cuda())[0].cpu().numpy()
+    assert rel_err(out, ref, scale=np.abs(ref).max()).max() <= TOL
+
+
+def test_fused_cp_dim4():
+    from thb_diff_b200 import engine
+
+    g, h, P, plan, cp, cs = _setup("block3d", cp_dim=4)
+    ref = O.eval_forward(cp, g["Jm"], g["PHI"], cs)
+    out = engine.eval_fused(P, plan, torch.from_numpy(cp).cuda())[0].cpu().numpy()
+    assert out.shape == ref.shape and rel_err(out, ref, scale=np.abs(ref).max()).max() <= TOL
+
+
+@pytest.mark.parametrize("name", ["graded2d", "block3d"])
+def test_greville_control_points_reproduce_the_parameters(name):
+    """Linear reproduction: evaluating with Greville abscissae as control points returns the params, and
+    the first derivatives are the identity."""
+    from thb_diff_b200 import configs, engine
+
+    g, h, P, plan, _, _ = _setup(name)
+    cp = torch.from_numpy(configs.greville_ctrl_pts(h, bump=0.0)).cuda()
+    out = engine.eval_fused(P, plan, cp)[0].cpu().numpy()
+    d = h.ndim
+    assert np.abs(out[:, :d] - g["params"]).max() < 1e-5
+    ders = engine.eval_fused(P, plan, cp, engine.grad_channels(d))
+    for k in range(d):
+        J = ders[k].cpu().numpy()[:, :d]
+        e = np.zeros(d)
+        e[k] = 1
+        assert np.abs(J - e).max() < 2e-4
+
+
+@pytest.mark.parametrize("name", IDENTITY_OK)
+def test_fused_backward(name):
+    from thb_diff_b200 import engine
+
+    g, h, P, plan, cp, cs = _setup(name)
+    go = np.random.default_rng(1).standard_normal((len(cs), 3)).astype(np.float32)
+    ref = O.eval_backward(go, cp.shape, g["Jm"], g["PHI"], cs)
+    got = engine.eval_fused_backward(P, plan, torch.from_numpy(go).cuda()).cpu().numpy()
+    assert rel_err(got, ref, scale=np.abs(ref).max()).max() <= TOL
+
+
+def test_fused_module_autograd_matches_csr_path():
+    from thb_diff_b200 import core
+    from thb_diff_b200.torch_funcs import THB_fused_module, THB_nn_module, prepare_data_for_CUDA_evaluation
+
+    g, h, P, plan, cp, cs = _setup("block3d")
+    supp, ns = core.compute_active_span(g["params"], h.knotvectors, h.cells, h.degrees, P)
+    PHI = core.THB_basis_fns(g["params"], supp, ns, P, h.sh_fns, h.knotvectors, h.degrees)
+    cpt, Jm, phi, cumsum, dev = prepare_data_for_CUDA_evaluation(PHI, supp, ns, cp, None, h.sh_fns, "cuda")
+    a = cpt.clone().requires_grad_(True)
+    b = cpt.clone().requires_grad_(True)
+    out_a = THB_nn_module(Jm, phi, cumsum, "cuda")(a)
+    out_b = THB_fused_module(P, g["params"])(b)
+    w = torch.randn_like(out_a)
+    (out_a * w).sum().backward()
+    (out_b * w).sum().backward()
+    assert rel_err(out_b.detach().cpu().numpy(), out_a.detach().cpu().numpy(), scale=float(out_a.abs().max())).max() <= TOL
+    assert rel_err(b.grad.cpu().numpy(), a.grad.cpu().numpy(), scale=float(a.grad.abs().max())).max() <= TOL
+
+
+def test_many_points_per_cell_and_ragged_tail():
+    """More points per cell than one work item holds, item tails, repeated evaluation with one plan."""
+    from thb_diff_b200 import engine
+    from thb_diff_b200.packed import PackedHierarchy
+
+    g = load_golden("block2d")
+    h = product_space_from_golden(g)
+    P = PackedHierarchy.from_space(h, device="cuda")
+    rng = np.random.default_rng(2)
+    prm = rng.random((20011, 2)).astype(np.float32)
+    prm[:5000] = prm[:5000] * 0.05 + np.array([0.31, 0.41], dtype=np.float32)  # ~5000 points in very few cells
+    plan = engine.Plan(P, prm)
+    cp = rng.standard_normal((P.nCP, 3)).astype(np.float32)
+    cpt = torch.from_numpy(cp).cuda()
+    out = engine.eval_fused(P, plan, cpt)[0]
+    out2 = engine.eval_fused(P, plan, cpt, cellnet=True)[0]
+    sp = __import__("helpers").oracle_space_from_golden(g)
+    de = O.DirectEvaluator(sp.knotvectors, sp.degrees, sp.cells, sp.fns, sp.Coeff)
+    idx = rng.choice(len(prm), 300, replace=False)
+    ref = np.stack([(lambda r: (r[3][:, None] * cp[r[2]].astype(np.float64)).sum(0))(de.point(prm[i])) for i in idx])
+    scale = np.abs(ref).max()
+    assert rel_err(out.cpu().numpy()[idx], ref, scale=scale).max() <= TOL
+    assert rel_err(out2.cpu().numpy()[idx], ref, scale=scale).max() <= TOL
+    assert torch.equal(engine.eval_fused(P, plan, cpt)[0], out)  # deterministic forward

@@ -1,0 +1,86 @@
+"""The plain-C oracle vs the NumPy oracle / golden fixtures (which are pinned to the reference), and the
+host-side packed-table builder (thb_diff_b200.packed) through it -- all on CPU."""
+import numpy as np
+import pytest
+
+from helpers import GOLDEN, SPACES, emulate_packed_point, host_tables_from_packed, load_golden, product_space_from_golden
+from oracle import c_oracle
+from oracle import thb_oracle as O
+
+IDENTITY_OK = [s for s in SPACES if s != "twoblock2d"]
+
+
+def test_c_spans_and_basis():
+    k = dict(np.load(f"{GOLDEN}/kat.npz"))
+    assert c_oracle.find_spans(k["span_u"], k["U_B"], 3).tolist() == [-1, 3, 3, 4, 4, 5, 9, 9, 9, 10]
+    N, dN = c_oracle.basis_funs(5, 0.45, 3, k["U_B"])
+    assert np.allclose(N, k["N_045"], atol=1e-15) and np.allclose(dN, k["dN_045"], atol=1e-12)
+
+
+def test_c_contraction_matches_compiled_reference():
+    c = dict(np.load(f"{GOLDEN}/contraction.npz"))
+    for tag in "abc":
+        fwd = c_oracle.eval_forward(c[f"{tag}_cp"], c[f"{tag}_Jm"], c[f"{tag}_phi"], c[f"{tag}_cumsum"])
+        bwd = c_oracle.eval_backward(c[f"{tag}_grad_out"], c[f"{tag}_cp"].shape, c[f"{tag}_Jm"], c[f"{tag}_phi"], c[f"{tag}_cumsum"])
+        assert np.array_equal(fwd, c[f"{tag}_fwd"])   # same float accumulation order as compute_pts.cpp
+        assert np.array_equal(bwd, c[f"{tag}_bwd"])
+
+
+@pytest.mark.parametrize("onehot", [True, False])
+@pytest.mark.parametrize("name", IDENTITY_OK)
+def test_packed_tables_reproduce_reference_phi(name, onehot):
+    from thb_diff_b200.packed import PackedHierarchy
+
+    g = load_golden(name)
+    h = product_space_from_golden(g)
+    P = PackedHierarchy.from_space(h, device="cpu", onehot_direct=onehot)
+    ht = host_tables_from_packed(P)
+    off = np.concatenate([[0], np.cumsum(g["num_supp"])[:-1]])
+    cp = np.random.default_rng(0).standard_normal((P.nCP, 3)).astype(np.float32)
+    r = ht.eval(g["params"], cp, want_phi=True, offsets=off, nnz=len(g["PHI"]))
+    info = P.cellinfo_host
+    assert np.array_equal(info[r["slot"], 0], g["span_level"])
+    assert np.array_equal(info[r["slot"], 1:1 + P.ndim], g["span_cell"])
+    assert np.array_equal(info[r["slot"], 5], g["num_supp"])
+    assert np.abs(r["phi"] - g["PHI"]).max() < 5e-7          # tables and knots are float32
+    ref = O.eval_forward(cp, g["Jm"], g["PHI"], np.cumsum(g["num_supp"]))
+    assert np.abs(r["out"] - ref).max() < 5e-6
+    # the python emulation used elsewhere agrees too
+    e = emulate_packed_point(P, g["params"][3])
+    assert np.abs(e[3] - g["PHI"][off[3]:off[3] + g["num_supp"][3]]).max() < 5e-7
+
+
+def test_packed_builder_rejects_bad_input():
+    from thb_diff_b200 import multilevel_spline_space as M
+    from thb_diff_b200.packed import PackedHierarchy
+
+    g = load_golden("block2d")
+    h = product_space_from_golden(g)
+    bad = {l: h.fns[l].copy() for l in h.fns}
+    bad[1][0, 0] = 1  # an active level-1 function over an active level-0 cell
+    with pytest.raises(ValueError):
+        PackedHierarchy.build(h.knotvectors, h.degrees, h.cells, bad, h.Coeff, device="cpu")
+    U = np.array([0, 0, 0, 0.5, 0.5, 1, 1, 1.0])  # repeated interior knot
+    with pytest.raises(ValueError):  # interior multiplicities are not supported (refinement would drop them)
+        sp = M.Space(M.TensorProduct([M.BSpline(U, 2), M.BSpline(U, 2)]), 2)
+        sp.build_hierarchy_from_domain_sequence()
+        PackedHierarchy.from_space(sp, device="cpu")
+
+
+def test_bench_space_partition_of_unity_and_linear_reproduction():
+    """The C3 space generator (graded nested boxes): PoU and Greville reproduction on random points."""
+    from thb_diff_b200 import configs
+    from thb_diff_b200.packed import PackedHierarchy
+
+    sp = configs.cubic3d_space(active_levels=4)  # BASELINE config 3 space
+    P = PackedHierarchy.from_space(sp, device="cpu")
+    ht = host_tables_from_packed(P)
+    prm = np.random.default_rng(1).random((20000, 3)).astype(np.float32)
+    cp = configs.greville_ctrl_pts(sp, bump=0.0)
+    ones = np.ones((P.nCP, 1), dtype=np.float32)
+    r = ht.eval(prm, cp)
+    assert r["inside"] == len(prm)
+    assert np.abs(r["out"] - prm).max() < 2e-6
+    assert np.abs(ht.eval(prm, ones)["out"] - 1).max() < 2e-6
+    levels = P.cellinfo_host[r["slot"], 0]
+    assert set(levels.tolist()) == {0, 1, 2, 3}

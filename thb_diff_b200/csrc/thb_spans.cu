@@ -1,0 +1,270 @@
+// Span search, 1-D basis API kernels, active-cell lookup and the plan (points grouped by active cell).
+//   find_span_array_jax      THB/bspline_funcs.py:77-83      -> thb_find_spans
+//   basis_fns_vmap / der_*   THB/bspline_funcs.py:185-194    -> thb_basis_1d
+//   compute_active_span      THB/core.py:157-189             -> thb_active_span, thb_plan_build
+//   Jm construction          THB/core.py:644-650             -> thb_expand_supports
+#include "thb_common.cuh"
+
+namespace {
+
+constexpr int kMaxSmemKnots = 2048;
+
+__global__ void __launch_bounds__(256) k_find_spans(const float* __restrict__ params, int64_t stride, int64_t n,
+                                                    const float* __restrict__ knots, int nknots, int degree,
+                                                    int32_t* __restrict__ spans) {
+    __shared__ float sk[kMaxSmemKnots];
+    const bool in_smem = nknots <= kMaxSmemKnots;
+    if (in_smem) {
+        for (int i = threadIdx.x; i < nknots; i += blockDim.x) sk[i] = knots[i];
+        __syncthreads();
+    }
+    const float* U = in_smem ? sk : knots;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        spans[i] = span_right(U, nknots, degree, params[i * stride]);
+}
+
+__global__ void __launch_bounds__(256) k_basis_1d(const float* __restrict__ params, int64_t stride, int64_t n,
+                                                  const float* __restrict__ knots, int nknots, int degree,
+                                                  float* __restrict__ values, float* __restrict__ derivs) {
+    __shared__ float sk[kMaxSmemKnots];
+    const bool in_smem = nknots <= kMaxSmemKnots;
+    if (in_smem) {
+        for (int i = threadIdx.x; i < nknots; i += blockDim.x) sk[i] = knots[i];
+        __syncthreads();
+    }
+    const float* U = in_smem ? sk : knots;
+    const int nf = nknots - degree - 1;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float u = params[i * stride];
+        const int s = span_right(U, nknots, degree, u);
+        float N[THB_MAX_DEG + 1], dN[THB_MAX_DEG + 1];
+        const bool ok = s >= degree && s < nf;
+        if (ok) cox_de_boor_rt(degree, s, u, U, N, derivs ? dN : nullptr);
+        for (int r = 0; r <= degree; ++r) {
+            values[i * (degree + 1) + r] = ok ? N[r] : 0.0f;
+            if (derivs) derivs[i * (degree + 1) + r] = ok ? dN[r] : 0.0f;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_active_span(const __grid_constant__ thb_space_desc sp, const float* __restrict__ params,
+                                                     int64_t n, int32_t* __restrict__ slot_out, int32_t* __restrict__ nsupp_out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float u[3] = {0.f, 0.f, 0.f};
+        for (int k = 0; k < sp.ndim; ++k) u[k] = params[i * sp.ndim + k];
+        const int slot = locate_slot(sp, u);
+        slot_out[i] = slot;
+        if (nsupp_out) nsupp_out[i] = slot >= 0 ? __ldg(sp.cellinfo + (int64_t)slot * THB_INFO_W + 5) : 0;
+    }
+}
+
+// One warp per point: copies the cell's support ids into the point's segment (coalesced both ways).
+template <typename JT>
+__global__ void __launch_bounds__(256) k_expand_supports(const __grid_constant__ thb_space_desc sp, const int32_t* __restrict__ slot,
+                                                         const int64_t* __restrict__ offsets, int64_t n, JT* __restrict__ jm_out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = warp0; i < n; i += nwarps) {
+        const int s = slot[i];
+        if (s < 0) continue;
+        const int32_t* ci = sp.cellinfo + (int64_t)s * THB_INFO_W;
+        const int soff = __ldg(ci + 4), S = __ldg(ci + 5);
+        const int64_t o = offsets[i];
+        for (int j = lane; j < S; j += 32) jm_out[o + j] = (JT)__ldg(sp.supp_jm + soff + j);
+    }
+}
+
+// ---- plan: counting sort of the points by slot ----------------------------------------------------------
+// pass 1: slot per point + histogram.  Lanes of a warp that hit the same slot are combined with
+// __match_any_sync so that one atomic is issued per distinct slot per warp (grid-ordered points share cells).
+__global__ void __launch_bounds__(256) k_plan_count(const __grid_constant__ thb_space_desc sp, const float* __restrict__ params,
+                                                    int64_t n, int32_t* __restrict__ slot_out, int32_t* __restrict__ count) {
+    const int lane = threadIdx.x & 31;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t nround = (n + stride - 1) / stride * stride;  // keep whole warps in the loop for match_any
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
+        int slot = -1;
+        if (i < n) {
+            float u[3] = {0.f, 0.f, 0.f};
+            for (int k = 0; k < sp.ndim; ++k) u[k] = params[i * sp.ndim + k];
+            slot = locate_slot(sp, u);
+            slot_out[i] = slot;
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, slot);
+        if (slot >= 0 && lane == (__ffs(peers) - 1)) atomicAdd(count + slot, __popc(peers));
+    }
+}
+
+// pass 2 (single CTA): exclusive scan of the histogram -> cell_start; number of work items per cell and
+// their exclusive scan -> cell_cursor is reused to hold the first item index of each cell.
+__global__ void __launch_bounds__(1024) k_plan_scan(const int32_t* __restrict__ count, int32_t* __restrict__ start,
+                                                    int32_t* __restrict__ item_start, int nslots, int ppi,
+                                                    int32_t* __restrict__ counters) {
+    __shared__ int s_pts[1024];
+    __shared__ int s_itm[1024];
+    const int t = threadIdx.x;
+    const int per = (nslots + 1023) / 1024;
+    const int b = t * per, e = min(b + per, nslots);
+    int pts = 0, itm = 0;
+    for (int i = b; i < e; ++i) {
+        const int c = count[i];
+        pts += c;
+        itm += (c + ppi - 1) / ppi;
+    }
+    s_pts[t] = pts;
+    s_itm[t] = itm;
+    __syncthreads();
+    // Hillis-Steele inclusive scan over 1024 partials
+    for (int o = 1; o < 1024; o <<= 1) {
+        int vp = 0, vi = 0;
+        if (t >= o) {
+            vp = s_pts[t - o];
+            vi = s_itm[t - o];
+        }
+        __syncthreads();
+        s_pts[t] += vp;
+        s_itm[t] += vi;
+        __syncthreads();
+    }
+    int rp = s_pts[t] - pts, ri = s_itm[t] - itm;  // exclusive prefix of this thread's chunk
+    for (int i = b; i < e; ++i) {
+        const int c = count[i];
+        start[i] = rp;
+        item_start[i] = ri;
+        rp += c;
+        ri += (c + ppi - 1) / ppi;
+    }
+    if (t == 1023) {
+        start[nslots] = s_pts[1023];
+        counters[0] = s_itm[1023];  // number of work items
+        counters[1] = 0;            // dynamic scheduler cursor
+        counters[2] = s_pts[1023];  // number of in-domain points
+    }
+}
+
+// pass 3: work items of every cell; afterwards cell_cursor is zeroed to serve as the scatter cursor.
+__global__ void __launch_bounds__(256) k_plan_items(const int32_t* __restrict__ count, const int32_t* __restrict__ start,
+                                                    int32_t* __restrict__ item_start_then_cursor, int nslots, int ppi,
+                                                    int max_items, int4* __restrict__ items) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nslots) return;
+    const int c = count[s], b = start[s];
+    int it = item_start_then_cursor[s];
+    for (int o = 0; o < c; o += ppi, ++it) {
+        if (it < max_items) items[it] = make_int4(s, b + o, min(ppi, c - o), 0);
+    }
+    item_start_then_cursor[s] = 0;
+}
+
+// pass 4: scatter point ids into cell order; lanes of one warp that share a slot take consecutive places,
+// which keeps runs of neighbouring points contiguous in the permutation.
+__global__ void __launch_bounds__(256) k_plan_scatter(const int32_t* __restrict__ slot, int64_t n, const int32_t* __restrict__ start,
+                                                      int32_t* __restrict__ cursor, int32_t* __restrict__ perm) {
+    const int lane = threadIdx.x & 31;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t nround = (n + stride - 1) / stride * stride;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
+        const int s = i < n ? slot[i] : -1;
+        const unsigned peers = __match_any_sync(0xffffffffu, s);
+        const int leader = __ffs(peers) - 1;
+        int base = 0;
+        if (s >= 0 && lane == leader) base = atomicAdd(cursor + s, __popc(peers));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (s >= 0) perm[start[s] + base + __popc(peers & ((1u << lane) - 1u))] = (int32_t)i;
+    }
+}
+
+int grid_for(int64_t n, int block, int per_sm) {
+    int64_t want = (n + block - 1) / block;
+    int64_t cap = (int64_t)thb_num_sms() * per_sm;
+    if (want < 1) want = 1;
+    return (int)(want < cap ? want : cap);
+}
+
+}  // namespace
+
+int thb_check_space(const thb_space_desc* sp, const char* who) {
+    THB_REQUIRE(sp, "%s: null space descriptor", who);
+    THB_REQUIRE(sp->ndim == 2 || sp->ndim == 3, "%s: ndim must be 2 or 3", who);
+    THB_REQUIRE(sp->nlevels >= 1 && sp->nlevels <= THB_MAX_LEVELS, "%s: bad level count", who);
+    THB_REQUIRE(sp->nslots > 0, "%s: no active cells", who);
+    THB_REQUIRE(sp->knots && sp->cell_slot && sp->cellinfo && sp->dmask && sp->supp_jm && sp->tiles, "%s: null table", who);
+    return THB_OK;
+}
+
+extern "C" int thb_find_spans(const float* params, int64_t stride, int64_t npoints, const float* knots, int nknots,
+                              int degree, int32_t* spans, void* stream) {
+    THB_REQUIRE(npoints >= 0 && degree >= 0 && nknots >= 2 * (degree + 1), "thb_find_spans: bad sizes");
+    if (npoints == 0) return THB_OK;
+    THB_REQUIRE(params && knots && spans && stride >= 1, "thb_find_spans: null pointer");
+    k_find_spans<<<grid_for(npoints, 256, 16), 256, 0, (cudaStream_t)stream>>>(params, stride, npoints, knots, nknots, degree, spans);
+    THB_LAUNCHED();
+    return THB_OK;
+}
+
+extern "C" int thb_basis_1d(const float* params, int64_t stride, int64_t npoints, const float* knots, int nknots, int degree,
+                            float* values, float* derivs, void* stream) {
+    THB_REQUIRE(npoints >= 0 && degree >= 0 && degree <= THB_MAX_DEG && nknots >= 2 * (degree + 1), "thb_basis_1d: bad sizes");
+    if (npoints == 0) return THB_OK;
+    THB_REQUIRE(params && knots && values && stride >= 1, "thb_basis_1d: null pointer");
+    k_basis_1d<<<grid_for(npoints, 256, 16), 256, 0, (cudaStream_t)stream>>>(params, stride, npoints, knots, nknots, degree, values, derivs);
+    THB_LAUNCHED();
+    return THB_OK;
+}
+
+extern "C" int thb_active_span(const thb_space_desc* space, const float* params, int64_t npoints, int32_t* slot,
+                               int32_t* num_supp, void* stream) {
+    int rc = thb_check_space(space, "thb_active_span");
+    if (rc) return rc;
+    THB_REQUIRE(npoints >= 0, "thb_active_span: negative point count");
+    if (npoints == 0) return THB_OK;
+    THB_REQUIRE(params && slot, "thb_active_span: null pointer");
+    k_active_span<<<grid_for(npoints, 256, 16), 256, 0, (cudaStream_t)stream>>>(*space, params, npoints, slot, num_supp);
+    THB_LAUNCHED();
+    return THB_OK;
+}
+
+extern "C" int thb_expand_supports(const thb_space_desc* space, const int32_t* slot, const int64_t* offsets, int64_t npoints,
+                                   void* jm_out, int jm_is_i64, void* stream) {
+    int rc = thb_check_space(space, "thb_expand_supports");
+    if (rc) return rc;
+    if (npoints <= 0) return THB_OK;
+    THB_REQUIRE(slot && offsets && jm_out, "thb_expand_supports: null pointer");
+    const int grid = grid_for(npoints * 32, 256, 16);
+    if (jm_is_i64)
+        k_expand_supports<long long><<<grid, 256, 0, (cudaStream_t)stream>>>(*space, slot, offsets, npoints, (long long*)jm_out);
+    else
+        k_expand_supports<int><<<grid, 256, 0, (cudaStream_t)stream>>>(*space, slot, offsets, npoints, (int*)jm_out);
+    THB_LAUNCHED();
+    return THB_OK;
+}
+
+extern "C" int thb_plan_build(const thb_space_desc* space, const float* params, const thb_plan_desc* plan, void* stream) {
+    int rc = thb_check_space(space, "thb_plan_build");
+    if (rc) return rc;
+    THB_REQUIRE(plan && plan->npoints >= 0 && plan->npoints < (int64_t)2147483647, "thb_plan_build: bad point count");
+    THB_REQUIRE(plan->points_per_item >= 32 && plan->points_per_item <= 1024, "thb_plan_build: points_per_item out of range");
+    THB_REQUIRE(plan->slot && plan->perm && plan->cell_count && plan->cell_start && plan->cell_cursor && plan->items && plan->counters,
+                "thb_plan_build: null plan buffer");
+    THB_REQUIRE((int64_t)plan->max_items >= plan->npoints / plan->points_per_item + space->nslots, "thb_plan_build: max_items too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n = plan->npoints;
+    const int ns = space->nslots;
+    THB_CUDA(cudaMemsetAsync(plan->cell_count, 0, sizeof(int32_t) * (ns + 1), st));
+    if (n > 0) {
+        THB_REQUIRE(params, "thb_plan_build: null params");
+        k_plan_count<<<grid_for(n, 256, 16), 256, 0, st>>>(*space, params, n, plan->slot, plan->cell_count);
+        THB_LAUNCHED();
+    }
+    k_plan_scan<<<1, 1024, 0, st>>>(plan->cell_count, plan->cell_start, plan->cell_cursor, ns, plan->points_per_item, plan->counters);
+    THB_LAUNCHED();
+    k_plan_items<<<(ns + 255) / 256, 256, 0, st>>>(plan->cell_count, plan->cell_start, plan->cell_cursor, ns, plan->points_per_item,
+                                                   plan->max_items, (int4*)plan->items);
+    THB_LAUNCHED();
+    if (n > 0) {
+        k_plan_scatter<<<grid_for(n, 256, 16), 256, 0, st>>>(plan->slot, n, plan->cell_start, plan->cell_cursor, plan->perm);
+        THB_LAUNCHED();
+    }
+    return THB_OK;
+}

@@ -1,0 +1,117 @@
+// Dispatch of the tile kernels by tensor-product shape, and the C entry points
+//   thb_basis_tiled (THB_basis_fns, THB/core.py:604-701), thb_eval_fused / thb_eval_fused_backward
+//   (THB_basis_fns + THBEval, THB/torch_funcs.py:22-47).
+#include <cstdlib>
+
+#include "thb_tile_impl.cuh"
+
+int thb_check_space(const thb_space_desc* sp, const char* who);
+
+namespace thb_tile {
+#define THB_SHAPES(X) \
+    X(2, 2, 1) X(3, 3, 1) X(4, 4, 1) X(3, 4, 1) X(4, 3, 1) X(2, 2, 2) X(3, 3, 3) X(4, 4, 4) X(3, 4, 3) X(3, 3, 4) X(3, 4, 4) X(4, 3, 3) X(4, 3, 4) X(4, 4, 3)
+#define THB_DECL(A, B, C) extern const ShapeOps shape_ops_##A##B##C;
+THB_SHAPES(THB_DECL)
+#define THB_REF(A, B, C) &shape_ops_##A##B##C,
+static const ShapeOps* const kShapes[] = {THB_SHAPES(THB_REF)};
+
+static const ShapeOps* find_shape(const thb_space_desc* sp) {
+    const int n0 = sp->degree[0] + 1, n1 = sp->degree[1] + 1, n2 = sp->ndim == 3 ? sp->degree[2] + 1 : 1;
+    for (const ShapeOps* s : kShapes)
+        if (s->n0 == n0 && s->n1 == n1 && s->n2 == n2) return s;
+    return nullptr;
+}
+
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+}  // namespace thb_tile
+
+using namespace thb_tile;
+
+static int check_plan(const thb_plan_desc* plan, const char* who) {
+    THB_REQUIRE(plan && plan->perm && plan->items && plan->counters, "%s: null plan buffer", who);
+    return THB_OK;
+}
+
+static int fill_channels(Args& ar, const int32_t* channels, int nchannels, int ndim, bool* der, const char* who) {
+    THB_REQUIRE(nchannels >= 1 && nchannels <= 4 && channels, "%s: 1..4 channels", who);
+    *der = false;
+    for (int c = 0; c < nchannels; ++c) {
+        THB_REQUIRE(channels[c] >= 0 && channels[c] < (1 << ndim), "%s: bad channel mask", who);
+        ar.channels[c] = channels[c];
+        if (channels[c]) *der = true;
+    }
+    ar.nch = nchannels;
+    return THB_OK;
+}
+
+extern "C" int thb_basis_tiled(const thb_space_desc* space, const thb_plan_desc* plan, const float* params,
+                               const int64_t* offsets, const int32_t* channels, int nchannels, float* const* phi_out_host,
+                               void* stream) {
+    int rc = thb_check_space(space, "thb_basis_tiled");
+    if (rc) return rc;
+    if ((rc = check_plan(plan, "thb_basis_tiled"))) return rc;
+    if (plan->npoints == 0) return THB_OK;
+    THB_REQUIRE(params && offsets && phi_out_host, "thb_basis_tiled: null pointer");
+    const ShapeOps* ops = find_shape(space);
+    if (!ops) return thb_set_error(THB_E_UNSUPPORTED, "thb_basis_tiled: no kernel for degrees (%d,%d,%d)", space->degree[0], space->degree[1], space->degree[2]);
+    Args ar = {};
+    bool der;
+    if ((rc = fill_channels(ar, channels, nchannels, space->ndim, &der, "thb_basis_tiled"))) return rc;
+    for (int c = 0; c < nchannels; ++c) {
+        THB_REQUIRE(phi_out_host[c], "thb_basis_tiled: null output");
+        ar.out[c] = phi_out_host[c];
+    }
+    ar.perm = plan->perm; ar.items = (const int4*)plan->items; ar.counters = plan->counters;
+    ar.params = params; ar.offsets = offsets;
+    cudaStream_t st = (cudaStream_t)stream;
+    THB_CUDA(cudaMemsetAsync(plan->counters + 1, 0, sizeof(int32_t), st));
+    return ops->basis(space, &ar, env_int("THB_BASIS_PPT", 1), der ? 1 : 0, st);
+}
+
+extern "C" int thb_eval_fused(const thb_space_desc* space, const thb_plan_desc* plan, const float* params,
+                              const float* ctrl_pts, int cp_dim, const int32_t* channels, int nchannels, float* const* out_host,
+                              int cellnet, void* stream) {
+    int rc = thb_check_space(space, "thb_eval_fused");
+    if (rc) return rc;
+    if ((rc = check_plan(plan, "thb_eval_fused"))) return rc;
+    if (plan->npoints == 0) return THB_OK;
+    THB_REQUIRE(params && ctrl_pts && out_host, "thb_eval_fused: null pointer");
+    THB_REQUIRE(cp_dim == 3 || cp_dim == 4, "thb_eval_fused: cp_dim must be 3 or 4 (pad other widths to 4)");
+    const ShapeOps* ops = find_shape(space);
+    if (!ops) return thb_set_error(THB_E_UNSUPPORTED, "thb_eval_fused: no kernel for degrees (%d,%d,%d)", space->degree[0], space->degree[1], space->degree[2]);
+    Args ar = {};
+    bool der;
+    if ((rc = fill_channels(ar, channels, nchannels, space->ndim, &der, "thb_eval_fused"))) return rc;
+    for (int c = 0; c < nchannels; ++c) {
+        THB_REQUIRE(out_host[c], "thb_eval_fused: null output");
+        ar.out[c] = out_host[c];
+    }
+    ar.perm = plan->perm; ar.items = (const int4*)plan->items; ar.counters = plan->counters;
+    ar.params = params; ar.ctrl_pts = ctrl_pts; ar.cellnet = cellnet ? 1 : 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    THB_CUDA(cudaMemsetAsync(plan->counters + 1, 0, sizeof(int32_t), st));
+    return ops->fused(space, &ar, env_int("THB_FUSED_PPT", 2), cp_dim, der ? 1 : 0, st);
+}
+
+extern "C" int thb_eval_fused_backward(const thb_space_desc* space, const thb_plan_desc* plan, const float* params,
+                                       const float* grad_out, int cp_dim, float* grad_ctrl_pts, int64_t nctrl, void* stream) {
+    int rc = thb_check_space(space, "thb_eval_fused_backward");
+    if (rc) return rc;
+    if ((rc = check_plan(plan, "thb_eval_fused_backward"))) return rc;
+    THB_REQUIRE(cp_dim == 3 || cp_dim == 4, "thb_eval_fused_backward: cp_dim must be 3 or 4");
+    THB_REQUIRE(grad_ctrl_pts && nctrl > 0, "thb_eval_fused_backward: null gradient buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    THB_CUDA(cudaMemsetAsync(grad_ctrl_pts, 0, sizeof(float) * nctrl * cp_dim, st));
+    if (plan->npoints == 0) return THB_OK;
+    THB_REQUIRE(params && grad_out, "thb_eval_fused_backward: null pointer");
+    const ShapeOps* ops = find_shape(space);
+    if (!ops) return thb_set_error(THB_E_UNSUPPORTED, "thb_eval_fused_backward: no kernel for degrees (%d,%d,%d)", space->degree[0], space->degree[1], space->degree[2]);
+    Args ar = {};
+    ar.perm = plan->perm; ar.items = (const int4*)plan->items; ar.counters = plan->counters;
+    ar.params = params; ar.grad_out = grad_out; ar.grad_cp = grad_ctrl_pts;
+    THB_CUDA(cudaMemsetAsync(plan->counters + 1, 0, sizeof(int32_t), st));
+    return ops->backward(space, &ar, cp_dim, st);
+}

@@ -1,0 +1,484 @@
+// Tile kernels: the hot path of THB_basis_fns (THB/core.py:604-701; float64 statement core.py:232-268)
+// fused with THBEval.forward / backward (THB/torch_funcs.py:22-47).
+//
+// Work decomposition:
+//   * the points of a batch are grouped by active cell (thb_plan_build); a work item = one cell and up to
+//     points_per_item of its points; persistent CTAs of 128 threads pull items from an atomic cursor
+//   * per item the CTA stages in shared memory: the 2p local knots per dimension, the control points of the
+//     cell's own-level window (SoA, zero where inactive) and -- in chunks of kChunk supports -- the
+//     (p+1)^d coefficient tiles of the coarser-level supports plus their control points
+//   * each thread owns PPT points: register-resident Cox-de Boor (values + first derivatives), the
+//     (p+1)^d tensor product kept as packed f32x2 register pairs, then
+//       PHI_s = <tile_s, tp>  with broadcast LDS.128 of the tile and FFMA2          (gather-multiply)
+//       out  += PHI_s * ctrl_pts[Jm_s]                                              (contraction)
+//     own-level supports have one-hot tiles: their PHI is tp[t] itself, so their contraction is three
+//     dot products of tp with the staged window control points.
+//   * MODE_BASIS writes PHI (THB_basis_fns); MODE_FUSED writes only the evaluated geometry.
+//   * cellnet: tiles are first folded into the window control points (a per-cell local control net
+//     Q[t] = CPwin[t] + sum_s tile_s[t] * CP_s), after which every point costs 3*(p+1)^d FMAs.
+#pragma once
+#include "thb_common.cuh"
+
+namespace thb_tile {
+
+constexpr int kThreads = 128;
+constexpr int kChunk = 64;  // supports staged per chunk
+
+enum { MODE_FUSED = 0, MODE_BASIS = 1 };
+
+struct Args {
+    const int32_t* perm;
+    const int4* items;
+    int32_t* counters;  // [0] = number of items, [1] = scheduler cursor
+    const float* params;
+    const float* ctrl_pts;   // fused
+    const int64_t* offsets;  // basis: exclusive prefix sum of num_supp (caller order)
+    float* out[4];           // per channel: fused [N, cp_dim] / basis [nnz]
+    int32_t channels[4];
+    int32_t nch;
+    int32_t cellnet;
+    // backward
+    const float* grad_out;
+    float* grad_cp;
+};
+
+template <int N0_, int N1_, int N2_>
+struct Shp {
+    static constexpr int N0 = N0_, N1 = N1_, N2 = N2_;
+    static constexpr int T = N0 * N1 * N2;
+    static constexpr int TS = (T + 3) / 4 * 4;
+    static constexpr int NP = TS / 2;  // f32x2 pairs
+    static constexpr int NQ = TS / 4;  // 16-byte quads
+    static constexpr int P0 = N0 - 1, P1 = N1 - 1, P2 = N2 - 1;
+};
+
+struct Item {
+    int slot, begin, count;
+    int lev, c0, c1, c2, soff, S, toff, ndir;
+    unsigned long long dm;
+};
+
+THB_DEV Item load_item(const thb_space_desc& sp, const int4* items, int it) {
+    Item r;
+    const int4 v = __ldg(items + it);
+    r.slot = v.x; r.begin = v.y; r.count = v.z;
+    const int4* ci = reinterpret_cast<const int4*>(sp.cellinfo + (int64_t)r.slot * THB_INFO_W);
+    const int4 a = __ldg(ci), b = __ldg(ci + 1);
+    r.lev = a.x; r.c0 = a.y; r.c1 = a.z; r.c2 = a.w;
+    r.soff = b.x; r.S = b.y; r.toff = b.z; r.ndir = b.w;
+    r.dm = __ldg(sp.dmask + r.slot);
+    return r;
+}
+
+template <class SH>
+THB_DEV void stage_knots(const thb_space_desc& sp, const Item& it, float (*s_knots)[8]) {
+    const int tid = threadIdx.x;
+    if (tid < 24) {
+        const int dim = tid >> 3, m = tid & 7;
+        const int P = dim == 0 ? SH::P0 : (dim == 1 ? SH::P1 : SH::P2);
+        const int c = dim == 0 ? it.c0 : (dim == 1 ? it.c1 : it.c2);
+        if (dim < sp.ndim && m < 2 * P) s_knots[dim][m] = __ldg(sp.knots + sp.knot_off[it.lev][dim] + c + 1 + m);
+    }
+}
+
+// 1-D bases of one point in the item's cell
+template <class SH, bool DER>
+struct Bases {
+    float n0[SH::N0], n1[SH::N1], n2[SH::N2];
+    float d0[DER ? SH::N0 : 1], d1[DER ? SH::N1 : 1], d2[DER ? SH::N2 : 1];
+    THB_DEV void eval(const float* u, const float (*s_knots)[8]) {
+        cox_de_boor<SH::P0, DER>(u[0], s_knots[0], n0, d0);
+        cox_de_boor<SH::P1, DER>(u[1], s_knots[1], n1, d1);
+        if (SH::N2 > 1) cox_de_boor<SH::P2, DER>(u[2], s_knots[2], n2, d2);
+        else { n2[0] = 1.0f; if (DER) d2[0] = 0.0f; }
+    }
+    // tensor product for a channel (bit k = derivative in dim k), C order (last dim fastest)
+    THB_DEV void tensor(int ch, float* tp) const {
+        float a[SH::N0], b[SH::N1], c[SH::N2];
+#pragma unroll
+        for (int i = 0; i < SH::N0; ++i) a[i] = (DER && (ch & 1)) ? d0[i] : n0[i];
+#pragma unroll
+        for (int i = 0; i < SH::N1; ++i) b[i] = (DER && (ch & 2)) ? d1[i] : n1[i];
+#pragma unroll
+        for (int i = 0; i < SH::N2; ++i) c[i] = (DER && (ch & 4)) ? d2[i] : n2[i];
+#pragma unroll
+        for (int i = 0; i < SH::N0; ++i)
+#pragma unroll
+            for (int j = 0; j < SH::N1; ++j) {
+                const float ab = a[i] * b[j];
+#pragma unroll
+                for (int k = 0; k < SH::N2; ++k) tp[(i * SH::N1 + j) * SH::N2 + k] = ab * c[k];
+            }
+#pragma unroll
+        for (int t = SH::T; t < SH::TS; ++t) tp[t] = 0.0f;
+    }
+};
+
+template <int N0, int N1, int N2, int PPT, int CPD, int MODE, bool DER>
+__global__ void __launch_bounds__(kThreads) k_tile(const __grid_constant__ thb_space_desc sp, const __grid_constant__ Args ar) {
+    using SH = Shp<N0, N1, N2>;
+    constexpr int T = SH::T, TS = SH::TS, NP = SH::NP, NQ = SH::NQ;
+    __shared__ float s_knots[3][8];
+    __shared__ __align__(16) float s_cpw[4][TS];
+    __shared__ __align__(16) float4 s_cc[kChunk];
+    __shared__ __align__(16) float s_tiles[kChunk * TS];
+    __shared__ int s_item;
+
+    const int tid = threadIdx.x;
+    const int nitems = ar.counters[0];
+    const int d = sp.ndim;
+
+    for (;;) {
+        if (tid == 0) s_item = atomicAdd(ar.counters + 1, 1);
+        __syncthreads();
+        const int iti = s_item;
+        if (iti >= nitems) break;
+        const Item it = load_item(sp, ar.items, iti);
+        const int ntile = it.S - it.ndir;
+        const int nchunks = (ntile + kChunk - 1) / kChunk;
+        const bool use_direct = (it.ndir > 0) || (MODE == MODE_FUSED && ar.cellnet);
+
+        stage_knots<SH>(sp, it, s_knots);
+        if (MODE == MODE_FUSED) {
+            for (int t = tid; t < TS; t += kThreads) {
+                float v[4] = {0.f, 0.f, 0.f, 0.f};
+                if (it.ndir > 0 && t < T && ((it.dm >> t) & 1ull)) {
+                    const int pos = __popcll(it.dm & ((1ull << t) - 1ull));
+                    const int64_t r = __ldg(sp.supp_jm + it.soff + pos);
+#pragma unroll
+                    for (int k = 0; k < CPD; ++k) v[k] = __ldg(ar.ctrl_pts + r * CPD + k);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) s_cpw[k][t] = v[k];
+            }
+        }
+        __syncthreads();
+
+        auto stage_chunk = [&](int c0) {
+            const int ns = min(kChunk, ntile - c0);
+            const float4* src = reinterpret_cast<const float4*>(sp.tiles + (int64_t)(it.toff + c0) * TS);
+            float4* dst = reinterpret_cast<float4*>(s_tiles);
+            for (int i = tid; i < ns * NQ; i += kThreads) dst[i] = __ldg(src + i);
+            if (MODE == MODE_FUSED) {
+                for (int s = tid; s < ns; s += kThreads) {
+                    const int64_t r = __ldg(sp.supp_jm + it.soff + it.ndir + c0 + s);
+                    float v[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int k = 0; k < CPD; ++k) v[k] = __ldg(ar.ctrl_pts + r * CPD + k);
+                    s_cc[s] = make_float4(v[0], v[1], v[2], v[3]);
+                }
+            }
+        };
+
+        if (MODE == MODE_FUSED && ar.cellnet) {
+            // fold every tile into the window control net: Q[t] += tile_s[t] * CP_s
+            for (int c0 = 0; c0 < ntile; c0 += kChunk) {
+                stage_chunk(c0);
+                __syncthreads();
+                const int ns = min(kChunk, ntile - c0);
+                for (int t = tid; t < TS; t += kThreads) {
+                    float q[4] = {0.f, 0.f, 0.f, 0.f};
+                    for (int s = 0; s < ns; ++s) {
+                        const float w = s_tiles[s * TS + t];
+                        const float4 cc = s_cc[s];
+                        q[0] = fmaf(w, cc.x, q[0]); q[1] = fmaf(w, cc.y, q[1]);
+                        q[2] = fmaf(w, cc.z, q[2]); q[3] = fmaf(w, cc.w, q[3]);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) s_cpw[k][t] += q[k];
+                }
+                __syncthreads();
+            }
+        }
+        const bool tile_loop = !(MODE == MODE_FUSED && ar.cellnet) && ntile > 0;
+
+        for (int base = 0; base < it.count; base += kThreads * PPT) {
+            // ---- per-thread points
+            int idx[PPT];
+            bool valid[PPT];
+            Bases<SH, DER> bs[PPT];
+#pragma unroll
+            for (int q = 0; q < PPT; ++q) {
+                const int li = base + q * kThreads + tid;
+                valid[q] = li < it.count;
+                idx[q] = __ldg(ar.perm + it.begin + (valid[q] ? li : 0));
+                float u[3] = {0.f, 0.f, 0.f};
+                for (int k = 0; k < d; ++k) u[k] = __ldg(ar.params + (int64_t)idx[q] * d + k);
+                bs[q].eval(u, s_knots);
+            }
+            for (int chi = 0; chi < ar.nch; ++chi) {
+                const int ch = ar.channels[chi];
+                f32x2 tp2[PPT][NP];
+                int64_t off[PPT];
+#pragma unroll
+                for (int q = 0; q < PPT; ++q) {
+                    float tp[TS];
+                    bs[q].tensor(ch, tp);
+                    if (MODE == MODE_BASIS) {
+                        off[q] = valid[q] ? __ldg(ar.offsets + idx[q]) : 0;
+                        if (it.ndir > 0 && valid[q]) {
+                            float* dst = ar.out[chi] + off[q];
+                            int pos = 0;
+#pragma unroll
+                            for (int t = 0; t < T; ++t) {
+                                if ((it.dm >> t) & 1ull) dst[pos++] = tp[t];
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int m = 0; m < NP; ++m) tp2[q][m] = pack2(tp[2 * m], tp[2 * m + 1]);
+                }
+                float acc[PPT][4];
+#pragma unroll
+                for (int q = 0; q < PPT; ++q)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) acc[q][k] = 0.0f;
+
+                if (MODE == MODE_FUSED && use_direct) {
+                    // own-level supports (or the folded control net): CPD dot products with the window
+#pragma unroll
+                    for (int k = 0; k < CPD; ++k) {
+                        f32x2 a[PPT][2];
+#pragma unroll
+                        for (int q = 0; q < PPT; ++q) a[q][0] = a[q][1] = 0ull;
+                        const ulonglong2* col = reinterpret_cast<const ulonglong2*>(s_cpw[k]);
+#pragma unroll
+                        for (int m = 0; m < NQ; ++m) {
+                            const ulonglong2 cv = col[m];
+#pragma unroll
+                            for (int q = 0; q < PPT; ++q) {
+                                ffma2(a[q][0], tp2[q][2 * m], cv.x);
+                                ffma2(a[q][1], tp2[q][2 * m + 1], cv.y);
+                            }
+                        }
+#pragma unroll
+                        for (int q = 0; q < PPT; ++q) acc[q][k] = hsum2(a[q][0]) + hsum2(a[q][1]);
+                    }
+                }
+                if (tile_loop) {
+                    for (int c0 = 0; c0 < ntile; c0 += kChunk) {
+                        if (!(nchunks == 1 && (chi > 0 || base > 0))) {
+                            __syncthreads();
+                            stage_chunk(c0);
+                            __syncthreads();
+                        }
+                        const int ns = min(kChunk, ntile - c0);
+#pragma unroll 2
+                        for (int s = 0; s < ns; ++s) {
+                            const ulonglong2* row = reinterpret_cast<const ulonglong2*>(s_tiles + s * TS);
+                            f32x2 a[PPT][2];
+#pragma unroll
+                            for (int q = 0; q < PPT; ++q) a[q][0] = a[q][1] = 0ull;
+#pragma unroll
+                            for (int m = 0; m < NQ; ++m) {
+                                const ulonglong2 tv = row[m];
+#pragma unroll
+                                for (int q = 0; q < PPT; ++q) {
+                                    ffma2(a[q][0], tp2[q][2 * m], tv.x);
+                                    ffma2(a[q][1], tp2[q][2 * m + 1], tv.y);
+                                }
+                            }
+                            if (MODE == MODE_FUSED) {
+                                const float4 cc = s_cc[s];
+#pragma unroll
+                                for (int q = 0; q < PPT; ++q) {
+                                    const float phi = hsum2(a[q][0]) + hsum2(a[q][1]);
+                                    acc[q][0] = fmaf(phi, cc.x, acc[q][0]);
+                                    acc[q][1] = fmaf(phi, cc.y, acc[q][1]);
+                                    acc[q][2] = fmaf(phi, cc.z, acc[q][2]);
+                                    if (CPD == 4) acc[q][3] = fmaf(phi, cc.w, acc[q][3]);
+                                }
+                            } else {
+#pragma unroll
+                                for (int q = 0; q < PPT; ++q) {
+                                    const float phi = hsum2(a[q][0]) + hsum2(a[q][1]);
+                                    if (valid[q]) ar.out[chi][off[q] + it.ndir + c0 + s] = phi;
+                                }
+                            }
+                        }
+                    }
+                }
+                if (MODE == MODE_FUSED) {
+#pragma unroll
+                    for (int q = 0; q < PPT; ++q) {
+                        if (valid[q]) {
+                            float* o = ar.out[chi] + (int64_t)idx[q] * CPD;
+#pragma unroll
+                            for (int k = 0; k < CPD; ++k) o[k] = acc[q][k];
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ---- fused backward: grad_ctrl_pts = A^T grad_out without materialising A --------------------------------
+// Per item: every thread writes the tensor product of its point into shared memory (point-minor layout),
+// the CTA reduces gQ[t][k] = sum_points tp[point][t] * g[point][k], then scatters
+//   own-level supports : grad_cp[Jm_t] += gQ[t]
+//   coarser supports   : grad_cp[Jm_s] += sum_t tile_s[t] * gQ[t]
+// i.e. S*cp_dim atomics per ITEM (up to 256 points) instead of per point as in the reference
+// (compute_pts_cuda_kernels.cu:28-47).
+template <int N0, int N1, int N2, int CPD>
+__global__ void __launch_bounds__(kThreads) k_tile_backward(const __grid_constant__ thb_space_desc sp,
+                                                            const __grid_constant__ Args ar) {
+    using SH = Shp<N0, N1, N2>;
+    constexpr int T = SH::T, TS = SH::TS;
+    constexpr int LD = kThreads + 1;  // padded row length: conflict-free column reads
+    __shared__ float s_knots[3][8];
+    __shared__ float s_tp[T * LD];
+    __shared__ float s_g[4][LD];
+    __shared__ float s_gq[TS][4];
+    __shared__ int s_item;
+
+    const int tid = threadIdx.x;
+    const int nitems = ar.counters[0];
+    const int d = sp.ndim;
+
+    for (;;) {
+        if (tid == 0) s_item = atomicAdd(ar.counters + 1, 1);
+        __syncthreads();
+        const int iti = s_item;
+        if (iti >= nitems) break;
+        const Item it = load_item(sp, ar.items, iti);
+        stage_knots<SH>(sp, it, s_knots);
+        float gq[(T * CPD + kThreads - 1) / kThreads];  // this thread's share of the (t,k) outputs
+#pragma unroll
+        for (int o = 0; o < (T * CPD + kThreads - 1) / kThreads; ++o) gq[o] = 0.0f;
+        __syncthreads();
+
+        for (int base = 0; base < it.count; base += kThreads) {
+            const int li = base + tid;
+            const bool valid = li < it.count;
+            const int idx = __ldg(ar.perm + it.begin + (valid ? li : 0));
+            float u[3] = {0.f, 0.f, 0.f};
+            for (int k = 0; k < d; ++k) u[k] = __ldg(ar.params + (int64_t)idx * d + k);
+            Bases<SH, false> bs;
+            bs.eval(u, s_knots);
+            float tp[TS];
+            bs.tensor(0, tp);
+#pragma unroll
+            for (int t = 0; t < T; ++t) s_tp[t * LD + tid] = valid ? tp[t] : 0.0f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) s_g[k][tid] = (valid && k < CPD) ? __ldg(ar.grad_out + (int64_t)idx * CPD + k) : 0.0f;
+            __syncthreads();
+            const int np = min(kThreads, it.count - base);
+#pragma unroll
+            for (int o = 0; o < (T * CPD + kThreads - 1) / kThreads; ++o) {
+                const int e = o * kThreads + tid;
+                if (e < T * CPD) {
+                    const int t = e / CPD, k = e - t * CPD;
+                    const float* row = s_tp + t * LD;
+                    const float* g = s_g[k];
+                    float a = 0.0f;
+                    for (int p = 0; p < np; ++p) a = fmaf(row[p], g[p], a);
+                    gq[o] += a;
+                }
+            }
+            __syncthreads();
+        }
+        // publish gQ
+#pragma unroll
+        for (int o = 0; o < (T * CPD + kThreads - 1) / kThreads; ++o) {
+            const int e = o * kThreads + tid;
+            if (e < T * CPD) s_gq[e / CPD][e % CPD] = gq[o];
+        }
+        __syncthreads();
+        // own-level supports
+        if (it.ndir > 0) {
+            for (int e = tid; e < T * CPD; e += kThreads) {
+                const int t = e / CPD, k = e - t * CPD;
+                if ((it.dm >> t) & 1ull) {
+                    const int pos = __popcll(it.dm & ((1ull << t) - 1ull));
+                    const int64_t r = __ldg(sp.supp_jm + it.soff + pos);
+                    atomicAdd(ar.grad_cp + r * CPD + k, s_gq[t][k]);
+                }
+            }
+        }
+        // coarser-level supports
+        const int ntile = it.S - it.ndir;
+        for (int e = tid; e < ntile * CPD; e += kThreads) {
+            const int s = e / CPD, k = e - s * CPD;
+            const float4* row = reinterpret_cast<const float4*>(sp.tiles + (int64_t)(it.toff + s) * TS);
+            float a = 0.0f;
+#pragma unroll
+            for (int m = 0; m < TS / 4; ++m) {
+                const float4 w = __ldg(row + m);
+                a = fmaf(w.x, s_gq[4 * m + 0][k], a);
+                a = fmaf(w.y, s_gq[4 * m + 1][k], a);
+                a = fmaf(w.z, s_gq[4 * m + 2][k], a);
+                a = fmaf(w.w, s_gq[4 * m + 3][k], a);
+            }
+            const int64_t r = __ldg(sp.supp_jm + it.soff + it.ndir + s);
+            atomicAdd(ar.grad_cp + r * CPD + k, a);
+        }
+        // s_gq / s_knots are rewritten only after the next item's first __syncthreads
+    }
+}
+
+// ---- launch plumbing ---------------------------------------------------------------------------------------
+struct ShapeOps {
+    int n0, n1, n2;
+    // ppt in {1,2}; cpd in {3,4}; der in {0,1}
+    int (*fused)(const thb_space_desc*, const Args*, int ppt, int cpd, int der, cudaStream_t);
+    int (*basis)(const thb_space_desc*, const Args*, int ppt, int der, cudaStream_t);
+    int (*backward)(const thb_space_desc*, const Args*, int cpd, cudaStream_t);
+};
+
+template <typename K>
+int persistent_grid(K kernel) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    return per_sm * thb_num_sms();
+}
+
+#define THB_TILE_LAUNCH(KERNEL)                                                   \
+    do {                                                                          \
+        static int grid = 0;                                                      \
+        if (grid == 0) grid = persistent_grid(KERNEL);                            \
+        KERNEL<<<grid, kThreads, 0, st>>>(*sp, *ar);                              \
+        THB_LAUNCHED();                                                           \
+        return THB_OK;                                                            \
+    } while (0)
+
+template <int N0, int N1, int N2>
+int launch_fused(const thb_space_desc* sp, const Args* ar, int ppt, int cpd, int der, cudaStream_t st) {
+    if (ppt == 2) {
+        if (cpd == 3 && !der) THB_TILE_LAUNCH((k_tile<N0, N1, N2, 2, 3, MODE_FUSED, false>));
+        if (cpd == 3 && der) THB_TILE_LAUNCH((k_tile<N0, N1, N2, 2, 3, MODE_FUSED, true>));
+        if (cpd == 4 && !der) THB_TILE_LAUNCH((k_tile<N0, N1, N2, 2, 4, MODE_FUSED, false>));
+        if (cpd == 4 && der) THB_TILE_LAUNCH((k_tile<N0, N1, N2, 2, 4, MODE_FUSED, true>));
+    } else {
+        if (cpd == 3 && !der) THB_TILE_LAUNCH((k_tile<N0, N1, N2, 1, 3, MODE_FUSED, false>));
+        if (cpd == 3 && der) THB_TILE_LAUNCH((k_tile<N0, N1, N2, 1, 3, MODE_FUSED, true>));
+        if (cpd == 4 && !der) THB_TILE_LAUNCH((k_tile<N0, N1, N2, 1, 4, MODE_FUSED, false>));
+        if (cpd == 4 && der) THB_TILE_LAUNCH((k_tile<N0, N1, N2, 1, 4, MODE_FUSED, true>));
+    }
+    return thb_set_error(THB_E_UNSUPPORTED, "fused: unsupported variant");
+}
+
+template <int N0, int N1, int N2>
+int launch_basis(const thb_space_desc* sp, const Args* ar, int ppt, int der, cudaStream_t st) {
+    if (ppt == 2) {
+        if (!der) THB_TILE_LAUNCH((k_tile<N0, N1, N2, 2, 3, MODE_BASIS, false>));
+        THB_TILE_LAUNCH((k_tile<N0, N1, N2, 2, 3, MODE_BASIS, true>));
+    }
+    if (!der) THB_TILE_LAUNCH((k_tile<N0, N1, N2, 1, 3, MODE_BASIS, false>));
+    THB_TILE_LAUNCH((k_tile<N0, N1, N2, 1, 3, MODE_BASIS, true>));
+}
+
+template <int N0, int N1, int N2>
+int launch_backward(const thb_space_desc* sp, const Args* ar, int cpd, cudaStream_t st) {
+    if (cpd == 3) THB_TILE_LAUNCH((k_tile_backward<N0, N1, N2, 3>));
+    if (cpd == 4) THB_TILE_LAUNCH((k_tile_backward<N0, N1, N2, 4>));
+    return thb_set_error(THB_E_UNSUPPORTED, "backward: unsupported cp_dim");
+}
+
+#define THB_DEFINE_SHAPE(A, B, C)                                                                         \
+    namespace thb_tile {                                                                                  \
+    extern const ShapeOps shape_ops_##A##B##C = {A, B, C, &launch_fused<A, B, C>, &launch_basis<A, B, C>,    \
+                                                 &launch_backward<A, B, C>};                              \
+    }
+
+}  // namespace thb_tile

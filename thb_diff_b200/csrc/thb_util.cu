@@ -1,0 +1,85 @@
+// Error handling, bookkeeping and the FP32 FMA micro-benchmark of libthb_b200.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "thb_common.cuh"
+
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+int thb_set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+void thb_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int thb_num_sms() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
+extern "C" int thb_version(void) { return 100; }
+extern "C" const char* thb_last_error(void) { return g_err; }
+extern "C" int64_t thb_launch_count(void) { return g_launches.load(); }
+
+// ---- FP32 peak probe ------------------------------------------------------------------------------------
+// 16 independent accumulator chains per thread, 8 warps per CTA, enough CTAs to fill every SM: what the
+// FMA pipe can do when nothing else competes for issue slots.  variant 0: FFMA, variant 1: FFMA2.
+template <int VARIANT>
+__global__ void __launch_bounds__(256) k_fma_peak(int iters, float* sink) {
+    float a = 1.0f + threadIdx.x * 1e-7f, b = 0.999f;
+    if (VARIANT == 0) {
+        float acc[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] = i;
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[i] = fmaf(acc[i], b, a);
+        }
+        float s = 0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) s += acc[i];
+        if (s == 12345.678f) sink[0] = s;
+    } else {
+        f32x2 acc[16];
+        f32x2 a2 = pack2(a, a * 0.5f), b2 = pack2(b, b);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] = pack2(float(i), float(-i));
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                // acc = acc * b2 + a2  (written as d = a*b + d with the roles swapped every other step)
+                asm("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(acc[i]) : "l"(b2), "l"(a2));
+            }
+        }
+        float s = 0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) s += hsum2(acc[i]);
+        if (s == 12345.678f) sink[0] = s;
+    }
+}
+
+extern "C" int thb_fma_peak(int variant, int iters, float* sink, double* flops_out_host, void* stream) {
+    THB_REQUIRE(sink && iters > 0, "thb_fma_peak: bad arguments");
+    const int ctas = thb_num_sms() * 8;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (variant == 0) {
+        k_fma_peak<0><<<ctas, 256, 0, st>>>(iters, sink);
+        if (flops_out_host) *flops_out_host = 2.0 * 16 * double(iters) * 256.0 * ctas;
+    } else {
+        k_fma_peak<1><<<ctas, 256, 0, st>>>(iters, sink);
+        if (flops_out_host) *flops_out_host = 2.0 * 2 * 16 * double(iters) * 256.0 * ctas;
+    }
+    THB_LAUNCHED();
+    return THB_OK;
+}

@@ -1,0 +1,205 @@
+"""Thin Python layer over the C ABI: allocates outputs with torch (so the caching allocator owns the
+memory), passes raw device pointers and the current CUDA stream, raises RuntimeError on library errors.
+No arithmetic happens here."""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import PlanDesc, check, lib, ptr, require_cuda, stream_ptr
+
+POINTS_PER_ITEM = 256
+
+CH_VALUE = 0
+
+
+def grad_channels(ndim):
+    return [1 << k for k in range(ndim)]
+
+
+def mixed_channel(ndim):
+    return (1 << ndim) - 1
+
+
+def _as_params(params, ndim, device):
+    """[N, ndim] float32 contiguous CUDA tensor (float64 / numpy inputs are rounded to f32 -- SURVEY Q11)."""
+    if not isinstance(params, torch.Tensor):
+        import numpy as np
+
+        params = torch.from_numpy(np.ascontiguousarray(np.asarray(params)))
+    if params.dim() != 2 or params.shape[1] != ndim:
+        raise RuntimeError(f"params must have shape [N, {ndim}]")
+    return params.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
+
+
+class Plan:
+    """The points of one batch grouped by active cell (device resident)."""
+
+    def __init__(self, P, params, points_per_item=POINTS_PER_ITEM):
+        self.P = P
+        self.params = _as_params(params, P.ndim, P.device)
+        n = self.params.shape[0]
+        dev = P.device
+        i32 = dict(dtype=torch.int32, device=dev)
+        self.n = n
+        self.slot = torch.empty(max(n, 1), **i32)
+        self.perm = torch.empty(max(n, 1), **i32)
+        self.cell_count = torch.empty(P.nslots + 1, **i32)
+        self.cell_start = torch.empty(P.nslots + 1, **i32)
+        self.cell_cursor = torch.empty(P.nslots + 1, **i32)
+        self.max_items = n // points_per_item + P.nslots + 1
+        self.items = torch.empty((self.max_items, 4), **i32)
+        self.counters = torch.zeros(4, **i32)
+        d = PlanDesc()
+        d.npoints, d.points_per_item, d.max_items = n, points_per_item, self.max_items
+        d.slot, d.perm = self.slot.data_ptr(), self.perm.data_ptr()
+        d.cell_count, d.cell_start, d.cell_cursor = self.cell_count.data_ptr(), self.cell_start.data_ptr(), self.cell_cursor.data_ptr()
+        d.items, d.counters = self.items.data_ptr(), self.counters.data_ptr()
+        self.desc = d
+        self.build()
+
+    def build(self):
+        check(lib.thb_plan_build(C.byref(self.P.desc()), ptr(self.params), C.byref(self.desc), stream_ptr(self.P.device)), "thb_plan_build")
+
+    # derived quantities (device tensors; no sync)
+    def num_supp(self):
+        S = self.P.cellinfo[:, 5]
+        s = self.slot[: self.n].long()
+        return torch.where(s >= 0, S[s.clamp(min=0)], torch.zeros_like(s, dtype=torch.int32))
+
+    def stats(self):
+        """(#in-domain points, nnz, nnz of tiled supports) -- synchronises."""
+        cnt = self.cell_count[: self.P.nslots].long()
+        S = self.P.cellinfo[:, 5].long()
+        nd = self.P.cellinfo[:, 7].long()
+        return int(cnt.sum()), int((cnt * S).sum()), int((cnt * (S - nd)).sum())
+
+
+def active_span(P, params, want_num_supp=True):
+    params = _as_params(params, P.ndim, P.device)
+    n = params.shape[0]
+    slot = torch.empty(n, dtype=torch.int32, device=P.device)
+    ns = torch.empty(n, dtype=torch.int32, device=P.device) if want_num_supp else None
+    check(lib.thb_active_span(C.byref(P.desc()), ptr(params), n, ptr(slot), ptr(ns), stream_ptr(P.device)), "thb_active_span")
+    return slot, ns
+
+
+def expand_supports(P, slot, offsets, nnz, dtype=torch.int64):
+    jm = torch.empty(nnz, dtype=dtype, device=P.device)
+    check(lib.thb_expand_supports(C.byref(P.desc()), ptr(slot), ptr(offsets), slot.shape[0], ptr(jm), int(dtype == torch.int64),
+                                  stream_ptr(P.device)), "thb_expand_supports")
+    return jm
+
+
+def _chan_array(channels):
+    return (C.c_int32 * len(channels))(*[int(c) for c in channels])
+
+
+def basis_tiled(P, plan, offsets, nnz, channels=(CH_VALUE,)):
+    """PHI for each channel, flat [nnz] in the reference's (point-major) pair order."""
+    outs = [torch.zeros(nnz, dtype=torch.float32, device=P.device) for _ in channels]
+    arr = (C.c_void_p * len(outs))(*[o.data_ptr() for o in outs])
+    check(lib.thb_basis_tiled(C.byref(P.desc()), C.byref(plan.desc), ptr(plan.params), ptr(offsets), _chan_array(channels),
+                              len(channels), arr, stream_ptr(P.device)), "thb_basis_tiled")
+    return outs
+
+
+def eval_fused(P, plan, ctrl_pts, channels=(CH_VALUE,), cellnet=False, out=None):
+    require_cuda(ctrl_pts, "ctrl_pts", torch.float32)
+    cpd = ctrl_pts.shape[1]
+    if cpd not in (3, 4):
+        raise RuntimeError("fused evaluation supports control points of width 3 or 4")
+    if ctrl_pts.shape[0] != P.nCP:
+        raise RuntimeError(f"ctrl_pts must have {P.nCP} rows")
+    if out is None:
+        out = [torch.zeros((plan.n, cpd), dtype=torch.float32, device=P.device) for _ in channels]
+    arr = (C.c_void_p * len(out))(*[o.data_ptr() for o in out])
+    check(lib.thb_eval_fused(C.byref(P.desc()), C.byref(plan.desc), ptr(plan.params), ptr(ctrl_pts), cpd, _chan_array(channels),
+                             len(channels), arr, int(bool(cellnet)), stream_ptr(P.device)), "thb_eval_fused")
+    return out
+
+
+def eval_fused_backward(P, plan, grad_out, cp_dim=None):
+    require_cuda(grad_out, "grad_out", torch.float32)
+    cpd = grad_out.shape[1]
+    g = torch.empty((P.nCP, cpd), dtype=torch.float32, device=P.device)
+    check(lib.thb_eval_fused_backward(C.byref(P.desc()), C.byref(plan.desc), ptr(plan.params), ptr(grad_out), cpd, ptr(g), P.nCP,
+                                      stream_ptr(P.device)), "thb_eval_fused_backward")
+    return g
+
+
+def _idx(t, name):
+    if t.dtype not in (torch.int64, torch.int32):
+        raise RuntimeError(f"{name} must be int64 or int32")
+    return int(t.dtype == torch.int64)
+
+
+def eval_forward(ctrl_pts, Jm, PHI, cumsum):
+    """THB_eval.forward: out[N, cp_dim] (freshly allocated, like the reference)."""
+    require_cuda(ctrl_pts, "ctrl_pts", torch.float32)
+    require_cuda(Jm, "Jm_array")
+    require_cuda(PHI, "tensor_prod", torch.float32)
+    require_cuda(cumsum, "num_supp_bs_cumsum")
+    if ctrl_pts.dim() != 2 or not 1 <= ctrl_pts.shape[1] <= 4:
+        raise RuntimeError("ctrl_pts must be [nCP, 1..4]")
+    if Jm.shape[0] != PHI.shape[0]:
+        raise RuntimeError("Jm_array and tensor_prod must have the same length")
+    n = cumsum.shape[0]
+    out = torch.zeros((n, ctrl_pts.shape[1]), dtype=torch.float32, device=ctrl_pts.device)
+    check(lib.thb_eval_forward(ptr(ctrl_pts), ptr(Jm), _idx(Jm, "Jm_array"), ptr(PHI), ptr(cumsum), _idx(cumsum, "cumsum"), ptr(out), n,
+                               ctrl_pts.shape[1], stream_ptr(ctrl_pts.device)), "thb_eval_forward")
+    return out
+
+
+def eval_backward(grad_output, ctrl_pts, Jm, PHI, cumsum):
+    """THB_eval.backward: grad_ctrl_pts[nCP, cp_dim]."""
+    require_cuda(ctrl_pts, "ctrl_pts", torch.float32)
+    grad_output = grad_output.contiguous()
+    require_cuda(grad_output, "grad_output", torch.float32)
+    require_cuda(Jm, "Jm_array")
+    require_cuda(PHI, "tensor_prod", torch.float32)
+    require_cuda(cumsum, "num_supp_bs_cumsum")
+    n = cumsum.shape[0]
+    if grad_output.shape != (n, ctrl_pts.shape[1]):
+        raise RuntimeError("grad_output must be [N, cp_dim]")
+    g = torch.empty_like(ctrl_pts)
+    check(lib.thb_eval_backward(ptr(grad_output), ptr(Jm), _idx(Jm, "Jm_array"), ptr(PHI), ptr(cumsum), _idx(cumsum, "cumsum"), ptr(g), n,
+                                ctrl_pts.shape[0], ctrl_pts.shape[1], stream_ptr(ctrl_pts.device)), "thb_eval_backward")
+    return g
+
+
+def find_spans(params1d, knots, degree):
+    require_cuda(params1d, "params", torch.float32)
+    require_cuda(knots, "knots", torch.float32)
+    n = params1d.shape[0]
+    out = torch.empty(n, dtype=torch.int32, device=params1d.device)
+    check(lib.thb_find_spans(ptr(params1d), 1, n, ptr(knots), knots.shape[0], int(degree), ptr(out), stream_ptr(params1d.device)), "thb_find_spans")
+    return out
+
+
+def basis_1d(params1d, knots, degree, derivs=False):
+    require_cuda(params1d, "params", torch.float32)
+    require_cuda(knots, "knots", torch.float32)
+    n = params1d.shape[0]
+    v = torch.empty((n, degree + 1), dtype=torch.float32, device=params1d.device)
+    dv = torch.empty_like(v) if derivs else None
+    check(lib.thb_basis_1d(ptr(params1d), 1, n, ptr(knots), knots.shape[0], int(degree), ptr(v), ptr(dv), stream_ptr(params1d.device)), "thb_basis_1d")
+    return (v, dv) if derivs else v
+
+
+def fma_peak(variant, iters=4096, repeats=5):
+    """Measured FP32 FMA throughput (TFLOP/s) of the running GPU -- the FP32 roofline denominator."""
+    sink = torch.zeros(4, dtype=torch.float32, device="cuda")
+    flops = C.c_double(0.0)
+    st = stream_ptr()
+    check(lib.thb_fma_peak(variant, iters, ptr(sink), C.byref(flops), st), "thb_fma_peak")
+    torch.cuda.synchronize()
+    best = 0.0
+    for _ in range(repeats):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(lib.thb_fma_peak(variant, iters, ptr(sink), C.byref(flops), st), "thb_fma_peak")
+        e1.record()
+        torch.cuda.synchronize()
+        best = max(best, flops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    return best

@@ -1,0 +1,315 @@
+"""PackedHierarchy -- the flat, device-resident form of a THB space that the CUDA kernels consume.
+
+The reference keeps the hierarchy as Python dicts: per-cell support lists
+(``compute_active_cells_active_supp``, THB/core.py:14-40,424-449) and dense per-level coefficient tables of
+shape [*sh_fns[lev], *sh_fns[max_lev]] (``compute_refinement_operators``, THB/core.py:43-114; 3.9 GB for
+the README 3-D toy, ~1e11 entries for BASELINE config 3).  Here the same information is stored as
+
+  knots      f32  all levels / dims concatenated                     (staged in shared memory by kernels)
+  cell_slot  i32  per level, one entry per cell: slot id of the active cell or -1
+  cellinfo   i32  [nslots, 8] = level, c0, c1, c2, supp_off, S, tile_off, n_direct
+  dmask      u64  [nslots]  which of the cell's own-level (p+1)^d window functions are active
+  supp_jm    i32  CSR of flat support ids (reference order: own level first, then ancestors, C order)
+  tiles      f32  [ntiles, TS]  for every (active cell, coarser-level support): the (p+1)^d coefficients
+                  of that (single-level-truncated) function in the CELL's-level basis on the cell
+
+PHI(point, support) = <tile, tensor product of the cell-level B-splines at the point>.  In exact
+arithmetic this equals the reference's finest-level formulation (the refinement relation is exact); the
+own-level supports have one-hot tiles, so they are not stored -- their PHI is the tensor-product entry
+itself (``onehot_direct=False`` stores them explicitly, which reproduces the reference's dense
+gather-multiply operation count).
+
+Semantics follow the reference: single-level truncation (core.py:98-111); the finest level
+uses the identity (the correct reading of core.py:113); no fp16 quantisation.
+"""
+import numpy as np
+import torch
+
+MAX_LEVELS = 8
+INFO_W = 8  # ints per cellinfo row
+
+
+def _ceil4(x):
+    return (x + 3) // 4 * 4
+
+
+class PackedHierarchy:
+    def __init__(self):
+        pass
+
+    # ------------------------------------------------------------------------------------------
+    @classmethod
+    def from_space(cls, space, device="cuda", onehot_direct=True, chunk=1 << 18):
+        if space.fns is None:
+            raise ValueError("call Space.build_hierarchy_from_domain_sequence() first")
+        return cls.build(space.knotvectors, space.degrees, space.cells, space.fns, space.Coeff,
+                         device=device, onehot_direct=onehot_direct, chunk=chunk)
+
+    @classmethod
+    def build(cls, knotvectors, degrees, cells, fns, Coeff=None, device="cuda", onehot_direct=True, chunk=1 << 18,
+              build_device=None):
+        self = cls()
+        L = max(knotvectors.keys()) + 1
+        d = len(degrees)
+        if d not in (2, 3):
+            raise ValueError("only 2-D and 3-D tensor products are supported")
+        if L > MAX_LEVELS:
+            raise ValueError(f"at most {MAX_LEVELS} levels")
+        p = tuple(int(x) for x in degrees)
+        T = int(np.prod([x + 1 for x in p]))
+        if T > 64:
+            raise ValueError("tensor-product size (p+1)^d must be <= 64")
+        TS = _ceil4(T)
+        self.ndim, self.nlevels, self.degrees, self.T, self.TS = d, L, p, T, TS
+        self.onehot_direct = bool(onehot_direct)
+        bdev = torch.device(build_device) if build_device is not None else torch.device(device)
+
+        kv = {l: [np.asarray(U, dtype=np.float64) for U in knotvectors[l]] for l in range(L)}
+        sh_cells, sh_fns = {}, {}
+        for l in range(L):
+            for k in range(d):
+                U = kv[l][k]
+                if len(np.unique(U)) != len(U) - 2 * p[k]:
+                    raise ValueError("knot vectors must be open with simple interior knots")
+                if np.any(U.astype(np.float32)[p[k]:len(U) - p[k] - 1] >= U.astype(np.float32)[p[k] + 1:len(U) - p[k]]):
+                    raise ValueError("knot spans collapse in float32")
+            sh_cells[l] = tuple(len(kv[l][k]) - 2 * p[k] - 1 for k in range(d))
+            sh_fns[l] = tuple(c + q for c, q in zip(sh_cells[l], p))
+            if tuple(cells[l].shape) != sh_cells[l] or tuple(fns[l].shape) != sh_fns[l]:
+                raise ValueError(f"mask shapes at level {l} do not match the knot vectors")
+            if l > 0:
+                for k in range(d):
+                    if sh_cells[l][k] != 2 * sh_cells[l - 1][k] or not np.array_equal(
+                            np.unique(kv[l][k])[::2], np.unique(kv[l - 1][k])):
+                        raise ValueError("levels must be dyadically nested (refine_knotvector)")
+        self.sh_cells, self.sh_fns = sh_cells, sh_fns
+        fn_off = np.zeros(L + 1, dtype=np.int64)
+        for l in range(L):
+            fn_off[l + 1] = fn_off[l] + int(np.prod(sh_fns[l]))
+        self.fn_off = fn_off
+
+        # ---- knots
+        knot_off = np.zeros((MAX_LEVELS, 3), dtype=np.int32)
+        knot_len = np.zeros((MAX_LEVELS, 3), dtype=np.int32)
+        flat = []
+        pos = 0
+        for l in range(L):
+            for k in range(d):
+                knot_off[l, k], knot_len[l, k] = pos, len(kv[l][k])
+                flat.append(kv[l][k].astype(np.float32))
+                pos += len(kv[l][k])
+        self.knot_off, self.knot_len = knot_off, knot_len
+        knots = np.concatenate(flat)
+
+        # ---- active cells -> slots
+        act_idx = {}
+        slot_base = np.zeros(L + 1, dtype=np.int64)
+        cs_off = np.zeros(MAX_LEVELS, dtype=np.int64)
+        tot = 0
+        for l in range(L):
+            cs_off[l] = tot
+            tot += int(np.prod(sh_cells[l]))
+            act_idx[l] = np.argwhere(np.asarray(cells[l]) == 1).astype(np.int64)
+            slot_base[l + 1] = slot_base[l] + len(act_idx[l])
+        nslots = int(slot_base[L])
+        if nslots == 0:
+            raise ValueError("no active cells")
+        cell_slot = np.full(tot, -1, dtype=np.int32)
+        for l in range(L):
+            if len(act_idx[l]):
+                lin = np.ravel_multi_index(tuple(act_idx[l].T), sh_cells[l])
+                cell_slot[cs_off[l] + lin] = slot_base[l] + np.arange(len(lin))
+        self.cell_slot_off, self.nslots = cs_off, nslots
+
+        # ---- admissibility: no active level-(l+1) function may overlap an active level-l cell
+        fmask = {l: (np.asarray(fns[l]) == 1) for l in range(L)}
+        for l in range(L - 1):
+            c = act_idx[l]
+            if not len(c):
+                continue
+            nxt = fmask[l + 1]
+            hit = np.zeros(len(c), dtype=bool)
+            rngs = [range(p[k] + 2) for k in range(d)]
+            for off in np.array(np.meshgrid(*rngs, indexing="ij")).reshape(d, -1).T:
+                hit |= nxt[tuple((2 * c[:, k] + off[k]) for k in range(d))]
+            if hit.any():
+                raise ValueError(f"inadmissible hierarchy: an active level-{l + 1} function overlaps an active level-{l} cell")
+
+        # ---- window offsets in C order
+        wt = np.array(np.meshgrid(*[range(q + 1) for q in p], indexing="ij")).reshape(d, -1).T.astype(np.int64)  # [T,d]
+
+        info = np.zeros((nslots, INFO_W), dtype=np.int32)
+        dmask = np.zeros(nslots, dtype=np.uint64)
+        jm_parts, batches = [], []
+        supp_pos, tile_pos = 0, 0
+        for lev in range(L):
+            c = act_idx[lev]
+            n = len(c)
+            if n == 0:
+                continue
+            flags, jms, fidx = [], [], []
+            for l in range(lev, -1, -1):
+                a = c >> (lev - l)
+                w = a[:, None, :] + wt[None, :, :]                                # [n,T,d]
+                lin = np.ravel_multi_index(tuple(w[..., k] for k in range(d)), sh_fns[l])
+                flags.append(fmask[l].reshape(-1)[lin])
+                jms.append(fn_off[l] + lin)
+                fidx.append(w)
+            F = np.concatenate(flags, axis=1)
+            J = np.concatenate(jms, axis=1)
+            S = F.sum(axis=1)
+            own = flags[0]
+            ndir = own.sum(axis=1) if onehot_direct else np.zeros(n, dtype=np.int64)
+            bits = (own.astype(np.uint64) << np.arange(T, dtype=np.uint64)[None, :]).sum(axis=1, dtype=np.uint64)
+            sl = slice(int(slot_base[lev]), int(slot_base[lev + 1]))
+            info[sl, 0] = lev
+            info[sl, 1:1 + d] = c
+            soff = supp_pos + np.concatenate([[0], np.cumsum(S)[:-1]])
+            info[sl, 4], info[sl, 5], info[sl, 7] = soff, S, ndir
+            dmask[sl] = bits
+            jm_parts.append(J[F])
+            supp_pos += int(S.sum())
+            # tiled supports, reference order
+            first = 1 if onehot_direct else 0
+            cnts = np.stack([flags[j].sum(axis=1) for j in range(first, lev + 1)], axis=1) if lev + 1 > first else np.zeros((n, 0), dtype=np.int64)
+            ntile = cnts.sum(axis=1)
+            toff = tile_pos + np.concatenate([[0], np.cumsum(ntile)[:-1]])
+            info[sl, 6] = toff
+            base = toff[:, None] + np.concatenate([np.zeros((n, 1), dtype=np.int64), np.cumsum(cnts, axis=1)[:, :-1]], axis=1) if cnts.shape[1] else None
+            for j in range(first, lev + 1):
+                l = lev - j
+                fl = flags[j]
+                rows, cols = np.nonzero(fl)
+                if len(rows) == 0:
+                    continue
+                rank = (np.cumsum(fl, axis=1) - 1)[rows, cols]
+                gidx = base[rows, j - first] + rank
+                batches.append((lev, l, c[rows], fidx[j][rows, cols], gidx))
+            tile_pos += int(ntile.sum())
+        ntiles = tile_pos
+        supp_jm = np.concatenate(jm_parts).astype(np.int32)
+        self.max_S = int(info[:, 5].max())
+        self.max_tiled = int((info[:, 5] - info[:, 7]).max())
+        self.ntiles, self.nsupp = ntiles, len(supp_jm)
+
+        self._batches, self._fmask, self._kv_shapes = batches, fmask, None
+        self._chunk, self._bdev = chunk, bdev
+        self.tiles = None
+        dev = torch.device(device)
+        self.device = dev
+        self.knots = torch.from_numpy(knots).to(dev)
+        self.cell_slot = torch.from_numpy(cell_slot).to(dev)
+        self.cellinfo = torch.from_numpy(info).to(dev)
+        self.dmask = torch.from_numpy(dmask.view(np.int64)).to(dev)
+        self.supp_jm = torch.from_numpy(supp_jm).to(dev)
+        self.tiles = torch.zeros((1, TS), dtype=torch.float32, device=dev)
+        self.has_tiles = ntiles == 0
+        if Coeff is not None:
+            self.attach_tiles(Coeff)
+        self.cellinfo_host = info
+        self.nCP = int(fn_off[L])
+        return self
+
+
+    def attach_tiles(self, Coeff):
+        """Computes the coefficient tiles of the coarser-level supports from the 1-D subdivision matrices
+        Coeff[lev][dim] ([nfns(lev), nfns(lev+1)], reference multilevel_spline_space.py:78-92)."""
+        if self.has_tiles and self.ntiles == 0:
+            return self
+        L, d, p, T, TS = self.nlevels, self.ndim, self.degrees, self.T, self.TS
+        sh_fns, fmask, batches, chunk, bdev, ntiles = self.sh_fns, self._fmask, self._batches, self._chunk, self._bdev, self.ntiles
+        # ---- 1-D refinement chains R[l][lev] = Coeff[l] ... Coeff[lev-1]
+        R = {}
+        for k in range(d):
+            for l in range(L):
+                R[(k, l, l)] = np.eye(sh_fns[l][k])
+                for lev in range(l + 1, L):
+                    R[(k, l, lev)] = R[(k, l, lev - 1)] @ np.asarray(Coeff[lev - 1][k], dtype=np.float64)
+
+        tiles = torch.zeros((max(ntiles, 1), TS), dtype=torch.float32, device=bdev)
+        es_u = {2: "ma,mb->mab", 3: "ma,mb,mc->mabc"}[d]
+        es_t = {2: "mab,max,mby->mxy", 3: "mabc,max,mby,mcz->mxyz"}[d]
+        tdev = lambda x, dt=torch.float64: torch.as_tensor(x, device=bdev, dtype=dt)
+        Rt = {key: tdev(v) for key, v in R.items()}
+        Ct = {(l, k): tdev(np.asarray(Coeff[l][k], dtype=np.float64)) for l in range(L - 1) for k in range(d)}
+        ar = [torch.arange(q + 1, device=bdev) for q in p]
+        for lev, l, cc, ff, gidx in batches:
+            for s in range(0, len(gidx), chunk):
+                c_ = torch.as_tensor(cc[s:s + chunk], device=bdev)
+                f_ = torch.as_tensor(ff[s:s + chunk], device=bdev)
+                g_ = torch.as_tensor(gidx[s:s + chunk], device=bdev)
+                if l == lev:
+                    t = torch.zeros((len(g_), TS), dtype=torch.float32, device=bdev)
+                    loc = f_ - c_
+                    lin = loc[:, 0]
+                    for k in range(1, d):
+                        lin = lin * (p[k] + 1) + loc[:, k]
+                    t[torch.arange(len(g_), device=bdev), lin] = 1.0
+                    tiles[g_] = t
+                    continue
+                A = [Rt[(k, l, lev)][f_[:, k, None], c_[:, k, None] + ar[k][None, :]] for k in range(d)]
+                tile = torch.einsum(es_u, *A)
+                e = l + 1
+                a_ = c_ >> (lev - e)
+                lin = a_[:, 0, None] + ar[0][None, :]
+                widx = [a_[:, k, None] + ar[k][None, :] for k in range(d)]          # [m, p_k+1]
+                if d == 2:
+                    M = torch.as_tensor(fmask[e], device=bdev)[widx[0][:, :, None], widx[1][:, None, :]]
+                else:
+                    M = torch.as_tensor(fmask[e], device=bdev)[widx[0][:, :, None, None], widx[1][:, None, :, None], widx[2][:, None, None, :]]
+                if bool(M.any()):
+                    G = []
+                    for k in range(d):
+                        W = Ct[(l, k)][f_[:, k, None], widx[k]]                                        # [m, δ]
+                        Rk = Rt[(k, e, lev)][widx[k][:, :, None], (c_[:, k, None] + ar[k][None, :])[:, None, :]]  # [m, δ, t]
+                        G.append(W[:, :, None] * Rk)
+                    tile = tile - torch.einsum(es_t, M.to(torch.float64), *G)
+                t = torch.zeros((len(g_), TS), dtype=torch.float32, device=bdev)
+                t[:, :T] = tile.reshape(len(g_), T).to(torch.float32)
+                tiles[g_] = t
+
+        self.tiles = tiles.to(self.device)
+        self.has_tiles = True
+        self._desc_cache = None
+        return self
+
+    # ------------------------------------------------------------------------------------------
+    def nbytes(self):
+        return sum(t.numel() * t.element_size() for t in (self.knots, self.cell_slot, self.cellinfo, self.dmask, self.supp_jm, self.tiles))
+
+    def summary(self):
+        return dict(ndim=self.ndim, levels=self.nlevels, degrees=self.degrees, nslots=self.nslots, nCP=self.nCP,
+                    nsupp=self.nsupp, ntiles=self.ntiles, max_S=self.max_S, max_tiled=self.max_tiled,
+                    bytes=self.nbytes(), onehot_direct=self.onehot_direct)
+
+
+def _desc(self):
+    """ctypes thb_space_desc for this hierarchy (cached; keeps the tensors alive through self)."""
+    d = getattr(self, "_desc_cache", None)
+    if d is not None:
+        return d
+    from ._lib import SpaceDesc
+
+    d = SpaceDesc()
+    d.ndim, d.nlevels = self.ndim, self.nlevels
+    for k in range(3):
+        d.degree[k] = self.degrees[k] if k < self.ndim else 0
+    d.tile_stride, d.nslots, d.max_tiled = self.TS, self.nslots, self.max_tiled
+    for l in range(self.nlevels):
+        for k in range(self.ndim):
+            d.knot_off[l][k] = int(self.knot_off[l, k])
+            d.knot_len[l][k] = int(self.knot_len[l, k])
+            d.ncells[l][k] = int(self.sh_cells[l][k])
+            d.nfns[l][k] = int(self.sh_fns[l][k])
+        if self.ndim == 2:
+            d.ncells[l][2], d.nfns[l][2] = 1, 1
+        d.cell_slot_off[l] = int(self.cell_slot_off[l])
+    for l in range(self.nlevels + 1):
+        d.fn_off[l] = int(self.fn_off[l])
+    d.knots, d.cell_slot, d.cellinfo = self.knots.data_ptr(), self.cell_slot.data_ptr(), self.cellinfo.data_ptr()
+    d.dmask, d.supp_jm, d.tiles = self.dmask.data_ptr(), self.supp_jm.data_ptr(), self.tiles.data_ptr()
+    self._desc_cache = d
+    return d
+
+
+PackedHierarchy.desc = _desc
