@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""Benchmark of the THB basis+evaluation hot path (BASELINE.json metric: points/sec, fraction of roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+Workload (config.workload): BASELINE config 3 -- 3-D, degree 3, 4 active levels (nested graded boxes, ~25 % of
+each region refined, 'uniform-ish' knots), a 256^3 parametric grid PER GPU (weak scaling: the y axis of a
+256 x 256N x 256 grid is dealt round-robin to the N ranks, so every rank sees the same mix of cells).
+One step = params (resident in HBM) -> points grouped by active cell (thb_plan_build) -> fused
+basis+evaluation kernel -> geometry [N,3] in HBM.  No collective is on this path (points are independent).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GRID = 256
+SAMPLE_REF = 2048
+
+
+def cdb_flops(p):
+    return sum(2 + 5 * j for j in range(1, p + 1))
+
+
+def flop_model(degrees, cpd, n_in, nnz, nnz_tiled):
+    """(executed FLOPs of the hybrid algorithm, FLOPs of SURVEY 8d's dense gather-multiply model)"""
+    d = len(degrees)
+    T = int(np.prod([p + 1 for p in degrees]))
+    tp = (degrees[0] + 1) * (degrees[1] + 1) + (T if d == 3 else 0)
+    per_pt = sum(cdb_flops(p) for p in degrees) + tp
+    executed = n_in * (per_pt + cpd * 2 * T) + nnz_tiled * (2 * T + 2 * cpd)
+    dense = n_in * per_pt + nnz * (2 * T + 2 * cpd)
+    return float(executed), float(dense)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop = index, [], threading.Event()
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop.is_set():
+            try:
+                o = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([x.strip() for x in o.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.1)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.t.join(timeout=6)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def build_workload(rank, world, device, dense_tables=False):
+    import torch
+
+    from thb_diff_b200 import bspline_funcs as B
+    from thb_diff_b200 import configs
+    from thb_diff_b200.packed import PackedHierarchy
+
+    sp = configs.cubic3d_space(active_levels=4)
+    P = PackedHierarchy.from_space(sp, device=device, onehot_direct=not dense_tables)
+    params = B.grid_parametric_coordinates_device((GRID, GRID * world, GRID), device=device, y_first=rank, y_step=world)
+    cp = torch.from_numpy(configs.greville_ctrl_pts(sp)).to(device)
+    return sp, P, params, cp
+
+
+def host_tables(P):
+    from oracle import c_oracle
+
+    return c_oracle.HostTables(P.ndim, P.nlevels, P.degrees, P.TS, P.knot_off, P.knot_len, [list(P.sh_cells[l]) for l in range(P.nlevels)],
+                               P.cell_slot_off, P.knots.cpu().numpy(), P.cell_slot.cpu().numpy(), P.cellinfo.cpu().numpy(),
+                               P.dmask.cpu().numpy().view(np.uint64), P.supp_jm.cpu().numpy(), P.tiles.cpu().numpy())
+
+
+def cpu_port_rate(P, params_host, cp_host, target_s=12.0):
+    """points/s of the plain-C oracle port (OpenMP, all host threads) on a strided sample of the workload."""
+    from oracle import c_oracle
+
+    ht = host_tables(P)
+    n = len(params_host)
+    probe = params_host[:: max(n // 100_000, 1)]
+    t0 = time.perf_counter()
+    ht.eval(probe, cp_host)
+    dt = time.perf_counter() - t0
+    m = int(min(n, max(len(probe), len(probe) * target_s / max(dt, 1e-3))))
+    sample = params_host[:: max(n // m, 1)]
+    t0 = time.perf_counter()
+    ht.eval(sample, cp_host)
+    dt = time.perf_counter() - t0
+    return len(sample) / dt, c_oracle.num_threads(), len(sample)
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the reference's CPU path on the host cores, on a bounded sample of the same workload.
+    The reference's Python basis code cannot hold this space (its dense tables would need ~1e11 entries), so
+    PHI comes from the plain-C oracle port (all host threads) and the PHI.ctrl_pts contraction runs through
+    the reference's own compiled CPU extension (oracle/_ref = THB_extensions/compute_pts.cpp, unmodified)
+    when it is present, else through the C restatement of it."""
+    if rank != 0:
+        return
+    import torch
+
+    from oracle import build_ref, c_oracle
+
+    sp, P, params, cp = build_workload(0, max(world, 1), "cpu")
+    n = params.shape[0]
+    sample = params[:: n // SAMPLE_REF][:SAMPLE_REF].contiguous().numpy()
+    cph = cp.numpy()
+    ht = host_tables(P)
+    ext = build_ref.load()
+    kind = "reference" if ext is not None else "port"
+
+    def step():
+        r = ht.eval(sample, None)
+        S = P.cellinfo_host[np.maximum(r["slot"], 0), 5] * (r["slot"] >= 0)
+        cs = np.cumsum(S).astype(np.int64)
+        off = cs - S
+        r = ht.eval(sample, None, want_phi=True, offsets=off, nnz=int(cs[-1]))
+        info = P.cellinfo_host
+        jm_all = P.supp_jm.numpy()
+        Jm = np.concatenate([jm_all[info[s, 4]: info[s, 4] + info[s, 5]] for s in r["slot"] if s >= 0]).astype(np.int64)
+        phi = r["phi"].astype(np.float32)
+        if ext is not None:
+            out = ext.cpp_forward(torch.from_numpy(cph), torch.from_numpy(Jm), torch.from_numpy(phi), torch.from_numpy(cs))
+        else:
+            out = c_oracle.eval_forward(cph, Jm, phi, cs)
+        return out
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    val = len(sample) / dt
+    port_rate, threads, _ = cpu_port_rate(P, params.numpy(), cph, target_s=5.0)
+    line = {
+        "impl": "reference", "metric": "THB basis+eval points/sec", "value": val, "unit": "points/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C3: 3-D degree-3 THB, 4 levels, 256^3 grid per GPU", "sample": len(sample)},
+        "cpu_baseline": {"value": val, "unit": "points/s", "cores": threads, "kind": kind,
+                         "sample": f"{len(sample)} strided points of the 256^3 grid per step; PHI by the C port on {threads} threads, "
+                                   f"contraction by {'the reference compute_pts.cpp (single thread)' if ext is not None else 'the C restatement'}; "
+                                   f"C port alone (basis+eval, all threads): {port_rate:.3e} points/s"},
+        "e2e": {"value": val, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dense", action="store_true", help="store one-hot tiles explicitly (SURVEY 8d's dense operation count)")
+    ap.add_argument("--cellnet", action="store_true", help="fold tiles into per-cell control nets (fewest FLOPs)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-variants", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+
+    from thb_diff_b200 import _lib, engine
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    sp, P, params, cp = build_workload(rank, world, device, dense_tables=args.dense)
+    n = params.shape[0]
+    plan = engine.Plan(P, params)
+    n_in, nnz, nnz_tiled = plan.stats()
+    out = [torch.zeros((n, 3), dtype=torch.float32, device=device)]
+    st = torch.cuda.current_stream()
+
+    def step(timers=None):
+        if timers is not None:
+            timers[0].record()
+        plan.build()
+        if timers is not None:
+            timers[1].record()
+        engine.eval_fused(P, plan, cp, cellnet=args.cellnet, out=out)
+        if timers is not None:
+            timers[2].record()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    fp32_peak = max(engine.fma_peak(0), engine.fma_peak(1))  # TFLOP/s, measured on this GPU now
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    barrier()
+    launches0 = _lib.launch_count()
+    with ClockSampler(local) as clk:
+        t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_beg.record()
+        for k in range(args.steps):
+            step(ev[k])
+        t_end.record()
+        barrier()
+    launches = _lib.launch_count() - launches0
+    total_ms = t_beg.elapsed_time(t_end)
+    plan_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
+    kern_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / args.steps
+    tmax = torch.tensor([total_ms], device=device)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_per_step = float(tmax.item()) / args.steps
+    value = n * world / (ms_per_step * 1e-3)
+
+    # ---- end to end through the public API with HOST buffers (pinned): H2D params, plan, fused eval, D2H geometry
+    params_host = params.cpu().pin_memory()
+    out_host = torch.empty((n, 3), dtype=torch.float32).pin_memory()
+    params_dev = torch.empty_like(params)
+    plan_e = engine.Plan(P, params_dev)  # plan buffers bound to the staging tensor
+
+    def e2e_step():
+        params_dev.copy_(params_host, non_blocking=True)
+        plan_e.build()
+        engine.eval_fused(P, plan_e, cp, cellnet=args.cellnet, out=out)
+        out_host.copy_(out[0], non_blocking=True)
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ksteps = max(3, min(args.steps, 10))
+    e0.record()
+    for _ in range(ksteps):
+        e2e_step()
+    e1.record()
+    barrier()
+    e2e_ms = torch.tensor([e0.elapsed_time(e1) / ksteps], device=device)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_value = n * world / (float(e2e_ms.item()) * 1e-3)
+
+    # ---- roofline of the dominant kernel (fused tile kernel), from the live CUDA-event timing above
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    f_exec, f_dense = flop_model(P.degrees, 3, n_in, nnz, nnz_tiled)
+    if args.cellnet:  # per point only the window dot products; tiles are folded once per work item
+        cnt = plan.cell_count[: P.nslots].long()
+        nt = (P.cellinfo[:, 5] - P.cellinfo[:, 7]).long()
+        items = (cnt + engine.POINTS_PER_ITEM - 1) // engine.POINTS_PER_ITEM
+        f_exec = flop_model(P.degrees, 3, n_in, 0, 0)[0] + float((items * nt).sum()) * P.T * 2 * 4
+    alg_bytes = n * (4 * P.ndim + 4 * 3 + 4) + P.tiles.numel() * 4 + cp.numel() * 4
+    t_fp32 = f_exec / (fp32_peak * 1e12)
+    t_hbm = alg_bytes / (hbm_peak * 1e9)
+    t_roof = max(t_fp32, t_hbm)
+    bound = "fp32" if t_fp32 >= t_hbm else "hbm"
+    roofline = {
+        "bound": bound, "kernel": "thb_tile::k_tile<4,4,4,PPT,3,FUSED>",
+        "achieved": (f_exec / (kern_ms * 1e-3) / 1e12) if bound == "fp32" else (alg_bytes / (kern_ms * 1e-3) / 1e9),
+        "peak": fp32_peak if bound == "fp32" else hbm_peak, "unit": "TFLOP/s" if bound == "fp32" else "GB/s",
+        "frac": t_roof / (kern_ms * 1e-3), "traffic": None,
+        "kernel_ms": kern_ms, "plan_ms": plan_ms, "kernel_share_of_step": kern_ms / (plan_ms + kern_ms),
+        "flops_executed": f_exec, "flops_dense_model_8d": f_dense, "algorithmic_bytes": alg_bytes,
+        "frac_vs_dense_model_8d": (f_dense / (fp32_peak * 1e12)) / (kern_ms * 1e-3),
+        "peak_source": "FP32: thb_fma_peak micro-kernel measured in this run (MEASURED_PEAKS.json has no FP32 entry); "
+                       f"HBM: {'MEASURED_PEAKS.json' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s'}",
+    }
+
+    line = {
+        "metric": "THB basis+eval points/sec", "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C3: 3-D degree-3 THB, 4 active levels (~25% refined per level, graded), 256^3 param grid per GPU",
+                   "points_per_gpu": n, "nnz": nnz, "nnz_tiled": nnz_tiled, "mean_supports": nnz / max(n_in, 1), "nCP": P.nCP,
+                   "table_bytes": P.nbytes(), "l2": "inputs (201 MB params + 201 MB output per step) exceed the 126 MB L2",
+                   "tables": "dense one-hot tiles" if args.dense else "hybrid (own-level supports direct)", "cellnet": bool(args.cellnet),
+                   "sharding": f"y planes round-robin over {world} rank(s), no collective"},
+        "clocks": clk.summary(), "gpu_launches": int(launches),
+        "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": n * P.ndim * 4, "d2h_bytes_per_step": n * 3 * 4,
+                "ms_per_step": float(e2e_ms.item())},
+        "roofline": roofline,
+    }
+
+    if rank == 0 and world == 1 and not args.no_variants:
+        # the other two formulations of the same evaluation, for context (same plan, same inputs)
+        def time_variant(Pv, cellnet):
+            pl = engine.Plan(Pv, params)
+            o = [torch.zeros((n, 3), dtype=torch.float32, device=device)]
+            for _ in range(3):
+                engine.eval_fused(Pv, pl, cp, cellnet=cellnet, out=o)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            a.record()
+            for _ in range(5):
+                engine.eval_fused(Pv, pl, cp, cellnet=cellnet, out=o)
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / 5, float((o[0] - out[0]).abs().max())
+
+        var = {}
+        ms, dev = time_variant(P, not args.cellnet)
+        var["cellnet" if not args.cellnet else "per_point_phi"] = {"kernel_ms": ms, "max_abs_diff_vs_headline": dev}
+        if not args.dense:
+            from thb_diff_b200.packed import PackedHierarchy
+
+            Pd = PackedHierarchy.from_space(sp, device=device, onehot_direct=False)
+            ms, dev = time_variant(Pd, False)
+            var["dense_one_hot_tiles"] = {"kernel_ms": ms, "max_abs_diff_vs_headline": dev,
+                                          "frac_of_fp32_roofline_8d": (f_dense / (fp32_peak * 1e12)) / (ms * 1e-3)}
+            del Pd
+        line["variants"] = var
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rate, threads, m = cpu_port_rate(P, params_host.numpy(), cp.cpu().numpy())
+        line["cpu_baseline"] = {"value": rate, "unit": "points/s", "cores": threads, "kind": "port",
+                                "sample": f"{m} strided points of the 256^3 grid, plain-C float64 oracle (oracle/thb_oracle_c.c, OpenMP)"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
