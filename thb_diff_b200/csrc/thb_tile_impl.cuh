@@ -21,8 +21,9 @@
 
 namespace thb_tile {
 
-constexpr int kThreads = 128;
-constexpr int kChunk = 64;  // supports staged per chunk
+constexpr int kThreads = 32;   // forward tile kernels: one warp per CTA
+constexpr int kBwdThreads = 128;
+constexpr int kChunk = 64;
 
 enum { MODE_FUSED = 0, MODE_BASIS = 1 };
 
@@ -114,33 +115,250 @@ struct Bases {
     }
 };
 
+// Reciprocal knot differences of one cell: den(j, r) = K[P+r] - K[P-j+r], stored at j(j-1)/2 + r.
+// They do not depend on the point, so the Cox-de Boor recursion of every point of the item multiplies by
+// these instead of dividing (one division per entry per ITEM instead of p(p+1)/2 per dimension per POINT).
+template <int P, bool DER>
+THB_DEV void cox_de_boor_rk(float u, const float* K, const float* RK, float* N, float* dN) {
+    float left[P + 1], right[P + 1];
+    N[0] = 1.0f;
+#pragma unroll
+    for (int j = 1; j <= P; ++j) {
+        left[j] = u - K[P - j];
+        right[j] = K[P - 1 + j] - u;
+        float carry = 0.0f, prev_t = 0.0f;
+#pragma unroll
+        for (int r = 0; r < j; ++r) {
+            const float t = N[r] * RK[j * (j - 1) / 2 + r];
+            if (DER && j == P) {
+                dN[r] = float(P) * (prev_t - t);
+                prev_t = t;
+            }
+            N[r] = fmaf(right[r + 1], t, carry);
+            carry = left[j - r] * t;
+        }
+        if (DER && j == P) dN[P] = float(P) * prev_t;
+        N[j] = carry;
+    }
+    if (DER && P == 0) dN[0] = 0.0f;
+}
+
+template <class SH, bool DER>
+struct BasesRK {
+    float n0[SH::N0], n1[SH::N1], n2[SH::N2];
+    float d0[DER ? SH::N0 : 1], d1[DER ? SH::N1 : 1], d2[DER ? SH::N2 : 1];
+    THB_DEV void eval(const float* u, const float (*s_knots)[8], const float (*s_rk)[8]) {
+        cox_de_boor_rk<SH::P0, DER>(u[0], s_knots[0], s_rk[0], n0, d0);
+        cox_de_boor_rk<SH::P1, DER>(u[1], s_knots[1], s_rk[1], n1, d1);
+        if (SH::N2 > 1) cox_de_boor_rk<SH::P2, DER>(u[2], s_knots[2], s_rk[2], n2, d2);
+        else { n2[0] = 1.0f; if (DER) d2[0] = 0.0f; }
+    }
+    THB_DEV void tensor(int ch, float* tp) const {
+        float a[SH::N0], b[SH::N1], c[SH::N2];
+#pragma unroll
+        for (int i = 0; i < SH::N0; ++i) a[i] = (DER && (ch & 1)) ? d0[i] : n0[i];
+#pragma unroll
+        for (int i = 0; i < SH::N1; ++i) b[i] = (DER && (ch & 2)) ? d1[i] : n1[i];
+#pragma unroll
+        for (int i = 0; i < SH::N2; ++i) c[i] = (DER && (ch & 4)) ? d2[i] : n2[i];
+#pragma unroll
+        for (int i = 0; i < SH::N0; ++i)
+#pragma unroll
+            for (int j = 0; j < SH::N1; ++j) {
+                const float ab = a[i] * b[j];
+#pragma unroll
+                for (int k = 0; k < SH::N2; ++k) tp[(i * SH::N1 + j) * SH::N2 + k] = ab * c[k];
+            }
+#pragma unroll
+        for (int t = SH::T; t < SH::TS; ++t) tp[t] = 0.0f;
+    }
+};
+
+constexpr int kWChunk = 16;  // supports staged per chunk by one warp
+
+// One sub-batch of an item: PPT*32 points (lane-major), all channels.
+template <class SH, int PPT, int CPD, int MODE, bool DER>
+THB_DEV void warp_points(const thb_space_desc& sp, const Args& ar, const Item& it, int base, int ntile, bool cellnet,
+                         const float (*s_knots)[8], const float (*s_rk)[8], float (*s_cpw)[SH::TS], float4* s_cc, float* s_tiles) {
+    constexpr int T = SH::T, TS = SH::TS, NP = SH::NP, NQ = SH::NQ;
+    const int lane = threadIdx.x;
+    const int d = sp.ndim;
+    const bool use_direct = (it.ndir > 0) || (MODE == MODE_FUSED && cellnet);
+    const bool tile_loop = !(MODE == MODE_FUSED && cellnet) && ntile > 0;
+    int idx[PPT];
+    bool valid[PPT];
+    BasesRK<SH, DER> bs[PPT];
+#pragma unroll
+    for (int q = 0; q < PPT; ++q) {
+        const int li = base + q * 32 + lane;
+        valid[q] = li < it.count;
+        idx[q] = __ldg(ar.perm + it.begin + (valid[q] ? li : 0));
+    }
+#pragma unroll
+    for (int q = 0; q < PPT; ++q) {
+        float u[3] = {0.f, 0.f, 0.f};
+        for (int k = 0; k < d; ++k) u[k] = __ldg(ar.params + (int64_t)idx[q] * d + k);
+        bs[q].eval(u, s_knots, s_rk);
+    }
+    for (int chi = 0; chi < ar.nch; ++chi) {
+        const int ch = ar.channels[chi];
+        f32x2 tp2[PPT][NP];
+        int64_t off[PPT];
+#pragma unroll
+        for (int q = 0; q < PPT; ++q) {
+            float tp[TS];
+            bs[q].tensor(ch, tp);
+            if (MODE == MODE_BASIS) {
+                off[q] = valid[q] ? __ldg(ar.offsets + idx[q]) : 0;
+                if (it.ndir > 0 && valid[q]) {
+                    float* dst = ar.out[chi] + off[q];
+                    int pos = 0;
+#pragma unroll
+                    for (int t = 0; t < T; ++t) {
+                        if ((it.dm >> t) & 1ull) dst[pos++] = tp[t];
+                    }
+                }
+            }
+#pragma unroll
+            for (int m = 0; m < NP; ++m) tp2[q][m] = pack2(tp[2 * m], tp[2 * m + 1]);
+        }
+        float acc[PPT][4];
+#pragma unroll
+        for (int q = 0; q < PPT; ++q)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[q][k] = 0.0f;
+
+        if (MODE == MODE_FUSED && use_direct) {
+#pragma unroll
+            for (int k = 0; k < CPD; ++k) {
+                f32x2 a[PPT][2];
+#pragma unroll
+                for (int q = 0; q < PPT; ++q) a[q][0] = a[q][1] = 0ull;
+                const ulonglong2* col = reinterpret_cast<const ulonglong2*>(s_cpw[k]);
+#pragma unroll
+                for (int m = 0; m < NQ; ++m) {
+                    const ulonglong2 cv = col[m];
+#pragma unroll
+                    for (int q = 0; q < PPT; ++q) {
+                        ffma2(a[q][0], tp2[q][2 * m], cv.x);
+                        ffma2(a[q][1], tp2[q][2 * m + 1], cv.y);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < PPT; ++q) acc[q][k] = hsum2(a[q][0]) + hsum2(a[q][1]);
+            }
+        }
+        if (tile_loop) {
+            for (int c0 = 0; c0 < ntile; c0 += kWChunk) {
+                const int ns = min(kWChunk, ntile - c0);
+                __syncwarp();
+                {
+                    const float4* src = reinterpret_cast<const float4*>(sp.tiles + (int64_t)(it.toff + c0) * TS);
+                    float4* dst = reinterpret_cast<float4*>(s_tiles);
+                    for (int i = lane; i < ns * NQ; i += 32) dst[i] = __ldg(src + i);
+                    if (MODE == MODE_FUSED && lane < ns) {
+                        const int64_t r = __ldg(sp.supp_jm + it.soff + it.ndir + c0 + lane);
+                        float v[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                        for (int k = 0; k < CPD; ++k) v[k] = __ldg(ar.ctrl_pts + r * CPD + k);
+                        s_cc[lane] = make_float4(v[0], v[1], v[2], v[3]);
+                    }
+                }
+                __syncwarp();
+#pragma unroll 2
+                for (int s = 0; s < ns; ++s) {
+                    const ulonglong2* row = reinterpret_cast<const ulonglong2*>(s_tiles + s * TS);
+                    f32x2 a[PPT][2];
+#pragma unroll
+                    for (int q = 0; q < PPT; ++q) a[q][0] = a[q][1] = 0ull;
+#pragma unroll
+                    for (int m = 0; m < NQ; ++m) {
+                        const ulonglong2 tv = row[m];
+#pragma unroll
+                        for (int q = 0; q < PPT; ++q) {
+                            ffma2(a[q][0], tp2[q][2 * m], tv.x);
+                            ffma2(a[q][1], tp2[q][2 * m + 1], tv.y);
+                        }
+                    }
+                    if (MODE == MODE_FUSED) {
+                        const float4 cc = s_cc[s];
+#pragma unroll
+                        for (int q = 0; q < PPT; ++q) {
+                            const float phi = hsum2(a[q][0]) + hsum2(a[q][1]);
+                            acc[q][0] = fmaf(phi, cc.x, acc[q][0]);
+                            acc[q][1] = fmaf(phi, cc.y, acc[q][1]);
+                            acc[q][2] = fmaf(phi, cc.z, acc[q][2]);
+                            if (CPD == 4) acc[q][3] = fmaf(phi, cc.w, acc[q][3]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < PPT; ++q) {
+                            const float phi = hsum2(a[q][0]) + hsum2(a[q][1]);
+                            if (valid[q]) ar.out[chi][off[q] + it.ndir + c0 + s] = phi;
+                        }
+                    }
+                }
+            }
+        }
+        if (MODE == MODE_FUSED) {
+#pragma unroll
+            for (int q = 0; q < PPT; ++q) {
+                if (valid[q]) {
+                    float* o = ar.out[chi] + (int64_t)idx[q] * CPD;
+#pragma unroll
+                    for (int k = 0; k < CPD; ++k) o[k] = acc[q][k];
+                }
+            }
+        }
+    }
+}
+
+// Persistent, warp-autonomous kernel: every CTA is ONE warp that pulls work items from an atomic cursor.
+// No CTA-wide barrier exists; the item record of the next item is prefetched while the current one is
+// computed.
 template <int N0, int N1, int N2, int PPT, int CPD, int MODE, bool DER>
 __global__ void __launch_bounds__(kThreads) k_tile(const __grid_constant__ thb_space_desc sp, const __grid_constant__ Args ar) {
     using SH = Shp<N0, N1, N2>;
-    constexpr int T = SH::T, TS = SH::TS, NP = SH::NP, NQ = SH::NQ;
+    constexpr int T = SH::T, TS = SH::TS, NQ = SH::NQ;
     __shared__ float s_knots[3][8];
+    __shared__ float s_rk[3][8];
     __shared__ __align__(16) float s_cpw[4][TS];
-    __shared__ __align__(16) float4 s_cc[kChunk];
-    __shared__ __align__(16) float s_tiles[kChunk * TS];
-    __shared__ int s_item;
+    __shared__ __align__(16) float4 s_cc[kWChunk];
+    __shared__ __align__(16) float s_tiles[kWChunk * TS];
 
-    const int tid = threadIdx.x;
+    const int lane = threadIdx.x;
     const int nitems = ar.counters[0];
-    const int d = sp.ndim;
+    const bool cellnet = (MODE == MODE_FUSED) && ar.cellnet;
+
+    int cur_id = 0;
+    if (lane == 0) cur_id = atomicAdd(ar.counters + 1, 1);
+    cur_id = __shfl_sync(0xffffffffu, cur_id, 0);
+    if (cur_id >= nitems) return;
+    Item it = load_item(sp, ar.items, cur_id);
 
     for (;;) {
-        if (tid == 0) s_item = atomicAdd(ar.counters + 1, 1);
-        __syncthreads();
-        const int iti = s_item;
-        if (iti >= nitems) break;
-        const Item it = load_item(sp, ar.items, iti);
+        // claim the next item now; its record is loaded after the staging below (latency hidden by compute)
+        int nxt_id = 0;
+        if (lane == 0) nxt_id = atomicAdd(ar.counters + 1, 1);
         const int ntile = it.S - it.ndir;
-        const int nchunks = (ntile + kChunk - 1) / kChunk;
-        const bool use_direct = (it.ndir > 0) || (MODE == MODE_FUSED && ar.cellnet);
 
-        stage_knots<SH>(sp, it, s_knots);
+        __syncwarp();  // previous item's readers of the shared tables are done
+        if (lane < 24) {
+            const int dim = lane >> 3, m = lane & 7;
+            const int P = dim == 0 ? SH::P0 : (dim == 1 ? SH::P1 : SH::P2);
+            const int c = dim == 0 ? it.c0 : (dim == 1 ? it.c1 : it.c2);
+            if (dim < sp.ndim) {
+                const float* U = sp.knots + sp.knot_off[it.lev][dim] + c + 1;  // K[m] = U[m]
+                if (m < 2 * P) s_knots[dim][m] = __ldg(U + m);
+                if (m < P * (P + 1) / 2) {
+                    int j = 1, r = m;
+                    while (r >= j) { r -= j; ++j; }
+                    s_rk[dim][m] = 1.0f / (__ldg(U + P + r) - __ldg(U + P - j + r));
+                }
+            }
+        }
         if (MODE == MODE_FUSED) {
-            for (int t = tid; t < TS; t += kThreads) {
+            for (int t = lane; t < TS; t += 32) {
                 float v[4] = {0.f, 0.f, 0.f, 0.f};
                 if (it.ndir > 0 && t < T && ((it.dm >> t) & 1ull)) {
                     const int pos = __popcll(it.dm & ((1ull << t) - 1ull));
@@ -152,31 +370,22 @@ __global__ void __launch_bounds__(kThreads) k_tile(const __grid_constant__ thb_s
                 for (int k = 0; k < 4; ++k) s_cpw[k][t] = v[k];
             }
         }
-        __syncthreads();
-
-        auto stage_chunk = [&](int c0) {
-            const int ns = min(kChunk, ntile - c0);
-            const float4* src = reinterpret_cast<const float4*>(sp.tiles + (int64_t)(it.toff + c0) * TS);
-            float4* dst = reinterpret_cast<float4*>(s_tiles);
-            for (int i = tid; i < ns * NQ; i += kThreads) dst[i] = __ldg(src + i);
-            if (MODE == MODE_FUSED) {
-                for (int s = tid; s < ns; s += kThreads) {
-                    const int64_t r = __ldg(sp.supp_jm + it.soff + it.ndir + c0 + s);
+        __syncwarp();
+        if (cellnet) {
+            for (int c0 = 0; c0 < ntile; c0 += kWChunk) {
+                const int ns = min(kWChunk, ntile - c0);
+                const float4* src = reinterpret_cast<const float4*>(sp.tiles + (int64_t)(it.toff + c0) * TS);
+                float4* dst = reinterpret_cast<float4*>(s_tiles);
+                for (int i = lane; i < ns * NQ; i += 32) dst[i] = __ldg(src + i);
+                if (lane < ns) {
+                    const int64_t r = __ldg(sp.supp_jm + it.soff + it.ndir + c0 + lane);
                     float v[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                     for (int k = 0; k < CPD; ++k) v[k] = __ldg(ar.ctrl_pts + r * CPD + k);
-                    s_cc[s] = make_float4(v[0], v[1], v[2], v[3]);
+                    s_cc[lane] = make_float4(v[0], v[1], v[2], v[3]);
                 }
-            }
-        };
-
-        if (MODE == MODE_FUSED && ar.cellnet) {
-            // fold every tile into the window control net: Q[t] += tile_s[t] * CP_s
-            for (int c0 = 0; c0 < ntile; c0 += kChunk) {
-                stage_chunk(c0);
-                __syncthreads();
-                const int ns = min(kChunk, ntile - c0);
-                for (int t = tid; t < TS; t += kThreads) {
+                __syncwarp();
+                for (int t = lane; t < TS; t += 32) {
                     float q[4] = {0.f, 0.f, 0.f, 0.f};
                     for (int s = 0; s < ns; ++s) {
                         const float w = s_tiles[s * TS + t];
@@ -187,129 +396,22 @@ __global__ void __launch_bounds__(kThreads) k_tile(const __grid_constant__ thb_s
 #pragma unroll
                     for (int k = 0; k < 4; ++k) s_cpw[k][t] += q[k];
                 }
-                __syncthreads();
+                __syncwarp();
             }
         }
-        const bool tile_loop = !(MODE == MODE_FUSED && ar.cellnet) && ntile > 0;
+        // prefetch the next item's record
+        nxt_id = __shfl_sync(0xffffffffu, nxt_id, 0);
+        Item nxt = it;
+        if (nxt_id < nitems) nxt = load_item(sp, ar.items, nxt_id);
 
-        for (int base = 0; base < it.count; base += kThreads * PPT) {
-            // ---- per-thread points
-            int idx[PPT];
-            bool valid[PPT];
-            Bases<SH, DER> bs[PPT];
-#pragma unroll
-            for (int q = 0; q < PPT; ++q) {
-                const int li = base + q * kThreads + tid;
-                valid[q] = li < it.count;
-                idx[q] = __ldg(ar.perm + it.begin + (valid[q] ? li : 0));
-                float u[3] = {0.f, 0.f, 0.f};
-                for (int k = 0; k < d; ++k) u[k] = __ldg(ar.params + (int64_t)idx[q] * d + k);
-                bs[q].eval(u, s_knots);
-            }
-            for (int chi = 0; chi < ar.nch; ++chi) {
-                const int ch = ar.channels[chi];
-                f32x2 tp2[PPT][NP];
-                int64_t off[PPT];
-#pragma unroll
-                for (int q = 0; q < PPT; ++q) {
-                    float tp[TS];
-                    bs[q].tensor(ch, tp);
-                    if (MODE == MODE_BASIS) {
-                        off[q] = valid[q] ? __ldg(ar.offsets + idx[q]) : 0;
-                        if (it.ndir > 0 && valid[q]) {
-                            float* dst = ar.out[chi] + off[q];
-                            int pos = 0;
-#pragma unroll
-                            for (int t = 0; t < T; ++t) {
-                                if ((it.dm >> t) & 1ull) dst[pos++] = tp[t];
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int m = 0; m < NP; ++m) tp2[q][m] = pack2(tp[2 * m], tp[2 * m + 1]);
-                }
-                float acc[PPT][4];
-#pragma unroll
-                for (int q = 0; q < PPT; ++q)
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) acc[q][k] = 0.0f;
-
-                if (MODE == MODE_FUSED && use_direct) {
-                    // own-level supports (or the folded control net): CPD dot products with the window
-#pragma unroll
-                    for (int k = 0; k < CPD; ++k) {
-                        f32x2 a[PPT][2];
-#pragma unroll
-                        for (int q = 0; q < PPT; ++q) a[q][0] = a[q][1] = 0ull;
-                        const ulonglong2* col = reinterpret_cast<const ulonglong2*>(s_cpw[k]);
-#pragma unroll
-                        for (int m = 0; m < NQ; ++m) {
-                            const ulonglong2 cv = col[m];
-#pragma unroll
-                            for (int q = 0; q < PPT; ++q) {
-                                ffma2(a[q][0], tp2[q][2 * m], cv.x);
-                                ffma2(a[q][1], tp2[q][2 * m + 1], cv.y);
-                            }
-                        }
-#pragma unroll
-                        for (int q = 0; q < PPT; ++q) acc[q][k] = hsum2(a[q][0]) + hsum2(a[q][1]);
-                    }
-                }
-                if (tile_loop) {
-                    for (int c0 = 0; c0 < ntile; c0 += kChunk) {
-                        if (!(nchunks == 1 && (chi > 0 || base > 0))) {
-                            __syncthreads();
-                            stage_chunk(c0);
-                            __syncthreads();
-                        }
-                        const int ns = min(kChunk, ntile - c0);
-#pragma unroll 2
-                        for (int s = 0; s < ns; ++s) {
-                            const ulonglong2* row = reinterpret_cast<const ulonglong2*>(s_tiles + s * TS);
-                            f32x2 a[PPT][2];
-#pragma unroll
-                            for (int q = 0; q < PPT; ++q) a[q][0] = a[q][1] = 0ull;
-#pragma unroll
-                            for (int m = 0; m < NQ; ++m) {
-                                const ulonglong2 tv = row[m];
-#pragma unroll
-                                for (int q = 0; q < PPT; ++q) {
-                                    ffma2(a[q][0], tp2[q][2 * m], tv.x);
-                                    ffma2(a[q][1], tp2[q][2 * m + 1], tv.y);
-                                }
-                            }
-                            if (MODE == MODE_FUSED) {
-                                const float4 cc = s_cc[s];
-#pragma unroll
-                                for (int q = 0; q < PPT; ++q) {
-                                    const float phi = hsum2(a[q][0]) + hsum2(a[q][1]);
-                                    acc[q][0] = fmaf(phi, cc.x, acc[q][0]);
-                                    acc[q][1] = fmaf(phi, cc.y, acc[q][1]);
-                                    acc[q][2] = fmaf(phi, cc.z, acc[q][2]);
-                                    if (CPD == 4) acc[q][3] = fmaf(phi, cc.w, acc[q][3]);
-                                }
-                            } else {
-#pragma unroll
-                                for (int q = 0; q < PPT; ++q) {
-                                    const float phi = hsum2(a[q][0]) + hsum2(a[q][1]);
-                                    if (valid[q]) ar.out[chi][off[q] + it.ndir + c0 + s] = phi;
-                                }
-                            }
-                        }
-                    }
-                }
-                if (MODE == MODE_FUSED) {
-#pragma unroll
-                    for (int q = 0; q < PPT; ++q) {
-                        if (valid[q]) {
-                            float* o = ar.out[chi] + (int64_t)idx[q] * CPD;
-#pragma unroll
-                            for (int k = 0; k < CPD; ++k) o[k] = acc[q][k];
-                        }
-                    }
-                }
-            }
+        for (int base = 0; base < it.count; base += 32 * PPT) {
+            if (PPT == 2 && it.count - base <= 32)
+                warp_points<SH, 1, CPD, MODE, DER>(sp, ar, it, base, ntile, cellnet, s_knots, s_rk, s_cpw, s_cc, s_tiles);
+            else
+                warp_points<SH, PPT, CPD, MODE, DER>(sp, ar, it, base, ntile, cellnet, s_knots, s_rk, s_cpw, s_cc, s_tiles);
         }
+        if (nxt_id >= nitems) break;
+        it = nxt;
     }
 }
 
@@ -321,11 +423,11 @@ __global__ void __launch_bounds__(kThreads) k_tile(const __grid_constant__ thb_s
 // i.e. S*cp_dim atomics per ITEM (up to 256 points) instead of per point as in the reference
 // (compute_pts_cuda_kernels.cu:28-47).
 template <int N0, int N1, int N2, int CPD>
-__global__ void __launch_bounds__(kThreads) k_tile_backward(const __grid_constant__ thb_space_desc sp,
+__global__ void __launch_bounds__(kBwdThreads) k_tile_backward(const __grid_constant__ thb_space_desc sp,
                                                             const __grid_constant__ Args ar) {
     using SH = Shp<N0, N1, N2>;
     constexpr int T = SH::T, TS = SH::TS;
-    constexpr int LD = kThreads + 1;  // padded row length: conflict-free column reads
+    constexpr int LD = kBwdThreads + 1;  // padded row length: conflict-free column reads
     __shared__ float s_knots[3][8];
     __shared__ float s_tp[T * LD];
     __shared__ float s_g[4][LD];
@@ -343,12 +445,12 @@ __global__ void __launch_bounds__(kThreads) k_tile_backward(const __grid_constan
         if (iti >= nitems) break;
         const Item it = load_item(sp, ar.items, iti);
         stage_knots<SH>(sp, it, s_knots);
-        float gq[(T * CPD + kThreads - 1) / kThreads];  // this thread's share of the (t,k) outputs
+        float gq[(T * CPD + kBwdThreads - 1) / kBwdThreads];  // this thread's share of the (t,k) outputs
 #pragma unroll
-        for (int o = 0; o < (T * CPD + kThreads - 1) / kThreads; ++o) gq[o] = 0.0f;
+        for (int o = 0; o < (T * CPD + kBwdThreads - 1) / kBwdThreads; ++o) gq[o] = 0.0f;
         __syncthreads();
 
-        for (int base = 0; base < it.count; base += kThreads) {
+        for (int base = 0; base < it.count; base += kBwdThreads) {
             const int li = base + tid;
             const bool valid = li < it.count;
             const int idx = __ldg(ar.perm + it.begin + (valid ? li : 0));
@@ -363,10 +465,10 @@ __global__ void __launch_bounds__(kThreads) k_tile_backward(const __grid_constan
 #pragma unroll
             for (int k = 0; k < 4; ++k) s_g[k][tid] = (valid && k < CPD) ? __ldg(ar.grad_out + (int64_t)idx * CPD + k) : 0.0f;
             __syncthreads();
-            const int np = min(kThreads, it.count - base);
+            const int np = min(kBwdThreads, it.count - base);
 #pragma unroll
-            for (int o = 0; o < (T * CPD + kThreads - 1) / kThreads; ++o) {
-                const int e = o * kThreads + tid;
+            for (int o = 0; o < (T * CPD + kBwdThreads - 1) / kBwdThreads; ++o) {
+                const int e = o * kBwdThreads + tid;
                 if (e < T * CPD) {
                     const int t = e / CPD, k = e - t * CPD;
                     const float* row = s_tp + t * LD;
@@ -380,14 +482,14 @@ __global__ void __launch_bounds__(kThreads) k_tile_backward(const __grid_constan
         }
         // publish gQ
 #pragma unroll
-        for (int o = 0; o < (T * CPD + kThreads - 1) / kThreads; ++o) {
-            const int e = o * kThreads + tid;
+        for (int o = 0; o < (T * CPD + kBwdThreads - 1) / kBwdThreads; ++o) {
+            const int e = o * kBwdThreads + tid;
             if (e < T * CPD) s_gq[e / CPD][e % CPD] = gq[o];
         }
         __syncthreads();
         // own-level supports
         if (it.ndir > 0) {
-            for (int e = tid; e < T * CPD; e += kThreads) {
+            for (int e = tid; e < T * CPD; e += kBwdThreads) {
                 const int t = e / CPD, k = e - t * CPD;
                 if ((it.dm >> t) & 1ull) {
                     const int pos = __popcll(it.dm & ((1ull << t) - 1ull));
@@ -398,7 +500,7 @@ __global__ void __launch_bounds__(kThreads) k_tile_backward(const __grid_constan
         }
         // coarser-level supports
         const int ntile = it.S - it.ndir;
-        for (int e = tid; e < ntile * CPD; e += kThreads) {
+        for (int e = tid; e < ntile * CPD; e += kBwdThreads) {
             const int s = e / CPD, k = e - s * CPD;
             const float4* row = reinterpret_cast<const float4*>(sp.tiles + (int64_t)(it.toff + s) * TS);
             float a = 0.0f;
@@ -427,20 +529,21 @@ struct ShapeOps {
 };
 
 template <typename K>
-int persistent_grid(K kernel) {
+int persistent_grid(K kernel, int threads) {
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
     return per_sm * thb_num_sms();
 }
 
-#define THB_TILE_LAUNCH(KERNEL)                                                   \
+#define THB_TILE_LAUNCH_N(KERNEL, NT)                                             \
     do {                                                                          \
         static int grid = 0;                                                      \
-        if (grid == 0) grid = persistent_grid(KERNEL);                            \
-        KERNEL<<<grid, kThreads, 0, st>>>(*sp, *ar);                              \
+        if (grid == 0) grid = persistent_grid(KERNEL, NT);                        \
+        KERNEL<<<grid, NT, 0, st>>>(*sp, *ar);                                    \
         THB_LAUNCHED();                                                           \
         return THB_OK;                                                            \
     } while (0)
+#define THB_TILE_LAUNCH(KERNEL) THB_TILE_LAUNCH_N(KERNEL, kThreads)
 
 template <int N0, int N1, int N2>
 int launch_fused(const thb_space_desc* sp, const Args* ar, int ppt, int cpd, int der, cudaStream_t st) {
@@ -470,8 +573,8 @@ int launch_basis(const thb_space_desc* sp, const Args* ar, int ppt, int der, cud
 
 template <int N0, int N1, int N2>
 int launch_backward(const thb_space_desc* sp, const Args* ar, int cpd, cudaStream_t st) {
-    if (cpd == 3) THB_TILE_LAUNCH((k_tile_backward<N0, N1, N2, 3>));
-    if (cpd == 4) THB_TILE_LAUNCH((k_tile_backward<N0, N1, N2, 4>));
+    if (cpd == 3) THB_TILE_LAUNCH_N((k_tile_backward<N0, N1, N2, 3>), kBwdThreads);
+    if (cpd == 4) THB_TILE_LAUNCH_N((k_tile_backward<N0, N1, N2, 4>), kBwdThreads);
     return thb_set_error(THB_E_UNSUPPORTED, "backward: unsupported cp_dim");
 }
 

@@ -8,7 +8,7 @@ import torch
 from . import _lib
 from ._lib import PlanDesc, check, lib, ptr, require_cuda, stream_ptr
 
-POINTS_PER_ITEM = 256
+POINTS_PER_ITEM = 128
 
 CH_VALUE = 0
 
