@@ -63,8 +63,10 @@ typedef struct thb_space_desc {
 } thb_space_desc;
 
 /* A plan = the points of one batch grouped by active cell. All arrays are caller-allocated device memory:
- *   slot [N] i32, perm [N] i32, cell_count/cell_start/cell_cursor [nslots+1] i32,
- *   items [max_items][4] i32 (slot, begin, count, 0), counters [4] i32 (counters[0] = number of items).
+ *   slot [N] i32, perm [N] i32, sorted_params [N, ndim] f32 (the params in cell order: sorted_params[j] =
+ *   params[perm[j]]), cell_count/cell_start/cell_cursor [nslots+1] i32,
+ *   items [max_items][16] i32 (slot, begin, count, level, c0, c1, c2, supp_off, S, tile_off, n_direct, 0,
+ *   dmask lo, dmask hi, 0, 0), counters [4] i32 (counters[0] = number of items).
  * max_items >= N / points_per_item + nslots. */
 typedef struct thb_plan_desc {
     int64_t npoints;
@@ -72,6 +74,7 @@ typedef struct thb_plan_desc {
     int32_t max_items;
     int32_t* slot;
     int32_t* perm;
+    float* sorted_params;
     int32_t* cell_count;
     int32_t* cell_start;
     int32_t* cell_cursor;

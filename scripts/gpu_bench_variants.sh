@@ -1,7 +1,7 @@
 #!/bin/bash
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
-for f in tests/test_gpu_basis.py tests/test_gpu_fused.py; do
+for f in tests/test_gpu_spans.py tests/test_gpu_basis.py tests/test_gpu_fused.py; do
   n=$(basename $f .py); timeout 900 python -m pytest $f -q -m gpu -x --tb=short > gpurun_out/$n.log 2>&1; echo "$n rc=$?"; tail -n 4 gpurun_out/$n.log
 done
 for ppt in 2 1; do

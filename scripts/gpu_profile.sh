@@ -5,7 +5,7 @@ tag=${1:-r01}
 mkdir -p gpurun_out
 CMD="python bench.py --steps 2 --warmup 3 --no-variants --no-cpu-baseline"
 $CMD > gpurun_out/prof_plain_$tag.json 2> gpurun_out/prof_plain_$tag.err && \
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$tag.csv $CMD > gpurun_out/ncu_l_$tag.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"k_" -c 60 --csv --log-file gpurun_out/launches_$tag.csv $CMD > gpurun_out/ncu_l_$tag.log 2>&1
 echo "launch list rc=$?"
 $CMD > /dev/null 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:k_tile -s 3 -c 1 -o gpurun_out/prof_$tag -f $CMD > gpurun_out/ncu_f_$tag.log 2>&1

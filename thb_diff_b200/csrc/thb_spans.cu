@@ -76,10 +76,91 @@ __global__ void __launch_bounds__(256) k_expand_supports(const __grid_constant__
 }
 
 // ---- plan: counting sort of the points by slot ----------------------------------------------------------
+// Finest-level span with the knots of that level staged in shared memory.  First guess from a uniform
+// partition, corrected by walking (exact for 'uniform-ish' knots in <= 2 steps), binary search otherwise;
+// the result is the same span as span_right() for every in-domain u.
+THB_DEV int finest_cell(const float* __restrict__ U, int nk, int p, int nc, float u) {
+    // U[p .. p+nc] are the breakpoints; cell c <=> U[p+c] <= u < U[p+c+1]
+    const float u0 = U[p], u1 = U[p + nc];
+    if (!(u >= u0) || u > u1) return -1;  // also rejects NaN
+    if (u == u1) return nc - 1;           // reference rule: u == U[-1] belongs to the last span
+    int c = (int)((u - u0) / (u1 - u0) * (float)nc);
+    c = min(max(c, 0), nc - 1);
+    int steps = 0;
+    while (steps < 3 && u < U[p + c]) { --c; ++steps; }
+    while (steps < 3 && u >= U[p + c + 1]) { ++c; ++steps; }
+    if (steps >= 3) {  // far from uniform: binary search on the breakpoints
+        int lo = 0, hi = nc;  // invariant: U[p+lo] <= u < U[p+hi]
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (U[p + mid] <= u) lo = mid; else hi = mid;
+        }
+        c = lo;
+    }
+    return c;
+}
+
+constexpr int kPlanSmemKnots = 3 * 1024;
+
+// slot of a point given the finest-level knots in shared memory; the cell_slot entries of ALL levels are
+// fetched at once (independent loads) and the finest active one is selected.
+THB_DEV int locate_slot_fast(const thb_space_desc& sp, const float* const* Uk, const float* u) {
+    const int L = sp.nlevels - 1;
+    int cf[3] = {0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        if (k < sp.ndim) {
+            const int c = finest_cell(Uk[k], sp.knot_len[L][k], sp.degree[k], sp.ncells[L][k], u[k]);
+            if (c < 0) return -1;
+            cf[k] = c;
+        }
+    }
+    int cand[THB_MAX_LEVELS];
+#pragma unroll
+    for (int lev = 0; lev < THB_MAX_LEVELS; ++lev) {
+        cand[lev] = -1;
+        if (lev <= L) {
+            const int sh = L - lev;
+            int64_t lin = cf[0] >> sh;
+            lin = lin * sp.ncells[lev][1] + (cf[1] >> sh);
+            if (sp.ndim == 3) lin = lin * sp.ncells[lev][2] + (cf[2] >> sh);
+            cand[lev] = __ldg(sp.cell_slot + sp.cell_slot_off[lev] + lin);
+        }
+    }
+    int slot = -1;
+#pragma unroll
+    for (int lev = 0; lev < THB_MAX_LEVELS; ++lev)
+        if (cand[lev] >= 0) slot = cand[lev];  // later (finer) levels override
+    return slot;
+}
+
+THB_DEV bool stage_finest_knots(const thb_space_desc& sp, float* sk, const float** Uk) {
+    const int L = sp.nlevels - 1;
+    int tot = 0;
+    for (int k = 0; k < sp.ndim; ++k) tot += sp.knot_len[L][k];
+    const bool fits = tot <= kPlanSmemKnots;
+    int pos = 0;
+    for (int k = 0; k < sp.ndim; ++k) {
+        const float* g = sp.knots + sp.knot_off[L][k];
+        if (fits) {
+            for (int i = threadIdx.x; i < sp.knot_len[L][k]; i += blockDim.x) sk[pos + i] = g[i];
+            Uk[k] = sk + pos;
+            pos += sp.knot_len[L][k];
+        } else {
+            Uk[k] = g;
+        }
+    }
+    __syncthreads();
+    return fits;
+}
+
 // pass 1: slot per point + histogram.  Lanes of a warp that hit the same slot are combined with
 // __match_any_sync so that one atomic is issued per distinct slot per warp (grid-ordered points share cells).
 __global__ void __launch_bounds__(256) k_plan_count(const __grid_constant__ thb_space_desc sp, const float* __restrict__ params,
                                                     int64_t n, int32_t* __restrict__ slot_out, int32_t* __restrict__ count) {
+    __shared__ float sk[kPlanSmemKnots];
+    const float* Uk[3] = {nullptr, nullptr, nullptr};
+    stage_finest_knots(sp, sk, Uk);
     const int lane = threadIdx.x & 31;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t nround = (n + stride - 1) / stride * stride;  // keep whole warps in the loop for match_any
@@ -88,7 +169,7 @@ __global__ void __launch_bounds__(256) k_plan_count(const __grid_constant__ thb_
         if (i < n) {
             float u[3] = {0.f, 0.f, 0.f};
             for (int k = 0; k < sp.ndim; ++k) u[k] = params[i * sp.ndim + k];
-            slot = locate_slot(sp, u);
+            slot = locate_slot_fast(sp, Uk, u);
             slot_out[i] = slot;
         }
         const unsigned peers = __match_any_sync(0xffffffffu, slot);
@@ -103,75 +184,97 @@ __global__ void __launch_bounds__(1024) k_plan_scan(const int32_t* __restrict__ 
                                                     int32_t* __restrict__ counters) {
     __shared__ int s_pts[1024];
     __shared__ int s_itm[1024];
+    __shared__ int s_carry[2];
     const int t = threadIdx.x;
-    const int per = (nslots + 1023) / 1024;
-    const int b = t * per, e = min(b + per, nslots);
-    int pts = 0, itm = 0;
-    for (int i = b; i < e; ++i) {
-        const int c = count[i];
-        pts += c;
-        itm += (c + ppi - 1) / ppi;
-    }
-    s_pts[t] = pts;
-    s_itm[t] = itm;
+    if (t == 0) s_carry[0] = s_carry[1] = 0;
     __syncthreads();
-    // Hillis-Steele inclusive scan over 1024 partials
-    for (int o = 1; o < 1024; o <<= 1) {
-        int vp = 0, vi = 0;
-        if (t >= o) {
-            vp = s_pts[t - o];
-            vi = s_itm[t - o];
+    // tiles of 1024 consecutive slots: coalesced loads, Hillis-Steele scan in shared memory, running carry
+    for (int base = 0; base < nslots; base += 1024) {
+        const int i = base + t;
+        const int c = i < nslots ? count[i] : 0;
+        const int m = (c + ppi - 1) / ppi;
+        s_pts[t] = c;
+        s_itm[t] = m;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {
+            int vp = 0, vi = 0;
+            if (t >= o) { vp = s_pts[t - o]; vi = s_itm[t - o]; }
+            __syncthreads();
+            s_pts[t] += vp;
+            s_itm[t] += vi;
+            __syncthreads();
+        }
+        const int cp = s_carry[0], ci = s_carry[1];
+        if (i < nslots) {
+            start[i] = cp + s_pts[t] - c;
+            item_start[i] = ci + s_itm[t] - m;
         }
         __syncthreads();
-        s_pts[t] += vp;
-        s_itm[t] += vi;
+        if (t == 1023) { s_carry[0] = cp + s_pts[1023]; s_carry[1] = ci + s_itm[1023]; }
         __syncthreads();
     }
-    int rp = s_pts[t] - pts, ri = s_itm[t] - itm;  // exclusive prefix of this thread's chunk
-    for (int i = b; i < e; ++i) {
-        const int c = count[i];
-        start[i] = rp;
-        item_start[i] = ri;
-        rp += c;
-        ri += (c + ppi - 1) / ppi;
-    }
-    if (t == 1023) {
-        start[nslots] = s_pts[1023];
-        counters[0] = s_itm[1023];  // number of work items
-        counters[1] = 0;            // dynamic scheduler cursor
-        counters[2] = s_pts[1023];  // number of in-domain points
+    if (t == 0) {
+        start[nslots] = s_carry[0];
+        counters[0] = s_carry[1];  // number of work items
+        counters[1] = 0;           // dynamic scheduler cursor
+        counters[2] = s_carry[0];  // number of in-domain points
     }
 }
 
-// pass 3: work items of every cell; afterwards cell_cursor is zeroed to serve as the scatter cursor.
-__global__ void __launch_bounds__(256) k_plan_items(const int32_t* __restrict__ count, const int32_t* __restrict__ start,
-                                                    int32_t* __restrict__ item_start_then_cursor, int nslots, int ppi,
-                                                    int max_items, int4* __restrict__ items) {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+// pass 3: work items of every cell (one warp per cell, lanes emit items in parallel); afterwards
+// cell_cursor is zeroed to serve as the scatter cursor.
+__global__ void __launch_bounds__(256) k_plan_items(const __grid_constant__ thb_space_desc sp, const int32_t* __restrict__ count,
+                                                    const int32_t* __restrict__ start, int32_t* __restrict__ item_start_then_cursor,
+                                                    int nslots, int ppi, int max_items, int4* __restrict__ items) {
+    const int lane = threadIdx.x & 31;
+    const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (s >= nslots) return;
     const int c = count[s], b = start[s];
-    int it = item_start_then_cursor[s];
-    for (int o = 0; o < c; o += ppi, ++it) {
-        if (it < max_items) items[it] = make_int4(s, b + o, min(ppi, c - o), 0);
+    const int it0 = item_start_then_cursor[s];
+    __syncwarp();
+    const int m = (c + ppi - 1) / ppi;
+    if (m == 0) {
+        if (lane == 0) item_start_then_cursor[s] = 0;
+        return;
     }
-    item_start_then_cursor[s] = 0;
+    const int4* ci = reinterpret_cast<const int4*>(sp.cellinfo + (int64_t)s * THB_INFO_W);
+    const int4 a = __ldg(ci), e = __ldg(ci + 1);  // level c0 c1 c2 | supp_off S tile_off n_direct
+    const unsigned long long dm = __ldg(sp.dmask + s);
+    for (int j = lane; j < m; j += 32) {
+        if (it0 + j < max_items) {
+            int4* o = items + (int64_t)(it0 + j) * 4;
+            o[0] = make_int4(s, b + j * ppi, min(ppi, c - j * ppi), a.x);
+            o[1] = make_int4(a.y, a.z, a.w, e.x);
+            o[2] = make_int4(e.y, e.z, e.w, 0);
+            o[3] = make_int4((int)(unsigned)(dm & 0xffffffffull), (int)(unsigned)(dm >> 32), 0, 0);
+        }
+    }
+    if (lane == 0) item_start_then_cursor[s] = 0;
 }
 
-// pass 4: scatter point ids into cell order; lanes of one warp that share a slot take consecutive places,
-// which keeps runs of neighbouring points contiguous in the permutation.
-__global__ void __launch_bounds__(256) k_plan_scatter(const int32_t* __restrict__ slot, int64_t n, const int32_t* __restrict__ start,
-                                                      int32_t* __restrict__ cursor, int32_t* __restrict__ perm) {
+// pass 4: scatter point ids AND the points themselves into cell order; lanes of one warp that share a slot
+// take consecutive places, which keeps runs of neighbouring points contiguous.
+__global__ void __launch_bounds__(256) k_plan_scatter(const int32_t* __restrict__ slot, const float* __restrict__ params, int ndim,
+                                                      int64_t n, const int32_t* __restrict__ start, int32_t* __restrict__ cursor,
+                                                      int32_t* __restrict__ perm, float* __restrict__ sorted) {
     const int lane = threadIdx.x & 31;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t nround = (n + stride - 1) / stride * stride;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
         const int s = i < n ? slot[i] : -1;
+        float u[3] = {0.f, 0.f, 0.f};
+        if (s >= 0)
+            for (int k = 0; k < ndim; ++k) u[k] = params[i * ndim + k];
         const unsigned peers = __match_any_sync(0xffffffffu, s);
         const int leader = __ffs(peers) - 1;
         int base = 0;
         if (s >= 0 && lane == leader) base = atomicAdd(cursor + s, __popc(peers));
         base = __shfl_sync(0xffffffffu, base, leader);
-        if (s >= 0) perm[start[s] + base + __popc(peers & ((1u << lane) - 1u))] = (int32_t)i;
+        if (s >= 0) {
+            const int64_t pos = (int64_t)start[s] + base + __popc(peers & ((1u << lane) - 1u));
+            perm[pos] = (int32_t)i;
+            for (int k = 0; k < ndim; ++k) sorted[pos * ndim + k] = u[k];
+        }
     }
 }
 
@@ -245,7 +348,7 @@ extern "C" int thb_plan_build(const thb_space_desc* space, const float* params, 
     if (rc) return rc;
     THB_REQUIRE(plan && plan->npoints >= 0 && plan->npoints < (int64_t)2147483647, "thb_plan_build: bad point count");
     THB_REQUIRE(plan->points_per_item >= 32 && plan->points_per_item <= 1024, "thb_plan_build: points_per_item out of range");
-    THB_REQUIRE(plan->slot && plan->perm && plan->cell_count && plan->cell_start && plan->cell_cursor && plan->items && plan->counters,
+    THB_REQUIRE(plan->slot && plan->perm && plan->sorted_params && plan->cell_count && plan->cell_start && plan->cell_cursor && plan->items && plan->counters,
                 "thb_plan_build: null plan buffer");
     THB_REQUIRE((int64_t)plan->max_items >= plan->npoints / plan->points_per_item + space->nslots, "thb_plan_build: max_items too small");
     cudaStream_t st = (cudaStream_t)stream;
@@ -259,11 +362,12 @@ extern "C" int thb_plan_build(const thb_space_desc* space, const float* params, 
     }
     k_plan_scan<<<1, 1024, 0, st>>>(plan->cell_count, plan->cell_start, plan->cell_cursor, ns, plan->points_per_item, plan->counters);
     THB_LAUNCHED();
-    k_plan_items<<<(ns + 255) / 256, 256, 0, st>>>(plan->cell_count, plan->cell_start, plan->cell_cursor, ns, plan->points_per_item,
+    k_plan_items<<<(ns * 32 + 255) / 256, 256, 0, st>>>(*space, plan->cell_count, plan->cell_start, plan->cell_cursor, ns, plan->points_per_item,
                                                    plan->max_items, (int4*)plan->items);
     THB_LAUNCHED();
     if (n > 0) {
-        k_plan_scatter<<<grid_for(n, 256, 16), 256, 0, st>>>(plan->slot, n, plan->cell_start, plan->cell_cursor, plan->perm);
+        k_plan_scatter<<<grid_for(n, 256, 16), 256, 0, st>>>(plan->slot, params, space->ndim, n, plan->cell_start, plan->cell_cursor,
+                                                             plan->perm, plan->sorted_params);
         THB_LAUNCHED();
     }
     return THB_OK;

@@ -31,7 +31,7 @@ static int env_int(const char* name, int dflt) {
 using namespace thb_tile;
 
 static int check_plan(const thb_plan_desc* plan, const char* who) {
-    THB_REQUIRE(plan && plan->perm && plan->items && plan->counters, "%s: null plan buffer", who);
+    THB_REQUIRE(plan && plan->perm && plan->sorted_params && plan->items && plan->counters, "%s: null plan buffer", who);
     return THB_OK;
 }
 
@@ -65,7 +65,7 @@ extern "C" int thb_basis_tiled(const thb_space_desc* space, const thb_plan_desc*
         ar.out[c] = phi_out_host[c];
     }
     ar.perm = plan->perm; ar.items = (const int4*)plan->items; ar.counters = plan->counters;
-    ar.params = params; ar.offsets = offsets;
+    ar.params = params; ar.sorted = plan->sorted_params; ar.offsets = offsets;
     cudaStream_t st = (cudaStream_t)stream;
     THB_CUDA(cudaMemsetAsync(plan->counters + 1, 0, sizeof(int32_t), st));
     return ops->basis(space, &ar, env_int("THB_BASIS_PPT", 1), der ? 1 : 0, st);
@@ -90,7 +90,7 @@ extern "C" int thb_eval_fused(const thb_space_desc* space, const thb_plan_desc* 
         ar.out[c] = out_host[c];
     }
     ar.perm = plan->perm; ar.items = (const int4*)plan->items; ar.counters = plan->counters;
-    ar.params = params; ar.ctrl_pts = ctrl_pts; ar.cellnet = cellnet ? 1 : 0;
+    ar.params = params; ar.sorted = plan->sorted_params; ar.ctrl_pts = ctrl_pts; ar.cellnet = cellnet ? 1 : 0;
     cudaStream_t st = (cudaStream_t)stream;
     THB_CUDA(cudaMemsetAsync(plan->counters + 1, 0, sizeof(int32_t), st));
     return ops->fused(space, &ar, env_int("THB_FUSED_PPT", 2), cp_dim, der ? 1 : 0, st);
@@ -111,7 +111,7 @@ extern "C" int thb_eval_fused_backward(const thb_space_desc* space, const thb_pl
     if (!ops) return thb_set_error(THB_E_UNSUPPORTED, "thb_eval_fused_backward: no kernel for degrees (%d,%d,%d)", space->degree[0], space->degree[1], space->degree[2]);
     Args ar = {};
     ar.perm = plan->perm; ar.items = (const int4*)plan->items; ar.counters = plan->counters;
-    ar.params = params; ar.grad_out = grad_out; ar.grad_cp = grad_ctrl_pts;
+    ar.params = params; ar.sorted = plan->sorted_params; ar.grad_out = grad_out; ar.grad_cp = grad_ctrl_pts;
     THB_CUDA(cudaMemsetAsync(plan->counters + 1, 0, sizeof(int32_t), st));
     return ops->backward(space, &ar, cp_dim, st);
 }

@@ -32,6 +32,7 @@ struct Args {
     const int4* items;
     int32_t* counters;  // [0] = number of items, [1] = scheduler cursor
     const float* params;
+    const float* sorted;     // plan->sorted_params (cell order)
     const float* ctrl_pts;   // fused
     const int64_t* offsets;  // basis: exclusive prefix sum of num_supp (caller order)
     float* out[4];           // per channel: fused [N, cp_dim] / basis [nnz]
@@ -59,16 +60,20 @@ struct Item {
     unsigned long long dm;
 };
 
-THB_DEV Item load_item(const thb_space_desc& sp, const int4* items, int it) {
+// Work-item record written by thb_plan_build: 16 ints = slot, begin, count, level, c0, c1, c2, supp_off,
+// S, tile_off, n_direct, 0, dmask lo, dmask hi, 0, 0  (the cell's row of cellinfo/dmask is copied in, so one
+// 64-byte read describes the item).
+THB_DEV Item unpack_item(const int4 v0, const int4 v1, const int4 v2, const int4 v3) {
     Item r;
-    const int4 v = __ldg(items + it);
-    r.slot = v.x; r.begin = v.y; r.count = v.z;
-    const int4* ci = reinterpret_cast<const int4*>(sp.cellinfo + (int64_t)r.slot * THB_INFO_W);
-    const int4 a = __ldg(ci), b = __ldg(ci + 1);
-    r.lev = a.x; r.c0 = a.y; r.c1 = a.z; r.c2 = a.w;
-    r.soff = b.x; r.S = b.y; r.toff = b.z; r.ndir = b.w;
-    r.dm = __ldg(sp.dmask + r.slot);
+    r.slot = v0.x; r.begin = v0.y; r.count = v0.z; r.lev = v0.w;
+    r.c0 = v1.x; r.c1 = v1.y; r.c2 = v1.z; r.soff = v1.w;
+    r.S = v2.x; r.toff = v2.y; r.ndir = v2.z;
+    r.dm = (unsigned long long)(unsigned)v3.x | ((unsigned long long)(unsigned)v3.y << 32);
     return r;
+}
+THB_DEV Item load_item(const thb_space_desc& sp, const int4* items, int it) {
+    const int4* p = items + (int64_t)it * 4;
+    return unpack_item(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
 }
 
 template <class SH>
@@ -175,43 +180,92 @@ struct BasesRK {
 };
 
 constexpr int kWChunk = 16;  // supports staged per chunk by one warp
+constexpr int kMaxCC = 128;  // coarse-support control points gathered once per item (else per chunk)
 
-// One sub-batch of an item: PPT*32 points (lane-major), all channels.
-template <class SH, int PPT, int CPD, int MODE, bool DER>
-THB_DEV void warp_points(const thb_space_desc& sp, const Args& ar, const Item& it, int base, int ntile, bool cellnet,
-                         const float (*s_knots)[8], const float (*s_rk)[8], float (*s_cpw)[SH::TS], float4* s_cc, float* s_tiles) {
-    constexpr int T = SH::T, TS = SH::TS, NP = SH::NP, NQ = SH::NQ;
+THB_DEV void cp_async16(void* smem, const void* gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+THB_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+THB_DEV void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Per-lane data of one sub-batch (PPT*32 points of one item, lane-major), loaded one sub-batch ahead.
+template <int PPT, int MODE>
+struct PtData {
+    int idx[PPT];          // caller-order index of the point, -1 = no point
+    float u[PPT][3];
+    int64_t off[MODE == MODE_BASIS ? PPT : 1];
+};
+
+template <int PPT, int MODE>
+THB_DEV void load_points(const Args& ar, int d, int begin, int count, int base, PtData<PPT, MODE>& pd) {
     const int lane = threadIdx.x;
-    const int d = sp.ndim;
-    const bool use_direct = (it.ndir > 0) || (MODE == MODE_FUSED && cellnet);
-    const bool tile_loop = !(MODE == MODE_FUSED && cellnet) && ntile > 0;
-    int idx[PPT];
-    bool valid[PPT];
-    BasesRK<SH, DER> bs[PPT];
 #pragma unroll
     for (int q = 0; q < PPT; ++q) {
         const int li = base + q * 32 + lane;
-        valid[q] = li < it.count;
-        idx[q] = __ldg(ar.perm + it.begin + (valid[q] ? li : 0));
-    }
+        const bool valid = li < count;
+        const int64_t j = begin + (valid ? li : 0);
+        const int id = __ldg(ar.perm + j);
+        pd.idx[q] = valid ? id : -1;
 #pragma unroll
-    for (int q = 0; q < PPT; ++q) {
-        float u[3] = {0.f, 0.f, 0.f};
-        for (int k = 0; k < d; ++k) u[k] = __ldg(ar.params + (int64_t)idx[q] * d + k);
-        bs[q].eval(u, s_knots, s_rk);
+        for (int k = 0; k < 3; ++k) pd.u[q][k] = (k < d) ? __ldg(ar.sorted + j * d + k) : 0.f;
+        if (MODE == MODE_BASIS) pd.off[q] = __ldg(ar.offsets + id);
     }
+}
+
+// flat ids of the own-level window functions handled by this lane (t = lane, lane + 32), -1 if inactive
+THB_DEV void load_window_ids(const thb_space_desc& sp, const Item& it, int T, int* wj) {
+    const int lane = threadIdx.x;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int t = lane + 32 * h;
+        wj[h] = -1;
+        if (it.ndir > 0 && t < T && ((it.dm >> t) & 1ull))
+            wj[h] = __ldg(sp.supp_jm + it.soff + __popcll(it.dm & ((1ull << t) - 1ull)));
+    }
+}
+
+template <int CPD>
+THB_DEV void gather_cc(const thb_space_desc& sp, const Args& ar, const Item& it, int first, int n, float4* s_cc) {
+    for (int s = threadIdx.x; s < n; s += 32) {
+        const int64_t r = __ldg(sp.supp_jm + it.soff + it.ndir + first + s);
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < CPD; ++k) v[k] = __ldg(ar.ctrl_pts + r * CPD + k);
+        s_cc[s] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
+
+template <int NQ>
+THB_DEV void issue_chunk(const thb_space_desc& sp, const Item& it, int c0, int ns, int TS, float* buf) {
+    const float4* src = reinterpret_cast<const float4*>(sp.tiles + (int64_t)(it.toff + c0) * TS);
+    float4* dst = reinterpret_cast<float4*>(buf);
+    for (int i = threadIdx.x; i < ns * NQ; i += 32) cp_async16(dst + i, src + i);
+    cp_async_commit();
+}
+
+// One sub-batch of an item: PPT*32 points (lane-major), all channels.
+template <class SH, int PPT, int CPD, int MODE, bool DER>
+THB_DEV void warp_points(const thb_space_desc& sp, const Args& ar, const Item& it, const PtData<PPT, MODE>& pd, int ntile, bool cellnet,
+                         const float (*s_knots)[8], const float (*s_rk)[8], float (*s_cpw)[SH::TS], float4* s_cc, float* s_tiles) {
+    constexpr int T = SH::T, TS = SH::TS, NP = SH::NP, NQ = SH::NQ;
+    const bool use_direct = (it.ndir > 0) || (MODE == MODE_FUSED && cellnet);
+    const bool tile_loop = !(MODE == MODE_FUSED && cellnet) && ntile > 0;
+    const bool cc_all = ntile <= kMaxCC;
+    BasesRK<SH, DER> bs[PPT];
+#pragma unroll
+    for (int q = 0; q < PPT; ++q) bs[q].eval(pd.u[q], s_knots, s_rk);
     for (int chi = 0; chi < ar.nch; ++chi) {
         const int ch = ar.channels[chi];
         f32x2 tp2[PPT][NP];
-        int64_t off[PPT];
 #pragma unroll
         for (int q = 0; q < PPT; ++q) {
             float tp[TS];
             bs[q].tensor(ch, tp);
             if (MODE == MODE_BASIS) {
-                off[q] = valid[q] ? __ldg(ar.offsets + idx[q]) : 0;
-                if (it.ndir > 0 && valid[q]) {
-                    float* dst = ar.out[chi] + off[q];
+                if (it.ndir > 0 && pd.idx[q] >= 0) {
+                    float* dst = ar.out[chi] + pd.off[q];
                     int pos = 0;
 #pragma unroll
                     for (int t = 0; t < T; ++t) {
@@ -249,25 +303,26 @@ THB_DEV void warp_points(const thb_space_desc& sp, const Args& ar, const Item& i
             }
         }
         if (tile_loop) {
+            // tiles stream through two shared-memory buffers: cp.async of chunk c+1 overlaps the FMAs of chunk c
+            __syncwarp();
+            issue_chunk<NQ>(sp, it, 0, min(kWChunk, ntile), TS, s_tiles);
+            int buf = 0;
             for (int c0 = 0; c0 < ntile; c0 += kWChunk) {
                 const int ns = min(kWChunk, ntile - c0);
-                __syncwarp();
-                {
-                    const float4* src = reinterpret_cast<const float4*>(sp.tiles + (int64_t)(it.toff + c0) * TS);
-                    float4* dst = reinterpret_cast<float4*>(s_tiles);
-                    for (int i = lane; i < ns * NQ; i += 32) dst[i] = __ldg(src + i);
-                    if (MODE == MODE_FUSED && lane < ns) {
-                        const int64_t r = __ldg(sp.supp_jm + it.soff + it.ndir + c0 + lane);
-                        float v[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                        for (int k = 0; k < CPD; ++k) v[k] = __ldg(ar.ctrl_pts + r * CPD + k);
-                        s_cc[lane] = make_float4(v[0], v[1], v[2], v[3]);
-                    }
+                const int c1 = c0 + kWChunk;
+                if (c1 < ntile) {
+                    issue_chunk<NQ>(sp, it, c1, min(kWChunk, ntile - c1), TS, s_tiles + (buf ^ 1) * (kWChunk * TS));
+                    cp_async_wait<1>();
+                } else {
+                    cp_async_wait<0>();
                 }
+                if (MODE == MODE_FUSED && !cc_all) gather_cc<CPD>(sp, ar, it, c0, ns, s_cc);
                 __syncwarp();
+                const float* tb = s_tiles + buf * (kWChunk * TS);
+                const float4* ccp = s_cc + (cc_all ? c0 : 0);
 #pragma unroll 2
                 for (int s = 0; s < ns; ++s) {
-                    const ulonglong2* row = reinterpret_cast<const ulonglong2*>(s_tiles + s * TS);
+                    const ulonglong2* row = reinterpret_cast<const ulonglong2*>(tb + s * TS);
                     f32x2 a[PPT][2];
 #pragma unroll
                     for (int q = 0; q < PPT; ++q) a[q][0] = a[q][1] = 0ull;
@@ -281,7 +336,7 @@ THB_DEV void warp_points(const thb_space_desc& sp, const Args& ar, const Item& i
                         }
                     }
                     if (MODE == MODE_FUSED) {
-                        const float4 cc = s_cc[s];
+                        const float4 cc = ccp[s];
 #pragma unroll
                         for (int q = 0; q < PPT; ++q) {
                             const float phi = hsum2(a[q][0]) + hsum2(a[q][1]);
@@ -294,17 +349,19 @@ THB_DEV void warp_points(const thb_space_desc& sp, const Args& ar, const Item& i
 #pragma unroll
                         for (int q = 0; q < PPT; ++q) {
                             const float phi = hsum2(a[q][0]) + hsum2(a[q][1]);
-                            if (valid[q]) ar.out[chi][off[q] + it.ndir + c0 + s] = phi;
+                            if (pd.idx[q] >= 0) ar.out[chi][pd.off[q] + it.ndir + c0 + s] = phi;
                         }
                     }
                 }
+                __syncwarp();
+                buf ^= 1;
             }
         }
         if (MODE == MODE_FUSED) {
 #pragma unroll
             for (int q = 0; q < PPT; ++q) {
-                if (valid[q]) {
-                    float* o = ar.out[chi] + (int64_t)idx[q] * CPD;
+                if (pd.idx[q] >= 0) {
+                    float* o = ar.out[chi] + (int64_t)pd.idx[q] * CPD;
 #pragma unroll
                     for (int k = 0; k < CPD; ++k) o[k] = acc[q][k];
                 }
@@ -314,40 +371,52 @@ THB_DEV void warp_points(const thb_space_desc& sp, const Args& ar, const Item& i
 }
 
 // Persistent, warp-autonomous kernel: every CTA is ONE warp that pulls work items from an atomic cursor.
-// No CTA-wide barrier exists; the item record of the next item is prefetched while the current one is
-// computed.
+// No CTA-wide barrier exists.  A three-deep software pipeline hides the global-memory latency chain:
+// while item i is computed, the record of item i+1 is already in registers, the id of item i+2 is being
+// claimed, and the point data (cell-sorted params, output index) of the next sub-batch is in flight.
 template <int N0, int N1, int N2, int PPT, int CPD, int MODE, bool DER>
 __global__ void __launch_bounds__(kThreads) k_tile(const __grid_constant__ thb_space_desc sp, const __grid_constant__ Args ar) {
     using SH = Shp<N0, N1, N2>;
     constexpr int T = SH::T, TS = SH::TS, NQ = SH::NQ;
+    constexpr int SB = 32 * PPT;
     __shared__ float s_knots[3][8];
     __shared__ float s_rk[3][8];
     __shared__ __align__(16) float s_cpw[4][TS];
-    __shared__ __align__(16) float4 s_cc[kWChunk];
-    __shared__ __align__(16) float s_tiles[kWChunk * TS];
+    __shared__ __align__(16) float4 s_cc[kMaxCC];
+    __shared__ __align__(16) float s_tiles[2 * kWChunk * TS];
 
     const int lane = threadIdx.x;
     const int nitems = ar.counters[0];
+    const int d = sp.ndim;
     const bool cellnet = (MODE == MODE_FUSED) && ar.cellnet;
 
-    int cur_id = 0;
-    if (lane == 0) cur_id = atomicAdd(ar.counters + 1, 1);
-    cur_id = __shfl_sync(0xffffffffu, cur_id, 0);
-    if (cur_id >= nitems) return;
-    Item it = load_item(sp, ar.items, cur_id);
+    __shared__ __align__(16) int4 s_nx[4];  // record of the next item (filled by cp.async)
+    int id = 0;
+    if (lane == 0) id = atomicAdd(ar.counters + 1, 1);
+    id = __shfl_sync(0xffffffffu, id, 0);
+    if (id >= nitems) return;
+    Item it = load_item(sp, ar.items, id);
+    if (lane == 0) id = atomicAdd(ar.counters + 1, 1);
+    id = __shfl_sync(0xffffffffu, id, 0);
+    bool nx_valid = id < nitems;
+    if (nx_valid && lane < 4) cp_async16(s_nx + lane, ar.items + (int64_t)id * 4 + lane);
+    cp_async_commit();
+    int nn_id = 0;
+    if (lane == 0) nn_id = atomicAdd(ar.counters + 1, 1);
+
+    PtData<PPT, MODE> pd;
+    load_points<PPT, MODE>(ar, d, it.begin, it.count, 0, pd);
+    int wj[2];
+    load_window_ids(sp, it, T, wj);
 
     for (;;) {
-        // claim the next item now; its record is loaded after the staging below (latency hidden by compute)
-        int nxt_id = 0;
-        if (lane == 0) nxt_id = atomicAdd(ar.counters + 1, 1);
         const int ntile = it.S - it.ndir;
-
-        __syncwarp();  // previous item's readers of the shared tables are done
+        __syncwarp();  // readers of the previous item's shared tables are done
         if (lane < 24) {
             const int dim = lane >> 3, m = lane & 7;
             const int P = dim == 0 ? SH::P0 : (dim == 1 ? SH::P1 : SH::P2);
             const int c = dim == 0 ? it.c0 : (dim == 1 ? it.c1 : it.c2);
-            if (dim < sp.ndim) {
+            if (dim < d) {
                 const float* U = sp.knots + sp.knot_off[it.lev][dim] + c + 1;  // K[m] = U[m]
                 if (m < 2 * P) s_knots[dim][m] = __ldg(U + m);
                 if (m < P * (P + 1) / 2) {
@@ -358,17 +427,20 @@ __global__ void __launch_bounds__(kThreads) k_tile(const __grid_constant__ thb_s
             }
         }
         if (MODE == MODE_FUSED) {
-            for (int t = lane; t < TS; t += 32) {
-                float v[4] = {0.f, 0.f, 0.f, 0.f};
-                if (it.ndir > 0 && t < T && ((it.dm >> t) & 1ull)) {
-                    const int pos = __popcll(it.dm & ((1ull << t) - 1ull));
-                    const int64_t r = __ldg(sp.supp_jm + it.soff + pos);
 #pragma unroll
-                    for (int k = 0; k < CPD; ++k) v[k] = __ldg(ar.ctrl_pts + r * CPD + k);
+            for (int h = 0; h < 2; ++h) {
+                const int t = lane + 32 * h;
+                if (t < TS) {
+                    float v[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (wj[h] >= 0) {
+#pragma unroll
+                        for (int k = 0; k < CPD; ++k) v[k] = __ldg(ar.ctrl_pts + (int64_t)wj[h] * CPD + k);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) s_cpw[k][t] = v[k];
                 }
-#pragma unroll
-                for (int k = 0; k < 4; ++k) s_cpw[k][t] = v[k];
             }
+            if (ntile > 0 && ntile <= kMaxCC) gather_cc<CPD>(sp, ar, it, 0, ntile, s_cc);
         }
         __syncwarp();
         if (cellnet) {
@@ -377,19 +449,14 @@ __global__ void __launch_bounds__(kThreads) k_tile(const __grid_constant__ thb_s
                 const float4* src = reinterpret_cast<const float4*>(sp.tiles + (int64_t)(it.toff + c0) * TS);
                 float4* dst = reinterpret_cast<float4*>(s_tiles);
                 for (int i = lane; i < ns * NQ; i += 32) dst[i] = __ldg(src + i);
-                if (lane < ns) {
-                    const int64_t r = __ldg(sp.supp_jm + it.soff + it.ndir + c0 + lane);
-                    float v[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                    for (int k = 0; k < CPD; ++k) v[k] = __ldg(ar.ctrl_pts + r * CPD + k);
-                    s_cc[lane] = make_float4(v[0], v[1], v[2], v[3]);
-                }
+                if (ntile > kMaxCC) gather_cc<CPD>(sp, ar, it, c0, ns, s_cc);
                 __syncwarp();
+                const float4* ccp = s_cc + (ntile > kMaxCC ? 0 : c0);
                 for (int t = lane; t < TS; t += 32) {
                     float q[4] = {0.f, 0.f, 0.f, 0.f};
                     for (int s = 0; s < ns; ++s) {
                         const float w = s_tiles[s * TS + t];
-                        const float4 cc = s_cc[s];
+                        const float4 cc = ccp[s];
                         q[0] = fmaf(w, cc.x, q[0]); q[1] = fmaf(w, cc.y, q[1]);
                         q[2] = fmaf(w, cc.z, q[2]); q[3] = fmaf(w, cc.w, q[3]);
                     }
@@ -399,19 +466,41 @@ __global__ void __launch_bounds__(kThreads) k_tile(const __grid_constant__ thb_s
                 __syncwarp();
             }
         }
-        // prefetch the next item's record
-        nxt_id = __shfl_sync(0xffffffffu, nxt_id, 0);
-        Item nxt = it;
-        if (nxt_id < nitems) nxt = load_item(sp, ar.items, nxt_id);
 
-        for (int base = 0; base < it.count; base += 32 * PPT) {
-            if (PPT == 2 && it.count - base <= 32)
-                warp_points<SH, 1, CPD, MODE, DER>(sp, ar, it, base, ntile, cellnet, s_knots, s_rk, s_cpw, s_cc, s_tiles);
-            else
-                warp_points<SH, PPT, CPD, MODE, DER>(sp, ar, it, base, ntile, cellnet, s_knots, s_rk, s_cpw, s_cc, s_tiles);
+        int wjn[2] = {-1, -1};
+        for (int base = 0; base < it.count; base += SB) {
+            // prefetch the next sub-batch (same item, or the first one of the next item)
+            PtData<PPT, MODE> pn = pd;
+            const bool more = base + SB < it.count;
+            if (more) {
+                load_points<PPT, MODE>(ar, d, it.begin, it.count, base + SB, pn);
+            } else if (nx_valid) {
+                cp_async_wait<0>();
+                __syncwarp();
+                const Item nx = unpack_item(s_nx[0], s_nx[1], s_nx[2], s_nx[3]);
+                load_points<PPT, MODE>(ar, d, nx.begin, nx.count, 0, pn);
+                load_window_ids(sp, nx, T, wjn);
+            }
+            if (PPT == 2 && it.count - base <= 32) {
+                PtData<1, MODE> p1;
+                p1.idx[0] = pd.idx[0];
+                p1.u[0][0] = pd.u[0][0]; p1.u[0][1] = pd.u[0][1]; p1.u[0][2] = pd.u[0][2];
+                if (MODE == MODE_BASIS) p1.off[0] = pd.off[0];
+                warp_points<SH, 1, CPD, MODE, DER>(sp, ar, it, p1, ntile, cellnet, s_knots, s_rk, s_cpw, s_cc, s_tiles);
+            } else {
+                warp_points<SH, PPT, CPD, MODE, DER>(sp, ar, it, pd, ntile, cellnet, s_knots, s_rk, s_cpw, s_cc, s_tiles);
+            }
+            pd = pn;
         }
-        if (nxt_id >= nitems) break;
-        it = nxt;
+        if (!nx_valid) break;
+        it = unpack_item(s_nx[0], s_nx[1], s_nx[2], s_nx[3]);
+        wj[0] = wjn[0]; wj[1] = wjn[1];
+        id = __shfl_sync(0xffffffffu, nn_id, 0);
+        nx_valid = id < nitems;
+        __syncwarp();  // every lane has read s_nx
+        if (nx_valid && lane < 4) cp_async16(s_nx + lane, ar.items + (int64_t)id * 4 + lane);
+        cp_async_commit();
+        if (lane == 0) nn_id = atomicAdd(ar.counters + 1, 1);
     }
 }
 
@@ -531,6 +620,7 @@ struct ShapeOps {
 template <typename K>
 int persistent_grid(K kernel, int threads) {
     int per_sm = 0;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
     return per_sm * thb_num_sms();
 }

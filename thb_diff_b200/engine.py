@@ -44,15 +44,16 @@ class Plan:
         self.n = n
         self.slot = torch.empty(max(n, 1), **i32)
         self.perm = torch.empty(max(n, 1), **i32)
+        self.sorted_params = torch.empty((max(n, 1), P.ndim), dtype=torch.float32, device=dev)
         self.cell_count = torch.empty(P.nslots + 1, **i32)
         self.cell_start = torch.empty(P.nslots + 1, **i32)
         self.cell_cursor = torch.empty(P.nslots + 1, **i32)
         self.max_items = n // points_per_item + P.nslots + 1
-        self.items = torch.empty((self.max_items, 4), **i32)
+        self.items = torch.empty((self.max_items, 16), **i32)
         self.counters = torch.zeros(4, **i32)
         d = PlanDesc()
         d.npoints, d.points_per_item, d.max_items = n, points_per_item, self.max_items
-        d.slot, d.perm = self.slot.data_ptr(), self.perm.data_ptr()
+        d.slot, d.perm, d.sorted_params = self.slot.data_ptr(), self.perm.data_ptr(), self.sorted_params.data_ptr()
         d.cell_count, d.cell_start, d.cell_cursor = self.cell_count.data_ptr(), self.cell_start.data_ptr(), self.cell_cursor.data_ptr()
         d.items, d.counters = self.items.data_ptr(), self.counters.data_ptr()
         self.desc = d
