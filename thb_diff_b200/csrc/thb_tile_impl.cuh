@@ -190,39 +190,73 @@ THB_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memo
 template <int N>
 THB_DEV void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// Per-lane data of one sub-batch (PPT*32 points of one item, lane-major), loaded one sub-batch ahead.
-template <int PPT, int MODE>
-struct PtData {
-    int idx[PPT];          // caller-order index of the point, -1 = no point
-    float u[PPT][3];
-    int64_t off[MODE == MODE_BASIS ? PPT : 1];
+THB_DEV void cp_async4(void* smem, const void* gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem) : "memory");
+}
+
+// Per-warp shared memory.  Everything that can be known ahead of time is double buffered and filled by
+// cp.async, so the global-memory latency of item i+1 is paid while item i is being computed and costs no
+// registers.
+template <class SH>
+struct WarpSmem {
+    int4 rec[3][4];                       // ring of work-item records (lookahead 2)
+    float knots[2][3][8];                 // local knots of the item's cell, per dimension
+    float rk[3][8];                       // reciprocal knot differences of the current item
+    float cpw[2][4][SH::TS];              // own-level window control points (SoA, 0 where inactive)
+    int pidx[2][64];                      // caller-order index of the points of a sub-batch
+    float pu[2][3][64];                   // their parameters (SoA)
+    float4 cc[kMaxCC];                    // control points of the coarser-level supports
+    float tiles[2][kWChunk * SH::TS];     // coefficient tiles, streamed in chunks
 };
 
-template <int PPT, int MODE>
-THB_DEV void load_points(const Args& ar, int d, int begin, int count, int base, PtData<PPT, MODE>& pd) {
+template <int PPT>
+THB_DEV void prefetch_points(const Args& ar, int d, int begin, int count, int base, int* pidx, float (*pu)[64]) {
     const int lane = threadIdx.x;
 #pragma unroll
     for (int q = 0; q < PPT; ++q) {
         const int li = base + q * 32 + lane;
-        const bool valid = li < count;
-        const int64_t j = begin + (valid ? li : 0);
-        const int id = __ldg(ar.perm + j);
-        pd.idx[q] = valid ? id : -1;
+        const int64_t j = begin + (li < count ? li : 0);
+        cp_async4(pidx + q * 32 + lane, ar.perm + j);
 #pragma unroll
-        for (int k = 0; k < 3; ++k) pd.u[q][k] = (k < d) ? __ldg(ar.sorted + j * d + k) : 0.f;
-        if (MODE == MODE_BASIS) pd.off[q] = __ldg(ar.offsets + id);
+        for (int k = 0; k < 3; ++k)
+            if (k < d) cp_async4(&pu[k][q * 32 + lane], ar.sorted + j * d + k);
     }
 }
 
-// flat ids of the own-level window functions handled by this lane (t = lane, lane + 32), -1 if inactive
-THB_DEV void load_window_ids(const thb_space_desc& sp, const Item& it, int T, int* wj) {
+// knots and own-level window control points of an item -> shared memory buffers (cp.async + zero fill).
+// Flat id of window position t: fn_off[lev] + ravel(c + t) (the reference's numbering, THB/core.py:644-650),
+// so no index table has to be read first.
+template <class SH, int CPD>
+THB_DEV void prefetch_item_tables(const thb_space_desc& sp, const Args& ar, const Item& it, float (*knots)[8], float (*cpw)[SH::TS],
+                                  bool want_cp) {
     const int lane = threadIdx.x;
+    if (lane < 24) {
+        const int dim = lane >> 3, m = lane & 7;
+        const int P = dim == 0 ? SH::P0 : (dim == 1 ? SH::P1 : SH::P2);
+        const int c = dim == 0 ? it.c0 : (dim == 1 ? it.c1 : it.c2);
+        if (dim < sp.ndim && m < 2 * P) cp_async4(&knots[dim][m], sp.knots + sp.knot_off[it.lev][dim] + c + 1 + m);
+    }
+    if (want_cp) {
+        const int n1 = sp.nfns[it.lev][1], n2 = sp.nfns[it.lev][2];
+        const int64_t f0 = sp.fn_off[it.lev];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const int t = lane + 32 * h;
-        wj[h] = -1;
-        if (it.ndir > 0 && t < T && ((it.dm >> t) & 1ull))
-            wj[h] = __ldg(sp.supp_jm + it.soff + __popcll(it.dm & ((1ull << t) - 1ull)));
+        for (int h = 0; h < 2; ++h) {
+            const int t = lane + 32 * h;
+            if (t < SH::TS) {
+                const bool on = it.ndir > 0 && t < SH::T && ((it.dm >> t) & 1ull);
+                if (on) {
+                    const int t2 = t % SH::N2, t1 = (t / SH::N2) % SH::N1, t0 = t / (SH::N2 * SH::N1);
+                    const int64_t r = f0 + ((int64_t)(it.c0 + t0) * n1 + (it.c1 + t1)) * n2 + (it.c2 + t2);
+#pragma unroll
+                    for (int k = 0; k < CPD; ++k) cp_async4(&cpw[k][t], ar.ctrl_pts + r * CPD + k);
+                    if (CPD < 4) cpw[3][t] = 0.f;
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) cpw[k][t] = 0.f;
+                }
+            }
+        }
     }
 }
 
@@ -247,15 +281,27 @@ THB_DEV void issue_chunk(const thb_space_desc& sp, const Item& it, int c0, int n
 
 // One sub-batch of an item: PPT*32 points (lane-major), all channels.
 template <class SH, int PPT, int CPD, int MODE, bool DER>
-THB_DEV void warp_points(const thb_space_desc& sp, const Args& ar, const Item& it, const PtData<PPT, MODE>& pd, int ntile, bool cellnet,
-                         const float (*s_knots)[8], const float (*s_rk)[8], float (*s_cpw)[SH::TS], float4* s_cc, float* s_tiles) {
+THB_DEV void warp_points(const thb_space_desc& sp, const Args& ar, const Item& it, int base, int ntile, bool cellnet,
+                         WarpSmem<SH>& sm, int tb, int pb) {
     constexpr int T = SH::T, TS = SH::TS, NP = SH::NP, NQ = SH::NQ;
+    const int lane = threadIdx.x;
     const bool use_direct = (it.ndir > 0) || (MODE == MODE_FUSED && cellnet);
     const bool tile_loop = !(MODE == MODE_FUSED && cellnet) && ntile > 0;
     const bool cc_all = ntile <= kMaxCC;
+    if (tile_loop) issue_chunk<NQ>(sp, it, 0, min(kWChunk, ntile), TS, sm.tiles[0]);  // overlaps the basis evaluation below
+
+    int idx[PPT];
+    bool valid[PPT];
+    int64_t off[PPT];
     BasesRK<SH, DER> bs[PPT];
 #pragma unroll
-    for (int q = 0; q < PPT; ++q) bs[q].eval(pd.u[q], s_knots, s_rk);
+    for (int q = 0; q < PPT; ++q) {
+        valid[q] = base + q * 32 + lane < it.count;
+        idx[q] = sm.pidx[pb][q * 32 + lane];
+        if (MODE == MODE_BASIS) off[q] = __ldg(ar.offsets + idx[q]);
+        const float u[3] = {sm.pu[pb][0][q * 32 + lane], sm.pu[pb][1][q * 32 + lane], SH::N2 > 1 ? sm.pu[pb][2][q * 32 + lane] : 0.f};
+        bs[q].eval(u, sm.knots[tb], sm.rk);
+    }
     for (int chi = 0; chi < ar.nch; ++chi) {
         const int ch = ar.channels[chi];
         f32x2 tp2[PPT][NP];
@@ -264,8 +310,8 @@ THB_DEV void warp_points(const thb_space_desc& sp, const Args& ar, const Item& i
             float tp[TS];
             bs[q].tensor(ch, tp);
             if (MODE == MODE_BASIS) {
-                if (it.ndir > 0 && pd.idx[q] >= 0) {
-                    float* dst = ar.out[chi] + pd.off[q];
+                if (it.ndir > 0 && valid[q]) {
+                    float* dst = ar.out[chi] + off[q];
                     int pos = 0;
 #pragma unroll
                     for (int t = 0; t < T; ++t) {
@@ -288,7 +334,7 @@ THB_DEV void warp_points(const thb_space_desc& sp, const Args& ar, const Item& i
                 f32x2 a[PPT][2];
 #pragma unroll
                 for (int q = 0; q < PPT; ++q) a[q][0] = a[q][1] = 0ull;
-                const ulonglong2* col = reinterpret_cast<const ulonglong2*>(s_cpw[k]);
+                const ulonglong2* col = reinterpret_cast<const ulonglong2*>(sm.cpw[tb][k]);
 #pragma unroll
                 for (int m = 0; m < NQ; ++m) {
                     const ulonglong2 cv = col[m];
@@ -304,25 +350,24 @@ THB_DEV void warp_points(const thb_space_desc& sp, const Args& ar, const Item& i
         }
         if (tile_loop) {
             // tiles stream through two shared-memory buffers: cp.async of chunk c+1 overlaps the FMAs of chunk c
-            __syncwarp();
-            issue_chunk<NQ>(sp, it, 0, min(kWChunk, ntile), TS, s_tiles);
+            if (chi > 0) issue_chunk<NQ>(sp, it, 0, min(kWChunk, ntile), TS, sm.tiles[0]);
             int buf = 0;
             for (int c0 = 0; c0 < ntile; c0 += kWChunk) {
                 const int ns = min(kWChunk, ntile - c0);
                 const int c1 = c0 + kWChunk;
                 if (c1 < ntile) {
-                    issue_chunk<NQ>(sp, it, c1, min(kWChunk, ntile - c1), TS, s_tiles + (buf ^ 1) * (kWChunk * TS));
+                    issue_chunk<NQ>(sp, it, c1, min(kWChunk, ntile - c1), TS, sm.tiles[buf ^ 1]);
                     cp_async_wait<1>();
                 } else {
                     cp_async_wait<0>();
                 }
-                if (MODE == MODE_FUSED && !cc_all) gather_cc<CPD>(sp, ar, it, c0, ns, s_cc);
+                if (MODE == MODE_FUSED && !cc_all) gather_cc<CPD>(sp, ar, it, c0, ns, sm.cc);
                 __syncwarp();
-                const float* tb = s_tiles + buf * (kWChunk * TS);
-                const float4* ccp = s_cc + (cc_all ? c0 : 0);
+                const float* tbuf = sm.tiles[buf];
+                const float4* ccp = sm.cc + (cc_all ? c0 : 0);
 #pragma unroll 2
                 for (int s = 0; s < ns; ++s) {
-                    const ulonglong2* row = reinterpret_cast<const ulonglong2*>(tb + s * TS);
+                    const ulonglong2* row = reinterpret_cast<const ulonglong2*>(tbuf + s * TS);
                     f32x2 a[PPT][2];
 #pragma unroll
                     for (int q = 0; q < PPT; ++q) a[q][0] = a[q][1] = 0ull;
@@ -349,7 +394,7 @@ THB_DEV void warp_points(const thb_space_desc& sp, const Args& ar, const Item& i
 #pragma unroll
                         for (int q = 0; q < PPT; ++q) {
                             const float phi = hsum2(a[q][0]) + hsum2(a[q][1]);
-                            if (pd.idx[q] >= 0) ar.out[chi][pd.off[q] + it.ndir + c0 + s] = phi;
+                            if (valid[q]) ar.out[chi][off[q] + it.ndir + c0 + s] = phi;
                         }
                     }
                 }
@@ -360,8 +405,8 @@ THB_DEV void warp_points(const thb_space_desc& sp, const Args& ar, const Item& i
         if (MODE == MODE_FUSED) {
 #pragma unroll
             for (int q = 0; q < PPT; ++q) {
-                if (pd.idx[q] >= 0) {
-                    float* o = ar.out[chi] + (int64_t)pd.idx[q] * CPD;
+                if (valid[q]) {
+                    float* o = ar.out[chi] + (int64_t)idx[q] * CPD;
 #pragma unroll
                     for (int k = 0; k < CPD; ++k) o[k] = acc[q][k];
                 }
@@ -371,134 +416,109 @@ THB_DEV void warp_points(const thb_space_desc& sp, const Args& ar, const Item& i
 }
 
 // Persistent, warp-autonomous kernel: every CTA is ONE warp that pulls work items from an atomic cursor.
-// No CTA-wide barrier exists.  A three-deep software pipeline hides the global-memory latency chain:
-// while item i is computed, the record of item i+1 is already in registers, the id of item i+2 is being
-// claimed, and the point data (cell-sorted params, output index) of the next sub-batch is in flight.
+// No CTA-wide barrier exists.  Software pipeline: while item i is computed, the records of items i+1 and
+// i+2 are (being) fetched, the id of item i+3 is being claimed, and the points of the next sub-batch plus
+// the knots / window control points of item i+1 stream into the other half of the shared-memory buffers.
 template <int N0, int N1, int N2, int PPT, int CPD, int MODE, bool DER>
 __global__ void __launch_bounds__(kThreads) k_tile(const __grid_constant__ thb_space_desc sp, const __grid_constant__ Args ar) {
     using SH = Shp<N0, N1, N2>;
-    constexpr int T = SH::T, TS = SH::TS, NQ = SH::NQ;
+    constexpr int TS = SH::TS, NQ = SH::NQ;
     constexpr int SB = 32 * PPT;
-    __shared__ float s_knots[3][8];
-    __shared__ float s_rk[3][8];
-    __shared__ __align__(16) float s_cpw[4][TS];
-    __shared__ __align__(16) float4 s_cc[kMaxCC];
-    __shared__ __align__(16) float s_tiles[2 * kWChunk * TS];
+    __shared__ __align__(16) WarpSmem<SH> sm;
 
     const int lane = threadIdx.x;
     const int nitems = ar.counters[0];
     const int d = sp.ndim;
     const bool cellnet = (MODE == MODE_FUSED) && ar.cellnet;
+    const bool want_cp = (MODE == MODE_FUSED);
 
-    __shared__ __align__(16) int4 s_nx[4];  // record of the next item (filled by cp.async)
-    int id = 0;
-    if (lane == 0) id = atomicAdd(ar.counters + 1, 1);
-    id = __shfl_sync(0xffffffffu, id, 0);
-    if (id >= nitems) return;
-    Item it = load_item(sp, ar.items, id);
-    if (lane == 0) id = atomicAdd(ar.counters + 1, 1);
-    id = __shfl_sync(0xffffffffu, id, 0);
-    bool nx_valid = id < nitems;
-    if (nx_valid && lane < 4) cp_async16(s_nx + lane, ar.items + (int64_t)id * 4 + lane);
+    // claim three items up front (ids are increasing); id3 is claimed asynchronously
+    int c3 = 0;
+    if (lane == 0) c3 = atomicAdd(ar.counters + 1, 3);
+    const int id0 = __shfl_sync(0xffffffffu, c3, 0);
+    if (id0 >= nitems) return;
+    int id1 = id0 + 1, id2 = id0 + 2;
+    Item it = load_item(sp, ar.items, id0);
+    if (lane < 4 && id1 < nitems) cp_async16(&sm.rec[1][lane], ar.items + (int64_t)id1 * 4 + lane);
+    if (lane < 4 && id2 < nitems) cp_async16(&sm.rec[2][lane], ar.items + (int64_t)id2 * 4 + lane);
+    prefetch_item_tables<SH, CPD>(sp, ar, it, sm.knots[0], sm.cpw[0], want_cp);
+    prefetch_points<PPT>(ar, d, it.begin, it.count, 0, sm.pidx[0], sm.pu[0]);
     cp_async_commit();
     int nn_id = 0;
     if (lane == 0) nn_id = atomicAdd(ar.counters + 1, 1);
-
-    PtData<PPT, MODE> pd;
-    load_points<PPT, MODE>(ar, d, it.begin, it.count, 0, pd);
-    int wj[2];
-    load_window_ids(sp, it, T, wj);
+    int ring = 0, tb = 0, pb = 0;
+    cp_async_wait<0>();
+    __syncwarp();
 
     for (;;) {
         const int ntile = it.S - it.ndir;
-        __syncwarp();  // readers of the previous item's shared tables are done
+        // reciprocal knot differences of this cell (from the staged knots)
         if (lane < 24) {
             const int dim = lane >> 3, m = lane & 7;
             const int P = dim == 0 ? SH::P0 : (dim == 1 ? SH::P1 : SH::P2);
-            const int c = dim == 0 ? it.c0 : (dim == 1 ? it.c1 : it.c2);
-            if (dim < d) {
-                const float* U = sp.knots + sp.knot_off[it.lev][dim] + c + 1;  // K[m] = U[m]
-                if (m < 2 * P) s_knots[dim][m] = __ldg(U + m);
-                if (m < P * (P + 1) / 2) {
-                    int j = 1, r = m;
-                    while (r >= j) { r -= j; ++j; }
-                    s_rk[dim][m] = 1.0f / (__ldg(U + P + r) - __ldg(U + P - j + r));
-                }
+            if (dim < d && m < P * (P + 1) / 2) {
+                int j = 1, r = m;
+                while (r >= j) { r -= j; ++j; }
+                sm.rk[dim][m] = 1.0f / (sm.knots[tb][dim][P + r] - sm.knots[tb][dim][P - j + r]);
             }
         }
-        if (MODE == MODE_FUSED) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int t = lane + 32 * h;
-                if (t < TS) {
-                    float v[4] = {0.f, 0.f, 0.f, 0.f};
-                    if (wj[h] >= 0) {
-#pragma unroll
-                        for (int k = 0; k < CPD; ++k) v[k] = __ldg(ar.ctrl_pts + (int64_t)wj[h] * CPD + k);
-                    }
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) s_cpw[k][t] = v[k];
-                }
-            }
-            if (ntile > 0 && ntile <= kMaxCC) gather_cc<CPD>(sp, ar, it, 0, ntile, s_cc);
-        }
+        if (MODE == MODE_FUSED && ntile > 0 && ntile <= kMaxCC) gather_cc<CPD>(sp, ar, it, 0, ntile, sm.cc);
         __syncwarp();
         if (cellnet) {
             for (int c0 = 0; c0 < ntile; c0 += kWChunk) {
                 const int ns = min(kWChunk, ntile - c0);
                 const float4* src = reinterpret_cast<const float4*>(sp.tiles + (int64_t)(it.toff + c0) * TS);
-                float4* dst = reinterpret_cast<float4*>(s_tiles);
+                float4* dst = reinterpret_cast<float4*>(sm.tiles[0]);
                 for (int i = lane; i < ns * NQ; i += 32) dst[i] = __ldg(src + i);
-                if (ntile > kMaxCC) gather_cc<CPD>(sp, ar, it, c0, ns, s_cc);
+                if (ntile > kMaxCC) gather_cc<CPD>(sp, ar, it, c0, ns, sm.cc);
                 __syncwarp();
-                const float4* ccp = s_cc + (ntile > kMaxCC ? 0 : c0);
+                const float4* ccp = sm.cc + (ntile > kMaxCC ? 0 : c0);
                 for (int t = lane; t < TS; t += 32) {
                     float q[4] = {0.f, 0.f, 0.f, 0.f};
                     for (int s = 0; s < ns; ++s) {
-                        const float w = s_tiles[s * TS + t];
+                        const float w = sm.tiles[0][s * TS + t];
                         const float4 cc = ccp[s];
                         q[0] = fmaf(w, cc.x, q[0]); q[1] = fmaf(w, cc.y, q[1]);
                         q[2] = fmaf(w, cc.z, q[2]); q[3] = fmaf(w, cc.w, q[3]);
                     }
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) s_cpw[k][t] += q[k];
+                    for (int k = 0; k < 4; ++k) sm.cpw[tb][k][t] += q[k];
                 }
                 __syncwarp();
             }
         }
-
-        int wjn[2] = {-1, -1};
+        const bool nx_valid = id1 < nitems;
         for (int base = 0; base < it.count; base += SB) {
-            // prefetch the next sub-batch (same item, or the first one of the next item)
-            PtData<PPT, MODE> pn = pd;
-            const bool more = base + SB < it.count;
-            if (more) {
-                load_points<PPT, MODE>(ar, d, it.begin, it.count, base + SB, pn);
+            // prefetch the next sub-batch: same item, or the first one of the next item together with its tables
+            if (base + SB < it.count) {
+                prefetch_points<PPT>(ar, d, it.begin, it.count, base + SB, sm.pidx[pb ^ 1], sm.pu[pb ^ 1]);
             } else if (nx_valid) {
-                cp_async_wait<0>();
-                __syncwarp();
-                const Item nx = unpack_item(s_nx[0], s_nx[1], s_nx[2], s_nx[3]);
-                load_points<PPT, MODE>(ar, d, nx.begin, nx.count, 0, pn);
-                load_window_ids(sp, nx, T, wjn);
+                const int4* r = sm.rec[(ring + 1) % 3];
+                const Item nx = unpack_item(r[0], r[1], r[2], r[3]);
+                prefetch_points<PPT>(ar, d, nx.begin, nx.count, 0, sm.pidx[pb ^ 1], sm.pu[pb ^ 1]);
+                prefetch_item_tables<SH, CPD>(sp, ar, nx, sm.knots[tb ^ 1], sm.cpw[tb ^ 1], want_cp);
             }
-            if (PPT == 2 && it.count - base <= 32) {
-                PtData<1, MODE> p1;
-                p1.idx[0] = pd.idx[0];
-                p1.u[0][0] = pd.u[0][0]; p1.u[0][1] = pd.u[0][1]; p1.u[0][2] = pd.u[0][2];
-                if (MODE == MODE_BASIS) p1.off[0] = pd.off[0];
-                warp_points<SH, 1, CPD, MODE, DER>(sp, ar, it, p1, ntile, cellnet, s_knots, s_rk, s_cpw, s_cc, s_tiles);
-            } else {
-                warp_points<SH, PPT, CPD, MODE, DER>(sp, ar, it, pd, ntile, cellnet, s_knots, s_rk, s_cpw, s_cc, s_tiles);
-            }
-            pd = pn;
+            cp_async_commit();
+            if (PPT == 2 && it.count - base <= 32)
+                warp_points<SH, 1, CPD, MODE, DER>(sp, ar, it, base, ntile, cellnet, sm, tb, pb);
+            else
+                warp_points<SH, PPT, CPD, MODE, DER>(sp, ar, it, base, ntile, cellnet, sm, tb, pb);
+            cp_async_wait<0>();
+            __syncwarp();
+            pb ^= 1;
         }
         if (!nx_valid) break;
-        it = unpack_item(s_nx[0], s_nx[1], s_nx[2], s_nx[3]);
-        wj[0] = wjn[0]; wj[1] = wjn[1];
-        id = __shfl_sync(0xffffffffu, nn_id, 0);
-        nx_valid = id < nitems;
-        __syncwarp();  // every lane has read s_nx
-        if (nx_valid && lane < 4) cp_async16(s_nx + lane, ar.items + (int64_t)id * 4 + lane);
+        // advance: item i+1 becomes current; fetch the record of item i+3 into the slot item i used
+        ring = (ring + 1) % 3;
+        {
+            const int4* r = sm.rec[ring];
+            it = unpack_item(r[0], r[1], r[2], r[3]);
+        }
+        tb ^= 1;
+        const int id3 = __shfl_sync(0xffffffffu, nn_id, 0);
+        id1 = id2;
+        id2 = id3;
+        if (lane < 4 && id3 < nitems) cp_async16(&sm.rec[(ring + 2) % 3][lane], ar.items + (int64_t)id3 * 4 + lane);
         cp_async_commit();
         if (lane == 0) nn_id = atomicAdd(ar.counters + 1, 1);
     }
