@@ -79,63 +79,61 @@ __global__ void __launch_bounds__(256) k_expand_supports(const __grid_constant__
 // Finest-level span with the knots of that level staged in shared memory.  First guess from a uniform
 // partition, corrected by walking (exact for 'uniform-ish' knots in <= 2 steps), binary search otherwise;
 // the result is the same span as span_right() for every in-domain u.
-THB_DEV int finest_cell(const float* __restrict__ U, int nk, int p, int nc, float u) {
+// `scale` = nc / (U[p+nc] - U[p]).
+THB_DEV int finest_cell(const float* __restrict__ U, int p, int nc, float scale, float u) {
     // U[p .. p+nc] are the breakpoints; cell c <=> U[p+c] <= u < U[p+c+1]
     const float u0 = U[p], u1 = U[p + nc];
     if (!(u >= u0) || u > u1) return -1;  // also rejects NaN
-    if (u == u1) return nc - 1;           // reference rule: u == U[-1] belongs to the last span
-    int c = (int)((u - u0) / (u1 - u0) * (float)nc);
+    int c = min((int)((u - u0) * scale), nc - 1);
+    // branch-free +-1 correction (covers knots jittered by less than one cell), then verify
+    c += (int)(u >= U[p + c + 1]) - (int)(u < U[p + c]);
     c = min(max(c, 0), nc - 1);
-    int steps = 0;
-    while (steps < 3 && u < U[p + c]) { --c; ++steps; }
-    while (steps < 3 && u >= U[p + c + 1]) { ++c; ++steps; }
-    if (steps >= 3) {  // far from uniform: binary search on the breakpoints
-        int lo = 0, hi = nc;  // invariant: U[p+lo] <= u < U[p+hi]
+    if (u < U[p + c] || (u >= U[p + c + 1] && c < nc - 1)) {  // far from uniform: binary search on the breakpoints
+        int lo = 0, hi = nc;  // invariant: U[p+lo] <= u < U[p+hi]  (u == u1 ends in the last cell)
         while (hi - lo > 1) {
             const int mid = (lo + hi) >> 1;
             if (U[p + mid] <= u) lo = mid; else hi = mid;
         }
         c = lo;
     }
-    return c;
+    return c;  // u == U[-1] lands in nc-1: the reference rule for the last knot
 }
 
 constexpr int kPlanSmemKnots = 3 * 1024;
 
 // slot of a point given the finest-level knots in shared memory; the cell_slot entries of ALL levels are
 // fetched at once (independent loads) and the finest active one is selected.
-THB_DEV int locate_slot_fast(const thb_space_desc& sp, const float* const* Uk, const float* u) {
+THB_DEV int locate_slot_fast(const thb_space_desc& sp, const float* const* Uk, const float* scale, const float* u) {
     const int L = sp.nlevels - 1;
     int cf[3] = {0, 0, 0};
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         if (k < sp.ndim) {
-            const int c = finest_cell(Uk[k], sp.knot_len[L][k], sp.degree[k], sp.ncells[L][k], u[k]);
+            const int c = finest_cell(Uk[k], sp.degree[k], sp.ncells[L][k], scale[k], u[k]);
             if (c < 0) return -1;
             cf[k] = c;
         }
     }
-    int cand[THB_MAX_LEVELS];
-#pragma unroll
-    for (int lev = 0; lev < THB_MAX_LEVELS; ++lev) {
-        cand[lev] = -1;
-        if (lev <= L) {
-            const int sh = L - lev;
-            int64_t lin = cf[0] >> sh;
-            lin = lin * sp.ncells[lev][1] + (cf[1] >> sh);
-            if (sp.ndim == 3) lin = lin * sp.ncells[lev][2] + (cf[2] >> sh);
-            cand[lev] = __ldg(sp.cell_slot + sp.cell_slot_off[lev] + lin);
-        }
-    }
+    // independent lookups at every level (issued back to back), finest active one wins
     int slot = -1;
-#pragma unroll
-    for (int lev = 0; lev < THB_MAX_LEVELS; ++lev)
-        if (cand[lev] >= 0) slot = cand[lev];  // later (finer) levels override
+#pragma unroll 4
+    for (int lev = 0; lev <= L; ++lev) {
+        const int sh = L - lev;
+        int lin = (cf[0] >> sh) * sp.ncells[lev][1] + (cf[1] >> sh);
+        if (sp.ndim == 3) lin = lin * sp.ncells[lev][2] + (cf[2] >> sh);
+        const int cand = __ldg(sp.cell_slot + sp.cell_slot_off[lev] + lin);
+        if (cand >= 0) slot = cand;
+    }
     return slot;
 }
 
-THB_DEV bool stage_finest_knots(const thb_space_desc& sp, float* sk, const float** Uk) {
+THB_DEV bool stage_finest_knots(const thb_space_desc& sp, float* sk, const float** Uk, float* scale) {
     const int L = sp.nlevels - 1;
+    for (int k = 0; k < sp.ndim; ++k) {
+        const float* g = sp.knots + sp.knot_off[L][k];
+        const int p = sp.degree[k], nc = sp.ncells[L][k];
+        scale[k] = (float)nc / (g[p + nc] - g[p]);
+    }
     int tot = 0;
     for (int k = 0; k < sp.ndim; ++k) tot += sp.knot_len[L][k];
     const bool fits = tot <= kPlanSmemKnots;
@@ -160,16 +158,20 @@ __global__ void __launch_bounds__(256) k_plan_count(const __grid_constant__ thb_
                                                     int64_t n, int32_t* __restrict__ slot_out, int32_t* __restrict__ count) {
     __shared__ float sk[kPlanSmemKnots];
     const float* Uk[3] = {nullptr, nullptr, nullptr};
-    stage_finest_knots(sp, sk, Uk);
+    float scale[3] = {0.f, 0.f, 0.f};
+    stage_finest_knots(sp, sk, Uk, scale);
     const int lane = threadIdx.x & 31;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t nround = (n + stride - 1) / stride * stride;  // keep whole warps in the loop for match_any
+    const int d = sp.ndim;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
         int slot = -1;
         if (i < n) {
-            float u[3] = {0.f, 0.f, 0.f};
-            for (int k = 0; k < sp.ndim; ++k) u[k] = params[i * sp.ndim + k];
-            slot = locate_slot_fast(sp, Uk, u);
+            float u[3];
+            u[0] = params[i * d];
+            u[1] = params[i * d + 1];
+            u[2] = d == 3 ? params[i * d + 2] : 0.f;
+            slot = locate_slot_fast(sp, Uk, scale, u);
             slot_out[i] = slot;
         }
         const unsigned peers = __match_any_sync(0xffffffffu, slot);
@@ -179,38 +181,57 @@ __global__ void __launch_bounds__(256) k_plan_count(const __grid_constant__ thb_
 
 // pass 2 (single CTA): exclusive scan of the histogram -> cell_start; number of work items per cell and
 // their exclusive scan -> cell_cursor is reused to hold the first item index of each cell.
+// 4096 slots per round: int4 loads, warp-shuffle scans, two barriers per round.
 __global__ void __launch_bounds__(1024) k_plan_scan(const int32_t* __restrict__ count, int32_t* __restrict__ start,
                                                     int32_t* __restrict__ item_start, int nslots, int ppi,
                                                     int32_t* __restrict__ counters) {
-    __shared__ int s_pts[1024];
-    __shared__ int s_itm[1024];
+    __shared__ int s_wp[32], s_wi[32];
     __shared__ int s_carry[2];
-    const int t = threadIdx.x;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
     if (t == 0) s_carry[0] = s_carry[1] = 0;
     __syncthreads();
-    // tiles of 1024 consecutive slots: coalesced loads, Hillis-Steele scan in shared memory, running carry
-    for (int base = 0; base < nslots; base += 1024) {
-        const int i = base + t;
-        const int c = i < nslots ? count[i] : 0;
-        const int m = (c + ppi - 1) / ppi;
-        s_pts[t] = c;
-        s_itm[t] = m;
-        __syncthreads();
-        for (int o = 1; o < 1024; o <<= 1) {
-            int vp = 0, vi = 0;
-            if (t >= o) { vp = s_pts[t - o]; vi = s_itm[t - o]; }
-            __syncthreads();
-            s_pts[t] += vp;
-            s_itm[t] += vi;
-            __syncthreads();
+    for (int base = 0; base < nslots; base += 4096) {
+        const int i0 = base + 4 * t;
+        int c[4], m[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            c[k] = (i0 + k < nslots) ? count[i0 + k] : 0;
+            m[k] = (c[k] + ppi - 1) / ppi;
         }
-        const int cp = s_carry[0], ci = s_carry[1];
-        if (i < nslots) {
-            start[i] = cp + s_pts[t] - c;
-            item_start[i] = ci + s_itm[t] - m;
+        const int tp = c[0] + c[1] + c[2] + c[3], ti = m[0] + m[1] + m[2] + m[3];
+        int sp_ = tp, si_ = ti;  // inclusive warp scan of the per-thread totals
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int a = __shfl_up_sync(0xffffffffu, sp_, o), b2 = __shfl_up_sync(0xffffffffu, si_, o);
+            if (lane >= o) { sp_ += a; si_ += b2; }
+        }
+        if (lane == 31) { s_wp[w] = sp_; s_wi[w] = si_; }
+        __syncthreads();
+        if (w == 0) {
+            int a = s_wp[lane], b2 = s_wi[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int x = __shfl_up_sync(0xffffffffu, a, o), y = __shfl_up_sync(0xffffffffu, b2, o);
+                if (lane >= o) { a += x; b2 += y; }
+            }
+            s_wp[lane] = a;
+            s_wi[lane] = b2;
         }
         __syncthreads();
-        if (t == 1023) { s_carry[0] = cp + s_pts[1023]; s_carry[1] = ci + s_itm[1023]; }
+        const int cp = s_carry[0] + (w ? s_wp[w - 1] : 0) + sp_ - tp;
+        const int ci = s_carry[1] + (w ? s_wi[w - 1] : 0) + si_ - ti;
+        int rp = cp, ri = ci;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (i0 + k < nslots) {
+                start[i0 + k] = rp;
+                item_start[i0 + k] = ri;
+            }
+            rp += c[k];
+            ri += m[k];
+        }
+        __syncthreads();
+        if (t == 1023) { s_carry[0] = rp; s_carry[1] = ri; }
         __syncthreads();
     }
     if (t == 0) {
