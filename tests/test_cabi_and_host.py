@@ -1,0 +1,91 @@
+"""CPU-only checks of the product's host side: the C-ABI library loads and exports every symbol the
+header declares (no compute calls), descriptor structs match the header layout, host set-up code."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from thb_diff_b200 import _lib
+
+    hdr = open(os.path.join(ROOT, "include", "thb_b200.h")).read()
+    declared = set(re.findall(r"THB_API\s+[\w\s\*]+?\b(thb_\w+)\s*\(", hdr))
+    assert len(declared) >= 15
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in thb_b200.h but not exported"
+    assert declared == set(_lib.EXPORTS), "ctypes binding and header disagree"
+    assert _lib.lib.thb_version() == 100
+    assert _lib.launch_count() == 0  # nothing was launched by loading
+
+
+def test_descriptor_layout_matches_header():
+    from thb_diff_b200 import _lib
+
+    # thb_space_desc: 8 ints, 4 x [8][3] ints, 9 + 8 int64, 6 pointers
+    assert ctypes.sizeof(_lib.SpaceDesc) == 8 * 4 + 4 * 8 * 3 * 4 + (9 + 8) * 8 + 6 * 8
+    assert _lib.SpaceDesc.knots.offset == 8 * 4 + 4 * 96 + 17 * 8
+    assert ctypes.sizeof(_lib.PlanDesc) == 8 + 4 + 4 + 8 * 8
+
+
+def test_no_cpu_fallback():
+    import torch
+
+    from thb_diff_b200 import THB_eval, engine
+
+    cp = torch.zeros((4, 3))
+    with pytest.raises(RuntimeError):
+        engine.eval_forward(cp, torch.zeros(1, dtype=torch.int64), torch.zeros(1), torch.ones(1, dtype=torch.int64))
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            THB_eval.cpp_forward(cp, torch.zeros(1, dtype=torch.int64), torch.zeros(1), torch.ones(1, dtype=torch.int64))
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "thb_diff_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.replace("CPU oracle", "").lower() or f == "distributed.py", f
+
+
+def test_host_setup_helpers():
+    from thb_diff_b200 import bspline_funcs as B
+    from thb_diff_b200 import multilevel_spline_space as M
+    from oracle import thb_oracle as O
+
+    U = np.array([0, 0, 0, 0, 0.2, 0.4, 0.5, 0.6, 0.8, 0.9, 1, 1, 1, 1.0])
+    V = M.refine_knotvector(U, 3)
+    assert np.array_equal(V, O.refine_knotvector(U, 3))
+    assert np.allclose(M.assemble_Tmatrix(U, V, len(U), len(V), 3), O.knot_insertion_matrix(U, V, 3), atol=1e-15)
+    assert np.array_equal(B.generate_parametric_coordinates((3, 4, 5)), O.generate_parametric_coordinates((3, 4, 5)))
+    g = B.grevilleAbscissae((10, 10), (3, 3), (U, U))
+    assert np.allclose(g, O.greville_abscissae((10, 10), (3, 3), (U, U)))
+    # device grid generator == numpy generator rounded to f32 (run on CPU here)
+    dev = B.grid_parametric_coordinates_device((3, 4, 5), device="cpu")
+    assert np.array_equal(dev.numpy(), O.generate_parametric_coordinates((3, 4, 5)).astype(np.float32))
+    a = B.grid_parametric_coordinates_device((3, 8, 5), device="cpu", y_first=1, y_step=2)
+    full = O.generate_parametric_coordinates((3, 8, 5)).astype(np.float32).reshape(8, 3, 5, 3)
+    assert np.array_equal(a.numpy(), full[1::2].reshape(-1, 3))
+
+
+def test_active_supports_dict_view_matches_reference_order():
+    from helpers import load_golden, product_space_from_golden
+    from oracle import thb_oracle as O
+    from thb_diff_b200 import core
+
+    g = load_golden("block2d")
+    h = product_space_from_golden(g)
+    ac = core.compute_active_cells_active_supp(h.cells, h.fns, h.degrees)
+    ref = O.compute_active_cells_active_supp(h.cells, h.fns, h.degrees)
+    assert sorted(ac.keys()) == sorted(ref.keys())
+    for lev in ref:
+        assert len(ac[lev]) == len(ref[lev])
+        for cell in list(ref[lev])[:20]:
+            assert ac[lev][cell] == ref[lev][cell]
