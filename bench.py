@@ -120,6 +120,69 @@ def cpu_port_rate(P, params_host, cp_host, target_s=12.0):
     return len(sample) / dt, c_oracle.num_threads(), len(sample)
 
 
+def time_cuda(fn, iters=5, warm=2):
+    import torch
+
+    for _ in range(warm):
+        fn()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+def extras(sp, P, params, cp, hbm_peak):
+    """Secondary measurements on the same workload (N=1 only): the API-faithful path with PHI materialised
+    (compute_active_span + THB_basis_fns, then THB_eval.forward / backward on the CSR) next to the REFERENCE'S
+    OWN CUDA KERNELS (oracle/_ref/cuda = compute_pts_cuda_kernels.cu compiled unmodified for sm_100a) on the
+    same tensors, and the fused backward."""
+    import torch
+
+    from oracle import build_ref
+    from thb_diff_b200 import core, engine
+
+    n = params.shape[0]
+    out = {}
+    supp, ns = core.compute_active_span(params, sp.knotvectors, sp.cells, sp.degrees, P)
+    off, nnz = supp.offsets()
+    t_basis = time_cuda(lambda: engine.basis_tiled(P, supp.plan, off, nnz), iters=3, warm=1)
+    PHI = engine.basis_tiled(P, supp.plan, off, nnz)[0]
+    out["THB_basis_fns"] = {"ms": t_basis, "points_per_s": n / (t_basis * 1e-3), "nnz": nnz,
+                            "hbm_frac": ((nnz * 4 + n * 24) / (t_basis * 1e-3) / 1e9) / hbm_peak}
+    cumsum = supp._cumsum
+    g = torch.randn((n, 3), device=params.device)
+    for name, dt in (("int64", torch.int64), ("int32", torch.int32)):
+        Jm = supp.Jm(dt)
+        cs = cumsum.to(dt) if dt == torch.int64 or nnz < 2 ** 31 else cumsum
+        isz = 8 if dt == torch.int64 else 4
+        tf = time_cuda(lambda: engine.eval_forward(cp, Jm, PHI, cs))
+        tb = time_cuda(lambda: engine.eval_backward(g, cp, Jm, PHI, cs))
+        out[f"THB_eval_{name}"] = {
+            "forward_ms": tf, "backward_ms": tb, "forward_points_per_s": n / (tf * 1e-3), "backward_points_per_s": n / (tb * 1e-3),
+            "forward_hbm_frac": ((nnz * (4 + isz) + n * (isz + 12)) / (tf * 1e-3) / 1e9) / hbm_peak,
+            "backward_hbm_frac": ((nnz * (4 + isz) + n * (isz + 12)) / (tb * 1e-3) / 1e9) / hbm_peak}
+        if dt == torch.int64:
+            ref = build_ref.load_cuda()
+            if ref is not None:
+                o_ref = ref.forward(cp, Jm, PHI, cs)
+                o_our = engine.eval_forward(cp, Jm, PHI, cs)
+                rf = time_cuda(lambda: ref.forward(cp, Jm, PHI, cs), iters=3, warm=1)
+                rb = time_cuda(lambda: ref.backward(g, cp, Jm, PHI, cs), iters=3, warm=1)
+                out["reference_cuda_kernels_sm100a"] = {
+                    "forward_ms": rf, "backward_ms": rb, "max_abs_diff_forward": float((o_ref - o_our).abs().max()),
+                    "speedup_forward": rf / tf, "speedup_backward": rb / tb,
+                    "what": "THB/THB_extensions/compute_pts_cuda_kernels.cu compiled unmodified (oracle/_ref/cuda), same tensors"}
+                del o_ref, o_our
+        del Jm
+    tfb = time_cuda(lambda: engine.eval_fused_backward(P, supp.plan, g))
+    out["fused_backward"] = {"ms": tfb, "points_per_s": n / (tfb * 1e-3)}
+    return out
+
+
 def run_reference(args, rank, world):
     """Reference arm: the reference's CPU path on the host cores, on a bounded sample of the same workload.
     The reference's Python basis code cannot hold this space (its dense tables would need ~1e11 entries), so
@@ -188,6 +251,7 @@ def main():
     ap.add_argument("--cellnet", action="store_true", help="fold tiles into per-cell control nets (fewest FLOPs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-variants", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -232,18 +296,19 @@ def main():
 
     fp32_peak = max(engine.fma_peak(0), engine.fma_peak(1))  # TFLOP/s, measured on this GPU now
 
+    clk = ClockSampler(local)
+    clk.__enter__()  # samples through warm-up, the timed region and the e2e region (the timed region alone lasts ~ms)
     for _ in range(max(args.warmup, 3)):
         step()
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     barrier()
     launches0 = _lib.launch_count()
-    with ClockSampler(local) as clk:
-        t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t_beg.record()
-        for k in range(args.steps):
-            step(ev[k])
-        t_end.record()
-        barrier()
+    t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_beg.record()
+    for k in range(args.steps):
+        step(ev[k])
+    t_end.record()
+    barrier()
     launches = _lib.launch_count() - launches0
     total_ms = t_beg.elapsed_time(t_end)
     plan_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
@@ -280,6 +345,10 @@ def main():
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_value = n * world / (float(e2e_ms.item()) * 1e-3)
+    for _ in range(200):  # keep the GPU busy long enough for a few more clock samples
+        step()
+    torch.cuda.synchronize()
+    clk.__exit__()
 
     # ---- roofline of the dominant kernel (fused tile kernel), from the live CUDA-event timing above
     peaks = {}
@@ -299,11 +368,16 @@ def main():
     t_hbm = alg_bytes / (hbm_peak * 1e9)
     t_roof = max(t_fp32, t_hbm)
     bound = "fp32" if t_fp32 >= t_hbm else "hbm"
+    traffic = None
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu capture of this kernel
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["k_tile_fused_c3_bytes"]
+    except Exception:
+        pass
     roofline = {
         "bound": bound, "kernel": "thb_tile::k_tile<4,4,4,PPT,3,FUSED>",
         "achieved": (f_exec / (kern_ms * 1e-3) / 1e12) if bound == "fp32" else (alg_bytes / (kern_ms * 1e-3) / 1e9),
         "peak": fp32_peak if bound == "fp32" else hbm_peak, "unit": "TFLOP/s" if bound == "fp32" else "GB/s",
-        "frac": t_roof / (kern_ms * 1e-3), "traffic": None,
+        "frac": t_roof / (kern_ms * 1e-3), "traffic": traffic,
         "kernel_ms": kern_ms, "plan_ms": plan_ms, "kernel_share_of_step": kern_ms / (plan_ms + kern_ms),
         "flops_executed": f_exec, "flops_dense_model_8d": f_dense, "algorithmic_bytes": alg_bytes,
         "frac_vs_dense_model_8d": (f_dense / (fp32_peak * 1e12)) / (kern_ms * 1e-3),
@@ -355,6 +429,11 @@ def main():
             del Pd
         line["variants"] = var
 
+    if rank == 0 and world == 1 and not args.no_extras:
+        try:
+            line["extras"] = extras(sp, P, params, cp, hbm_peak)
+        except Exception as e:  # secondary numbers must never take the headline down
+            line["extras"] = {"error": repr(e)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rate, threads, m = cpu_port_rate(P, params_host.numpy(), cp.cpu().numpy())
         line["cpu_baseline"] = {"value": rate, "unit": "points/s", "cores": threads, "kind": "port",

@@ -13,6 +13,8 @@ namespace {
 
 constexpr int kWarpsPerCta = 8;
 
+constexpr int kFwdStrips = 4;  // segments up to 128 entries are fetched in one batch of independent loads
+
 template <typename JT, typename CT, int CPD>
 __global__ void __launch_bounds__(kWarpsPerCta * 32) k_csr_forward(const float* __restrict__ cp, const JT* __restrict__ jm,
                                                                      const float* __restrict__ phi,
@@ -27,11 +29,21 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_csr_forward(const float* 
         float acc[CPD];
 #pragma unroll
         for (int k = 0; k < CPD; ++k) acc[k] = 0.0f;
-        for (int64_t j = beg + lane; j < end; j += 32) {
-            const float w = __ldg(phi + j);
-            const int64_t r = (int64_t)__ldg(jm + j);
+        for (int64_t j0 = beg; j0 < end; j0 += 32 * kFwdStrips) {
+            float w[kFwdStrips];
+            int64_t r[kFwdStrips];
 #pragma unroll
-            for (int k = 0; k < CPD; ++k) acc[k] = fmaf(w, __ldg(cp + r * CPD + k), acc[k]);
+            for (int s = 0; s < kFwdStrips; ++s) {  // all index / weight loads of the batch are in flight together
+                const int64_t j = j0 + s * 32 + lane;
+                const bool ok = j < end;
+                w[s] = ok ? __ldg(phi + j) : 0.0f;
+                r[s] = ok ? (int64_t)__ldg(jm + j) : 0;
+            }
+#pragma unroll
+            for (int s = 0; s < kFwdStrips; ++s) {
+#pragma unroll
+                for (int k = 0; k < CPD; ++k) acc[k] = fmaf(w[s], __ldg(cp + r[s] * CPD + k), acc[k]);
+            }
         }
 #pragma unroll
         for (int k = 0; k < CPD; ++k) {

@@ -198,7 +198,7 @@ THB_DEV void cp_async4(void* smem, const void* gmem) {
 // Per-warp shared memory.  Everything that can be known ahead of time is double buffered and filled by
 // cp.async, so the global-memory latency of item i+1 is paid while item i is being computed and costs no
 // registers.
-template <class SH>
+template <class SH, int MODE>
 struct WarpSmem {
     int4 rec[3][4];                       // ring of work-item records (lookahead 2)
     float knots[2][3][8];                 // local knots of the item's cell, per dimension
@@ -208,6 +208,9 @@ struct WarpSmem {
     float pu[2][3][64];                   // their parameters (SoA)
     float4 cc[kMaxCC];                    // control points of the coarser-level supports
     float tiles[2][kWChunk * SH::TS];     // coefficient tiles, streamed in chunks
+    // MODE_BASIS: PHI values are transposed through here so that every point's row is written coalesced
+    float stage[MODE == MODE_BASIS ? (32 * (SH::TS + 1) > 64 * (kWChunk + 1) ? 32 * (SH::TS + 1) : 64 * (kWChunk + 1)) : 1];
+    long long poff[MODE == MODE_BASIS ? 64 : 1];
 };
 
 template <int PPT>
@@ -282,7 +285,7 @@ THB_DEV void issue_chunk(const thb_space_desc& sp, const Item& it, int c0, int n
 // One sub-batch of an item: PPT*32 points (lane-major), all channels.
 template <class SH, int PPT, int CPD, int MODE, bool DER>
 THB_DEV void warp_points(const thb_space_desc& sp, const Args& ar, const Item& it, int base, int ntile, bool cellnet,
-                         WarpSmem<SH>& sm, int tb, int pb) {
+                         WarpSmem<SH, MODE>& sm, int tb, int pb) {
     constexpr int T = SH::T, TS = SH::TS, NP = SH::NP, NQ = SH::NQ;
     const int lane = threadIdx.x;
     const bool use_direct = (it.ndir > 0) || (MODE == MODE_FUSED && cellnet);
@@ -301,7 +304,20 @@ THB_DEV void warp_points(const thb_space_desc& sp, const Args& ar, const Item& i
         if (MODE == MODE_BASIS) off[q] = __ldg(ar.offsets + idx[q]);
         const float u[3] = {sm.pu[pb][0][q * 32 + lane], sm.pu[pb][1][q * 32 + lane], SH::N2 > 1 ? sm.pu[pb][2][q * 32 + lane] : 0.f};
         bs[q].eval(u, sm.knots[tb], sm.rk);
+        if (MODE == MODE_BASIS) sm.poff[q * 32 + lane] = off[q];
     }
+    constexpr int LDS_ = TS + 1;  // padded row of the PHI staging area
+    int nval[PPT];
+#pragma unroll
+    for (int q = 0; q < PPT; ++q) nval[q] = min(32, max(0, it.count - base - q * 32));
+    // positions of this lane's window entries (t = lane, lane + 32) among the cell's own-level supports
+    int dpos[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int t = lane + 32 * h;
+        dpos[h] = (it.ndir > 0 && t < T && ((it.dm >> t) & 1ull)) ? __popcll(it.dm & ((1ull << t) - 1ull)) : -1;
+    }
+    if (MODE == MODE_BASIS) __syncwarp();
     for (int chi = 0; chi < ar.nch; ++chi) {
         const int ch = ar.channels[chi];
         f32x2 tp2[PPT][NP];
@@ -309,15 +325,19 @@ THB_DEV void warp_points(const thb_space_desc& sp, const Args& ar, const Item& i
         for (int q = 0; q < PPT; ++q) {
             float tp[TS];
             bs[q].tensor(ch, tp);
-            if (MODE == MODE_BASIS) {
-                if (it.ndir > 0 && valid[q]) {
-                    float* dst = ar.out[chi] + off[q];
-                    int pos = 0;
+            if (MODE == MODE_BASIS && it.ndir > 0) {
+                // own-level supports: PHI = tp[t].  Transpose through shared memory: lane = point on the way in,
+                // lane = window entry on the way out, so each point's row goes out as one coalesced store.
 #pragma unroll
-                    for (int t = 0; t < T; ++t) {
-                        if ((it.dm >> t) & 1ull) dst[pos++] = tp[t];
-                    }
+                for (int t = 0; t < T; ++t) sm.stage[lane * LDS_ + t] = tp[t];
+                __syncwarp();
+                for (int pt = 0; pt < nval[q]; ++pt) {
+                    float* dst = ar.out[chi] + sm.poff[q * 32 + pt];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+                        if (dpos[h] >= 0) dst[dpos[h]] = sm.stage[pt * LDS_ + lane + 32 * h];
                 }
+                __syncwarp();
             }
 #pragma unroll
             for (int m = 0; m < NP; ++m) tp2[q][m] = pack2(tp[2 * m], tp[2 * m + 1]);
@@ -392,13 +412,21 @@ THB_DEV void warp_points(const thb_space_desc& sp, const Args& ar, const Item& i
                         }
                     } else {
 #pragma unroll
-                        for (int q = 0; q < PPT; ++q) {
-                            const float phi = hsum2(a[q][0]) + hsum2(a[q][1]);
-                            if (valid[q]) ar.out[chi][off[q] + it.ndir + c0 + s] = phi;
-                        }
+                        for (int q = 0; q < PPT; ++q) sm.stage[(q * 32 + lane) * (kWChunk + 1) + s] = hsum2(a[q][0]) + hsum2(a[q][1]);
                     }
                 }
                 __syncwarp();
+                if (MODE == MODE_BASIS) {
+                    // coalesced write-out of the chunk: 16 consecutive supports of a point are contiguous in PHI
+#pragma unroll
+                    for (int q = 0; q < PPT; ++q) {
+                        for (int e = lane; e < nval[q] * kWChunk; e += 32) {
+                            const int pt = e / kWChunk, sc = e - pt * kWChunk;
+                            if (sc < ns) ar.out[chi][sm.poff[q * 32 + pt] + it.ndir + c0 + sc] = sm.stage[(q * 32 + pt) * (kWChunk + 1) + sc];
+                        }
+                    }
+                    __syncwarp();
+                }
                 buf ^= 1;
             }
         }
@@ -424,7 +452,7 @@ __global__ void __launch_bounds__(kThreads) k_tile(const __grid_constant__ thb_s
     using SH = Shp<N0, N1, N2>;
     constexpr int TS = SH::TS, NQ = SH::NQ;
     constexpr int SB = 32 * PPT;
-    __shared__ __align__(16) WarpSmem<SH> sm;
+    __shared__ __align__(16) WarpSmem<SH, MODE> sm;
 
     const int lane = threadIdx.x;
     const int nitems = ar.counters[0];

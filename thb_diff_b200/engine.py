@@ -98,7 +98,7 @@ def _chan_array(channels):
 
 def basis_tiled(P, plan, offsets, nnz, channels=(CH_VALUE,)):
     """PHI for each channel, flat [nnz] in the reference's (point-major) pair order."""
-    outs = [torch.zeros(nnz, dtype=torch.float32, device=P.device) for _ in channels]
+    outs = [torch.empty(nnz, dtype=torch.float32, device=P.device) for _ in channels]  # every entry is written
     arr = (C.c_void_p * len(outs))(*[o.data_ptr() for o in outs])
     check(lib.thb_basis_tiled(C.byref(P.desc()), C.byref(plan.desc), ptr(plan.params), ptr(offsets), _chan_array(channels),
                               len(channels), arr, stream_ptr(P.device)), "thb_basis_tiled")
