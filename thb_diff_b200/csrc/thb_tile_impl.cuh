@@ -21,6 +21,9 @@
 
 namespace thb_tile {
 
+#ifndef THB_TILE_MINB
+#define THB_TILE_MINB 1  // register budget hint (9 => 168 registers + spills in the FFMA2 loop: measured slower)
+#endif
 constexpr int kThreads = 32;   // forward tile kernels: one warp per CTA
 constexpr int kBwdThreads = 128;
 constexpr int kChunk = 64;
@@ -448,7 +451,7 @@ THB_DEV void warp_points(const thb_space_desc& sp, const Args& ar, const Item& i
 // i+2 are (being) fetched, the id of item i+3 is being claimed, and the points of the next sub-batch plus
 // the knots / window control points of item i+1 stream into the other half of the shared-memory buffers.
 template <int N0, int N1, int N2, int PPT, int CPD, int MODE, bool DER>
-__global__ void __launch_bounds__(kThreads) k_tile(const __grid_constant__ thb_space_desc sp, const __grid_constant__ Args ar) {
+__global__ void __launch_bounds__(kThreads, THB_TILE_MINB) k_tile(const __grid_constant__ thb_space_desc sp, const __grid_constant__ Args ar) {
     using SH = Shp<N0, N1, N2>;
     constexpr int TS = SH::TS, NQ = SH::NQ;
     constexpr int SB = 32 * PPT;

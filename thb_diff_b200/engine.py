@@ -204,3 +204,65 @@ def fma_peak(variant, iters=4096, repeats=5):
         torch.cuda.synchronize()
         best = max(best, flops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
     return best
+
+
+class HostPipeline:
+    """Evaluation from HOST buffers: params (pinned, [N, d] f32) -> geometry (pinned, [N, cp_dim] f32).
+
+    The batch is cut into contiguous chunks; three CUDA streams overlap the H2D copy of chunk c+1, the
+    plan + fused kernel of chunk c and the D2H copy of chunk c-1 (PCIe is full duplex), so a step costs about
+    max(H2D, D2H, compute) instead of their sum.  Device buffers are allocated once."""
+
+    def __init__(self, P, n_points, cp_dim=3, n_chunks=8, cellnet=False):
+        self.P, self.n, self.cpd, self.cellnet = P, int(n_points), cp_dim, cellnet
+        n_chunks = max(1, min(n_chunks, (self.n + 65535) // 65536))
+        base, rem = divmod(self.n, n_chunks)
+        self.bounds = []
+        lo = 0
+        for c in range(n_chunks):
+            hi = lo + base + (1 if c < rem else 0)
+            self.bounds.append((lo, hi))
+            lo = hi
+        m = max(hi - lo for lo, hi in self.bounds)
+        dev = P.device
+        self.pbuf = [torch.empty((m, P.ndim), dtype=torch.float32, device=dev) for _ in range(2)]
+        self.obuf = [torch.empty((m, cp_dim), dtype=torch.float32, device=dev) for _ in range(2)]
+        self.plans = [None, None]
+        self.s_in, self.s_cmp, self.s_out = (torch.cuda.Stream(device=dev) for _ in range(3))
+
+    def run(self, params_host, ctrl_pts, out_host):
+        """Enqueues one full evaluation; returns after everything is enqueued (call torch.cuda.synchronize()
+        or wait on the returned event before reading out_host)."""
+        cur = torch.cuda.current_stream(self.P.device)
+        for s in (self.s_in, self.s_cmp, self.s_out):
+            s.wait_stream(cur)
+        done, outd = {}, {}
+        for c, (lo, hi) in enumerate(self.bounds):
+            b, m = c % 2, hi - lo
+            with torch.cuda.stream(self.s_in):
+                if c >= 2:
+                    self.s_in.wait_event(done[c - 2])  # the kernel that read this params buffer has finished
+                self.pbuf[b][:m].copy_(params_host[lo:hi], non_blocking=True)
+                ev_in = torch.cuda.Event()
+                ev_in.record(self.s_in)
+            with torch.cuda.stream(self.s_cmp):
+                self.s_cmp.wait_event(ev_in)
+                if c >= 2:
+                    self.s_cmp.wait_event(outd[c - 2])  # the D2H copy that read this output buffer has finished
+                pl = self.plans[b]
+                if pl is None or pl.n != m:
+                    pl = self.plans[b] = Plan(self.P, self.pbuf[b][:m])
+                else:
+                    pl.build()
+                eval_fused(self.P, pl, ctrl_pts, cellnet=self.cellnet, out=[self.obuf[b][:m]])
+                done[c] = torch.cuda.Event()
+                done[c].record(self.s_cmp)
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(done[c])
+                out_host[lo:hi].copy_(self.obuf[b][:m], non_blocking=True)
+                outd[c] = torch.cuda.Event()
+                outd[c].record(self.s_out)
+        cur.wait_stream(self.s_out)
+        cur.wait_stream(self.s_cmp)
+        cur.wait_stream(self.s_in)
+        return outd[len(self.bounds) - 1]
