@@ -184,6 +184,7 @@ struct BasesRK {
 
 constexpr int kWChunk = 16;  // supports staged per chunk by one warp
 constexpr int kMaxCC = 128;  // coarse-support control points gathered once per item (else per chunk)
+constexpr int kRowPad = 4;   // floats of padding per staged tile row: rows s..s+3 start in different banks
 
 THB_DEV void cp_async16(void* smem, const void* gmem) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -210,7 +211,7 @@ struct WarpSmem {
     int pidx[2][64];                      // caller-order index of the points of a sub-batch
     float pu[2][3][64];                   // their parameters (SoA)
     float4 cc[kMaxCC];                    // control points of the coarser-level supports
-    float tiles[2][kWChunk * SH::TS];     // coefficient tiles, streamed in chunks
+    float tiles[2][kWChunk * (SH::TS + kRowPad)];  // coefficient tiles, streamed in chunks (padded rows)
     // MODE_BASIS: PHI values are transposed through here so that every point's row is written coalesced
     float stage[MODE == MODE_BASIS ? (32 * (SH::TS + 1) > 64 * (kWChunk + 1) ? 32 * (SH::TS + 1) : 64 * (kWChunk + 1)) : 1];
     long long poff[MODE == MODE_BASIS ? 64 : 1];
@@ -280,17 +281,27 @@ THB_DEV void gather_cc(const thb_space_desc& sp, const Args& ar, const Item& it,
 template <int NQ>
 THB_DEV void issue_chunk(const thb_space_desc& sp, const Item& it, int c0, int ns, int TS, float* buf) {
     const float4* src = reinterpret_cast<const float4*>(sp.tiles + (int64_t)(it.toff + c0) * TS);
-    float4* dst = reinterpret_cast<float4*>(buf);
-    for (int i = threadIdx.x; i < ns * NQ; i += 32) cp_async16(dst + i, src + i);
+    for (int i = threadIdx.x; i < ns * NQ; i += 32) {
+        const int row = i / NQ, quad = i - row * NQ;
+        cp_async16(buf + row * (TS + kRowPad) + quad * 4, src + i);
+    }
     cp_async_commit();
 }
 
 // One sub-batch of an item: PPT*32 points (lane-major), all channels.
-template <class SH, int PPT, int CPD, int MODE, bool DER>
+// G > 1 (only with PPT == 1): "support split" for sub-batches of <= 32/G points -- G lane groups hold the same
+// points and each takes every G-th tiled support, so small cells do not leave 3/4 of the lanes idle; the
+// groups read G different (bank-staggered) tile rows with one LDS and their partial sums are combined by shuffles.
+template <class SH, int PPT, int G, int CPD, int MODE, bool DER>
 THB_DEV void warp_points(const thb_space_desc& sp, const Args& ar, const Item& it, int base, int ntile, bool cellnet,
                          WarpSmem<SH, MODE>& sm, int tb, int pb) {
+    static_assert(G == 1 || (PPT == 1 && MODE == MODE_FUSED), "support split: one point per lane, fused mode only");
     constexpr int T = SH::T, TS = SH::TS, NP = SH::NP, NQ = SH::NQ;
-    const int lane = threadIdx.x;
+    constexpr int NPT = 32 / G;                // points per pass
+    constexpr int TSP = TS + kRowPad;          // staged tile row stride
+    const int lane_raw = threadIdx.x;
+    const int grp = lane_raw / NPT;            // support group of this lane
+    const int lane = lane_raw % NPT;           // point slot of this lane
     const bool use_direct = (it.ndir > 0) || (MODE == MODE_FUSED && cellnet);
     const bool tile_loop = !(MODE == MODE_FUSED && cellnet) && ntile > 0;
     const bool cc_all = ntile <= kMaxCC;
@@ -368,7 +379,7 @@ THB_DEV void warp_points(const thb_space_desc& sp, const Args& ar, const Item& i
                     }
                 }
 #pragma unroll
-                for (int q = 0; q < PPT; ++q) acc[q][k] = hsum2(a[q][0]) + hsum2(a[q][1]);
+                for (int q = 0; q < PPT; ++q) acc[q][k] = (G == 1 || grp == 0) ? hsum2(a[q][0]) + hsum2(a[q][1]) : 0.0f;
             }
         }
         if (tile_loop) {
@@ -389,8 +400,10 @@ THB_DEV void warp_points(const thb_space_desc& sp, const Args& ar, const Item& i
                 const float* tbuf = sm.tiles[buf];
                 const float4* ccp = sm.cc + (cc_all ? c0 : 0);
 #pragma unroll 2
-                for (int s = 0; s < ns; ++s) {
-                    const ulonglong2* row = reinterpret_cast<const ulonglong2*>(tbuf + s * TS);
+                for (int s0 = 0; s0 < ns; s0 += G) {
+                    const bool s_on = G == 1 || s0 + grp < ns;
+                    const int s = (G == 1) ? s0 : min(s0 + grp, ns - 1);
+                    const ulonglong2* row = reinterpret_cast<const ulonglong2*>(tbuf + s * TSP);
                     f32x2 a[PPT][2];
 #pragma unroll
                     for (int q = 0; q < PPT; ++q) a[q][0] = a[q][1] = 0ull;
@@ -407,7 +420,7 @@ THB_DEV void warp_points(const thb_space_desc& sp, const Args& ar, const Item& i
                         const float4 cc = ccp[s];
 #pragma unroll
                         for (int q = 0; q < PPT; ++q) {
-                            const float phi = hsum2(a[q][0]) + hsum2(a[q][1]);
+                            const float phi = s_on ? hsum2(a[q][0]) + hsum2(a[q][1]) : 0.0f;
                             acc[q][0] = fmaf(phi, cc.x, acc[q][0]);
                             acc[q][1] = fmaf(phi, cc.y, acc[q][1]);
                             acc[q][2] = fmaf(phi, cc.z, acc[q][2]);
@@ -434,9 +447,15 @@ THB_DEV void warp_points(const thb_space_desc& sp, const Args& ar, const Item& i
             }
         }
         if (MODE == MODE_FUSED) {
+            if (G > 1) {  // combine the support groups
+#pragma unroll
+                for (int k = 0; k < CPD; ++k)
+#pragma unroll
+                    for (int o = NPT; o < 32; o <<= 1) acc[0][k] += __shfl_xor_sync(0xffffffffu, acc[0][k], o);
+            }
 #pragma unroll
             for (int q = 0; q < PPT; ++q) {
-                if (valid[q]) {
+                if (valid[q] && (G == 1 || grp == 0)) {
                     float* o = ar.out[chi] + (int64_t)idx[q] * CPD;
 #pragma unroll
                     for (int k = 0; k < CPD; ++k) o[k] = acc[q][k];
@@ -530,10 +549,15 @@ __global__ void __launch_bounds__(kThreads, THB_TILE_MINB) k_tile(const __grid_c
                 prefetch_item_tables<SH, CPD>(sp, ar, nx, sm.knots[tb ^ 1], sm.cpw[tb ^ 1], want_cp);
             }
             cp_async_commit();
-            if (PPT == 2 && it.count - base <= 32)
-                warp_points<SH, 1, CPD, MODE, DER>(sp, ar, it, base, ntile, cellnet, sm, tb, pb);
+            const int rem = it.count - base;
+            if (MODE == MODE_FUSED && rem <= 8 && ntile > 0)
+                warp_points<SH, 1, (MODE == MODE_FUSED ? 4 : 1), CPD, MODE, DER>(sp, ar, it, base, ntile, cellnet, sm, tb, pb);
+            else if (MODE == MODE_FUSED && rem <= 16 && ntile > 0)
+                warp_points<SH, 1, (MODE == MODE_FUSED ? 2 : 1), CPD, MODE, DER>(sp, ar, it, base, ntile, cellnet, sm, tb, pb);
+            else if (PPT == 2 && rem <= 32)
+                warp_points<SH, 1, 1, CPD, MODE, DER>(sp, ar, it, base, ntile, cellnet, sm, tb, pb);
             else
-                warp_points<SH, PPT, CPD, MODE, DER>(sp, ar, it, base, ntile, cellnet, sm, tb, pb);
+                warp_points<SH, PPT, 1, CPD, MODE, DER>(sp, ar, it, base, ntile, cellnet, sm, tb, pb);
             cp_async_wait<0>();
             __syncwarp();
             pb ^= 1;
