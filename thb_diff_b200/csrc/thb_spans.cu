@@ -79,37 +79,41 @@ __global__ void __launch_bounds__(256) k_expand_supports(const __grid_constant__
 // Finest-level span with the knots of that level staged in shared memory.  First guess from a uniform
 // partition, corrected by walking (exact for 'uniform-ish' knots in <= 2 steps), binary search otherwise;
 // the result is the same span as span_right() for every in-domain u.
-// `scale` = nc / (U[p+nc] - U[p]).
-THB_DEV int finest_cell(const float* __restrict__ U, int p, int nc, float scale, float u) {
+// `scale` = nc / (U[p+nc] - U[p]); u0 = U[p], u1 = U[p+nc] (kept in registers by the caller).
+THB_DEV int finest_cell(const float* __restrict__ U, int p, int nc, float scale, float u0, float u1, float u) {
     // U[p .. p+nc] are the breakpoints; cell c <=> U[p+c] <= u < U[p+c+1]
-    const float u0 = U[p], u1 = U[p + nc];
     if (!(u >= u0) || u > u1) return -1;  // also rejects NaN
     int c = min((int)((u - u0) * scale), nc - 1);
-    // branch-free +-1 correction (covers knots jittered by less than one cell), then verify
-    c += (int)(u >= U[p + c + 1]) - (int)(u < U[p + c]);
+    if (u >= U[p + c] && u < U[p + c + 1]) return c;  // common case: two shared-memory reads
+    if (u == u1) return nc - 1;                       // reference rule for the last knot
+    // one step off (jittered knots), else binary search on the breakpoints
+    c += (u >= U[p + c + 1]) ? 1 : -1;
     c = min(max(c, 0), nc - 1);
-    if (u < U[p + c] || (u >= U[p + c + 1] && c < nc - 1)) {  // far from uniform: binary search on the breakpoints
-        int lo = 0, hi = nc;  // invariant: U[p+lo] <= u < U[p+hi]  (u == u1 ends in the last cell)
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (U[p + mid] <= u) lo = mid; else hi = mid;
-        }
-        c = lo;
+    if (u >= U[p + c] && u < U[p + c + 1]) return c;
+    int lo = 0, hi = nc;  // invariant: U[p+lo] <= u < U[p+hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (U[p + mid] <= u) lo = mid; else hi = mid;
     }
-    return c;  // u == U[-1] lands in nc-1: the reference rule for the last knot
+    return lo;
 }
 
 constexpr int kPlanSmemKnots = 3 * 1024;
 
 // slot of a point given the finest-level knots in shared memory; the cell_slot entries of ALL levels are
 // fetched at once (independent loads) and the finest active one is selected.
-THB_DEV int locate_slot_fast(const thb_space_desc& sp, const float* const* Uk, const float* scale, const float* u) {
+struct PlanKnots {
+    const float* U[3];
+    float scale[3], u0[3], u1[3];
+};
+
+THB_DEV int locate_slot_fast(const thb_space_desc& sp, const PlanKnots& pk, const float* u) {
     const int L = sp.nlevels - 1;
     int cf[3] = {0, 0, 0};
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         if (k < sp.ndim) {
-            const int c = finest_cell(Uk[k], sp.degree[k], sp.ncells[L][k], scale[k], u[k]);
+            const int c = finest_cell(pk.U[k], sp.degree[k], sp.ncells[L][k], pk.scale[k], pk.u0[k], pk.u1[k], u[k]);
             if (c < 0) return -1;
             cf[k] = c;
         }
@@ -127,12 +131,19 @@ THB_DEV int locate_slot_fast(const thb_space_desc& sp, const float* const* Uk, c
     return slot;
 }
 
-THB_DEV bool stage_finest_knots(const thb_space_desc& sp, float* sk, const float** Uk, float* scale) {
+THB_DEV bool stage_finest_knots(const thb_space_desc& sp, float* sk, PlanKnots& pk) {
     const int L = sp.nlevels - 1;
-    for (int k = 0; k < sp.ndim; ++k) {
-        const float* g = sp.knots + sp.knot_off[L][k];
-        const int p = sp.degree[k], nc = sp.ncells[L][k];
-        scale[k] = (float)nc / (g[p + nc] - g[p]);
+    const float** Uk = pk.U;
+    for (int k = 0; k < 3; ++k) {
+        pk.U[k] = nullptr;
+        pk.scale[k] = pk.u0[k] = pk.u1[k] = 0.f;
+        if (k < sp.ndim) {
+            const float* g = sp.knots + sp.knot_off[L][k];
+            const int p = sp.degree[k], nc = sp.ncells[L][k];
+            pk.u0[k] = g[p];
+            pk.u1[k] = g[p + nc];
+            pk.scale[k] = (float)nc / (pk.u1[k] - pk.u0[k]);
+        }
     }
     int tot = 0;
     for (int k = 0; k < sp.ndim; ++k) tot += sp.knot_len[L][k];
@@ -157,25 +168,38 @@ THB_DEV bool stage_finest_knots(const thb_space_desc& sp, float* sk, const float
 __global__ void __launch_bounds__(256) k_plan_count(const __grid_constant__ thb_space_desc sp, const float* __restrict__ params,
                                                     int64_t n, int32_t* __restrict__ slot_out, int32_t* __restrict__ count) {
     __shared__ float sk[kPlanSmemKnots];
-    const float* Uk[3] = {nullptr, nullptr, nullptr};
-    float scale[3] = {0.f, 0.f, 0.f};
-    stage_finest_knots(sp, sk, Uk, scale);
+    PlanKnots pk;
+    stage_finest_knots(sp, sk, pk);
     const int lane = threadIdx.x & 31;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    const int64_t nround = (n + stride - 1) / stride * stride;  // keep whole warps in the loop for match_any
+    const int64_t nround = (n + 2 * stride - 1) / (2 * stride) * (2 * stride);  // whole warps stay in the loop (match_any)
     const int d = sp.ndim;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
-        int slot = -1;
-        if (i < n) {
-            float u[3];
-            u[0] = params[i * d];
-            u[1] = params[i * d + 1];
-            u[2] = d == 3 ? params[i * d + 2] : 0.f;
-            slot = locate_slot_fast(sp, Uk, scale, u);
-            slot_out[i] = slot;
+    // two points per thread per iteration: their loads and lookups are independent and overlap
+    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < nround; i0 += 2 * stride) {
+        int slot[2];
+        float u[2][3];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int64_t i = i0 + h * stride;
+            const int64_t j = i < n ? i : 0;
+            u[h][0] = params[j * d];
+            u[h][1] = params[j * d + 1];
+            u[h][2] = d == 3 ? params[j * d + 2] : 0.f;
         }
-        const unsigned peers = __match_any_sync(0xffffffffu, slot);
-        if (slot >= 0 && lane == (__ffs(peers) - 1)) atomicAdd(count + slot, __popc(peers));
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int64_t i = i0 + h * stride;
+            slot[h] = -1;
+            if (i < n) {
+                slot[h] = locate_slot_fast(sp, pk, u[h]);
+                slot_out[i] = slot[h];
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const unsigned peers = __match_any_sync(0xffffffffu, slot[h]);
+            if (slot[h] >= 0 && lane == (__ffs(peers) - 1)) atomicAdd(count + slot[h], __popc(peers));
+        }
     }
 }
 
@@ -280,21 +304,38 @@ __global__ void __launch_bounds__(256) k_plan_scatter(const int32_t* __restrict_
                                                       int32_t* __restrict__ perm, float* __restrict__ sorted) {
     const int lane = threadIdx.x & 31;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    const int64_t nround = (n + stride - 1) / stride * stride;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
-        const int s = i < n ? slot[i] : -1;
-        float u[3] = {0.f, 0.f, 0.f};
-        if (s >= 0)
-            for (int k = 0; k < ndim; ++k) u[k] = params[i * ndim + k];
-        const unsigned peers = __match_any_sync(0xffffffffu, s);
-        const int leader = __ffs(peers) - 1;
-        int base = 0;
-        if (s >= 0 && lane == leader) base = atomicAdd(cursor + s, __popc(peers));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (s >= 0) {
-            const int64_t pos = (int64_t)start[s] + base + __popc(peers & ((1u << lane) - 1u));
-            perm[pos] = (int32_t)i;
-            for (int k = 0; k < ndim; ++k) sorted[pos * ndim + k] = u[k];
+    const int64_t nround = (n + 2 * stride - 1) / (2 * stride) * (2 * stride);
+    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < nround; i0 += 2 * stride) {
+        int s[2], st[2], base[2], leader[2];
+        unsigned peers[2];
+        float u[2][3];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {  // all loads of both points first
+            const int64_t i = i0 + h * stride;
+            const int64_t j = i < n ? i : 0;
+            s[h] = i < n ? slot[j] : -1;
+            u[h][0] = params[j * ndim];
+            u[h][1] = params[j * ndim + 1];
+            u[h][2] = ndim == 3 ? params[j * ndim + 2] : 0.f;
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            st[h] = s[h] >= 0 ? __ldg(start + s[h]) : 0;
+            peers[h] = __match_any_sync(0xffffffffu, s[h]);
+            leader[h] = __ffs(peers[h]) - 1;
+            base[h] = 0;
+            if (s[h] >= 0 && lane == leader[h]) base[h] = atomicAdd(cursor + s[h], __popc(peers[h]));
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            base[h] = __shfl_sync(0xffffffffu, base[h], leader[h]);
+            if (s[h] >= 0) {
+                const int64_t pos = (int64_t)st[h] + base[h] + __popc(peers[h] & ((1u << lane) - 1u));
+                perm[pos] = (int32_t)(i0 + h * stride);
+                sorted[pos * ndim] = u[h][0];
+                sorted[pos * ndim + 1] = u[h][1];
+                if (ndim == 3) sorted[pos * ndim + 2] = u[h][2];
+            }
         }
     }
 }
