@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(256) k_expand_supports(const __grid_constant__
 // partition, corrected by walking (exact for 'uniform-ish' knots in <= 2 steps), binary search otherwise;
 // the result is the same span as span_right() for every in-domain u.
 // `scale` = nc / (U[p+nc] - U[p]); u0 = U[p], u1 = U[p+nc] (kept in registers by the caller).
-THB_DEV int finest_cell(const float* __restrict__ U, int p, int nc, float scale, float u0, float u1, float u) {
+THB_DEV int finest_cell(const float* U, int p, int nc, float scale, float u0, float u1, float u) {
     // U[p .. p+nc] are the breakpoints; cell c <=> U[p+c] <= u < U[p+c+1]
     if (!(u >= u0) || u > u1) return -1;  // also rejects NaN
     int c = min((int)((u - u0) * scale), nc - 1);
@@ -103,17 +103,17 @@ constexpr int kPlanSmemKnots = 3 * 1024;
 // slot of a point given the finest-level knots in shared memory; the cell_slot entries of ALL levels are
 // fetched at once (independent loads) and the finest active one is selected.
 struct PlanKnots {
-    const float* U[3];
+    int off[3];  // offsets of the finest knot vectors inside the shared-memory copy
     float scale[3], u0[3], u1[3];
 };
 
-THB_DEV int locate_slot_fast(const thb_space_desc& sp, const PlanKnots& pk, const float* u) {
+THB_DEV int locate_slot_fast(const thb_space_desc& sp, const float* sk, const PlanKnots& pk, const float* u) {
     const int L = sp.nlevels - 1;
     int cf[3] = {0, 0, 0};
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         if (k < sp.ndim) {
-            const int c = finest_cell(pk.U[k], sp.degree[k], sp.ncells[L][k], pk.scale[k], pk.u0[k], pk.u1[k], u[k]);
+            const int c = finest_cell(sk + pk.off[k], sp.degree[k], sp.ncells[L][k], pk.scale[k], pk.u0[k], pk.u1[k], u[k]);
             if (c < 0) return -1;
             cf[k] = c;
         }
@@ -131,32 +131,26 @@ THB_DEV int locate_slot_fast(const thb_space_desc& sp, const PlanKnots& pk, cons
     return slot;
 }
 
+// Stages the finest knots in shared memory; false when they do not fit (the caller then uses locate_slot()).
 THB_DEV bool stage_finest_knots(const thb_space_desc& sp, float* sk, PlanKnots& pk) {
     const int L = sp.nlevels - 1;
-    const float** Uk = pk.U;
-    for (int k = 0; k < 3; ++k) {
-        pk.U[k] = nullptr;
-        pk.scale[k] = pk.u0[k] = pk.u1[k] = 0.f;
-        if (k < sp.ndim) {
-            const float* g = sp.knots + sp.knot_off[L][k];
-            const int p = sp.degree[k], nc = sp.ncells[L][k];
-            pk.u0[k] = g[p];
-            pk.u1[k] = g[p + nc];
-            pk.scale[k] = (float)nc / (pk.u1[k] - pk.u0[k]);
-        }
-    }
     int tot = 0;
     for (int k = 0; k < sp.ndim; ++k) tot += sp.knot_len[L][k];
     const bool fits = tot <= kPlanSmemKnots;
     int pos = 0;
-    for (int k = 0; k < sp.ndim; ++k) {
-        const float* g = sp.knots + sp.knot_off[L][k];
-        if (fits) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        pk.off[k] = 0;
+        pk.scale[k] = pk.u0[k] = pk.u1[k] = 0.f;
+        if (k < sp.ndim && fits) {
+            const float* g = sp.knots + sp.knot_off[L][k];
+            const int p = sp.degree[k], nc = sp.ncells[L][k];
             for (int i = threadIdx.x; i < sp.knot_len[L][k]; i += blockDim.x) sk[pos + i] = g[i];
-            Uk[k] = sk + pos;
+            pk.off[k] = pos;
+            pk.u0[k] = g[p];
+            pk.u1[k] = g[p + nc];
+            pk.scale[k] = (float)nc / (pk.u1[k] - pk.u0[k]);
             pos += sp.knot_len[L][k];
-        } else {
-            Uk[k] = g;
         }
     }
     __syncthreads();
@@ -169,7 +163,7 @@ __global__ void __launch_bounds__(256) k_plan_count(const __grid_constant__ thb_
                                                     int64_t n, int32_t* __restrict__ slot_out, int32_t* __restrict__ count) {
     __shared__ float sk[kPlanSmemKnots];
     PlanKnots pk;
-    stage_finest_knots(sp, sk, pk);
+    const bool in_smem = stage_finest_knots(sp, sk, pk);
     const int lane = threadIdx.x & 31;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t nround = (n + 2 * stride - 1) / (2 * stride) * (2 * stride);  // whole warps stay in the loop (match_any)
@@ -191,7 +185,7 @@ __global__ void __launch_bounds__(256) k_plan_count(const __grid_constant__ thb_
             const int64_t i = i0 + h * stride;
             slot[h] = -1;
             if (i < n) {
-                slot[h] = locate_slot_fast(sp, pk, u[h]);
+                slot[h] = in_smem ? locate_slot_fast(sp, sk, pk, u[h]) : locate_slot(sp, u[h]);
                 slot_out[i] = slot[h];
             }
         }
