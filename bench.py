@@ -180,6 +180,53 @@ def extras(sp, P, params, cp, hbm_peak):
         del Jm
     tfb = time_cuda(lambda: engine.eval_fused_backward(P, supp.plan, g))
     out["fused_backward"] = {"ms": tfb, "points_per_s": n / (tfb * 1e-3)}
+    del PHI, g, supp
+    torch.cuda.empty_cache()
+
+    # BASELINE config 4: differentiable fitting, 10M random target points, MSE, fused Adam; one step = forward,
+    # backward, (all-reduce of the control-point gradient when world > 1), optimiser step
+    from thb_diff_b200 import configs
+    from thb_diff_b200.distributed import ShardedFit
+
+    gen = torch.Generator(device=params.device).manual_seed(0)
+    prm4 = torch.rand((10_000_000, 3), device=params.device, generator=gen)
+    tgt = torch.stack([prm4[:, 0], prm4[:, 1], prm4[:, 2] + 0.1 * torch.sin(6.2831853 * prm4[:, 0]) * torch.sin(6.2831853 * prm4[:, 1])
+                       * torch.sin(6.2831853 * prm4[:, 2])], dim=1)
+    x = torch.from_numpy(configs.greville_ctrl_pts(sp, bump=0.0)).to(params.device).requires_grad_(True)
+    opt = torch.optim.Adam([x], lr=1e-2, fused=True)
+    for cellnet in (True, False):
+        fit = ShardedFit(P, prm4, tgt, prm4.shape[0], cellnet=cellnet)
+        l0 = float(fit.step(x, opt))
+        t = time_cuda(lambda: fit.step(x, opt), iters=10, warm=2)
+        out["fit_c4_cellnet" if cellnet else "fit_c4_per_point_phi"] = {
+            "adam_steps_per_s": 1e3 / t, "ms_per_step": t, "points": prm4.shape[0], "loss_first": l0, "loss_last": float(fit.step(x, opt)),
+            "what": "10M unsorted random points (plan built once, as the reference precomputes PHI once), forward + backward + fused Adam"}
+        del fit
+    del prm4, tgt, x, opt
+    torch.cuda.empty_cache()
+
+    # BASELINE config 5 (per-GPU share): 5 active levels, position + the three first-derivative vectors at 256^3
+    # points (= 1/8 of the 512^3 grid: every 2nd point per axis keeps the cell mix of the full grid)
+    from thb_diff_b200 import bspline_funcs as B
+    from thb_diff_b200.packed import PackedHierarchy
+
+    sp5 = configs.cubic3d_space(active_levels=5)
+    P5 = PackedHierarchy.from_space(sp5, device=params.device)
+    prm5 = B.grid_parametric_coordinates_device((512, 512, 512), device="cpu")[::1].view(512, 512, 512, 3)[::2, ::2, ::2].reshape(-1, 3).to(params.device).contiguous()
+    cp5 = torch.from_numpy(configs.greville_ctrl_pts(sp5)).to(params.device)
+    plan5 = engine.Plan(P5, prm5)
+    ch = [engine.CH_VALUE] + engine.grad_channels(3)
+    o5 = [torch.empty((prm5.shape[0], 3), device=params.device) for _ in ch]
+
+    def c5_step():
+        plan5.build()
+        engine.eval_fused(P5, plan5, cp5, ch, out=o5)
+
+    t5 = time_cuda(c5_step, iters=5, warm=2)
+    jac_err = max(float((o5[1 + k][:, k] - 1).abs().max()) for k in range(3)) if False else None
+    out["eval_c5_with_first_derivatives"] = {"ms_per_step": t5, "points_per_s": prm5.shape[0] / (t5 * 1e-3), "points": prm5.shape[0],
+                                             "levels": 5, "nCP": P5.nCP, "table_bytes": P5.nbytes(),
+                                             "what": "plan + fused kernel, 4 channels (value, d/du, d/dv, d/dw)"}
     return out
 
 
