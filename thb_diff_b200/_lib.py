@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libthb_b200.so")
+LIB_PATH = os.environ.get("THB_LIB", os.path.join(_HERE, "libthb_b200.so"))  # THB_LIB: tuning builds only
 MAX_LEVELS = 8
 INFO_W = 8
 

@@ -8,8 +8,12 @@
 int thb_check_space(const thb_space_desc* sp, const char* who);
 
 namespace thb_tile {
+#ifdef THB_ONLY_444  // tuning builds: only the cubic 3-D kernels
+#define THB_SHAPES(X) X(4, 4, 4)
+#else
 #define THB_SHAPES(X) \
     X(2, 2, 1) X(3, 3, 1) X(4, 4, 1) X(3, 4, 1) X(4, 3, 1) X(2, 2, 2) X(3, 3, 3) X(4, 4, 4) X(3, 4, 3) X(3, 3, 4) X(3, 4, 4) X(4, 3, 3) X(4, 3, 4) X(4, 4, 3)
+#endif
 #define THB_DECL(A, B, C) extern const ShapeOps shape_ops_##A##B##C;
 THB_SHAPES(THB_DECL)
 #define THB_REF(A, B, C) &shape_ops_##A##B##C,

@@ -182,7 +182,15 @@ struct BasesRK {
     }
 };
 
-constexpr int kWChunk = 16;  // supports staged per chunk by one warp
+#ifndef THB_WCHUNK
+#define THB_WCHUNK 16
+#endif
+#ifndef THB_SUNROLL
+#define THB_SUNROLL 2
+#endif
+#define THB_PRAGMA_(x) _Pragma(#x)
+#define THB_PRAGMA(x) THB_PRAGMA_(x)
+constexpr int kWChunk = THB_WCHUNK;  // supports staged per chunk by one warp
 constexpr int kMaxCC = 128;  // coarse-support control points gathered once per item (else per chunk)
 constexpr int kRowPad = 4;   // floats of padding per staged tile row: rows s..s+3 start in different banks
 
@@ -399,7 +407,7 @@ THB_DEV void warp_points(const thb_space_desc& sp, const Args& ar, const Item& i
                 __syncwarp();
                 const float* tbuf = sm.tiles[buf];
                 const float4* ccp = sm.cc + (cc_all ? c0 : 0);
-#pragma unroll 2
+THB_PRAGMA(unroll THB_SUNROLL)
                 for (int s0 = 0; s0 < ns; s0 += G) {
                     const bool s_on = G == 1 || s0 + grp < ns;
                     const int s = (G == 1) ? s0 : min(s0 + grp, ns - 1);

@@ -8,7 +8,9 @@ import torch
 from . import _lib
 from ._lib import PlanDesc, check, lib, ptr, require_cuda, stream_ptr
 
-POINTS_PER_ITEM = 128
+import os as _os
+
+POINTS_PER_ITEM = int(_os.environ.get("THB_POINTS_PER_ITEM", "256"))  # points per work item (multiple of 64)
 
 CH_VALUE = 0
 
