@@ -101,7 +101,7 @@ def test_fused_module_autograd_matches_csr_path():
     w = torch.randn_like(out_a)
     (out_a * w).sum().backward()
     (out_b * w).sum().backward()
-    assert rel_err(out_b.detach().cpu().numpy(), out_a.detach().cpu().numpy(), scale=float(out_a.abs().max())).max() <= TOL
+    assert rel_err(out_b.detach().cpu().numpy(), out_a.detach().cpu().numpy(), scale=float(out_a.detach().abs().max())).max() <= TOL
     assert rel_err(b.grad.cpu().numpy(), a.grad.cpu().numpy(), scale=float(a.grad.abs().max())).max() <= TOL
 
 

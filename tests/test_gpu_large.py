@@ -54,7 +54,7 @@ def test_c3_against_c_oracle_everywhere(c3):
         r = ht.eval(prm, cph, mode=1 << k, want_phi=True, offsets=off, nnz=int(S.sum()))
         cond = O.eval_forward(np.abs(cph), Jm, np.abs(r["phi"]), cs)
         assert (np.abs(o.cpu().numpy() - r["out"]) <= TOL * np.maximum(cond, 1.0)).all()
-        assert rel_err(o.cpu().numpy(), r["out"], scale=np.abs(r["out"]).max()).max() <= 1e-4
+        assert rel_err(o.cpu().numpy(), r["out"], scale=np.abs(r["out"]).max()).max() <= TOL  # thanks to the relative-CP contraction
 
 
 def test_c3_sampled_against_table_free_oracle(c3):

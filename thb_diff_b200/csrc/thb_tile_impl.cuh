@@ -210,7 +210,7 @@ THB_DEV void cp_async4(void* smem, const void* gmem) {
 // Per-warp shared memory.  Everything that can be known ahead of time is double buffered and filled by
 // cp.async, so the global-memory latency of item i+1 is paid while item i is being computed and costs no
 // registers.
-template <class SH, int MODE>
+template <class SH, int MODE, bool DER>
 struct WarpSmem {
     int4 rec[3][4];                       // ring of work-item records (lookahead 2)
     float knots[2][3][8];                 // local knots of the item's cell, per dimension
@@ -220,6 +220,12 @@ struct WarpSmem {
     float pu[2][3][64];                   // their parameters (SoA)
     float4 cc[kMaxCC];                    // control points of the coarser-level supports
     float tiles[2][kWChunk * (SH::TS + kRowPad)];  // coefficient tiles, streamed in chunks (padded rows)
+    // derivative channels contract against control points RELATIVE to a reference point of the item: the
+    // derivative basis values sum to zero, so the result is unchanged, but the summed terms are O(p/h * h)
+    // instead of O(p/h * |CP|) -- this removes the float32 cancellation error of parametric derivatives
+    float cpw_rel[(MODE == MODE_FUSED && DER) ? 4 : 1][(MODE == MODE_FUSED && DER) ? SH::TS : 1];
+    float4 cc_rel[(MODE == MODE_FUSED && DER) ? kMaxCC : 1];
+    float ref[4];
     // MODE_BASIS: PHI values are transposed through here so that every point's row is written coalesced
     float stage[MODE == MODE_BASIS ? (32 * (SH::TS + 1) > 64 * (kWChunk + 1) ? 32 * (SH::TS + 1) : 64 * (kWChunk + 1)) : 1];
     long long poff[MODE == MODE_BASIS ? 64 : 1];
@@ -302,7 +308,7 @@ THB_DEV void issue_chunk(const thb_space_desc& sp, const Item& it, int c0, int n
 // groups read G different (bank-staggered) tile rows with one LDS and their partial sums are combined by shuffles.
 template <class SH, int PPT, int G, int CPD, int MODE, bool DER>
 THB_DEV void warp_points(const thb_space_desc& sp, const Args& ar, const Item& it, int base, int ntile, bool cellnet,
-                         WarpSmem<SH, MODE>& sm, int tb, int pb) {
+                         WarpSmem<SH, MODE, DER>& sm, int tb, int pb) {
     static_assert(G == 1 || (PPT == 1 && MODE == MODE_FUSED), "support split: one point per lane, fused mode only");
     constexpr int T = SH::T, TS = SH::TS, NP = SH::NP, NQ = SH::NQ;
     constexpr int NPT = 32 / G;                // points per pass
@@ -342,6 +348,7 @@ THB_DEV void warp_points(const thb_space_desc& sp, const Args& ar, const Item& i
     if (MODE == MODE_BASIS) __syncwarp();
     for (int chi = 0; chi < ar.nch; ++chi) {
         const int ch = ar.channels[chi];
+        const bool use_rel = DER && MODE == MODE_FUSED && ch != 0 && !cellnet && cc_all;  // see WarpSmem::cpw_rel
         f32x2 tp2[PPT][NP];
 #pragma unroll
         for (int q = 0; q < PPT; ++q) {
@@ -376,7 +383,7 @@ THB_DEV void warp_points(const thb_space_desc& sp, const Args& ar, const Item& i
                 f32x2 a[PPT][2];
 #pragma unroll
                 for (int q = 0; q < PPT; ++q) a[q][0] = a[q][1] = 0ull;
-                const ulonglong2* col = reinterpret_cast<const ulonglong2*>(sm.cpw[tb][k]);
+                const ulonglong2* col = reinterpret_cast<const ulonglong2*>(use_rel ? sm.cpw_rel[k] : sm.cpw[tb][k]);
 #pragma unroll
                 for (int m = 0; m < NQ; ++m) {
                     const ulonglong2 cv = col[m];
@@ -406,7 +413,7 @@ THB_DEV void warp_points(const thb_space_desc& sp, const Args& ar, const Item& i
                 if (MODE == MODE_FUSED && !cc_all) gather_cc<CPD>(sp, ar, it, c0, ns, sm.cc);
                 __syncwarp();
                 const float* tbuf = sm.tiles[buf];
-                const float4* ccp = sm.cc + (cc_all ? c0 : 0);
+                const float4* ccp = (use_rel ? sm.cc_rel : sm.cc) + (cc_all ? c0 : 0);
 THB_PRAGMA(unroll THB_SUNROLL)
                 for (int s0 = 0; s0 < ns; s0 += G) {
                     const bool s_on = G == 1 || s0 + grp < ns;
@@ -482,7 +489,7 @@ __global__ void __launch_bounds__(kThreads, THB_TILE_MINB) k_tile(const __grid_c
     using SH = Shp<N0, N1, N2>;
     constexpr int TS = SH::TS, NQ = SH::NQ;
     constexpr int SB = 32 * PPT;
-    __shared__ __align__(16) WarpSmem<SH, MODE> sm;
+    __shared__ __align__(16) WarpSmem<SH, MODE, DER> sm;
 
     const int lane = threadIdx.x;
     const int nitems = ar.counters[0];
@@ -521,7 +528,26 @@ __global__ void __launch_bounds__(kThreads, THB_TILE_MINB) k_tile(const __grid_c
             }
         }
         if (MODE == MODE_FUSED && ntile > 0 && ntile <= kMaxCC) gather_cc<CPD>(sp, ar, it, 0, ntile, sm.cc);
+        if (MODE == MODE_FUSED && DER && lane < 4) {
+            // reference point: the control point of the item's first support
+            const int64_t r = __ldg(sp.supp_jm + it.soff);
+            sm.ref[lane] = (lane < CPD && it.S > 0) ? __ldg(ar.ctrl_pts + r * CPD + lane) : 0.f;
+        }
         __syncwarp();
+        if (MODE == MODE_FUSED && DER) {
+            for (int t = lane; t < TS; t += 32) {
+                const bool on = it.ndir > 0 && t < SH::T && ((it.dm >> t) & 1ull);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) sm.cpw_rel[k][t] = on ? sm.cpw[tb][k][t] - sm.ref[k] : 0.f;
+            }
+            if (ntile <= kMaxCC) {
+                for (int s = lane; s < ntile; s += 32) {
+                    const float4 c = sm.cc[s];
+                    sm.cc_rel[s] = make_float4(c.x - sm.ref[0], c.y - sm.ref[1], c.z - sm.ref[2], c.w - sm.ref[3]);
+                }
+            }
+            __syncwarp();
+        }
         if (cellnet) {
             for (int c0 = 0; c0 < ntile; c0 += kWChunk) {
                 const int ns = min(kWChunk, ntile - c0);
