@@ -92,3 +92,22 @@ def test_legacy_dict_input():
     supp, ns = core.compute_active_span(g["params"], h.knotvectors, h.cells, h.degrees, d)
     assert np.array_equal(np.asarray(ns), g["num_supp"])
     assert np.array_equal(supp.Jm().cpu().numpy(), g["Jm"])
+
+
+def test_reference_named_aliases():
+    from thb_diff_b200 import bspline_funcs as B
+    from thb_diff_b200 import core
+
+    k = dict(np.load(f"{GOLDEN}/kat.npz"))
+    assert B.findSpan(9, 3, 0.45, k["U_B"]) == 5
+    assert np.allclose(B.basisFun(5, 0.45, 3, k["U_B"]), k["N_045"], atol=2e-6)
+    assert np.allclose(B.basisFun_jax(0.45, k["U_B"], 3).cpu().numpy()[0], k["N_045"], atol=2e-6)
+    g = load_golden("block2d")
+    h = product_space_from_golden(g)
+    ac = core.compute_active_cells_active_supp(h.cells, h.fns, h.degrees)
+    fc = core.compute_refinement_operators(h.fns, h.Coeff, h.degrees)
+    spans, ns, supp = core.compute_active_span_v2(g["params"], h.knotvectors, h.cells, h.degrees, ac, fc)
+    assert [s[0] for s in spans] == g["span_level"].tolist()
+    PHI = core.THB_basis_fns_tp_parallel(g["params"], supp, fc, h.sh_fns, h.knotvectors, h.degrees)
+    PHI2, ns2 = core.compute_THB_fns_tp(g["params"], spans, ac, fc, h.sh_fns, h.knotvectors, h.degrees)
+    assert np.abs(PHI.cpu().numpy() - g["PHI"]).max() < 1e-5 and torch.equal(PHI, PHI2)

@@ -87,3 +87,8 @@ def compute_tensor_product(args):
     if len(a) == 2:
         return torch.einsum("i,j->ij", *a)
     return torch.einsum("i,j,k->ijk", *a)
+
+
+def basisFun_jax(param, knotvector, degree):
+    """[THB/bspline_funcs.py:149-182] the degree+1 non-vanishing basis values of one parameter, shape [1, p+1]."""
+    return basis_fns_vmap(np.atleast_1d(np.asarray(param, dtype=np.float32)).reshape(-1)[:1], knotvector, degree)

@@ -333,3 +333,9 @@ def compute_THB_fns_tp(params, ac_spans, ac_cells_supp, fn_coeffs, fn_shapes, kn
     cells = ac_cells_supp.cells
     supp, ns = compute_active_span(params, knotvectors, cells, degrees, ac_cells_supp)
     return THB_basis_fns(params, supp, ns, fn_coeffs, fn_shapes, knotvectors, degrees), ns
+
+
+def THB_basis_fns_tp_parallel(params, ac_cells_supp, fn_coeffs, fn_shapes, knotvectors, degrees):
+    """[THB/core.py:573-601] the reference's process-pool variant of the basis loop; here the same GPU kernel
+    as THB_basis_fns (`ac_cells_supp` is the per-point support object of compute_active_span)."""
+    return THB_basis_fns(params, ac_cells_supp, getattr(ac_cells_supp, "num_supp", None), fn_coeffs, fn_shapes, knotvectors, degrees)
