@@ -69,10 +69,70 @@ __global__ void __launch_bounds__(256) k_fma_peak(int iters, float* sink) {
     }
 }
 
+// Synthetic replica of the tile loop of thb_tile_impl.cuh: PPT points per lane whose 64-entry tensor product
+// sits in registers as 32 f32x2 pairs, 16 tile rows in shared memory read with broadcast LDS.128, FFMA2.
+// One warp per CTA; `smem_pad` bytes of dynamic shared memory cap the number of resident warps per SM.
+// It measures what this loop STRUCTURE can reach on the FMA pipe, without any of the surrounding work.
+template <int PPT>
+__global__ void __launch_bounds__(32) k_tile_loop_probe(int iters, float* sink) {
+    extern __shared__ __align__(16) float dyn[];
+    __shared__ __align__(16) float tiles[16 * 68];
+    for (int i = threadIdx.x; i < 16 * 68; i += 32) tiles[i] = 1.0f / (1.0f + i);
+    if (dyn == nullptr) tiles[0] = 0.f;
+    __syncwarp();
+    f32x2 tp2[PPT][32];
+#pragma unroll
+    for (int q = 0; q < PPT; ++q)
+#pragma unroll
+        for (int m = 0; m < 32; ++m) tp2[q][m] = pack2(threadIdx.x * 1e-3f + m, q + 0.5f * m);
+    float acc[PPT] = {};
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll 2
+        for (int s = 0; s < 16; ++s) {
+            const ulonglong2* row = reinterpret_cast<const ulonglong2*>(tiles + s * 68);
+            f32x2 a[PPT][2];
+#pragma unroll
+            for (int q = 0; q < PPT; ++q) a[q][0] = a[q][1] = 0ull;
+#pragma unroll
+            for (int m = 0; m < 16; ++m) {
+                const ulonglong2 tv = row[m];
+#pragma unroll
+                for (int q = 0; q < PPT; ++q) {
+                    ffma2(a[q][0], tp2[q][2 * m], tv.x);
+                    ffma2(a[q][1], tp2[q][2 * m + 1], tv.y);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < PPT; ++q) acc[q] += hsum2(a[q][0]) + hsum2(a[q][1]);
+        }
+    }
+    float t = 0;
+#pragma unroll
+    for (int q = 0; q < PPT; ++q) t += acc[q];
+    if (t == 12345.678f) sink[0] = t;
+}
+
 extern "C" int thb_fma_peak(int variant, int iters, float* sink, double* flops_out_host, void* stream) {
     THB_REQUIRE(sink && iters > 0, "thb_fma_peak: bad arguments");
     const int ctas = thb_num_sms() * 8;
     cudaStream_t st = (cudaStream_t)stream;
+    if (variant >= 2) {
+        // 2: PPT=2 / 8 warps per SM, 3: PPT=1 / 8 warps, 4: PPT=1 / 16 warps, 5: PPT=2 / 4 warps
+        const int ppt = (variant == 2 || variant == 5) ? 2 : 1;
+        const int warps = variant == 4 ? 16 : (variant == 5 ? 4 : 8);
+        const int pad = (200 * 1024) / warps - 5 * 1024;  // dynamic smem so that exactly `warps` CTAs fit per SM
+        const int grid = thb_num_sms() * warps;
+        if (ppt == 2) {
+            cudaFuncSetAttribute(k_tile_loop_probe<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
+            k_tile_loop_probe<2><<<grid, 32, pad, st>>>(iters, sink);
+        } else {
+            cudaFuncSetAttribute(k_tile_loop_probe<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
+            k_tile_loop_probe<1><<<grid, 32, pad, st>>>(iters, sink);
+        }
+        if (flops_out_host) *flops_out_host = 2.0 * 2 * 32 * 16 * ppt * double(iters) * 32.0 * grid;
+        THB_LAUNCHED();
+        return THB_OK;
+    }
     if (variant == 0) {
         k_fma_peak<0><<<ctas, 256, 0, st>>>(iters, sink);
         if (flops_out_host) *flops_out_host = 2.0 * 16 * double(iters) * 256.0 * ctas;
