@@ -152,3 +152,47 @@ def test_host_pipeline_matches_device_path():
         torch.cuda.synchronize()
         # same points, possibly a different sub-batch path (summation order) than in the one-shot plan
         assert float((out.cuda() - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
+
+
+@pytest.mark.parametrize("n", [0, 1, 33])
+def test_tiny_batches(n):
+    """empty / single-point / ragged batches through the whole pipeline (plan, PHI, fused forward + backward)"""
+    from thb_diff_b200 import core, engine
+    from thb_diff_b200.packed import PackedHierarchy
+
+    g = load_golden("block3d")
+    h = product_space_from_golden(g)
+    P = PackedHierarchy.from_space(h, device="cuda")
+    prm = g["params"][:n].astype(np.float32).reshape(n, 3)
+    supp, ns = core.compute_active_span(prm, h.knotvectors, h.cells, h.degrees, P)
+    PHI = core.THB_basis_fns(prm, supp, ns, P, h.sh_fns, h.knotvectors, h.degrees)
+    nnz = int(g["num_supp"][:n].sum())
+    assert len(ns) == n and PHI.shape == (nnz,)
+    assert rel_err(PHI.cpu().numpy(), g["PHI"][:nnz]).max(initial=0.0) <= TOL
+    cp = torch.randn((P.nCP, 3), device="cuda")
+    out = engine.eval_fused(P, supp.plan, cp)[0]
+    assert out.shape == (n, 3)
+    grad = engine.eval_fused_backward(P, supp.plan, torch.ones((n, 3), device="cuda"))
+    assert grad.shape == (P.nCP, 3)
+    if n == 0:
+        assert float(grad.abs().max()) == 0.0
+    else:
+        ref = O.eval_forward(cp.cpu().numpy(), g["Jm"][:nnz], g["PHI"][:nnz], np.cumsum(g["num_supp"][:n]))
+        assert rel_err(out.cpu().numpy(), ref, scale=np.abs(ref).max()).max() <= TOL
+
+
+def test_domain_boundary_and_outside_points_fused():
+    """u == last knot evaluates in the last cell (reference span rule); outside / NaN points give zeros"""
+    from thb_diff_b200 import configs, engine
+    from thb_diff_b200.packed import PackedHierarchy
+
+    g = load_golden("block3d")
+    h = product_space_from_golden(g)
+    P = PackedHierarchy.from_space(h, device="cuda")
+    prm = np.array([[1.0, 1.0, 1.0], [0.0, 0.0, 0.0], [1.0, 0.3, 0.0], [1.5, 0.5, 0.5], [np.nan, 0.1, 0.1], [0.5, -1e-6, 0.5]], dtype=np.float32)
+    plan = engine.Plan(P, prm)
+    cp = torch.from_numpy(configs.greville_ctrl_pts(h, bump=0.0)).cuda()
+    out = engine.eval_fused(P, plan, cp)[0].cpu().numpy()
+    assert np.abs(out[:3] - prm[:3]).max() < 1e-6      # linear reproduction right at the boundary
+    assert np.all(out[3:] == 0.0)                       # out-of-domain points: flagged (slot -1), zero output
+    assert plan.slot[:6].cpu().numpy()[3:].tolist() == [-1, -1, -1]
