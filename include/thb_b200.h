@@ -60,6 +60,14 @@ typedef struct thb_space_desc {
     const uint64_t* dmask;                  /* [nslots] own-level window activity bits */
     const int32_t* supp_jm;                 /* CSR values: flat ids of each cell's supports, reference order */
     const float* tiles;                     /* [ntiles][tile_stride] */
+    const int32_t* span_lut;                /* optional (may be NULL): per dimension lut_n[k] uniform bins over the domain;
+                                               entry = finest-level cell that contains the bin's left edge */
+    int32_t lut_off[3];
+    int32_t lut_n[3];
+    float lut_scale[3];                     /* bins per unit parameter: bin = (u - U[p]) * lut_scale */
+    int32_t pad_;
+    const int32_t* finest_slot;             /* optional (may be NULL): per FINEST-level cell the slot of the active cell
+                                               that contains it (-1 if none) -- one lookup instead of one per level */
 } thb_space_desc;
 
 /* A plan = the points of one batch grouped by active cell. All arrays are caller-allocated device memory:

@@ -79,23 +79,48 @@ __global__ void __launch_bounds__(256) k_expand_supports(const __grid_constant__
 // Finest-level span with the knots of that level staged in shared memory.  First guess from a uniform
 // partition, corrected by walking (exact for 'uniform-ish' knots in <= 2 steps), binary search otherwise;
 // the result is the same span as span_right() for every in-domain u.
-// `scale` = nc / (U[p+nc] - U[p]); u0 = U[p], u1 = U[p+nc] (kept in registers by the caller).
-THB_DEV int finest_cell(const float* U, int p, int nc, float scale, float u0, float u1, float u) {
-    // U[p .. p+nc] are the breakpoints; cell c <=> U[p+c] <= u < U[p+c+1]
+// Finest-level cell of u.  B = finest breakpoints (B[i] = U[p+i]) in shared memory, nc0 level-0 cells, L levels
+// above level 0.  Levels are dyadically nested with bit-identical breakpoints and the refinement inserts
+// midpoints, so inside a level-0 cell the finest breakpoints are uniform up to rounding: guess the level-0 cell
+// from the uniform partition (corrected by one if needed), then the sub-cell by linear interpolation, and VERIFY
+// against the two bracketing breakpoints; a one-step correction and finally a binary search catch every other
+// knot vector.  The verified result is exactly searchsorted(U, u, 'right') - 1 - p, with the reference's rule
+// that u == U[-1] belongs to the last cell (THB/bspline_funcs.py:77-83).
+THB_DEV float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+THB_DEV int finest_cell(const float* B, int nc0, int L, float scale0, float u0, float u1, float u) {
     if (!(u >= u0) || u > u1) return -1;  // also rejects NaN
-    int c = min((int)((u - u0) * scale), nc - 1);
-    if (u >= U[p + c] && u < U[p + c + 1]) return c;  // common case: two shared-memory reads
-    if (u == u1) return nc - 1;                       // reference rule for the last knot
-    // one step off (jittered knots), else binary search on the breakpoints
-    c += (u >= U[p + c + 1]) ? 1 : -1;
-    c = min(max(c, 0), nc - 1);
-    if (u >= U[p + c] && u < U[p + c + 1]) return c;
-    int lo = 0, hi = nc;  // invariant: U[p+lo] <= u < U[p+hi]
+    const int nc = nc0 << L;
+    // level-0 cell: uniform guess, branch-free correction by one
+    int c0 = min((int)((u - u0) * scale0), nc0 - 1);
+    c0 = min(max(c0 + (int)(u >= B[(c0 + 1) << L]) - (int)(u < B[c0 << L]), 0), nc0 - 1);
+    const float lo0 = B[c0 << L], hi0 = B[(c0 + 1) << L];
+    // sub-cell by linear interpolation (the guess only has to be close: it is verified below)
+    const int f = min(max((int)((u - lo0) * rcp_approx(hi0 - lo0) * (float)(1 << L)), 0), (1 << L) - 1);
+    int c = (c0 << L) + f;
+    c = min(max(c + (int)(u >= B[c + 1]) - (int)(u < B[c]), 0), nc - 1);  // rounding of the guess: one step at most
+    if (u >= B[c] && (u < B[c + 1] || c == nc - 1)) return c;            // verified: taken by (almost) every point
+    if (u == u1) return nc - 1;
+    int lo = 0, hi = nc;  // arbitrary knot vectors: binary search, invariant B[lo] <= u < B[hi]
     while (hi - lo > 1) {
         const int mid = (lo + hi) >> 1;
-        if (U[p + mid] <= u) lo = mid; else hi = mid;
+        if (B[mid] <= u) lo = mid; else hi = mid;
     }
     return lo;
+}
+
+// Same result through a lookup table: bins at most 0.4 finest cells wide, lut[bin] = cell of the bin's left edge,
+// so the cell of u is lut[bin] or the next one.  Verified like above; any miss falls back to finest_cell().
+THB_DEV int finest_cell_lut(const float* B, const int32_t* __restrict__ lut, int nbins, float lscale, int nc, float u0, float u1, float u) {
+    if (!(u >= u0) || u > u1) return -1;
+    int c = __ldg(lut + min((int)((u - u0) * lscale), nbins - 1));
+    c = min(c + (int)(u >= B[c + 1]), nc - 1);
+    if (u >= B[c] && (u < B[c + 1] || c == nc - 1)) return c;
+    return -2;  // not verified
 }
 
 constexpr int kPlanSmemKnots = 3 * 1024;
@@ -103,7 +128,8 @@ constexpr int kPlanSmemKnots = 3 * 1024;
 // slot of a point given the finest-level knots in shared memory; the cell_slot entries of ALL levels are
 // fetched at once (independent loads) and the finest active one is selected.
 struct PlanKnots {
-    int off[3];  // offsets of the finest knot vectors inside the shared-memory copy
+    int off[3];  // offset of the first BREAKPOINT (knot p) of each finest knot vector inside the shared-memory copy
+    int nc0[3];  // level-0 cells
     float scale[3], u0[3], u1[3];
 };
 
@@ -113,10 +139,18 @@ THB_DEV int locate_slot_fast(const thb_space_desc& sp, const float* sk, const Pl
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         if (k < sp.ndim) {
-            const int c = finest_cell(sk + pk.off[k], sp.degree[k], sp.ncells[L][k], pk.scale[k], pk.u0[k], pk.u1[k], u[k]);
+            int c = -2;
+            if (sp.span_lut)
+                c = finest_cell_lut(sk + pk.off[k], sp.span_lut + sp.lut_off[k], sp.lut_n[k], sp.lut_scale[k], pk.nc0[k] << L, pk.u0[k], pk.u1[k], u[k]);
+            if (c == -2) c = finest_cell(sk + pk.off[k], pk.nc0[k], L, pk.scale[k], pk.u0[k], pk.u1[k], u[k]);
             if (c < 0) return -1;
             cf[k] = c;
         }
+    }
+    if (sp.finest_slot) {  // one lookup: finest cell -> slot of the active cell that contains it
+        int lin = cf[0] * sp.ncells[L][1] + cf[1];
+        if (sp.ndim == 3) lin = lin * sp.ncells[L][2] + cf[2];
+        return __ldg(sp.finest_slot + lin);
     }
     // independent lookups at every level (issued back to back), finest active one wins
     int slot = -1;
@@ -141,15 +175,17 @@ THB_DEV bool stage_finest_knots(const thb_space_desc& sp, float* sk, PlanKnots& 
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         pk.off[k] = 0;
+        pk.nc0[k] = 1;
         pk.scale[k] = pk.u0[k] = pk.u1[k] = 0.f;
         if (k < sp.ndim && fits) {
             const float* g = sp.knots + sp.knot_off[L][k];
             const int p = sp.degree[k], nc = sp.ncells[L][k];
             for (int i = threadIdx.x; i < sp.knot_len[L][k]; i += blockDim.x) sk[pos + i] = g[i];
-            pk.off[k] = pos;
+            pk.off[k] = pos + p;
+            pk.nc0[k] = sp.ncells[0][k];
             pk.u0[k] = g[p];
             pk.u1[k] = g[p + nc];
-            pk.scale[k] = (float)nc / (pk.u1[k] - pk.u0[k]);
+            pk.scale[k] = (float)pk.nc0[k] / (pk.u1[k] - pk.u0[k]);
             pos += sp.knot_len[L][k];
         }
     }

@@ -120,6 +120,36 @@ class PackedHierarchy:
                 lin = np.ravel_multi_index(tuple(act_idx[l].T), sh_cells[l])
                 cell_slot[cs_off[l] + lin] = slot_base[l] + np.arange(len(lin))
         self.cell_slot_off, self.nslots = cs_off, nslots
+        # span lookup tables of the finest level: uniform bins at most 0.4 cells wide; entry = cell of the bin's left
+        # edge, so the true cell of a point is that cell or the next one (the kernel compares once and verifies)
+        lut_parts, lut_off, lut_n, lut_scale = [], [0, 0, 0], [0, 0, 0], [0.0, 0.0, 0.0]
+        lpos = 0
+        for k in range(d):
+            Bk = kv[L - 1][k].astype(np.float32).astype(np.float64)[p[k]:len(kv[L - 1][k]) - p[k]]
+            nb = int(np.ceil(2.5 * (Bk[-1] - Bk[0]) / np.min(np.diff(Bk))))
+            if nb > 8192:
+                lut_parts = None
+                break
+            sc = np.float32(nb / (Bk[-1] - Bk[0]))
+            left = Bk[0] + (np.arange(nb) - 0.05) / float(sc)
+            lut_parts.append(np.clip(np.searchsorted(Bk, left, side="right") - 1, 0, len(Bk) - 2).astype(np.int32))
+            lut_off[k], lut_n[k], lut_scale[k] = lpos, nb, float(sc)
+            lpos += nb
+        self._lut = (np.concatenate(lut_parts), lut_off, lut_n, lut_scale) if lut_parts else None
+        # finest-cell -> active-slot map (every finest cell lies in exactly one active cell): lets the kernels
+        # find a point's cell with ONE lookup instead of one per level.  Skipped for very deep hierarchies.
+        finest_map = None
+        if int(np.prod(sh_cells[L - 1])) <= (1 << 26):
+            finest_map = np.full(sh_cells[L - 1], -1, dtype=np.int32)
+            for l in range(L):
+                if not len(act_idx[l]):
+                    continue
+                grid = cell_slot[cs_off[l]:cs_off[l] + int(np.prod(sh_cells[l]))].reshape(sh_cells[l])
+                f = 1 << (L - 1 - l)
+                up = grid
+                for k in range(d):
+                    up = np.repeat(up, f, axis=k)
+                np.maximum(finest_map, up, out=finest_map)
 
         # ---- admissibility: no active level-(l+1) function may overlap an active level-l cell
         fmask = {l: (np.asarray(fns[l]) == 1) for l in range(L)}
@@ -199,6 +229,8 @@ class PackedHierarchy:
         self.device = dev
         self.knots = torch.from_numpy(knots).to(dev)
         self.cell_slot = torch.from_numpy(cell_slot).to(dev)
+        self.finest_slot = torch.from_numpy(finest_map.reshape(-1)).to(dev) if finest_map is not None else None
+        self.span_lut = torch.from_numpy(self._lut[0]).to(dev) if self._lut is not None else None
         self.cellinfo = torch.from_numpy(info).to(dev)
         self.dmask = torch.from_numpy(dmask.view(np.int64)).to(dev)
         self.supp_jm = torch.from_numpy(supp_jm).to(dev)
@@ -275,7 +307,8 @@ class PackedHierarchy:
 
     # ------------------------------------------------------------------------------------------
     def nbytes(self):
-        return sum(t.numel() * t.element_size() for t in (self.knots, self.cell_slot, self.cellinfo, self.dmask, self.supp_jm, self.tiles))
+        ts = [self.knots, self.cell_slot, self.cellinfo, self.dmask, self.supp_jm, self.tiles] + ([self.finest_slot] if self.finest_slot is not None else [])
+        return sum(t.numel() * t.element_size() for t in ts)
 
     def summary(self):
         return dict(ndim=self.ndim, levels=self.nlevels, degrees=self.degrees, nslots=self.nslots, nCP=self.nCP,
@@ -308,6 +341,11 @@ def _desc(self):
         d.fn_off[l] = int(self.fn_off[l])
     d.knots, d.cell_slot, d.cellinfo = self.knots.data_ptr(), self.cell_slot.data_ptr(), self.cellinfo.data_ptr()
     d.dmask, d.supp_jm, d.tiles = self.dmask.data_ptr(), self.supp_jm.data_ptr(), self.tiles.data_ptr()
+    d.finest_slot = self.finest_slot.data_ptr() if self.finest_slot is not None else None
+    d.span_lut = self.span_lut.data_ptr() if self.span_lut is not None else None
+    if self.span_lut is not None:
+        for k in range(self.ndim):
+            d.lut_off[k], d.lut_n[k], d.lut_scale[k] = self._lut[1][k], self._lut[2][k], self._lut[3][k]
     self._desc_cache = d
     return d
 
