@@ -89,3 +89,37 @@ def test_active_supports_dict_view_matches_reference_order():
         assert len(ac[lev]) == len(ref[lev])
         for cell in list(ref[lev])[:20]:
             assert ac[lev][cell] == ref[lev][cell]
+
+
+def test_update_cp_preserves_the_geometry():
+    """ControlPoints.update_CP (prolongation of control points on refinement).  The reference's own method
+    cannot run (its level offsets are not cumulative, multilevel_spline_space.py:166-176 -> reshape error), so
+    the intended semantics are pinned by their defining property: refining cells and prolonging the control
+    points leaves the geometry unchanged.  Evaluated on CPU with the C oracle on the packed tables."""
+    from helpers import host_tables_from_packed
+    from thb_diff_b200 import configs
+    from thb_diff_b200 import multilevel_spline_space as M
+    from thb_diff_b200.packed import PackedHierarchy
+
+    h = M.Space(M.TensorProduct([M.BSpline(configs.README_U0, 2), M.BSpline(configs.README_U1, 3)]), 4)
+    h.build_hierarchy_from_domain_sequence()
+    cps = M.ControlPoints(h)
+    rng = np.random.default_rng(9)
+    n = sum(int(np.prod(h.sh_fns[l])) for l in range(4))
+    CP = np.zeros((n, 2))
+    CP[: int(np.prod(h.sh_fns[0]))] = rng.standard_normal((int(np.prod(h.sh_fns[0])), 2))
+    prm = rng.random((4000, 2)).astype(np.float32)
+
+    def evaluate(cp):
+        P = PackedHierarchy.from_space(h, device="cpu")
+        cp3 = np.concatenate([cp, np.zeros((len(cp), 1))], axis=1).astype(np.float32)
+        return host_tables_from_packed(P).eval(prm, cp3)["out"][:, :2]
+
+    ref = evaluate(CP)
+    for lev, lo, hi in ((0, (1, 0), (9, 7)), (1, (6, 4), (14, 10))):   # graded nested boxes (SURVEY App. A)
+        h.refine_box(lo, hi, lev)
+        h.build_hierarchy_from_domain_sequence()
+        c = cps.update_CP(CP, h.fns, h.Coeff)
+        CP = np.concatenate([c[l].reshape(-1, 2) for l in range(4)])
+        assert np.abs(evaluate(CP) - ref).max() < 5e-6
+    assert {l: int(h.fns[l].sum()) for l in h.fns} == {0: 60, 1: 220, 2: 126, 3: 0}

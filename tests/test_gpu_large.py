@@ -129,3 +129,16 @@ def test_sharded_fit_reduces_loss(c3):
     fit = ShardedFit(P, prm, tgt, prm.shape[0])
     losses = [float(fit.step(x, opt)) for _ in range(30)]
     assert losses[-1] < 0.5 * losses[0]
+
+
+def test_adaptive_fit_example_improves_with_refinement():
+    """examples/adaptive_fit.py: fit -> refine -> prolong control points (ControlPoints.update_CP) -> refit."""
+    import importlib.util
+    import os
+
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "adaptive_fit.py")
+    spec = importlib.util.spec_from_file_location("adaptive_fit", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    losses = mod.main(steps=150, n=50_000, verbose=False)
+    assert losses[1] < losses[0] and losses[2] < losses[1]

@@ -170,3 +170,36 @@ class Space:
         self.cells[level - 1][tuple(cellIdx)] = 1
         for off in _iproduct(range(2), repeat=self.ndim):
             self.cells[level][tuple(2 * c + o for c, o in zip(parent, off))] = 0
+
+
+class ControlPoints:
+    """Control-point bookkeeping across refinements.  [reference: THB/multilevel_spline_space.py:154-188]
+
+    update_CP(CP_arr, fns, Coeffs): control points of functions that became active since the last call are
+    obtained by prolongation of the next coarser level (knot-insertion weights, separable per dimension);
+    all other rows are kept.  Returns {lev: ndarray [*sh_fns[lev], ndim]} like the reference.  Vectorised:
+    the prolongation of a whole level is one tensor contraction per dimension."""
+
+    def __init__(self, H_space):
+        self.h_space = H_space
+        self.max_lev = H_space.num_levels - 1
+        self.ndim = H_space.ndim
+        self.CP_status = {lev: np.zeros_like(H_space.fns[lev]) for lev in range(self.max_lev + 1)}
+        self.CP_status[0] = np.ones_like(self.CP_status[0])
+
+    def update_CP(self, CP_arr, fns, Coeffs):
+        CP_arr = np.asarray(CP_arr, dtype=np.float64)
+        sh = self.h_space.sh_fns
+        off = np.cumsum([0] + [int(np.prod(sh[lev])) for lev in range(self.max_lev + 1)])
+        cpd = CP_arr.shape[1]
+        ctrl = {lev: CP_arr[off[lev]:off[lev + 1]].reshape(*sh[lev], cpd).copy() for lev in range(self.max_lev + 1)}
+        for lev in range(1, self.max_lev + 1):
+            new = (np.asarray(self.CP_status[lev]) == 0) & (np.asarray(fns[lev]) == 1)
+            if not new.any():
+                continue
+            fine = ctrl[lev - 1]
+            for k in range(self.ndim):  # P[j] = sum_i Coeff[i, j] * P_coarse[i] along every dimension
+                fine = np.moveaxis(np.tensordot(fine, np.asarray(Coeffs[lev - 1][k], dtype=np.float64), axes=([k], [0])), -1, k)
+            ctrl[lev][new] = fine[new]
+        self.CP_status = {lev: np.array(fns[lev], copy=True) for lev in fns}
+        return ctrl
