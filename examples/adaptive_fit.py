@@ -27,7 +27,7 @@ def fit(space, cp, params, tgt, steps):
         loss = ((mod(x) - tgt) ** 2).mean()
         loss.backward()
         opt.step()
-    return x.detach(), float(loss)
+    return x.detach(), float(loss.detach())
 
 
 def main(steps=200, n=200_000, verbose=True):

@@ -84,3 +84,30 @@ def test_bench_space_partition_of_unity_and_linear_reproduction():
     assert np.abs(ht.eval(prm, ones)["out"] - 1).max() < 2e-6
     levels = P.cellinfo_host[r["slot"], 0]
     assert set(levels.tolist()) == {0, 1, 2, 3}
+
+
+def test_recursive_truncation_option():
+    """truncation='recursive' (proper THB) == the reference's single-level truncation on graded spaces, and
+    restores partition of unity / linear reproduction where single-level truncation loses them."""
+    from thb_diff_b200 import configs
+    from thb_diff_b200.packed import PackedHierarchy
+
+    rng = np.random.default_rng(0)
+    for name, graded in (("graded2d", True), ("block3d", True), ("twoblock2d", False)):
+        g = load_golden(name)
+        h = product_space_from_golden(g)
+        prm = rng.random((3000, h.ndim)).astype(np.float32)
+        res = {}
+        for tr in ("single", "recursive"):
+            P = PackedHierarchy.from_space(h, device="cpu", truncation=tr)
+            ht = host_tables_from_packed(P)
+            pou = np.abs(ht.eval(prm, np.ones((P.nCP, 3), dtype=np.float32))["out"][:, 0] - 1).max()
+            lin = np.abs(ht.eval(prm, configs.greville_ctrl_pts(h, bump=0.0))["out"][:, :h.ndim] - prm).max()
+            res[tr] = (P.tiles.numpy(), pou, lin)
+        assert res["recursive"][1] < 1e-6 and res["recursive"][2] < 1e-6
+        if graded:
+            assert np.array_equal(res["single"][0], res["recursive"][0])
+        else:
+            assert res["single"][1] > 0.3   # the reference's behaviour on this non-graded space
+    with pytest.raises(ValueError):
+        PackedHierarchy.from_space(h, device="cpu", truncation="both")

@@ -39,15 +39,15 @@ class PackedHierarchy:
 
     # ------------------------------------------------------------------------------------------
     @classmethod
-    def from_space(cls, space, device="cuda", onehot_direct=True, chunk=1 << 18):
+    def from_space(cls, space, device="cuda", onehot_direct=True, chunk=1 << 18, truncation="single"):
         if space.fns is None:
             raise ValueError("call Space.build_hierarchy_from_domain_sequence() first")
         return cls.build(space.knotvectors, space.degrees, space.cells, space.fns, space.Coeff,
-                         device=device, onehot_direct=onehot_direct, chunk=chunk)
+                         device=device, onehot_direct=onehot_direct, chunk=chunk, truncation=truncation)
 
     @classmethod
     def build(cls, knotvectors, degrees, cells, fns, Coeff=None, device="cuda", onehot_direct=True, chunk=1 << 18,
-              build_device=None):
+              build_device=None, truncation="single"):
         self = cls()
         L = max(knotvectors.keys()) + 1
         d = len(degrees)
@@ -62,6 +62,9 @@ class PackedHierarchy:
         TS = _ceil4(T)
         self.ndim, self.nlevels, self.degrees, self.T, self.TS = d, L, p, T, TS
         self.onehot_direct = bool(onehot_direct)
+        if truncation not in ("single", "recursive"):
+            raise ValueError("truncation must be 'single' (the reference's, THB/core.py:98-111) or 'recursive'")
+        self.truncation = truncation
         bdev = torch.device(build_device) if build_device is not None else torch.device(device)
 
         kv = {l: [np.asarray(U, dtype=np.float64) for U in knotvectors[l]] for l in range(L)}
@@ -243,6 +246,38 @@ class PackedHierarchy:
         return self
 
 
+    def _recursive_tiles(self, lev, l, c_, f_, Ct, fmask, ar, bdev):
+        """Tiles under the PROPER (recursive) truncation: the level-l function is written in level l+1, the active
+        level-(l+1) functions are removed, the rest is refined to level l+2, the active level-(l+2) functions are
+        removed, ... up to the cell's level.  Everything stays inside the (p+1)^d window of the cell's ancestors:
+        a function that is non-zero on the cell only has parents that are non-zero on it."""
+        d, p, T, TS = self.ndim, self.degrees, self.T, self.TS
+        m = len(c_)
+        let = "abc"[:d]
+
+        def window_mask(level, a):
+            idx = [a[:, k, None] + ar[k][None, :] for k in range(d)]
+            fm = torch.as_tensor(fmask[level], device=bdev)
+            if d == 2:
+                return fm[idx[0][:, :, None], idx[1][:, None, :]]
+            return fm[idx[0][:, :, None, None], idx[1][:, None, :, None], idx[2][:, None, None, :]]
+
+        # level l+1: subdivision weights of function f in the window of the cell's level-(l+1) ancestor
+        a = c_ >> (lev - (l + 1))
+        W = [Ct[(l, k)][f_[:, k, None], a[:, k, None] + ar[k][None, :]] for k in range(d)]
+        w = torch.einsum(",".join("m" + x for x in let) + "->m" + let, *W)
+        w = w * (~window_mask(l + 1, a)).to(w.dtype)
+        for lv in range(l + 2, lev + 1):
+            a_prev, a = a, c_ >> (lev - lv)
+            # local blocks of the 1-D subdivision matrices: rows = previous window, columns = this window
+            blocks = [Ct[(lv - 1, k)][(a_prev[:, k, None] + ar[k][None, :])[:, :, None], (a[:, k, None] + ar[k][None, :])[:, None, :]] for k in range(d)]
+            up = "xyz"[:d]
+            w = torch.einsum("m" + let + "," + ",".join("m" + x + y for x, y in zip(let, up)) + "->m" + up, w, *blocks)
+            w = w * (~window_mask(lv, a)).to(w.dtype)
+        t = torch.zeros((m, TS), dtype=torch.float32, device=bdev)
+        t[:, :T] = w.reshape(m, T).to(torch.float32)
+        return t
+
     def attach_tiles(self, Coeff):
         """Computes the coefficient tiles of the coarser-level supports from the 1-D subdivision matrices
         Coeff[lev][dim] ([nfns(lev), nfns(lev+1)], reference multilevel_spline_space.py:78-92)."""
@@ -278,6 +313,9 @@ class PackedHierarchy:
                         lin = lin * (p[k] + 1) + loc[:, k]
                     t[torch.arange(len(g_), device=bdev), lin] = 1.0
                     tiles[g_] = t
+                    continue
+                if self.truncation == "recursive":
+                    tiles[g_] = self._recursive_tiles(lev, l, c_, f_, Ct, fmask, ar, bdev)
                     continue
                 A = [Rt[(k, l, lev)][f_[:, k, None], c_[:, k, None] + ar[k][None, :]] for k in range(d)]
                 tile = torch.einsum(es_u, *A)
