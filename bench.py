@@ -31,13 +31,17 @@ def cdb_flops(p):
     return sum(2 + 5 * j for j in range(1, p + 1))
 
 
-def flop_model(degrees, cpd, n_in, nnz, nnz_tiled):
-    """(executed FLOPs of the hybrid algorithm, FLOPs of SURVEY 8d's dense gather-multiply model)"""
+def flop_model(degrees, cpd, n_in, nnz, nnz_tiled, nnz_sep=0):
+    """(executed FLOPs of the kernel's algorithm, FLOPs of SURVEY 8d's dense gather-multiply model).
+    Executed: per point Cox-de Boor + tensor product + cp_dim window dot products (own-level supports);
+    per (point, rank-one tiled support) one (p_k+1)-dot per dimension, two multiplications, the contraction;
+    per (point, full-tile support) a (p+1)^d dot and the contraction."""
     d = len(degrees)
     T = int(np.prod([p + 1 for p in degrees]))
     tp = (degrees[0] + 1) * (degrees[1] + 1) + (T if d == 3 else 0)
     per_pt = sum(cdb_flops(p) for p in degrees) + tp
-    executed = n_in * (per_pt + cpd * 2 * T) + nnz_tiled * (2 * T + 2 * cpd)
+    sep = 2 * sum(p + 1 for p in degrees) + (d - 1) + 2 * cpd
+    executed = n_in * (per_pt + cpd * 2 * T) + nnz_sep * sep + (nnz_tiled - nnz_sep) * (2 * T + 2 * cpd)
     dense = n_in * per_pt + nnz * (2 * T + 2 * cpd)
     return float(executed), float(dense)
 
@@ -322,7 +326,9 @@ def main():
     sp, P, params, cp = build_workload(rank, world, device, dense_tables=args.dense)
     n = params.shape[0]
     plan = engine.Plan(P, params)
-    n_in, nnz, nnz_tiled = plan.stats()
+    n_in, nnz, nnz_tiled, nnz_sep = plan.stats(with_sep=True)
+    if args.dense or args.cellnet:
+        nnz_sep = 0 if args.dense else nnz_sep
     out = [torch.zeros((n, 3), dtype=torch.float32, device=device)]
     st = torch.cuda.current_stream()
 
@@ -405,13 +411,14 @@ def main():
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    f_exec, f_dense = flop_model(P.degrees, 3, n_in, nnz, nnz_tiled)
+    f_exec, f_dense = flop_model(P.degrees, 3, n_in, nnz, nnz_tiled, nnz_sep)
     if args.cellnet:  # per point only the window dot products; tiles are folded once per work item
         cnt = plan.cell_count[: P.nslots].long()
         nt = (P.cellinfo[:, 5] - P.cellinfo[:, 7]).long()
         items = (cnt + engine.POINTS_PER_ITEM - 1) // engine.POINTS_PER_ITEM
         f_exec = flop_model(P.degrees, 3, n_in, 0, 0)[0] + float((items * nt).sum()) * P.T * 2 * 4
-    alg_bytes = n * (4 * P.ndim + 4 * 3 + 4) + P.tiles.numel() * 4 + cp.numel() * 4
+    tile_bytes = (P.sep_vec.numel() + P.full_tiles.numel()) * 4 if (getattr(P, "sep_vec", None) is not None and not args.cellnet) else P.tiles.numel() * 4
+    alg_bytes = n * (4 * P.ndim + 4 * 3 + 4) + tile_bytes + cp.numel() * 4
     t_fp32 = f_exec / (fp32_peak * 1e12)
     t_hbm = alg_bytes / (hbm_peak * 1e9)
     t_roof = max(t_fp32, t_hbm)
@@ -438,9 +445,9 @@ def main():
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "C3: 3-D degree-3 THB, 4 active levels (~25% refined per level, graded), 256^3 param grid per GPU",
-                   "points_per_gpu": n, "nnz": nnz, "nnz_tiled": nnz_tiled, "mean_supports": nnz / max(n_in, 1), "nCP": P.nCP,
+                   "points_per_gpu": n, "nnz": nnz, "nnz_tiled": nnz_tiled, "nnz_tiled_rank_one": nnz_sep, "mean_supports": nnz / max(n_in, 1), "nCP": P.nCP,
                    "table_bytes": P.nbytes(), "l2": "inputs (201 MB params + 201 MB output per step) exceed the 126 MB L2",
-                   "tables": "dense one-hot tiles" if args.dense else "hybrid (own-level supports direct)", "cellnet": bool(args.cellnet),
+                   "tables": "dense one-hot tiles" if args.dense else "own-level supports direct, rank-one tiles as 3 factor vectors, full tiles otherwise", "cellnet": bool(args.cellnet),
                    "sharding": f"y planes round-robin over {world} rank(s), no collective"},
         "clocks": clk.summary(), "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": n * P.ndim * 4, "d2h_bytes_per_step": n * 3 * 4,
@@ -467,6 +474,13 @@ def main():
             return a.elapsed_time(b) / 5, float((o[0] - out[0]).abs().max())
 
         var = {}
+        if not args.dense and not args.cellnet and getattr(P, "sep_vec", None) is not None:
+            keep = (P.sep_vec, P._desc_cache)
+            P.sep_vec, P._desc_cache = None, None      # same tables without the rank-one split (every tiled support a full tile)
+            ms, dev = time_variant(P, False)
+            f_full = flop_model(P.degrees, 3, n_in, nnz, nnz_tiled, 0)[0]
+            var["all_full_tiles"] = {"kernel_ms": ms, "max_abs_diff_vs_headline": dev, "frac_of_fp32_roofline": (f_full / (fp32_peak * 1e12)) / (ms * 1e-3)}
+            P.sep_vec, P._desc_cache = keep[0], None
         ms, dev = time_variant(P, not args.cellnet)
         var["cellnet" if not args.cellnet else "per_point_phi"] = {"kernel_ms": ms, "max_abs_diff_vs_headline": dev}
         if not args.dense:

@@ -24,7 +24,7 @@ extern "C" {
 #endif
 
 #define THB_MAX_LEVELS 8
-#define THB_INFO_W 8 /* ints per cellinfo row: level, c0, c1, c2, supp_off, S, tile_off, n_direct */
+#define THB_INFO_W 12 /* ints per cellinfo row: level, c0, c1, c2, supp_off, S, tile_off, n_direct, sep_off, n_sep, full_off, 0 */
 
 enum {
     THB_OK = 0,
@@ -60,6 +60,14 @@ typedef struct thb_space_desc {
     const uint64_t* dmask;                  /* [nslots] own-level window activity bits */
     const int32_t* supp_jm;                 /* CSR values: flat ids of each cell's supports, reference order */
     const float* tiles;                     /* [ntiles][tile_stride] */
+    /* Split of each cell's tiled supports for the fused kernel: supports whose tile is rank one (an outer product of
+     * one (p_k+1)-vector per dimension -- every untruncated function and every function truncated across a flat face of
+     * a refinement region) are stored as 12 floats (3 x 4, zero padded), the rest as full tiles.  sep_off / n_sep /
+     * full_off of a cell are in cellinfo; n_full = S - n_direct - n_sep.  All four may be NULL (then `tiles` is used). */
+    const float* sep_vec;                   /* [nsep_total][12] */
+    const int32_t* sep_jm;                  /* [nsep_total] flat support ids */
+    const float* full_tiles;                /* [nfull_total][tile_stride] */
+    const int32_t* full_jm;                 /* [nfull_total] */
     const int32_t* span_lut;                /* optional (may be NULL): per dimension lut_n[k] uniform bins over the domain;
                                                entry = finest-level cell that contains the bin's left edge */
     int32_t lut_off[3];
@@ -73,8 +81,8 @@ typedef struct thb_space_desc {
 /* A plan = the points of one batch grouped by active cell. All arrays are caller-allocated device memory:
  *   slot [N] i32, perm [N] i32, sorted_params [N, ndim] f32 (the params in cell order: sorted_params[j] =
  *   params[perm[j]]), cell_count/cell_start/cell_cursor [nslots+1] i32,
- *   items [max_items][16] i32 (slot, begin, count, level, c0, c1, c2, supp_off, S, tile_off, n_direct, 0,
- *   dmask lo, dmask hi, 0, 0), counters [4] i32 (counters[0] = number of items).
+ *   items [max_items][16] i32 (slot, begin, count, level, c0, c1, c2, supp_off, S, tile_off, n_direct, n_sep,
+ *   dmask lo, dmask hi, sep_off, full_off), counters [4] i32 (counters[0] = number of items).
  * max_items >= N / points_per_item + nslots. */
 typedef struct thb_plan_desc {
     int64_t npoints;

@@ -11,7 +11,7 @@ MAXL = 8
 
 class OracleSpace(C.Structure):
     _fields_ = [
-        ("ndim", C.c_int32), ("nlevels", C.c_int32), ("degree", C.c_int32 * 3), ("tile_stride", C.c_int32),
+        ("ndim", C.c_int32), ("nlevels", C.c_int32), ("degree", C.c_int32 * 3), ("tile_stride", C.c_int32), ("info_w", C.c_int32),
         ("knot_off", (C.c_int32 * 3) * MAXL), ("knot_len", (C.c_int32 * 3) * MAXL), ("ncells", (C.c_int32 * 3) * MAXL),
         ("cell_slot_off", C.c_int64 * MAXL),
         ("knots", C.c_void_p), ("cell_slot", C.c_void_p), ("cellinfo", C.c_void_p), ("dmask", C.c_void_p),
@@ -53,6 +53,7 @@ class HostTables:
         self.keep = [np.ascontiguousarray(a) for a in (knots, cell_slot, cellinfo, dmask, supp_jm, tiles)]
         s = OracleSpace()
         s.ndim, s.nlevels, s.tile_stride = ndim, nlevels, tile_stride
+        s.info_w = int(self.keep[2].shape[1])
         for k in range(3):
             s.degree[k] = int(degrees[k]) if k < ndim else 0
         for l in range(nlevels):

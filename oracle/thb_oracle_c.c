@@ -95,11 +95,12 @@ void oracle_eval_backward(const float* go, const int64_t* jm, const float* phi, 
 
 typedef struct {
     int32_t ndim, nlevels, degree[3], tile_stride;
+    int32_t info_w; /* ints per cellinfo row (columns 0..7 are used here) */
     int32_t knot_off[MAXL][3], knot_len[MAXL][3], ncells[MAXL][3];
     int64_t cell_slot_off[MAXL];
     const float* knots;
     const int32_t* cell_slot;
-    const int32_t* cellinfo; /* [nslots][8]: level, c0, c1, c2, supp_off, S, tile_off, n_direct */
+    const int32_t* cellinfo; /* [nslots][info_w]: level, c0, c1, c2, supp_off, S, tile_off, n_direct, ... */
     const uint64_t* dmask;
     const int32_t* supp_jm;
     const float* tiles;
@@ -134,7 +135,7 @@ int64_t oracle_thb_eval(const oracle_space* sp, const float* params, int64_t n, 
         if (out) for (int k = 0; k < cpd; ++k) out[i * cpd + k] = 0.0;
         if (slot < 0) continue;
         inside += 1;
-        const int32_t* ci = sp->cellinfo + (int64_t)slot * 8;
+        const int32_t* ci = sp->cellinfo + (int64_t)slot * sp->info_w;
         const int lev = ci[0], soff = ci[4], S = ci[5], toff = ci[6], ndir = ci[7];
         double N[3][MAXD + 1], dN[3][MAXD + 1], Ud[4 * MAXD + 4];
         for (int k = 0; k < d; ++k) {

@@ -27,8 +27,8 @@ def test_library_exports_every_declared_symbol():
 def test_descriptor_layout_matches_header():
     from thb_diff_b200 import _lib
 
-    # thb_space_desc: 8 ints, 4 x [8][3] ints, 9 + 8 int64, 8 pointers, span-LUT block of 10 x 4 bytes
-    assert ctypes.sizeof(_lib.SpaceDesc) == 8 * 4 + 4 * 8 * 3 * 4 + (9 + 8) * 8 + 8 * 8 + 10 * 4
+    # thb_space_desc: 8 ints, 4 x [8][3] ints, 9 + 8 int64, 12 pointers, span-LUT block of 10 x 4 bytes
+    assert ctypes.sizeof(_lib.SpaceDesc) == 8 * 4 + 4 * 8 * 3 * 4 + (9 + 8) * 8 + 12 * 8 + 10 * 4
     assert _lib.SpaceDesc.knots.offset == 8 * 4 + 4 * 96 + 17 * 8
     assert ctypes.sizeof(_lib.PlanDesc) == 8 + 4 + 4 + 8 * 8
 

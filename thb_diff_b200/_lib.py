@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("THB_LIB", os.path.join(_HERE, "libthb_b200.so"))  # THB_LIB: tuning builds only
 MAX_LEVELS = 8
-INFO_W = 8
+INFO_W = 12
 
 
 class SpaceDesc(C.Structure):
@@ -22,6 +22,7 @@ class SpaceDesc(C.Structure):
         ("fn_off", C.c_int64 * (MAX_LEVELS + 1)), ("cell_slot_off", C.c_int64 * MAX_LEVELS),
         ("knots", C.c_void_p), ("cell_slot", C.c_void_p), ("cellinfo", C.c_void_p), ("dmask", C.c_void_p),
         ("supp_jm", C.c_void_p), ("tiles", C.c_void_p),
+        ("sep_vec", C.c_void_p), ("sep_jm", C.c_void_p), ("full_tiles", C.c_void_p), ("full_jm", C.c_void_p),
         ("span_lut", C.c_void_p), ("lut_off", C.c_int32 * 3), ("lut_n", C.c_int32 * 3), ("lut_scale", C.c_float * 3), ("pad_", C.c_int32),
         ("finest_slot", C.c_void_p),
     ]

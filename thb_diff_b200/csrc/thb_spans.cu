@@ -313,15 +313,15 @@ __global__ void __launch_bounds__(256) k_plan_items(const __grid_constant__ thb_
         return;
     }
     const int4* ci = reinterpret_cast<const int4*>(sp.cellinfo + (int64_t)s * THB_INFO_W);
-    const int4 a = __ldg(ci), e = __ldg(ci + 1);  // level c0 c1 c2 | supp_off S tile_off n_direct
+    const int4 a = __ldg(ci), e = __ldg(ci + 1), f = __ldg(ci + 2);  // level c0 c1 c2 | supp_off S tile_off n_direct | sep_off n_sep full_off 0
     const unsigned long long dm = __ldg(sp.dmask + s);
     for (int j = lane; j < m; j += 32) {
         if (it0 + j < max_items) {
             int4* o = items + (int64_t)(it0 + j) * 4;
             o[0] = make_int4(s, b + j * ppi, min(ppi, c - j * ppi), a.x);
             o[1] = make_int4(a.y, a.z, a.w, e.x);
-            o[2] = make_int4(e.y, e.z, e.w, 0);
-            o[3] = make_int4((int)(unsigned)(dm & 0xffffffffull), (int)(unsigned)(dm >> 32), 0, 0);
+            o[2] = make_int4(e.y, e.z, e.w, f.y);
+            o[3] = make_int4((int)(unsigned)(dm & 0xffffffffull), (int)(unsigned)(dm >> 32), f.x, f.z);
         }
     }
     if (lane == 0) item_start_then_cursor[s] = 0;

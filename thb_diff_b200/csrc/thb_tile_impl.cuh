@@ -60,17 +60,19 @@ struct Shp {
 struct Item {
     int slot, begin, count;
     int lev, c0, c1, c2, soff, S, toff, ndir;
+    int nsep, sep_off, full_off;  // split of the tiled supports: rank-one (12 floats) / full tiles
     unsigned long long dm;
 };
 
 // Work-item record written by thb_plan_build: 16 ints = slot, begin, count, level, c0, c1, c2, supp_off,
-// S, tile_off, n_direct, 0, dmask lo, dmask hi, 0, 0  (the cell's row of cellinfo/dmask is copied in, so one
+// S, tile_off, n_direct, n_sep, dmask lo, dmask hi, sep_off, full_off  (the cell's row of cellinfo/dmask is copied in, so one
 // 64-byte read describes the item).
 THB_DEV Item unpack_item(const int4 v0, const int4 v1, const int4 v2, const int4 v3) {
     Item r;
     r.slot = v0.x; r.begin = v0.y; r.count = v0.z; r.lev = v0.w;
     r.c0 = v1.x; r.c1 = v1.y; r.c2 = v1.z; r.soff = v1.w;
-    r.S = v2.x; r.toff = v2.y; r.ndir = v2.z;
+    r.S = v2.x; r.toff = v2.y; r.ndir = v2.z; r.nsep = v2.w;
+    r.sep_off = v3.z; r.full_off = v3.w;
     r.dm = (unsigned long long)(unsigned)v3.x | ((unsigned long long)(unsigned)v3.y << 32);
     return r;
 }
@@ -161,14 +163,18 @@ struct BasesRK {
         if (SH::N2 > 1) cox_de_boor_rk<SH::P2, DER>(u[2], s_knots[2], s_rk[2], n2, d2);
         else { n2[0] = 1.0f; if (DER) d2[0] = 0.0f; }
     }
-    THB_DEV void tensor(int ch, float* tp) const {
-        float a[SH::N0], b[SH::N1], c[SH::N2];
+    // 1-D factors of a channel (bit k = first derivative in dimension k)
+    THB_DEV void select(int ch, float* a, float* b, float* c) const {
 #pragma unroll
         for (int i = 0; i < SH::N0; ++i) a[i] = (DER && (ch & 1)) ? d0[i] : n0[i];
 #pragma unroll
         for (int i = 0; i < SH::N1; ++i) b[i] = (DER && (ch & 2)) ? d1[i] : n1[i];
 #pragma unroll
         for (int i = 0; i < SH::N2; ++i) c[i] = (DER && (ch & 4)) ? d2[i] : n2[i];
+    }
+    THB_DEV void tensor(int ch, float* tp) const {
+        float a[SH::N0], b[SH::N1], c[SH::N2];
+        select(ch, a, b, c);
 #pragma unroll
         for (int i = 0; i < SH::N0; ++i)
 #pragma unroll
@@ -181,6 +187,8 @@ struct BasesRK {
         for (int t = SH::T; t < SH::TS; ++t) tp[t] = 0.0f;
     }
 };
+
+THB_DEV float f4c(const float4& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
 
 #ifndef THB_WCHUNK
 #define THB_WCHUNK 16
@@ -218,7 +226,8 @@ struct WarpSmem {
     float cpw[2][4][SH::TS];              // own-level window control points (SoA, 0 where inactive)
     int pidx[2][64];                      // caller-order index of the points of a sub-batch
     float pu[2][3][64];                   // their parameters (SoA)
-    float4 cc[kMaxCC];                    // control points of the coarser-level supports
+    float4 cc[kMaxCC];                    // control points of the coarser-level supports (rank-one ones first)
+    float4 sepv[MODE == MODE_FUSED ? kMaxCC : 1][3];  // factor vectors of the rank-one tiled supports
     float tiles[2][kWChunk * (SH::TS + kRowPad)];  // coefficient tiles, streamed in chunks (padded rows)
     // derivative channels contract against control points RELATIVE to a reference point of the item: the
     // derivative basis values sum to zero, so the result is unchanged, but the summed terms are O(p/h * h)
@@ -282,6 +291,17 @@ THB_DEV void prefetch_item_tables(const thb_space_desc& sp, const Args& ar, cons
 }
 
 template <int CPD>
+THB_DEV void gather_ids(const int32_t* __restrict__ ids, const Args& ar, int n, float4* s_cc) {
+    for (int s = threadIdx.x; s < n; s += 32) {
+        const int64_t r = __ldg(ids + s);
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < CPD; ++k) v[k] = __ldg(ar.ctrl_pts + r * CPD + k);
+        s_cc[s] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
+
+template <int CPD>
 THB_DEV void gather_cc(const thb_space_desc& sp, const Args& ar, const Item& it, int first, int n, float4* s_cc) {
     for (int s = threadIdx.x; s < n; s += 32) {
         const int64_t r = __ldg(sp.supp_jm + it.soff + it.ndir + first + s);
@@ -293,8 +313,8 @@ THB_DEV void gather_cc(const thb_space_desc& sp, const Args& ar, const Item& it,
 }
 
 template <int NQ>
-THB_DEV void issue_chunk(const thb_space_desc& sp, const Item& it, int c0, int ns, int TS, float* buf) {
-    const float4* src = reinterpret_cast<const float4*>(sp.tiles + (int64_t)(it.toff + c0) * TS);
+THB_DEV void issue_chunk(const float* tile_src, int c0, int ns, int TS, float* buf) {
+    const float4* src = reinterpret_cast<const float4*>(tile_src + (int64_t)c0 * TS);
     for (int i = threadIdx.x; i < ns * NQ; i += 32) {
         const int row = i / NQ, quad = i - row * NQ;
         cp_async16(buf + row * (TS + kRowPad) + quad * 4, src + i);
@@ -317,9 +337,15 @@ THB_DEV void warp_points(const thb_space_desc& sp, const Args& ar, const Item& i
     const int grp = lane_raw / NPT;            // support group of this lane
     const int lane = lane_raw % NPT;           // point slot of this lane
     const bool use_direct = (it.ndir > 0) || (MODE == MODE_FUSED && cellnet);
-    const bool tile_loop = !(MODE == MODE_FUSED && cellnet) && ntile > 0;
+    // fused per-point mode with split tables: rank-one tiled supports are evaluated from their three factor vectors
+    // (12 FMAs + 2 multiplications instead of a (p+1)^d dot product), only the remaining ones stream full tiles
+    const bool split = MODE == MODE_FUSED && !cellnet && sp.sep_vec != nullptr && ntile <= kMaxCC;
+    const int nsep = split ? it.nsep : 0;
+    const int nfl = split ? ntile - it.nsep : ntile;                                  // supports that need a full tile
+    const float* tile_src = split ? sp.full_tiles + (int64_t)it.full_off * TS : sp.tiles + (int64_t)it.toff * TS;
+    const bool tile_loop = !(MODE == MODE_FUSED && cellnet) && nfl > 0;
     const bool cc_all = ntile <= kMaxCC;
-    if (tile_loop) issue_chunk<NQ>(sp, it, 0, min(kWChunk, ntile), TS, sm.tiles[0]);  // overlaps the basis evaluation below
+    if (tile_loop) issue_chunk<NQ>(tile_src, 0, min(kWChunk, nfl), TS, sm.tiles[0]);  // overlaps the basis evaluation below
 
     int idx[PPT];
     bool valid[PPT];
@@ -397,15 +423,43 @@ THB_DEV void warp_points(const thb_space_desc& sp, const Args& ar, const Item& i
                 for (int q = 0; q < PPT; ++q) acc[q][k] = (G == 1 || grp == 0) ? hsum2(a[q][0]) + hsum2(a[q][1]) : 0.0f;
             }
         }
+        if (MODE == MODE_FUSED && nsep > 0) {
+            float fa[PPT][SH::N0], fb[PPT][SH::N1], fc[PPT][SH::N2];
+#pragma unroll
+            for (int q = 0; q < PPT; ++q) bs[q].select(ch, fa[q], fb[q], fc[q]);
+            const float4* ccs = use_rel ? sm.cc_rel : sm.cc;
+#pragma unroll 2
+            for (int s0 = 0; s0 < nsep; s0 += G) {
+                const bool s_on = G == 1 || s0 + grp < nsep;
+                const int s = (G == 1) ? s0 : min(s0 + grp, nsep - 1);
+                const float4 v0 = sm.sepv[s][0], v1 = sm.sepv[s][1], v2 = sm.sepv[s][2];
+                const float4 cc = ccs[s];
+#pragma unroll
+                for (int q = 0; q < PPT; ++q) {
+                    float e0 = 0.f, e1 = 0.f, e2 = 0.f;
+#pragma unroll
+                    for (int i = 0; i < SH::N0; ++i) e0 = fmaf(f4c(v0, i), fa[q][i], e0);
+#pragma unroll
+                    for (int i = 0; i < SH::N1; ++i) e1 = fmaf(f4c(v1, i), fb[q][i], e1);
+#pragma unroll
+                    for (int i = 0; i < SH::N2; ++i) e2 = fmaf(f4c(v2, i), fc[q][i], e2);
+                    const float phi = s_on ? e0 * e1 * e2 : 0.0f;
+                    acc[q][0] = fmaf(phi, cc.x, acc[q][0]);
+                    acc[q][1] = fmaf(phi, cc.y, acc[q][1]);
+                    acc[q][2] = fmaf(phi, cc.z, acc[q][2]);
+                    if (CPD == 4) acc[q][3] = fmaf(phi, cc.w, acc[q][3]);
+                }
+            }
+        }
         if (tile_loop) {
             // tiles stream through two shared-memory buffers: cp.async of chunk c+1 overlaps the FMAs of chunk c
-            if (chi > 0) issue_chunk<NQ>(sp, it, 0, min(kWChunk, ntile), TS, sm.tiles[0]);
+            if (chi > 0) issue_chunk<NQ>(tile_src, 0, min(kWChunk, nfl), TS, sm.tiles[0]);
             int buf = 0;
-            for (int c0 = 0; c0 < ntile; c0 += kWChunk) {
-                const int ns = min(kWChunk, ntile - c0);
+            for (int c0 = 0; c0 < nfl; c0 += kWChunk) {
+                const int ns = min(kWChunk, nfl - c0);
                 const int c1 = c0 + kWChunk;
-                if (c1 < ntile) {
-                    issue_chunk<NQ>(sp, it, c1, min(kWChunk, ntile - c1), TS, sm.tiles[buf ^ 1]);
+                if (c1 < nfl) {
+                    issue_chunk<NQ>(tile_src, c1, min(kWChunk, nfl - c1), TS, sm.tiles[buf ^ 1]);
                     cp_async_wait<1>();
                 } else {
                     cp_async_wait<0>();
@@ -413,7 +467,7 @@ THB_DEV void warp_points(const thb_space_desc& sp, const Args& ar, const Item& i
                 if (MODE == MODE_FUSED && !cc_all) gather_cc<CPD>(sp, ar, it, c0, ns, sm.cc);
                 __syncwarp();
                 const float* tbuf = sm.tiles[buf];
-                const float4* ccp = (use_rel ? sm.cc_rel : sm.cc) + (cc_all ? c0 : 0);
+                const float4* ccp = (use_rel ? sm.cc_rel : sm.cc) + (cc_all ? nsep + c0 : 0);
 THB_PRAGMA(unroll THB_SUNROLL)
                 for (int s0 = 0; s0 < ns; s0 += G) {
                     const bool s_on = G == 1 || s0 + grp < ns;
@@ -527,7 +581,18 @@ __global__ void __launch_bounds__(kThreads, THB_TILE_MINB) k_tile(const __grid_c
                 sm.rk[dim][m] = 1.0f / (sm.knots[tb][dim][P + r] - sm.knots[tb][dim][P - j + r]);
             }
         }
-        if (MODE == MODE_FUSED && ntile > 0 && ntile <= kMaxCC) gather_cc<CPD>(sp, ar, it, 0, ntile, sm.cc);
+        const bool split = MODE == MODE_FUSED && !cellnet && sp.sep_vec != nullptr && ntile <= kMaxCC;
+        if (split) {
+            // rank-one supports: factor vectors by cp.async, their control points, then the full-tile supports' ones
+            const float4* src = reinterpret_cast<const float4*>(sp.sep_vec + (int64_t)it.sep_off * 12);
+            for (int i = lane; i < it.nsep * 3; i += 32) cp_async16(&sm.sepv[0][0] + i, src + i);
+            cp_async_commit();
+            gather_ids<CPD>(sp.sep_jm + it.sep_off, ar, it.nsep, sm.cc);
+            gather_ids<CPD>(sp.full_jm + it.full_off, ar, ntile - it.nsep, sm.cc + it.nsep);
+            cp_async_wait<0>();
+        } else if (MODE == MODE_FUSED && ntile > 0 && ntile <= kMaxCC) {
+            gather_cc<CPD>(sp, ar, it, 0, ntile, sm.cc);
+        }
         if (MODE == MODE_FUSED && DER && lane < 4) {
             // reference point: the control point of the item's first support
             const int64_t r = __ldg(sp.supp_jm + it.soff);

@@ -62,7 +62,14 @@ class Plan:
         self.build()
 
     def build(self):
+        self.version = self.P.version
         check(lib.thb_plan_build(C.byref(self.P.desc()), ptr(self.params), C.byref(self.desc), stream_ptr(self.P.device)), "thb_plan_build")
+
+    def refresh(self):
+        """Work items embed per-cell table offsets: rebuild if the hierarchy's tables changed since build()."""
+        if self.version != self.P.version:
+            self.build()
+        return self
 
     # derived quantities (device tensors; no sync)
     def num_supp(self):
@@ -70,12 +77,15 @@ class Plan:
         s = self.slot[: self.n].long()
         return torch.where(s >= 0, S[s.clamp(min=0)], torch.zeros_like(s, dtype=torch.int32))
 
-    def stats(self):
-        """(#in-domain points, nnz, nnz of tiled supports) -- synchronises."""
+    def stats(self, with_sep=False):
+        """(#in-domain points, nnz, nnz of tiled supports[, nnz of rank-one tiled supports]) -- synchronises."""
         cnt = self.cell_count[: self.P.nslots].long()
         S = self.P.cellinfo[:, 5].long()
         nd = self.P.cellinfo[:, 7].long()
-        return int(cnt.sum()), int((cnt * S).sum()), int((cnt * (S - nd)).sum())
+        res = (int(cnt.sum()), int((cnt * S).sum()), int((cnt * (S - nd)).sum()))
+        if with_sep:
+            res = res + (int((cnt * self.P.cellinfo[:, 9].long()).sum()),)
+        return res
 
 
 def active_span(P, params, want_num_supp=True):
@@ -100,6 +110,7 @@ def _chan_array(channels):
 
 def basis_tiled(P, plan, offsets, nnz, channels=(CH_VALUE,)):
     """PHI for each channel, flat [nnz] in the reference's (point-major) pair order."""
+    plan.refresh()
     outs = [torch.empty(nnz, dtype=torch.float32, device=P.device) for _ in channels]  # every entry is written
     arr = (C.c_void_p * len(outs))(*[o.data_ptr() for o in outs])
     check(lib.thb_basis_tiled(C.byref(P.desc()), C.byref(plan.desc), ptr(plan.params), ptr(offsets), _chan_array(channels),
@@ -114,6 +125,9 @@ def eval_fused(P, plan, ctrl_pts, channels=(CH_VALUE,), cellnet=False, out=None)
         raise RuntimeError("fused evaluation supports control points of width 3 or 4")
     if ctrl_pts.shape[0] != P.nCP:
         raise RuntimeError(f"ctrl_pts must have {P.nCP} rows")
+    if not P.has_tiles:
+        raise RuntimeError("the hierarchy has no coefficient tiles yet (PackedHierarchy.attach_tiles / from_space)")
+    plan.refresh()
     if out is None:
         out = [torch.zeros((plan.n, cpd), dtype=torch.float32, device=P.device) for _ in channels]
     arr = (C.c_void_p * len(out))(*[o.data_ptr() for o in out])
@@ -125,6 +139,7 @@ def eval_fused(P, plan, ctrl_pts, channels=(CH_VALUE,), cellnet=False, out=None)
 def eval_fused_backward(P, plan, grad_out, cp_dim=None):
     require_cuda(grad_out, "grad_out", torch.float32)
     cpd = grad_out.shape[1]
+    plan.refresh()
     g = torch.empty((P.nCP, cpd), dtype=torch.float32, device=P.device)
     check(lib.thb_eval_fused_backward(C.byref(P.desc()), C.byref(plan.desc), ptr(plan.params), ptr(grad_out), cpd, ptr(g), P.nCP,
                                       stream_ptr(P.device)), "thb_eval_fused_backward")

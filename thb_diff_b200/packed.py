@@ -26,7 +26,7 @@ import numpy as np
 import torch
 
 MAX_LEVELS = 8
-INFO_W = 8  # ints per cellinfo row
+INFO_W = 12  # ints per cellinfo row
 
 
 def _ceil4(x):
@@ -49,6 +49,7 @@ class PackedHierarchy:
     def build(cls, knotvectors, degrees, cells, fns, Coeff=None, device="cuda", onehot_direct=True, chunk=1 << 18,
               build_device=None, truncation="single"):
         self = cls()
+        self.version = 0
         L = max(knotvectors.keys()) + 1
         d = len(degrees)
         if d not in (2, 3):
@@ -230,6 +231,7 @@ class PackedHierarchy:
         self.tiles = None
         dev = torch.device(device)
         self.device = dev
+        self.cellinfo_host = info
         self.knots = torch.from_numpy(knots).to(dev)
         self.cell_slot = torch.from_numpy(cell_slot).to(dev)
         self.finest_slot = torch.from_numpy(finest_map.reshape(-1)).to(dev) if finest_map is not None else None
@@ -241,7 +243,6 @@ class PackedHierarchy:
         self.has_tiles = ntiles == 0
         if Coeff is not None:
             self.attach_tiles(Coeff)
-        self.cellinfo_host = info
         self.nCP = int(fn_off[L])
         return self
 
@@ -276,7 +277,74 @@ class PackedHierarchy:
             w = w * (~window_mask(lv, a)).to(w.dtype)
         t = torch.zeros((m, TS), dtype=torch.float32, device=bdev)
         t[:, :T] = w.reshape(m, T).to(torch.float32)
-        return t
+        return t, w
+
+    def _rank_one(self, tile):
+        """tile [m, n0, n1(, n2)] float64 -> (is rank one [m] bool, factor vectors [m, 12] f32: 4 floats per dimension,
+        zero padded; the third vector is (1,0,0,0) in 2-D).  Rank one = the tile is the outer product of the fibres
+        through its largest entry (exact for untruncated functions and for truncation across a flat face)."""
+        d, p = self.ndim, self.degrees
+        m = tile.shape[0]
+        dev = tile.device
+        flat = tile.reshape(m, -1)
+        idx = flat.abs().argmax(dim=1)
+        piv = flat[torch.arange(m, device=dev), idx]
+        n = [q + 1 for q in p]
+        if d == 2:
+            i0, j0 = idx // n[1], idx % n[1]
+            a = tile[torch.arange(m, device=dev), :, j0]
+            b = tile[torch.arange(m, device=dev), i0, :]
+            safe = torch.where(piv == 0, torch.ones_like(piv), piv)
+            b = b / safe[:, None]
+            rec = torch.einsum("ma,mb->mab", a, b)
+            vecs = [a, b, None]
+        else:
+            i0, r = idx // (n[1] * n[2]), idx % (n[1] * n[2])
+            j0, k0 = r // n[2], r % n[2]
+            ar_ = torch.arange(m, device=dev)
+            a = tile[ar_, :, j0, k0]
+            b = tile[ar_, i0, :, k0]
+            c = tile[ar_, i0, j0, :]
+            safe = torch.where(piv == 0, torch.ones_like(piv), piv)
+            b = b / safe[:, None]
+            c = c / safe[:, None]
+            rec = torch.einsum("ma,mb,mc->mabc", a, b, c)
+            vecs = [a, b, c]
+        ok = (rec - tile).reshape(m, -1).abs().max(dim=1).values <= 1e-12
+        out = torch.zeros((m, 12), dtype=torch.float32, device=dev)
+        for k in range(3):
+            if vecs[k] is None:
+                out[:, 4 * k] = 1.0
+            else:
+                out[:, 4 * k:4 * k + n[k]] = vecs[k].to(torch.float32)
+        return ok, out
+
+    def _split_tiled_supports(self, sepflag, sepvec):
+        """Per cell: the rank-one tiled supports (12 floats each) and the others (full tiles), each list in the
+        reference's relative order; offsets go into cellinfo columns 8..10."""
+        info = self.cellinfo_host
+        S, ndir, soff = info[:, 5].astype(np.int64), info[:, 7].astype(np.int64), info[:, 4].astype(np.int64)
+        nt = S - ndir
+        supp = self.supp_jm.cpu().numpy()
+        pos_in_cell = np.arange(len(supp)) - np.repeat(soff, S)
+        tiled = pos_in_cell >= np.repeat(ndir, S)
+        jm_tiled = supp[tiled]                                   # aligned with the global tile order
+        assert len(jm_tiled) == self.ntiles == len(sepflag)
+        cell_of_tile = np.repeat(np.arange(len(info)), nt)
+        nsep = np.bincount(cell_of_tile[sepflag], minlength=len(info)).astype(np.int64)
+        nfull = nt - nsep
+        info[:, 8] = np.concatenate([[0], np.cumsum(nsep)[:-1]])
+        info[:, 9] = nsep
+        info[:, 10] = np.concatenate([[0], np.cumsum(nfull)[:-1]])
+        dev = self.device
+        self.sep_vec = torch.from_numpy(np.ascontiguousarray(sepvec[sepflag])).to(dev) if sepflag.any() else torch.zeros((1, 12), dtype=torch.float32, device=dev)
+        self.sep_jm = torch.from_numpy(np.ascontiguousarray(jm_tiled[sepflag]).astype(np.int32)).to(dev) if sepflag.any() else torch.zeros(1, dtype=torch.int32, device=dev)
+        full = ~sepflag
+        self.full_tiles = self.tiles[torch.from_numpy(np.nonzero(full)[0]).to(dev)].contiguous() if full.any() else torch.zeros((1, self.TS), dtype=torch.float32, device=dev)
+        self.full_jm = torch.from_numpy(np.ascontiguousarray(jm_tiled[full]).astype(np.int32)).to(dev) if full.any() else torch.zeros(1, dtype=torch.int32, device=dev)
+        self.cellinfo = torch.from_numpy(info).to(dev)
+        self.nsep_total, self.nfull_total = int(nsep.sum()), int(nfull.sum())
+        self.max_sep = int(nsep.max()) if len(nsep) else 0
 
     def attach_tiles(self, Coeff):
         """Computes the coefficient tiles of the coarser-level supports from the 1-D subdivision matrices
@@ -294,6 +362,8 @@ class PackedHierarchy:
                     R[(k, l, lev)] = R[(k, l, lev - 1)] @ np.asarray(Coeff[lev - 1][k], dtype=np.float64)
 
         tiles = torch.zeros((max(ntiles, 1), TS), dtype=torch.float32, device=bdev)
+        sepflag = torch.zeros(max(ntiles, 1), dtype=torch.bool, device=bdev)
+        sepvec = torch.zeros((max(ntiles, 1), 12), dtype=torch.float32, device=bdev)
         es_u = {2: "ma,mb->mab", 3: "ma,mb,mc->mabc"}[d]
         es_t = {2: "mab,max,mby->mxy", 3: "mabc,max,mby,mcz->mxyz"}[d]
         tdev = lambda x, dt=torch.float64: torch.as_tensor(x, device=bdev, dtype=dt)
@@ -315,7 +385,11 @@ class PackedHierarchy:
                     tiles[g_] = t
                     continue
                 if self.truncation == "recursive":
-                    tiles[g_] = self._recursive_tiles(lev, l, c_, f_, Ct, fmask, ar, bdev)
+                    t, w64 = self._recursive_tiles(lev, l, c_, f_, Ct, fmask, ar, bdev)
+                    tiles[g_] = t
+                    fl, vec = self._rank_one(w64)
+                    sepflag[g_] = fl
+                    sepvec[g_] = vec
                     continue
                 A = [Rt[(k, l, lev)][f_[:, k, None], c_[:, k, None] + ar[k][None, :]] for k in range(d)]
                 tile = torch.einsum(es_u, *A)
@@ -337,15 +411,20 @@ class PackedHierarchy:
                 t = torch.zeros((len(g_), TS), dtype=torch.float32, device=bdev)
                 t[:, :T] = tile.reshape(len(g_), T).to(torch.float32)
                 tiles[g_] = t
+                fl, vec = self._rank_one(tile)
+                sepflag[g_] = fl
+                sepvec[g_] = vec
 
+        self.version = getattr(self, "version", 0) + 1  # plans copy per-cell table offsets: older plans must be rebuilt
         self.tiles = tiles.to(self.device)
+        self._split_tiled_supports(sepflag[:ntiles].cpu().numpy(), sepvec[:ntiles].cpu().numpy())
         self.has_tiles = True
         self._desc_cache = None
         return self
 
     # ------------------------------------------------------------------------------------------
     def nbytes(self):
-        ts = [self.knots, self.cell_slot, self.cellinfo, self.dmask, self.supp_jm, self.tiles] + ([self.finest_slot] if self.finest_slot is not None else [])
+        ts = [self.knots, self.cell_slot, self.cellinfo, self.dmask, self.supp_jm, self.tiles] + [t for t in (getattr(self, 'sep_vec', None), getattr(self, 'full_tiles', None)) if t is not None] + ([self.finest_slot] if self.finest_slot is not None else [])
         return sum(t.numel() * t.element_size() for t in ts)
 
     def summary(self):
@@ -380,6 +459,9 @@ def _desc(self):
     d.knots, d.cell_slot, d.cellinfo = self.knots.data_ptr(), self.cell_slot.data_ptr(), self.cellinfo.data_ptr()
     d.dmask, d.supp_jm, d.tiles = self.dmask.data_ptr(), self.supp_jm.data_ptr(), self.tiles.data_ptr()
     d.finest_slot = self.finest_slot.data_ptr() if self.finest_slot is not None else None
+    if getattr(self, "sep_vec", None) is not None:
+        d.sep_vec, d.sep_jm = self.sep_vec.data_ptr(), self.sep_jm.data_ptr()
+        d.full_tiles, d.full_jm = self.full_tiles.data_ptr(), self.full_jm.data_ptr()
     d.span_lut = self.span_lut.data_ptr() if self.span_lut is not None else None
     if self.span_lut is not None:
         for k in range(self.ndim):
