@@ -487,6 +487,7 @@ def main():
             from thb_diff_b200.packed import PackedHierarchy
 
             Pd = PackedHierarchy.from_space(sp, device=device, onehot_direct=False)
+            Pd.sep_vec, Pd._desc_cache = None, None   # literally dense: every support a full (p+1)^d tile dot
             ms, dev = time_variant(Pd, False)
             var["dense_one_hot_tiles"] = {"kernel_ms": ms, "max_abs_diff_vs_headline": dev,
                                           "frac_of_fp32_roofline_8d": (f_dense / (fp32_peak * 1e12)) / (ms * 1e-3)}

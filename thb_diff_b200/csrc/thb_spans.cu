@@ -235,7 +235,11 @@ __global__ void __launch_bounds__(256) k_plan_count(const __grid_constant__ thb_
 
 // pass 2 (single CTA): exclusive scan of the histogram -> cell_start; number of work items per cell and
 // their exclusive scan -> cell_cursor is reused to hold the first item index of each cell.
-// 4096 slots per round: int4 loads, warp-shuffle scans, two barriers per round.
+// 4096 slots per round (int4 per thread), warp-shuffle scans, two barriers per round.  All loads of up to
+// kScanRounds rounds are issued before the first round is scanned, so the kernel pays ONE global-memory
+// latency instead of one per round (it is pure latency: 52 k slots = 13 rounds).
+constexpr int kScanRounds = 16;
+
 __global__ void __launch_bounds__(1024) k_plan_scan(const int32_t* __restrict__ count, int32_t* __restrict__ start,
                                                     int32_t* __restrict__ item_start, int nslots, int ppi,
                                                     int32_t* __restrict__ counters) {
@@ -244,49 +248,64 @@ __global__ void __launch_bounds__(1024) k_plan_scan(const int32_t* __restrict__ 
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
     if (t == 0) s_carry[0] = s_carry[1] = 0;
     __syncthreads();
-    for (int base = 0; base < nslots; base += 4096) {
-        const int i0 = base + 4 * t;
-        int c[4], m[4];
+    for (int base0 = 0; base0 < nslots; base0 += 4096 * kScanRounds) {
+        int4 cv[kScanRounds];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            c[k] = (i0 + k < nslots) ? count[i0 + k] : 0;
-            m[k] = (c[k] + ppi - 1) / ppi;
+        for (int r = 0; r < kScanRounds; ++r) {
+            const int i0 = base0 + r * 4096 + 4 * t;
+            cv[r] = make_int4(0, 0, 0, 0);
+            if (i0 + 3 < nslots) {
+                cv[r] = *reinterpret_cast<const int4*>(count + i0);  // count has nslots+1 entries, 16-byte aligned rows
+            } else {
+                if (i0 < nslots) cv[r].x = count[i0];
+                if (i0 + 1 < nslots) cv[r].y = count[i0 + 1];
+                if (i0 + 2 < nslots) cv[r].z = count[i0 + 2];
+            }
         }
-        const int tp = c[0] + c[1] + c[2] + c[3], ti = m[0] + m[1] + m[2] + m[3];
-        int sp_ = tp, si_ = ti;  // inclusive warp scan of the per-thread totals
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int a = __shfl_up_sync(0xffffffffu, sp_, o), b2 = __shfl_up_sync(0xffffffffu, si_, o);
-            if (lane >= o) { sp_ += a; si_ += b2; }
-        }
-        if (lane == 31) { s_wp[w] = sp_; s_wi[w] = si_; }
-        __syncthreads();
-        if (w == 0) {
-            int a = s_wp[lane], b2 = s_wi[lane];
+        for (int r = 0; r < kScanRounds; ++r) {
+            const int base = base0 + r * 4096;
+            if (base >= nslots) break;
+            const int i0 = base + 4 * t;
+            const int c[4] = {cv[r].x, cv[r].y, cv[r].z, cv[r].w};
+            int m[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) m[k] = (c[k] + ppi - 1) / ppi;
+            const int tp = c[0] + c[1] + c[2] + c[3], ti = m[0] + m[1] + m[2] + m[3];
+            int sp_ = tp, si_ = ti;  // inclusive warp scan of the per-thread totals
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                const int x = __shfl_up_sync(0xffffffffu, a, o), y = __shfl_up_sync(0xffffffffu, b2, o);
-                if (lane >= o) { a += x; b2 += y; }
+                const int a = __shfl_up_sync(0xffffffffu, sp_, o), b2 = __shfl_up_sync(0xffffffffu, si_, o);
+                if (lane >= o) { sp_ += a; si_ += b2; }
             }
-            s_wp[lane] = a;
-            s_wi[lane] = b2;
-        }
-        __syncthreads();
-        const int cp = s_carry[0] + (w ? s_wp[w - 1] : 0) + sp_ - tp;
-        const int ci = s_carry[1] + (w ? s_wi[w - 1] : 0) + si_ - ti;
-        int rp = cp, ri = ci;
+            if (lane == 31) { s_wp[w] = sp_; s_wi[w] = si_; }
+            __syncthreads();
+            if (w == 0) {
+                int a = s_wp[lane], b2 = s_wi[lane];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (i0 + k < nslots) {
-                start[i0 + k] = rp;
-                item_start[i0 + k] = ri;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int x = __shfl_up_sync(0xffffffffu, a, o), y = __shfl_up_sync(0xffffffffu, b2, o);
+                    if (lane >= o) { a += x; b2 += y; }
+                }
+                s_wp[lane] = a;
+                s_wi[lane] = b2;
             }
-            rp += c[k];
-            ri += m[k];
+            __syncthreads();
+            int rp = s_carry[0] + (w ? s_wp[w - 1] : 0) + sp_ - tp;
+            int ri = s_carry[1] + (w ? s_wi[w - 1] : 0) + si_ - ti;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (i0 + k < nslots) {
+                    start[i0 + k] = rp;
+                    item_start[i0 + k] = ri;
+                }
+                rp += c[k];
+                ri += m[k];
+            }
+            __syncthreads();
+            if (t == 1023) { s_carry[0] = rp; s_carry[1] = ri; }
+            __syncthreads();
         }
-        __syncthreads();
-        if (t == 1023) { s_carry[0] = rp; s_carry[1] = ri; }
-        __syncthreads();
     }
     if (t == 0) {
         start[nslots] = s_carry[0];
