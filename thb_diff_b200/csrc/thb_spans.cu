@@ -233,6 +233,96 @@ __global__ void __launch_bounds__(256) k_plan_count(const __grid_constant__ thb_
     }
 }
 
+// pass 1, fast form (needs the span lookup tables, the finest-cell slot map and knots that fit in shared memory):
+// straight-line code per point -- bin -> candidate cell -> one comparison -> verification against the two bracketing
+// breakpoints -> one slot lookup.  A point whose span is not verified (possible only for knot vectors the tables do
+// not resolve) is appended to `fail_list` and handled by k_plan_fixup with the robust search.
+__global__ void __launch_bounds__(256) k_plan_count_fast(const __grid_constant__ thb_space_desc sp, const float* __restrict__ params,
+                                                         int64_t n, int32_t* __restrict__ slot_out, int32_t* __restrict__ count,
+                                                         int32_t* __restrict__ fail_list, int32_t* __restrict__ counters) {
+    __shared__ float sk[kPlanSmemKnots];
+    PlanKnots pk;
+    stage_finest_knots(sp, sk, pk);
+    const int L = sp.nlevels - 1, d = sp.ndim;
+    const int32_t* lut[3];
+    int nb[3], nc[3];
+    float ls[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        lut[k] = sp.span_lut + sp.lut_off[k];
+        nb[k] = sp.lut_n[k];
+        ls[k] = sp.lut_scale[k];
+        nc[k] = k < d ? sp.ncells[L][k] : 1;
+    }
+    const int n1 = sp.ncells[L][1], n2 = d == 3 ? sp.ncells[L][2] : 1;
+    const int lane = threadIdx.x & 31;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t nround = (n + 2 * stride - 1) / (2 * stride) * (2 * stride);
+    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < nround; i0 += 2 * stride) {
+        float u[2][3];
+        int slot[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int64_t i = i0 + h * stride;
+            const int64_t j = i < n ? i : 0;
+            u[h][0] = params[j * d];
+            u[h][1] = params[j * d + 1];
+            u[h][2] = d == 3 ? params[j * d + 2] : 0.f;
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int64_t i = i0 + h * stride;
+            bool inside = true, good = true;
+            int c[3] = {0, 0, 0};
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                if (k < d) {
+                    const float x = u[h][k];
+                    const bool in = (x >= pk.u0[k]) && (x <= pk.u1[k]);   // false for NaN
+                    const float* B = sk + pk.off[k];
+                    const int bin = in ? min((int)((x - pk.u0[k]) * ls[k]), nb[k] - 1) : 0;
+                    int cc = __ldg(lut[k] + bin);
+                    cc = min(cc + (int)(x >= B[cc + 1]), nc[k] - 1);
+                    good = good && (x >= B[cc]) && ((x < B[cc + 1]) || (cc == nc[k] - 1));
+                    inside = inside && in;
+                    c[k] = cc;
+                }
+            }
+            int sl = -1;
+            if (i < n) {
+                if (inside && good) {
+                    sl = __ldg(sp.finest_slot + (c[0] * n1 + c[1]) * n2 + c[2]);
+                    slot_out[i] = sl;
+                } else if (!inside) {
+                    slot_out[i] = -1;
+                } else {
+                    fail_list[atomicAdd(counters + 3, 1)] = (int32_t)i;  // robust path in k_plan_fixup
+                }
+            }
+            slot[h] = sl;
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const unsigned peers = __match_any_sync(0xffffffffu, slot[h]);
+            if (slot[h] >= 0 && lane == (__ffs(peers) - 1)) atomicAdd(count + slot[h], __popc(peers));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_plan_fixup(const __grid_constant__ thb_space_desc sp, const float* __restrict__ params,
+                                                    const int32_t* __restrict__ fail_list, const int32_t* __restrict__ counters,
+                                                    int32_t* __restrict__ slot_out, int32_t* __restrict__ count) {
+    const int nfail = counters[3];
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nfail; j += gridDim.x * blockDim.x) {
+        const int64_t i = fail_list[j];
+        float u[3] = {0.f, 0.f, 0.f};
+        for (int k = 0; k < sp.ndim; ++k) u[k] = params[i * sp.ndim + k];
+        const int sl = locate_slot(sp, u);
+        slot_out[i] = sl;
+        if (sl >= 0) atomicAdd(count + sl, 1);
+    }
+}
+
 // pass 2 (single CTA): exclusive scan of the histogram -> cell_start; number of work items per cell and
 // their exclusive scan -> cell_cursor is reused to hold the first item index of each cell.
 // 4096 slots per round (int4 per thread), warp-shuffle scans, two barriers per round.  All loads of up to
@@ -468,8 +558,19 @@ extern "C" int thb_plan_build(const thb_space_desc* space, const float* params, 
     THB_CUDA(cudaMemsetAsync(plan->cell_count, 0, sizeof(int32_t) * (ns + 1), st));
     if (n > 0) {
         THB_REQUIRE(params, "thb_plan_build: null params");
-        k_plan_count<<<grid_for(n, 256, 16), 256, 0, st>>>(*space, params, n, plan->slot, plan->cell_count);
-        THB_LAUNCHED();
+        int finest_knots = 0;
+        for (int k = 0; k < space->ndim; ++k) finest_knots += space->knot_len[space->nlevels - 1][k];
+        if (space->span_lut && space->finest_slot && finest_knots <= kPlanSmemKnots) {
+            THB_CUDA(cudaMemsetAsync(plan->counters + 3, 0, sizeof(int32_t), st));
+            // plan->perm is free until the scatter pass: it holds the (normally empty) list of unverified points
+            k_plan_count_fast<<<grid_for(n, 256, 16), 256, 0, st>>>(*space, params, n, plan->slot, plan->cell_count, plan->perm, plan->counters);
+            THB_LAUNCHED();
+            k_plan_fixup<<<thb_num_sms(), 256, 0, st>>>(*space, params, plan->perm, plan->counters, plan->slot, plan->cell_count);
+            THB_LAUNCHED();
+        } else {
+            k_plan_count<<<grid_for(n, 256, 16), 256, 0, st>>>(*space, params, n, plan->slot, plan->cell_count);
+            THB_LAUNCHED();
+        }
     }
     k_plan_scan<<<1, 1024, 0, st>>>(plan->cell_count, plan->cell_start, plan->cell_cursor, ns, plan->points_per_item, plan->counters);
     THB_LAUNCHED();
