@@ -73,7 +73,9 @@ typedef struct thb_space_desc {
     int32_t lut_off[3];
     int32_t lut_n[3];
     float lut_scale[3];                     /* bins per unit parameter: bin = (u - U[p]) * lut_scale */
-    int32_t pad_;
+    int32_t n_light_slots;                  /* slots [0, n_light_slots) are the cells whose coarser-level supports are ALL
+                                               rank one (n_sep == S - n_direct <= 120): their work items lead the plan's item
+                                               list and are evaluated without coefficient tiles.  0 = no such ordering. */
     const int32_t* finest_slot;             /* optional (may be NULL): per FINEST-level cell the slot of the active cell
                                                that contains it (-1 if none) -- one lookup instead of one per level */
 } thb_space_desc;
@@ -82,7 +84,8 @@ typedef struct thb_space_desc {
  *   slot [N] i32, perm [N] i32, sorted_params [N, ndim] f32 (the params in cell order: sorted_params[j] =
  *   params[perm[j]]), cell_count/cell_start/cell_cursor [nslots+1] i32,
  *   items [max_items][16] i32 (slot, begin, count, level, c0, c1, c2, supp_off, S, tile_off, n_direct, n_sep,
- *   dmask lo, dmask hi, sep_off, full_off), counters [4] i32 (counters[0] = number of items).
+ *   dmask lo, dmask hi, sep_off, full_off), counters [8] i32 (counters[0] = number of items, counters[5] = number of leading items of light slots; the rest is
+ *   scheduler state).
  * max_items >= N / points_per_item + nslots. */
 typedef struct thb_plan_desc {
     int64_t npoints;

@@ -41,6 +41,11 @@ THB_DEV f32x2 pack2(float lo, float hi) {
 }
 THB_DEV void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
 THB_DEV void ffma2(f32x2& d, f32x2 a, f32x2 b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b)); }
+THB_DEV f32x2 fmul2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
 THB_DEV float hsum2(f32x2 v) {
     float lo, hi;
     unpack2(v, lo, hi);

@@ -97,6 +97,16 @@ extern "C" int thb_eval_fused(const thb_space_desc* space, const thb_plan_desc* 
     ar.params = params; ar.sorted = plan->sorted_params; ar.ctrl_pts = ctrl_pts; ar.cellnet = cellnet ? 1 : 0;
     cudaStream_t st = (cudaStream_t)stream;
     THB_CUDA(cudaMemsetAsync(plan->counters + 1, 0, sizeof(int32_t), st));
+    // cells whose coarser-level supports are all rank one have the lowest slot numbers, so their items lead the list:
+    // they go to the light kernel (no tensor product, no tile stream, twice the occupancy), the rest to the tile kernel
+    const int nlight = (cellnet || env_int("THB_NO_LIGHT", 0)) ? 0 : space->n_light_slots;
+    if (nlight > 0) {
+        THB_CUDA(cudaMemsetAsync(plan->counters + 4, 0, sizeof(int32_t), st));
+        ar.range = 1;
+        if ((rc = ops->light(space, &ar, env_int("THB_LIGHT_PPT", 2), cp_dim, der ? 1 : 0, st))) return rc;
+        if (nlight >= space->nslots) return THB_OK;
+        ar.range = 2;
+    }
     return ops->fused(space, &ar, env_int("THB_FUSED_PPT", 2), cp_dim, der ? 1 : 0, st);
 }
 

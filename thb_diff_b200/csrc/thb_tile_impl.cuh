@@ -21,6 +21,9 @@
 
 namespace thb_tile {
 
+#ifndef THB_LIGHT_MINB
+#define THB_LIGHT_MINB 16  // light kernel: 128 registers, 16 warps per SM
+#endif
 #ifndef THB_TILE_MINB
 #define THB_TILE_MINB 1  // register budget hint (9 => 168 registers + spills in the FFMA2 loop: measured slower)
 #endif
@@ -28,12 +31,16 @@ constexpr int kThreads = 32;   // forward tile kernels: one warp per CTA
 constexpr int kBwdThreads = 128;
 constexpr int kChunk = 64;
 
-enum { MODE_FUSED = 0, MODE_BASIS = 1 };
+// MODE_LIGHT: fused evaluation of the items whose coarser-level supports are all rank one (no coefficient tile is
+// streamed).  It never forms the (p+1)^d tensor product -- own-level supports are contracted by sum factorisation,
+// rank-one supports from their factor vectors -- so it runs in half the registers and at twice the occupancy.
+enum { MODE_FUSED = 0, MODE_BASIS = 1, MODE_LIGHT = 2 };
 
 struct Args {
     const int32_t* perm;
     const int4* items;
-    int32_t* counters;  // [0] = number of items, [1] = scheduler cursor
+    int32_t* counters;  // [0] = number of items, [1] = scheduler cursor, [4] = cursor of the light kernel, [5] = light items
+    int32_t range;      // 0: all items, 1: light items [0, counters[5]), 2: the others [counters[5], counters[0])
     const float* params;
     const float* sorted;     // plan->sorted_params (cell order)
     const float* ctrl_pts;   // fused
@@ -200,6 +207,7 @@ THB_DEV float f4c(const float4& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y 
 #define THB_PRAGMA(x) THB_PRAGMA_(x)
 constexpr int kWChunk = THB_WCHUNK;  // supports staged per chunk by one warp
 constexpr int kMaxCC = 128;  // coarse-support control points gathered once per item (else per chunk)
+constexpr int kMaxLight = 120;  // same bound for the light kernel (sized so that 16 of its warps fit in one SM's shared memory)
 constexpr int kRowPad = 4;   // floats of padding per staged tile row: rows s..s+3 start in different banks
 
 THB_DEV void cp_async16(void* smem, const void* gmem) {
@@ -226,14 +234,15 @@ struct WarpSmem {
     float cpw[2][4][SH::TS];              // own-level window control points (SoA, 0 where inactive)
     int pidx[2][64];                      // caller-order index of the points of a sub-batch
     float pu[2][3][64];                   // their parameters (SoA)
-    float4 cc[kMaxCC];                    // control points of the coarser-level supports (rank-one ones first)
-    float4 sepv[MODE == MODE_FUSED ? kMaxCC : 1][3];  // factor vectors of the rank-one tiled supports
-    float tiles[2][kWChunk * (SH::TS + kRowPad)];  // coefficient tiles, streamed in chunks (padded rows)
+    static constexpr int kCC = MODE == MODE_LIGHT ? kMaxLight : kMaxCC;
+    float4 cc[kCC];                       // control points of the coarser-level supports (rank-one ones first)
+    float4 sepv[MODE != MODE_BASIS ? kCC : 1][3];  // factor vectors of the rank-one tiled supports
+    float tiles[2][MODE == MODE_LIGHT ? 4 : kWChunk * (SH::TS + kRowPad)];  // coefficient tiles, streamed in chunks (padded rows)
     // derivative channels contract against control points RELATIVE to a reference point of the item: the
     // derivative basis values sum to zero, so the result is unchanged, but the summed terms are O(p/h * h)
     // instead of O(p/h * |CP|) -- this removes the float32 cancellation error of parametric derivatives
-    float cpw_rel[(MODE == MODE_FUSED && DER) ? 4 : 1][(MODE == MODE_FUSED && DER) ? SH::TS : 1];
-    float4 cc_rel[(MODE == MODE_FUSED && DER) ? kMaxCC : 1];
+    float cpw_rel[(MODE != MODE_BASIS && DER) ? 4 : 1][(MODE != MODE_BASIS && DER) ? SH::TS : 1];
+    float4 cc_rel[(MODE != MODE_BASIS && DER) ? kCC : 1];
     float ref[4];
     // MODE_BASIS: PHI values are transposed through here so that every point's row is written coalesced
     float stage[MODE == MODE_BASIS ? (32 * (SH::TS + 1) > 64 * (kWChunk + 1) ? 32 * (SH::TS + 1) : 64 * (kWChunk + 1)) : 1];
@@ -534,26 +543,214 @@ THB_PRAGMA(unroll THB_SUNROLL)
     }
 }
 
+// MODE_LIGHT sub-batch: PPT*32 points of an item whose tiled supports are all rank one.
+//   own-level supports:  out_k = sum_a A[a] sum_b B[b] sum_c C[c] * CPwin[k][a][b][c]   (sum factorisation; the
+//       innermost sum is two FFMA2 on one broadcast LDS.128 of the staged window, the partial (even, odd) sums stay
+//       packed through the outer two stages) -- (p+1)^d + (p+1)^(d-1) + (p+1)^(d-2) FMAs per output component and no
+//       (p+1)^d-entry register array
+//   rank-one supports:   PHI_s = <v0_s, A> <v1_s, B> <v2_s, C>
+// G > 1 (PPT == 1): G lane groups share the <= 32/G points; group g takes every G-th `a` slab and every G-th
+// rank-one support, partial sums are combined by shuffles.
+template <class SH, int PPT, int G, int CPD, bool DER>
+THB_DEV void warp_points_light(const Args& ar, const Item& it, int base, WarpSmem<SH, MODE_LIGHT, DER>& sm, int tb, int pb) {
+    static_assert(G == 1 || PPT == 1, "support split: one point per lane");
+    constexpr int N0 = SH::N0, N1 = SH::N1, N2 = SH::N2;
+    constexpr int NPT = 32 / G;
+    const int lane_raw = threadIdx.x;
+    const int grp = lane_raw / NPT, lane = lane_raw % NPT;
+    const int nsep = it.nsep;
+
+    int idx[PPT];
+    bool valid[PPT];
+    BasesRK<SH, DER> bs[PPT];
+#pragma unroll
+    for (int q = 0; q < PPT; ++q) {
+        valid[q] = base + q * 32 + lane < it.count;
+        idx[q] = sm.pidx[pb][q * 32 + lane];
+        const float u[3] = {sm.pu[pb][0][q * 32 + lane], sm.pu[pb][1][q * 32 + lane], N2 > 1 ? sm.pu[pb][2][q * 32 + lane] : 0.f};
+        bs[q].eval(u, sm.knots[tb], sm.rk);
+    }
+    for (int chi = 0; chi < ar.nch; ++chi) {
+        const int ch = ar.channels[chi];
+        const bool use_rel = DER && ch != 0;  // see WarpSmem::cpw_rel
+        float fa[PPT][N0], fb[PPT][N1], fc[PPT][N2];
+#pragma unroll
+        for (int q = 0; q < PPT; ++q) bs[q].select(ch, fa[q], fb[q], fc[q]);
+        float acc[PPT][4];
+#pragma unroll
+        for (int q = 0; q < PPT; ++q)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[q][k] = 0.0f;
+
+        if (it.ndir > 0) {
+            if constexpr (N2 == 4) {
+                // Order of contraction b -> c -> a.  Stage 1 (the (p+1)^3 one) is e[a][h] += B[b] * CPwin[a][b][2h..2h+1]:
+                // FFMA2 with a SCALAR multiplier that stays the same for 2*N0 consecutive instructions, so it comes from
+                // the operand reuse cache and each FFMA2 fetches only two register pairs (an FMA stream that fetches
+                // three fresh operands per instruction is register-file-bound at ~64 % of the FP32 peak, scripts/probe).
+                f32x2 fc2[PPT][2];
+#pragma unroll
+                for (int q = 0; q < PPT; ++q) {
+                    fc2[q][0] = pack2(fc[q][0], fc[q][1]);
+                    fc2[q][1] = pack2(fc[q][2], fc[q][3]);
+                }
+#pragma unroll
+                for (int k = 0; k < CPD; ++k) {
+                    const ulonglong2* col = reinterpret_cast<const ulonglong2*>(use_rel ? sm.cpw_rel[k] : sm.cpw[tb][k]);
+                    f32x2 e[PPT][N0][2];
+#pragma unroll
+                    for (int b = 0; b < N1; ++b) {
+                        ulonglong2 cv[N0];
+#pragma unroll
+                        for (int a = 0; a < N0; ++a) cv[a] = col[a * N1 + b];
+#pragma unroll
+                        for (int q = 0; q < PPT; ++q) {
+                            const f32x2 bb = pack2(fb[q][b], fb[q][b]);
+#pragma unroll
+                            for (int a = 0; a < N0; ++a) {
+                                if (b == 0) {
+                                    e[q][a][0] = fmul2(bb, cv[a].x);
+                                    e[q][a][1] = fmul2(bb, cv[a].y);
+                                } else {
+                                    ffma2(e[q][a][0], bb, cv[a].x);
+                                    ffma2(e[q][a][1], bb, cv[a].y);
+                                }
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < PPT; ++q) {
+                        f32x2 f = 0ull;
+#pragma unroll
+                        for (int a0 = 0; a0 < N0; a0 += G) {
+                            // G > 1: lane group g keeps slab a0 + g (the others were computed but are dropped: the
+                            // sub-batches that use G > 1 hold <= 16 points, their cost is the rank-one loop below)
+                            f32x2 g2 = fmul2(fc2[q][0], e[q][a0][0]);
+                            ffma2(g2, fc2[q][1], e[q][a0][1]);
+                            float av = fa[q][a0];
+                            if (G > 1) {
+#pragma unroll
+                                for (int j = 1; j < G; ++j) {
+                                    if (a0 + j < N0) {
+                                        f32x2 h2 = fmul2(fc2[q][0], e[q][a0 + j][0]);
+                                        ffma2(h2, fc2[q][1], e[q][a0 + j][1]);
+                                        g2 = (grp == j) ? h2 : g2;
+                                        av = (grp == j) ? fa[q][a0 + j] : av;
+                                    } else if (grp == j) {
+                                        g2 = 0ull;
+                                    }
+                                }
+                            }
+                            ffma2(f, pack2(av, av), g2);
+                        }
+                        acc[q][k] = hsum2(f);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < CPD; ++k) {
+                    const float* col = use_rel ? sm.cpw_rel[k] : sm.cpw[tb][k];
+                    float f[PPT];
+#pragma unroll
+                    for (int q = 0; q < PPT; ++q) f[q] = 0.0f;
+#pragma unroll
+                    for (int a0 = 0; a0 < N0; a0 += G) {
+                        const int a = (G == 1) ? a0 : a0 + grp;
+                        if (G > 1 && a >= N0) break;
+                        float e[PPT];
+#pragma unroll
+                        for (int q = 0; q < PPT; ++q) e[q] = 0.0f;
+#pragma unroll
+                        for (int b = 0; b < N1; ++b) {
+                            float cv[N2];
+#pragma unroll
+                            for (int c = 0; c < N2; ++c) cv[c] = col[(a * N1 + b) * N2 + c];
+#pragma unroll
+                            for (int q = 0; q < PPT; ++q) {
+                                float dd = fc[q][0] * cv[0];
+#pragma unroll
+                                for (int c = 1; c < N2; ++c) dd = fmaf(fc[q][c], cv[c], dd);
+                                e[q] = fmaf(fb[q][b], dd, e[q]);
+                            }
+                        }
+#pragma unroll
+                        for (int q = 0; q < PPT; ++q) {
+                            float av = fa[q][0];
+#pragma unroll
+                            for (int i = 1; i < N0; ++i) av = (a == i) ? fa[q][i] : av;
+                            f[q] = fmaf(av, e[q], f[q]);
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < PPT; ++q) acc[q][k] = f[q];
+                }
+            }
+        }
+        if (nsep > 0) {
+            const float4* ccs = use_rel ? sm.cc_rel : sm.cc;
+#pragma unroll 2
+            for (int s0 = 0; s0 < nsep; s0 += G) {
+                const bool s_on = G == 1 || s0 + grp < nsep;
+                const int s = (G == 1) ? s0 : min(s0 + grp, nsep - 1);
+                const float4 v0 = sm.sepv[s][0], v1 = sm.sepv[s][1], v2 = sm.sepv[s][2];
+                const float4 cc = ccs[s];
+#pragma unroll
+                for (int q = 0; q < PPT; ++q) {
+                    float e0 = 0.f, e1 = 0.f, e2 = 0.f;
+#pragma unroll
+                    for (int i = 0; i < N0; ++i) e0 = fmaf(f4c(v0, i), fa[q][i], e0);
+#pragma unroll
+                    for (int i = 0; i < N1; ++i) e1 = fmaf(f4c(v1, i), fb[q][i], e1);
+#pragma unroll
+                    for (int i = 0; i < N2; ++i) e2 = fmaf(f4c(v2, i), fc[q][i], e2);
+                    const float phi = s_on ? e0 * e1 * e2 : 0.0f;
+                    acc[q][0] = fmaf(phi, cc.x, acc[q][0]);
+                    acc[q][1] = fmaf(phi, cc.y, acc[q][1]);
+                    acc[q][2] = fmaf(phi, cc.z, acc[q][2]);
+                    if (CPD == 4) acc[q][3] = fmaf(phi, cc.w, acc[q][3]);
+                }
+            }
+        }
+        if (G > 1) {
+#pragma unroll
+            for (int k = 0; k < CPD; ++k)
+#pragma unroll
+                for (int o = NPT; o < 32; o <<= 1) acc[0][k] += __shfl_xor_sync(0xffffffffu, acc[0][k], o);
+        }
+#pragma unroll
+        for (int q = 0; q < PPT; ++q) {
+            if (valid[q] && (G == 1 || grp == 0)) {
+                float* o = ar.out[chi] + (int64_t)idx[q] * CPD;
+#pragma unroll
+                for (int k = 0; k < CPD; ++k) o[k] = acc[q][k];
+            }
+        }
+    }
+}
+
 // Persistent, warp-autonomous kernel: every CTA is ONE warp that pulls work items from an atomic cursor.
 // No CTA-wide barrier exists.  Software pipeline: while item i is computed, the records of items i+1 and
 // i+2 are (being) fetched, the id of item i+3 is being claimed, and the points of the next sub-batch plus
 // the knots / window control points of item i+1 stream into the other half of the shared-memory buffers.
 template <int N0, int N1, int N2, int PPT, int CPD, int MODE, bool DER>
-__global__ void __launch_bounds__(kThreads, THB_TILE_MINB) k_tile(const __grid_constant__ thb_space_desc sp, const __grid_constant__ Args ar) {
+__global__ void __launch_bounds__(kThreads, MODE == MODE_LIGHT ? THB_LIGHT_MINB : THB_TILE_MINB) k_tile(const __grid_constant__ thb_space_desc sp, const __grid_constant__ Args ar) {
     using SH = Shp<N0, N1, N2>;
     constexpr int TS = SH::TS, NQ = SH::NQ;
     constexpr int SB = 32 * PPT;
     __shared__ __align__(16) WarpSmem<SH, MODE, DER> sm;
 
     const int lane = threadIdx.x;
-    const int nitems = ar.counters[0];
+    // item range of this launch (light items come first in the list: their cells have the lowest slot numbers)
+    const int item_lo = ar.range == 2 ? ar.counters[5] : 0;
+    const int nitems = ar.range == 1 ? ar.counters[5] : ar.counters[0];
+    int32_t* const cursor = ar.counters + (MODE == MODE_LIGHT ? 4 : 1);
     const int d = sp.ndim;
     const bool cellnet = (MODE == MODE_FUSED) && ar.cellnet;
-    const bool want_cp = (MODE == MODE_FUSED);
+    const bool want_cp = (MODE != MODE_BASIS);
 
     // claim three items up front (ids are increasing); id3 is claimed asynchronously
     int c3 = 0;
-    if (lane == 0) c3 = atomicAdd(ar.counters + 1, 3);
+    if (lane == 0) c3 = item_lo + atomicAdd(cursor, 3);
     const int id0 = __shfl_sync(0xffffffffu, c3, 0);
     if (id0 >= nitems) return;
     int id1 = id0 + 1, id2 = id0 + 2;
@@ -564,7 +761,7 @@ __global__ void __launch_bounds__(kThreads, THB_TILE_MINB) k_tile(const __grid_c
     prefetch_points<PPT>(ar, d, it.begin, it.count, 0, sm.pidx[0], sm.pu[0]);
     cp_async_commit();
     int nn_id = 0;
-    if (lane == 0) nn_id = atomicAdd(ar.counters + 1, 1);
+    if (lane == 0) nn_id = item_lo + atomicAdd(cursor, 1);
     int ring = 0, tb = 0, pb = 0;
     cp_async_wait<0>();
     __syncwarp();
@@ -581,7 +778,7 @@ __global__ void __launch_bounds__(kThreads, THB_TILE_MINB) k_tile(const __grid_c
                 sm.rk[dim][m] = 1.0f / (sm.knots[tb][dim][P + r] - sm.knots[tb][dim][P - j + r]);
             }
         }
-        const bool split = MODE == MODE_FUSED && !cellnet && sp.sep_vec != nullptr && ntile <= kMaxCC;
+        const bool split = MODE == MODE_LIGHT || (MODE == MODE_FUSED && !cellnet && sp.sep_vec != nullptr && ntile <= kMaxCC);
         if (split) {
             // rank-one supports: factor vectors by cp.async, their control points, then the full-tile supports' ones
             const float4* src = reinterpret_cast<const float4*>(sp.sep_vec + (int64_t)it.sep_off * 12);
@@ -593,13 +790,13 @@ __global__ void __launch_bounds__(kThreads, THB_TILE_MINB) k_tile(const __grid_c
         } else if (MODE == MODE_FUSED && ntile > 0 && ntile <= kMaxCC) {
             gather_cc<CPD>(sp, ar, it, 0, ntile, sm.cc);
         }
-        if (MODE == MODE_FUSED && DER && lane < 4) {
+        if (MODE != MODE_BASIS && DER && lane < 4) {
             // reference point: the control point of the item's first support
             const int64_t r = __ldg(sp.supp_jm + it.soff);
             sm.ref[lane] = (lane < CPD && it.S > 0) ? __ldg(ar.ctrl_pts + r * CPD + lane) : 0.f;
         }
         __syncwarp();
-        if (MODE == MODE_FUSED && DER) {
+        if (MODE != MODE_BASIS && DER) {
             for (int t = lane; t < TS; t += 32) {
                 const bool on = it.ndir > 0 && t < SH::T && ((it.dm >> t) & 1ull);
 #pragma unroll
@@ -649,6 +846,12 @@ __global__ void __launch_bounds__(kThreads, THB_TILE_MINB) k_tile(const __grid_c
             }
             cp_async_commit();
             const int rem = it.count - base;
+            if constexpr (MODE == MODE_LIGHT) {
+                if (rem <= 8) warp_points_light<SH, 1, 4, CPD, DER>(ar, it, base, sm, tb, pb);
+                else if (rem <= 16) warp_points_light<SH, 1, 2, CPD, DER>(ar, it, base, sm, tb, pb);
+                else if (PPT == 2 && rem <= 32) warp_points_light<SH, 1, 1, CPD, DER>(ar, it, base, sm, tb, pb);
+                else warp_points_light<SH, PPT, 1, CPD, DER>(ar, it, base, sm, tb, pb);
+            } else
             if (MODE == MODE_FUSED && rem <= 8 && ntile > 0)
                 warp_points<SH, 1, (MODE == MODE_FUSED ? 4 : 1), CPD, MODE, DER>(sp, ar, it, base, ntile, cellnet, sm, tb, pb);
             else if (MODE == MODE_FUSED && rem <= 16 && ntile > 0)
@@ -674,7 +877,7 @@ __global__ void __launch_bounds__(kThreads, THB_TILE_MINB) k_tile(const __grid_c
         id2 = id3;
         if (lane < 4 && id3 < nitems) cp_async16(&sm.rec[(ring + 2) % 3][lane], ar.items + (int64_t)id3 * 4 + lane);
         cp_async_commit();
-        if (lane == 0) nn_id = atomicAdd(ar.counters + 1, 1);
+        if (lane == 0) nn_id = item_lo + atomicAdd(cursor, 1);
     }
 }
 
@@ -787,6 +990,7 @@ struct ShapeOps {
     int n0, n1, n2;
     // ppt in {1,2}; cpd in {3,4}; der in {0,1}
     int (*fused)(const thb_space_desc*, const Args*, int ppt, int cpd, int der, cudaStream_t);
+    int (*light)(const thb_space_desc*, const Args*, int ppt, int cpd, int der, cudaStream_t);
     int (*basis)(const thb_space_desc*, const Args*, int ppt, int der, cudaStream_t);
     int (*backward)(const thb_space_desc*, const Args*, int cpd, cudaStream_t);
 };
@@ -826,6 +1030,22 @@ int launch_fused(const thb_space_desc* sp, const Args* ar, int ppt, int cpd, int
 }
 
 template <int N0, int N1, int N2>
+int launch_light(const thb_space_desc* sp, const Args* ar, int ppt, int cpd, int der, cudaStream_t st) {
+    if (ppt == 2) {
+        if (cpd == 3 && !der) THB_TILE_LAUNCH((k_tile<N0, N1, N2, 2, 3, MODE_LIGHT, false>));
+        if (cpd == 3 && der) THB_TILE_LAUNCH((k_tile<N0, N1, N2, 2, 3, MODE_LIGHT, true>));
+        if (cpd == 4 && !der) THB_TILE_LAUNCH((k_tile<N0, N1, N2, 2, 4, MODE_LIGHT, false>));
+        if (cpd == 4 && der) THB_TILE_LAUNCH((k_tile<N0, N1, N2, 2, 4, MODE_LIGHT, true>));
+    } else {
+        if (cpd == 3 && !der) THB_TILE_LAUNCH((k_tile<N0, N1, N2, 1, 3, MODE_LIGHT, false>));
+        if (cpd == 3 && der) THB_TILE_LAUNCH((k_tile<N0, N1, N2, 1, 3, MODE_LIGHT, true>));
+        if (cpd == 4 && !der) THB_TILE_LAUNCH((k_tile<N0, N1, N2, 1, 4, MODE_LIGHT, false>));
+        if (cpd == 4 && der) THB_TILE_LAUNCH((k_tile<N0, N1, N2, 1, 4, MODE_LIGHT, true>));
+    }
+    return thb_set_error(THB_E_UNSUPPORTED, "fused (light): unsupported variant");
+}
+
+template <int N0, int N1, int N2>
 int launch_basis(const thb_space_desc* sp, const Args* ar, int ppt, int der, cudaStream_t st) {
     if (ppt == 2) {
         if (!der) THB_TILE_LAUNCH((k_tile<N0, N1, N2, 2, 3, MODE_BASIS, false>));
@@ -844,7 +1064,7 @@ int launch_backward(const thb_space_desc* sp, const Args* ar, int cpd, cudaStrea
 
 #define THB_DEFINE_SHAPE(A, B, C)                                                                         \
     namespace thb_tile {                                                                                  \
-    extern const ShapeOps shape_ops_##A##B##C = {A, B, C, &launch_fused<A, B, C>, &launch_basis<A, B, C>,    \
+    extern const ShapeOps shape_ops_##A##B##C = {A, B, C, &launch_fused<A, B, C>, &launch_light<A, B, C>, &launch_basis<A, B, C>,    \
                                                  &launch_backward<A, B, C>};                              \
     }
 

@@ -52,7 +52,7 @@ class Plan:
         self.cell_cursor = torch.empty(P.nslots + 1, **i32)
         self.max_items = n // points_per_item + P.nslots + 1
         self.items = torch.empty((self.max_items, 16), **i32)
-        self.counters = torch.zeros(4, **i32)
+        self.counters = torch.zeros(8, **i32)
         d = PlanDesc()
         d.npoints, d.points_per_item, d.max_items = n, points_per_item, self.max_items
         d.slot, d.perm, d.sorted_params = self.slot.data_ptr(), self.perm.data_ptr(), self.sorted_params.data_ptr()
