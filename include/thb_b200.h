@@ -73,9 +73,7 @@ typedef struct thb_space_desc {
     int32_t lut_off[3];
     int32_t lut_n[3];
     float lut_scale[3];                     /* bins per unit parameter: bin = (u - U[p]) * lut_scale */
-    int32_t n_light_slots;                  /* slots [0, n_light_slots) are the cells whose coarser-level supports are ALL
-                                               rank one (n_sep == S - n_direct <= 120): their work items lead the plan's item
-                                               list and are evaluated without coefficient tiles.  0 = no such ordering. */
+    int32_t pad_;
     const int32_t* finest_slot;             /* optional (may be NULL): per FINEST-level cell the slot of the active cell
                                                that contains it (-1 if none) -- one lookup instead of one per level */
 } thb_space_desc;
@@ -84,8 +82,7 @@ typedef struct thb_space_desc {
  *   slot [N] i32, perm [N] i32, sorted_params [N, ndim] f32 (the params in cell order: sorted_params[j] =
  *   params[perm[j]]), cell_count/cell_start/cell_cursor [nslots+1] i32,
  *   items [max_items][16] i32 (slot, begin, count, level, c0, c1, c2, supp_off, S, tile_off, n_direct, n_sep,
- *   dmask lo, dmask hi, sep_off, full_off), counters [8] i32 (counters[0] = number of items, counters[5] = number of leading items of light slots; the rest is
- *   scheduler state).
+ *   dmask lo, dmask hi, sep_off, full_off), counters [4] i32 (counters[0] = number of items).
  * max_items >= N / points_per_item + nslots. */
 typedef struct thb_plan_desc {
     int64_t npoints;
@@ -162,12 +159,19 @@ THB_API int thb_basis_dense(const float* params, int64_t npoints, int ndim, cons
                     float* phi_out, void* stream);
 
 /* ---- fused basis + evaluation (PHI never leaves the SM) ----------------------------------------------------
- * out_host[c] is a device buffer [N, cp_dim] per channel.  cellnet != 0 folds the tiles into a per-cell local
- * control net first (same result, far fewer FLOPs).  Replaces THB_basis_fns followed by THBEval.forward
- * (THB/torch_funcs.py:22-33). */
+ * out_host[c] is a device buffer [N, cp_dim] per channel.  Replaces THB_basis_fns followed by THBEval.forward
+ * (THB/torch_funcs.py:22-33).  formulation selects how sum_s PHI_s(u) CP_s is evaluated (same result to rounding):
+ *   THB_EVAL_LOCAL_NET (0, default)  coarser-level supports are folded into the cell's local control net once per work
+ *                                    item, points are evaluated against the net by sum factorisation
+ *   THB_EVAL_TILE_NET  (1)           the per-point tile kernel with a per-item fold of all tiles
+ *   THB_EVAL_PER_POINT (2)           PHI_s(u) of every support is formed per point, then contracted -- the reference's
+ *                                    gather-multiply + contraction, without PHI leaving the SM */
+#define THB_EVAL_LOCAL_NET 0
+#define THB_EVAL_TILE_NET 1
+#define THB_EVAL_PER_POINT 2
 THB_API int thb_eval_fused(const thb_space_desc* space, const thb_plan_desc* plan, const float* params,
                    const float* ctrl_pts, int cp_dim, const int32_t* channels, int nchannels, float* const* out_host,
-                   int cellnet, void* stream);
+                   int formulation, void* stream);
 /* grad_ctrl_pts[nctrl, cp_dim] (zeroed by the callee) = A^T grad_out, A = value-channel basis matrix.
  * Replaces THBEval.backward (THB/torch_funcs.py:35-47) for the fused path. */
 THB_API int thb_eval_fused_backward(const thb_space_desc* space, const thb_plan_desc* plan, const float* params,

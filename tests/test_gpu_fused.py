@@ -24,15 +24,15 @@ def _setup(name, onehot=True, cp_dim=3, seed=0):
     return g, h, P, plan, cp, cs
 
 
-@pytest.mark.parametrize("cellnet", [False, True])
+@pytest.mark.parametrize("formulation", ["local_net", "per_point", "tile_net"])
 @pytest.mark.parametrize("onehot", [True, False])
 @pytest.mark.parametrize("name", IDENTITY_OK)
-def test_fused_forward(name, onehot, cellnet):
+def test_fused_forward(name, onehot, formulation):
     from thb_diff_b200 import engine
 
     g, h, P, plan, cp, cs = _setup(name, onehot)
     ref = O.eval_forward(cp, g["Jm"], g["PHI"], cs)
-    out = engine.eval_fused(P, plan, torch.from_numpy(cp).cuda(), cellnet=cellnet)[0].cpu().numpy()
+    out = engine.eval_fused(P, plan, torch.from_numpy(cp).cuda(), formulation=formulation)[0].cpu().numpy()
     assert rel_err(out, ref, scale=np.abs(ref).max()).max() <= TOL
 
 
@@ -56,18 +56,19 @@ def test_fused_cp_dim4():
     assert out.shape == ref.shape and rel_err(out, ref, scale=np.abs(ref).max()).max() <= TOL
 
 
+@pytest.mark.parametrize("formulation", ["local_net", "per_point"])
 @pytest.mark.parametrize("name", ["graded2d", "block3d"])
-def test_greville_control_points_reproduce_the_parameters(name):
+def test_greville_control_points_reproduce_the_parameters(name, formulation):
     """Linear reproduction: evaluating with Greville abscissae as control points returns the params, and
     the first derivatives are the identity."""
     from thb_diff_b200 import configs, engine
 
     g, h, P, plan, _, _ = _setup(name)
     cp = torch.from_numpy(configs.greville_ctrl_pts(h, bump=0.0)).cuda()
-    out = engine.eval_fused(P, plan, cp)[0].cpu().numpy()
+    out = engine.eval_fused(P, plan, cp, formulation=formulation)[0].cpu().numpy()
     d = h.ndim
     assert np.abs(out[:, :d] - g["params"]).max() < 1e-5
-    ders = engine.eval_fused(P, plan, cp, engine.grad_channels(d))
+    ders = engine.eval_fused(P, plan, cp, engine.grad_channels(d), formulation=formulation)
     for k in range(d):
         J = ders[k].cpu().numpy()[:, :d]
         e = np.zeros(d)
@@ -119,8 +120,8 @@ def test_many_points_per_cell_and_ragged_tail():
     plan = engine.Plan(P, prm)
     cp = rng.standard_normal((P.nCP, 3)).astype(np.float32)
     cpt = torch.from_numpy(cp).cuda()
-    out = engine.eval_fused(P, plan, cpt)[0]
-    out2 = engine.eval_fused(P, plan, cpt, cellnet=True)[0]
+    out = engine.eval_fused(P, plan, cpt, formulation="per_point")[0]
+    out2 = engine.eval_fused(P, plan, cpt, formulation="local_net")[0]
     sp = __import__("helpers").oracle_space_from_golden(g)
     de = O.DirectEvaluator(sp.knotvectors, sp.degrees, sp.cells, sp.fns, sp.Coeff)
     idx = rng.choice(len(prm), 300, replace=False)
@@ -128,7 +129,8 @@ def test_many_points_per_cell_and_ragged_tail():
     scale = np.abs(ref).max()
     assert rel_err(out.cpu().numpy()[idx], ref, scale=scale).max() <= TOL
     assert rel_err(out2.cpu().numpy()[idx], ref, scale=scale).max() <= TOL
-    assert torch.equal(engine.eval_fused(P, plan, cpt)[0], out)  # deterministic forward
+    assert torch.equal(engine.eval_fused(P, plan, cpt, formulation="per_point")[0], out)  # deterministic forward
+    assert torch.equal(engine.eval_fused(P, plan, cpt)[0], out2)
 
 
 def test_host_pipeline_matches_device_path():

@@ -39,8 +39,8 @@ def test_c3_against_c_oracle_everywhere(c3):
     PHI = core.THB_basis_fns(prm, supp, ns, P, sp.sh_fns, sp.knotvectors, sp.degrees)
     assert rel_err(PHI.cpu().numpy(), ref["phi"]).max() <= TOL
     scale = np.abs(ref["out"]).max()
-    for cellnet in (False, True):
-        out = engine.eval_fused(P, supp.plan, cp, cellnet=cellnet)[0].cpu().numpy()
+    for formulation in ("local_net", "per_point", "tile_net"):
+        out = engine.eval_fused(P, supp.plan, cp, formulation=formulation)[0].cpu().numpy()
         assert rel_err(out, ref["out"], scale=scale).max() <= TOL
     # true gradient channels against the oracle's derivative modes.  The derivative basis values are
     # O(p * #cells) ~ 400 here while the geometry derivative they sum to is O(1): float32 cancellation bounds
@@ -50,11 +50,14 @@ def test_c3_against_c_oracle_everywhere(c3):
     Jm = supp.Jm().cpu().numpy()
     cs = np.cumsum(S)
     cph = cp.cpu().numpy()
-    for k, o in enumerate(engine.eval_fused(P, supp.plan, cp, engine.grad_channels(3))):
+    ders = {f: engine.eval_fused(P, supp.plan, cp, engine.grad_channels(3), formulation=f) for f in ("local_net", "per_point")}
+    for k in range(3):
         r = ht.eval(prm, cph, mode=1 << k, want_phi=True, offsets=off, nnz=int(S.sum()))
         cond = O.eval_forward(np.abs(cph), Jm, np.abs(r["phi"]), cs)
-        assert (np.abs(o.cpu().numpy() - r["out"]) <= TOL * np.maximum(cond, 1.0)).all()
-        assert rel_err(o.cpu().numpy(), r["out"], scale=np.abs(r["out"]).max()).max() <= TOL  # thanks to the relative-CP contraction
+        for f, dd in ders.items():
+            o = dd[k].cpu().numpy()
+            assert (np.abs(o - r["out"]) <= TOL * np.maximum(cond, 1.0)).all(), f
+            assert rel_err(o, r["out"], scale=np.abs(r["out"]).max()).max() <= TOL, f  # thanks to the relative-CP contraction
 
 
 def test_c3_sampled_against_table_free_oracle(c3):
@@ -100,7 +103,7 @@ def test_c3_full_size_properties(c3):
     grev = torch.from_numpy(configs.greville_ctrl_pts(sp, bump=0.0)).cuda()
     out = engine.eval_fused(P, plan, grev)[0]
     assert float((out - prm).abs().max()) < 1e-5
-    out_c = engine.eval_fused(P, plan, grev, cellnet=True)[0]
+    out_c = engine.eval_fused(P, plan, grev, formulation="per_point")[0]
     assert float((out_c - prm).abs().max()) < 1e-5
     ders = engine.eval_fused(P, plan, grev, engine.grad_channels(3))
     eye = torch.eye(3, device="cuda")

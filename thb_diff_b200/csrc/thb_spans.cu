@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(256) k_plan_fixup(const __grid_constant__ thb_
 constexpr int kScanRounds = 16;
 
 __global__ void __launch_bounds__(1024) k_plan_scan(const int32_t* __restrict__ count, int32_t* __restrict__ start,
-                                                    int32_t* __restrict__ item_start, int nslots, int ppi, int nlight,
+                                                    int32_t* __restrict__ item_start, int nslots, int ppi,
                                                     int32_t* __restrict__ counters) {
     __shared__ int s_wp[32], s_wi[32];
     __shared__ int s_carry[2];
@@ -388,7 +388,6 @@ __global__ void __launch_bounds__(1024) k_plan_scan(const int32_t* __restrict__ 
                 if (i0 + k < nslots) {
                     start[i0 + k] = rp;
                     item_start[i0 + k] = ri;
-                    if (i0 + k == nlight) counters[5] = ri;  // items of the light slots [0, nlight) come first
                 }
                 rp += c[k];
                 ri += m[k];
@@ -403,8 +402,6 @@ __global__ void __launch_bounds__(1024) k_plan_scan(const int32_t* __restrict__ 
         counters[0] = s_carry[1];  // number of work items
         counters[1] = 0;           // dynamic scheduler cursor
         counters[2] = s_carry[0];  // number of in-domain points
-        counters[4] = 0;           // cursor of the light kernel
-        if (nlight >= nslots) counters[5] = s_carry[1];
     }
 }
 
@@ -496,7 +493,6 @@ int thb_check_space(const thb_space_desc* sp, const char* who) {
     THB_REQUIRE(sp->ndim == 2 || sp->ndim == 3, "%s: ndim must be 2 or 3", who);
     THB_REQUIRE(sp->nlevels >= 1 && sp->nlevels <= THB_MAX_LEVELS, "%s: bad level count", who);
     THB_REQUIRE(sp->nslots > 0, "%s: no active cells", who);
-    THB_REQUIRE(sp->n_light_slots >= 0 && sp->n_light_slots <= sp->nslots, "%s: n_light_slots out of range", who);
     THB_REQUIRE(sp->knots && sp->cell_slot && sp->cellinfo && sp->dmask && sp->supp_jm && sp->tiles, "%s: null table", who);
     return THB_OK;
 }
@@ -576,7 +572,7 @@ extern "C" int thb_plan_build(const thb_space_desc* space, const float* params, 
             THB_LAUNCHED();
         }
     }
-    k_plan_scan<<<1, 1024, 0, st>>>(plan->cell_count, plan->cell_start, plan->cell_cursor, ns, plan->points_per_item, space->n_light_slots, plan->counters);
+    k_plan_scan<<<1, 1024, 0, st>>>(plan->cell_count, plan->cell_start, plan->cell_cursor, ns, plan->points_per_item, plan->counters);
     THB_LAUNCHED();
     k_plan_items<<<(ns * 32 + 255) / 256, 256, 0, st>>>(*space, plan->cell_count, plan->cell_start, plan->cell_cursor, ns, plan->points_per_item,
                                                    plan->max_items, (int4*)plan->items);

@@ -77,7 +77,7 @@ extern "C" int thb_basis_tiled(const thb_space_desc* space, const thb_plan_desc*
 
 extern "C" int thb_eval_fused(const thb_space_desc* space, const thb_plan_desc* plan, const float* params,
                               const float* ctrl_pts, int cp_dim, const int32_t* channels, int nchannels, float* const* out_host,
-                              int cellnet, void* stream) {
+                              int formulation, void* stream) {
     int rc = thb_check_space(space, "thb_eval_fused");
     if (rc) return rc;
     if ((rc = check_plan(plan, "thb_eval_fused"))) return rc;
@@ -94,19 +94,12 @@ extern "C" int thb_eval_fused(const thb_space_desc* space, const thb_plan_desc* 
         ar.out[c] = out_host[c];
     }
     ar.perm = plan->perm; ar.items = (const int4*)plan->items; ar.counters = plan->counters;
-    ar.params = params; ar.sorted = plan->sorted_params; ar.ctrl_pts = ctrl_pts; ar.cellnet = cellnet ? 1 : 0;
+    ar.params = params; ar.sorted = plan->sorted_params; ar.ctrl_pts = ctrl_pts; ar.cellnet = formulation == THB_EVAL_TILE_NET ? 1 : 0;
     cudaStream_t st = (cudaStream_t)stream;
     THB_CUDA(cudaMemsetAsync(plan->counters + 1, 0, sizeof(int32_t), st));
-    // cells whose coarser-level supports are all rank one have the lowest slot numbers, so their items lead the list:
-    // they go to the light kernel (no tensor product, no tile stream, twice the occupancy), the rest to the tile kernel
-    const int nlight = (cellnet || env_int("THB_NO_LIGHT", 0)) ? 0 : space->n_light_slots;
-    if (nlight > 0) {
-        THB_CUDA(cudaMemsetAsync(plan->counters + 4, 0, sizeof(int32_t), st));
-        ar.range = 1;
-        if ((rc = ops->light(space, &ar, env_int("THB_LIGHT_PPT", 2), cp_dim, der ? 1 : 0, st))) return rc;
-        if (nlight >= space->nslots) return THB_OK;
-        ar.range = 2;
-    }
+    THB_REQUIRE(formulation >= 0 && formulation <= 2, "thb_eval_fused: unknown formulation");
+    if (formulation == THB_EVAL_LOCAL_NET && (space->sep_vec != nullptr || space->max_tiled == 0))
+        return ops->light(space, &ar, env_int("THB_LIGHT_PPT", 2), cp_dim, der ? 1 : 0, st);
     return ops->fused(space, &ar, env_int("THB_FUSED_PPT", 2), cp_dim, der ? 1 : 0, st);
 }
 

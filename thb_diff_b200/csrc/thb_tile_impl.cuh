@@ -31,16 +31,16 @@ constexpr int kThreads = 32;   // forward tile kernels: one warp per CTA
 constexpr int kBwdThreads = 128;
 constexpr int kChunk = 64;
 
-// MODE_LIGHT: fused evaluation of the items whose coarser-level supports are all rank one (no coefficient tile is
-// streamed).  It never forms the (p+1)^d tensor product -- own-level supports are contracted by sum factorisation,
-// rank-one supports from their factor vectors -- so it runs in half the registers and at twice the occupancy.
+// MODE_LIGHT: the default fused evaluation.  Coarser-level supports are folded into the cell's local control net once
+// per item (light_item_setup), points are evaluated against that net by sum factorisation: no (p+1)^d tensor product
+// in registers and no tile stream, so it runs in half the registers and at twice the occupancy of MODE_FUSED, which
+// is kept for the per-point formulation (the reference's gather-multiply, bench.py variants) and for MODE_BASIS.
 enum { MODE_FUSED = 0, MODE_BASIS = 1, MODE_LIGHT = 2 };
 
 struct Args {
     const int32_t* perm;
     const int4* items;
-    int32_t* counters;  // [0] = number of items, [1] = scheduler cursor, [4] = cursor of the light kernel, [5] = light items
-    int32_t range;      // 0: all items, 1: light items [0, counters[5]), 2: the others [counters[5], counters[0])
+    int32_t* counters;  // [0] = number of items, [1] = scheduler cursor
     const float* params;
     const float* sorted;     // plan->sorted_params (cell order)
     const float* ctrl_pts;   // fused
@@ -543,22 +543,145 @@ THB_PRAGMA(unroll THB_SUNROLL)
     }
 }
 
-// MODE_LIGHT sub-batch: PPT*32 points of an item whose tiled supports are all rank one.
-//   own-level supports:  out_k = sum_a A[a] sum_b B[b] sum_c C[c] * CPwin[k][a][b][c]   (sum factorisation; the
-//       innermost sum is two FFMA2 on one broadcast LDS.128 of the staged window, the partial (even, odd) sums stay
-//       packed through the outer two stages) -- (p+1)^d + (p+1)^(d-1) + (p+1)^(d-2) FMAs per output component and no
-//       (p+1)^d-entry register array
-//   rank-one supports:   PHI_s = <v0_s, A> <v1_s, B> <v2_s, C>
-// G > 1 (PPT == 1): G lane groups share the <= 32/G points; group g takes every G-th `a` slab and every G-th
-// rank-one support, partial sums are combined by shuffles.
+// ---- MODE_LIGHT: fused evaluation through the cell's LOCAL CONTROL NET ------------------------------------------
+// A coarser-level support s contributes PHI_s(u) * CP_s with PHI_s(u) = <tile_s, tp(u)>, so over a cell
+//     sum_s PHI_s(u) CP_s = < tp(u), W >,   W[t] = sum_s tile_s[t] * CP_s
+// and W can be added to the staged own-level window once per ITEM instead of once per point: 2*cp_dim FMAs per lane
+// and support (the lane owns window entries t = lane, lane + 32) against (p+1)^d FMAs per POINT and support.  Full
+// tiles are always folded (rows read coalesced from global memory, never staged); rank-one supports are folded from
+// their factor vectors unless the item has <= 16 points, where evaluating them per point with the lane-group split
+// is cheaper.  Returns true when the rank-one supports are left to the per-point loop.
+template <class SH, int CPD, bool DER>
+THB_DEV bool light_item_setup(const thb_space_desc& sp, const Args& ar, const Item& it, WarpSmem<SH, MODE_LIGHT, DER>& sm, int tb) {
+    constexpr int T = SH::T, TS = SH::TS, N1 = SH::N1, N2 = SH::N2;
+    constexpr int NT = (TS + 31) / 32;
+    const int lane = threadIdx.x;
+    const int ntile = it.S - it.ndir, nsep = it.nsep;
+    const bool per_point = nsep > 0 && it.count <= 16 && ntile <= kMaxLight;
+    if (DER) {
+        if (lane < 4) {  // reference point: the control point of the item's first support (see WarpSmem::cpw_rel)
+            const int64_t r = __ldg(sp.supp_jm + it.soff);
+            sm.ref[lane] = (lane < CPD && it.S > 0) ? __ldg(ar.ctrl_pts + r * CPD + lane) : 0.f;
+        }
+        __syncwarp();
+        for (int t = lane; t < TS; t += 32) {
+            const bool on = it.ndir > 0 && t < T && ((it.dm >> t) & 1ull);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) sm.cpw_rel[k][t] = on ? sm.cpw[tb][k][t] - sm.ref[k] : 0.f;
+        }
+    }
+    if (ntile == 0) {
+        __syncwarp();
+        return false;
+    }
+    float w[NT][4], wr[DER ? NT : 1][4];
+    int ia[NT], ib, ic;
+    bool tv[NT];
+#pragma unroll
+    for (int h = 0; h < NT; ++h) {
+        const int t = lane + 32 * h;
+        tv[h] = t < T;
+        ia[h] = tv[h] ? t / (N1 * N2) : 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { w[h][k] = 0.f; if (DER) wr[h][k] = 0.f; }
+    }
+    ib = 4 + (lane / N2) % N1;  // positions inside a 12-float factor record (t and t + 32 differ in the first index only
+    ic = 8 + lane % N2;         // when 32 is a multiple of N1*N2; otherwise recomputed below)
+    constexpr bool kSameBC = (32 % (N1 * N2)) == 0;
+    for (int c0 = 0; c0 < ntile; c0 += kMaxLight) {
+        const int n = min(kMaxLight, ntile - c0);
+        const int s_lo = min(c0, nsep), s_n = min(c0 + n, nsep) - s_lo;  // rank-one supports of this chunk
+        const int f_lo = max(c0, nsep) - nsep, f_n = n - s_n;               // full-tile supports of this chunk
+        if (c0 > 0) __syncwarp();
+        if (s_n > 0) {
+            const float4* src = reinterpret_cast<const float4*>(sp.sep_vec + (int64_t)(it.sep_off + s_lo) * 12);
+            for (int i = lane; i < s_n * 3; i += 32) cp_async16(&sm.sepv[0][0] + i, src + i);
+            cp_async_commit();
+            gather_ids<CPD>(sp.sep_jm + it.sep_off + s_lo, ar, s_n, sm.cc);
+        }
+        if (f_n > 0) gather_ids<CPD>(sp.full_jm + it.full_off + f_lo, ar, f_n, sm.cc + s_n);
+        cp_async_wait<0>();
+        __syncwarp();
+        if (DER) {
+            for (int i = lane; i < n; i += 32) {
+                const float4 c = sm.cc[i];
+                sm.cc_rel[i] = make_float4(c.x - sm.ref[0], c.y - sm.ref[1], c.z - sm.ref[2], c.w - sm.ref[3]);
+            }
+            __syncwarp();
+        }
+        if (!per_point) {
+#pragma unroll 4
+            for (int i = 0; i < s_n; ++i) {
+                const float* sv = reinterpret_cast<const float*>(&sm.sepv[i][0]);
+                const float4 cc = sm.cc[i];
+                float4 cr = cc;
+                if (DER) cr = sm.cc_rel[i];
+                const float bc = sv[ib] * sv[ic];
+#pragma unroll
+                for (int h = 0; h < NT; ++h) {
+                    float x;
+                    if (kSameBC || h == 0) {
+                        x = tv[h] ? sv[ia[h]] * bc : 0.f;
+                    } else {
+                        const int t = lane + 32 * h;
+                        x = tv[h] ? sv[ia[h]] * sv[4 + (t / N2) % N1] * sv[8 + t % N2] : 0.f;
+                    }
+                    w[h][0] = fmaf(x, cc.x, w[h][0]); w[h][1] = fmaf(x, cc.y, w[h][1]); w[h][2] = fmaf(x, cc.z, w[h][2]);
+                    if (CPD == 4) w[h][3] = fmaf(x, cc.w, w[h][3]);
+                    if (DER) {
+                        wr[h][0] = fmaf(x, cr.x, wr[h][0]); wr[h][1] = fmaf(x, cr.y, wr[h][1]); wr[h][2] = fmaf(x, cr.z, wr[h][2]);
+                        if (CPD == 4) wr[h][3] = fmaf(x, cr.w, wr[h][3]);
+                    }
+                }
+            }
+        }
+        const float* rows = sp.full_tiles + (int64_t)(it.full_off + f_lo) * TS + lane;
+#pragma unroll 4
+        for (int j = 0; j < f_n; ++j) {
+            const float4 cc = sm.cc[s_n + j];
+            float4 cr = cc;
+            if (DER) cr = sm.cc_rel[s_n + j];
+#pragma unroll
+            for (int h = 0; h < NT; ++h) {
+                const float x = (lane + 32 * h < TS) ? __ldg(rows + (int64_t)j * TS + 32 * h) : 0.f;
+                w[h][0] = fmaf(x, cc.x, w[h][0]); w[h][1] = fmaf(x, cc.y, w[h][1]); w[h][2] = fmaf(x, cc.z, w[h][2]);
+                if (CPD == 4) w[h][3] = fmaf(x, cc.w, w[h][3]);
+                if (DER) {
+                    wr[h][0] = fmaf(x, cr.x, wr[h][0]); wr[h][1] = fmaf(x, cr.y, wr[h][1]); wr[h][2] = fmaf(x, cr.z, wr[h][2]);
+                    if (CPD == 4) wr[h][3] = fmaf(x, cr.w, wr[h][3]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int h = 0; h < NT; ++h) {
+        const int t = lane + 32 * h;
+        if (t < TS) {
+#pragma unroll
+            for (int k = 0; k < CPD; ++k) {
+                sm.cpw[tb][k][t] += w[h][k];
+                if (DER) sm.cpw_rel[k][t] += wr[h][k];
+            }
+        }
+    }
+    __syncwarp();
+    return per_point;
+}
+
+// MODE_LIGHT sub-batch: PPT*32 points of an item.
+//   window (own-level supports + folded net):  out_k = sum_a A[a] sum_c C[c] sum_b B[b] * W[k][a][b][c]   (sum
+//       factorisation: (p+1)^d + (p+1)^(d-1) + (p+1)^(d-2) FMAs per output component, no (p+1)^d register array)
+//   rank-one supports left to the points (nsep > 0):   PHI_s = <v0_s, A> <v1_s, B> <v2_s, C>
+// G > 1 (PPT == 1): G lane groups share the <= 32/G points and each takes every G-th rank-one support; partial sums
+// are combined by shuffles.
 template <class SH, int PPT, int G, int CPD, bool DER>
-THB_DEV void warp_points_light(const Args& ar, const Item& it, int base, WarpSmem<SH, MODE_LIGHT, DER>& sm, int tb, int pb) {
+THB_DEV void warp_points_light(const Args& ar, const Item& it, int base, WarpSmem<SH, MODE_LIGHT, DER>& sm, int tb, int pb,
+                                  bool direct, int nsep) {
     static_assert(G == 1 || PPT == 1, "support split: one point per lane");
     constexpr int N0 = SH::N0, N1 = SH::N1, N2 = SH::N2;
     constexpr int NPT = 32 / G;
     const int lane_raw = threadIdx.x;
     const int grp = lane_raw / NPT, lane = lane_raw % NPT;
-    const int nsep = it.nsep;
 
     int idx[PPT];
     bool valid[PPT];
@@ -582,7 +705,7 @@ THB_DEV void warp_points_light(const Args& ar, const Item& it, int base, WarpSme
 #pragma unroll
             for (int k = 0; k < 4; ++k) acc[q][k] = 0.0f;
 
-        if (it.ndir > 0) {
+        if (direct) {
             if constexpr (N2 == 4) {
                 // Order of contraction b -> c -> a.  Stage 1 (the (p+1)^3 one) is e[a][h] += B[b] * CPwin[a][b][2h..2h+1]:
                 // FFMA2 with a SCALAR multiplier that stays the same for 2*N0 consecutive instructions, so it comes from
@@ -622,28 +745,12 @@ THB_DEV void warp_points_light(const Args& ar, const Item& it, int base, WarpSme
                     for (int q = 0; q < PPT; ++q) {
                         f32x2 f = 0ull;
 #pragma unroll
-                        for (int a0 = 0; a0 < N0; a0 += G) {
-                            // G > 1: lane group g keeps slab a0 + g (the others were computed but are dropped: the
-                            // sub-batches that use G > 1 hold <= 16 points, their cost is the rank-one loop below)
-                            f32x2 g2 = fmul2(fc2[q][0], e[q][a0][0]);
-                            ffma2(g2, fc2[q][1], e[q][a0][1]);
-                            float av = fa[q][a0];
-                            if (G > 1) {
-#pragma unroll
-                                for (int j = 1; j < G; ++j) {
-                                    if (a0 + j < N0) {
-                                        f32x2 h2 = fmul2(fc2[q][0], e[q][a0 + j][0]);
-                                        ffma2(h2, fc2[q][1], e[q][a0 + j][1]);
-                                        g2 = (grp == j) ? h2 : g2;
-                                        av = (grp == j) ? fa[q][a0 + j] : av;
-                                    } else if (grp == j) {
-                                        g2 = 0ull;
-                                    }
-                                }
-                            }
-                            ffma2(f, pack2(av, av), g2);
+                        for (int a = 0; a < N0; ++a) {
+                            f32x2 g2 = fmul2(fc2[q][0], e[q][a][0]);
+                            ffma2(g2, fc2[q][1], e[q][a][1]);
+                            ffma2(f, pack2(fa[q][a], fa[q][a]), g2);
                         }
-                        acc[q][k] = hsum2(f);
+                        acc[q][k] = (G == 1 || grp == 0) ? hsum2(f) : 0.0f;  // G > 1: every group computed it, one keeps it
                     }
                 }
             } else {
@@ -654,9 +761,7 @@ THB_DEV void warp_points_light(const Args& ar, const Item& it, int base, WarpSme
 #pragma unroll
                     for (int q = 0; q < PPT; ++q) f[q] = 0.0f;
 #pragma unroll
-                    for (int a0 = 0; a0 < N0; a0 += G) {
-                        const int a = (G == 1) ? a0 : a0 + grp;
-                        if (G > 1 && a >= N0) break;
+                    for (int a = 0; a < N0; ++a) {
                         float e[PPT];
 #pragma unroll
                         for (int q = 0; q < PPT; ++q) e[q] = 0.0f;
@@ -674,15 +779,10 @@ THB_DEV void warp_points_light(const Args& ar, const Item& it, int base, WarpSme
                             }
                         }
 #pragma unroll
-                        for (int q = 0; q < PPT; ++q) {
-                            float av = fa[q][0];
-#pragma unroll
-                            for (int i = 1; i < N0; ++i) av = (a == i) ? fa[q][i] : av;
-                            f[q] = fmaf(av, e[q], f[q]);
-                        }
+                        for (int q = 0; q < PPT; ++q) f[q] = fmaf(fa[q][a], e[q], f[q]);
                     }
 #pragma unroll
-                    for (int q = 0; q < PPT; ++q) acc[q][k] = f[q];
+                    for (int q = 0; q < PPT; ++q) acc[q][k] = (G == 1 || grp == 0) ? f[q] : 0.0f;
                 }
             }
         }
@@ -740,17 +840,15 @@ __global__ void __launch_bounds__(kThreads, MODE == MODE_LIGHT ? THB_LIGHT_MINB 
     __shared__ __align__(16) WarpSmem<SH, MODE, DER> sm;
 
     const int lane = threadIdx.x;
-    // item range of this launch (light items come first in the list: their cells have the lowest slot numbers)
-    const int item_lo = ar.range == 2 ? ar.counters[5] : 0;
-    const int nitems = ar.range == 1 ? ar.counters[5] : ar.counters[0];
-    int32_t* const cursor = ar.counters + (MODE == MODE_LIGHT ? 4 : 1);
+    const int nitems = ar.counters[0];
+    int32_t* const cursor = ar.counters + 1;
     const int d = sp.ndim;
     const bool cellnet = (MODE == MODE_FUSED) && ar.cellnet;
     const bool want_cp = (MODE != MODE_BASIS);
 
     // claim three items up front (ids are increasing); id3 is claimed asynchronously
     int c3 = 0;
-    if (lane == 0) c3 = item_lo + atomicAdd(cursor, 3);
+    if (lane == 0) c3 = atomicAdd(cursor, 3);
     const int id0 = __shfl_sync(0xffffffffu, c3, 0);
     if (id0 >= nitems) return;
     int id1 = id0 + 1, id2 = id0 + 2;
@@ -761,7 +859,7 @@ __global__ void __launch_bounds__(kThreads, MODE == MODE_LIGHT ? THB_LIGHT_MINB 
     prefetch_points<PPT>(ar, d, it.begin, it.count, 0, sm.pidx[0], sm.pu[0]);
     cp_async_commit();
     int nn_id = 0;
-    if (lane == 0) nn_id = item_lo + atomicAdd(cursor, 1);
+    if (lane == 0) nn_id = atomicAdd(cursor, 1);
     int ring = 0, tb = 0, pb = 0;
     cp_async_wait<0>();
     __syncwarp();
@@ -778,7 +876,12 @@ __global__ void __launch_bounds__(kThreads, MODE == MODE_LIGHT ? THB_LIGHT_MINB 
                 sm.rk[dim][m] = 1.0f / (sm.knots[tb][dim][P + r] - sm.knots[tb][dim][P - j + r]);
             }
         }
-        const bool split = MODE == MODE_LIGHT || (MODE == MODE_FUSED && !cellnet && sp.sep_vec != nullptr && ntile <= kMaxCC);
+        bool light_pp = false;
+        if constexpr (MODE == MODE_LIGHT) {
+            __syncwarp();
+            light_pp = light_item_setup<SH, CPD, DER>(sp, ar, it, sm, tb);
+        }
+        const bool split = MODE == MODE_FUSED && !cellnet && sp.sep_vec != nullptr && ntile <= kMaxCC;
         if (split) {
             // rank-one supports: factor vectors by cp.async, their control points, then the full-tile supports' ones
             const float4* src = reinterpret_cast<const float4*>(sp.sep_vec + (int64_t)it.sep_off * 12);
@@ -790,13 +893,13 @@ __global__ void __launch_bounds__(kThreads, MODE == MODE_LIGHT ? THB_LIGHT_MINB 
         } else if (MODE == MODE_FUSED && ntile > 0 && ntile <= kMaxCC) {
             gather_cc<CPD>(sp, ar, it, 0, ntile, sm.cc);
         }
-        if (MODE != MODE_BASIS && DER && lane < 4) {
+        if (MODE == MODE_FUSED && DER && lane < 4) {
             // reference point: the control point of the item's first support
             const int64_t r = __ldg(sp.supp_jm + it.soff);
             sm.ref[lane] = (lane < CPD && it.S > 0) ? __ldg(ar.ctrl_pts + r * CPD + lane) : 0.f;
         }
         __syncwarp();
-        if (MODE != MODE_BASIS && DER) {
+        if (MODE == MODE_FUSED && DER) {
             for (int t = lane; t < TS; t += 32) {
                 const bool on = it.ndir > 0 && t < SH::T && ((it.dm >> t) & 1ull);
 #pragma unroll
@@ -847,10 +950,11 @@ __global__ void __launch_bounds__(kThreads, MODE == MODE_LIGHT ? THB_LIGHT_MINB 
             cp_async_commit();
             const int rem = it.count - base;
             if constexpr (MODE == MODE_LIGHT) {
-                if (rem <= 8) warp_points_light<SH, 1, 4, CPD, DER>(ar, it, base, sm, tb, pb);
-                else if (rem <= 16) warp_points_light<SH, 1, 2, CPD, DER>(ar, it, base, sm, tb, pb);
-                else if (PPT == 2 && rem <= 32) warp_points_light<SH, 1, 1, CPD, DER>(ar, it, base, sm, tb, pb);
-                else warp_points_light<SH, PPT, 1, CPD, DER>(ar, it, base, sm, tb, pb);
+                const bool direct = it.ndir > 0 || ntile > (light_pp ? it.nsep : 0);
+                if (light_pp && rem <= 8) warp_points_light<SH, 1, 4, CPD, DER>(ar, it, base, sm, tb, pb, direct, it.nsep);
+                else if (light_pp) warp_points_light<SH, 1, 2, CPD, DER>(ar, it, base, sm, tb, pb, direct, it.nsep);
+                else if (PPT == 2 && rem <= 32) warp_points_light<SH, 1, 1, CPD, DER>(ar, it, base, sm, tb, pb, direct, 0);
+                else warp_points_light<SH, PPT, 1, CPD, DER>(ar, it, base, sm, tb, pb, direct, 0);
             } else
             if (MODE == MODE_FUSED && rem <= 8 && ntile > 0)
                 warp_points<SH, 1, (MODE == MODE_FUSED ? 4 : 1), CPD, MODE, DER>(sp, ar, it, base, ntile, cellnet, sm, tb, pb);
@@ -877,7 +981,7 @@ __global__ void __launch_bounds__(kThreads, MODE == MODE_LIGHT ? THB_LIGHT_MINB 
         id2 = id3;
         if (lane < 4 && id3 < nitems) cp_async16(&sm.rec[(ring + 2) % 3][lane], ar.items + (int64_t)id3 * 4 + lane);
         cp_async_commit();
-        if (lane == 0) nn_id = item_lo + atomicAdd(cursor, 1);
+        if (lane == 0) nn_id = atomicAdd(cursor, 1);
     }
 }
 

@@ -52,7 +52,7 @@ class Plan:
         self.cell_cursor = torch.empty(P.nslots + 1, **i32)
         self.max_items = n // points_per_item + P.nslots + 1
         self.items = torch.empty((self.max_items, 16), **i32)
-        self.counters = torch.zeros(8, **i32)
+        self.counters = torch.zeros(4, **i32)
         d = PlanDesc()
         d.npoints, d.points_per_item, d.max_items = n, points_per_item, self.max_items
         d.slot, d.perm, d.sorted_params = self.slot.data_ptr(), self.perm.data_ptr(), self.sorted_params.data_ptr()
@@ -118,7 +118,13 @@ def basis_tiled(P, plan, offsets, nnz, channels=(CH_VALUE,)):
     return outs
 
 
-def eval_fused(P, plan, ctrl_pts, channels=(CH_VALUE,), cellnet=False, out=None):
+FORMULATIONS = {"local_net": 0, "tile_net": 1, "per_point": 2}
+
+
+def eval_fused(P, plan, ctrl_pts, channels=(CH_VALUE,), cellnet=True, out=None, formulation=None):
+    """Fused THB_basis_fns + THBEval.forward.  formulation: "local_net" (default; cellnet=True), "per_point"
+    (cellnet=False: PHI of every support is formed per point, the reference's formulation) or "tile_net"."""
+    form = FORMULATIONS[formulation] if formulation is not None else (0 if cellnet else 2)
     require_cuda(ctrl_pts, "ctrl_pts", torch.float32)
     cpd = ctrl_pts.shape[1]
     if cpd not in (3, 4):
@@ -132,7 +138,7 @@ def eval_fused(P, plan, ctrl_pts, channels=(CH_VALUE,), cellnet=False, out=None)
         out = [torch.zeros((plan.n, cpd), dtype=torch.float32, device=P.device) for _ in channels]
     arr = (C.c_void_p * len(out))(*[o.data_ptr() for o in out])
     check(lib.thb_eval_fused(C.byref(P.desc()), C.byref(plan.desc), ptr(plan.params), ptr(ctrl_pts), cpd, _chan_array(channels),
-                             len(channels), arr, int(bool(cellnet)), stream_ptr(P.device)), "thb_eval_fused")
+                             len(channels), arr, form, stream_ptr(P.device)), "thb_eval_fused")
     return out
 
 
@@ -230,7 +236,7 @@ class HostPipeline:
     plan + fused kernel of chunk c and the D2H copy of chunk c-1 (PCIe is full duplex), so a step costs about
     max(H2D, D2H, compute) instead of their sum.  Device buffers are allocated once."""
 
-    def __init__(self, P, n_points, cp_dim=3, n_chunks=8, cellnet=False):
+    def __init__(self, P, n_points, cp_dim=3, n_chunks=8, cellnet=True):
         self.P, self.n, self.cpd, self.cellnet = P, int(n_points), cp_dim, cellnet
         n_chunks = max(1, min(n_chunks, (self.n + 65535) // 65536))
         base, rem = divmod(self.n, n_chunks)

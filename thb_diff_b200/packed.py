@@ -29,9 +29,6 @@ MAX_LEVELS = 8
 INFO_W = 12  # ints per cellinfo row
 
 
-MAX_LIGHT_TILED = 120  # kMaxLight of csrc/thb_tile_impl.cuh: rank-one supports one warp of the light kernel stages at once
-
-
 def _ceil4(x):
     return (x + 3) // 4 * 4
 
@@ -244,7 +241,6 @@ class PackedHierarchy:
         self.supp_jm = torch.from_numpy(supp_jm).to(dev)
         self.tiles = torch.zeros((1, TS), dtype=torch.float32, device=dev)
         self.has_tiles = ntiles == 0
-        self.n_light_slots = nslots if ntiles == 0 else 0
         if Coeff is not None:
             self.attach_tiles(Coeff)
         self.nCP = int(fn_off[L])
@@ -349,30 +345,6 @@ class PackedHierarchy:
         self.cellinfo = torch.from_numpy(info).to(dev)
         self.nsep_total, self.nfull_total = int(nsep.sum()), int(nfull.sum())
         self.max_sep = int(nsep.max()) if len(nsep) else 0
-        self._light_slots_first((nfull == 0) & (nt <= MAX_LIGHT_TILED))
-
-    def _light_slots_first(self, light):
-        """Renumbers the slots so that the cells whose coarser-level supports are all rank one come first (stable, so
-        each group keeps the level / C-order sequence).  Work items follow slot order, hence the items of these cells
-        lead every plan's item list and can be given to the kernel that needs no coefficient tiles."""
-        self.n_light_slots = int(light.sum())
-        if self.n_light_slots in (0, self.nslots) or bool(light[:self.n_light_slots].all()):
-            return
-        order = np.concatenate([np.nonzero(light)[0], np.nonzero(~light)[0]])        # new slot -> old slot
-        new_of_old = np.empty(self.nslots, dtype=np.int32)
-        new_of_old[order] = np.arange(self.nslots, dtype=np.int32)
-        dev = self.device
-
-        def remap(t):
-            a = t.cpu().numpy()
-            return torch.from_numpy(np.where(a >= 0, new_of_old[np.maximum(a, 0)], a).astype(np.int32)).to(dev)
-
-        self.cell_slot = remap(self.cell_slot)
-        if self.finest_slot is not None:
-            self.finest_slot = remap(self.finest_slot)
-        self.cellinfo_host = np.ascontiguousarray(self.cellinfo_host[order])
-        self.cellinfo = torch.from_numpy(self.cellinfo_host).to(dev)
-        self.dmask = self.dmask[torch.from_numpy(order).to(dev)].contiguous()
 
     def attach_tiles(self, Coeff):
         """Computes the coefficient tiles of the coarser-level supports from the 1-D subdivision matrices
@@ -473,7 +445,6 @@ def _desc(self):
     for k in range(3):
         d.degree[k] = self.degrees[k] if k < self.ndim else 0
     d.tile_stride, d.nslots, d.max_tiled = self.TS, self.nslots, self.max_tiled
-    d.n_light_slots = int(getattr(self, "n_light_slots", 0))
     for l in range(self.nlevels):
         for k in range(self.ndim):
             d.knot_off[l][k] = int(self.knot_off[l, k])

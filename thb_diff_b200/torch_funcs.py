@@ -112,7 +112,7 @@ class THB_fused_module(torch.nn.Module):
         m = THB_fused_module(space_or_packed, params); pts = m(ctrl_pts); pts.sum().backward()
     """
 
-    def __init__(self, space, params, device="cuda", cellnet=False):
+    def __init__(self, space, params, device="cuda", cellnet=True):
         super().__init__()
         self.P = space if isinstance(space, PackedHierarchy) else PackedHierarchy.from_space(space, device=device)
         self.plan = engine.Plan(self.P, params)
