@@ -46,6 +46,32 @@ def flop_model(degrees, cpd, n_in, nnz, nnz_tiled, nnz_sep=0):
     return float(executed), float(dense)
 
 
+def flop_model_local_net(P, plan, cpd, n_in, ppi):
+    """Executed FLOPs of the local-control-net kernel (thb_tile_impl.cuh, MODE_LIGHT): per point Cox-de Boor and the
+    sum-factorised contraction with the item's net (T + N0*N2 + N0 FMAs per output component, 3-D); per work item
+    the fold of its coarser-level supports into the net: per rank-one support 2 multiplications + cp_dim FMAs for each
+    of the TS window entries, per full tile cp_dim FMAs per entry; items of <= 16 points evaluate their rank-one
+    supports per point instead (one (p_k+1)-dot per dimension, two multiplications, the contraction)."""
+    import torch
+
+    deg = P.degrees
+    d = len(deg)
+    N = [p + 1 for p in deg] + ([1] if d == 2 else [])
+    T = N[0] * N[1] * N[2]
+    per_pt = sum(cdb_flops(p) for p in deg) + cpd * 2 * (T + N[0] * N[2] + N[0])
+    cnt = plan.cell_count[: P.nslots].long()
+    info = P.cellinfo.long()
+    nt, nsep = info[:, 5] - info[:, 7], info[:, 9]
+    nfull = nt - nsep
+    items = (cnt + ppi - 1) // ppi
+    last = cnt - (items - 1).clamp(min=0) * ppi                      # points of the last (possibly small) item
+    small = (items > 0) & (last <= 16) & (nsep > 0) & (nt <= 120)      # that item takes the per-point path
+    folded_items = items - small.long()
+    fold = (folded_items * nsep).sum() * P.TS * (2 + 2 * cpd) + (items * nfull).sum() * P.TS * 2 * cpd
+    sep_pp = (small.long() * last * nsep).sum() * (2 * sum(N[:d]) + (d - 1) + 2 * cpd)
+    return float(n_in * per_pt + fold + sep_pp)
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
@@ -202,7 +228,7 @@ def extras(sp, P, params, cp, hbm_peak):
         fit = ShardedFit(P, prm4, tgt, prm4.shape[0], cellnet=cellnet)
         l0 = float(fit.step(x, opt))
         t = time_cuda(lambda: fit.step(x, opt), iters=10, warm=2)
-        out["fit_c4_cellnet" if cellnet else "fit_c4_per_point_phi"] = {
+        out["fit_c4_local_net" if cellnet else "fit_c4_per_point_phi"] = {
             "adam_steps_per_s": 1e3 / t, "ms_per_step": t, "points": prm4.shape[0], "loss_first": l0, "loss_last": float(fit.step(x, opt)),
             "what": "10M unsorted random points (plan built once, as the reference precomputes PHI once), forward + backward + fused Adam"}
         del fit
@@ -299,7 +325,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dense", action="store_true", help="store one-hot tiles explicitly (SURVEY 8d's dense operation count)")
-    ap.add_argument("--cellnet", action="store_true", help="fold tiles into per-cell control nets (fewest FLOPs)")
+    ap.add_argument("--formulation", default="local_net", choices=["local_net", "per_point", "tile_net"],
+                    help="local_net (default): supports folded into a per-cell control net; per_point: PHI of every support per point")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-variants", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
@@ -327,8 +354,9 @@ def main():
     n = params.shape[0]
     plan = engine.Plan(P, params)
     n_in, nnz, nnz_tiled, nnz_sep = plan.stats(with_sep=True)
-    if args.dense or args.cellnet:
-        nnz_sep = 0 if args.dense else nnz_sep
+    if args.dense:
+        nnz_sep = 0
+        args.formulation = "per_point"
     out = [torch.zeros((n, 3), dtype=torch.float32, device=device)]
     st = torch.cuda.current_stream()
 
@@ -338,7 +366,7 @@ def main():
         plan.build()
         if timers is not None:
             timers[1].record()
-        engine.eval_fused(P, plan, cp, cellnet=args.cellnet, out=out)
+        engine.eval_fused(P, plan, cp, formulation=args.formulation, out=out)
         if timers is not None:
             timers[2].record()
 
@@ -376,7 +404,7 @@ def main():
     # ---- end to end through the public API with HOST buffers (pinned): H2D params, plan, fused eval, D2H geometry
     params_host = params.cpu().pin_memory()
     out_host = torch.empty((n, 3), dtype=torch.float32).pin_memory()
-    pipe = engine.HostPipeline(P, n, cp_dim=3, n_chunks=args.e2e_chunks, cellnet=args.cellnet)
+    pipe = engine.HostPipeline(P, n, cp_dim=3, n_chunks=args.e2e_chunks, formulation=args.formulation)
 
     def e2e_step():
         # public host-buffer API: chunked H2D -> plan + fused kernel -> D2H, overlapped on three streams
@@ -412,12 +440,14 @@ def main():
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     f_exec, f_dense = flop_model(P.degrees, 3, n_in, nnz, nnz_tiled, nnz_sep)
-    if args.cellnet:  # per point only the window dot products; tiles are folded once per work item
+    if args.formulation == "local_net":
+        f_exec = flop_model_local_net(P, plan, 3, n_in, engine.POINTS_PER_ITEM)
+    elif args.formulation == "tile_net":  # per point the tensor product and the window dot products; all tiles folded per item
         cnt = plan.cell_count[: P.nslots].long()
         nt = (P.cellinfo[:, 5] - P.cellinfo[:, 7]).long()
         items = (cnt + engine.POINTS_PER_ITEM - 1) // engine.POINTS_PER_ITEM
         f_exec = flop_model(P.degrees, 3, n_in, 0, 0)[0] + float((items * nt).sum()) * P.T * 2 * 4
-    tile_bytes = (P.sep_vec.numel() + P.full_tiles.numel()) * 4 if (getattr(P, "sep_vec", None) is not None and not args.cellnet) else P.tiles.numel() * 4
+    tile_bytes = (P.sep_vec.numel() + P.full_tiles.numel()) * 4 if (getattr(P, "sep_vec", None) is not None and args.formulation != "tile_net") else P.tiles.numel() * 4
     alg_bytes = n * (4 * P.ndim + 4 * 3 + 4) + tile_bytes + cp.numel() * 4
     t_fp32 = f_exec / (fp32_peak * 1e12)
     t_hbm = alg_bytes / (hbm_peak * 1e9)
@@ -429,7 +459,7 @@ def main():
     except Exception:
         pass
     roofline = {
-        "bound": bound, "kernel": "thb_tile::k_tile<4,4,4,PPT,3,FUSED>",
+        "bound": bound, "kernel": "thb_tile::k_tile<4,4,4,2,3,%s>" % ("LIGHT" if args.formulation == "local_net" else "FUSED"),
         "achieved": (f_exec / (kern_ms * 1e-3) / 1e12) if bound == "fp32" else (alg_bytes / (kern_ms * 1e-3) / 1e9),
         "peak": fp32_peak if bound == "fp32" else hbm_peak, "unit": "TFLOP/s" if bound == "fp32" else "GB/s",
         "frac": t_roof / (kern_ms * 1e-3), "traffic": traffic,
@@ -447,7 +477,7 @@ def main():
         "config": {"workload": "C3: 3-D degree-3 THB, 4 active levels (~25% refined per level, graded), 256^3 param grid per GPU",
                    "points_per_gpu": n, "nnz": nnz, "nnz_tiled": nnz_tiled, "nnz_tiled_rank_one": nnz_sep, "mean_supports": nnz / max(n_in, 1), "nCP": P.nCP,
                    "table_bytes": P.nbytes(), "l2": "inputs (201 MB params + 201 MB output per step) exceed the 126 MB L2",
-                   "tables": "dense one-hot tiles" if args.dense else "own-level supports direct, rank-one tiles as 3 factor vectors, full tiles otherwise", "cellnet": bool(args.cellnet),
+                   "tables": "dense one-hot tiles" if args.dense else "own-level supports direct, rank-one tiles as 3 factor vectors, full tiles otherwise", "formulation": args.formulation,
                    "sharding": f"y planes round-robin over {world} rank(s), no collective"},
         "clocks": clk.summary(), "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": n * P.ndim * 4, "d2h_bytes_per_step": n * 3 * 4,
@@ -459,36 +489,41 @@ def main():
 
     if rank == 0 and world == 1 and not args.no_variants:
         # the other two formulations of the same evaluation, for context (same plan, same inputs)
-        def time_variant(Pv, cellnet):
+        def time_variant(Pv, form):
             pl = engine.Plan(Pv, params)
             o = [torch.zeros((n, 3), dtype=torch.float32, device=device)]
             for _ in range(3):
-                engine.eval_fused(Pv, pl, cp, cellnet=cellnet, out=o)
+                engine.eval_fused(Pv, pl, cp, formulation=form, out=o)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             torch.cuda.synchronize()
             a.record()
             for _ in range(5):
-                engine.eval_fused(Pv, pl, cp, cellnet=cellnet, out=o)
+                engine.eval_fused(Pv, pl, cp, formulation=form, out=o)
             b.record()
             torch.cuda.synchronize()
             return a.elapsed_time(b) / 5, float((o[0] - out[0]).abs().max())
 
         var = {}
-        if not args.dense and not args.cellnet and getattr(P, "sep_vec", None) is not None:
+        if not args.dense and getattr(P, "sep_vec", None) is not None:
             keep = (P.sep_vec, P._desc_cache)
             P.sep_vec, P._desc_cache = None, None      # same tables without the rank-one split (every tiled support a full tile)
-            ms, dev = time_variant(P, False)
+            ms, dev = time_variant(P, "per_point")
             f_full = flop_model(P.degrees, 3, n_in, nnz, nnz_tiled, 0)[0]
             var["all_full_tiles"] = {"kernel_ms": ms, "max_abs_diff_vs_headline": dev, "frac_of_fp32_roofline": (f_full / (fp32_peak * 1e12)) / (ms * 1e-3)}
             P.sep_vec, P._desc_cache = keep[0], None
-        ms, dev = time_variant(P, not args.cellnet)
-        var["cellnet" if not args.cellnet else "per_point_phi"] = {"kernel_ms": ms, "max_abs_diff_vs_headline": dev}
+        for form in ("local_net", "per_point", "tile_net"):
+            if form != args.formulation and not args.dense:
+                ms, dev = time_variant(P, form)
+                var[form] = {"kernel_ms": ms, "max_abs_diff_vs_headline": dev}
+                if form == "per_point":  # PHI of every support formed per point (the reference's gather-multiply, fused)
+                    f_pp = flop_model(P.degrees, 3, n_in, nnz, nnz_tiled, nnz_sep)[0]
+                    var[form]["frac_of_fp32_roofline"] = (f_pp / (fp32_peak * 1e12)) / (ms * 1e-3)
         if not args.dense:
             from thb_diff_b200.packed import PackedHierarchy
 
             Pd = PackedHierarchy.from_space(sp, device=device, onehot_direct=False)
             Pd.sep_vec, Pd._desc_cache = None, None   # literally dense: every support a full (p+1)^d tile dot
-            ms, dev = time_variant(Pd, False)
+            ms, dev = time_variant(Pd, "per_point")
             var["dense_one_hot_tiles"] = {"kernel_ms": ms, "max_abs_diff_vs_headline": dev,
                                           "frac_of_fp32_roofline_8d": (f_dense / (fp32_peak * 1e12)) / (ms * 1e-3)}
             del Pd

@@ -79,8 +79,9 @@ typedef struct thb_space_desc {
 } thb_space_desc;
 
 /* A plan = the points of one batch grouped by active cell. All arrays are caller-allocated device memory:
- *   slot [N] i32, perm [N] i32, sorted_params [N, ndim] f32 (the params in cell order: sorted_params[j] =
- *   params[perm[j]]), cell_count/cell_start/cell_cursor [nslots+1] i32,
+ *   slot [N] i32, scratch [N] i32, sorted_params [N][4] f32 = the points in cell order as 16-byte records
+ *   (u0, u1, u2 or 0, caller index i as raw bits: record j of cell c, cell_start[c] <= j < cell_start[c+1], is point i),
+ *   cell_count/cell_start/cell_cursor [nslots+1] i32 (16-byte aligned: read / written as int4),
  *   items [max_items][16] i32 (slot, begin, count, level, c0, c1, c2, supp_off, S, tile_off, n_direct, n_sep,
  *   dmask lo, dmask hi, sep_off, full_off), counters [4] i32 (counters[0] = number of items).
  * max_items >= N / points_per_item + nslots. */
@@ -89,7 +90,7 @@ typedef struct thb_plan_desc {
     int32_t points_per_item;
     int32_t max_items;
     int32_t* slot;
-    int32_t* perm;
+    int32_t* scratch;
     float* sorted_params;
     int32_t* cell_count;
     int32_t* cell_start;

@@ -62,10 +62,12 @@ def test_compute_active_span_bit_exact(name):
         lev, c = cells[i]
         assert supp[i] == [(fl, tuple(fn)) for fl, fn in oa[lev][c]]
     # plan is a permutation grouped by cell
-    perm = supp.plan.perm[: supp.plan.n].cpu().numpy()
+    rec = supp.plan.sorted_params[: supp.plan.n].cpu().numpy()
+    perm = np.ascontiguousarray(rec[:, 3]).view(np.int32)
     assert np.array_equal(np.sort(perm), np.arange(len(perm)))
     slot_sorted = supp.slot.cpu().numpy()[perm]
     assert np.all(np.diff(slot_sorted) >= 0)
+    assert np.array_equal(rec[:, : h.ndim], np.asarray(g["params"], dtype=np.float32)[perm])
 
 
 def test_out_of_domain_points_are_flagged():

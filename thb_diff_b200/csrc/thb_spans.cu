@@ -325,83 +325,75 @@ __global__ void __launch_bounds__(256) k_plan_fixup(const __grid_constant__ thb_
 
 // pass 2 (single CTA): exclusive scan of the histogram -> cell_start; number of work items per cell and
 // their exclusive scan -> cell_cursor is reused to hold the first item index of each cell.
-// 4096 slots per round (int4 per thread), warp-shuffle scans, two barriers per round.  All loads of up to
-// kScanRounds rounds are issued before the first round is scanned, so the kernel pays ONE global-memory
-// latency instead of one per round (it is pure latency: 52 k slots = 13 rounds).
-constexpr int kScanRounds = 16;
-
+// Every thread owns a CONTIGUOUS run of slots (a multiple of 4, read as int4): it sums its run, one block-wide scan
+// of the 1024 run totals follows (warp shuffles, two barriers in all), then it re-reads its run (L1 hits) and writes
+// the prefix sums.  The earlier round-by-round form paid two barriers per 4096 slots (13 rounds for C3's 52 k slots).
 __global__ void __launch_bounds__(1024) k_plan_scan(const int32_t* __restrict__ count, int32_t* __restrict__ start,
                                                     int32_t* __restrict__ item_start, int nslots, int ppi,
                                                     int32_t* __restrict__ counters) {
     __shared__ int s_wp[32], s_wi[32];
-    __shared__ int s_carry[2];
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-    if (t == 0) s_carry[0] = s_carry[1] = 0;
-    __syncthreads();
-    for (int base0 = 0; base0 < nslots; base0 += 4096 * kScanRounds) {
-        int4 cv[kScanRounds];
-#pragma unroll
-        for (int r = 0; r < kScanRounds; ++r) {
-            const int i0 = base0 + r * 4096 + 4 * t;
-            cv[r] = make_int4(0, 0, 0, 0);
-            if (i0 + 3 < nslots) {
-                cv[r] = *reinterpret_cast<const int4*>(count + i0);  // count has nslots+1 entries, 16-byte aligned rows
-            } else {
-                if (i0 < nslots) cv[r].x = count[i0];
-                if (i0 + 1 < nslots) cv[r].y = count[i0 + 1];
-                if (i0 + 2 < nslots) cv[r].z = count[i0 + 2];
-            }
+    const int per = (((nslots + 1023) >> 10) + 3) & ~3;
+    const int b0 = t * per, b1 = min(b0 + per, nslots);
+    int tp = 0, ti = 0;
+    for (int i = b0; i < b1; i += 4) {
+        int4 c = make_int4(0, 0, 0, 0);
+        if (i + 3 < nslots) {
+            c = *reinterpret_cast<const int4*>(count + i);  // count has nslots+1 entries in a 16-byte aligned row
+        } else {
+            c.x = count[i];
+            if (i + 1 < nslots) c.y = count[i + 1];
+            if (i + 2 < nslots) c.z = count[i + 2];
         }
+        tp += c.x + c.y + c.z + c.w;
+        ti += (c.x + ppi - 1) / ppi + (c.y + ppi - 1) / ppi + (c.z + ppi - 1) / ppi + (c.w + ppi - 1) / ppi;
+    }
+    int sp_ = tp, si_ = ti;  // inclusive warp scan of the run totals
 #pragma unroll
-        for (int r = 0; r < kScanRounds; ++r) {
-            const int base = base0 + r * 4096;
-            if (base >= nslots) break;
-            const int i0 = base + 4 * t;
-            const int c[4] = {cv[r].x, cv[r].y, cv[r].z, cv[r].w};
-            int m[4];
+    for (int o = 1; o < 32; o <<= 1) {
+        const int a = __shfl_up_sync(0xffffffffu, sp_, o), b2 = __shfl_up_sync(0xffffffffu, si_, o);
+        if (lane >= o) { sp_ += a; si_ += b2; }
+    }
+    if (lane == 31) { s_wp[w] = sp_; s_wi[w] = si_; }
+    __syncthreads();
+    if (w == 0) {
+        int a = s_wp[lane], b2 = s_wi[lane];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) m[k] = (c[k] + ppi - 1) / ppi;
-            const int tp = c[0] + c[1] + c[2] + c[3], ti = m[0] + m[1] + m[2] + m[3];
-            int sp_ = tp, si_ = ti;  // inclusive warp scan of the per-thread totals
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int a = __shfl_up_sync(0xffffffffu, sp_, o), b2 = __shfl_up_sync(0xffffffffu, si_, o);
-                if (lane >= o) { sp_ += a; si_ += b2; }
+        for (int o = 1; o < 32; o <<= 1) {
+            const int x = __shfl_up_sync(0xffffffffu, a, o), y = __shfl_up_sync(0xffffffffu, b2, o);
+            if (lane >= o) { a += x; b2 += y; }
+        }
+        s_wp[lane] = a;
+        s_wi[lane] = b2;
+    }
+    __syncthreads();
+    int rp = (w ? s_wp[w - 1] : 0) + sp_ - tp;
+    int ri = (w ? s_wi[w - 1] : 0) + si_ - ti;
+    for (int i = b0; i < b1; i += 4) {
+        if (i + 3 < nslots) {
+            const int4 c = *reinterpret_cast<const int4*>(count + i);
+            int4 ps, is;
+            ps.x = rp; is.x = ri; rp += c.x; ri += (c.x + ppi - 1) / ppi;
+            ps.y = rp; is.y = ri; rp += c.y; ri += (c.y + ppi - 1) / ppi;
+            ps.z = rp; is.z = ri; rp += c.z; ri += (c.z + ppi - 1) / ppi;
+            ps.w = rp; is.w = ri; rp += c.w; ri += (c.w + ppi - 1) / ppi;
+            *reinterpret_cast<int4*>(start + i) = ps;
+            *reinterpret_cast<int4*>(item_start + i) = is;
+        } else {
+            for (int k = i; k < nslots; ++k) {
+                const int c = count[k];
+                start[k] = rp;
+                item_start[k] = ri;
+                rp += c;
+                ri += (c + ppi - 1) / ppi;
             }
-            if (lane == 31) { s_wp[w] = sp_; s_wi[w] = si_; }
-            __syncthreads();
-            if (w == 0) {
-                int a = s_wp[lane], b2 = s_wi[lane];
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int x = __shfl_up_sync(0xffffffffu, a, o), y = __shfl_up_sync(0xffffffffu, b2, o);
-                    if (lane >= o) { a += x; b2 += y; }
-                }
-                s_wp[lane] = a;
-                s_wi[lane] = b2;
-            }
-            __syncthreads();
-            int rp = s_carry[0] + (w ? s_wp[w - 1] : 0) + sp_ - tp;
-            int ri = s_carry[1] + (w ? s_wi[w - 1] : 0) + si_ - ti;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (i0 + k < nslots) {
-                    start[i0 + k] = rp;
-                    item_start[i0 + k] = ri;
-                }
-                rp += c[k];
-                ri += m[k];
-            }
-            __syncthreads();
-            if (t == 1023) { s_carry[0] = rp; s_carry[1] = ri; }
-            __syncthreads();
         }
     }
-    if (t == 0) {
-        start[nslots] = s_carry[0];
-        counters[0] = s_carry[1];  // number of work items
-        counters[1] = 0;           // dynamic scheduler cursor
-        counters[2] = s_carry[0];  // number of in-domain points
+    if (t == 1023) {
+        start[nslots] = s_wp[31];
+        counters[0] = s_wi[31];  // number of work items
+        counters[1] = 0;         // dynamic scheduler cursor
+        counters[2] = s_wp[31];  // number of in-domain points
     }
 }
 
@@ -418,7 +410,7 @@ __global__ void __launch_bounds__(256) k_plan_items(const __grid_constant__ thb_
     __syncwarp();
     const int m = (c + ppi - 1) / ppi;
     if (m == 0) {
-        if (lane == 0) item_start_then_cursor[s] = 0;
+        if (lane == 0) item_start_then_cursor[s] = b;
         return;
     }
     const int4* ci = reinterpret_cast<const int4*>(sp.cellinfo + (int64_t)s * THB_INFO_W);
@@ -433,23 +425,26 @@ __global__ void __launch_bounds__(256) k_plan_items(const __grid_constant__ thb_
             o[3] = make_int4((int)(unsigned)(dm & 0xffffffffull), (int)(unsigned)(dm >> 32), f.x, f.z);
         }
     }
-    if (lane == 0) item_start_then_cursor[s] = 0;
+    if (lane == 0) item_start_then_cursor[s] = b;  // from here on the scatter cursor of the cell: next free place
 }
 
-// pass 4: scatter point ids AND the points themselves into cell order; lanes of one warp that share a slot
-// take consecutive places, which keeps runs of neighbouring points contiguous.
+// pass 4: scatter the points into cell order as 16-byte records (u0, u1, u2 or 0, caller index as bits) -- one
+// STG.128 per point here, one 16-byte cp.async per point in the evaluation kernels.  Lanes of one warp that share a
+// slot take consecutive places, which keeps runs of neighbouring points contiguous.  The cursor of a cell starts at
+// the cell's first place (k_plan_items), so one atomic returns the destination.
+constexpr int kScatterPts = 2;
 __global__ void __launch_bounds__(256) k_plan_scatter(const int32_t* __restrict__ slot, const float* __restrict__ params, int ndim,
-                                                      int64_t n, const int32_t* __restrict__ start, int32_t* __restrict__ cursor,
-                                                      int32_t* __restrict__ perm, float* __restrict__ sorted) {
+                                                      int64_t n, int32_t* __restrict__ cursor, float4* __restrict__ sorted) {
+    constexpr int H = kScatterPts;
     const int lane = threadIdx.x & 31;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    const int64_t nround = (n + 2 * stride - 1) / (2 * stride) * (2 * stride);
-    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < nround; i0 += 2 * stride) {
-        int s[2], st[2], base[2], leader[2];
-        unsigned peers[2];
-        float u[2][3];
+    const int64_t nround = (n + H * stride - 1) / (H * stride) * (H * stride);
+    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < nround; i0 += H * stride) {
+        int s[H], base[H], leader[H];
+        unsigned peers[H];
+        float u[H][3];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {  // all loads of both points first
+        for (int h = 0; h < H; ++h) {  // all loads of the points first
             const int64_t i = i0 + h * stride;
             const int64_t j = i < n ? i : 0;
             s[h] = i < n ? slot[j] : -1;
@@ -458,22 +453,18 @@ __global__ void __launch_bounds__(256) k_plan_scatter(const int32_t* __restrict_
             u[h][2] = ndim == 3 ? params[j * ndim + 2] : 0.f;
         }
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            st[h] = s[h] >= 0 ? __ldg(start + s[h]) : 0;
+        for (int h = 0; h < H; ++h) {
             peers[h] = __match_any_sync(0xffffffffu, s[h]);
             leader[h] = __ffs(peers[h]) - 1;
             base[h] = 0;
             if (s[h] >= 0 && lane == leader[h]) base[h] = atomicAdd(cursor + s[h], __popc(peers[h]));
         }
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < H; ++h) {
             base[h] = __shfl_sync(0xffffffffu, base[h], leader[h]);
             if (s[h] >= 0) {
-                const int64_t pos = (int64_t)st[h] + base[h] + __popc(peers[h] & ((1u << lane) - 1u));
-                perm[pos] = (int32_t)(i0 + h * stride);
-                sorted[pos * ndim] = u[h][0];
-                sorted[pos * ndim + 1] = u[h][1];
-                if (ndim == 3) sorted[pos * ndim + 2] = u[h][2];
+                const int64_t pos = (int64_t)base[h] + __popc(peers[h] & ((1u << lane) - 1u));
+                sorted[pos] = make_float4(u[h][0], u[h][1], u[h][2], __int_as_float((int32_t)(i0 + h * stride)));
             }
         }
     }
@@ -549,9 +540,11 @@ extern "C" int thb_plan_build(const thb_space_desc* space, const float* params, 
     if (rc) return rc;
     THB_REQUIRE(plan && plan->npoints >= 0 && plan->npoints < (int64_t)2147483647, "thb_plan_build: bad point count");
     THB_REQUIRE(plan->points_per_item >= 32 && plan->points_per_item <= 1024, "thb_plan_build: points_per_item out of range");
-    THB_REQUIRE(plan->slot && plan->perm && plan->sorted_params && plan->cell_count && plan->cell_start && plan->cell_cursor && plan->items && plan->counters,
+    THB_REQUIRE(plan->slot && plan->scratch && plan->sorted_params && plan->cell_count && plan->cell_start && plan->cell_cursor && plan->items && plan->counters,
                 "thb_plan_build: null plan buffer");
     THB_REQUIRE((int64_t)plan->max_items >= plan->npoints / plan->points_per_item + space->nslots, "thb_plan_build: max_items too small");
+    THB_REQUIRE((((uintptr_t)plan->cell_count | (uintptr_t)plan->cell_start | (uintptr_t)plan->cell_cursor) & 15) == 0,
+                "thb_plan_build: cell_count / cell_start / cell_cursor must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t n = plan->npoints;
     const int ns = space->nslots;
@@ -562,10 +555,10 @@ extern "C" int thb_plan_build(const thb_space_desc* space, const float* params, 
         for (int k = 0; k < space->ndim; ++k) finest_knots += space->knot_len[space->nlevels - 1][k];
         if (space->span_lut && space->finest_slot && finest_knots <= kPlanSmemKnots) {
             THB_CUDA(cudaMemsetAsync(plan->counters + 3, 0, sizeof(int32_t), st));
-            // plan->perm is free until the scatter pass: it holds the (normally empty) list of unverified points
-            k_plan_count_fast<<<grid_for(n, 256, 16), 256, 0, st>>>(*space, params, n, plan->slot, plan->cell_count, plan->perm, plan->counters);
+            // plan->scratch holds the (normally empty) list of unverified points
+            k_plan_count_fast<<<grid_for(n, 256, 16), 256, 0, st>>>(*space, params, n, plan->slot, plan->cell_count, plan->scratch, plan->counters);
             THB_LAUNCHED();
-            k_plan_fixup<<<thb_num_sms(), 256, 0, st>>>(*space, params, plan->perm, plan->counters, plan->slot, plan->cell_count);
+            k_plan_fixup<<<thb_num_sms(), 256, 0, st>>>(*space, params, plan->scratch, plan->counters, plan->slot, plan->cell_count);
             THB_LAUNCHED();
         } else {
             k_plan_count<<<grid_for(n, 256, 16), 256, 0, st>>>(*space, params, n, plan->slot, plan->cell_count);
@@ -578,8 +571,8 @@ extern "C" int thb_plan_build(const thb_space_desc* space, const float* params, 
                                                    plan->max_items, (int4*)plan->items);
     THB_LAUNCHED();
     if (n > 0) {
-        k_plan_scatter<<<grid_for(n, 256, 16), 256, 0, st>>>(plan->slot, params, space->ndim, n, plan->cell_start, plan->cell_cursor,
-                                                             plan->perm, plan->sorted_params);
+        k_plan_scatter<<<grid_for(n, 256, 16), 256, 0, st>>>(plan->slot, params, space->ndim, n, plan->cell_cursor,
+                                                             (float4*)plan->sorted_params);
         THB_LAUNCHED();
     }
     return THB_OK;

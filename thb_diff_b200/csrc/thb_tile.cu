@@ -35,7 +35,7 @@ static int env_int(const char* name, int dflt) {
 using namespace thb_tile;
 
 static int check_plan(const thb_plan_desc* plan, const char* who) {
-    THB_REQUIRE(plan && plan->perm && plan->sorted_params && plan->items && plan->counters, "%s: null plan buffer", who);
+    THB_REQUIRE(plan && plan->sorted_params && plan->items && plan->counters, "%s: null plan buffer", who);
     return THB_OK;
 }
 
@@ -68,7 +68,7 @@ extern "C" int thb_basis_tiled(const thb_space_desc* space, const thb_plan_desc*
         THB_REQUIRE(phi_out_host[c], "thb_basis_tiled: null output");
         ar.out[c] = phi_out_host[c];
     }
-    ar.perm = plan->perm; ar.items = (const int4*)plan->items; ar.counters = plan->counters;
+    ar.items = (const int4*)plan->items; ar.counters = plan->counters;
     ar.params = params; ar.sorted = plan->sorted_params; ar.offsets = offsets;
     cudaStream_t st = (cudaStream_t)stream;
     THB_CUDA(cudaMemsetAsync(plan->counters + 1, 0, sizeof(int32_t), st));
@@ -93,7 +93,7 @@ extern "C" int thb_eval_fused(const thb_space_desc* space, const thb_plan_desc* 
         THB_REQUIRE(out_host[c], "thb_eval_fused: null output");
         ar.out[c] = out_host[c];
     }
-    ar.perm = plan->perm; ar.items = (const int4*)plan->items; ar.counters = plan->counters;
+    ar.items = (const int4*)plan->items; ar.counters = plan->counters;
     ar.params = params; ar.sorted = plan->sorted_params; ar.ctrl_pts = ctrl_pts; ar.cellnet = formulation == THB_EVAL_TILE_NET ? 1 : 0;
     cudaStream_t st = (cudaStream_t)stream;
     THB_CUDA(cudaMemsetAsync(plan->counters + 1, 0, sizeof(int32_t), st));
@@ -117,7 +117,7 @@ extern "C" int thb_eval_fused_backward(const thb_space_desc* space, const thb_pl
     const ShapeOps* ops = find_shape(space);
     if (!ops) return thb_set_error(THB_E_UNSUPPORTED, "thb_eval_fused_backward: no kernel for degrees (%d,%d,%d)", space->degree[0], space->degree[1], space->degree[2]);
     Args ar = {};
-    ar.perm = plan->perm; ar.items = (const int4*)plan->items; ar.counters = plan->counters;
+    ar.items = (const int4*)plan->items; ar.counters = plan->counters;
     ar.params = params; ar.sorted = plan->sorted_params; ar.grad_out = grad_out; ar.grad_cp = grad_ctrl_pts;
     THB_CUDA(cudaMemsetAsync(plan->counters + 1, 0, sizeof(int32_t), st));
     return ops->backward(space, &ar, cp_dim, st);

@@ -38,11 +38,10 @@ constexpr int kChunk = 64;
 enum { MODE_FUSED = 0, MODE_BASIS = 1, MODE_LIGHT = 2 };
 
 struct Args {
-    const int32_t* perm;
     const int4* items;
     int32_t* counters;  // [0] = number of items, [1] = scheduler cursor
     const float* params;
-    const float* sorted;     // plan->sorted_params (cell order)
+    const float* sorted;     // plan->sorted_params: [N][4] records in cell order (u0, u1, u2 or 0, caller index bits)
     const float* ctrl_pts;   // fused
     const int64_t* offsets;  // basis: exclusive prefix sum of num_supp (caller order)
     float* out[4];           // per channel: fused [N, cp_dim] / basis [nnz]
@@ -232,8 +231,7 @@ struct WarpSmem {
     float knots[2][3][8];                 // local knots of the item's cell, per dimension
     float rk[3][8];                       // reciprocal knot differences of the current item
     float cpw[2][4][SH::TS];              // own-level window control points (SoA, 0 where inactive)
-    int pidx[2][64];                      // caller-order index of the points of a sub-batch
-    float pu[2][3][64];                   // their parameters (SoA)
+    float4 prec[2][64];                   // point records of a sub-batch: (u0, u1, u2, caller-order index as bits)
     static constexpr int kCC = MODE == MODE_LIGHT ? kMaxLight : kMaxCC;
     float4 cc[kCC];                       // control points of the coarser-level supports (rank-one ones first)
     float4 sepv[MODE != MODE_BASIS ? kCC : 1][3];  // factor vectors of the rank-one tiled supports
@@ -250,16 +248,13 @@ struct WarpSmem {
 };
 
 template <int PPT>
-THB_DEV void prefetch_points(const Args& ar, int d, int begin, int count, int base, int* pidx, float (*pu)[64]) {
+THB_DEV void prefetch_points(const Args& ar, int begin, int count, int base, float4* prec) {
     const int lane = threadIdx.x;
+    const float4* src = reinterpret_cast<const float4*>(ar.sorted);
 #pragma unroll
     for (int q = 0; q < PPT; ++q) {
         const int li = base + q * 32 + lane;
-        const int64_t j = begin + (li < count ? li : 0);
-        cp_async4(pidx + q * 32 + lane, ar.perm + j);
-#pragma unroll
-        for (int k = 0; k < 3; ++k)
-            if (k < d) cp_async4(&pu[k][q * 32 + lane], ar.sorted + j * d + k);
+        cp_async16(prec + q * 32 + lane, src + begin + (li < count ? li : 0));
     }
 }
 
@@ -363,9 +358,10 @@ THB_DEV void warp_points(const thb_space_desc& sp, const Args& ar, const Item& i
 #pragma unroll
     for (int q = 0; q < PPT; ++q) {
         valid[q] = base + q * 32 + lane < it.count;
-        idx[q] = sm.pidx[pb][q * 32 + lane];
+        const float4 rec = sm.prec[pb][q * 32 + lane];
+        idx[q] = __float_as_int(rec.w);
         if (MODE == MODE_BASIS) off[q] = __ldg(ar.offsets + idx[q]);
-        const float u[3] = {sm.pu[pb][0][q * 32 + lane], sm.pu[pb][1][q * 32 + lane], SH::N2 > 1 ? sm.pu[pb][2][q * 32 + lane] : 0.f};
+        const float u[3] = {rec.x, rec.y, rec.z};
         bs[q].eval(u, sm.knots[tb], sm.rk);
         if (MODE == MODE_BASIS) sm.poff[q * 32 + lane] = off[q];
     }
@@ -689,8 +685,9 @@ THB_DEV void warp_points_light(const Args& ar, const Item& it, int base, WarpSme
 #pragma unroll
     for (int q = 0; q < PPT; ++q) {
         valid[q] = base + q * 32 + lane < it.count;
-        idx[q] = sm.pidx[pb][q * 32 + lane];
-        const float u[3] = {sm.pu[pb][0][q * 32 + lane], sm.pu[pb][1][q * 32 + lane], N2 > 1 ? sm.pu[pb][2][q * 32 + lane] : 0.f};
+        const float4 rec = sm.prec[pb][q * 32 + lane];
+        idx[q] = __float_as_int(rec.w);
+        const float u[3] = {rec.x, rec.y, rec.z};
         bs[q].eval(u, sm.knots[tb], sm.rk);
     }
     for (int chi = 0; chi < ar.nch; ++chi) {
@@ -856,7 +853,7 @@ __global__ void __launch_bounds__(kThreads, MODE == MODE_LIGHT ? THB_LIGHT_MINB 
     if (lane < 4 && id1 < nitems) cp_async16(&sm.rec[1][lane], ar.items + (int64_t)id1 * 4 + lane);
     if (lane < 4 && id2 < nitems) cp_async16(&sm.rec[2][lane], ar.items + (int64_t)id2 * 4 + lane);
     prefetch_item_tables<SH, CPD>(sp, ar, it, sm.knots[0], sm.cpw[0], want_cp);
-    prefetch_points<PPT>(ar, d, it.begin, it.count, 0, sm.pidx[0], sm.pu[0]);
+    prefetch_points<PPT>(ar, it.begin, it.count, 0, sm.prec[0]);
     cp_async_commit();
     int nn_id = 0;
     if (lane == 0) nn_id = atomicAdd(cursor, 1);
@@ -940,11 +937,11 @@ __global__ void __launch_bounds__(kThreads, MODE == MODE_LIGHT ? THB_LIGHT_MINB 
         for (int base = 0; base < it.count; base += SB) {
             // prefetch the next sub-batch: same item, or the first one of the next item together with its tables
             if (base + SB < it.count) {
-                prefetch_points<PPT>(ar, d, it.begin, it.count, base + SB, sm.pidx[pb ^ 1], sm.pu[pb ^ 1]);
+                prefetch_points<PPT>(ar, it.begin, it.count, base + SB, sm.prec[pb ^ 1]);
             } else if (nx_valid) {
                 const int4* r = sm.rec[(ring + 1) % 3];
                 const Item nx = unpack_item(r[0], r[1], r[2], r[3]);
-                prefetch_points<PPT>(ar, d, nx.begin, nx.count, 0, sm.pidx[pb ^ 1], sm.pu[pb ^ 1]);
+                prefetch_points<PPT>(ar, nx.begin, nx.count, 0, sm.prec[pb ^ 1]);
                 prefetch_item_tables<SH, CPD>(sp, ar, nx, sm.knots[tb ^ 1], sm.cpw[tb ^ 1], want_cp);
             }
             cp_async_commit();
@@ -1023,9 +1020,9 @@ __global__ void __launch_bounds__(kBwdThreads) k_tile_backward(const __grid_cons
         for (int base = 0; base < it.count; base += kBwdThreads) {
             const int li = base + tid;
             const bool valid = li < it.count;
-            const int idx = __ldg(ar.perm + it.begin + (valid ? li : 0));
-            float u[3] = {0.f, 0.f, 0.f};
-            for (int k = 0; k < d; ++k) u[k] = __ldg(ar.params + (int64_t)idx * d + k);
+            const float4 rec = __ldg(reinterpret_cast<const float4*>(ar.sorted) + it.begin + (valid ? li : 0));
+            const int idx = __float_as_int(rec.w);
+            const float u[3] = {rec.x, rec.y, rec.z};
             Bases<SH, false> bs;
             bs.eval(u, s_knots);
             float tp[TS];

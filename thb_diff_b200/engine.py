@@ -45,8 +45,8 @@ class Plan:
         i32 = dict(dtype=torch.int32, device=dev)
         self.n = n
         self.slot = torch.empty(max(n, 1), **i32)
-        self.perm = torch.empty(max(n, 1), **i32)
-        self.sorted_params = torch.empty((max(n, 1), P.ndim), dtype=torch.float32, device=dev)
+        self.scratch = torch.empty(max(n, 1), **i32)
+        self.sorted_params = torch.empty((max(n, 1), 4), dtype=torch.float32, device=dev)  # (u0, u1, u2|0, caller index bits)
         self.cell_count = torch.empty(P.nslots + 1, **i32)
         self.cell_start = torch.empty(P.nslots + 1, **i32)
         self.cell_cursor = torch.empty(P.nslots + 1, **i32)
@@ -55,7 +55,7 @@ class Plan:
         self.counters = torch.zeros(4, **i32)
         d = PlanDesc()
         d.npoints, d.points_per_item, d.max_items = n, points_per_item, self.max_items
-        d.slot, d.perm, d.sorted_params = self.slot.data_ptr(), self.perm.data_ptr(), self.sorted_params.data_ptr()
+        d.slot, d.scratch, d.sorted_params = self.slot.data_ptr(), self.scratch.data_ptr(), self.sorted_params.data_ptr()
         d.cell_count, d.cell_start, d.cell_cursor = self.cell_count.data_ptr(), self.cell_start.data_ptr(), self.cell_cursor.data_ptr()
         d.items, d.counters = self.items.data_ptr(), self.counters.data_ptr()
         self.desc = d
@@ -236,8 +236,9 @@ class HostPipeline:
     plan + fused kernel of chunk c and the D2H copy of chunk c-1 (PCIe is full duplex), so a step costs about
     max(H2D, D2H, compute) instead of their sum.  Device buffers are allocated once."""
 
-    def __init__(self, P, n_points, cp_dim=3, n_chunks=8, cellnet=True):
-        self.P, self.n, self.cpd, self.cellnet = P, int(n_points), cp_dim, cellnet
+    def __init__(self, P, n_points, cp_dim=3, n_chunks=8, cellnet=True, formulation=None):
+        self.P, self.n, self.cpd = P, int(n_points), cp_dim
+        self.formulation = formulation if formulation is not None else ("local_net" if cellnet else "per_point")
         n_chunks = max(1, min(n_chunks, (self.n + 65535) // 65536))
         base, rem = divmod(self.n, n_chunks)
         self.bounds = []
@@ -277,7 +278,7 @@ class HostPipeline:
                     pl = self.plans[b] = Plan(self.P, self.pbuf[b][:m])
                 else:
                     pl.build()
-                eval_fused(self.P, pl, ctrl_pts, cellnet=self.cellnet, out=[self.obuf[b][:m]])
+                eval_fused(self.P, pl, ctrl_pts, formulation=self.formulation, out=[self.obuf[b][:m]])
                 done[c] = torch.cuda.Event()
                 done[c].record(self.s_cmp)
             with torch.cuda.stream(self.s_out):
