@@ -237,61 +237,65 @@ __global__ void __launch_bounds__(256) k_plan_count(const __grid_constant__ thb_
 // straight-line code per point -- bin -> candidate cell -> one comparison -> verification against the two bracketing
 // breakpoints -> one slot lookup.  A point whose span is not verified (possible only for knot vectors the tables do
 // not resolve) is appended to `fail_list` and handled by k_plan_fixup with the robust search.
+template <int D>
 __global__ void __launch_bounds__(256) k_plan_count_fast(const __grid_constant__ thb_space_desc sp, const float* __restrict__ params,
-                                                         int64_t n, int32_t* __restrict__ slot_out, int32_t* __restrict__ count,
+                                                         unsigned n, int32_t* __restrict__ slot_out, int32_t* __restrict__ count,
                                                          int32_t* __restrict__ fail_list, int32_t* __restrict__ counters) {
     __shared__ float sk[kPlanSmemKnots];
     PlanKnots pk;
     stage_finest_knots(sp, sk, pk);
-    const int L = sp.nlevels - 1, d = sp.ndim;
-    const int32_t* lut[3];
-    int nb[3], nc[3];
-    float ls[3];
+    const int L = sp.nlevels - 1;
+    const int32_t* lut[D];
+    int nbm1[D], ncm1[D], off[D];
+    float ls[D], u0[D], u1[D];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
+    for (int k = 0; k < D; ++k) {
         lut[k] = sp.span_lut + sp.lut_off[k];
-        nb[k] = sp.lut_n[k];
+        nbm1[k] = sp.lut_n[k] - 1;
+        ncm1[k] = sp.ncells[L][k] - 1;
         ls[k] = sp.lut_scale[k];
-        nc[k] = k < d ? sp.ncells[L][k] : 1;
+        off[k] = pk.off[k];
+        u0[k] = pk.u0[k];
+        u1[k] = pk.u1[k];
     }
-    const int n1 = sp.ncells[L][1], n2 = d == 3 ? sp.ncells[L][2] : 1;
-    const int lane = threadIdx.x & 31;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    const int64_t nround = (n + 2 * stride - 1) / (2 * stride) * (2 * stride);
-    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < nround; i0 += 2 * stride) {
-        float u[2][3];
+    const int n1 = sp.ncells[L][1], n2 = D == 3 ? sp.ncells[L][2] : 1;
+    const int32_t* __restrict__ fslot = sp.finest_slot;
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned stride = gridDim.x * blockDim.x;
+    const unsigned nround = (n + 2 * stride - 1) / (2 * stride) * (2 * stride);  // n < 2^31 and stride < 2^20: no overflow
+    for (unsigned i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < nround; i0 += 2 * stride) {
+        float u[2][D];
         int slot[2];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            const int64_t i = i0 + h * stride;
-            const int64_t j = i < n ? i : 0;
-            u[h][0] = params[j * d];
-            u[h][1] = params[j * d + 1];
-            u[h][2] = d == 3 ? params[j * d + 2] : 0.f;
+            const unsigned i = i0 + h * stride;
+            const float* src = params + (size_t)(i < n ? i : 0u) * D;
+#pragma unroll
+            for (int k = 0; k < D; ++k) u[h][k] = src[k];
         }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            const int64_t i = i0 + h * stride;
+            const unsigned i = i0 + h * stride;
             bool inside = true, good = true;
-            int c[3] = {0, 0, 0};
+            int c[D];
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                if (k < d) {
-                    const float x = u[h][k];
-                    const bool in = (x >= pk.u0[k]) && (x <= pk.u1[k]);   // false for NaN
-                    const float* B = sk + pk.off[k];
-                    const int bin = in ? min((int)((x - pk.u0[k]) * ls[k]), nb[k] - 1) : 0;
-                    int cc = __ldg(lut[k] + bin);
-                    cc = min(cc + (int)(x >= B[cc + 1]), nc[k] - 1);
-                    good = good && (x >= B[cc]) && ((x < B[cc + 1]) || (cc == nc[k] - 1));
-                    inside = inside && in;
-                    c[k] = cc;
-                }
+            for (int k = 0; k < D; ++k) {
+                const float x = u[h][k];
+                const bool in = (x >= u0[k]) && (x <= u1[k]);   // false for NaN
+                const int bin = in ? min((int)((x - u0[k]) * ls[k]), nbm1[k]) : 0;
+                int cc = __ldg(lut[k] + bin) + off[k];          // index into sk of the candidate cell's left breakpoint
+                cc += (x >= sk[cc + 1]) ? 1 : 0;
+                cc = min(cc, ncm1[k] + off[k]);
+                good &= (x >= sk[cc]) && ((x < sk[cc + 1]) || (cc == ncm1[k] + off[k]));
+                inside &= in;
+                c[k] = cc - off[k];
             }
             int sl = -1;
             if (i < n) {
                 if (inside && good) {
-                    sl = __ldg(sp.finest_slot + (c[0] * n1 + c[1]) * n2 + c[2]);
+                    int lin = c[0] * n1 + c[1];
+                    if (D == 3) lin = lin * n2 + c[2];
+                    sl = __ldg(fslot + lin);
                     slot_out[i] = sl;
                 } else if (!inside) {
                     slot_out[i] = -1;
@@ -304,7 +308,7 @@ __global__ void __launch_bounds__(256) k_plan_count_fast(const __grid_constant__
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const unsigned peers = __match_any_sync(0xffffffffu, slot[h]);
-            if (slot[h] >= 0 && lane == (__ffs(peers) - 1)) atomicAdd(count + slot[h], __popc(peers));
+            if (slot[h] >= 0 && lane == (unsigned)(__ffs(peers) - 1)) atomicAdd(count + slot[h], __popc(peers));
         }
     }
 }
@@ -556,7 +560,10 @@ extern "C" int thb_plan_build(const thb_space_desc* space, const float* params, 
         if (space->span_lut && space->finest_slot && finest_knots <= kPlanSmemKnots) {
             THB_CUDA(cudaMemsetAsync(plan->counters + 3, 0, sizeof(int32_t), st));
             // plan->scratch holds the (normally empty) list of unverified points
-            k_plan_count_fast<<<grid_for(n, 256, 16), 256, 0, st>>>(*space, params, n, plan->slot, plan->cell_count, plan->scratch, plan->counters);
+            if (space->ndim == 3)
+                k_plan_count_fast<3><<<grid_for(n, 256, 16), 256, 0, st>>>(*space, params, (unsigned)n, plan->slot, plan->cell_count, plan->scratch, plan->counters);
+            else
+                k_plan_count_fast<2><<<grid_for(n, 256, 16), 256, 0, st>>>(*space, params, (unsigned)n, plan->slot, plan->cell_count, plan->scratch, plan->counters);
             THB_LAUNCHED();
             k_plan_fixup<<<thb_num_sms(), 256, 0, st>>>(*space, params, plan->scratch, plan->counters, plan->slot, plan->cell_count);
             THB_LAUNCHED();
