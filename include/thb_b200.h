@@ -162,8 +162,8 @@ THB_API int thb_basis_dense(const float* params, int64_t npoints, int ndim, cons
 /* ---- fused basis + evaluation (PHI never leaves the SM) ----------------------------------------------------
  * out_host[c] is a device buffer [N, cp_dim] per channel.  Replaces THB_basis_fns followed by THBEval.forward
  * (THB/torch_funcs.py:22-33).  formulation selects how sum_s PHI_s(u) CP_s is evaluated (same result to rounding):
- *   THB_EVAL_LOCAL_NET (0, default)  coarser-level supports are folded into the cell's local control net once per work
- *                                    item, points are evaluated against the net by sum factorisation
+ *   THB_EVAL_LOCAL_NET (0, default)  thb_cell_nets for the cells that hold points of the plan + thb_eval_nets (below);
+ *                                    needs `workspace` (thb_net_workspace_floats floats), NULL for the other two
  *   THB_EVAL_TILE_NET  (1)           the per-point tile kernel with a per-item fold of all tiles
  *   THB_EVAL_PER_POINT (2)           PHI_s(u) of every support is formed per point, then contracted -- the reference's
  *                                    gather-multiply + contraction, without PHI leaving the SM */
@@ -172,7 +172,20 @@ THB_API int thb_basis_dense(const float* params, int64_t npoints, int ndim, cons
 #define THB_EVAL_PER_POINT 2
 THB_API int thb_eval_fused(const thb_space_desc* space, const thb_plan_desc* plan, const float* params,
                    const float* ctrl_pts, int cp_dim, const int32_t* channels, int nchannels, float* const* out_host,
-                   int formulation, void* stream);
+                   int formulation, float* workspace, void* stream);
+
+/* Local control nets.  Over one active cell  sum_s PHI_s(u) CP_s = <tp(u), W>  with tp the (p+1)^d tensor product of
+ * the cell's own-level B-splines and  W[t] = [t active] CP_own[t] + sum_{coarser s} tile_s[t] CP_s : W depends on the
+ * hierarchy and the control points only, so it is built once per cell (and may be kept across batches of points for as
+ * long as ctrl_pts do not change) and a point costs Cox-de Boor plus one sum-factorised contraction with W.
+ * nets: [nslots][planes][tile_stride] f32, planes = 4 (value channel only) or 8 (with_derivatives: planes 4..7 are W
+ * built from control points relative to the cell's first support, used by the derivative channels).
+ * thb_cell_nets: plan == NULL builds every active cell, otherwise only the cells that hold points of the plan. */
+THB_API int64_t thb_net_workspace_floats(const thb_space_desc* space, int with_derivatives);
+THB_API int thb_cell_nets(const thb_space_desc* space, const thb_plan_desc* plan, const float* ctrl_pts, int cp_dim,
+                  int with_derivatives, float* nets, void* stream);
+THB_API int thb_eval_nets(const thb_space_desc* space, const thb_plan_desc* plan, const float* nets, int with_derivatives,
+                  int cp_dim, const int32_t* channels, int nchannels, float* const* out_host, void* stream);
 /* grad_ctrl_pts[nctrl, cp_dim] (zeroed by the callee) = A^T grad_out, A = value-channel basis matrix.
  * Replaces THBEval.backward (THB/torch_funcs.py:35-47) for the fused path. */
 THB_API int thb_eval_fused_backward(const thb_space_desc* space, const thb_plan_desc* plan, const float* params,

@@ -15,4 +15,4 @@ a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True
 torch.cuda.synchronize(); a.record()
 for _ in range(10): engine.eval_fused(P, plan, cp, out=out)
 b.record(); torch.cuda.synchronize()
-print(f"c3 kernel {a.elapsed_time(b) / 10:.3f} ms; light slots {P.n_light_slots}/{P.nslots}; counters {plan.counters.tolist()}")
+print(f"c3 kernel {a.elapsed_time(b) / 10:.3f} ms; items {plan.counters.tolist()[0]}")

@@ -58,7 +58,10 @@ def _load():
         "thb_basis_tiled": (i32, [C.POINTER(SpaceDesc), C.POINTER(PlanDesc), vp, vp, C.POINTER(C.c_int32), i32, C.POINTER(vp), vp]),
         "thb_basis_dense": (i32, [vp, i64, i32, C.POINTER(C.c_int32), vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                   C.POINTER(C.c_int32), vp, vp, i32, vp, i32, vp, vp]),
-        "thb_eval_fused": (i32, [C.POINTER(SpaceDesc), C.POINTER(PlanDesc), vp, vp, i32, C.POINTER(C.c_int32), i32, C.POINTER(vp), i32, vp]),
+        "thb_eval_fused": (i32, [C.POINTER(SpaceDesc), C.POINTER(PlanDesc), vp, vp, i32, C.POINTER(C.c_int32), i32, C.POINTER(vp), i32, vp, vp]),
+        "thb_net_workspace_floats": (i64, [C.POINTER(SpaceDesc), i32]),
+        "thb_cell_nets": (i32, [C.POINTER(SpaceDesc), C.POINTER(PlanDesc), vp, i32, i32, vp, vp]),
+        "thb_eval_nets": (i32, [C.POINTER(SpaceDesc), C.POINTER(PlanDesc), vp, i32, i32, C.POINTER(C.c_int32), i32, C.POINTER(vp), vp]),
         "thb_eval_fused_backward": (i32, [C.POINTER(SpaceDesc), C.POINTER(PlanDesc), vp, vp, i32, vp, i64, vp]),
         "thb_fma_peak": (i32, [i32, i32, vp, C.POINTER(C.c_double), vp]),
     }

@@ -1,0 +1,441 @@
+// Local-control-net evaluation: the default formulation of the fused THB_basis_fns + THBEval.forward path
+// (THB/core.py:604-701 + THB/torch_funcs.py:22-33).
+//
+// A coarser-level support s of a cell contributes PHI_s(u) * CP_s with PHI_s(u) = <tile_s, tp(u)>, tp = the (p+1)^d
+// tensor product of the cell's own-level B-splines.  Summed over the supports of the cell
+//     sum_s PHI_s(u) CP_s = < tp(u), W >,      W[t] = [t active] * CP_own[t] + sum_s tile_s[t] * CP_s
+// so W -- the cell's LOCAL CONTROL NET, (p+1)^d control points -- depends on the hierarchy and the control points only.
+//   k_cell_nets : one warp per active cell builds W (own-level window + fold of the coarser-level supports: rank-one
+//                 ones from their three factor vectors, the others from their tiles) and writes it to the workspace
+//                 [nslots][planes][TS]; planes 0..3 = W, planes 4..7 (derivative channels) = W built from control
+//                 points RELATIVE to the cell's first support (derivative basis values sum to zero, so the result is
+//                 the same, but the summed terms are O(p/h * h) instead of O(p/h * |CP|): no float32 cancellation)
+//   k_net_eval  : persistent warp-autonomous kernel over the plan's work items; a point costs Cox-de Boor plus the
+//                 sum-factorised contraction with W ((p+1)^d + (p+1)^(d-1) + (p+1)^(d-2) FMAs per output component),
+//                 no (p+1)^d register array and no per-point table traffic.
+#pragma once
+#include "thb_tile_impl.cuh"
+
+namespace thb_tile {
+
+#ifndef THB_NET_MINB
+#define THB_NET_MINB 16  // k_net_eval: <= 128 registers, 16 one-warp CTAs per SM
+#endif
+constexpr int kNetChunk = 64;     // tiled supports staged at once by one warp of k_cell_nets
+constexpr int kNetWarps = 4;      // warps (= cells in flight) per CTA of k_cell_nets
+
+struct NetArgs {
+    const float* ctrl_pts;
+    const int32_t* cell_count;  // plan histogram: cells without points are skipped (nullptr = every cell)
+    float* nets;                // [nslots][planes][TS]
+    int32_t planes;             // 4, or 8 with the relative planes
+};
+
+template <int CPD>
+THB_DEV float4 load_cp(const float* __restrict__ cp, int64_t r) {
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < CPD; ++k) v[k] = __ldg(cp + r * CPD + k);
+    return make_float4(v[0], v[1], v[2], v[3]);
+}
+
+template <int N0, int N1, int N2, int CPD, bool REL>
+__global__ void __launch_bounds__(32 * kNetWarps) k_cell_nets(const __grid_constant__ thb_space_desc sp, const __grid_constant__ NetArgs na) {
+    using SH = Shp<N0, N1, N2>;
+    constexpr int T = SH::T, TS = SH::TS;
+    constexpr int NT = (TS + 31) / 32;
+    constexpr bool kSameBC = (32 % (N1 * N2)) == 0;  // t and t + 32 differ in the first index only
+    __shared__ __align__(16) float4 s_sepv[kNetWarps][kNetChunk][3];
+    __shared__ __align__(16) float4 s_cc[kNetWarps][kNetChunk];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    float4(*sepv)[3] = s_sepv[wid];
+    float4* cc = s_cc[wid];
+    const bool split = sp.sep_vec != nullptr;
+    const int ib = 4 + (lane / N2) % N1, ic = 8 + lane % N2;
+
+    for (int slot = blockIdx.x * kNetWarps + wid; slot < sp.nslots; slot += gridDim.x * kNetWarps) {
+        if (na.cell_count && __ldg(na.cell_count + slot) == 0) continue;
+        const int4* ci = reinterpret_cast<const int4*>(sp.cellinfo + (int64_t)slot * THB_INFO_W);
+        const int4 a = __ldg(ci), e = __ldg(ci + 1), f = __ldg(ci + 2);  // level c0 c1 c2 | supp_off S tile_off n_direct | sep_off n_sep full_off
+        const unsigned long long dm = __ldg(sp.dmask + slot);
+        const int lev = a.x, soff = e.x, S = e.y, ndir = e.w;
+        const int ntile = S - ndir;
+        const int nsep = split ? f.y : 0;
+        float ref[4] = {0.f, 0.f, 0.f, 0.f};
+        if (REL && S > 0) {
+            const float4 r = load_cp<CPD>(na.ctrl_pts, __ldg(sp.supp_jm + soff));
+            ref[0] = r.x; ref[1] = r.y; ref[2] = r.z; ref[3] = r.w;
+        }
+        float w[NT][4], wr[REL ? NT : 1][4];
+        int ia[NT];
+        bool tv[NT];
+        {
+            const int n1 = sp.nfns[lev][1], n2 = sp.nfns[lev][2];
+            const int64_t f0 = sp.fn_off[lev];
+#pragma unroll
+            for (int h = 0; h < NT; ++h) {
+                const int t = lane + 32 * h;
+                tv[h] = t < T;
+                const int t2 = t % N2, t1 = (t / N2) % N1, t0 = t / (N2 * N1);
+                ia[h] = tv[h] ? t0 : 0;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                const bool on = ndir > 0 && tv[h] && ((dm >> t) & 1ull);
+                if (on) v = load_cp<CPD>(na.ctrl_pts, f0 + ((int64_t)(a.y + t0) * n1 + (a.z + t1)) * n2 + (a.w + t2));
+                w[h][0] = v.x; w[h][1] = v.y; w[h][2] = v.z; w[h][3] = v.w;
+                if (REL) {
+                    wr[h][0] = on ? v.x - ref[0] : 0.f; wr[h][1] = on ? v.y - ref[1] : 0.f;
+                    wr[h][2] = on ? v.z - ref[2] : 0.f; wr[h][3] = on ? v.w - ref[3] : 0.f;
+                }
+            }
+        }
+        // tiled supports in chunks: [0, nsep) rank one, [nsep, ntile) full tiles
+        const float* tile_src = split ? sp.full_tiles + (int64_t)f.z * TS : sp.tiles + (int64_t)e.z * TS;
+        const int32_t* full_jm = split ? sp.full_jm + f.z : sp.supp_jm + soff + ndir;
+        for (int c0 = 0; c0 < ntile; c0 += kNetChunk) {
+            const int n = min(kNetChunk, ntile - c0);
+            const int s_lo = min(c0, nsep), s_n = min(c0 + n, nsep) - s_lo;
+            const int f_lo = max(c0, nsep) - nsep, f_n = n - s_n;
+            __syncwarp();
+            if (s_n > 0) {
+                const float4* src = reinterpret_cast<const float4*>(sp.sep_vec + (int64_t)(f.x + s_lo) * 12);
+                for (int i = lane; i < s_n * 3; i += 32) cp_async16(&sepv[0][0] + i, src + i);
+                cp_async_commit();
+                for (int i = lane; i < s_n; i += 32) cc[i] = load_cp<CPD>(na.ctrl_pts, __ldg(sp.sep_jm + f.x + s_lo + i));
+            }
+            for (int i = lane; i < f_n; i += 32) cc[s_n + i] = load_cp<CPD>(na.ctrl_pts, __ldg(full_jm + f_lo + i));
+            cp_async_wait<0>();
+            __syncwarp();
+#pragma unroll 4
+            for (int i = 0; i < s_n; ++i) {
+                const float* sv = reinterpret_cast<const float*>(&sepv[i][0]);
+                const float4 c = cc[i];
+                const float bc = sv[ib] * sv[ic];
+#pragma unroll
+                for (int h = 0; h < NT; ++h) {
+                    float x;
+                    if (kSameBC || h == 0) {
+                        x = tv[h] ? sv[ia[h]] * bc : 0.f;
+                    } else {
+                        const int t = lane + 32 * h;
+                        x = tv[h] ? sv[ia[h]] * sv[4 + (t / N2) % N1] * sv[8 + t % N2] : 0.f;
+                    }
+                    w[h][0] = fmaf(x, c.x, w[h][0]); w[h][1] = fmaf(x, c.y, w[h][1]); w[h][2] = fmaf(x, c.z, w[h][2]);
+                    if (CPD == 4) w[h][3] = fmaf(x, c.w, w[h][3]);
+                    if (REL) {
+                        wr[h][0] = fmaf(x, c.x - ref[0], wr[h][0]); wr[h][1] = fmaf(x, c.y - ref[1], wr[h][1]);
+                        wr[h][2] = fmaf(x, c.z - ref[2], wr[h][2]);
+                        if (CPD == 4) wr[h][3] = fmaf(x, c.w - ref[3], wr[h][3]);
+                    }
+                }
+            }
+            const float* rows = tile_src + (int64_t)f_lo * TS + lane;
+#pragma unroll 4
+            for (int j = 0; j < f_n; ++j) {
+                const float4 c = cc[s_n + j];
+#pragma unroll
+                for (int h = 0; h < NT; ++h) {
+                    const float x = (lane + 32 * h < TS) ? __ldg(rows + (int64_t)j * TS + 32 * h) : 0.f;
+                    w[h][0] = fmaf(x, c.x, w[h][0]); w[h][1] = fmaf(x, c.y, w[h][1]); w[h][2] = fmaf(x, c.z, w[h][2]);
+                    if (CPD == 4) w[h][3] = fmaf(x, c.w, w[h][3]);
+                    if (REL) {
+                        wr[h][0] = fmaf(x, c.x - ref[0], wr[h][0]); wr[h][1] = fmaf(x, c.y - ref[1], wr[h][1]);
+                        wr[h][2] = fmaf(x, c.z - ref[2], wr[h][2]);
+                        if (CPD == 4) wr[h][3] = fmaf(x, c.w - ref[3], wr[h][3]);
+                    }
+                }
+            }
+        }
+        float* dst = na.nets + (int64_t)slot * na.planes * TS;
+#pragma unroll
+        for (int h = 0; h < NT; ++h) {
+            const int t = lane + 32 * h;
+            if (t < TS) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    dst[k * TS + t] = w[h][k];
+                    if (REL) dst[(4 + k) * TS + t] = wr[h][k];
+                }
+            }
+        }
+    }
+}
+
+// ---- evaluation against the nets --------------------------------------------------------------------------------
+template <class SH, bool DER>
+struct NetSmem {
+    static constexpr int NPL = DER ? 8 : 4;
+    int4 rec[3][4];                  // ring of work-item records (lookahead 2)
+    float knots[2][3][8];            // local knots of the item's cell, per dimension
+    float rk[3][8];                  // reciprocal knot differences of the current item
+    float net[2][NPL][SH::TS];       // the item's local control net (planes 4..7: relative), double buffered
+    float4 prec[2][64];              // point records of a sub-batch: (u0, u1, u2, caller-order index as bits)
+};
+
+template <class SH, bool DER>
+THB_DEV void prefetch_net(const thb_space_desc& sp, const float* __restrict__ nets, const Item& it, float (*knots)[8],
+                          float (*net)[SH::TS]) {
+    constexpr int NPL = DER ? 8 : 4;
+    const int lane = threadIdx.x;
+    if (lane < 24) {
+        const int dim = lane >> 3, m = lane & 7;
+        const int P = dim == 0 ? SH::P0 : (dim == 1 ? SH::P1 : SH::P2);
+        const int c = dim == 0 ? it.c0 : (dim == 1 ? it.c1 : it.c2);
+        if (dim < sp.ndim && m < 2 * P) cp_async4(&knots[dim][m], sp.knots + sp.knot_off[it.lev][dim] + c + 1 + m);
+    }
+    const float4* src = reinterpret_cast<const float4*>(nets + (int64_t)it.slot * NPL * SH::TS);
+    float4* dst = reinterpret_cast<float4*>(&net[0][0]);
+#pragma unroll
+    for (int i = 0; i < (NPL * SH::TS / 4 + 31) / 32; ++i) {
+        const int j = lane + 32 * i;
+        if (j < NPL * SH::TS / 4) cp_async16(dst + j, src + j);
+    }
+}
+
+// PPT*32 points of an item:  out_k = sum_a A[a] sum_c C[c] sum_b B[b] * W[k][a][b][c]
+template <class SH, int PPT, int CPD, bool DER>
+THB_DEV void net_points(const Args& ar, const Item& it, int base, NetSmem<SH, DER>& sm, int tb, int pb) {
+    constexpr int N0 = SH::N0, N1 = SH::N1, N2 = SH::N2;
+    const int lane = threadIdx.x;
+    int idx[PPT];
+    bool valid[PPT];
+    BasesRK<SH, DER> bs[PPT];
+#pragma unroll
+    for (int q = 0; q < PPT; ++q) {
+        valid[q] = base + q * 32 + lane < it.count;
+        const float4 rec = sm.prec[pb][q * 32 + lane];
+        idx[q] = __float_as_int(rec.w);
+        const float u[3] = {rec.x, rec.y, rec.z};
+        bs[q].eval(u, sm.knots[tb], sm.rk);
+    }
+    for (int chi = 0; chi < ar.nch; ++chi) {
+        const int ch = ar.channels[chi];
+        const int pl = (DER && ch != 0) ? 4 : 0;  // derivative channels use the relative planes
+        float fa[PPT][N0], fb[PPT][N1], fc[PPT][N2];
+#pragma unroll
+        for (int q = 0; q < PPT; ++q) bs[q].select(ch, fa[q], fb[q], fc[q]);
+        float acc[PPT][4];
+        if constexpr (N2 == 4) {
+            // Stage 1 (the (p+1)^3 one) is e[a][h] += B[b] * W[a][b][2h..2h+1]: FFMA2 with a scalar multiplier shared by
+            // consecutive instructions (operand reuse cache), so each FFMA2 fetches two register pairs -- an FMA stream
+            // with three fresh operands per instruction is register-file-bound at ~64 % of the FP32 peak (scripts/probe).
+            f32x2 fc2[PPT][2];
+#pragma unroll
+            for (int q = 0; q < PPT; ++q) {
+                fc2[q][0] = pack2(fc[q][0], fc[q][1]);
+                fc2[q][1] = pack2(fc[q][2], fc[q][3]);
+            }
+#pragma unroll
+            for (int k = 0; k < CPD; ++k) {
+                const ulonglong2* col = reinterpret_cast<const ulonglong2*>(sm.net[tb][pl + k]);
+                f32x2 e[PPT][N0][2];
+#pragma unroll
+                for (int b = 0; b < N1; ++b) {
+                    ulonglong2 cv[N0];
+#pragma unroll
+                    for (int a = 0; a < N0; ++a) cv[a] = col[a * N1 + b];
+#pragma unroll
+                    for (int q = 0; q < PPT; ++q) {
+                        const f32x2 bb = pack2(fb[q][b], fb[q][b]);
+#pragma unroll
+                        for (int a = 0; a < N0; ++a) {
+                            if (b == 0) {
+                                e[q][a][0] = fmul2(bb, cv[a].x);
+                                e[q][a][1] = fmul2(bb, cv[a].y);
+                            } else {
+                                ffma2(e[q][a][0], bb, cv[a].x);
+                                ffma2(e[q][a][1], bb, cv[a].y);
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < PPT; ++q) {
+                    f32x2 f = 0ull;
+#pragma unroll
+                    for (int a = 0; a < N0; ++a) {
+                        f32x2 g2 = fmul2(fc2[q][0], e[q][a][0]);
+                        ffma2(g2, fc2[q][1], e[q][a][1]);
+                        ffma2(f, pack2(fa[q][a], fa[q][a]), g2);
+                    }
+                    acc[q][k] = hsum2(f);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < CPD; ++k) {
+                const float* col = sm.net[tb][pl + k];
+                float f[PPT];
+#pragma unroll
+                for (int q = 0; q < PPT; ++q) f[q] = 0.0f;
+#pragma unroll
+                for (int a = 0; a < N0; ++a) {
+                    float e[PPT];
+#pragma unroll
+                    for (int q = 0; q < PPT; ++q) e[q] = 0.0f;
+#pragma unroll
+                    for (int b = 0; b < N1; ++b) {
+                        float cv[N2];
+#pragma unroll
+                        for (int c = 0; c < N2; ++c) cv[c] = col[(a * N1 + b) * N2 + c];
+#pragma unroll
+                        for (int q = 0; q < PPT; ++q) {
+                            float dd = fc[q][0] * cv[0];
+#pragma unroll
+                            for (int c = 1; c < N2; ++c) dd = fmaf(fc[q][c], cv[c], dd);
+                            e[q] = fmaf(fb[q][b], dd, e[q]);
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < PPT; ++q) f[q] = fmaf(fa[q][a], e[q], f[q]);
+                }
+#pragma unroll
+                for (int q = 0; q < PPT; ++q) acc[q][k] = f[q];
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < PPT; ++q) {
+            if (valid[q]) {
+                float* o = ar.out[chi] + (int64_t)idx[q] * CPD;
+#pragma unroll
+                for (int k = 0; k < CPD; ++k) o[k] = acc[q][k];
+            }
+        }
+    }
+}
+
+// Persistent, warp-autonomous (one warp per CTA, no CTA barrier): work items from an atomic cursor; while item i is
+// computed the records of items i+1, i+2 are in flight, and the points of the next sub-batch plus the knots / net of
+// item i+1 stream into the other half of the shared-memory buffers (cp.async).
+template <int N0, int N1, int N2, int PPT, int CPD, bool DER>
+__global__ void __launch_bounds__(kThreads, THB_NET_MINB) k_net_eval(const __grid_constant__ thb_space_desc sp, const __grid_constant__ Args ar,
+                                                                    const float* __restrict__ nets) {
+    using SH = Shp<N0, N1, N2>;
+    constexpr int SB = 32 * PPT;
+    __shared__ __align__(16) NetSmem<SH, DER> sm;
+    const int lane = threadIdx.x;
+    const int nitems = ar.counters[0];
+    int32_t* const cursor = ar.counters + 1;
+    const int d = sp.ndim;
+
+    int c3 = 0;
+    if (lane == 0) c3 = atomicAdd(cursor, 3);
+    const int id0 = __shfl_sync(0xffffffffu, c3, 0);
+    if (id0 >= nitems) return;
+    int id1 = id0 + 1, id2 = id0 + 2;
+    Item it = load_item(sp, ar.items, id0);
+    if (lane < 4 && id1 < nitems) cp_async16(&sm.rec[1][lane], ar.items + (int64_t)id1 * 4 + lane);
+    if (lane < 4 && id2 < nitems) cp_async16(&sm.rec[2][lane], ar.items + (int64_t)id2 * 4 + lane);
+    prefetch_net<SH, DER>(sp, nets, it, sm.knots[0], sm.net[0]);
+    prefetch_points<PPT>(ar, it.begin, it.count, 0, sm.prec[0]);
+    cp_async_commit();
+    int nn_id = 0;
+    if (lane == 0) nn_id = atomicAdd(cursor, 1);
+    int ring = 0, tb = 0, pb = 0;
+    cp_async_wait<0>();
+    __syncwarp();
+
+    for (;;) {
+        if (lane < 24) {  // reciprocal knot differences of this cell (from the staged knots)
+            const int dim = lane >> 3, m = lane & 7;
+            const int P = dim == 0 ? SH::P0 : (dim == 1 ? SH::P1 : SH::P2);
+            if (dim < d && m < P * (P + 1) / 2) {
+                int j = 1, r = m;
+                while (r >= j) { r -= j; ++j; }
+                sm.rk[dim][m] = 1.0f / (sm.knots[tb][dim][P + r] - sm.knots[tb][dim][P - j + r]);
+            }
+        }
+        __syncwarp();
+        const bool nx_valid = id1 < nitems;
+        for (int base = 0; base < it.count; base += SB) {
+            if (base + SB < it.count) {
+                prefetch_points<PPT>(ar, it.begin, it.count, base + SB, sm.prec[pb ^ 1]);
+            } else if (nx_valid) {
+                const int4* r = sm.rec[(ring + 1) % 3];
+                const Item nx = unpack_item(r[0], r[1], r[2], r[3]);
+                prefetch_points<PPT>(ar, nx.begin, nx.count, 0, sm.prec[pb ^ 1]);
+                prefetch_net<SH, DER>(sp, nets, nx, sm.knots[tb ^ 1], sm.net[tb ^ 1]);
+            }
+            cp_async_commit();
+            if (PPT == 2 && it.count - base <= 32) net_points<SH, 1, CPD, DER>(ar, it, base, sm, tb, pb);
+            else net_points<SH, PPT, CPD, DER>(ar, it, base, sm, tb, pb);
+            cp_async_wait<0>();
+            __syncwarp();
+            pb ^= 1;
+        }
+        if (!nx_valid) break;
+        ring = (ring + 1) % 3;
+        {
+            const int4* r = sm.rec[ring];
+            it = unpack_item(r[0], r[1], r[2], r[3]);
+        }
+        tb ^= 1;
+        const int id3 = __shfl_sync(0xffffffffu, nn_id, 0);
+        id1 = id2;
+        id2 = id3;
+        if (lane < 4 && id3 < nitems) cp_async16(&sm.rec[(ring + 2) % 3][lane], ar.items + (int64_t)id3 * 4 + lane);
+        cp_async_commit();
+        if (lane == 0) nn_id = atomicAdd(cursor, 1);
+    }
+}
+
+template <int N0, int N1, int N2>
+int launch_nets(const thb_space_desc* sp, const NetArgs* na, int cpd, cudaStream_t st) {
+    const int grid = min((sp->nslots + kNetWarps - 1) / kNetWarps, thb_num_sms() * 16);
+#define THB_NETS(CPD_, REL_)                                                                  \
+    do {                                                                                      \
+        k_cell_nets<N0, N1, N2, CPD_, REL_><<<grid, 32 * kNetWarps, 0, st>>>(*sp, *na);        \
+        THB_LAUNCHED();                                                                       \
+        return THB_OK;                                                                        \
+    } while (0)
+    if (cpd == 3 && na->planes == 4) THB_NETS(3, false);
+    if (cpd == 3 && na->planes == 8) THB_NETS(3, true);
+    if (cpd == 4 && na->planes == 4) THB_NETS(4, false);
+    if (cpd == 4 && na->planes == 8) THB_NETS(4, true);
+#undef THB_NETS
+    return thb_set_error(THB_E_UNSUPPORTED, "cell nets: unsupported variant");
+}
+
+template <int N0, int N1, int N2>
+int launch_net_eval(const thb_space_desc* sp, const Args* ar, const float* nets, int ppt, int cpd, int der, cudaStream_t st) {
+#define THB_NET_EVAL(PPT_, CPD_, DER_)                                                        \
+    do {                                                                                      \
+        static int grid = 0;                                                                  \
+        if (grid == 0) grid = persistent_grid(k_net_eval<N0, N1, N2, PPT_, CPD_, DER_>, kThreads); \
+        k_net_eval<N0, N1, N2, PPT_, CPD_, DER_><<<grid, kThreads, 0, st>>>(*sp, *ar, nets);   \
+        THB_LAUNCHED();                                                                       \
+        return THB_OK;                                                                        \
+    } while (0)
+    if (ppt == 2) {
+        if (cpd == 3 && !der) THB_NET_EVAL(2, 3, false);
+        if (cpd == 3 && der) THB_NET_EVAL(2, 3, true);
+        if (cpd == 4 && !der) THB_NET_EVAL(2, 4, false);
+        if (cpd == 4 && der) THB_NET_EVAL(2, 4, true);
+    } else {
+        if (cpd == 3 && !der) THB_NET_EVAL(1, 3, false);
+        if (cpd == 3 && der) THB_NET_EVAL(1, 3, true);
+        if (cpd == 4 && !der) THB_NET_EVAL(1, 4, false);
+        if (cpd == 4 && der) THB_NET_EVAL(1, 4, true);
+    }
+#undef THB_NET_EVAL
+    return thb_set_error(THB_E_UNSUPPORTED, "net evaluation: unsupported variant");
+}
+
+// ---- per-shape launch table (one translation unit per tensor-product shape, see thb_tile_inst_*.cu) ---------------
+struct ShapeOps {
+    int n0, n1, n2;
+    // ppt in {1,2}; cpd in {3,4}; der in {0,1}
+    int (*fused)(const thb_space_desc*, const Args*, int ppt, int cpd, int der, cudaStream_t);
+    int (*nets)(const thb_space_desc*, const NetArgs*, int cpd, cudaStream_t);
+    int (*net_eval)(const thb_space_desc*, const Args*, const float* nets, int ppt, int cpd, int der, cudaStream_t);
+    int (*basis)(const thb_space_desc*, const Args*, int ppt, int der, cudaStream_t);
+    int (*backward)(const thb_space_desc*, const Args*, int cpd, cudaStream_t);
+};
+
+#define THB_DEFINE_SHAPE(A, B, C)                                                                                    \
+    namespace thb_tile {                                                                                             \
+    extern const ShapeOps shape_ops_##A##B##C = {A, B, C, &launch_fused<A, B, C>, &launch_nets<A, B, C>,              \
+                                                 &launch_net_eval<A, B, C>, &launch_basis<A, B, C>,                  \
+                                                 &launch_backward<A, B, C>};                                         \
+    }
+
+}  // namespace thb_tile

@@ -3,7 +3,7 @@
 //   (THB_basis_fns + THBEval, THB/torch_funcs.py:22-47).
 #include <cstdlib>
 
-#include "thb_tile_impl.cuh"
+#include "thb_net_impl.cuh"
 
 int thb_check_space(const thb_space_desc* sp, const char* who);
 
@@ -77,7 +77,7 @@ extern "C" int thb_basis_tiled(const thb_space_desc* space, const thb_plan_desc*
 
 extern "C" int thb_eval_fused(const thb_space_desc* space, const thb_plan_desc* plan, const float* params,
                               const float* ctrl_pts, int cp_dim, const int32_t* channels, int nchannels, float* const* out_host,
-                              int formulation, void* stream) {
+                              int formulation, float* workspace, void* stream) {
     int rc = thb_check_space(space, "thb_eval_fused");
     if (rc) return rc;
     if ((rc = check_plan(plan, "thb_eval_fused"))) return rc;
@@ -89,6 +89,12 @@ extern "C" int thb_eval_fused(const thb_space_desc* space, const thb_plan_desc* 
     Args ar = {};
     bool der;
     if ((rc = fill_channels(ar, channels, nchannels, space->ndim, &der, "thb_eval_fused"))) return rc;
+    THB_REQUIRE(formulation >= 0 && formulation <= 2, "thb_eval_fused: unknown formulation");
+    if (formulation == THB_EVAL_LOCAL_NET) {
+        THB_REQUIRE(workspace, "thb_eval_fused: the local-net formulation needs a workspace (thb_net_workspace_floats)");
+        if ((rc = thb_cell_nets(space, plan, ctrl_pts, cp_dim, der ? 1 : 0, workspace, stream))) return rc;
+        return thb_eval_nets(space, plan, workspace, der ? 1 : 0, cp_dim, channels, nchannels, out_host, stream);
+    }
     for (int c = 0; c < nchannels; ++c) {
         THB_REQUIRE(out_host[c], "thb_eval_fused: null output");
         ar.out[c] = out_host[c];
@@ -97,10 +103,50 @@ extern "C" int thb_eval_fused(const thb_space_desc* space, const thb_plan_desc* 
     ar.params = params; ar.sorted = plan->sorted_params; ar.ctrl_pts = ctrl_pts; ar.cellnet = formulation == THB_EVAL_TILE_NET ? 1 : 0;
     cudaStream_t st = (cudaStream_t)stream;
     THB_CUDA(cudaMemsetAsync(plan->counters + 1, 0, sizeof(int32_t), st));
-    THB_REQUIRE(formulation >= 0 && formulation <= 2, "thb_eval_fused: unknown formulation");
-    if (formulation == THB_EVAL_LOCAL_NET && (space->sep_vec != nullptr || space->max_tiled == 0))
-        return ops->light(space, &ar, env_int("THB_LIGHT_PPT", 2), cp_dim, der ? 1 : 0, st);
     return ops->fused(space, &ar, env_int("THB_FUSED_PPT", 2), cp_dim, der ? 1 : 0, st);
+}
+
+extern "C" int64_t thb_net_workspace_floats(const thb_space_desc* space, int with_derivatives) {
+    if (!space) return 0;
+    return (int64_t)space->nslots * (with_derivatives ? 8 : 4) * space->tile_stride;
+}
+
+extern "C" int thb_cell_nets(const thb_space_desc* space, const thb_plan_desc* plan, const float* ctrl_pts, int cp_dim,
+                             int with_derivatives, float* nets, void* stream) {
+    int rc = thb_check_space(space, "thb_cell_nets");
+    if (rc) return rc;
+    THB_REQUIRE(ctrl_pts && nets, "thb_cell_nets: null pointer");
+    THB_REQUIRE(cp_dim == 3 || cp_dim == 4, "thb_cell_nets: cp_dim must be 3 or 4 (pad other widths to 4)");
+    THB_REQUIRE(!plan || plan->cell_count, "thb_cell_nets: plan without cell_count");
+    const ShapeOps* ops = find_shape(space);
+    if (!ops) return thb_set_error(THB_E_UNSUPPORTED, "thb_cell_nets: no kernel for degrees (%d,%d,%d)", space->degree[0], space->degree[1], space->degree[2]);
+    NetArgs na = {};
+    na.ctrl_pts = ctrl_pts; na.cell_count = plan ? plan->cell_count : nullptr; na.nets = nets; na.planes = with_derivatives ? 8 : 4;
+    return ops->nets(space, &na, cp_dim, (cudaStream_t)stream);
+}
+
+extern "C" int thb_eval_nets(const thb_space_desc* space, const thb_plan_desc* plan, const float* nets, int with_derivatives,
+                             int cp_dim, const int32_t* channels, int nchannels, float* const* out_host, void* stream) {
+    int rc = thb_check_space(space, "thb_eval_nets");
+    if (rc) return rc;
+    if ((rc = check_plan(plan, "thb_eval_nets"))) return rc;
+    if (plan->npoints == 0) return THB_OK;
+    THB_REQUIRE(nets && out_host, "thb_eval_nets: null pointer");
+    THB_REQUIRE(cp_dim == 3 || cp_dim == 4, "thb_eval_nets: cp_dim must be 3 or 4 (pad other widths to 4)");
+    const ShapeOps* ops = find_shape(space);
+    if (!ops) return thb_set_error(THB_E_UNSUPPORTED, "thb_eval_nets: no kernel for degrees (%d,%d,%d)", space->degree[0], space->degree[1], space->degree[2]);
+    Args ar = {};
+    bool der;
+    if ((rc = fill_channels(ar, channels, nchannels, space->ndim, &der, "thb_eval_nets"))) return rc;
+    THB_REQUIRE(!der || with_derivatives, "thb_eval_nets: derivative channels need nets built with_derivatives");
+    for (int c = 0; c < nchannels; ++c) {
+        THB_REQUIRE(out_host[c], "thb_eval_nets: null output");
+        ar.out[c] = out_host[c];
+    }
+    ar.items = (const int4*)plan->items; ar.counters = plan->counters; ar.sorted = plan->sorted_params;
+    cudaStream_t st = (cudaStream_t)stream;
+    THB_CUDA(cudaMemsetAsync(plan->counters + 1, 0, sizeof(int32_t), st));
+    return ops->net_eval(space, &ar, nets, env_int("THB_NET_PPT", 2), cp_dim, with_derivatives ? 1 : 0, st);
 }
 
 extern "C" int thb_eval_fused_backward(const thb_space_desc* space, const thb_plan_desc* plan, const float* params,

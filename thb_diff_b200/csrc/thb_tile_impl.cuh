@@ -21,9 +21,6 @@
 
 namespace thb_tile {
 
-#ifndef THB_LIGHT_MINB
-#define THB_LIGHT_MINB 16  // light kernel: 128 registers, 16 warps per SM
-#endif
 #ifndef THB_TILE_MINB
 #define THB_TILE_MINB 1  // register budget hint (9 => 168 registers + spills in the FFMA2 loop: measured slower)
 #endif
@@ -31,11 +28,9 @@ constexpr int kThreads = 32;   // forward tile kernels: one warp per CTA
 constexpr int kBwdThreads = 128;
 constexpr int kChunk = 64;
 
-// MODE_LIGHT: the default fused evaluation.  Coarser-level supports are folded into the cell's local control net once
-// per item (light_item_setup), points are evaluated against that net by sum factorisation: no (p+1)^d tensor product
-// in registers and no tile stream, so it runs in half the registers and at twice the occupancy of MODE_FUSED, which
-// is kept for the per-point formulation (the reference's gather-multiply, bench.py variants) and for MODE_BASIS.
-enum { MODE_FUSED = 0, MODE_BASIS = 1, MODE_LIGHT = 2 };
+// (the default fused evaluation -- local control nets -- lives in thb_net_impl.cuh; MODE_FUSED here is the per-point
+// formulation, the reference's gather-multiply + contraction without PHI leaving the SM)
+enum { MODE_FUSED = 0, MODE_BASIS = 1 };
 
 struct Args {
     const int4* items;
@@ -206,7 +201,6 @@ THB_DEV float f4c(const float4& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y 
 #define THB_PRAGMA(x) THB_PRAGMA_(x)
 constexpr int kWChunk = THB_WCHUNK;  // supports staged per chunk by one warp
 constexpr int kMaxCC = 128;  // coarse-support control points gathered once per item (else per chunk)
-constexpr int kMaxLight = 120;  // same bound for the light kernel (sized so that 16 of its warps fit in one SM's shared memory)
 constexpr int kRowPad = 4;   // floats of padding per staged tile row: rows s..s+3 start in different banks
 
 THB_DEV void cp_async16(void* smem, const void* gmem) {
@@ -232,15 +226,15 @@ struct WarpSmem {
     float rk[3][8];                       // reciprocal knot differences of the current item
     float cpw[2][4][SH::TS];              // own-level window control points (SoA, 0 where inactive)
     float4 prec[2][64];                   // point records of a sub-batch: (u0, u1, u2, caller-order index as bits)
-    static constexpr int kCC = MODE == MODE_LIGHT ? kMaxLight : kMaxCC;
+    static constexpr int kCC = kMaxCC;
     float4 cc[kCC];                       // control points of the coarser-level supports (rank-one ones first)
-    float4 sepv[MODE != MODE_BASIS ? kCC : 1][3];  // factor vectors of the rank-one tiled supports
-    float tiles[2][MODE == MODE_LIGHT ? 4 : kWChunk * (SH::TS + kRowPad)];  // coefficient tiles, streamed in chunks (padded rows)
+    float4 sepv[MODE == MODE_FUSED ? kCC : 1][3];  // factor vectors of the rank-one tiled supports
+    float tiles[2][kWChunk * (SH::TS + kRowPad)];  // coefficient tiles, streamed in chunks (padded rows)
     // derivative channels contract against control points RELATIVE to a reference point of the item: the
     // derivative basis values sum to zero, so the result is unchanged, but the summed terms are O(p/h * h)
     // instead of O(p/h * |CP|) -- this removes the float32 cancellation error of parametric derivatives
-    float cpw_rel[(MODE != MODE_BASIS && DER) ? 4 : 1][(MODE != MODE_BASIS && DER) ? SH::TS : 1];
-    float4 cc_rel[(MODE != MODE_BASIS && DER) ? kCC : 1];
+    float cpw_rel[(MODE == MODE_FUSED && DER) ? 4 : 1][(MODE == MODE_FUSED && DER) ? SH::TS : 1];
+    float4 cc_rel[(MODE == MODE_FUSED && DER) ? kCC : 1];
     float ref[4];
     // MODE_BASIS: PHI values are transposed through here so that every point's row is written coalesced
     float stage[MODE == MODE_BASIS ? (32 * (SH::TS + 1) > 64 * (kWChunk + 1) ? 32 * (SH::TS + 1) : 64 * (kWChunk + 1)) : 1];
@@ -539,298 +533,12 @@ THB_PRAGMA(unroll THB_SUNROLL)
     }
 }
 
-// ---- MODE_LIGHT: fused evaluation through the cell's LOCAL CONTROL NET ------------------------------------------
-// A coarser-level support s contributes PHI_s(u) * CP_s with PHI_s(u) = <tile_s, tp(u)>, so over a cell
-//     sum_s PHI_s(u) CP_s = < tp(u), W >,   W[t] = sum_s tile_s[t] * CP_s
-// and W can be added to the staged own-level window once per ITEM instead of once per point: 2*cp_dim FMAs per lane
-// and support (the lane owns window entries t = lane, lane + 32) against (p+1)^d FMAs per POINT and support.  Full
-// tiles are always folded (rows read coalesced from global memory, never staged); rank-one supports are folded from
-// their factor vectors unless the item has <= 16 points, where evaluating them per point with the lane-group split
-// is cheaper.  Returns true when the rank-one supports are left to the per-point loop.
-template <class SH, int CPD, bool DER>
-THB_DEV bool light_item_setup(const thb_space_desc& sp, const Args& ar, const Item& it, WarpSmem<SH, MODE_LIGHT, DER>& sm, int tb) {
-    constexpr int T = SH::T, TS = SH::TS, N1 = SH::N1, N2 = SH::N2;
-    constexpr int NT = (TS + 31) / 32;
-    const int lane = threadIdx.x;
-    const int ntile = it.S - it.ndir, nsep = it.nsep;
-    const bool per_point = nsep > 0 && it.count <= 16 && ntile <= kMaxLight;
-    if (DER) {
-        if (lane < 4) {  // reference point: the control point of the item's first support (see WarpSmem::cpw_rel)
-            const int64_t r = __ldg(sp.supp_jm + it.soff);
-            sm.ref[lane] = (lane < CPD && it.S > 0) ? __ldg(ar.ctrl_pts + r * CPD + lane) : 0.f;
-        }
-        __syncwarp();
-        for (int t = lane; t < TS; t += 32) {
-            const bool on = it.ndir > 0 && t < T && ((it.dm >> t) & 1ull);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) sm.cpw_rel[k][t] = on ? sm.cpw[tb][k][t] - sm.ref[k] : 0.f;
-        }
-    }
-    if (ntile == 0) {
-        __syncwarp();
-        return false;
-    }
-    float w[NT][4], wr[DER ? NT : 1][4];
-    int ia[NT], ib, ic;
-    bool tv[NT];
-#pragma unroll
-    for (int h = 0; h < NT; ++h) {
-        const int t = lane + 32 * h;
-        tv[h] = t < T;
-        ia[h] = tv[h] ? t / (N1 * N2) : 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { w[h][k] = 0.f; if (DER) wr[h][k] = 0.f; }
-    }
-    ib = 4 + (lane / N2) % N1;  // positions inside a 12-float factor record (t and t + 32 differ in the first index only
-    ic = 8 + lane % N2;         // when 32 is a multiple of N1*N2; otherwise recomputed below)
-    constexpr bool kSameBC = (32 % (N1 * N2)) == 0;
-    for (int c0 = 0; c0 < ntile; c0 += kMaxLight) {
-        const int n = min(kMaxLight, ntile - c0);
-        const int s_lo = min(c0, nsep), s_n = min(c0 + n, nsep) - s_lo;  // rank-one supports of this chunk
-        const int f_lo = max(c0, nsep) - nsep, f_n = n - s_n;               // full-tile supports of this chunk
-        if (c0 > 0) __syncwarp();
-        if (s_n > 0) {
-            const float4* src = reinterpret_cast<const float4*>(sp.sep_vec + (int64_t)(it.sep_off + s_lo) * 12);
-            for (int i = lane; i < s_n * 3; i += 32) cp_async16(&sm.sepv[0][0] + i, src + i);
-            cp_async_commit();
-            gather_ids<CPD>(sp.sep_jm + it.sep_off + s_lo, ar, s_n, sm.cc);
-        }
-        if (f_n > 0) gather_ids<CPD>(sp.full_jm + it.full_off + f_lo, ar, f_n, sm.cc + s_n);
-        cp_async_wait<0>();
-        __syncwarp();
-        if (DER) {
-            for (int i = lane; i < n; i += 32) {
-                const float4 c = sm.cc[i];
-                sm.cc_rel[i] = make_float4(c.x - sm.ref[0], c.y - sm.ref[1], c.z - sm.ref[2], c.w - sm.ref[3]);
-            }
-            __syncwarp();
-        }
-        if (!per_point) {
-#pragma unroll 4
-            for (int i = 0; i < s_n; ++i) {
-                const float* sv = reinterpret_cast<const float*>(&sm.sepv[i][0]);
-                const float4 cc = sm.cc[i];
-                float4 cr = cc;
-                if (DER) cr = sm.cc_rel[i];
-                const float bc = sv[ib] * sv[ic];
-#pragma unroll
-                for (int h = 0; h < NT; ++h) {
-                    float x;
-                    if (kSameBC || h == 0) {
-                        x = tv[h] ? sv[ia[h]] * bc : 0.f;
-                    } else {
-                        const int t = lane + 32 * h;
-                        x = tv[h] ? sv[ia[h]] * sv[4 + (t / N2) % N1] * sv[8 + t % N2] : 0.f;
-                    }
-                    w[h][0] = fmaf(x, cc.x, w[h][0]); w[h][1] = fmaf(x, cc.y, w[h][1]); w[h][2] = fmaf(x, cc.z, w[h][2]);
-                    if (CPD == 4) w[h][3] = fmaf(x, cc.w, w[h][3]);
-                    if (DER) {
-                        wr[h][0] = fmaf(x, cr.x, wr[h][0]); wr[h][1] = fmaf(x, cr.y, wr[h][1]); wr[h][2] = fmaf(x, cr.z, wr[h][2]);
-                        if (CPD == 4) wr[h][3] = fmaf(x, cr.w, wr[h][3]);
-                    }
-                }
-            }
-        }
-        const float* rows = sp.full_tiles + (int64_t)(it.full_off + f_lo) * TS + lane;
-#pragma unroll 4
-        for (int j = 0; j < f_n; ++j) {
-            const float4 cc = sm.cc[s_n + j];
-            float4 cr = cc;
-            if (DER) cr = sm.cc_rel[s_n + j];
-#pragma unroll
-            for (int h = 0; h < NT; ++h) {
-                const float x = (lane + 32 * h < TS) ? __ldg(rows + (int64_t)j * TS + 32 * h) : 0.f;
-                w[h][0] = fmaf(x, cc.x, w[h][0]); w[h][1] = fmaf(x, cc.y, w[h][1]); w[h][2] = fmaf(x, cc.z, w[h][2]);
-                if (CPD == 4) w[h][3] = fmaf(x, cc.w, w[h][3]);
-                if (DER) {
-                    wr[h][0] = fmaf(x, cr.x, wr[h][0]); wr[h][1] = fmaf(x, cr.y, wr[h][1]); wr[h][2] = fmaf(x, cr.z, wr[h][2]);
-                    if (CPD == 4) wr[h][3] = fmaf(x, cr.w, wr[h][3]);
-                }
-            }
-        }
-    }
-#pragma unroll
-    for (int h = 0; h < NT; ++h) {
-        const int t = lane + 32 * h;
-        if (t < TS) {
-#pragma unroll
-            for (int k = 0; k < CPD; ++k) {
-                sm.cpw[tb][k][t] += w[h][k];
-                if (DER) sm.cpw_rel[k][t] += wr[h][k];
-            }
-        }
-    }
-    __syncwarp();
-    return per_point;
-}
-
-// MODE_LIGHT sub-batch: PPT*32 points of an item.
-//   window (own-level supports + folded net):  out_k = sum_a A[a] sum_c C[c] sum_b B[b] * W[k][a][b][c]   (sum
-//       factorisation: (p+1)^d + (p+1)^(d-1) + (p+1)^(d-2) FMAs per output component, no (p+1)^d register array)
-//   rank-one supports left to the points (nsep > 0):   PHI_s = <v0_s, A> <v1_s, B> <v2_s, C>
-// G > 1 (PPT == 1): G lane groups share the <= 32/G points and each takes every G-th rank-one support; partial sums
-// are combined by shuffles.
-template <class SH, int PPT, int G, int CPD, bool DER>
-THB_DEV void warp_points_light(const Args& ar, const Item& it, int base, WarpSmem<SH, MODE_LIGHT, DER>& sm, int tb, int pb,
-                                  bool direct, int nsep) {
-    static_assert(G == 1 || PPT == 1, "support split: one point per lane");
-    constexpr int N0 = SH::N0, N1 = SH::N1, N2 = SH::N2;
-    constexpr int NPT = 32 / G;
-    const int lane_raw = threadIdx.x;
-    const int grp = lane_raw / NPT, lane = lane_raw % NPT;
-
-    int idx[PPT];
-    bool valid[PPT];
-    BasesRK<SH, DER> bs[PPT];
-#pragma unroll
-    for (int q = 0; q < PPT; ++q) {
-        valid[q] = base + q * 32 + lane < it.count;
-        const float4 rec = sm.prec[pb][q * 32 + lane];
-        idx[q] = __float_as_int(rec.w);
-        const float u[3] = {rec.x, rec.y, rec.z};
-        bs[q].eval(u, sm.knots[tb], sm.rk);
-    }
-    for (int chi = 0; chi < ar.nch; ++chi) {
-        const int ch = ar.channels[chi];
-        const bool use_rel = DER && ch != 0;  // see WarpSmem::cpw_rel
-        float fa[PPT][N0], fb[PPT][N1], fc[PPT][N2];
-#pragma unroll
-        for (int q = 0; q < PPT; ++q) bs[q].select(ch, fa[q], fb[q], fc[q]);
-        float acc[PPT][4];
-#pragma unroll
-        for (int q = 0; q < PPT; ++q)
-#pragma unroll
-            for (int k = 0; k < 4; ++k) acc[q][k] = 0.0f;
-
-        if (direct) {
-            if constexpr (N2 == 4) {
-                // Order of contraction b -> c -> a.  Stage 1 (the (p+1)^3 one) is e[a][h] += B[b] * CPwin[a][b][2h..2h+1]:
-                // FFMA2 with a SCALAR multiplier that stays the same for 2*N0 consecutive instructions, so it comes from
-                // the operand reuse cache and each FFMA2 fetches only two register pairs (an FMA stream that fetches
-                // three fresh operands per instruction is register-file-bound at ~64 % of the FP32 peak, scripts/probe).
-                f32x2 fc2[PPT][2];
-#pragma unroll
-                for (int q = 0; q < PPT; ++q) {
-                    fc2[q][0] = pack2(fc[q][0], fc[q][1]);
-                    fc2[q][1] = pack2(fc[q][2], fc[q][3]);
-                }
-#pragma unroll
-                for (int k = 0; k < CPD; ++k) {
-                    const ulonglong2* col = reinterpret_cast<const ulonglong2*>(use_rel ? sm.cpw_rel[k] : sm.cpw[tb][k]);
-                    f32x2 e[PPT][N0][2];
-#pragma unroll
-                    for (int b = 0; b < N1; ++b) {
-                        ulonglong2 cv[N0];
-#pragma unroll
-                        for (int a = 0; a < N0; ++a) cv[a] = col[a * N1 + b];
-#pragma unroll
-                        for (int q = 0; q < PPT; ++q) {
-                            const f32x2 bb = pack2(fb[q][b], fb[q][b]);
-#pragma unroll
-                            for (int a = 0; a < N0; ++a) {
-                                if (b == 0) {
-                                    e[q][a][0] = fmul2(bb, cv[a].x);
-                                    e[q][a][1] = fmul2(bb, cv[a].y);
-                                } else {
-                                    ffma2(e[q][a][0], bb, cv[a].x);
-                                    ffma2(e[q][a][1], bb, cv[a].y);
-                                }
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int q = 0; q < PPT; ++q) {
-                        f32x2 f = 0ull;
-#pragma unroll
-                        for (int a = 0; a < N0; ++a) {
-                            f32x2 g2 = fmul2(fc2[q][0], e[q][a][0]);
-                            ffma2(g2, fc2[q][1], e[q][a][1]);
-                            ffma2(f, pack2(fa[q][a], fa[q][a]), g2);
-                        }
-                        acc[q][k] = (G == 1 || grp == 0) ? hsum2(f) : 0.0f;  // G > 1: every group computed it, one keeps it
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int k = 0; k < CPD; ++k) {
-                    const float* col = use_rel ? sm.cpw_rel[k] : sm.cpw[tb][k];
-                    float f[PPT];
-#pragma unroll
-                    for (int q = 0; q < PPT; ++q) f[q] = 0.0f;
-#pragma unroll
-                    for (int a = 0; a < N0; ++a) {
-                        float e[PPT];
-#pragma unroll
-                        for (int q = 0; q < PPT; ++q) e[q] = 0.0f;
-#pragma unroll
-                        for (int b = 0; b < N1; ++b) {
-                            float cv[N2];
-#pragma unroll
-                            for (int c = 0; c < N2; ++c) cv[c] = col[(a * N1 + b) * N2 + c];
-#pragma unroll
-                            for (int q = 0; q < PPT; ++q) {
-                                float dd = fc[q][0] * cv[0];
-#pragma unroll
-                                for (int c = 1; c < N2; ++c) dd = fmaf(fc[q][c], cv[c], dd);
-                                e[q] = fmaf(fb[q][b], dd, e[q]);
-                            }
-                        }
-#pragma unroll
-                        for (int q = 0; q < PPT; ++q) f[q] = fmaf(fa[q][a], e[q], f[q]);
-                    }
-#pragma unroll
-                    for (int q = 0; q < PPT; ++q) acc[q][k] = (G == 1 || grp == 0) ? f[q] : 0.0f;
-                }
-            }
-        }
-        if (nsep > 0) {
-            const float4* ccs = use_rel ? sm.cc_rel : sm.cc;
-#pragma unroll 2
-            for (int s0 = 0; s0 < nsep; s0 += G) {
-                const bool s_on = G == 1 || s0 + grp < nsep;
-                const int s = (G == 1) ? s0 : min(s0 + grp, nsep - 1);
-                const float4 v0 = sm.sepv[s][0], v1 = sm.sepv[s][1], v2 = sm.sepv[s][2];
-                const float4 cc = ccs[s];
-#pragma unroll
-                for (int q = 0; q < PPT; ++q) {
-                    float e0 = 0.f, e1 = 0.f, e2 = 0.f;
-#pragma unroll
-                    for (int i = 0; i < N0; ++i) e0 = fmaf(f4c(v0, i), fa[q][i], e0);
-#pragma unroll
-                    for (int i = 0; i < N1; ++i) e1 = fmaf(f4c(v1, i), fb[q][i], e1);
-#pragma unroll
-                    for (int i = 0; i < N2; ++i) e2 = fmaf(f4c(v2, i), fc[q][i], e2);
-                    const float phi = s_on ? e0 * e1 * e2 : 0.0f;
-                    acc[q][0] = fmaf(phi, cc.x, acc[q][0]);
-                    acc[q][1] = fmaf(phi, cc.y, acc[q][1]);
-                    acc[q][2] = fmaf(phi, cc.z, acc[q][2]);
-                    if (CPD == 4) acc[q][3] = fmaf(phi, cc.w, acc[q][3]);
-                }
-            }
-        }
-        if (G > 1) {
-#pragma unroll
-            for (int k = 0; k < CPD; ++k)
-#pragma unroll
-                for (int o = NPT; o < 32; o <<= 1) acc[0][k] += __shfl_xor_sync(0xffffffffu, acc[0][k], o);
-        }
-#pragma unroll
-        for (int q = 0; q < PPT; ++q) {
-            if (valid[q] && (G == 1 || grp == 0)) {
-                float* o = ar.out[chi] + (int64_t)idx[q] * CPD;
-#pragma unroll
-                for (int k = 0; k < CPD; ++k) o[k] = acc[q][k];
-            }
-        }
-    }
-}
-
 // Persistent, warp-autonomous kernel: every CTA is ONE warp that pulls work items from an atomic cursor.
 // No CTA-wide barrier exists.  Software pipeline: while item i is computed, the records of items i+1 and
 // i+2 are (being) fetched, the id of item i+3 is being claimed, and the points of the next sub-batch plus
 // the knots / window control points of item i+1 stream into the other half of the shared-memory buffers.
 template <int N0, int N1, int N2, int PPT, int CPD, int MODE, bool DER>
-__global__ void __launch_bounds__(kThreads, MODE == MODE_LIGHT ? THB_LIGHT_MINB : THB_TILE_MINB) k_tile(const __grid_constant__ thb_space_desc sp, const __grid_constant__ Args ar) {
+__global__ void __launch_bounds__(kThreads, THB_TILE_MINB) k_tile(const __grid_constant__ thb_space_desc sp, const __grid_constant__ Args ar) {
     using SH = Shp<N0, N1, N2>;
     constexpr int TS = SH::TS, NQ = SH::NQ;
     constexpr int SB = 32 * PPT;
@@ -841,7 +549,7 @@ __global__ void __launch_bounds__(kThreads, MODE == MODE_LIGHT ? THB_LIGHT_MINB 
     int32_t* const cursor = ar.counters + 1;
     const int d = sp.ndim;
     const bool cellnet = (MODE == MODE_FUSED) && ar.cellnet;
-    const bool want_cp = (MODE != MODE_BASIS);
+    const bool want_cp = (MODE == MODE_FUSED);
 
     // claim three items up front (ids are increasing); id3 is claimed asynchronously
     int c3 = 0;
@@ -872,11 +580,6 @@ __global__ void __launch_bounds__(kThreads, MODE == MODE_LIGHT ? THB_LIGHT_MINB 
                 while (r >= j) { r -= j; ++j; }
                 sm.rk[dim][m] = 1.0f / (sm.knots[tb][dim][P + r] - sm.knots[tb][dim][P - j + r]);
             }
-        }
-        bool light_pp = false;
-        if constexpr (MODE == MODE_LIGHT) {
-            __syncwarp();
-            light_pp = light_item_setup<SH, CPD, DER>(sp, ar, it, sm, tb);
         }
         const bool split = MODE == MODE_FUSED && !cellnet && sp.sep_vec != nullptr && ntile <= kMaxCC;
         if (split) {
@@ -946,13 +649,6 @@ __global__ void __launch_bounds__(kThreads, MODE == MODE_LIGHT ? THB_LIGHT_MINB 
             }
             cp_async_commit();
             const int rem = it.count - base;
-            if constexpr (MODE == MODE_LIGHT) {
-                const bool direct = it.ndir > 0 || ntile > (light_pp ? it.nsep : 0);
-                if (light_pp && rem <= 8) warp_points_light<SH, 1, 4, CPD, DER>(ar, it, base, sm, tb, pb, direct, it.nsep);
-                else if (light_pp) warp_points_light<SH, 1, 2, CPD, DER>(ar, it, base, sm, tb, pb, direct, it.nsep);
-                else if (PPT == 2 && rem <= 32) warp_points_light<SH, 1, 1, CPD, DER>(ar, it, base, sm, tb, pb, direct, 0);
-                else warp_points_light<SH, PPT, 1, CPD, DER>(ar, it, base, sm, tb, pb, direct, 0);
-            } else
             if (MODE == MODE_FUSED && rem <= 8 && ntile > 0)
                 warp_points<SH, 1, (MODE == MODE_FUSED ? 4 : 1), CPD, MODE, DER>(sp, ar, it, base, ntile, cellnet, sm, tb, pb);
             else if (MODE == MODE_FUSED && rem <= 16 && ntile > 0)
@@ -1087,14 +783,6 @@ __global__ void __launch_bounds__(kBwdThreads) k_tile_backward(const __grid_cons
 }
 
 // ---- launch plumbing ---------------------------------------------------------------------------------------
-struct ShapeOps {
-    int n0, n1, n2;
-    // ppt in {1,2}; cpd in {3,4}; der in {0,1}
-    int (*fused)(const thb_space_desc*, const Args*, int ppt, int cpd, int der, cudaStream_t);
-    int (*light)(const thb_space_desc*, const Args*, int ppt, int cpd, int der, cudaStream_t);
-    int (*basis)(const thb_space_desc*, const Args*, int ppt, int der, cudaStream_t);
-    int (*backward)(const thb_space_desc*, const Args*, int cpd, cudaStream_t);
-};
 
 template <typename K>
 int persistent_grid(K kernel, int threads) {
@@ -1131,22 +819,6 @@ int launch_fused(const thb_space_desc* sp, const Args* ar, int ppt, int cpd, int
 }
 
 template <int N0, int N1, int N2>
-int launch_light(const thb_space_desc* sp, const Args* ar, int ppt, int cpd, int der, cudaStream_t st) {
-    if (ppt == 2) {
-        if (cpd == 3 && !der) THB_TILE_LAUNCH((k_tile<N0, N1, N2, 2, 3, MODE_LIGHT, false>));
-        if (cpd == 3 && der) THB_TILE_LAUNCH((k_tile<N0, N1, N2, 2, 3, MODE_LIGHT, true>));
-        if (cpd == 4 && !der) THB_TILE_LAUNCH((k_tile<N0, N1, N2, 2, 4, MODE_LIGHT, false>));
-        if (cpd == 4 && der) THB_TILE_LAUNCH((k_tile<N0, N1, N2, 2, 4, MODE_LIGHT, true>));
-    } else {
-        if (cpd == 3 && !der) THB_TILE_LAUNCH((k_tile<N0, N1, N2, 1, 3, MODE_LIGHT, false>));
-        if (cpd == 3 && der) THB_TILE_LAUNCH((k_tile<N0, N1, N2, 1, 3, MODE_LIGHT, true>));
-        if (cpd == 4 && !der) THB_TILE_LAUNCH((k_tile<N0, N1, N2, 1, 4, MODE_LIGHT, false>));
-        if (cpd == 4 && der) THB_TILE_LAUNCH((k_tile<N0, N1, N2, 1, 4, MODE_LIGHT, true>));
-    }
-    return thb_set_error(THB_E_UNSUPPORTED, "fused (light): unsupported variant");
-}
-
-template <int N0, int N1, int N2>
 int launch_basis(const thb_space_desc* sp, const Args* ar, int ppt, int der, cudaStream_t st) {
     if (ppt == 2) {
         if (!der) THB_TILE_LAUNCH((k_tile<N0, N1, N2, 2, 3, MODE_BASIS, false>));
@@ -1162,11 +834,5 @@ int launch_backward(const thb_space_desc* sp, const Args* ar, int cpd, cudaStrea
     if (cpd == 4) THB_TILE_LAUNCH_N((k_tile_backward<N0, N1, N2, 4>), kBwdThreads);
     return thb_set_error(THB_E_UNSUPPORTED, "backward: unsupported cp_dim");
 }
-
-#define THB_DEFINE_SHAPE(A, B, C)                                                                         \
-    namespace thb_tile {                                                                                  \
-    extern const ShapeOps shape_ops_##A##B##C = {A, B, C, &launch_fused<A, B, C>, &launch_light<A, B, C>, &launch_basis<A, B, C>,    \
-                                                 &launch_backward<A, B, C>};                              \
-    }
 
 }  // namespace thb_tile

@@ -1,3 +1,3 @@
 // Tile-kernel instantiations for tensor-product shape (3,3,1) = degrees (2,2,0); generated list, see thb_tile.cu
-#include "thb_tile_impl.cuh"
+#include "thb_net_impl.cuh"
 THB_DEFINE_SHAPE(3, 3, 1)

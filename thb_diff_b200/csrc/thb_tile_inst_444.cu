@@ -1,3 +1,3 @@
 // Tile-kernel instantiations for tensor-product shape (4,4,4) = degrees (3,3,3); generated list, see thb_tile.cu
-#include "thb_tile_impl.cuh"
+#include "thb_net_impl.cuh"
 THB_DEFINE_SHAPE(4, 4, 4)

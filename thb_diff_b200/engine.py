@@ -121,6 +121,46 @@ def basis_tiled(P, plan, offsets, nnz, channels=(CH_VALUE,)):
 FORMULATIONS = {"local_net": 0, "tile_net": 1, "per_point": 2}
 
 
+def net_workspace(P, with_derivatives=False):
+    """Device buffer for the local control nets of P ([nslots][4 or 8][TS] f32), allocated once per hierarchy."""
+    key = "_net_ws8" if with_derivatives else "_net_ws4"
+    ws = getattr(P, key, None)
+    n = lib.thb_net_workspace_floats(C.byref(P.desc()), int(with_derivatives))
+    if ws is None or ws.numel() != n:
+        ws = torch.empty(n, dtype=torch.float32, device=P.device)
+        setattr(P, key, ws)
+    return ws
+
+
+def cell_nets(P, ctrl_pts, with_derivatives=False, plan=None, out=None):
+    """Local control nets W of the active cells (thb_cell_nets): every cell, or only those holding points of `plan`.
+    They stay valid for as long as ctrl_pts (and the hierarchy) do not change."""
+    require_cuda(ctrl_pts, "ctrl_pts", torch.float32)
+    if ctrl_pts.shape[1] not in (3, 4) or ctrl_pts.shape[0] != P.nCP:
+        raise RuntimeError(f"ctrl_pts must be [{P.nCP}, 3 or 4]")
+    if not P.has_tiles:
+        raise RuntimeError("the hierarchy has no coefficient tiles yet (PackedHierarchy.attach_tiles / from_space)")
+    nets = out if out is not None else net_workspace(P, with_derivatives)
+    if plan is not None:
+        plan.refresh()
+    check(lib.thb_cell_nets(C.byref(P.desc()), C.byref(plan.desc) if plan is not None else None, ptr(ctrl_pts), ctrl_pts.shape[1],
+                            int(with_derivatives), ptr(nets), stream_ptr(P.device)), "thb_cell_nets")
+    return nets
+
+
+def eval_nets(P, plan, nets, cp_dim=3, channels=(CH_VALUE,), out=None, with_derivatives=None):
+    """Evaluates the plan's points against prebuilt nets (thb_eval_nets)."""
+    if with_derivatives is None:
+        with_derivatives = nets.numel() == lib.thb_net_workspace_floats(C.byref(P.desc()), 1)
+    plan.refresh()
+    if out is None:
+        out = [torch.zeros((plan.n, cp_dim), dtype=torch.float32, device=P.device) for _ in channels]
+    arr = (C.c_void_p * len(out))(*[o.data_ptr() for o in out])
+    check(lib.thb_eval_nets(C.byref(P.desc()), C.byref(plan.desc), ptr(nets), int(with_derivatives), cp_dim, _chan_array(channels),
+                            len(channels), arr, stream_ptr(P.device)), "thb_eval_nets")
+    return out
+
+
 def eval_fused(P, plan, ctrl_pts, channels=(CH_VALUE,), cellnet=True, out=None, formulation=None):
     """Fused THB_basis_fns + THBEval.forward.  formulation: "local_net" (default; cellnet=True), "per_point"
     (cellnet=False: PHI of every support is formed per point, the reference's formulation) or "tile_net"."""
@@ -137,8 +177,9 @@ def eval_fused(P, plan, ctrl_pts, channels=(CH_VALUE,), cellnet=True, out=None, 
     if out is None:
         out = [torch.zeros((plan.n, cpd), dtype=torch.float32, device=P.device) for _ in channels]
     arr = (C.c_void_p * len(out))(*[o.data_ptr() for o in out])
+    ws = net_workspace(P, any(int(c) != 0 for c in channels)) if form == 0 else None
     check(lib.thb_eval_fused(C.byref(P.desc()), C.byref(plan.desc), ptr(plan.params), ptr(ctrl_pts), cpd, _chan_array(channels),
-                             len(channels), arr, form, stream_ptr(P.device)), "thb_eval_fused")
+                             len(channels), arr, form, ptr(ws) if ws is not None else None, stream_ptr(P.device)), "thb_eval_fused")
     return out
 
 
@@ -261,6 +302,10 @@ class HostPipeline:
         for s in (self.s_in, self.s_cmp, self.s_out):
             s.wait_stream(cur)
         done, outd = {}, {}
+        nets = None
+        if self.formulation == "local_net":  # the nets depend on ctrl_pts only: built once, shared by all chunks
+            with torch.cuda.stream(self.s_cmp):
+                nets = cell_nets(self.P, ctrl_pts)
         for c, (lo, hi) in enumerate(self.bounds):
             b, m = c % 2, hi - lo
             with torch.cuda.stream(self.s_in):
@@ -278,7 +323,10 @@ class HostPipeline:
                     pl = self.plans[b] = Plan(self.P, self.pbuf[b][:m])
                 else:
                     pl.build()
-                eval_fused(self.P, pl, ctrl_pts, formulation=self.formulation, out=[self.obuf[b][:m]])
+                if nets is not None:
+                    eval_nets(self.P, pl, nets, self.cpd, out=[self.obuf[b][:m]], with_derivatives=False)
+                else:
+                    eval_fused(self.P, pl, ctrl_pts, formulation=self.formulation, out=[self.obuf[b][:m]])
                 done[c] = torch.cuda.Event()
                 done[c].record(self.s_cmp)
             with torch.cuda.stream(self.s_out):
