@@ -46,30 +46,22 @@ def flop_model(degrees, cpd, n_in, nnz, nnz_tiled, nnz_sep=0):
     return float(executed), float(dense)
 
 
-def flop_model_local_net(P, plan, cpd, n_in, ppi):
-    """Executed FLOPs of the local-control-net kernel (thb_tile_impl.cuh, MODE_LIGHT): per point Cox-de Boor and the
-    sum-factorised contraction with the item's net (T + N0*N2 + N0 FMAs per output component, 3-D); per work item
-    the fold of its coarser-level supports into the net: per rank-one support 2 multiplications + cp_dim FMAs for each
-    of the TS window entries, per full tile cp_dim FMAs per entry; items of <= 16 points evaluate their rank-one
-    supports per point instead (one (p_k+1)-dot per dimension, two multiplications, the contraction)."""
-    import torch
+def flop_model_local_net(P, plan, cpd, n_in):
+    """(FLOPs of k_net_eval, FLOPs of k_cell_nets), thb_net_impl.cuh.  Evaluation: per point Cox-de Boor and the
+    sum-factorised contraction with the cell's net (T + N0*N2 + N0 FMAs per output component, 3-D).  Nets: per cell
+    that holds points, per rank-one support 1.5 multiplications + cp_dim FMAs for each of the TS window entries, per
+    full tile cp_dim FMAs per entry."""
 
     deg = P.degrees
     d = len(deg)
     N = [p + 1 for p in deg] + ([1] if d == 2 else [])
     T = N[0] * N[1] * N[2]
     per_pt = sum(cdb_flops(p) for p in deg) + cpd * 2 * (T + N[0] * N[2] + N[0])
-    cnt = plan.cell_count[: P.nslots].long()
+    used = (plan.cell_count[: P.nslots] > 0).long()
     info = P.cellinfo.long()
     nt, nsep = info[:, 5] - info[:, 7], info[:, 9]
-    nfull = nt - nsep
-    items = (cnt + ppi - 1) // ppi
-    last = cnt - (items - 1).clamp(min=0) * ppi                      # points of the last (possibly small) item
-    small = (items > 0) & (last <= 16) & (nsep > 0) & (nt <= 120)      # that item takes the per-point path
-    folded_items = items - small.long()
-    fold = (folded_items * nsep).sum() * P.TS * (2 + 2 * cpd) + (items * nfull).sum() * P.TS * 2 * cpd
-    sep_pp = (small.long() * last * nsep).sum() * (2 * sum(N[:d]) + (d - 1) + 2 * cpd)
-    return float(n_in * per_pt + fold + sep_pp)
+    fold = (used * nsep).sum() * P.TS * (1.5 + 2 * cpd) + (used * (nt - nsep)).sum() * P.TS * 2 * cpd
+    return float(n_in * per_pt), float(fold)
 
 
 class ClockSampler:
@@ -366,7 +358,15 @@ def main():
         plan.build()
         if timers is not None:
             timers[1].record()
-        engine.eval_fused(P, plan, cp, formulation=args.formulation, out=out)
+        if args.formulation == "local_net":   # = engine.eval_fused(..., formulation="local_net"), its two launches timed apart
+            nets = engine.cell_nets(P, cp, plan=plan)
+            if timers is not None:
+                timers[3].record()
+            engine.eval_nets(P, plan, nets, 3, out=out, with_derivatives=False)
+        else:
+            if timers is not None:
+                timers[3].record()
+            engine.eval_fused(P, plan, cp, formulation=args.formulation, out=out)
         if timers is not None:
             timers[2].record()
 
@@ -382,7 +382,7 @@ def main():
     clk.__enter__()  # samples through warm-up, the timed region and the e2e region (the timed region alone lasts ~ms)
     for _ in range(max(args.warmup, 3)):
         step()
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
     barrier()
     launches0 = _lib.launch_count()
     t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -394,7 +394,8 @@ def main():
     launches = _lib.launch_count() - launches0
     total_ms = t_beg.elapsed_time(t_end)
     plan_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
-    kern_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / args.steps
+    nets_ms = sum(e[1].elapsed_time(e[3]) for e in ev) / args.steps   # local control nets of the cells that hold points
+    kern_ms = sum(e[3].elapsed_time(e[2]) for e in ev) / args.steps   # the evaluation kernel
     tmax = torch.tensor([total_ms], device=device)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -424,6 +425,37 @@ def main():
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_value = n * world / (float(e2e_ms.item()) * 1e-3)
+
+    def copy_floor():
+        """The two host<->device copies of one e2e step alone, on two streams (PCIe is full duplex): the floor of e2e."""
+        d_in = torch.empty_like(params)
+        s1, s2 = torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)
+        res = {}
+        for name, both in (("h2d", False), ("d2h", False), ("duplex", True)):
+            best = 1e9
+            for _ in range(3):
+                torch.cuda.synchronize()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                s1.wait_stream(torch.cuda.current_stream())
+                s2.wait_stream(torch.cuda.current_stream())
+                if both or name == "h2d":
+                    with torch.cuda.stream(s1):
+                        d_in.copy_(params_host, non_blocking=True)
+                if both or name == "d2h":
+                    with torch.cuda.stream(s2):
+                        out_host.copy_(out[0], non_blocking=True)
+                torch.cuda.current_stream().wait_stream(s1)
+                torch.cuda.current_stream().wait_stream(s2)
+                b.record()
+                torch.cuda.synchronize()
+                best = min(best, a.elapsed_time(b))
+            res[name + "_ms"] = best
+        res["h2d_gbs"] = n * P.ndim * 4 / res["h2d_ms"] / 1e6
+        res["d2h_gbs"] = n * 3 * 4 / res["d2h_ms"] / 1e6
+        return res
+
+    copies = copy_floor()
     step()
     torch.cuda.synchronize()
     e2e_diff = float((out_host.to(device) - out[0]).abs().max())  # the pipelined host path must reproduce the device path
@@ -440,30 +472,35 @@ def main():
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     f_exec, f_dense = flop_model(P.degrees, 3, n_in, nnz, nnz_tiled, nnz_sep)
+    f_nets = 0.0
     if args.formulation == "local_net":
-        f_exec = flop_model_local_net(P, plan, 3, n_in, engine.POINTS_PER_ITEM)
+        f_exec, f_nets = flop_model_local_net(P, plan, 3, n_in)
     elif args.formulation == "tile_net":  # per point the tensor product and the window dot products; all tiles folded per item
         cnt = plan.cell_count[: P.nslots].long()
         nt = (P.cellinfo[:, 5] - P.cellinfo[:, 7]).long()
         items = (cnt + engine.POINTS_PER_ITEM - 1) // engine.POINTS_PER_ITEM
         f_exec = flop_model(P.degrees, 3, n_in, 0, 0)[0] + float((items * nt).sum()) * P.T * 2 * 4
     tile_bytes = (P.sep_vec.numel() + P.full_tiles.numel()) * 4 if (getattr(P, "sep_vec", None) is not None and args.formulation != "tile_net") else P.tiles.numel() * 4
-    alg_bytes = n * (4 * P.ndim + 4 * 3 + 4) + tile_bytes + cp.numel() * 4
+    if args.formulation == "local_net":  # evaluation kernel: 16-byte point records in, geometry out, one net per work item
+        alg_bytes = n * (16 + 4 * 3) + int(plan.counters[0].item()) * 4 * P.TS * 4
+    else:
+        alg_bytes = n * (16 + 4 * 3) + tile_bytes + cp.numel() * 4
     t_fp32 = f_exec / (fp32_peak * 1e12)
     t_hbm = alg_bytes / (hbm_peak * 1e9)
     t_roof = max(t_fp32, t_hbm)
     bound = "fp32" if t_fp32 >= t_hbm else "hbm"
     traffic = None
     try:  # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu capture of this kernel
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["k_tile_fused_c3_bytes"]
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["k_net_eval_c3_bytes" if args.formulation == "local_net" else "k_tile_fused_c3_bytes"]
     except Exception:
         pass
     roofline = {
-        "bound": bound, "kernel": "thb_tile::k_tile<4,4,4,2,3,%s>" % ("LIGHT" if args.formulation == "local_net" else "FUSED"),
+        "bound": bound, "kernel": "thb_tile::k_net_eval<4,4,4,2,3,0>" if args.formulation == "local_net" else "thb_tile::k_tile<4,4,4,2,3,FUSED>",
         "achieved": (f_exec / (kern_ms * 1e-3) / 1e12) if bound == "fp32" else (alg_bytes / (kern_ms * 1e-3) / 1e9),
         "peak": fp32_peak if bound == "fp32" else hbm_peak, "unit": "TFLOP/s" if bound == "fp32" else "GB/s",
         "frac": t_roof / (kern_ms * 1e-3), "traffic": traffic,
-        "kernel_ms": kern_ms, "plan_ms": plan_ms, "kernel_share_of_step": kern_ms / (plan_ms + kern_ms),
+        "kernel_ms": kern_ms, "plan_ms": plan_ms, "nets_ms": nets_ms, "kernel_share_of_step": kern_ms / (plan_ms + nets_ms + kern_ms),
+        "nets_flops": f_nets,
         "flops_executed": f_exec, "flops_dense_model_8d": f_dense, "algorithmic_bytes": alg_bytes,
         "frac_vs_dense_model_8d": (f_dense / (fp32_peak * 1e12)) / (kern_ms * 1e-3),
         "peak_source": "FP32: thb_fma_peak micro-kernel measured in this run (MEASURED_PEAKS.json has no FP32 entry); "
@@ -483,7 +520,8 @@ def main():
         "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": n * P.ndim * 4, "d2h_bytes_per_step": n * 3 * 4,
                 "ms_per_step": float(e2e_ms.item()),
                 "how": f"engine.HostPipeline: {len(pipe.bounds)} chunks, H2D / compute / D2H overlapped on 3 streams, pinned host buffers",
-                "check_max_abs_diff_vs_device_path": e2e_diff},
+                "check_max_abs_diff_vs_device_path": e2e_diff,
+                "host_copies_alone": copies},
         "roofline": roofline,
     }
 

@@ -8,5 +8,5 @@ $CMD > gpurun_out/prof_plain_$tag.json 2> gpurun_out/prof_plain_$tag.err && \
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"k_" -c 60 --csv --log-file gpurun_out/launches_$tag.csv $CMD > gpurun_out/ncu_l_$tag.log 2>&1
 echo "launch list rc=$?"
 $CMD > /dev/null 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:k_tile -s 3 -c 1 -o gpurun_out/prof_$tag -f $CMD > gpurun_out/ncu_f_$tag.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_net_eval -s 3 -c 1 -o gpurun_out/prof_$tag -f $CMD > gpurun_out/ncu_f_$tag.log 2>&1
 echo "full capture rc=$?"; tail -n 5 gpurun_out/ncu_f_$tag.log

@@ -21,7 +21,11 @@ namespace thb_tile {
 #ifndef THB_NET_MINB
 #define THB_NET_MINB 16  // k_net_eval: <= 128 registers, 16 one-warp CTAs per SM
 #endif
-constexpr int kNetChunk = 64;     // tiled supports staged at once by one warp of k_cell_nets
+#ifndef THB_NETS_MINB
+#define THB_NETS_MINB 9  // k_cell_nets: <= 56 registers, 36 warps per SM (it is latency-bound: occupancy matters; prefetching
+                         // the next cell's descriptor / control points one chunk ahead cost more registers than it hid latency)
+#endif
+constexpr int kNetChunk = 32;     // tiled supports staged at once by one warp of k_cell_nets
 constexpr int kNetWarps = 4;      // warps (= cells in flight) per CTA of k_cell_nets
 
 struct NetArgs {
@@ -39,8 +43,26 @@ THB_DEV float4 load_cp(const float* __restrict__ cp, int64_t r) {
     return make_float4(v[0], v[1], v[2], v[3]);
 }
 
+// (w01, w23)[k] += (x01, x23) * c[k]   (and the relative planes with c - ref)
+template <int CPD, bool REL>
+THB_DEV void fold2(f32x2 (*w2)[4], f32x2 (*wr2)[4], f32x2 x01, f32x2 x23, const float4& c, const float* ref) {
+    const float ck[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+    for (int k = 0; k < CPD; ++k) {
+        const f32x2 c2 = pack2(ck[k], ck[k]);
+        ffma2(w2[0][k], x01, c2);
+        ffma2(w2[1][k], x23, c2);
+        if (REL) {
+            const float r = ck[k] - ref[k];
+            const f32x2 r2 = pack2(r, r);
+            ffma2(wr2[0][k], x01, r2);
+            ffma2(wr2[1][k], x23, r2);
+        }
+    }
+}
+
 template <int N0, int N1, int N2, int CPD, bool REL>
-__global__ void __launch_bounds__(32 * kNetWarps) k_cell_nets(const __grid_constant__ thb_space_desc sp, const __grid_constant__ NetArgs na) {
+__global__ void __launch_bounds__(32 * kNetWarps, (REL || CPD == 4) ? 6 : THB_NETS_MINB) k_cell_nets(const __grid_constant__ thb_space_desc sp, const __grid_constant__ NetArgs na) {
     using SH = Shp<N0, N1, N2>;
     constexpr int T = SH::T, TS = SH::TS;
     constexpr int NT = (TS + 31) / 32;
@@ -66,6 +88,105 @@ __global__ void __launch_bounds__(32 * kNetWarps) k_cell_nets(const __grid_const
             const float4 r = load_cp<CPD>(na.ctrl_pts, __ldg(sp.supp_jm + soff));
             ref[0] = r.x; ref[1] = r.y; ref[2] = r.z; ref[3] = r.w;
         }
+        if constexpr (N0 == 4 && N1 * N2 == 16) {
+            // Cubic-in-u shapes with a 16-entry (b, c) face: lane = (half, b, c) owns the four window entries a = 0..3 of
+            // its (b, c); the two half-warps take alternate supports and are summed with one shuffle per value at the
+            // end.  Per support a lane issues 4 shared-memory loads and 8 packed FP32 instructions for 12 FMAs (the
+            // generic path below: 5 loads and 5 instructions for 6 FMAs, and twice the shared-memory wavefronts).
+            const int half = lane >> 4, l16 = lane & 15;
+            const int jb = 4 + l16 / N2, jc = 8 + l16 % N2;
+            f32x2 w2[2][4], wr2[REL ? 2 : 1][4];
+            {
+                const int n1 = sp.nfns[lev][1], n2 = sp.nfns[lev][2];
+                const int64_t f0 = sp.fn_off[lev];
+                const int t1 = l16 / N2, t2 = l16 % N2;
+#pragma unroll
+                for (int p = 0; p < 2; ++p) {
+                    float4 v[2];
+                    bool on[2];
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const int t0 = 2 * p + q, t = t0 * 16 + l16;
+                        on[q] = ndir > 0 && p == half && ((dm >> t) & 1ull);  // half h loads the entries a = 2h, 2h+1
+                        v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (on[q]) v[q] = load_cp<CPD>(na.ctrl_pts, f0 + ((int64_t)(a.y + t0) * n1 + (a.z + t1)) * n2 + (a.w + t2));
+                    }
+                    w2[p][0] = pack2(v[0].x, v[1].x); w2[p][1] = pack2(v[0].y, v[1].y); w2[p][2] = pack2(v[0].z, v[1].z);
+                    w2[p][3] = pack2(v[0].w, v[1].w);
+                    if (REL) {
+                        wr2[p][0] = pack2(on[0] ? v[0].x - ref[0] : 0.f, on[1] ? v[1].x - ref[0] : 0.f);
+                        wr2[p][1] = pack2(on[0] ? v[0].y - ref[1] : 0.f, on[1] ? v[1].y - ref[1] : 0.f);
+                        wr2[p][2] = pack2(on[0] ? v[0].z - ref[2] : 0.f, on[1] ? v[1].z - ref[2] : 0.f);
+                        wr2[p][3] = pack2(on[0] ? v[0].w - ref[3] : 0.f, on[1] ? v[1].w - ref[3] : 0.f);
+                    }
+                }
+            }
+            const float* tile_src = split ? sp.full_tiles + (int64_t)f.z * TS : sp.tiles + (int64_t)e.z * TS;
+            const int32_t* full_jm = split ? sp.full_jm + f.z : sp.supp_jm + soff + ndir;
+            static_assert(kNetChunk == 32, "one tiled support per lane and chunk");
+            for (int c0 = 0; c0 < ntile; c0 += kNetChunk) {
+                const int n = min(kNetChunk, ntile - c0);
+                const int s_lo = min(c0, nsep), s_n = min(c0 + n, nsep) - s_lo;
+                const int f_lo = max(c0, nsep) - nsep, f_n = n - s_n;
+                __syncwarp();
+                if (s_n > 0) {
+                    const float4* src = reinterpret_cast<const float4*>(sp.sep_vec + (int64_t)(f.x + s_lo) * 12);
+#pragma unroll
+                    for (int i = 0; i < 3; ++i)
+                        if (lane + 32 * i < s_n * 3) cp_async16(&sepv[0][0] + lane + 32 * i, src + lane + 32 * i);
+                    cp_async_commit();
+                }
+                {   // control point of tiled support c0 + lane (rank-one ones first)
+                    const int g = c0 + lane;
+                    if (g < ntile) cc[lane] = load_cp<CPD>(na.ctrl_pts, __ldg(g < nsep ? sp.sep_jm + f.x + g : full_jm + (g - nsep)));
+                }
+                cp_async_wait<0>();
+                __syncwarp();
+#pragma unroll 4
+                for (int i = half; i < s_n; i += 2) {
+                    const float* sv = reinterpret_cast<const float*>(&sepv[i][0]);
+                    const float4 v0 = sepv[i][0];
+                    const float4 c = cc[i];
+                    const float bc = sv[jb] * sv[jc];
+                    const f32x2 bc2 = pack2(bc, bc);
+                    const f32x2 x01 = fmul2(pack2(v0.x, v0.y), bc2), x23 = fmul2(pack2(v0.z, v0.w), bc2);
+                    fold2<CPD, REL>(w2, wr2, x01, x23, c, ref);
+                }
+                const float* rows = tile_src + (int64_t)f_lo * TS + l16;
+#pragma unroll 4
+                for (int j = half; j < f_n; j += 2) {
+                    const float* r = rows + (int64_t)j * TS;
+                    const float4 c = cc[s_n + j];
+                    const f32x2 x01 = pack2(__ldg(r), __ldg(r + 16)), x23 = pack2(__ldg(r + 32), __ldg(r + 48));
+                    fold2<CPD, REL>(w2, wr2, x01, x23, c, ref);
+                }
+            }
+            // sum the two halves; half h then writes the entries a = 2h, 2h+1
+            float* dst = na.nets + (int64_t)slot * na.planes * TS;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float o[2][2], orr[2][2];
+#pragma unroll
+                for (int p = 0; p < 2; ++p) {
+                    unpack2(w2[p][k], o[p][0], o[p][1]);
+                    o[p][0] += __shfl_xor_sync(0xffffffffu, o[p][0], 16);
+                    o[p][1] += __shfl_xor_sync(0xffffffffu, o[p][1], 16);
+                    if (REL) {
+                        unpack2(wr2[p][k], orr[p][0], orr[p][1]);
+                        orr[p][0] += __shfl_xor_sync(0xffffffffu, orr[p][0], 16);
+                        orr[p][1] += __shfl_xor_sync(0xffffffffu, orr[p][1], 16);
+                    }
+                }
+                const int tb = half * 32 + l16;
+                dst[k * TS + tb] = half ? o[1][0] : o[0][0];
+                dst[k * TS + tb + 16] = half ? o[1][1] : o[0][1];
+                if (REL) {
+                    dst[(4 + k) * TS + tb] = half ? orr[1][0] : orr[0][0];
+                    dst[(4 + k) * TS + tb + 16] = half ? orr[1][1] : orr[0][1];
+                }
+            }
+            continue;
+        }
         float w[NT][4], wr[REL ? NT : 1][4];
         int ia[NT];
         bool tv[NT];
@@ -88,6 +209,12 @@ __global__ void __launch_bounds__(32 * kNetWarps) k_cell_nets(const __grid_const
                 }
             }
         }
+        // packed accumulators of the rank-one fold (two window entries per lane), added to w / wr at the end
+        f32x2 w2[4] = {0ull, 0ull, 0ull, 0ull}, wr2[REL ? 4 : 1];
+        if (REL) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) wr2[k] = 0ull;
+        }
         // tiled supports in chunks: [0, nsep) rank one, [nsep, ntile) full tiles
         const float* tile_src = split ? sp.full_tiles + (int64_t)f.z * TS : sp.tiles + (int64_t)e.z * TS;
         const int32_t* full_jm = split ? sp.full_jm + f.z : sp.supp_jm + soff + ndir;
@@ -105,26 +232,48 @@ __global__ void __launch_bounds__(32 * kNetWarps) k_cell_nets(const __grid_const
             for (int i = lane; i < f_n; i += 32) cc[s_n + i] = load_cp<CPD>(na.ctrl_pts, __ldg(full_jm + f_lo + i));
             cp_async_wait<0>();
             __syncwarp();
-#pragma unroll 4
-            for (int i = 0; i < s_n; ++i) {
-                const float* sv = reinterpret_cast<const float*>(&sepv[i][0]);
-                const float4 c = cc[i];
-                const float bc = sv[ib] * sv[ic];
-#pragma unroll
-                for (int h = 0; h < NT; ++h) {
-                    float x;
-                    if (kSameBC || h == 0) {
-                        x = tv[h] ? sv[ia[h]] * bc : 0.f;
-                    } else {
-                        const int t = lane + 32 * h;
-                        x = tv[h] ? sv[ia[h]] * sv[4 + (t / N2) % N1] * sv[8 + t % N2] : 0.f;
-                    }
-                    w[h][0] = fmaf(x, c.x, w[h][0]); w[h][1] = fmaf(x, c.y, w[h][1]); w[h][2] = fmaf(x, c.z, w[h][2]);
-                    if (CPD == 4) w[h][3] = fmaf(x, c.w, w[h][3]);
+            if constexpr (NT == 2 && kSameBC && T == TS) {
+                // both window entries of a lane share v1[b] * v2[c]: one FMUL2 forms the pair of tile entries, one FFMA2
+                // per output component accumulates both (scalar second operand)
+#pragma unroll 8
+                for (int i = 0; i < s_n; ++i) {
+                    const float* sv = reinterpret_cast<const float*>(&sepv[i][0]);
+                    const float4 c = cc[i];
+                    const float bc = sv[ib] * sv[ic];
+                    const f32x2 x2 = fmul2(pack2(sv[ia[0]], sv[ia[1]]), pack2(bc, bc));
+                    ffma2(w2[0], x2, pack2(c.x, c.x));
+                    ffma2(w2[1], x2, pack2(c.y, c.y));
+                    ffma2(w2[2], x2, pack2(c.z, c.z));
+                    if (CPD == 4) ffma2(w2[3], x2, pack2(c.w, c.w));
                     if (REL) {
-                        wr[h][0] = fmaf(x, c.x - ref[0], wr[h][0]); wr[h][1] = fmaf(x, c.y - ref[1], wr[h][1]);
-                        wr[h][2] = fmaf(x, c.z - ref[2], wr[h][2]);
-                        if (CPD == 4) wr[h][3] = fmaf(x, c.w - ref[3], wr[h][3]);
+                        ffma2(wr2[0], x2, pack2(c.x - ref[0], c.x - ref[0]));
+                        ffma2(wr2[1], x2, pack2(c.y - ref[1], c.y - ref[1]));
+                        ffma2(wr2[2], x2, pack2(c.z - ref[2], c.z - ref[2]));
+                        if (CPD == 4) ffma2(wr2[3], x2, pack2(c.w - ref[3], c.w - ref[3]));
+                    }
+                }
+            } else {
+#pragma unroll 4
+                for (int i = 0; i < s_n; ++i) {
+                    const float* sv = reinterpret_cast<const float*>(&sepv[i][0]);
+                    const float4 c = cc[i];
+                    const float bc = sv[ib] * sv[ic];
+#pragma unroll
+                    for (int h = 0; h < NT; ++h) {
+                        float x;
+                        if (kSameBC || h == 0) {
+                            x = tv[h] ? sv[ia[h]] * bc : 0.f;
+                        } else {
+                            const int t = lane + 32 * h;
+                            x = tv[h] ? sv[ia[h]] * sv[4 + (t / N2) % N1] * sv[8 + t % N2] : 0.f;
+                        }
+                        w[h][0] = fmaf(x, c.x, w[h][0]); w[h][1] = fmaf(x, c.y, w[h][1]); w[h][2] = fmaf(x, c.z, w[h][2]);
+                        if (CPD == 4) w[h][3] = fmaf(x, c.w, w[h][3]);
+                        if (REL) {
+                            wr[h][0] = fmaf(x, c.x - ref[0], wr[h][0]); wr[h][1] = fmaf(x, c.y - ref[1], wr[h][1]);
+                            wr[h][2] = fmaf(x, c.z - ref[2], wr[h][2]);
+                            if (CPD == 4) wr[h][3] = fmaf(x, c.w - ref[3], wr[h][3]);
+                        }
                     }
                 }
             }
@@ -142,6 +291,18 @@ __global__ void __launch_bounds__(32 * kNetWarps) k_cell_nets(const __grid_const
                         wr[h][2] = fmaf(x, c.z - ref[2], wr[h][2]);
                         if (CPD == 4) wr[h][3] = fmaf(x, c.w - ref[3], wr[h][3]);
                     }
+                }
+            }
+        }
+        if constexpr (NT == 2) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float lo, hi;
+                unpack2(w2[k], lo, hi);
+                w[0][k] += lo; w[1][k] += hi;
+                if (REL) {
+                    unpack2(wr2[k], lo, hi);
+                    wr[0][k] += lo; wr[1][k] += hi;
                 }
             }
         }
@@ -380,9 +541,11 @@ __global__ void __launch_bounds__(kThreads, THB_NET_MINB) k_net_eval(const __gri
 
 template <int N0, int N1, int N2>
 int launch_nets(const thb_space_desc* sp, const NetArgs* na, int cpd, cudaStream_t st) {
-    const int grid = min((sp->nslots + kNetWarps - 1) / kNetWarps, thb_num_sms() * 16);
 #define THB_NETS(CPD_, REL_)                                                                  \
     do {                                                                                      \
+        static int full = 0; /* one resident wave: no partial second wave */                  \
+        if (full == 0) full = persistent_grid(k_cell_nets<N0, N1, N2, CPD_, REL_>, 32 * kNetWarps); \
+        const int grid = min((sp->nslots + kNetWarps - 1) / kNetWarps, full);                  \
         k_cell_nets<N0, N1, N2, CPD_, REL_><<<grid, 32 * kNetWarps, 0, st>>>(*sp, *na);        \
         THB_LAUNCHED();                                                                       \
         return THB_OK;                                                                        \
