@@ -237,29 +237,37 @@ __global__ void __launch_bounds__(256) k_plan_count(const __grid_constant__ thb_
 // straight-line code per point -- bin -> candidate cell -> one comparison -> verification against the two bracketing
 // breakpoints -> one slot lookup.  A point whose span is not verified (possible only for knot vectors the tables do
 // not resolve) is appended to `fail_list` and handled by k_plan_fixup with the robust search.
-template <int D>
+constexpr int kPlanSmemLut = 3 * 1024;  // span lookup tables staged in shared memory when they fit (else read through L1)
+
+template <int D, bool SLUT>
 __global__ void __launch_bounds__(256) k_plan_count_fast(const __grid_constant__ thb_space_desc sp, const float* __restrict__ params,
                                                          unsigned n, int32_t* __restrict__ slot_out, int32_t* __restrict__ count,
                                                          int32_t* __restrict__ fail_list, int32_t* __restrict__ counters) {
     __shared__ float sk[kPlanSmemKnots];
+    __shared__ int s_lut[SLUT ? kPlanSmemLut : 1];
     PlanKnots pk;
     stage_finest_knots(sp, sk, pk);
     const int L = sp.nlevels - 1;
-    const int32_t* lut[D];
-    int nbm1[D], ncm1[D], off[D];
+    int loff[D], nbm1[D], last[D], off[D];
     float ls[D], u0[D], u1[D];
 #pragma unroll
     for (int k = 0; k < D; ++k) {
-        lut[k] = sp.span_lut + sp.lut_off[k];
+        loff[k] = sp.lut_off[k];
         nbm1[k] = sp.lut_n[k] - 1;
-        ncm1[k] = sp.ncells[L][k] - 1;
+        last[k] = sp.ncells[L][k] - 1 + pk.off[k];   // index into sk of the last cell's left breakpoint
         ls[k] = sp.lut_scale[k];
         off[k] = pk.off[k];
         u0[k] = pk.u0[k];
         u1[k] = pk.u1[k];
     }
+    if (SLUT) {
+        const int tot = sp.lut_off[D - 1] + sp.lut_n[D - 1];
+        for (int i = threadIdx.x; i < tot; i += blockDim.x) s_lut[i] = sp.span_lut[i];
+        __syncthreads();
+    }
     const int n1 = sp.ncells[L][1], n2 = D == 3 ? sp.ncells[L][2] : 1;
     const int32_t* __restrict__ fslot = sp.finest_slot;
+    const int32_t* __restrict__ glut = sp.span_lut;
     const unsigned lane = threadIdx.x & 31;
     const unsigned stride = gridDim.x * blockDim.x;
     const unsigned nround = (n + 2 * stride - 1) / (2 * stride) * (2 * stride);  // n < 2^31 and stride < 2^20: no overflow
@@ -276,23 +284,28 @@ __global__ void __launch_bounds__(256) k_plan_count_fast(const __grid_constant__
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const unsigned i = i0 + h * stride;
-            bool inside = true, good = true;
+            bool ok = true, inside = true;
             int c[D];
 #pragma unroll
             for (int k = 0; k < D; ++k) {
+                // branch-free: bin -> candidate cell c0 -> (b0, b1, b2) = its breakpoints and the next one -> the cell is c0
+                // or c0 + 1 -> verified against its own two breakpoints
                 const float x = u[h][k];
-                const bool in = (x >= u0[k]) && (x <= u1[k]);   // false for NaN
-                const int bin = in ? min((int)((x - u0[k]) * ls[k]), nbm1[k]) : 0;
-                int cc = __ldg(lut[k] + bin) + off[k];          // index into sk of the candidate cell's left breakpoint
-                cc += (x >= sk[cc + 1]) ? 1 : 0;
-                cc = min(cc, ncm1[k] + off[k]);
-                good &= (x >= sk[cc]) && ((x < sk[cc + 1]) || (cc == ncm1[k] + off[k]));
+                const bool in = (x >= u0[k]) & (x <= u1[k]);   // false for NaN
+                int bin = min((int)((x - u0[k]) * ls[k]), nbm1[k]);
+                bin = in ? bin : 0;
+                const int c0 = (SLUT ? s_lut[loff[k] + bin] : __ldg(glut + loff[k] + bin)) + off[k];
+                const float b0 = sk[c0], b1 = sk[c0 + 1], b2 = sk[c0 + 2];   // the p repeated end knots pad the last read
+                const bool inc = x >= b1;
+                const float lo = inc ? b1 : b0, hi = inc ? b2 : b1;
+                const int cc = min(c0 + (inc ? 1 : 0), last[k]);
+                ok &= (x >= lo) & ((x < hi) | (cc == last[k]));
                 inside &= in;
                 c[k] = cc - off[k];
             }
             int sl = -1;
             if (i < n) {
-                if (inside && good) {
+                if (inside & ok) {
                     int lin = c[0] * n1 + c[1];
                     if (D == 3) lin = lin * n2 + c[2];
                     sl = __ldg(fslot + lin);
@@ -560,10 +573,12 @@ extern "C" int thb_plan_build(const thb_space_desc* space, const float* params, 
         if (space->span_lut && space->finest_slot && finest_knots <= kPlanSmemKnots) {
             THB_CUDA(cudaMemsetAsync(plan->counters + 3, 0, sizeof(int32_t), st));
             // plan->scratch holds the (normally empty) list of unverified points
-            if (space->ndim == 3)
-                k_plan_count_fast<3><<<grid_for(n, 256, 16), 256, 0, st>>>(*space, params, (unsigned)n, plan->slot, plan->cell_count, plan->scratch, plan->counters);
-            else
-                k_plan_count_fast<2><<<grid_for(n, 256, 16), 256, 0, st>>>(*space, params, (unsigned)n, plan->slot, plan->cell_count, plan->scratch, plan->counters);
+            const int lut_tot = space->lut_off[space->ndim - 1] + space->lut_n[space->ndim - 1];
+            const int g = grid_for(n, 256, 16);
+#define THB_COUNT(D_, S_) k_plan_count_fast<D_, S_><<<g, 256, 0, st>>>(*space, params, (unsigned)n, plan->slot, plan->cell_count, plan->scratch, plan->counters)
+            if (space->ndim == 3) { if (lut_tot <= kPlanSmemLut) THB_COUNT(3, true); else THB_COUNT(3, false); }
+            else { if (lut_tot <= kPlanSmemLut) THB_COUNT(2, true); else THB_COUNT(2, false); }
+#undef THB_COUNT
             THB_LAUNCHED();
             k_plan_fixup<<<thb_num_sms(), 256, 0, st>>>(*space, params, plan->scratch, plan->counters, plan->slot, plan->cell_count);
             THB_LAUNCHED();
