@@ -139,6 +139,59 @@ __global__ void __launch_bounds__(32) v4(int iters, float* sink) {
     for (int m = 0; m < 8; ++m) t += hsum2(a[m]);
     if (t == 12345.678f) sink[0] = t;
 }
+// V5: FFMA2 with a SCALAR multiplier shared by 16 consecutive instructions (register operands only)
+__global__ void __launch_bounds__(32) v5(int iters, float* sink) {
+    f32x2 x[16], acc[16]; float sc[4];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { x[i] = pack2(threadIdx.x * 1e-3f + i, 0.5f * i); acc[i] = 0ull; }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sc[j] = 1.0f + 1e-3f * j + threadIdx.x * 1e-6f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const f32x2 s2 = pack2(sc[j], sc[j]);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) ffma2(acc[i], s2, x[i]); }
+    }
+    float t = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) t += hsum2(acc[i]);
+    if (t == 12345.678f) sink[0] = t;
+}
+// V6: the first stage of the net evaluation: per b four broadcast LDS.128 (W[a][b][0..3]), 2 points, e[q][a][h] += B[q][b] * W
+__global__ void __launch_bounds__(32) v6(int iters, float* sink) {
+    extern __shared__ __align__(16) float dyn[]; __shared__ __align__(16) float net[64];
+    for (int i = threadIdx.x; i < 64; i += 32) net[i] = 1.0f / (1.0f + i);
+    if (dyn == nullptr) net[0] = 0; __syncwarp();
+    float fb[2][4];
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) fb[q][b] = 1.0f + 1e-3f * b + q + threadIdx.x * 1e-6f;
+    f32x2 e[2][4][2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int a = 0; a < 4; ++a) e[q][a][0] = e[q][a][1] = 0ull;
+    for (int it = 0; it < iters; ++it) {
+        const ulonglong2* col = (const ulonglong2*)net;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            ulonglong2 cv[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) cv[a] = col[a * 4 + b];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) { const f32x2 bb = pack2(fb[q][b], fb[q][b]);
+#pragma unroll
+                for (int a = 0; a < 4; ++a) { ffma2(e[q][a][0], bb, cv[a].x); ffma2(e[q][a][1], bb, cv[a].y); } }
+        }
+    }
+    float t = 0;
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int a = 0; a < 4; ++a) t += hsum2(e[q][a][0]) + hsum2(e[q][a][1]);
+    if (t == 12345.678f) sink[0] = t;
+}
 template <typename K> void run(const char* name, K k, int warps, int iters, double flop_per_thread_iter, int pad_extra = 0) {
     int sms; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     int pad = (200 * 1024) / warps - 5 * 1024; cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
@@ -156,5 +209,7 @@ int main() {
     run("V1 FFMA   3 pts x 1 supp", v1<3>, 8, it, f1 * 3); run("V1 FFMA   3 pts x 1 supp", v1<3>, 6, it, f1 * 3); run("V1 FFMA   2 pts x 1 supp", v1<2>, 10, it, f1 * 2); run("V1 FFMA   2 pts x 1 supp", v1<2>, 6, it, f1 * 2);
     run("V2 FFMA   2 pts x 2 supp block", v2, 8, it, f1 * 2); run("V3 FFMA2  2 pts x 2 supp block", v3, 8, it, f1 * 2);
     run("V4 FFMA2  register operands only", v4, 8, it, 2.0 * 2 * 32 * 16); run("V4 FFMA2  register operands only", v4, 16, it, 2.0 * 2 * 32 * 16);
+    run("V5 FFMA2  scalar multiplier x16, registers", v5, 8, it, 2.0 * 2 * 64); run("V5 FFMA2  scalar multiplier x16, registers", v5, 16, it, 2.0 * 2 * 64);
+    run("V6 FFMA2  net stage 1 (LDS.128 + scalar)", v6, 8, it, 2.0 * 2 * 64); run("V6 FFMA2  net stage 1 (LDS.128 + scalar)", v6, 16, it, 2.0 * 2 * 64);
     return 0;
 }

@@ -165,8 +165,63 @@ def contraction(R):
     return out
 
 
+def bezier_and_vtu(R):
+    """Bezier extraction (bspline_funcs.py:242-284), per-point multilevel extraction operators
+    (core.py:295-379) and the hexahedral adaptive grid of plot3DAdaptiveGrid (utils.py:296-399; pyvista is replaced
+    by a stand-in that records what would have been written to the .vtu file)."""
+    import types
+    from itertools import product
+
+    S, C, B, U = R.space, R.core, R.bspline_funcs, R.utils
+    out = {}
+    for tag, knots, p in (("A", U_A, 2), ("B", U_B, 3), ("D", U_D, 3)):
+        out[f"bez_{tag}"] = np.stack(B.bezier_extraction(np.asarray(knots, dtype=np.float64), p))
+    for name in ("block2d", "block3d"):
+        knots, degrees, nlev, boxes, grid, extra = CONFIGS[name]
+        tp = S.TensorProduct([S.BSpline(np.array(Uk, dtype=np.float64), p) for Uk, p in zip(knots, degrees)])
+        h = S.Space(tp, nlev)
+        h.build_hierarchy_from_domain_sequence()
+        for lev, lo, hi in boxes:
+            for c in product(*[range(a, b) for a, b in zip(lo, hi)]):
+                h._refine_cell(tuple(c), lev)
+        h.build_hierarchy_from_domain_sequence()
+        ac = C.compute_active_cells_active_supp(h.cells, h.fns, h.degrees)
+        fc = C.compute_refinement_operators(h.fns, h.Coeff, h.degrees)
+        rng = np.random.default_rng(11)
+        prm = rng.random((23, len(degrees))).astype(np.float32).astype(np.float64) * 0.998 + 0.001
+        spans, num_supp, _ = C.compute_active_span_v2(prm, h.knotvectors, h.cells, h.degrees, ac, fc)
+        ops = C.compute_multilevel_bezier_extraction_operators(prm, spans, ac, fc, h.sh_cells, h.sh_fns, h.knotvectors, h.degrees)
+        out[f"{name}_params"] = prm
+        out[f"{name}_num_supp"] = np.array(num_supp, dtype=np.int64)
+        out[f"{name}_ops"] = np.concatenate([np.asarray(o, dtype=np.float64).reshape(len(o), -1) for o in ops])
+        if name == "block3d":
+            rec = {}
+
+            class Grid:
+                def __init__(self, cells, cell_types, points):
+                    rec["cells"], rec["types"], rec["points"] = np.asarray(cells), np.asarray(cell_types), np.asarray(points)
+
+                def save(self, filename):
+                    rec["filename"] = filename
+
+            U.pv.CellType = types.SimpleNamespace(HEXAHEDRON=12)
+            U.pv.UnstructuredGrid = Grid
+            off = np.cumsum([0] + [int(np.prod(h.sh_fns[l])) for l in range(nlev)])
+            from thb_diff_b200 import configs as my_configs  # Greville control points (same formula as bench.py)
+            import thb_diff_b200.multilevel_spline_space as mine
+
+            hs = mine.Space(mine.TensorProduct([mine.BSpline(np.array(Uk, dtype=np.float64), p) for Uk, p in zip(knots, degrees)]), nlev)
+            cp = my_configs.greville_ctrl_pts(hs).astype(np.float64)
+            cps = {l: cp[off[l]:off[l + 1]].reshape(*h.sh_fns[l], 3) for l in range(nlev)}
+            U.plot3DAdaptiveGrid("golden_grid", ac, cps, h.knotvectors, fc, h.sh_fns, h.degrees)
+            out["vtu_cells"], out["vtu_types"], out["vtu_points"] = rec["cells"], rec["types"], rec["points"]
+            out["vtu_ctrl_pts"] = cp
+    return out
+
+
 def main():
     R = _refshim.load_reference(fp16_tables=False)
+    np.savez_compressed(os.path.join(HERE, "bezier_vtu.npz"), **bezier_and_vtu(R))
     for name, spec in CONFIGS.items():
         np.savez_compressed(os.path.join(HERE, f"space_{name}.npz"), **run_config(R, name, spec))
     np.savez_compressed(os.path.join(HERE, "kat.npz"), **kat(R))
