@@ -38,3 +38,15 @@ pts = THB_nn_module(Jm, phi, cumsum, device)(cp)
 print("max |evaluated - params| with Greville control points:", float((pts.detach().cpu() - torch.from_numpy(params).float()).abs().max()))
 pts.square().mean().backward()
 print("grad w.r.t. control points:", tuple(cp.grad.shape))
+
+# the adaptive grid as a .vtu file (reference: utils.plot3DAdaptiveGrid) and the Bezier extraction operators of a few points
+from thb_diff_b200.bezier import compute_multilevel_bezier_extraction_operators  # noqa: E402
+from thb_diff_b200.utils import plot3DAdaptiveGrid  # noqa: E402
+
+path, vtu_pts, vtu_conn = plot3DAdaptiveGrid("/tmp/thb_adaptive_grid", ac_cells, ctrl_pts, h_space.knotvectors, fn_coeffs,
+                                             h_space.sh_fns, h_space.degrees)
+print("wrote", path, "with", len(vtu_conn), "hexahedra and", len(vtu_pts), "nodes")
+few, few_ns = compute_active_span(params[:5], h_space.knotvectors, h_space.cells, h_space.degrees, ac_cells)
+ops = compute_multilevel_bezier_extraction_operators(params[:5], few, ac_cells, fn_coeffs, h_space.sh_cells, h_space.sh_fns,
+                                                     h_space.knotvectors, h_space.degrees)
+print("Bezier operators of point 0:", ops[0].shape)
