@@ -352,7 +352,10 @@ __global__ void __launch_bounds__(1024) k_plan_scan(const int32_t* __restrict__ 
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
     const int per = (((nslots + 1023) >> 10) + 3) & ~3;
     const int b0 = t * per, b1 = min(b0 + per, nslots);
+    const int sh = (ppi & (ppi - 1)) == 0 ? 31 - __clz(ppi) : -1;  // points_per_item is normally a power of two
+    auto items_of = [&](int c) { return sh >= 0 ? (c + ppi - 1) >> sh : (c + ppi - 1) / ppi; };
     int tp = 0, ti = 0;
+#pragma unroll 4
     for (int i = b0; i < b1; i += 4) {
         int4 c = make_int4(0, 0, 0, 0);
         if (i + 3 < nslots) {
@@ -363,7 +366,7 @@ __global__ void __launch_bounds__(1024) k_plan_scan(const int32_t* __restrict__ 
             if (i + 2 < nslots) c.z = count[i + 2];
         }
         tp += c.x + c.y + c.z + c.w;
-        ti += (c.x + ppi - 1) / ppi + (c.y + ppi - 1) / ppi + (c.z + ppi - 1) / ppi + (c.w + ppi - 1) / ppi;
+        ti += items_of(c.x) + items_of(c.y) + items_of(c.z) + items_of(c.w);
     }
     int sp_ = tp, si_ = ti;  // inclusive warp scan of the run totals
 #pragma unroll
@@ -386,14 +389,15 @@ __global__ void __launch_bounds__(1024) k_plan_scan(const int32_t* __restrict__ 
     __syncthreads();
     int rp = (w ? s_wp[w - 1] : 0) + sp_ - tp;
     int ri = (w ? s_wi[w - 1] : 0) + si_ - ti;
+#pragma unroll 4
     for (int i = b0; i < b1; i += 4) {
         if (i + 3 < nslots) {
             const int4 c = *reinterpret_cast<const int4*>(count + i);
             int4 ps, is;
-            ps.x = rp; is.x = ri; rp += c.x; ri += (c.x + ppi - 1) / ppi;
-            ps.y = rp; is.y = ri; rp += c.y; ri += (c.y + ppi - 1) / ppi;
-            ps.z = rp; is.z = ri; rp += c.z; ri += (c.z + ppi - 1) / ppi;
-            ps.w = rp; is.w = ri; rp += c.w; ri += (c.w + ppi - 1) / ppi;
+            ps.x = rp; is.x = ri; rp += c.x; ri += items_of(c.x);
+            ps.y = rp; is.y = ri; rp += c.y; ri += items_of(c.y);
+            ps.z = rp; is.z = ri; rp += c.z; ri += items_of(c.z);
+            ps.w = rp; is.w = ri; rp += c.w; ri += items_of(c.w);
             *reinterpret_cast<int4*>(start + i) = ps;
             *reinterpret_cast<int4*>(item_start + i) = is;
         } else {
@@ -402,7 +406,7 @@ __global__ void __launch_bounds__(1024) k_plan_scan(const int32_t* __restrict__ 
                 start[k] = rp;
                 item_start[k] = ri;
                 rp += c;
-                ri += (c + ppi - 1) / ppi;
+                ri += items_of(c);
             }
         }
     }
