@@ -7,42 +7,86 @@
 // coalesced; the backward keeps per-lane partial sums while consecutive points share one support list
 // (points of the same cell do) and only issues atomics when the list changes -- "warp-aggregated"
 // scatter-add: 3*S atomics per run of points instead of per point.
+#include <cstdlib>
+#include <cstdint>
+
 #include "thb_common.cuh"
 
 namespace {
 
 constexpr int kWarpsPerCta = 8;
 
-constexpr int kFwdStrips = 4;  // segments up to 128 entries are fetched in one batch of independent loads
+constexpr int kFwdStrips = 5;   // support lists up to 160 entries live in registers (one entry per lane and strip)
+#ifndef THB_FWD_POINTS
+#define THB_FWD_POINTS 16
+#endif
+constexpr int kFwdPoints = THB_FWD_POINTS;  // consecutive points per warp
 
+// A warp owns kFwdPoints consecutive points.  Per point the lanes read the segment coalesced (one entry per lane and
+// strip).  The gathered control points stay in registers for as long as consecutive points have the same support
+// list (points of one cell do), so the dependent second round trip of a point -- the gather through Jm -- disappears
+// inside a run.  (A variant that streams the warp's contiguous PHI / Jm run through a shared-memory ring with
+// 16-byte cp.async was measured at 4.4 ms int64 / 3.2 ms int32 against 3.7 / 3.7 ms for this one on config 3: its
+// per-point bookkeeping executes 3.2 G warp-instructions, so it is issue-bound before it is bandwidth-bound.)
 template <typename JT, typename CT, int CPD>
 __global__ void __launch_bounds__(kWarpsPerCta * 32) k_csr_forward(const float* __restrict__ cp, const JT* __restrict__ jm,
                                                                      const float* __restrict__ phi,
                                                                      const CT* __restrict__ cumsum, float* __restrict__ out,
                                                                      int64_t npoints) {
     const int lane = threadIdx.x & 31;
-    const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
-    const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerCta;
-    for (int64_t i = warp0; i < npoints; i += nwarps) {
-        const int64_t beg = i ? (int64_t)cumsum[i - 1] : 0;
-        const int64_t end = (int64_t)cumsum[i];
+    const int64_t warp = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+    const int64_t p0 = warp * kFwdPoints;
+    if (p0 >= npoints) return;
+    const int np = (int)min((int64_t)kFwdPoints, npoints - p0);
+    // segment bounds of the warp's points: lane l holds the END of point p0 + l
+    const int64_t my_end = lane < np ? (int64_t)cumsum[p0 + lane] : 0;
+    int64_t beg = p0 ? (int64_t)cumsum[p0 - 1] : 0;
+
+    JT key[kFwdStrips];
+    float cpv[kFwdStrips][CPD];
+    int runS = -1;
+#pragma unroll
+    for (int s = 0; s < kFwdStrips; ++s) key[s] = (JT)-2;
+
+    for (int i = 0; i < np; ++i) {
+        const int64_t end = __shfl_sync(0xffffffffu, my_end, i);
+        const int64_t S64 = end - beg;
         float acc[CPD];
 #pragma unroll
         for (int k = 0; k < CPD; ++k) acc[k] = 0.0f;
-        for (int64_t j0 = beg; j0 < end; j0 += 32 * kFwdStrips) {
-            float w[kFwdStrips];
-            int64_t r[kFwdStrips];
-#pragma unroll
-            for (int s = 0; s < kFwdStrips; ++s) {  // all index / weight loads of the batch are in flight together
-                const int64_t j = j0 + s * 32 + lane;
-                const bool ok = j < end;
-                w[s] = ok ? __ldg(phi + j) : 0.0f;
-                r[s] = ok ? (int64_t)__ldg(jm + j) : 0;
-            }
+        if (S64 <= 32 * kFwdStrips) {
+            const int S = (int)S64;
+            JT cj[kFwdStrips];
+            float cw[kFwdStrips];
+            bool same = S == runS;
 #pragma unroll
             for (int s = 0; s < kFwdStrips; ++s) {
+                const int o = s * 32 + lane;
+                const bool ok = o < S;
+                cj[s] = ok ? __ldg(jm + beg + o) : (JT)-1;
+                cw[s] = ok ? __ldg(phi + beg + o) : 0.0f;
+            }
 #pragma unroll
-                for (int k = 0; k < CPD; ++k) acc[k] = fmaf(w[s], __ldg(cp + r[s] * CPD + k), acc[k]);
+            for (int s = 0; s < kFwdStrips; ++s) same = same && (cj[s] == key[s]);
+            if (!__all_sync(0xffffffffu, same)) {
+#pragma unroll
+                for (int s = 0; s < kFwdStrips; ++s) {
+                    key[s] = cj[s];
+#pragma unroll
+                    for (int k = 0; k < CPD; ++k) cpv[s][k] = cj[s] >= 0 ? __ldg(cp + (int64_t)cj[s] * CPD + k) : 0.0f;
+                }
+                runS = S;
+            }
+#pragma unroll
+            for (int s = 0; s < kFwdStrips; ++s)
+#pragma unroll
+                for (int k = 0; k < CPD; ++k) acc[k] = fmaf(cw[s], cpv[s][k], acc[k]);
+        } else {  // very long list: streamed, nothing cached
+            for (int64_t j = beg + lane; j < end; j += 32) {
+                const float w = __ldg(phi + j);
+                const int64_t r = (int64_t)__ldg(jm + j);
+#pragma unroll
+                for (int k = 0; k < CPD; ++k) acc[k] = fmaf(w, __ldg(cp + r * CPD + k), acc[k]);
             }
         }
 #pragma unroll
@@ -52,8 +96,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_csr_forward(const float* 
         }
         if (lane == 0) {
 #pragma unroll
-            for (int k = 0; k < CPD; ++k) out[i * CPD + k] = acc[k];
+            for (int k = 0; k < CPD; ++k) out[(p0 + i) * CPD + k] = acc[k];
         }
+        beg = end;
     }
 }
 
@@ -142,9 +187,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_csr_backward(const float*
 template <typename JT, typename CT>
 int launch_fwd(const float* cp, const void* jm, const float* phi, const void* cs, float* out, int64_t n, int cpd,
                cudaStream_t st) {
-    const int64_t want = (n + kWarpsPerCta - 1) / kWarpsPerCta;
-    const int64_t cap = (int64_t)thb_num_sms() * 64;
-    const int grid = (int)(want < cap ? want : cap);
+    const int64_t warps = (n + kFwdPoints - 1) / kFwdPoints;
+    const int grid = (int)((warps + kWarpsPerCta - 1) / kWarpsPerCta);
 #define THB_FWD(C)                                                                                             \
     k_csr_forward<JT, CT, C><<<grid, kWarpsPerCta * 32, 0, st>>>(cp, (const JT*)jm, phi, (const CT*)cs, out, n)
     switch (cpd) {

@@ -203,19 +203,6 @@ constexpr int kWChunk = THB_WCHUNK;  // supports staged per chunk by one warp
 constexpr int kMaxCC = 128;  // coarse-support control points gathered once per item (else per chunk)
 constexpr int kRowPad = 4;   // floats of padding per staged tile row: rows s..s+3 start in different banks
 
-THB_DEV void cp_async16(void* smem, const void* gmem) {
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
-}
-THB_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-THB_DEV void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-THB_DEV void cp_async4(void* smem, const void* gmem) {
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem) : "memory");
-}
-
 // Per-warp shared memory.  Everything that can be known ahead of time is double buffered and filled by
 // cp.async, so the global-memory latency of item i+1 is paid while item i is being computed and costs no
 // registers.
