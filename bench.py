@@ -322,7 +322,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-variants", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
-    ap.add_argument("--e2e-chunks", type=int, default=16)
+    ap.add_argument("--e2e-chunks", type=int, default=8)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -519,7 +519,8 @@ def main():
         "clocks": clk.summary(), "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": n * P.ndim * 4, "d2h_bytes_per_step": n * 3 * 4,
                 "ms_per_step": float(e2e_ms.item()),
-                "how": f"engine.HostPipeline: {len(pipe.bounds)} chunks, H2D / compute / D2H overlapped on 3 streams, pinned host buffers",
+                "how": f"engine.HostPipeline: {len(pipe.bounds)} chunks, H2D / compute / D2H overlapped on 3 streams, pinned host buffers, "
+                       f"{'one CUDA graph replay per step' if pipe._graph is not None else 'eager launches'}",
                 "check_max_abs_diff_vs_device_path": e2e_diff,
                 "host_copies_alone": copies},
         "roofline": roofline,

@@ -275,10 +275,16 @@ class HostPipeline:
 
     The batch is cut into contiguous chunks; three CUDA streams overlap the H2D copy of chunk c+1, the
     plan + fused kernel of chunk c and the D2H copy of chunk c-1 (PCIe is full duplex), so a step costs about
-    max(H2D, D2H, compute) instead of their sum.  Device buffers are allocated once."""
+    max(H2D, D2H, compute) instead of their sum.  Device buffers are allocated once.
 
-    def __init__(self, P, n_points, cp_dim=3, n_chunks=8, cellnet=True, formulation=None):
+    use_graph: the whole step (copies, ~10 launches per chunk, the cross-stream dependencies) is captured into ONE CUDA
+    graph the first time it runs with a given set of buffers and replayed afterwards, so the host issues a single
+    launch per step instead of a few hundred calls; a step with other buffers is captured again (eager fallback if
+    capture is not possible)."""
+
+    def __init__(self, P, n_points, cp_dim=3, n_chunks=8, cellnet=True, formulation=None, use_graph=True):
         self.P, self.n, self.cpd = P, int(n_points), cp_dim
+        self.use_graph, self._graph, self._graph_key = bool(use_graph), None, None
         self.formulation = formulation if formulation is not None else ("local_net" if cellnet else "per_point")
         n_chunks = max(1, min(n_chunks, (self.n + 65535) // 65536))
         base, rem = divmod(self.n, n_chunks)
@@ -296,8 +302,28 @@ class HostPipeline:
         self.s_in, self.s_cmp, self.s_out = (torch.cuda.Stream(device=dev) for _ in range(3))
 
     def run(self, params_host, ctrl_pts, out_host):
-        """Enqueues one full evaluation; returns after everything is enqueued (call torch.cuda.synchronize()
-        or wait on the returned event before reading out_host)."""
+        """Enqueues one full evaluation on the current stream; returns after everything is enqueued (synchronise the
+        stream / device before reading out_host)."""
+        if not self.use_graph:
+            return self._enqueue(params_host, ctrl_pts, out_host)
+        key = (params_host.data_ptr(), ctrl_pts.data_ptr(), out_host.data_ptr(), self.P.version, self.formulation)
+        if self._graph_key != key:
+            self._enqueue(params_host, ctrl_pts, out_host)   # eager once: allocates plans / workspaces, sizes the grids
+            torch.cuda.synchronize(self.P.device)
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._enqueue(params_host, ctrl_pts, out_host)
+                self._graph, self._graph_key = g, key
+                self._keep = (params_host, ctrl_pts, out_host)  # the graph holds raw pointers into these
+            except Exception:
+                self.use_graph, self._graph, self._graph_key = False, None, None
+                torch.cuda.synchronize(self.P.device)
+                return self._enqueue(params_host, ctrl_pts, out_host)
+        self._graph.replay()
+        return None
+
+    def _enqueue(self, params_host, ctrl_pts, out_host):
         cur = torch.cuda.current_stream(self.P.device)
         for s in (self.s_in, self.s_cmp, self.s_out):
             s.wait_stream(cur)
