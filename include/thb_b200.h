@@ -187,9 +187,12 @@ THB_API int thb_cell_nets(const thb_space_desc* space, const thb_plan_desc* plan
 THB_API int thb_eval_nets(const thb_space_desc* space, const thb_plan_desc* plan, const float* nets, int with_derivatives,
                   int cp_dim, const int32_t* channels, int nchannels, float* const* out_host, void* stream);
 /* grad_ctrl_pts[nctrl, cp_dim] (zeroed by the callee) = A^T grad_out, A = value-channel basis matrix.
- * Replaces THBEval.backward (THB/torch_funcs.py:35-47) for the fused path. */
+ * Replaces THBEval.backward (THB/torch_funcs.py:35-47) for the fused path.  workspace: thb_net_workspace_floats(space, 0)
+ * floats (overwritten) -> the gradient goes through per-cell net gradients (one reduction per work item, one transposed
+ * fold per cell); NULL -> the per-item tile kernel. */
 THB_API int thb_eval_fused_backward(const thb_space_desc* space, const thb_plan_desc* plan, const float* params,
-                            const float* grad_out, int cp_dim, float* grad_ctrl_pts, int64_t nctrl, void* stream);
+                            const float* grad_out, int cp_dim, float* grad_ctrl_pts, int64_t nctrl, float* workspace,
+                            void* stream);
 
 /* ---- measurement helpers -----------------------------------------------------------------------------------
  * Dependent-chain FP32 FMA micro-kernel used by bench.py to measure the FP32 roofline denominator.

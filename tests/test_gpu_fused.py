@@ -76,14 +76,16 @@ def test_greville_control_points_reproduce_the_parameters(name, formulation):
         assert np.abs(J - e).max() < 2e-4
 
 
+@pytest.mark.parametrize("cp_dim", [3, 4])
+@pytest.mark.parametrize("formulation", ["local_net", "per_point"])
 @pytest.mark.parametrize("name", IDENTITY_OK)
-def test_fused_backward(name):
+def test_fused_backward(name, formulation, cp_dim):
     from thb_diff_b200 import engine
 
-    g, h, P, plan, cp, cs = _setup(name)
-    go = np.random.default_rng(1).standard_normal((len(cs), 3)).astype(np.float32)
+    g, h, P, plan, cp, cs = _setup(name, cp_dim=cp_dim)
+    go = np.random.default_rng(1).standard_normal((len(cs), cp_dim)).astype(np.float32)
     ref = O.eval_backward(go, cp.shape, g["Jm"], g["PHI"], cs)
-    got = engine.eval_fused_backward(P, plan, torch.from_numpy(go).cuda()).cpu().numpy()
+    got = engine.eval_fused_backward(P, plan, torch.from_numpy(go).cuda(), formulation=formulation).cpu().numpy()
     assert rel_err(got, ref, scale=np.abs(ref).max()).max() <= TOL
 
 

@@ -114,6 +114,8 @@ def test_c3_full_size_properties(c3):
     x = torch.randn((P.nCP, 3), device="cuda")
     Ax = engine.eval_fused(P, plan, x)[0]
     ATg = engine.eval_fused_backward(P, plan, g)
+    ATg2 = engine.eval_fused_backward(P, plan, g, formulation="per_point")
+    assert float((ATg - ATg2).abs().max()) <= 1e-4 * float(ATg2.abs().max())
     lhs = float((Ax.double() * g.double()).sum())
     rhs = float((x.double() * ATg.double()).sum())
     assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), float(Ax.double().norm() * g.double().norm()))

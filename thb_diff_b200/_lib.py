@@ -62,7 +62,7 @@ def _load():
         "thb_net_workspace_floats": (i64, [C.POINTER(SpaceDesc), i32]),
         "thb_cell_nets": (i32, [C.POINTER(SpaceDesc), C.POINTER(PlanDesc), vp, i32, i32, vp, vp]),
         "thb_eval_nets": (i32, [C.POINTER(SpaceDesc), C.POINTER(PlanDesc), vp, i32, i32, C.POINTER(C.c_int32), i32, C.POINTER(vp), vp]),
-        "thb_eval_fused_backward": (i32, [C.POINTER(SpaceDesc), C.POINTER(PlanDesc), vp, vp, i32, vp, i64, vp]),
+        "thb_eval_fused_backward": (i32, [C.POINTER(SpaceDesc), C.POINTER(PlanDesc), vp, vp, i32, vp, i64, vp, vp]),
         "thb_fma_peak": (i32, [i32, i32, vp, C.POINTER(C.c_double), vp]),
     }
     for name, (res, args) in sig.items():

@@ -539,6 +539,274 @@ __global__ void __launch_bounds__(kThreads, THB_NET_MINB) k_net_eval(const __gri
     }
 }
 
+// ---- backward through the nets -------------------------------------------------------------------------------------
+// grad_ctrl_pts = A^T grad_out with A the value-channel basis matrix (THBEval.backward, THB/torch_funcs.py:35-47).  With
+// out = <tp(u), W_cell> the chain rule splits the same way as the forward pass:
+//   k_net_backward : gW_cell[t][k] += sum_{points of the item} tp(u)[t] * g[k]      (per work item, atomics into the
+//                    per-cell net-gradient workspace: T*cp_dim per ITEM instead of S*cp_dim per point)
+//   k_cell_unfold  : grad_cp[own t] += gW[t],   grad_cp[Jm_s] += <tile_s, gW>          (per cell, the transposed fold)
+struct NetBwdSmem {
+    int4 rec[3][4];
+    float knots[2][3][8];
+    float rk[3][8];
+    float4 prec[2][64];
+    float4 fa[64], fb[64], fc[64], g[64];  // 1-D basis values (padded to 4) and output gradient of a sub-batch
+};
+
+template <int N0, int N1, int N2, int CPD>
+__global__ void __launch_bounds__(kThreads, 16) k_net_backward(const __grid_constant__ thb_space_desc sp, const __grid_constant__ Args ar,
+                                                              float* __restrict__ gnets) {
+    using SH = Shp<N0, N1, N2>;
+    constexpr int TS = SH::TS, BC = N1 * N2;
+    static_assert(BC <= 16 && N0 <= 4, "lane = (half, b, c) owns the entries a = 0..3 of its (b, c)");
+    constexpr int SB = 64;
+    __shared__ __align__(16) NetBwdSmem sm;
+    const int lane = threadIdx.x;
+    const int half = lane >> 4, l16 = lane & 15;
+    const bool live = l16 < BC;
+    const int jb = live ? l16 / N2 : 0, jc = live ? l16 % N2 : 0;
+    const int nitems = ar.counters[0];
+    int32_t* const cursor = ar.counters + 1;
+    const int d = sp.ndim;
+
+    int c3 = 0;
+    if (lane == 0) c3 = atomicAdd(cursor, 3);
+    const int id0 = __shfl_sync(0xffffffffu, c3, 0);
+    if (id0 >= nitems) return;
+    int id1 = id0 + 1, id2 = id0 + 2;
+    Item it = load_item(sp, ar.items, id0);
+    if (lane < 4 && id1 < nitems) cp_async16(&sm.rec[1][lane], ar.items + (int64_t)id1 * 4 + lane);
+    if (lane < 4 && id2 < nitems) cp_async16(&sm.rec[2][lane], ar.items + (int64_t)id2 * 4 + lane);
+    auto prefetch_knots = [&](const Item& x, float (*knots)[8]) {
+        if (lane < 24) {
+            const int dim = lane >> 3, m = lane & 7;
+            const int P = dim == 0 ? SH::P0 : (dim == 1 ? SH::P1 : SH::P2);
+            const int c = dim == 0 ? x.c0 : (dim == 1 ? x.c1 : x.c2);
+            if (dim < d && m < 2 * P) cp_async4(&knots[dim][m], sp.knots + sp.knot_off[x.lev][dim] + c + 1 + m);
+        }
+    };
+    prefetch_knots(it, sm.knots[0]);
+    prefetch_points<2>(ar, it.begin, it.count, 0, sm.prec[0]);
+    cp_async_commit();
+    int nn_id = 0;
+    if (lane == 0) nn_id = atomicAdd(cursor, 1);
+    int ring = 0, tb = 0, pb = 0;
+    cp_async_wait<0>();
+    __syncwarp();
+
+    for (;;) {
+        if (lane < 24) {
+            const int dim = lane >> 3, m = lane & 7;
+            const int P = dim == 0 ? SH::P0 : (dim == 1 ? SH::P1 : SH::P2);
+            if (dim < d && m < P * (P + 1) / 2) {
+                int j = 1, r = m;
+                while (r >= j) { r -= j; ++j; }
+                sm.rk[dim][m] = 1.0f / (sm.knots[tb][dim][P + r] - sm.knots[tb][dim][P - j + r]);
+            }
+        }
+        __syncwarp();
+        f32x2 w2[2][4];
+#pragma unroll
+        for (int p = 0; p < 2; ++p)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) w2[p][k] = 0ull;
+        const bool nx_valid = id1 < nitems;
+        for (int base = 0; base < it.count; base += SB) {
+            if (base + SB < it.count) {
+                prefetch_points<2>(ar, it.begin, it.count, base + SB, sm.prec[pb ^ 1]);
+            } else if (nx_valid) {
+                const int4* r = sm.rec[(ring + 1) % 3];
+                const Item nx = unpack_item(r[0], r[1], r[2], r[3]);
+                prefetch_points<2>(ar, nx.begin, nx.count, 0, sm.prec[pb ^ 1]);
+                prefetch_knots(nx, sm.knots[tb ^ 1]);
+            }
+            cp_async_commit();
+            // phase 1: lane = point (two per lane): 1-D bases and the point's output gradient -> shared memory
+            const int npts = min(SB, it.count - base);
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int pi = q * 32 + lane;
+                const float4 rec = sm.prec[pb][pi];
+                const float u[3] = {rec.x, rec.y, rec.z};
+                BasesRK<SH, false> bs;
+                bs.eval(u, sm.knots[tb], sm.rk);
+                float a4[4] = {0.f, 0.f, 0.f, 0.f}, b4[4] = {0.f, 0.f, 0.f, 0.f}, c4[4] = {0.f, 0.f, 0.f, 0.f}, g4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int i = 0; i < N0; ++i) a4[i] = bs.n0[i];
+#pragma unroll
+                for (int i = 0; i < N1; ++i) b4[i] = bs.n1[i];
+#pragma unroll
+                for (int i = 0; i < N2; ++i) c4[i] = bs.n2[i];
+                if (pi < npts) {
+                    const int64_t idx = __float_as_int(rec.w);
+#pragma unroll
+                    for (int k = 0; k < CPD; ++k) g4[k] = __ldg(ar.grad_out + idx * CPD + k);
+                }
+                sm.fa[pi] = make_float4(a4[0], a4[1], a4[2], a4[3]);
+                sm.fb[pi] = make_float4(b4[0], b4[1], b4[2], b4[3]);
+                sm.fc[pi] = make_float4(c4[0], c4[1], c4[2], c4[3]);
+                sm.g[pi] = make_float4(g4[0], g4[1], g4[2], g4[3]);   // zero for the slots beyond the item's points
+            }
+            __syncwarp();
+            // phase 2: lane = (half, b, c); the halves take alternate points
+            const float* fbp = reinterpret_cast<const float*>(sm.fb) + jb;
+            const float* fcp = reinterpret_cast<const float*>(sm.fc) + jc;
+            const int nloop = (npts + 1) >> 1;
+#pragma unroll 4
+            for (int j = 0; j < nloop; ++j) {
+                const int pi = 2 * j + half;   // pi == npts (odd count) reads a zero gradient
+                const float4 av = sm.fa[pi];
+                const float4 gv = sm.g[pi];
+                const float bc = fbp[pi * 4] * fcp[pi * 4];
+                const f32x2 bc2 = pack2(bc, bc);
+                const f32x2 x01 = fmul2(pack2(av.x, av.y), bc2), x23 = fmul2(pack2(av.z, av.w), bc2);
+                ffma2(w2[0][0], x01, pack2(gv.x, gv.x)); ffma2(w2[1][0], x23, pack2(gv.x, gv.x));
+                ffma2(w2[0][1], x01, pack2(gv.y, gv.y)); ffma2(w2[1][1], x23, pack2(gv.y, gv.y));
+                ffma2(w2[0][2], x01, pack2(gv.z, gv.z)); ffma2(w2[1][2], x23, pack2(gv.z, gv.z));
+                if (CPD == 4) { ffma2(w2[0][3], x01, pack2(gv.w, gv.w)); ffma2(w2[1][3], x23, pack2(gv.w, gv.w)); }
+            }
+            cp_async_wait<0>();
+            __syncwarp();
+            pb ^= 1;
+        }
+        // the item's contribution to its cell's net gradient: halves summed, half h adds the entries a = 2h, 2h+1
+        {
+            float* dst = gnets + (int64_t)it.slot * 4 * TS;
+#pragma unroll
+            for (int k = 0; k < CPD; ++k) {
+                float o[2][2];
+#pragma unroll
+                for (int p = 0; p < 2; ++p) {
+                    unpack2(w2[p][k], o[p][0], o[p][1]);
+                    o[p][0] += __shfl_xor_sync(0xffffffffu, o[p][0], 16);
+                    o[p][1] += __shfl_xor_sync(0xffffffffu, o[p][1], 16);
+                }
+                if (live) {
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const int a = 2 * half + q;
+                        if (a < N0) atomicAdd(dst + k * TS + a * BC + l16, half ? o[1][q] : o[0][q]);
+                    }
+                }
+            }
+        }
+        if (!nx_valid) break;
+        ring = (ring + 1) % 3;
+        {
+            const int4* r = sm.rec[ring];
+            it = unpack_item(r[0], r[1], r[2], r[3]);
+        }
+        tb ^= 1;
+        const int id3 = __shfl_sync(0xffffffffu, nn_id, 0);
+        id1 = id2;
+        id2 = id3;
+        if (lane < 4 && id3 < nitems) cp_async16(&sm.rec[(ring + 2) % 3][lane], ar.items + (int64_t)id3 * 4 + lane);
+        cp_async_commit();
+        if (lane == 0) nn_id = atomicAdd(cursor, 1);
+    }
+}
+
+// One warp per active cell that holds points: lanes over the window entries scatter the own-level part, then lane = one
+// tiled support: <tile_s, gW> from the factor vectors (rank one) or the tile row, three atomics per support.
+template <int N0, int N1, int N2, int CPD>
+__global__ void __launch_bounds__(32 * kNetWarps) k_cell_unfold(const __grid_constant__ thb_space_desc sp, const __grid_constant__ NetArgs na,
+                                                               float* __restrict__ grad_cp) {
+    using SH = Shp<N0, N1, N2>;
+    constexpr int T = SH::T, TS = SH::TS;
+    __shared__ __align__(16) float4 s_gw[kNetWarps][TS];   // [t] -> (gW[0][t], gW[1][t], gW[2][t], gW[3][t])
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    float4* gw = s_gw[wid];
+    const bool split = sp.sep_vec != nullptr;
+    for (int slot = blockIdx.x * kNetWarps + wid; slot < sp.nslots; slot += gridDim.x * kNetWarps) {
+        if (na.cell_count && __ldg(na.cell_count + slot) == 0) continue;
+        const int4* ci = reinterpret_cast<const int4*>(sp.cellinfo + (int64_t)slot * THB_INFO_W);
+        const int4 a = __ldg(ci), e = __ldg(ci + 1), f = __ldg(ci + 2);
+        const unsigned long long dm = __ldg(sp.dmask + slot);
+        const int lev = a.x, soff = e.x, S = e.y, ndir = e.w;
+        const int ntile = S - ndir, nsep = split ? f.y : 0;
+        const float* src = na.nets + (int64_t)slot * 4 * TS;
+        __syncwarp();
+        for (int t = lane; t < TS; t += 32) gw[t] = make_float4(src[t], src[TS + t], src[2 * TS + t], src[3 * TS + t]);
+        __syncwarp();
+        if (ndir > 0) {
+            const int n1 = sp.nfns[lev][1], n2 = sp.nfns[lev][2];
+            const int64_t f0 = sp.fn_off[lev];
+            for (int t = lane; t < T; t += 32) {
+                if ((dm >> t) & 1ull) {
+                    const int t2 = t % N2, t1 = (t / N2) % N1, t0 = t / (N2 * N1);
+                    const int64_t r = f0 + ((int64_t)(a.y + t0) * n1 + (a.z + t1)) * n2 + (a.w + t2);
+                    const float4 v = gw[t];
+                    atomicAdd(grad_cp + r * CPD, v.x);
+                    if (CPD > 1) atomicAdd(grad_cp + r * CPD + 1, v.y);
+                    if (CPD > 2) atomicAdd(grad_cp + r * CPD + 2, v.z);
+                    if (CPD > 3) atomicAdd(grad_cp + r * CPD + 3, v.w);
+                }
+            }
+        }
+        const float* tile_src = split ? sp.full_tiles + (int64_t)f.z * TS : sp.tiles + (int64_t)e.z * TS;
+        const int32_t* full_jm = split ? sp.full_jm + f.z : sp.supp_jm + soff + ndir;
+        for (int s0 = 0; s0 < ntile; s0 += 32) {
+            const int sidx = s0 + lane;
+            if (sidx >= ntile) continue;
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            int64_t r;
+            if (sidx < nsep) {
+                const float4* fv = reinterpret_cast<const float4*>(sp.sep_vec + (int64_t)(f.x + sidx) * 12);
+                const float4 v0 = __ldg(fv), v1 = __ldg(fv + 1), v2 = __ldg(fv + 2);
+                r = __ldg(sp.sep_jm + f.x + sidx);
+#pragma unroll
+                for (int i = 0; i < N0; ++i)
+#pragma unroll
+                    for (int j = 0; j < N1; ++j) {
+                        const float ab = f4c(v0, i) * f4c(v1, j);
+#pragma unroll
+                        for (int k = 0; k < N2; ++k) {
+                            const float x = ab * f4c(v2, k);
+                            const float4 gv = gw[(i * N1 + j) * N2 + k];
+                            acc[0] = fmaf(x, gv.x, acc[0]); acc[1] = fmaf(x, gv.y, acc[1]); acc[2] = fmaf(x, gv.z, acc[2]);
+                            if (CPD == 4) acc[3] = fmaf(x, gv.w, acc[3]);
+                        }
+                    }
+            } else {
+                const float* row = tile_src + (int64_t)(sidx - nsep) * TS;
+                r = __ldg(full_jm + (sidx - nsep));
+#pragma unroll 4
+                for (int t4 = 0; t4 < TS; t4 += 4) {
+                    const float4 x = __ldg(reinterpret_cast<const float4*>(row + t4));
+                    const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) {
+                        const float4 gv = gw[t4 + m];
+                        acc[0] = fmaf(xs[m], gv.x, acc[0]); acc[1] = fmaf(xs[m], gv.y, acc[1]); acc[2] = fmaf(xs[m], gv.z, acc[2]);
+                        if (CPD == 4) acc[3] = fmaf(xs[m], gv.w, acc[3]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < CPD; ++k) atomicAdd(grad_cp + r * CPD + k, acc[k]);
+        }
+    }
+}
+
+template <int N0, int N1, int N2>
+int launch_net_backward(const thb_space_desc* sp, const Args* ar, const NetArgs* na, float* grad_cp, int cpd, cudaStream_t st) {
+#define THB_NET_BWD(CPD_)                                                                              \
+    do {                                                                                               \
+        static int g1 = 0, g2 = 0;                                                                     \
+        if (g1 == 0) g1 = persistent_grid(k_net_backward<N0, N1, N2, CPD_>, kThreads);                  \
+        if (g2 == 0) g2 = persistent_grid(k_cell_unfold<N0, N1, N2, CPD_>, 32 * kNetWarps);             \
+        k_net_backward<N0, N1, N2, CPD_><<<g1, kThreads, 0, st>>>(*sp, *ar, na->nets);                  \
+        THB_LAUNCHED();                                                                                \
+        k_cell_unfold<N0, N1, N2, CPD_><<<min((sp->nslots + kNetWarps - 1) / kNetWarps, g2), 32 * kNetWarps, 0, st>>>(*sp, *na, grad_cp); \
+        THB_LAUNCHED();                                                                                \
+        return THB_OK;                                                                                 \
+    } while (0)
+    if (cpd == 3) THB_NET_BWD(3);
+    if (cpd == 4) THB_NET_BWD(4);
+#undef THB_NET_BWD
+    return thb_set_error(THB_E_UNSUPPORTED, "net backward: unsupported cp_dim");
+}
+
 template <int N0, int N1, int N2>
 int launch_nets(const thb_space_desc* sp, const NetArgs* na, int cpd, cudaStream_t st) {
 #define THB_NETS(CPD_, REL_)                                                                  \
@@ -590,6 +858,7 @@ struct ShapeOps {
     int (*fused)(const thb_space_desc*, const Args*, int ppt, int cpd, int der, cudaStream_t);
     int (*nets)(const thb_space_desc*, const NetArgs*, int cpd, cudaStream_t);
     int (*net_eval)(const thb_space_desc*, const Args*, const float* nets, int ppt, int cpd, int der, cudaStream_t);
+    int (*net_backward)(const thb_space_desc*, const Args*, const NetArgs*, float* grad_cp, int cpd, cudaStream_t);
     int (*basis)(const thb_space_desc*, const Args*, int ppt, int der, cudaStream_t);
     int (*backward)(const thb_space_desc*, const Args*, int cpd, cudaStream_t);
 };
@@ -597,7 +866,7 @@ struct ShapeOps {
 #define THB_DEFINE_SHAPE(A, B, C)                                                                                    \
     namespace thb_tile {                                                                                             \
     extern const ShapeOps shape_ops_##A##B##C = {A, B, C, &launch_fused<A, B, C>, &launch_nets<A, B, C>,              \
-                                                 &launch_net_eval<A, B, C>, &launch_basis<A, B, C>,                  \
+                                                 &launch_net_eval<A, B, C>, &launch_net_backward<A, B, C>, &launch_basis<A, B, C>, \
                                                  &launch_backward<A, B, C>};                                         \
     }
 

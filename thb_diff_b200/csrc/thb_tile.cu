@@ -150,7 +150,8 @@ extern "C" int thb_eval_nets(const thb_space_desc* space, const thb_plan_desc* p
 }
 
 extern "C" int thb_eval_fused_backward(const thb_space_desc* space, const thb_plan_desc* plan, const float* params,
-                                       const float* grad_out, int cp_dim, float* grad_ctrl_pts, int64_t nctrl, void* stream) {
+                                       const float* grad_out, int cp_dim, float* grad_ctrl_pts, int64_t nctrl, float* workspace,
+                                       void* stream) {
     int rc = thb_check_space(space, "thb_eval_fused_backward");
     if (rc) return rc;
     if ((rc = check_plan(plan, "thb_eval_fused_backward"))) return rc;
@@ -166,5 +167,12 @@ extern "C" int thb_eval_fused_backward(const thb_space_desc* space, const thb_pl
     ar.items = (const int4*)plan->items; ar.counters = plan->counters;
     ar.params = params; ar.sorted = plan->sorted_params; ar.grad_out = grad_out; ar.grad_cp = grad_ctrl_pts;
     THB_CUDA(cudaMemsetAsync(plan->counters + 1, 0, sizeof(int32_t), st));
+    if (workspace) {  // through the per-cell net gradients (thb_net_impl.cuh); workspace: thb_net_workspace_floats(space, 0)
+        THB_REQUIRE(plan->cell_count, "thb_eval_fused_backward: plan without cell_count");
+        THB_CUDA(cudaMemsetAsync(workspace, 0, sizeof(float) * (size_t)thb_net_workspace_floats(space, 0), st));
+        NetArgs na = {};
+        na.cell_count = plan->cell_count; na.nets = workspace; na.planes = 4;
+        return ops->net_backward(space, &ar, &na, grad_ctrl_pts, cp_dim, st);
+    }
     return ops->backward(space, &ar, cp_dim, st);
 }

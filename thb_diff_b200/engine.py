@@ -183,13 +183,25 @@ def eval_fused(P, plan, ctrl_pts, channels=(CH_VALUE,), cellnet=True, out=None, 
     return out
 
 
-def eval_fused_backward(P, plan, grad_out, cp_dim=None):
+def eval_fused_backward(P, plan, grad_out, cp_dim=None, formulation="local_net"):
+    """grad_ctrl_pts = A^T grad_out for the plan's points.  "local_net" (default): per-item reduction into per-cell net
+    gradients + one transposed fold per cell; "per_point": the per-item tile kernel."""
     require_cuda(grad_out, "grad_out", torch.float32)
     cpd = grad_out.shape[1]
+    if cpd not in (3, 4):
+        raise RuntimeError("fused backward supports control points of width 3 or 4")
+    if not P.has_tiles:
+        raise RuntimeError("the hierarchy has no coefficient tiles yet (PackedHierarchy.attach_tiles / from_space)")
     plan.refresh()
     g = torch.empty((P.nCP, cpd), dtype=torch.float32, device=P.device)
+    ws = None
+    if formulation == "local_net":
+        ws = getattr(P, "_gnet_ws", None)
+        n = lib.thb_net_workspace_floats(C.byref(P.desc()), 0)
+        if ws is None or ws.numel() != n:
+            ws = P._gnet_ws = torch.empty(n, dtype=torch.float32, device=P.device)
     check(lib.thb_eval_fused_backward(C.byref(P.desc()), C.byref(plan.desc), ptr(plan.params), ptr(grad_out), cpd, ptr(g), P.nCP,
-                                      stream_ptr(P.device)), "thb_eval_fused_backward")
+                                      ptr(ws) if ws is not None else None, stream_ptr(P.device)), "thb_eval_fused_backward")
     return g
 
 

@@ -103,7 +103,8 @@ class THBFusedEval(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_output):
         m = ctx.module
-        return engine.eval_fused_backward(m.P, m.plan, grad_output.contiguous()), None
+        return engine.eval_fused_backward(m.P, m.plan, grad_output.contiguous(),
+                                          formulation="local_net" if m.cellnet else "per_point"), None
 
 
 class THB_fused_module(torch.nn.Module):
