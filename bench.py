@@ -201,7 +201,9 @@ def extras(sp, P, params, cp, hbm_peak):
                 del o_ref, o_our
         del Jm
     tfb = time_cuda(lambda: engine.eval_fused_backward(P, supp.plan, g))
-    out["fused_backward"] = {"ms": tfb, "points_per_s": n / (tfb * 1e-3)}
+    tfb_pp = time_cuda(lambda: engine.eval_fused_backward(P, supp.plan, g, formulation="per_point"))
+    out["fused_backward"] = {"ms": tfb, "points_per_s": n / (tfb * 1e-3), "per_point_formulation_ms": tfb_pp,
+                             "what": "k_net_backward (per-item reduction into per-cell net gradients) + k_cell_unfold (transposed fold per cell)"}
     del PHI, g, supp
     torch.cuda.empty_cache()
 
