@@ -31,6 +31,23 @@ def allreduce_grad_(grad, group=None):
     return grad
 
 
+class _ScaledSumSquaredError(torch.autograd.Function):
+    """scale * sum((out - target)^2) in three passes over the data (difference, dot product, scaled difference as
+    the gradient) instead of the ~10 of the composed torch expression; the fit loop's loss is bandwidth-bound."""
+
+    @staticmethod
+    def forward(ctx, out, target, scale):
+        diff = out - target
+        ctx.save_for_backward(diff)
+        ctx.scale = scale
+        return torch.dot(diff.reshape(-1), diff.reshape(-1)) * scale
+
+    @staticmethod
+    def backward(ctx, g):
+        (diff,) = ctx.saved_tensors
+        return diff * (g * (2.0 * ctx.scale)), None, None
+
+
 class ShardedFit:
     """MSE fitting of the control points to targets at this rank's points.
 
@@ -51,7 +68,7 @@ class ShardedFit:
         out = self.module(ctrl_pts)
         # sum of squared errors over this shard, normalised by the GLOBAL point count, so that the
         # all-reduced gradient is the gradient of the global mean squared error
-        loss = ((out - self.targets) ** 2).sum() / (self.n_total * out.shape[1])
+        loss = _ScaledSumSquaredError.apply(out, self.targets, 1.0 / (self.n_total * out.shape[1]))
         loss.backward()
         allreduce_grad_(ctrl_pts.grad, self.group)
         optimizer.step()
