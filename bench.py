@@ -64,6 +64,27 @@ def flop_model_local_net(P, plan, cpd, n_in):
     return float(n_in * per_pt), float(fold)
 
 
+def bind_host_to_gpu(index):
+    """Pin this process to the CPUs NVML reports as local to GPU `index` (the e2e path moves 400 MB per step through
+    pinned host memory; with one rank per GPU the ranks otherwise share whatever NUMA node the launcher started them
+    on).  Returns the number of CPUs bound to, or None when NVML / affinity is not available."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1 and 64 * w + b < ncpu}
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if cpus and cpus != allowed:
+            os.sched_setaffinity(0, cpus)
+        return len(cpus) if cpus else None
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
@@ -341,6 +362,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    numa = bind_host_to_gpu(local)   # before any pinned allocation: host buffers land on the GPU's NUMA node
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
 
@@ -524,7 +546,7 @@ def main():
                 "how": f"engine.HostPipeline: {len(pipe.bounds)} chunks, H2D / compute / D2H overlapped on 3 streams, pinned host buffers, "
                        f"{'one CUDA graph replay per step' if pipe._graph is not None else 'eager launches'}",
                 "check_max_abs_diff_vs_device_path": e2e_diff,
-                "host_copies_alone": copies},
+                "host_copies_alone": copies, "host_cpus_bound_to_gpu_numa_node": numa},
         "roofline": roofline,
     }
 
