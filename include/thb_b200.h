@@ -180,7 +180,11 @@ THB_API int thb_eval_fused(const thb_space_desc* space, const thb_plan_desc* pla
  * long as ctrl_pts do not change) and a point costs Cox-de Boor plus one sum-factorised contraction with W.
  * nets: [nslots][planes][tile_stride] f32, planes = 4 (value channel only) or 8 (with_derivatives: planes 4..7 are W
  * built from control points relative to the cell's first support, used by the derivative channels).
- * thb_cell_nets: plan == NULL builds every active cell, otherwise only the cells that hold points of the plan. */
+ * thb_cell_nets: plan == NULL builds every active cell, otherwise only the cells that hold points of the plan.
+ * Together the two calls replace THB_basis_fns (THB/core.py:604-701) + prepare_data_for_CUDA_evaluation
+ * (THB/torch_funcs.py:50-80) + THBEval.forward / THB_eval.forward (THB/torch_funcs.py:22-33,
+ * THB_extensions/compute_pts_cuda_kernels.cu:3-26); thb_cell_nets alone takes the place of the dense coefficient tables
+ * of compute_refinement_operators (THB/core.py:43-114) on the evaluation side. */
 THB_API int64_t thb_net_workspace_floats(const thb_space_desc* space, int with_derivatives);
 THB_API int thb_cell_nets(const thb_space_desc* space, const thb_plan_desc* plan, const float* ctrl_pts, int cp_dim,
                   int with_derivatives, float* nets, void* stream);
