@@ -360,13 +360,23 @@ THB_DEV void net_points(const Args& ar, const Item& it, int base, NetSmem<SH, DE
     int idx[PPT];
     bool valid[PPT];
     BasesRK<SH, DER> bs[PPT];
+    // the cell's knots and reciprocal differences are warp-uniform: four LDS.128 per dimension instead of 2p + p(p+1)/2
+    // scalar loads per point
+    float K[3][8], RK[3][8];
+#pragma unroll
+    for (int dim = 0; dim < 3; ++dim) {
+        const float4 k0 = *reinterpret_cast<const float4*>(&sm.knots[tb][dim][0]), k1 = *reinterpret_cast<const float4*>(&sm.knots[tb][dim][4]);
+        const float4 r0 = *reinterpret_cast<const float4*>(&sm.rk[dim][0]), r1 = *reinterpret_cast<const float4*>(&sm.rk[dim][4]);
+        K[dim][0] = k0.x; K[dim][1] = k0.y; K[dim][2] = k0.z; K[dim][3] = k0.w; K[dim][4] = k1.x; K[dim][5] = k1.y; K[dim][6] = k1.z; K[dim][7] = k1.w;
+        RK[dim][0] = r0.x; RK[dim][1] = r0.y; RK[dim][2] = r0.z; RK[dim][3] = r0.w; RK[dim][4] = r1.x; RK[dim][5] = r1.y; RK[dim][6] = r1.z; RK[dim][7] = r1.w;
+    }
 #pragma unroll
     for (int q = 0; q < PPT; ++q) {
         valid[q] = base + q * 32 + lane < it.count;
         const float4 rec = sm.prec[pb][q * 32 + lane];
         idx[q] = __float_as_int(rec.w);
         const float u[3] = {rec.x, rec.y, rec.z};
-        bs[q].eval(u, sm.knots[tb], sm.rk);
+        bs[q].eval(u, K, RK);
     }
     for (int chi = 0; chi < ar.nch; ++chi) {
         const int ch = ar.channels[chi];
