@@ -160,7 +160,8 @@ THB_API int thb_basis_dense(const float* params, int64_t npoints, int ndim, cons
                     float* phi_out, void* stream);
 
 /* ---- fused basis + evaluation (PHI never leaves the SM) ----------------------------------------------------
- * out_host[c] is a device buffer [N, cp_dim] per channel.  Replaces THB_basis_fns followed by THBEval.forward
+ * out_host[c] is a device buffer [N, cp_dim] per channel; rows of points outside the domain (slot -1) are NOT written,
+ * pass zero-filled buffers if such points can occur.  Replaces THB_basis_fns followed by THBEval.forward
  * (THB/torch_funcs.py:22-33).  formulation selects how sum_s PHI_s(u) CP_s is evaluated (same result to rounding):
  *   THB_EVAL_LOCAL_NET (0, default)  thb_cell_nets for the cells that hold points of the plan + thb_eval_nets (below);
  *                                    needs `workspace` (thb_net_workspace_floats floats), NULL for the other two

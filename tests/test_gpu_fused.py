@@ -145,13 +145,16 @@ def test_host_pipeline_matches_device_path():
     P = PackedHierarchy.from_space(h, device="cuda")
     rng = np.random.default_rng(5)
     n = 300001
-    prm = torch.from_numpy(rng.random((n, 3)).astype(np.float32)).pin_memory()
+    prm_np = rng.random((n, 3)).astype(np.float32)
+    prm_np[7::1001] += 1.5                                   # a few points outside the domain: their rows must come back zero
+    prm = torch.from_numpy(prm_np).pin_memory()
     cp = torch.from_numpy(rng.standard_normal((P.nCP, 3)).astype(np.float32)).cuda()
     ref = engine.eval_fused(P, engine.Plan(P, prm.cuda()), cp)[0]
+    assert float(ref[7::1001].abs().max()) == 0.0
     out = torch.empty((n, 3), dtype=torch.float32).pin_memory()
     pipe = engine.HostPipeline(P, n, n_chunks=4)
     for _ in range(2):  # second run reuses plans and buffers
-        out.zero_()
+        out.fill_(123.0)
         pipe.run(prm, cp, out)
         torch.cuda.synchronize()
         # same points, possibly a different sub-batch path (summation order) than in the one-shot plan

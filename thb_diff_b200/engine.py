@@ -361,6 +361,7 @@ class HostPipeline:
                     pl = self.plans[b] = Plan(self.P, self.pbuf[b][:m])
                 else:
                     pl.build()
+                self.obuf[b][:m].zero_()  # rows of points outside the domain are not written by the kernels
                 if nets is not None:
                     eval_nets(self.P, pl, nets, self.cpd, out=[self.obuf[b][:m]], with_derivatives=False)
                 else:
