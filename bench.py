@@ -346,6 +346,7 @@ def main():
     ap.add_argument("--no-variants", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--e2e-chunks", type=int, default=8)
+    ap.add_argument("--e2e-ramp", type=int, default=0, help="number of doubling chunk sizes at each end of the e2e pipeline")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -429,7 +430,7 @@ def main():
     # ---- end to end through the public API with HOST buffers (pinned): H2D params, plan, fused eval, D2H geometry
     params_host = params.cpu().pin_memory()
     out_host = torch.empty((n, 3), dtype=torch.float32).pin_memory()
-    pipe = engine.HostPipeline(P, n, cp_dim=3, n_chunks=args.e2e_chunks, formulation=args.formulation)
+    pipe = engine.HostPipeline(P, n, cp_dim=3, n_chunks=args.e2e_chunks, formulation=args.formulation, ramp=args.e2e_ramp)
 
     def e2e_step():
         # public host-buffer API: chunked H2D -> plan + fused kernel -> D2H, overlapped on three streams

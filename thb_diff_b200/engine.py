@@ -37,20 +37,21 @@ def _as_params(params, ndim, device):
 class Plan:
     """The points of one batch grouped by active cell (device resident)."""
 
-    def __init__(self, P, params, points_per_item=POINTS_PER_ITEM):
+    def __init__(self, P, params, points_per_item=POINTS_PER_ITEM, capacity=None):
         self.P = P
         self.params = _as_params(params, P.ndim, P.device)
         n = self.params.shape[0]
         dev = P.device
         i32 = dict(dtype=torch.int32, device=dev)
         self.n = n
-        self.slot = torch.empty(max(n, 1), **i32)
-        self.scratch = torch.empty(max(n, 1), **i32)
-        self.sorted_params = torch.empty((max(n, 1), 4), dtype=torch.float32, device=dev)  # (u0, u1, u2|0, caller index bits)
+        self.capacity = cap = max(n, int(capacity or 0), 1)   # buffers hold up to `capacity` points (see rebind)
+        self.slot = torch.empty(cap, **i32)
+        self.scratch = torch.empty(cap, **i32)
+        self.sorted_params = torch.empty((cap, 4), dtype=torch.float32, device=dev)  # (u0, u1, u2|0, caller index bits)
         self.cell_count = torch.empty(P.nslots + 1, **i32)
         self.cell_start = torch.empty(P.nslots + 1, **i32)
         self.cell_cursor = torch.empty(P.nslots + 1, **i32)
-        self.max_items = n // points_per_item + P.nslots + 1
+        self.max_items = cap // points_per_item + P.nslots + 1
         self.items = torch.empty((self.max_items, 16), **i32)
         self.counters = torch.zeros(4, **i32)
         d = PlanDesc()
@@ -64,6 +65,16 @@ class Plan:
     def build(self):
         self.version = self.P.version
         check(lib.thb_plan_build(C.byref(self.P.desc()), ptr(self.params), C.byref(self.desc), stream_ptr(self.P.device)), "thb_plan_build")
+
+    def rebind(self, params):
+        """Plans another batch (at most `capacity` points) in the same buffers."""
+        params = _as_params(params, self.P.ndim, self.P.device)
+        if params.shape[0] > self.capacity:
+            raise RuntimeError("batch larger than the plan's capacity")
+        self.params, self.n = params, params.shape[0]
+        self.desc.npoints = self.n
+        self.build()
+        return self
 
     def refresh(self):
         """Work items embed per-cell table offsets: rebuild if the hierarchy's tables changed since build()."""
@@ -294,18 +305,21 @@ class HostPipeline:
     launch per step instead of a few hundred calls; a step with other buffers is captured again (eager fallback if
     capture is not possible)."""
 
-    def __init__(self, P, n_points, cp_dim=3, n_chunks=8, cellnet=True, formulation=None, use_graph=True):
+    def __init__(self, P, n_points, cp_dim=3, n_chunks=8, cellnet=True, formulation=None, use_graph=True, ramp=0):
         self.P, self.n, self.cpd = P, int(n_points), cp_dim
         self.use_graph, self._graph, self._graph_key = bool(use_graph), None, None
         self.formulation = formulation if formulation is not None else ("local_net" if cellnet else "per_point")
         n_chunks = max(1, min(n_chunks, (self.n + 65535) // 65536))
-        base, rem = divmod(self.n, n_chunks)
-        self.bounds = []
-        lo = 0
-        for c in range(n_chunks):
-            hi = lo + base + (1 if c < rem else 0)
-            self.bounds.append((lo, hi))
-            lo = hi
+        # chunk sizes ramp up (1, 2, 4, ...) at the start and down at the end: the pipeline's fill time is the H2D copy of
+        # the FIRST chunk and its drain time the D2H copy of the LAST one, so those two are kept small
+        r = min(ramp, max(0, (n_chunks - 1) // 2))
+        w = [1 << i for i in range(r)] + [1 << r] * (n_chunks - 2 * r) + [1 << i for i in reversed(range(r))]
+        edges = [0]
+        acc = 0
+        for x in w:
+            acc += x
+            edges.append((self.n * acc) // sum(w))
+        self.bounds = [(edges[i], edges[i + 1]) for i in range(n_chunks) if edges[i + 1] > edges[i]]
         m = max(hi - lo for lo, hi in self.bounds)
         dev = P.device
         self.pbuf = [torch.empty((m, P.ndim), dtype=torch.float32, device=dev) for _ in range(2)]
@@ -357,10 +371,10 @@ class HostPipeline:
                 if c >= 2:
                     self.s_cmp.wait_event(outd[c - 2])  # the D2H copy that read this output buffer has finished
                 pl = self.plans[b]
-                if pl is None or pl.n != m:
-                    pl = self.plans[b] = Plan(self.P, self.pbuf[b][:m])
+                if pl is None:
+                    pl = self.plans[b] = Plan(self.P, self.pbuf[b][:m], capacity=self.pbuf[b].shape[0])
                 else:
-                    pl.build()
+                    pl.rebind(self.pbuf[b][:m])
                 self.obuf[b][:m].zero_()  # rows of points outside the domain are not written by the kernels
                 if nets is not None:
                     eval_nets(self.P, pl, nets, self.cpd, out=[self.obuf[b][:m]], with_derivatives=False)
