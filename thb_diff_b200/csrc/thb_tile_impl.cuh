@@ -1,21 +1,24 @@
-// Tile kernels: the hot path of THB_basis_fns (THB/core.py:604-701; float64 statement core.py:232-268)
-// fused with THBEval.forward / backward (THB/torch_funcs.py:22-47).
+// Tile kernels: THB_basis_fns with PHI materialised (THB/core.py:604-701; float64 statement core.py:232-268) and the
+// per-point formulations of the fused THB_basis_fns + THBEval.forward / backward (THB/torch_funcs.py:22-47).  The
+// default fused evaluation (local control nets) is in thb_net_impl.cuh and reuses the pieces defined here.
 //
-// Work decomposition (see DESIGN.md):
+// Work decomposition (see DESIGN.md 3.2):
 //   * the points of a batch are grouped by active cell (thb_plan_build); a work item = one cell and up to
-//     points_per_item of its points; persistent CTAs of 128 threads pull items from an atomic cursor
-//   * per item the CTA stages in shared memory: the 2p local knots per dimension, the control points of the
-//     cell's own-level window (SoA, zero where inactive) and -- in chunks of kChunk supports -- the
-//     (p+1)^d coefficient tiles of the coarser-level supports plus their control points
-//   * each thread owns PPT points: register-resident Cox-de Boor (values + first derivatives), the
+//     points_per_item of its points; persistent one-warp CTAs pull 64-byte item records from an atomic cursor
+//   * per item the warp stages in shared memory (cp.async, double buffered): the 2p local knots per dimension, the
+//     control points of the cell's own-level window (SoA, zero where inactive), the factor vectors of the rank-one
+//     coarser-level supports and -- in chunks of kWChunk supports -- the (p+1)^d coefficient tiles of the others, plus
+//     the supports' control points
+//   * each lane owns PPT points: register-resident Cox-de Boor (values + first derivatives), the
 //     (p+1)^d tensor product kept as packed f32x2 register pairs, then
 //       PHI_s = <tile_s, tp>  with broadcast LDS.128 of the tile and FFMA2          (gather-multiply)
 //       out  += PHI_s * ctrl_pts[Jm_s]                                              (contraction)
 //     own-level supports have one-hot tiles: their PHI is tp[t] itself, so their contraction is three
 //     dot products of tp with the staged window control points.
 //   * MODE_BASIS writes PHI (THB_basis_fns); MODE_FUSED writes only the evaluated geometry.
-//   * cellnet: tiles are first folded into the window control points (a per-cell local control net
-//     Q[t] = CPwin[t] + sum_s tile_s[t] * CP_s), after which every point costs 3*(p+1)^d FMAs.
+//   * cellnet (formulation tile_net): tiles are first folded into the window control points (a per-item local control
+//     net Q[t] = CPwin[t] + sum_s tile_s[t] * CP_s), after which every point costs 3*(p+1)^d FMAs.
+//   * k_tile_backward (CTAs of 128 threads): the per-point formulation of the fused backward.
 #pragma once
 #include "thb_common.cuh"
 
