@@ -76,6 +76,9 @@ typedef struct thb_space_desc {
     int32_t pad_;
     const int32_t* finest_slot;             /* optional (may be NULL): per FINEST-level cell the slot of the active cell
                                                that contains it (-1 if none) -- one lookup instead of one per level */
+    const int32_t* tiled_ref;               /* optional (NULL without the split tables): for tiled support j of the global
+                                               tile order (tile_off + position in the cell's reference-ordered list):
+                                               (row of sep_vec << 1) or (row of full_tiles << 1) | 1 */
 } thb_space_desc;
 
 /* A plan = the points of one batch grouped by active cell. All arrays are caller-allocated device memory:

@@ -861,6 +861,220 @@ int launch_net_eval(const thb_space_desc* sp, const Args* ar, const float* nets,
     return thb_set_error(THB_E_UNSUPPORTED, "net evaluation: unsupported variant");
 }
 
+// ---- THB_basis_fns with PHI materialised, factor form -------------------------------------------------------------
+// PHI rows in the reference's pair order (THB/core.py:604-701): own-level supports first, then the coarser ones.
+//   phase 1 (lane = point): Cox-de Boor; the 1-D values (and derivatives) go to shared memory, the row offset too
+//   own-level supports (lane = window entry t): PHI = A[a_t] * B[b_t] * C[c_t] per point, written straight to the row --
+//       a coalesced store per point, no (p+1)^d register array and no transpose
+//   coarser supports, 32 at a time in reference order (lane = point): rank-one ones as <v0,A><v1,B><v2,C> (14 instead of
+//       2*(p+1)^d FMAs), the others by a sum-factorised dot with their tile; staged [point][support] and written as
+//       row pieces (lane = support).  tiled_ref says for every tiled support which of the two tables holds it.
+struct BasisSmem {
+    int4 rec[3][4];
+    float knots[2][3][8];
+    float rk[3][8];
+    float4 prec[2][32];
+    float4 fac[6][32];        // [2 * dim + derivative][point] -> the (up to) four 1-D values of that point
+    long long poff[32];       // row offset of the point in PHI
+    float stage[32][33];      // [point][support of the chunk]
+    float4 vec[32][3];        // factor vectors of the chunk's rank-one supports (lane = support on the way in)
+    float tile[64];           // one full tile at a time
+    int ref[32];              // tiled_ref of the chunk
+};
+
+template <int N0, int N1, int N2, bool DER>
+__global__ void __launch_bounds__(kThreads, 16) k_basis_rows(const __grid_constant__ thb_space_desc sp, const __grid_constant__ Args ar) {
+    using SH = Shp<N0, N1, N2>;
+    constexpr int T = SH::T, TS = SH::TS;
+    constexpr int NT = (T + 31) / 32;
+    __shared__ __align__(16) BasisSmem sm;
+    const int lane = threadIdx.x;
+    const int nitems = ar.counters[0];
+    int32_t* const cursor = ar.counters + 1;
+    const int d = sp.ndim;
+
+    int c3 = 0;
+    if (lane == 0) c3 = atomicAdd(cursor, 3);
+    const int id0 = __shfl_sync(0xffffffffu, c3, 0);
+    if (id0 >= nitems) return;
+    int id1 = id0 + 1, id2 = id0 + 2;
+    Item it = load_item(sp, ar.items, id0);
+    if (lane < 4 && id1 < nitems) cp_async16(&sm.rec[1][lane], ar.items + (int64_t)id1 * 4 + lane);
+    if (lane < 4 && id2 < nitems) cp_async16(&sm.rec[2][lane], ar.items + (int64_t)id2 * 4 + lane);
+    auto prefetch_knots = [&](const Item& x, float (*knots)[8]) {
+        if (lane < 24) {
+            const int dim = lane >> 3, m = lane & 7;
+            const int P = dim == 0 ? SH::P0 : (dim == 1 ? SH::P1 : SH::P2);
+            const int c = dim == 0 ? x.c0 : (dim == 1 ? x.c1 : x.c2);
+            if (dim < d && m < 2 * P) cp_async4(&knots[dim][m], sp.knots + sp.knot_off[x.lev][dim] + c + 1 + m);
+        }
+    };
+    prefetch_knots(it, sm.knots[0]);
+    prefetch_points<1>(ar, it.begin, it.count, 0, sm.prec[0]);
+    cp_async_commit();
+    int nn_id = 0;
+    if (lane == 0) nn_id = atomicAdd(cursor, 1);
+    int ring = 0, tb = 0, pb = 0;
+    cp_async_wait<0>();
+    __syncwarp();
+
+    // this lane's window entries (own-level part): t = lane + 32 h -> (a, b, c) and its place among the active ones
+    int ta[NT], tb_[NT], tc[NT];
+#pragma unroll
+    for (int h = 0; h < NT; ++h) {
+        const int t = min(lane + 32 * h, T - 1);
+        ta[h] = t / (N1 * N2); tb_[h] = (t / N2) % N1; tc[h] = t % N2;
+    }
+
+    for (;;) {
+        if (lane < 24) {
+            const int dim = lane >> 3, m = lane & 7;
+            const int P = dim == 0 ? SH::P0 : (dim == 1 ? SH::P1 : SH::P2);
+            if (dim < d && m < P * (P + 1) / 2) {
+                int j = 1, r = m;
+                while (r >= j) { r -= j; ++j; }
+                sm.rk[dim][m] = 1.0f / (sm.knots[tb][dim][P + r] - sm.knots[tb][dim][P - j + r]);
+            }
+        }
+        __syncwarp();
+        const int ntile = it.S - it.ndir;
+        int dpos[NT];
+#pragma unroll
+        for (int h = 0; h < NT; ++h) {
+            const int t = lane + 32 * h;
+            dpos[h] = (it.ndir > 0 && t < T && ((it.dm >> t) & 1ull)) ? __popcll(it.dm & ((1ull << t) - 1ull)) : -1;
+        }
+        const bool nx_valid = id1 < nitems;
+        for (int base = 0; base < it.count; base += 32) {
+            if (base + 32 < it.count) {
+                prefetch_points<1>(ar, it.begin, it.count, base + 32, sm.prec[pb ^ 1]);
+            } else if (nx_valid) {
+                const int4* r = sm.rec[(ring + 1) % 3];
+                const Item nx = unpack_item(r[0], r[1], r[2], r[3]);
+                prefetch_points<1>(ar, nx.begin, nx.count, 0, sm.prec[pb ^ 1]);
+                prefetch_knots(nx, sm.knots[tb ^ 1]);
+            }
+            cp_async_commit();
+            const int nval = min(32, it.count - base);
+            // phase 1: lane = point
+            BasesRK<SH, DER> bs;
+            {
+                const float4 rec = sm.prec[pb][lane];
+                const float u[3] = {rec.x, rec.y, rec.z};
+                bs.eval(u, sm.knots[tb], sm.rk);
+                sm.poff[lane] = lane < nval ? (long long)__ldg(ar.offsets + __float_as_int(rec.w)) : 0;
+                float v[6][4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    v[0][i] = i < N0 ? bs.n0[i] : 0.f; v[2][i] = i < N1 ? bs.n1[i] : 0.f; v[4][i] = i < N2 ? bs.n2[i] : 0.f;
+                    v[1][i] = (DER && i < N0) ? bs.d0[i] : 0.f; v[3][i] = (DER && i < N1) ? bs.d1[i] : 0.f; v[5][i] = (DER && i < N2) ? bs.d2[i] : 0.f;
+                }
+#pragma unroll
+                for (int q = 0; q < 6; ++q)
+                    if (DER || (q & 1) == 0) sm.fac[q][lane] = make_float4(v[q][0], v[q][1], v[q][2], v[q][3]);
+            }
+            __syncwarp();
+            for (int chi = 0; chi < ar.nch; ++chi) {
+                const int ch = ar.channels[chi];
+                float* const outp = ar.out[chi];
+                const int q0 = (DER && (ch & 1)) ? 1 : 0, q1 = (DER && (ch & 2)) ? 3 : 2, q2 = (DER && (ch & 4)) ? 5 : 4;
+                if (it.ndir > 0) {
+                    // own-level supports: lane = window entry
+                    const float* fa = reinterpret_cast<const float*>(sm.fac[q0]);
+                    const float* fb = reinterpret_cast<const float*>(sm.fac[q1]);
+                    const float* fc = reinterpret_cast<const float*>(sm.fac[q2]);
+#pragma unroll 4
+                    for (int pt = 0; pt < nval; ++pt) {
+                        float* dst = outp + sm.poff[pt];
+#pragma unroll
+                        for (int h = 0; h < NT; ++h) {
+                            const float val = fa[pt * 4 + ta[h]] * fb[pt * 4 + tb_[h]] * fc[pt * 4 + tc[h]];
+                            if (dpos[h] >= 0) dst[dpos[h]] = val;
+                        }
+                    }
+                }
+                // coarser-level supports, 32 at a time: lane = point computes, lane = support writes
+                float A[N0], B[N1], Cc[N2];
+                bs.select(ch, A, B, Cc);
+                for (int c0 = 0; c0 < ntile; c0 += 32) {
+                    const int ns = min(32, ntile - c0);
+                    __syncwarp();
+                    if (lane < ns) {
+                        int r = sp.tiled_ref ? __ldg(sp.tiled_ref + it.toff + c0 + lane) : (((it.toff + c0 + lane) << 1) | 1);
+                        sm.ref[lane] = r;
+                        if (!(r & 1)) {
+                            const float4* fv = reinterpret_cast<const float4*>(sp.sep_vec + (int64_t)(r >> 1) * 12);
+                            sm.vec[lane][0] = __ldg(fv); sm.vec[lane][1] = __ldg(fv + 1); sm.vec[lane][2] = __ldg(fv + 2);
+                        }
+                    }
+                    __syncwarp();
+                    for (int j = 0; j < ns; ++j) {
+                        const int r = sm.ref[j];
+                        float e;
+                        if (!(r & 1)) {
+                            const float4 v0 = sm.vec[j][0], v1 = sm.vec[j][1], v2 = sm.vec[j][2];
+                            float e0 = 0.f, e1 = 0.f, e2 = 0.f;
+#pragma unroll
+                            for (int i = 0; i < N0; ++i) e0 = fmaf(f4c(v0, i), A[i], e0);
+#pragma unroll
+                            for (int i = 0; i < N1; ++i) e1 = fmaf(f4c(v1, i), B[i], e1);
+#pragma unroll
+                            for (int i = 0; i < N2; ++i) e2 = fmaf(f4c(v2, i), Cc[i], e2);
+                            e = e0 * e1 * e2;
+                        } else {
+                            const float* row = (sp.tiled_ref ? sp.full_tiles : sp.tiles) + (int64_t)(r >> 1) * TS;
+                            __syncwarp();
+                            for (int t = lane; t < TS; t += 32) sm.tile[t] = __ldg(row + t);
+                            __syncwarp();
+                            e = 0.f;
+#pragma unroll
+                            for (int i = 0; i < N0; ++i) {
+                                float ei = 0.f;
+#pragma unroll
+                                for (int k = 0; k < N1; ++k) {
+                                    float ek = 0.f;
+#pragma unroll
+                                    for (int m = 0; m < N2; ++m) ek = fmaf(Cc[m], sm.tile[(i * N1 + k) * N2 + m], ek);
+                                    ei = fmaf(B[k], ek, ei);
+                                }
+                                e = fmaf(A[i], ei, e);
+                            }
+                        }
+                        sm.stage[lane][j] = e;
+                    }
+                    __syncwarp();
+                    if (lane < ns) {
+#pragma unroll 4
+                        for (int pt = 0; pt < nval; ++pt) outp[sm.poff[pt] + it.ndir + c0 + lane] = sm.stage[pt][lane];
+                    }
+                }
+            }
+            cp_async_wait<0>();
+            __syncwarp();
+            pb ^= 1;
+        }
+        if (!nx_valid) break;
+        ring = (ring + 1) % 3;
+        {
+            const int4* r = sm.rec[ring];
+            it = unpack_item(r[0], r[1], r[2], r[3]);
+        }
+        tb ^= 1;
+        const int id3 = __shfl_sync(0xffffffffu, nn_id, 0);
+        id1 = id2;
+        id2 = id3;
+        if (lane < 4 && id3 < nitems) cp_async16(&sm.rec[(ring + 2) % 3][lane], ar.items + (int64_t)id3 * 4 + lane);
+        cp_async_commit();
+        if (lane == 0) nn_id = atomicAdd(cursor, 1);
+    }
+}
+
+template <int N0, int N1, int N2>
+int launch_basis_rows(const thb_space_desc* sp, const Args* ar, int der, cudaStream_t st) {
+    if (!der) THB_TILE_LAUNCH((k_basis_rows<N0, N1, N2, false>));
+    THB_TILE_LAUNCH((k_basis_rows<N0, N1, N2, true>));
+}
+
 // ---- per-shape launch table (one translation unit per tensor-product shape, see thb_tile_inst_*.cu) ---------------
 struct ShapeOps {
     int n0, n1, n2;
@@ -870,6 +1084,7 @@ struct ShapeOps {
     int (*net_eval)(const thb_space_desc*, const Args*, const float* nets, int ppt, int cpd, int der, cudaStream_t);
     int (*net_backward)(const thb_space_desc*, const Args*, const NetArgs*, float* grad_cp, int cpd, cudaStream_t);
     int (*basis)(const thb_space_desc*, const Args*, int ppt, int der, cudaStream_t);
+    int (*basis_rows)(const thb_space_desc*, const Args*, int der, cudaStream_t);
     int (*backward)(const thb_space_desc*, const Args*, int cpd, cudaStream_t);
 };
 
@@ -877,6 +1092,7 @@ struct ShapeOps {
     namespace thb_tile {                                                                                             \
     extern const ShapeOps shape_ops_##A##B##C = {A, B, C, &launch_fused<A, B, C>, &launch_nets<A, B, C>,              \
                                                  &launch_net_eval<A, B, C>, &launch_net_backward<A, B, C>, &launch_basis<A, B, C>, \
+                                                 &launch_basis_rows<A, B, C>,                                          \
                                                  &launch_backward<A, B, C>};                                         \
     }
 

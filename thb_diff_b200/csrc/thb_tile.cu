@@ -72,6 +72,7 @@ extern "C" int thb_basis_tiled(const thb_space_desc* space, const thb_plan_desc*
     ar.params = params; ar.sorted = plan->sorted_params; ar.offsets = offsets;
     cudaStream_t st = (cudaStream_t)stream;
     THB_CUDA(cudaMemsetAsync(plan->counters + 1, 0, sizeof(int32_t), st));
+    if (!env_int("THB_BASIS_TILE_KERNEL", 0)) return ops->basis_rows(space, &ar, der ? 1 : 0, st);  // factor-form rows
     return ops->basis(space, &ar, env_int("THB_BASIS_PPT", 1), der ? 1 : 0, st);
 }
 

@@ -340,6 +340,9 @@ class PackedHierarchy:
         self.sep_vec = torch.from_numpy(np.ascontiguousarray(sepvec[sepflag])).to(dev) if sepflag.any() else torch.zeros((1, 12), dtype=torch.float32, device=dev)
         self.sep_jm = torch.from_numpy(np.ascontiguousarray(jm_tiled[sepflag]).astype(np.int32)).to(dev) if sepflag.any() else torch.zeros(1, dtype=torch.int32, device=dev)
         full = ~sepflag
+        # where each tiled support (global tile order = reference order inside every cell) lives after the split
+        ref = np.where(sepflag, (np.cumsum(sepflag) - 1) << 1, ((np.cumsum(full) - 1) << 1) | 1).astype(np.int32)
+        self.tiled_ref = torch.from_numpy(ref).to(dev) if len(ref) else torch.zeros(1, dtype=torch.int32, device=dev)
         self.full_tiles = self.tiles[torch.from_numpy(np.nonzero(full)[0]).to(dev)].contiguous() if full.any() else torch.zeros((1, self.TS), dtype=torch.float32, device=dev)
         self.full_jm = torch.from_numpy(np.ascontiguousarray(jm_tiled[full]).astype(np.int32)).to(dev) if full.any() else torch.zeros(1, dtype=torch.int32, device=dev)
         self.cellinfo = torch.from_numpy(info).to(dev)
@@ -462,6 +465,7 @@ def _desc(self):
     if getattr(self, "sep_vec", None) is not None:
         d.sep_vec, d.sep_jm = self.sep_vec.data_ptr(), self.sep_jm.data_ptr()
         d.full_tiles, d.full_jm = self.full_tiles.data_ptr(), self.full_jm.data_ptr()
+    d.tiled_ref = self.tiled_ref.data_ptr() if getattr(self, "tiled_ref", None) is not None and getattr(self, "sep_vec", None) is not None else None
     d.span_lut = self.span_lut.data_ptr() if self.span_lut is not None else None
     if self.span_lut is not None:
         for k in range(self.ndim):
