@@ -887,6 +887,7 @@ __global__ void __launch_bounds__(kThreads, 16) k_basis_rows(const __grid_consta
     using SH = Shp<N0, N1, N2>;
     constexpr int T = SH::T, TS = SH::TS;
     constexpr int NT = (T + 31) / 32;
+    constexpr bool kPairA = NT == 2 && N0 == 4 && (N1 * N2) == 16;  // t and t + 32 = entries (a, b, c) and (a + 2, b, c)
     __shared__ __align__(16) BasisSmem sm;
     const int lane = threadIdx.x;
     const int nitems = ar.counters[0];
@@ -970,8 +971,12 @@ __global__ void __launch_bounds__(kThreads, 16) k_basis_rows(const __grid_consta
                     v[1][i] = (DER && i < N0) ? bs.d0[i] : 0.f; v[3][i] = (DER && i < N1) ? bs.d1[i] : 0.f; v[5][i] = (DER && i < N2) ? bs.d2[i] : 0.f;
                 }
 #pragma unroll
-                for (int q = 0; q < 6; ++q)
-                    if (DER || (q & 1) == 0) sm.fac[q][lane] = make_float4(v[q][0], v[q][1], v[q][2], v[q][3]);
+                for (int q = 0; q < 6; ++q) {
+                    if (!DER && (q & 1)) continue;
+                    // first dimension stored as (v0, v2, v1, v3) when a lane owns the entries a and a + 2: one LDS.64
+                    if (kPairA && q < 2) sm.fac[q][lane] = make_float4(v[q][0], v[q][2], v[q][1], v[q][3]);
+                    else sm.fac[q][lane] = make_float4(v[q][0], v[q][1], v[q][2], v[q][3]);
+                }
             }
             __syncwarp();
             for (int chi = 0; chi < ar.nch; ++chi) {
@@ -983,13 +988,27 @@ __global__ void __launch_bounds__(kThreads, 16) k_basis_rows(const __grid_consta
                     const float* fa = reinterpret_cast<const float*>(sm.fac[q0]);
                     const float* fb = reinterpret_cast<const float*>(sm.fac[q1]);
                     const float* fc = reinterpret_cast<const float*>(sm.fac[q2]);
+                    if constexpr (kPairA) {
+                        const float2* fa2 = reinterpret_cast<const float2*>(sm.fac[q0]) + ta[0];  // (A[a], A[a + 2]) of point 0
+                        const float* fbp = fb + tb_[0];
+                        const float* fcp = fc + tc[0];
 #pragma unroll 4
-                    for (int pt = 0; pt < nval; ++pt) {
-                        float* dst = outp + sm.poff[pt];
+                        for (int pt = 0; pt < nval; ++pt) {
+                            float* dst = outp + sm.poff[pt];
+                            const float2 aa = fa2[pt * 2];
+                            const float bc = fbp[pt * 4] * fcp[pt * 4];
+                            if (dpos[0] >= 0) dst[dpos[0]] = aa.x * bc;
+                            if (dpos[1] >= 0) dst[dpos[1]] = aa.y * bc;
+                        }
+                    } else {
+#pragma unroll 4
+                        for (int pt = 0; pt < nval; ++pt) {
+                            float* dst = outp + sm.poff[pt];
 #pragma unroll
-                        for (int h = 0; h < NT; ++h) {
-                            const float val = fa[pt * 4 + ta[h]] * fb[pt * 4 + tb_[h]] * fc[pt * 4 + tc[h]];
-                            if (dpos[h] >= 0) dst[dpos[h]] = val;
+                            for (int h = 0; h < NT; ++h) {
+                                const float val = fa[pt * 4 + ta[h]] * fb[pt * 4 + tb_[h]] * fc[pt * 4 + tc[h]];
+                                if (dpos[h] >= 0) dst[dpos[h]] = val;
+                            }
                         }
                     }
                 }
