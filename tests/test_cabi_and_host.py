@@ -24,13 +24,27 @@ def test_library_exports_every_declared_symbol():
     assert _lib.launch_count() == 0  # nothing was launched by loading
 
 
-def test_descriptor_layout_matches_header():
+def test_descriptor_layout_matches_header(tmp_path):
+    """sizeof / offsetof of every field as the C compiler sees include/thb_b200.h == the ctypes mirror."""
+    import subprocess
+
     from thb_diff_b200 import _lib
 
-    # thb_space_desc: 8 ints, 4 x [8][3] ints, 9 + 8 int64, 12 pointers, span-LUT block of 10 x 4 bytes
-    assert ctypes.sizeof(_lib.SpaceDesc) == 8 * 4 + 4 * 8 * 3 * 4 + (9 + 8) * 8 + 12 * 8 + 10 * 4
-    assert _lib.SpaceDesc.knots.offset == 8 * 4 + 4 * 96 + 17 * 8
-    assert ctypes.sizeof(_lib.PlanDesc) == 8 + 4 + 4 + 8 * 8
+    structs = {"thb_space_desc": _lib.SpaceDesc, "thb_plan_desc": _lib.PlanDesc}
+    lines = []
+    for cname, cls in structs.items():
+        lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stddef.h>\n#include <stdio.h>\n#include "thb_b200.h"\nint main(void) {\n' + "\n".join(lines) + "\nreturn 0; }\n")
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, cls in structs.items():
+        assert int(got[cname]) == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, f"{cname}.{fname}"
 
 
 def test_no_cpu_fallback():
