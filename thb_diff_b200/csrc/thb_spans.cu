@@ -453,7 +453,10 @@ __global__ void __launch_bounds__(256) k_plan_items(const __grid_constant__ thb_
 // STG.128 per point here, one 16-byte cp.async per point in the evaluation kernels.  Lanes of one warp that share a
 // slot take consecutive places, which keeps runs of neighbouring points contiguous.  The cursor of a cell starts at
 // the cell's first place (k_plan_items), so one atomic returns the destination.
-constexpr int kScatterPts = 2;
+#ifndef THB_SCATTER_PTS
+#define THB_SCATTER_PTS 2
+#endif
+constexpr int kScatterPts = THB_SCATTER_PTS;
 __global__ void __launch_bounds__(256) k_plan_scatter(const int32_t* __restrict__ slot, const float* __restrict__ params, int ndim,
                                                       int64_t n, int32_t* __restrict__ cursor, float4* __restrict__ sorted) {
     constexpr int H = kScatterPts;
