@@ -239,6 +239,11 @@ __global__ void __launch_bounds__(256) k_plan_count(const __grid_constant__ thb_
 // not resolve) is appended to `fail_list` and handled by k_plan_fixup with the robust search.
 constexpr int kPlanSmemLut = 3 * 1024;  // span lookup tables staged in shared memory when they fit (else read through L1)
 
+#ifndef THB_COUNT_PTS
+#define THB_COUNT_PTS 2
+#endif
+constexpr int kCountPts = THB_COUNT_PTS;  // points per thread and iteration of the count pass
+
 template <int D, bool SLUT>
 __global__ void __launch_bounds__(256) k_plan_count_fast(const __grid_constant__ thb_space_desc sp, const float* __restrict__ params,
                                                          unsigned n, int32_t* __restrict__ slot_out, int32_t* __restrict__ count,
@@ -270,19 +275,19 @@ __global__ void __launch_bounds__(256) k_plan_count_fast(const __grid_constant__
     const int32_t* __restrict__ glut = sp.span_lut;
     const unsigned lane = threadIdx.x & 31;
     const unsigned stride = gridDim.x * blockDim.x;
-    const unsigned nround = (n + 2 * stride - 1) / (2 * stride) * (2 * stride);  // n < 2^31 and stride < 2^20: no overflow
-    for (unsigned i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < nround; i0 += 2 * stride) {
-        float u[2][D];
-        int slot[2];
+    const unsigned nround = (n + kCountPts * stride - 1) / (kCountPts * stride) * (kCountPts * stride);  // n < 2^31 and stride < 2^20: no overflow
+    for (unsigned i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < nround; i0 += kCountPts * stride) {
+        float u[kCountPts][D];
+        int slot[kCountPts];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < kCountPts; ++h) {
             const unsigned i = i0 + h * stride;
             const float* src = params + (size_t)(i < n ? i : 0u) * D;
 #pragma unroll
             for (int k = 0; k < D; ++k) u[h][k] = src[k];
         }
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < kCountPts; ++h) {
             const unsigned i = i0 + h * stride;
             bool ok = true, inside = true;
             int c[D];
@@ -319,7 +324,7 @@ __global__ void __launch_bounds__(256) k_plan_count_fast(const __grid_constant__
             slot[h] = sl;
         }
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < kCountPts; ++h) {
             const unsigned peers = __match_any_sync(0xffffffffu, slot[h]);
             if (slot[h] >= 0 && lane == (unsigned)(__ffs(peers) - 1)) atomicAdd(count + slot[h], __popc(peers));
         }
