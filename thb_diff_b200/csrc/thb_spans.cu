@@ -423,6 +423,110 @@ __global__ void __launch_bounds__(1024) k_plan_scan(const int32_t* __restrict__ 
     }
 }
 
+// pass 2, two-kernel form for larger hierarchies: every CTA owns 4096 consecutive slots (int4 per thread, coalesced).
+// k_plan_scan_sums writes the per-CTA totals, k_plan_scan_write adds the totals of the CTAs before it (every CTA sums
+// them itself: a few hundred values at most) to its local scan.  Two short launches instead of one CTA walking all slots.
+constexpr int kScanTile = 4096;
+
+THB_DEV void scan_tile_load(const int32_t* __restrict__ count, int nslots, int i0, int ppi, int sh, int (&c)[4], int (&m)[4]) {
+    int4 v = make_int4(0, 0, 0, 0);
+    if (i0 + 3 < nslots) {
+        v = *reinterpret_cast<const int4*>(count + i0);
+    } else {
+        if (i0 < nslots) v.x = count[i0];
+        if (i0 + 1 < nslots) v.y = count[i0 + 1];
+        if (i0 + 2 < nslots) v.z = count[i0 + 2];
+    }
+    c[0] = v.x; c[1] = v.y; c[2] = v.z; c[3] = v.w;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) m[k] = sh >= 0 ? (c[k] + ppi - 1) >> sh : (c[k] + ppi - 1) / ppi;
+}
+
+// block-wide inclusive scan of one (points, items) pair per thread; returns the block totals in (tot_p, tot_i)
+THB_DEV void scan_block(int& sp_, int& si_, int& tot_p, int& tot_i, int* s_wp, int* s_wi) {
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int a = __shfl_up_sync(0xffffffffu, sp_, o), b2 = __shfl_up_sync(0xffffffffu, si_, o);
+        if (lane >= o) { sp_ += a; si_ += b2; }
+    }
+    if (lane == 31) { s_wp[w] = sp_; s_wi[w] = si_; }
+    __syncthreads();
+    if (w == 0) {
+        int a = s_wp[lane], b2 = s_wi[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int x = __shfl_up_sync(0xffffffffu, a, o), y = __shfl_up_sync(0xffffffffu, b2, o);
+            if (lane >= o) { a += x; b2 += y; }
+        }
+        s_wp[lane] = a;
+        s_wi[lane] = b2;
+    }
+    __syncthreads();
+    sp_ += w ? s_wp[w - 1] : 0;
+    si_ += w ? s_wi[w - 1] : 0;
+    tot_p = s_wp[31];
+    tot_i = s_wi[31];
+}
+
+__global__ void __launch_bounds__(1024) k_plan_scan_sums(const int32_t* __restrict__ count, int nslots, int ppi,
+                                                         int32_t* __restrict__ sums) {
+    __shared__ int s_wp[32], s_wi[32];
+    const int sh = (ppi & (ppi - 1)) == 0 ? 31 - __clz(ppi) : -1;
+    int c[4], m[4];
+    scan_tile_load(count, nslots, blockIdx.x * kScanTile + 4 * threadIdx.x, ppi, sh, c, m);
+    int sp_ = c[0] + c[1] + c[2] + c[3], si_ = m[0] + m[1] + m[2] + m[3], tp, ti;
+    scan_block(sp_, si_, tp, ti, s_wp, s_wi);
+    if (threadIdx.x == 0) { sums[2 * blockIdx.x] = tp; sums[2 * blockIdx.x + 1] = ti; }
+}
+
+__global__ void __launch_bounds__(1024) k_plan_scan_write(const int32_t* __restrict__ count, int32_t* __restrict__ start,
+                                                          int32_t* __restrict__ item_start, int nslots, int ppi,
+                                                          const int32_t* __restrict__ sums, int32_t* __restrict__ counters) {
+    __shared__ int s_wp[32], s_wi[32], s_base[2];
+    const int t = threadIdx.x;
+    const int sh = (ppi & (ppi - 1)) == 0 ? 31 - __clz(ppi) : -1;
+    // totals of the tiles before this one
+    int bp = 0, bi = 0;
+    for (int j = t; j < (int)blockIdx.x; j += 1024) { bp += sums[2 * j]; bi += sums[2 * j + 1]; }
+    {
+        int dp, di;
+        scan_block(bp, bi, dp, di, s_wp, s_wi);   // only the totals are used
+        if (t == 0) { s_base[0] = dp; s_base[1] = di; }
+        __syncthreads();
+    }
+    const int base_p = s_base[0], base_i = s_base[1];
+    const int i0 = blockIdx.x * kScanTile + 4 * t;
+    int c[4], m[4];
+    scan_tile_load(count, nslots, i0, ppi, sh, c, m);
+    const int tp0 = c[0] + c[1] + c[2] + c[3], ti0 = m[0] + m[1] + m[2] + m[3];
+    int sp_ = tp0, si_ = ti0, tot_p, tot_i;
+    __syncthreads();   // s_wp / s_wi are reused
+    scan_block(sp_, si_, tot_p, tot_i, s_wp, s_wi);
+    int rp = base_p + sp_ - tp0, ri = base_i + si_ - ti0;
+    if (i0 + 3 < nslots) {
+        int4 ps, is;
+        ps.x = rp; is.x = ri; rp += c[0]; ri += m[0];
+        ps.y = rp; is.y = ri; rp += c[1]; ri += m[1];
+        ps.z = rp; is.z = ri; rp += c[2]; ri += m[2];
+        ps.w = rp; is.w = ri;
+        *reinterpret_cast<int4*>(start + i0) = ps;
+        *reinterpret_cast<int4*>(item_start + i0) = is;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (i0 + k < nslots) { start[i0 + k] = rp; item_start[i0 + k] = ri; }
+            rp += c[k]; ri += m[k];
+        }
+    }
+    if (blockIdx.x == gridDim.x - 1 && t == 0) {
+        start[nslots] = base_p + tot_p;
+        counters[0] = base_i + tot_i;  // number of work items
+        counters[1] = 0;               // dynamic scheduler cursor
+        counters[2] = base_p + tot_p;  // number of in-domain points
+    }
+}
+
 // pass 3: work items of every cell (one warp per cell, lanes emit items in parallel); afterwards
 // cell_cursor is zeroed to serve as the scatter cursor.
 __global__ void __launch_bounds__(256) k_plan_items(const __grid_constant__ thb_space_desc sp, const int32_t* __restrict__ count,
@@ -599,8 +703,18 @@ extern "C" int thb_plan_build(const thb_space_desc* space, const float* params, 
             THB_LAUNCHED();
         }
     }
-    k_plan_scan<<<1, 1024, 0, st>>>(plan->cell_count, plan->cell_start, plan->cell_cursor, ns, plan->points_per_item, plan->counters);
-    THB_LAUNCHED();
+    const int ntile = (ns + kScanTile - 1) / kScanTile;
+    if (ntile >= 4 && n >= 2 * (int64_t)ntile && (((uintptr_t)plan->scratch) & 3) == 0) {
+        // plan->scratch is free between the fix-up pass and the end of the plan: it holds the per-tile totals
+        k_plan_scan_sums<<<ntile, 1024, 0, st>>>(plan->cell_count, ns, plan->points_per_item, plan->scratch);
+        THB_LAUNCHED();
+        k_plan_scan_write<<<ntile, 1024, 0, st>>>(plan->cell_count, plan->cell_start, plan->cell_cursor, ns, plan->points_per_item,
+                                                  plan->scratch, plan->counters);
+        THB_LAUNCHED();
+    } else {
+        k_plan_scan<<<1, 1024, 0, st>>>(plan->cell_count, plan->cell_start, plan->cell_cursor, ns, plan->points_per_item, plan->counters);
+        THB_LAUNCHED();
+    }
     k_plan_items<<<(ns * 32 + 255) / 256, 256, 0, st>>>(*space, plan->cell_count, plan->cell_start, plan->cell_cursor, ns, plan->points_per_item,
                                                    plan->max_items, (int4*)plan->items);
     THB_LAUNCHED();
