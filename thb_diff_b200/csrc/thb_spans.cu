@@ -532,21 +532,17 @@ __global__ void __launch_bounds__(1024) k_plan_scan_write(const int32_t* __restr
 __global__ void __launch_bounds__(256) k_plan_items(const __grid_constant__ thb_space_desc sp, const int32_t* __restrict__ count,
                                                     const int32_t* __restrict__ start, int32_t* __restrict__ item_start_then_cursor,
                                                     int nslots, int ppi, int max_items, int4* __restrict__ items) {
-    const int lane = threadIdx.x & 31;
-    const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    // one THREAD per cell: the kernel is one global round trip long whatever the mapping, and a thread per cell fits
+    // the whole hierarchy in a single wave of CTAs (a warp per cell needed 5.5 waves for C3's 52 k cells)
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= nslots) return;
-    const int c = count[s], b = start[s];
-    const int it0 = item_start_then_cursor[s];
-    __syncwarp();
-    const int m = (c + ppi - 1) / ppi;
-    if (m == 0) {
-        if (lane == 0) item_start_then_cursor[s] = b;
-        return;
-    }
     const int4* ci = reinterpret_cast<const int4*>(sp.cellinfo + (int64_t)s * THB_INFO_W);
     const int4 a = __ldg(ci), e = __ldg(ci + 1), f = __ldg(ci + 2);  // level c0 c1 c2 | supp_off S tile_off n_direct | sep_off n_sep full_off 0
     const unsigned long long dm = __ldg(sp.dmask + s);
-    for (int j = lane; j < m; j += 32) {
+    const int c = count[s], b = start[s];
+    const int it0 = item_start_then_cursor[s];
+    const int m = (c + ppi - 1) / ppi;
+    for (int j = 0; j < m; ++j) {
         if (it0 + j < max_items) {
             int4* o = items + (int64_t)(it0 + j) * 4;
             o[0] = make_int4(s, b + j * ppi, min(ppi, c - j * ppi), a.x);
@@ -555,7 +551,7 @@ __global__ void __launch_bounds__(256) k_plan_items(const __grid_constant__ thb_
             o[3] = make_int4((int)(unsigned)(dm & 0xffffffffull), (int)(unsigned)(dm >> 32), f.x, f.z);
         }
     }
-    if (lane == 0) item_start_then_cursor[s] = b;  // from here on the scatter cursor of the cell: next free place
+    item_start_then_cursor[s] = b;  // from here on the scatter cursor of the cell: next free place
 }
 
 // pass 4: scatter the points into cell order as 16-byte records (u0, u1, u2 or 0, caller index as bits) -- one
@@ -715,7 +711,7 @@ extern "C" int thb_plan_build(const thb_space_desc* space, const float* params, 
         k_plan_scan<<<1, 1024, 0, st>>>(plan->cell_count, plan->cell_start, plan->cell_cursor, ns, plan->points_per_item, plan->counters);
         THB_LAUNCHED();
     }
-    k_plan_items<<<(ns * 32 + 255) / 256, 256, 0, st>>>(*space, plan->cell_count, plan->cell_start, plan->cell_cursor, ns, plan->points_per_item,
+    k_plan_items<<<(ns + 255) / 256, 256, 0, st>>>(*space, plan->cell_count, plan->cell_start, plan->cell_cursor, ns, plan->points_per_item,
                                                    plan->max_items, (int4*)plan->items);
     THB_LAUNCHED();
     if (n > 0) {
