@@ -203,3 +203,31 @@ def test_domain_boundary_and_outside_points_fused():
     assert np.abs(out[:3] - prm[:3]).max() < 1e-6      # linear reproduction right at the boundary
     assert np.all(out[3:] == 0.0)                       # out-of-domain points: flagged (slot -1), zero output
     assert plan.slot[:6].cpu().numpy()[3:].tolist() == [-1, -1, -1]
+
+
+def test_local_net_needs_a_workspace_and_nets_are_reusable():
+    """C-ABI contract of the nets entry points: thb_eval_fused(local_net) without a workspace is an error, not a
+    fallback; nets built once (all cells) serve several batches until the control points change."""
+    import ctypes as C
+
+    from thb_diff_b200 import _lib, engine
+
+    g, h, P, plan, cp, cs = _setup("block3d")
+    cpt = torch.from_numpy(cp).cuda()
+    out = torch.zeros((plan.n, 3), device="cuda")
+    arr = (C.c_void_p * 1)(out.data_ptr())
+    ch = (C.c_int32 * 1)(0)
+    rc = _lib.lib.thb_eval_fused(C.byref(P.desc()), C.byref(plan.desc), _lib.ptr(plan.params), _lib.ptr(cpt), 3, ch, 1, arr, 0, None,
+                                 _lib.stream_ptr(P.device))
+    assert rc != 0 and b"workspace" in _lib.lib.thb_last_error()
+    assert _lib.lib.thb_net_workspace_floats(C.byref(P.desc()), 0) == P.nslots * 4 * P.TS
+    assert _lib.lib.thb_net_workspace_floats(C.byref(P.desc()), 1) == P.nslots * 8 * P.TS
+    nets = engine.cell_nets(P, cpt)                                  # every active cell
+    ref = O.eval_forward(cp, g["Jm"], g["PHI"], cs)
+    a = engine.eval_nets(P, plan, nets, 3)[0].cpu().numpy()
+    assert rel_err(a, ref, scale=np.abs(ref).max()).max() <= TOL
+    half = engine.Plan(P, g["params"][: len(cs) // 2])               # another batch, same nets
+    b = engine.eval_nets(P, half, nets, 3)[0].cpu().numpy()
+    assert rel_err(b, ref[: len(cs) // 2], scale=np.abs(ref).max()).max() <= TOL
+    with pytest.raises(RuntimeError):                                # derivative channels need nets built with them
+        engine.eval_nets(P, plan, nets, 3, channels=engine.grad_channels(3), with_derivatives=False)
