@@ -21,6 +21,9 @@ namespace thb_tile {
 #ifndef THB_NET_MINB
 #define THB_NET_MINB 16  // k_net_eval: <= 128 registers, 16 one-warp CTAs per SM
 #endif
+#ifndef THB_NET_MINB_DER
+#define THB_NET_MINB_DER 16  // derivative channels: more live values (both planes sets, values and derivatives of the bases)
+#endif
 #ifndef THB_NETS_MINB
 #define THB_NETS_MINB 9  // k_cell_nets: <= 56 registers, 36 warps per SM (it is latency-bound: occupancy matters; prefetching
                          // the next cell's descriptor / control points one chunk ahead cost more registers than it hid latency)
@@ -478,7 +481,7 @@ THB_DEV void net_points(const Args& ar, const Item& it, int base, NetSmem<SH, DE
 // computed the records of items i+1, i+2 are in flight, and the points of the next sub-batch plus the knots / net of
 // item i+1 stream into the other half of the shared-memory buffers (cp.async).
 template <int N0, int N1, int N2, int PPT, int CPD, bool DER>
-__global__ void __launch_bounds__(kThreads, THB_NET_MINB) k_net_eval(const __grid_constant__ thb_space_desc sp, const __grid_constant__ Args ar,
+__global__ void __launch_bounds__(kThreads, DER ? THB_NET_MINB_DER : THB_NET_MINB) k_net_eval(const __grid_constant__ thb_space_desc sp, const __grid_constant__ Args ar,
                                                                     const float* __restrict__ nets) {
     using SH = Shp<N0, N1, N2>;
     constexpr int SB = 32 * PPT;
