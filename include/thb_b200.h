@@ -100,6 +100,12 @@ typedef struct thb_plan_desc {
     int32_t* cell_cursor;
     int32_t* items;
     int32_t* counters;
+    int32_t rows_in_plan_order;  /* 0: row i of out / grad_out belongs to point i of params (the reference's layout).
+                                    1: row j belongs to the point of record j of sorted_params -- coalesced rows for callers
+                                    that keep their per-point data in plan order (a fit loop permutes its targets once);
+                                    honoured by thb_eval_nets / thb_eval_fused (local nets) / thb_eval_fused_backward with
+                                    a workspace, an error elsewhere */
+    int32_t pad_;
 } thb_plan_desc;
 
 THB_API int thb_version(void);

@@ -231,3 +231,31 @@ def test_local_net_needs_a_workspace_and_nets_are_reusable():
     assert rel_err(b, ref[: len(cs) // 2], scale=np.abs(ref).max()).max() <= TOL
     with pytest.raises(RuntimeError):                                # derivative channels need nets built with them
         engine.eval_nets(P, plan, nets, 3, channels=engine.grad_channels(3), with_derivatives=False)
+
+
+def test_rows_in_plan_order():
+    """thb_plan_desc::rows_in_plan_order: the same numbers, rows permuted by Plan.caller_index() -- forward and backward."""
+    from thb_diff_b200 import engine
+    from thb_diff_b200.packed import PackedHierarchy
+
+    g = load_golden("block3d")
+    h = product_space_from_golden(g)
+    P = PackedHierarchy.from_space(h, device="cuda")
+    rng = np.random.default_rng(9)
+    prm = rng.random((50021, 3)).astype(np.float32)
+    cp = torch.from_numpy(rng.standard_normal((P.nCP, 3)).astype(np.float32)).cuda()
+    go = torch.from_numpy(rng.standard_normal((len(prm), 3)).astype(np.float32)).cuda()
+    plan = engine.Plan(P, prm)
+    ref = engine.eval_fused(P, plan, cp)[0]
+    refg = engine.eval_fused_backward(P, plan, go)
+    perm = plan.caller_index()
+    assert torch.equal(torch.sort(perm).values, torch.arange(len(prm), device="cuda"))
+    plan.set_rows_in_plan_order(True)
+    out = engine.eval_fused(P, plan, cp)[0]
+    assert torch.equal(out, ref[perm])
+    gs = engine.eval_fused_backward(P, plan, go[perm].contiguous())
+    assert float((gs - refg).abs().max()) <= 1e-5 * float(refg.abs().max())
+    with pytest.raises(RuntimeError):
+        engine.eval_fused(P, plan, cp, formulation="per_point")      # only the nets path knows the row order
+    plan.set_rows_in_plan_order(False)
+    assert torch.equal(engine.eval_fused(P, plan, cp)[0], ref)

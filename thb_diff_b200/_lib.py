@@ -32,7 +32,7 @@ class PlanDesc(C.Structure):
     _fields_ = [
         ("npoints", C.c_int64), ("points_per_item", C.c_int32), ("max_items", C.c_int32),
         ("slot", C.c_void_p), ("scratch", C.c_void_p), ("sorted_params", C.c_void_p), ("cell_count", C.c_void_p), ("cell_start", C.c_void_p),
-        ("cell_cursor", C.c_void_p), ("items", C.c_void_p), ("counters", C.c_void_p),
+        ("cell_cursor", C.c_void_p), ("items", C.c_void_p), ("counters", C.c_void_p), ("rows_in_plan_order", C.c_int32), ("pad_", C.c_int32),
     ]
 
 

@@ -377,7 +377,7 @@ THB_DEV void net_points(const Args& ar, const Item& it, int base, NetSmem<SH, DE
     for (int q = 0; q < PPT; ++q) {
         valid[q] = base + q * 32 + lane < it.count;
         const float4 rec = sm.prec[pb][q * 32 + lane];
-        idx[q] = __float_as_int(rec.w);
+        idx[q] = ar.rows_sorted ? it.begin + base + q * 32 + lane : __float_as_int(rec.w);
         const float u[3] = {rec.x, rec.y, rec.z};
         bs[q].eval(u, K, RK);
     }
@@ -651,7 +651,7 @@ __global__ void __launch_bounds__(kThreads, 16) k_net_backward(const __grid_cons
 #pragma unroll
                 for (int i = 0; i < N2; ++i) c4[i] = bs.n2[i];
                 if (pi < npts) {
-                    const int64_t idx = __float_as_int(rec.w);
+                    const int64_t idx = ar.rows_sorted ? it.begin + base + pi : __float_as_int(rec.w);
 #pragma unroll
                     for (int k = 0; k < CPD; ++k) g4[k] = __ldg(ar.grad_out + idx * CPD + k);
                 }

@@ -59,6 +59,7 @@ extern "C" int thb_basis_tiled(const thb_space_desc* space, const thb_plan_desc*
     if ((rc = check_plan(plan, "thb_basis_tiled"))) return rc;
     if (plan->npoints == 0) return THB_OK;
     THB_REQUIRE(params && offsets && phi_out_host, "thb_basis_tiled: null pointer");
+    THB_REQUIRE(!plan->rows_in_plan_order, "thb_basis_tiled: rows_in_plan_order is not supported (PHI rows follow `offsets`)");
     const ShapeOps* ops = find_shape(space);
     if (!ops) return thb_set_error(THB_E_UNSUPPORTED, "thb_basis_tiled: no kernel for degrees (%d,%d,%d)", space->degree[0], space->degree[1], space->degree[2]);
     Args ar = {};
@@ -96,6 +97,7 @@ extern "C" int thb_eval_fused(const thb_space_desc* space, const thb_plan_desc* 
         if ((rc = thb_cell_nets(space, plan, ctrl_pts, cp_dim, der ? 1 : 0, workspace, stream))) return rc;
         return thb_eval_nets(space, plan, workspace, der ? 1 : 0, cp_dim, channels, nchannels, out_host, stream);
     }
+    THB_REQUIRE(!plan->rows_in_plan_order, "thb_eval_fused: rows_in_plan_order is only supported by the local-net formulation");
     for (int c = 0; c < nchannels; ++c) {
         THB_REQUIRE(out_host[c], "thb_eval_fused: null output");
         ar.out[c] = out_host[c];
@@ -145,6 +147,7 @@ extern "C" int thb_eval_nets(const thb_space_desc* space, const thb_plan_desc* p
         ar.out[c] = out_host[c];
     }
     ar.items = (const int4*)plan->items; ar.counters = plan->counters; ar.sorted = plan->sorted_params;
+    ar.rows_sorted = plan->rows_in_plan_order ? 1 : 0;
     cudaStream_t st = (cudaStream_t)stream;
     THB_CUDA(cudaMemsetAsync(plan->counters + 1, 0, sizeof(int32_t), st));
     return ops->net_eval(space, &ar, nets, env_int("THB_NET_PPT", 2), cp_dim, with_derivatives ? 1 : 0, st);
@@ -168,11 +171,13 @@ extern "C" int thb_eval_fused_backward(const thb_space_desc* space, const thb_pl
     ar.items = (const int4*)plan->items; ar.counters = plan->counters;
     ar.params = params; ar.sorted = plan->sorted_params; ar.grad_out = grad_out; ar.grad_cp = grad_ctrl_pts;
     THB_CUDA(cudaMemsetAsync(plan->counters + 1, 0, sizeof(int32_t), st));
+    THB_REQUIRE(workspace || !plan->rows_in_plan_order, "thb_eval_fused_backward: rows_in_plan_order needs the workspace (local nets) path");
     if (workspace) {  // through the per-cell net gradients (thb_net_impl.cuh); workspace: thb_net_workspace_floats(space, 0)
         THB_REQUIRE(plan->cell_count, "thb_eval_fused_backward: plan without cell_count");
         THB_CUDA(cudaMemsetAsync(workspace, 0, sizeof(float) * (size_t)thb_net_workspace_floats(space, 0), st));
         NetArgs na = {};
         na.cell_count = plan->cell_count; na.nets = workspace; na.planes = 4;
+        ar.rows_sorted = plan->rows_in_plan_order ? 1 : 0;
         return ops->net_backward(space, &ar, &na, grad_ctrl_pts, cp_dim, st);
     }
     return ops->backward(space, &ar, cp_dim, st);

@@ -46,6 +46,7 @@ struct Args {
     int32_t channels[4];
     int32_t nch;
     int32_t cellnet;
+    int32_t rows_sorted;     // rows of out / grad_out are in plan order (thb_plan_desc::rows_in_plan_order)
     // backward
     const float* grad_out;
     float* grad_cp;

@@ -58,8 +58,13 @@ class ShardedFit:
     def __init__(self, packed, params, targets, n_total, cellnet=True, group=None):
         from .torch_funcs import THB_fused_module
 
-        self.module = THB_fused_module(packed, params, cellnet=cellnet)
-        self.targets = targets
+        # the points are fixed for the whole fit: keep outputs, targets and gradients in the plan's cell order (coalesced
+        # rows) when the local-net kernels are used and every point lies inside the domain
+        try:
+            self.module = THB_fused_module(packed, params, cellnet=cellnet, plan_order_rows=bool(cellnet))
+        except RuntimeError:
+            self.module = THB_fused_module(packed, params, cellnet=cellnet)
+        self.targets = targets if self.module.perm is None else targets[self.module.perm].contiguous()
         self.n_total = int(n_total)
         self.group = group
 

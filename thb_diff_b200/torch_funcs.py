@@ -113,11 +113,21 @@ class THB_fused_module(torch.nn.Module):
         m = THB_fused_module(space_or_packed, params); pts = m(ctrl_pts); pts.sum().backward()
     """
 
-    def __init__(self, space, params, device="cuda", cellnet=True):
+    def __init__(self, space, params, device="cuda", cellnet=True, plan_order_rows=False):
+        """plan_order_rows=True: the rows of the output (and of the incoming gradient) follow the plan's cell order, row j
+        = point self.perm[j] of `params` -- coalesced rows; permute per-point data (targets) with self.perm once."""
         super().__init__()
         self.P = space if isinstance(space, PackedHierarchy) else PackedHierarchy.from_space(space, device=device)
         self.plan = engine.Plan(self.P, params)
         self.cellnet = cellnet
+        self.perm = None
+        if plan_order_rows:
+            if not cellnet:
+                raise RuntimeError("plan_order_rows needs the local-net formulation (cellnet=True)")
+            self.perm = self.plan.caller_index()
+            if self.perm.numel() != self.plan.n:
+                raise RuntimeError("plan_order_rows needs every point inside the domain")
+            self.plan.set_rows_in_plan_order(True)
 
     def forward(self, ctrl_pts):
         return THBFusedEval.apply(ctrl_pts, self)
