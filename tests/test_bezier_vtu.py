@@ -116,3 +116,37 @@ def test_adaptive_grid_export_matches_the_reference(tmp_path):
     assert np.array_equal(a["connectivity"].reshape(-1, 8), conn)
     assert np.array_equal(a["Points"].reshape(-1, 3), pts)
     assert set(np.unique(a["level"])) <= set(range(h.num_levels))
+
+
+def test_extraction_tables_reproduce_coarse_functions_on_fine_cells():
+    """ExtractionTables.M[(lev, k)][cf]: Bernstein coefficients, on the finest cell cf, of the level-`lev` B-splines of
+    the ancestor cell -- checked against scipy B-splines of that level (host-only arithmetic, no GPU)."""
+    from math import comb
+
+    from scipy.interpolate import BSpline
+
+    from thb_diff_b200.bezier import ExtractionTables
+    from thb_diff_b200.multilevel_spline_space import refine_knotvector
+
+    p = 3
+    kv = {0: [U_B]}
+    for lev in (1, 2):
+        kv[lev] = [refine_knotvector(kv[lev - 1][0], p)]
+    tabs = ExtractionTables(kv, (p,))
+    fine = np.unique(kv[2][0])
+    rng = np.random.default_rng(0)
+    for lev in (0, 1, 2):
+        U = kv[lev][0]
+        M = tabs.M[(lev, 0)]
+        assert M.shape == (len(fine) - 1, p + 1, p + 1)
+        for cf in rng.choice(len(fine) - 1, 6, replace=False):
+            c = cf >> (2 - lev)
+            u = np.linspace(fine[cf], fine[cf + 1], 5)[1:-1]
+            t = (u - fine[cf]) / (fine[cf + 1] - fine[cf])
+            bern = np.stack([comb(p, j) * t**j * (1 - t) ** (p - j) for j in range(p + 1)])
+            for i in range(p + 1):
+                coef = np.zeros(len(U) - p - 1)
+                coef[c + i] = 1
+                assert np.abs(BSpline(U, coef, p)(u) - M[cf, i] @ bern).max() <= 1e-12
+    cells = tabs.finest_cells(np.array([[0.0], [0.31], [1.0]]))
+    assert cells[0, 0] == 0 and cells[2, 0] == len(fine) - 2 and fine[cells[1, 0]] <= 0.31 < fine[cells[1, 0] + 1]
