@@ -60,3 +60,19 @@ def test_shard_bounds():
         assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
         sizes = [hi - lo for lo, hi in b]
         assert max(sizes) - min(sizes) <= 1
+
+
+def test_three_pass_loss_matches_the_composed_expression():
+    """distributed._ScaledSumSquaredError (the fit loop's loss) == scale * ((out - target) ** 2).sum(), value and gradient."""
+    from thb_diff_b200.distributed import _ScaledSumSquaredError
+
+    torch.manual_seed(0)
+    out = torch.randn(1000, 3, dtype=torch.float64, requires_grad=True)
+    tgt = torch.randn(1000, 3, dtype=torch.float64)
+    scale = 1.0 / 3000
+    a = _ScaledSumSquaredError.apply(out, tgt, scale)
+    (ga,) = torch.autograd.grad(3.0 * a, out)
+    out2 = out.detach().clone().requires_grad_(True)
+    b = ((out2 - tgt) ** 2).sum() * scale
+    (gb,) = torch.autograd.grad(3.0 * b, out2)
+    assert abs(float(a) - float(b)) <= 1e-12 and float((ga - gb).abs().max()) <= 1e-14
