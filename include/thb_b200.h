@@ -161,8 +161,8 @@ THB_API int thb_basis_tiled(const thb_space_desc* space, const thb_plan_desc* pl
 
 /* Legacy form of THB_basis_fns for callers that hold the reference's dense tables: coeffs is
  * [nfn_total, prod(nfns_finest)] f32 (THB/core.py:636-643), jm/cumsum as in thb_eval_forward, evaluation at the
- * finest level exactly as THB/core.py:652-677 (with the SURVEY Q2/Q3 repairs).  The only entry point that
- * synchronises the stream (it reads nnz = cumsum[npoints-1] back to size its grid). */
+ * finest level exactly as THB/core.py:652-677 (with the SURVEY Q2/Q3 repairs).  nnz = cumsum[npoints-1] is read by
+ * the kernel itself: like every other entry point this one never synchronises. */
 THB_API int thb_basis_dense(const float* params, int64_t npoints, int ndim, const int32_t* degree, const float* knots,
                     const int32_t* knot_off, const int32_t* knot_len, const int32_t* nfns_finest,
                     const float* coeffs, const void* jm, int jm_is_i64, const int64_t* cumsum, int channel,
@@ -207,6 +207,33 @@ THB_API int thb_eval_nets(const thb_space_desc* space, const thb_plan_desc* plan
 THB_API int thb_eval_fused_backward(const thb_space_desc* space, const thb_plan_desc* plan, const float* params,
                             const float* grad_out, int cp_dim, float* grad_ctrl_pts, int64_t nctrl, float* workspace,
                             void* stream);
+
+/* Same gradient in COMPACT rows: grad_rows[row_map[f], :] receives the gradient of flat function / control-point id f.
+ * Only active functions ever get one (config 3: 42 153 of 2 598 588 rows), so a fit loop keeps, all-reduces and steps
+ * nrows x cp_dim values instead of nctrl x cp_dim.  row_map: [nctrl] i32, >= 0 for every support of an active cell
+ * (thb_diff_b200/packed.py: PackedHierarchy.active_rows()); grad_rows [nrows, cp_dim] is zeroed by the callee;
+ * workspace as above (required).  The reference has no counterpart: its backward always fills the dense
+ * [nCP, 3] tensor (THB/THB_extensions/compute_pts_cuda_kernels.cu:73-97). */
+THB_API int thb_eval_fused_backward_rows(const thb_space_desc* space, const thb_plan_desc* plan, const float* params,
+                                 const float* grad_out, int cp_dim, const int32_t* row_map, float* grad_rows,
+                                 int64_t nrows, float* workspace, void* stream);
+
+/* ---- fit loop helpers (BASELINE config 4; the reference composes these from torch ops around THBEval,
+ * THB/torch_funcs.py:8-47) ----------------------------------------------------------------------------------
+ * thb_mse_grad: loss[0] = scale * sum_i (out[i] - target[i])^2 and grad_out[i] = 2 scale (out[i] - target[i]) over
+ *     nvalues floats in one pass.  Deterministic (fixed-order reduction).  workspace: thb_mse_workspace_bytes() bytes,
+ *     zero-filled before the FIRST call (the kernel leaves it ready for the next one); buffers 16-byte aligned.
+ * thb_adam_rows: torch.optim.Adam's update (betas, eps, no weight decay, no amsgrad) applied to the rows row_ids[r] of the
+ *     dense parameter params[nctrl, cp_dim] with gradient grad_rows[r, :] * grad_scale and state exp_avg / exp_avg_sq
+ *     [nrows, cp_dim].  Rows outside row_ids keep a zero gradient for ever, and Adam never moves such a row, so this is
+ *     the dense optimiser restricted to the rows it can change.  step: 1-based step number; when step_dev (device i32)
+ *     is non-null the number is step_dev[0] + 1 and the call increments it (CUDA-graph replay). */
+THB_API int64_t thb_mse_workspace_bytes(void);
+THB_API int thb_mse_grad(const float* out, const float* target, int64_t nvalues, float scale, float* grad_out, float* loss,
+                 void* workspace, void* stream);
+THB_API int thb_adam_rows(float* params, const int32_t* row_ids, const float* grad_rows, float* exp_avg, float* exp_avg_sq,
+                  int64_t nrows, int cp_dim, float lr, float beta1, float beta2, float eps, float grad_scale, int step,
+                  int32_t* step_dev, void* stream);
 
 /* ---- measurement helpers -----------------------------------------------------------------------------------
  * Dependent-chain FP32 FMA micro-kernel used by bench.py to measure the FP32 roofline denominator.

@@ -63,6 +63,10 @@ def _load():
         "thb_cell_nets": (i32, [C.POINTER(SpaceDesc), C.POINTER(PlanDesc), vp, i32, i32, vp, vp]),
         "thb_eval_nets": (i32, [C.POINTER(SpaceDesc), C.POINTER(PlanDesc), vp, i32, i32, C.POINTER(C.c_int32), i32, C.POINTER(vp), vp]),
         "thb_eval_fused_backward": (i32, [C.POINTER(SpaceDesc), C.POINTER(PlanDesc), vp, vp, i32, vp, i64, vp, vp]),
+        "thb_eval_fused_backward_rows": (i32, [C.POINTER(SpaceDesc), C.POINTER(PlanDesc), vp, vp, i32, vp, vp, i64, vp, vp]),
+        "thb_mse_workspace_bytes": (i64, []),
+        "thb_mse_grad": (i32, [vp, vp, i64, C.c_float, vp, vp, vp, vp]),
+        "thb_adam_rows": (i32, [vp, vp, vp, vp, vp, i64, i32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, i32, vp, vp]),
         "thb_fma_peak": (i32, [i32, i32, vp, C.POINTER(C.c_double), vp]),
     }
     for name, (res, args) in sig.items():

@@ -8,7 +8,9 @@
 // ---- host side -------------------------------------------------------------------------------------------
 int thb_set_error(int code, const char* fmt, ...);
 void thb_count_launch(int n = 1);
-int thb_num_sms();
+#define THB_MAX_DEVICES 64
+int thb_device();   // current device ordinal (0 if it cannot be read)
+int thb_num_sms();  // of the current device
 
 #define THB_REQUIRE(cond, ...)                                  \
     do {                                                        \

@@ -23,7 +23,8 @@ template <typename JT>
 __global__ void __launch_bounds__(256) k_basis_dense(const float* __restrict__ params, int64_t npoints, DenseArgs a,
                                                      const float* __restrict__ knots, const float* __restrict__ coeffs,
                                                      const JT* __restrict__ jm, const int64_t* __restrict__ cumsum, int channel,
-                                                     float* __restrict__ phi_out, int64_t nnz) {
+                                                     float* __restrict__ phi_out) {
+    const int64_t nnz = __ldg(cumsum + (npoints - 1));   // read on the device: the host never waits for it
     const int64_t row_len = (int64_t)a.nf[0] * a.nf[1] * (a.ndim == 3 ? a.nf[2] : 1);
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nnz; j += (int64_t)gridDim.x * blockDim.x) {
         // first point i with cumsum[i] > j
@@ -81,18 +82,14 @@ extern "C" int thb_basis_dense(const float* params, int64_t npoints, int ndim, c
         a.degree[k] = degree[k]; a.knot_off[k] = knot_off[k]; a.knot_len[k] = knot_len[k]; a.nf[k] = nfns_finest[k];
     }
     cudaStream_t st = (cudaStream_t)stream;
-    // nnz = cumsum[npoints-1] lives on the device; the grid is sized for the machine and strides over nnz,
-    // which the kernel receives through a tiny device-to-host copy on the same stream.
-    int64_t nnz = 0;
-    THB_CUDA(cudaMemcpyAsync(&nnz, cumsum + (npoints - 1), sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-    THB_CUDA(cudaStreamSynchronize(st));
-    if (nnz <= 0) return THB_OK;
-    int64_t want = (nnz + 255) / 256, cap = (int64_t)thb_num_sms() * 16;
+    // nnz = cumsum[npoints-1] lives on the device and stays there: the grid is sized from npoints (every point has
+    // at least one pair, so this never exceeds the pair count by much) capped at the machine, and strides over nnz
+    int64_t want = (npoints * 8 + 255) / 256, cap = (int64_t)thb_num_sms() * 16;
     const int grid = (int)(want < cap ? want : cap);
     if (jm_is_i64)
-        k_basis_dense<long long><<<grid, 256, 0, st>>>(params, npoints, a, knots, coeffs, (const long long*)jm, cumsum, channel, phi_out, nnz);
+        k_basis_dense<long long><<<grid, 256, 0, st>>>(params, npoints, a, knots, coeffs, (const long long*)jm, cumsum, channel, phi_out);
     else
-        k_basis_dense<int><<<grid, 256, 0, st>>>(params, npoints, a, knots, coeffs, (const int*)jm, cumsum, channel, phi_out, nnz);
+        k_basis_dense<int><<<grid, 256, 0, st>>>(params, npoints, a, knots, coeffs, (const int*)jm, cumsum, channel, phi_out);
     THB_LAUNCHED();
     return THB_OK;
 }

@@ -36,6 +36,7 @@ struct NetArgs {
     const int32_t* cell_count;  // plan histogram: cells without points are skipped (nullptr = every cell)
     float* nets;                // [nslots][planes][TS]
     int32_t planes;             // 4, or 8 with the relative planes
+    const int32_t* row_map;     // k_cell_unfold: flat function id -> row of the (compact) gradient buffer; nullptr = identity
 };
 
 template <int CPD>
@@ -747,7 +748,8 @@ __global__ void __launch_bounds__(32 * kNetWarps) k_cell_unfold(const __grid_con
             for (int t = lane; t < T; t += 32) {
                 if ((dm >> t) & 1ull) {
                     const int t2 = t % N2, t1 = (t / N2) % N1, t0 = t / (N2 * N1);
-                    const int64_t r = f0 + ((int64_t)(a.y + t0) * n1 + (a.z + t1)) * n2 + (a.w + t2);
+                    int64_t r = f0 + ((int64_t)(a.y + t0) * n1 + (a.z + t1)) * n2 + (a.w + t2);
+                    if (na.row_map) r = __ldg(na.row_map + r);   // compact rows: active functions only
                     const float4 v = gw[t];
                     atomicAdd(grad_cp + r * CPD, v.x);
                     if (CPD > 1) atomicAdd(grad_cp + r * CPD + 1, v.y);
@@ -795,6 +797,7 @@ __global__ void __launch_bounds__(32 * kNetWarps) k_cell_unfold(const __grid_con
                     }
                 }
             }
+            if (na.row_map) r = __ldg(na.row_map + r);
 #pragma unroll
             for (int k = 0; k < CPD; ++k) atomicAdd(grad_cp + r * CPD + k, acc[k]);
         }
@@ -805,7 +808,8 @@ template <int N0, int N1, int N2>
 int launch_net_backward(const thb_space_desc* sp, const Args* ar, const NetArgs* na, float* grad_cp, int cpd, cudaStream_t st) {
 #define THB_NET_BWD(CPD_)                                                                              \
     do {                                                                                               \
-        static int g1 = 0, g2 = 0;                                                                     \
+        static int g1_[THB_MAX_DEVICES] = {}, g2_[THB_MAX_DEVICES] = {};                               \
+        int &g1 = g1_[thb_device()], &g2 = g2_[thb_device()];                                          \
         if (g1 == 0) g1 = persistent_grid(k_net_backward<N0, N1, N2, CPD_>, kThreads);                  \
         if (g2 == 0) g2 = persistent_grid(k_cell_unfold<N0, N1, N2, CPD_>, 32 * kNetWarps);             \
         k_net_backward<N0, N1, N2, CPD_><<<g1, kThreads, 0, st>>>(*sp, *ar, na->nets);                  \
@@ -824,7 +828,8 @@ template <int N0, int N1, int N2>
 int launch_nets(const thb_space_desc* sp, const NetArgs* na, int cpd, cudaStream_t st) {
 #define THB_NETS(CPD_, REL_)                                                                  \
     do {                                                                                      \
-        static int full = 0; /* one resident wave: no partial second wave */                  \
+        static int full_[THB_MAX_DEVICES] = {}; /* one resident wave: no partial second wave */ \
+        int& full = full_[thb_device()];                                                      \
         if (full == 0) full = persistent_grid(k_cell_nets<N0, N1, N2, CPD_, REL_>, 32 * kNetWarps); \
         const int grid = min((sp->nslots + kNetWarps - 1) / kNetWarps, full);                  \
         k_cell_nets<N0, N1, N2, CPD_, REL_><<<grid, 32 * kNetWarps, 0, st>>>(*sp, *na);        \
@@ -843,7 +848,8 @@ template <int N0, int N1, int N2>
 int launch_net_eval(const thb_space_desc* sp, const Args* ar, const float* nets, int ppt, int cpd, int der, cudaStream_t st) {
 #define THB_NET_EVAL(PPT_, CPD_, DER_)                                                        \
     do {                                                                                      \
-        static int grid = 0;                                                                  \
+        static int grid_[THB_MAX_DEVICES] = {};                                               \
+        int& grid = grid_[thb_device()];                                                      \
         if (grid == 0) grid = persistent_grid(k_net_eval<N0, N1, N2, PPT_, CPD_, DER_>, kThreads); \
         k_net_eval<N0, N1, N2, PPT_, CPD_, DER_><<<grid, kThreads, 0, st>>>(*sp, *ar, nets);   \
         THB_LAUNCHED();                                                                       \

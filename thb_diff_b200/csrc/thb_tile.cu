@@ -153,32 +153,48 @@ extern "C" int thb_eval_nets(const thb_space_desc* space, const thb_plan_desc* p
     return ops->net_eval(space, &ar, nets, env_int("THB_NET_PPT", 2), cp_dim, with_derivatives ? 1 : 0, st);
 }
 
+static int fused_backward_impl(const thb_space_desc* space, const thb_plan_desc* plan, const float* params, const float* grad_out,
+                               int cp_dim, const int32_t* row_map, float* grad, int64_t nrows, float* workspace, void* stream,
+                               const char* who) {
+    int rc = thb_check_space(space, who);
+    if (rc) return rc;
+    if ((rc = check_plan(plan, who))) return rc;
+    THB_REQUIRE(cp_dim == 3 || cp_dim == 4, "%s: cp_dim must be 3 or 4", who);
+    THB_REQUIRE(grad && nrows > 0, "%s: null gradient buffer", who);
+    cudaStream_t st = (cudaStream_t)stream;
+    THB_CUDA(cudaMemsetAsync(grad, 0, sizeof(float) * nrows * cp_dim, st));
+    if (plan->npoints == 0) return THB_OK;
+    THB_REQUIRE(params && grad_out, "%s: null pointer", who);
+    const ShapeOps* ops = find_shape(space);
+    if (!ops) return thb_set_error(THB_E_UNSUPPORTED, "%s: no kernel for degrees (%d,%d,%d)", who, space->degree[0], space->degree[1], space->degree[2]);
+    Args ar = {};
+    ar.items = (const int4*)plan->items; ar.counters = plan->counters;
+    ar.params = params; ar.sorted = plan->sorted_params; ar.grad_out = grad_out; ar.grad_cp = grad;
+    THB_CUDA(cudaMemsetAsync(plan->counters + 1, 0, sizeof(int32_t), st));
+    THB_REQUIRE(workspace || !plan->rows_in_plan_order, "%s: rows_in_plan_order needs the workspace (local nets) path", who);
+    THB_REQUIRE(workspace || !row_map, "%s: compact gradient rows need the workspace (local nets) path", who);
+    if (workspace) {  // through the per-cell net gradients (thb_net_impl.cuh); workspace: thb_net_workspace_floats(space, 0)
+        THB_REQUIRE(plan->cell_count, "%s: plan without cell_count", who);
+        THB_CUDA(cudaMemsetAsync(workspace, 0, sizeof(float) * (size_t)thb_net_workspace_floats(space, 0), st));
+        NetArgs na = {};
+        na.cell_count = plan->cell_count; na.nets = workspace; na.planes = 4; na.row_map = row_map;
+        ar.rows_sorted = plan->rows_in_plan_order ? 1 : 0;
+        return ops->net_backward(space, &ar, &na, grad, cp_dim, st);
+    }
+    return ops->backward(space, &ar, cp_dim, st);
+}
+
 extern "C" int thb_eval_fused_backward(const thb_space_desc* space, const thb_plan_desc* plan, const float* params,
                                        const float* grad_out, int cp_dim, float* grad_ctrl_pts, int64_t nctrl, float* workspace,
                                        void* stream) {
-    int rc = thb_check_space(space, "thb_eval_fused_backward");
-    if (rc) return rc;
-    if ((rc = check_plan(plan, "thb_eval_fused_backward"))) return rc;
-    THB_REQUIRE(cp_dim == 3 || cp_dim == 4, "thb_eval_fused_backward: cp_dim must be 3 or 4");
-    THB_REQUIRE(grad_ctrl_pts && nctrl > 0, "thb_eval_fused_backward: null gradient buffer");
-    cudaStream_t st = (cudaStream_t)stream;
-    THB_CUDA(cudaMemsetAsync(grad_ctrl_pts, 0, sizeof(float) * nctrl * cp_dim, st));
-    if (plan->npoints == 0) return THB_OK;
-    THB_REQUIRE(params && grad_out, "thb_eval_fused_backward: null pointer");
-    const ShapeOps* ops = find_shape(space);
-    if (!ops) return thb_set_error(THB_E_UNSUPPORTED, "thb_eval_fused_backward: no kernel for degrees (%d,%d,%d)", space->degree[0], space->degree[1], space->degree[2]);
-    Args ar = {};
-    ar.items = (const int4*)plan->items; ar.counters = plan->counters;
-    ar.params = params; ar.sorted = plan->sorted_params; ar.grad_out = grad_out; ar.grad_cp = grad_ctrl_pts;
-    THB_CUDA(cudaMemsetAsync(plan->counters + 1, 0, sizeof(int32_t), st));
-    THB_REQUIRE(workspace || !plan->rows_in_plan_order, "thb_eval_fused_backward: rows_in_plan_order needs the workspace (local nets) path");
-    if (workspace) {  // through the per-cell net gradients (thb_net_impl.cuh); workspace: thb_net_workspace_floats(space, 0)
-        THB_REQUIRE(plan->cell_count, "thb_eval_fused_backward: plan without cell_count");
-        THB_CUDA(cudaMemsetAsync(workspace, 0, sizeof(float) * (size_t)thb_net_workspace_floats(space, 0), st));
-        NetArgs na = {};
-        na.cell_count = plan->cell_count; na.nets = workspace; na.planes = 4;
-        ar.rows_sorted = plan->rows_in_plan_order ? 1 : 0;
-        return ops->net_backward(space, &ar, &na, grad_ctrl_pts, cp_dim, st);
-    }
-    return ops->backward(space, &ar, cp_dim, st);
+    return fused_backward_impl(space, plan, params, grad_out, cp_dim, nullptr, grad_ctrl_pts, nctrl, workspace, stream,
+                               "thb_eval_fused_backward");
+}
+
+extern "C" int thb_eval_fused_backward_rows(const thb_space_desc* space, const thb_plan_desc* plan, const float* params,
+                                            const float* grad_out, int cp_dim, const int32_t* row_map, float* grad_rows,
+                                            int64_t nrows, float* workspace, void* stream) {
+    THB_REQUIRE(row_map, "thb_eval_fused_backward_rows: null row map");
+    return fused_backward_impl(space, plan, params, grad_out, cp_dim, row_map, grad_rows, nrows, workspace, stream,
+                               "thb_eval_fused_backward_rows");
 }

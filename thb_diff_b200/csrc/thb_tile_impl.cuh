@@ -785,7 +785,8 @@ int persistent_grid(K kernel, int threads) {
 
 #define THB_TILE_LAUNCH_N(KERNEL, NT)                                             \
     do {                                                                          \
-        static int grid = 0;                                                      \
+        static int grid_[THB_MAX_DEVICES] = {};                                   \
+        int& grid = grid_[thb_device()];                                          \
         if (grid == 0) grid = persistent_grid(KERNEL, NT);                        \
         KERNEL<<<grid, NT, 0, st>>>(*sp, *ar);                                    \
         THB_LAUNCHED();                                                           \

@@ -17,15 +17,22 @@ int thb_set_error(int code, const char* fmt, ...) {
 }
 void thb_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+int thb_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= THB_MAX_DEVICES) dev = 0;
+    return dev;
+}
+
+// cached per device ordinal: a process may drive several GPUs (kernel attributes and grids are per device too)
 int thb_num_sms() {
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 148;
+    static int sms[THB_MAX_DEVICES] = {};
+    const int dev = thb_device();
+    if (sms[dev] == 0) {
+        int v = 0;
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        sms[dev] = v > 0 ? v : 148;
     }
-    return sms;
+    return sms[dev];
 }
 
 extern "C" int thb_version(void) { return 100; }

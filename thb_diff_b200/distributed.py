@@ -2,8 +2,15 @@
 
 Evaluation (spans, basis, geometry, derivatives) needs NO communication: every rank evaluates its own
 points against replicated tables.  Differentiable fitting reduces exactly one tensor per step -- the
-control-point gradient [nCP, cp_dim] -- with an NCCL all-reduce (SUM); parameters stay replicated, so the
-optimiser step is identical on every rank.  The reference has no distributed code at all."""
+control-point gradient -- with an NCCL all-reduce (SUM); parameters stay replicated, so the optimiser step is
+identical on every rank.  Only ACTIVE functions ever receive a gradient, so the tensor that is reduced is the compact
+[n_active, cp_dim] form (0.5 MB instead of 31 MB on BASELINE config 3), not the dense [nCP, cp_dim] one.
+The reference has no distributed code at all; its fit loop is THB/torch_funcs.py:8-47 on one device.
+
+Sharding a FIT (fixed points, many steps) by cells: the per-cell work of a step (local control nets, the transposed
+fold of the net gradients) is as large as the per-point work, so ranks must own disjoint sets of CELLS, not arbitrary
+subsets of the points -- `partition_by_cell` moves every point to the rank that owns its cell once, at set-up
+(all-to-all), balanced by points + per-cell cost ("sort by active cell then split evenly")."""
 import torch
 import torch.distributed as dist
 
@@ -24,11 +31,69 @@ def shard_points(params, rank, world, mode="contiguous"):
     return params[lo:hi]
 
 
+def _world(group=None):
+    return dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+
+
 def allreduce_grad_(grad, group=None):
     """SUM all-reduce of the control-point gradient in place (NCCL on GPUs, any backend for tests)."""
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+    if _world(group) > 1:
         dist.all_reduce(grad, op=dist.ReduceOp.SUM, group=group)
     return grad
+
+
+def allreduce_active_rows_(grad, active_ids, group=None):
+    """The same reduction for a DENSE [nCP, cp_dim] gradient (a generic torch optimiser wants one) moving only the rows
+    that can be non-zero: gather the active rows, all-reduce them, put them back."""
+    if _world(group) > 1:
+        idx = active_ids.long()
+        rows = grad.index_select(0, idx)
+        dist.all_reduce(rows, op=dist.ReduceOp.SUM, group=group)
+        grad.index_copy_(0, idx, rows)
+    return grad
+
+
+def cell_owner_bounds(cell_points, world, cell_cost=100.0):
+    """Splits the active cells (slot order = level-major, C order: spatially coherent) into `world` contiguous ranges of
+    equal cost; cost of a cell = its points + cell_cost if it holds any (the nets / unfold work of a cell is worth about
+    a hundred point evaluations).  cell_points: [nslots] global point counts.  Returns int64 [world + 1] slot bounds."""
+    c = cell_points.to(torch.float64)
+    cost = c + (c > 0).to(torch.float64) * float(cell_cost)
+    cum = torch.cumsum(cost, 0)
+    total = float(cum[-1]) if cum.numel() else 0.0
+    targets = torch.arange(1, world, dtype=torch.float64, device=cum.device) * (total / world)
+    inner = torch.searchsorted(cum, targets, right=False) + 1   # first slot NOT owned by rank r-1
+    b = torch.cat([torch.zeros(1, dtype=torch.int64, device=cum.device), inner.to(torch.int64),
+                   torch.tensor([cum.numel()], dtype=torch.int64, device=cum.device)])
+    return torch.cummax(b.clamp(max=cum.numel()), 0).values
+
+
+def partition_by_cell(slot, nslots, payload, group=None, cell_cost=100.0):
+    """Moves every point to the rank that owns its active cell.
+
+    slot: int32/int64 [n] active-cell slot of this rank's points (engine.active_span; -1 = outside the domain: such a
+    point goes to rank 0); payload: float tensor [n, w] travelling with the points (parameters, targets, ...).
+    Returns (payload rows now owned by this rank [m, w], slot bounds [world + 1]).  Collectives: one all-reduce of the
+    cell histogram, one all-to-all of the counts, one all-to-all of the rows -- once per fit, not per step."""
+    world = _world(group)
+    slot = slot.long()
+    inside = slot >= 0
+    hist = torch.bincount(slot[inside], minlength=nslots)
+    if world > 1:
+        dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)
+    bounds = cell_owner_bounds(hist, world, cell_cost)
+    if world == 1:
+        return payload, bounds
+    dest = torch.searchsorted(bounds[1:-1].contiguous(), slot.clamp(min=0), right=True)
+    dest = torch.where(inside, dest, torch.zeros_like(dest))
+    order = torch.argsort(dest, stable=True)
+    send = payload.index_select(0, order).contiguous()
+    n_send = torch.bincount(dest, minlength=world)
+    n_recv = torch.empty_like(n_send)
+    dist.all_to_all_single(n_recv, n_send, group=group)
+    recv = payload.new_empty((int(n_recv.sum()), payload.shape[1]))
+    dist.all_to_all_single(recv, send, output_split_sizes=n_recv.tolist(), input_split_sizes=n_send.tolist(), group=group)
+    return recv, bounds
 
 
 class _ScaledSumSquaredError(torch.autograd.Function):
@@ -49,24 +114,26 @@ class _ScaledSumSquaredError(torch.autograd.Function):
 
 
 class ShardedFit:
-    """MSE fitting of the control points to targets at this rank's points.
+    """MSE fitting of the control points to targets at this rank's points, through autograd and ANY torch optimiser.
 
         fit = ShardedFit(packed, params_of_this_rank, targets_of_this_rank, n_total)
         loss = fit.step(ctrl_pts, optimizer)      # forward, backward, grad all-reduce, optimiser step
-    """
+
+    The gradient handed to the optimiser is the dense [nCP, cp_dim] tensor; only its active rows cross the wire.
+    FitEngine below is the same loop without autograd, with the gradient kept compact end to end."""
 
     def __init__(self, packed, params, targets, n_total, cellnet=True, group=None):
         from .torch_funcs import THB_fused_module
 
         # the points are fixed for the whole fit: keep outputs, targets and gradients in the plan's cell order (coalesced
         # rows) when the local-net kernels are used and every point lies inside the domain
-        try:
-            self.module = THB_fused_module(packed, params, cellnet=cellnet, plan_order_rows=bool(cellnet))
-        except RuntimeError:
-            self.module = THB_fused_module(packed, params, cellnet=cellnet)
+        self.module = THB_fused_module(packed, params, cellnet=cellnet)
+        if cellnet and self.module.points_inside() == self.module.plan.n:
+            self.module.use_plan_order_rows()
         self.targets = targets if self.module.perm is None else targets[self.module.perm].contiguous()
         self.n_total = int(n_total)
         self.group = group
+        self.active_ids = packed.active_rows()[0]
 
     def step(self, ctrl_pts, optimizer):
         optimizer.zero_grad(set_to_none=True)
@@ -75,6 +142,106 @@ class ShardedFit:
         # all-reduced gradient is the gradient of the global mean squared error
         loss = _ScaledSumSquaredError.apply(out, self.targets, 1.0 / (self.n_total * out.shape[1]))
         loss.backward()
-        allreduce_grad_(ctrl_pts.grad, self.group)
+        allreduce_active_rows_(ctrl_pts.grad, self.active_ids, self.group)
         optimizer.step()
         return loss.detach()
+
+
+class FitEngine:
+    """The fit step of BASELINE config 4 with everything compact and nothing through autograd:
+
+        nets(ctrl_pts) -> evaluation -> one-pass MSE loss + output gradient -> backward into COMPACT active rows
+        -> all-reduce of [n_active, cp_dim] (NCCL) -> Adam on those rows of the dense parameter
+
+        eng = FitEngine(packed, params_of_this_rank, targets_of_this_rank, n_total, lr=1e-2)
+        loss = eng.step(ctrl_pts)        # ctrl_pts: dense [nCP, 3|4] float32 CUDA tensor, updated in place
+
+    Adam never moves a row whose gradient has always been zero, so updating the active rows only is the dense
+    torch.optim.Adam step (tests compare the two).  `loss` is this rank's share of the global mean squared error
+    (device tensor, no synchronisation); sum it over ranks for the global value.
+    use_graph: the whole step, all-reduce included, is captured into one CUDA graph after the first eager step."""
+
+    def __init__(self, packed, params, targets, n_total, lr=1e-2, betas=(0.9, 0.999), eps=1e-8, group=None, use_graph=False,
+                 comm_stream=False):
+        from . import engine
+
+        self.E, self.P, self.group = engine, packed, group
+        self.plan = engine.Plan(packed, params)
+        n_in = int(self.plan.counters[2])
+        if n_in != self.plan.n:
+            raise RuntimeError("FitEngine needs every point inside the domain")
+        perm = self.plan.caller_index()
+        self.plan.set_rows_in_plan_order(True)
+        dev = packed.device
+        cpd = targets.shape[1]
+        if cpd not in (3, 4):
+            raise RuntimeError("targets must be [N, 3] or [N, 4]")
+        self.cpd, self.n, self.n_total = cpd, self.plan.n, int(n_total)
+        self.targets = targets.to(device=dev, dtype=torch.float32)[perm].contiguous()
+        self.out = torch.empty((self.n, cpd), dtype=torch.float32, device=dev)
+        self.gout = torch.empty_like(self.out)
+        self.ids, self.row_map = packed.active_rows()
+        na = self.ids.shape[0]
+        self.grad = torch.zeros((na, cpd), dtype=torch.float32, device=dev)
+        self.m, self.v = torch.zeros_like(self.grad), torch.zeros_like(self.grad)
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.mse_ws = engine.mse_workspace(dev)
+        self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
+        self.use_graph, self._graph, self._graph_x = bool(use_graph), None, None
+        self.timers = None
+
+    def _enqueue(self, x):
+        E, P = self.E, self.P
+        t = self.timers
+        if t:
+            t[0].record()
+        nets = E.cell_nets(P, x, plan=self.plan)
+        E.eval_nets(P, self.plan, nets, self.cpd, out=[self.out], with_derivatives=False)
+        E.mse_grad(self.out, self.targets, 1.0 / (self.n_total * self.cpd), self.gout, self.loss, self.mse_ws)
+        E.eval_fused_backward_rows(P, self.plan, self.gout, out=self.grad)
+        if t:
+            t[1].record()
+        allreduce_grad_(self.grad, self.group)
+        if t:
+            t[2].record()
+        E.adam_rows(x, self.ids, self.grad, self.m, self.v, self.lr, self.betas, self.eps, step_dev=self.step_dev)
+        if t:
+            t[3].record()
+
+    def step(self, ctrl_pts):
+        x = ctrl_pts
+        if x.requires_grad:
+            x = x.detach()
+        if not self.use_graph:
+            self._enqueue(x)
+            return self.loss
+        if self._graph is None or self._graph_x != x.data_ptr():
+            self._enqueue(x)   # eager once (allocations, NCCL warm-up)
+            torch.cuda.synchronize(self.P.device)
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._enqueue(x)
+                self._graph, self._graph_x = g, x.data_ptr()
+                # the capture itself does not run the step
+            except Exception:
+                self.use_graph, self._graph = False, None
+                torch.cuda.synchronize(self.P.device)
+            return self.loss
+        self._graph.replay()
+        return self.loss
+
+    def time_phases(self, ctrl_pts, iters=10):
+        """(compute ms, all-reduce ms, optimiser ms) per step from CUDA events around the three phases (eager launches)."""
+        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(iters)]
+        keep = self.use_graph
+        self.use_graph = False
+        for k in range(iters):
+            self.timers = ev[k]
+            self.step(ctrl_pts)
+        self.timers = None
+        self.use_graph = keep
+        torch.cuda.synchronize(self.P.device)
+        f = lambda a, b: sum(e[a].elapsed_time(e[b]) for e in ev) / iters
+        return f(0, 1), f(1, 2), f(2, 3)

@@ -23,6 +23,13 @@ def mixed_channel(ndim):
     return (1 << ndim) - 1
 
 
+def _on(device):
+    """Every library call runs with the tensors' device current: the library launches on the CURRENT device, so a
+    hierarchy on cuda:1 used from a process whose current device is cuda:0 must switch first (stream handles, cached
+    grids and kernel attributes are per device)."""
+    return torch.cuda.device(device)
+
+
 def _as_params(params, ndim, device):
     """[N, ndim] float32 contiguous CUDA tensor (float64 / numpy inputs are rounded to f32 -- SURVEY Q11)."""
     if not isinstance(params, torch.Tensor):
@@ -64,7 +71,8 @@ class Plan:
 
     def build(self):
         self.version = self.P.version
-        check(lib.thb_plan_build(C.byref(self.P.desc()), ptr(self.params), C.byref(self.desc), stream_ptr(self.P.device)), "thb_plan_build")
+        with _on(self.P.device):
+            check(lib.thb_plan_build(C.byref(self.P.desc()), ptr(self.params), C.byref(self.desc), stream_ptr(self.P.device)), "thb_plan_build")
 
     def rebind(self, params):
         """Plans another batch (at most `capacity` points) in the same buffers."""
@@ -116,14 +124,16 @@ def active_span(P, params, want_num_supp=True):
     n = params.shape[0]
     slot = torch.empty(n, dtype=torch.int32, device=P.device)
     ns = torch.empty(n, dtype=torch.int32, device=P.device) if want_num_supp else None
-    check(lib.thb_active_span(C.byref(P.desc()), ptr(params), n, ptr(slot), ptr(ns), stream_ptr(P.device)), "thb_active_span")
+    with _on(P.device):
+        check(lib.thb_active_span(C.byref(P.desc()), ptr(params), n, ptr(slot), ptr(ns), stream_ptr(P.device)), "thb_active_span")
     return slot, ns
 
 
 def expand_supports(P, slot, offsets, nnz, dtype=torch.int64):
     jm = torch.empty(nnz, dtype=dtype, device=P.device)
-    check(lib.thb_expand_supports(C.byref(P.desc()), ptr(slot), ptr(offsets), slot.shape[0], ptr(jm), int(dtype == torch.int64),
-                                  stream_ptr(P.device)), "thb_expand_supports")
+    with _on(P.device):
+        check(lib.thb_expand_supports(C.byref(P.desc()), ptr(slot), ptr(offsets), slot.shape[0], ptr(jm), int(dtype == torch.int64),
+                                      stream_ptr(P.device)), "thb_expand_supports")
     return jm
 
 
@@ -133,15 +143,27 @@ def _chan_array(channels):
 
 def basis_tiled(P, plan, offsets, nnz, channels=(CH_VALUE,)):
     """PHI for each channel, flat [nnz] in the reference's (point-major) pair order."""
+    if not P.has_tiles:
+        raise RuntimeError("the hierarchy has no coefficient tiles yet (PackedHierarchy.attach_tiles / from_space)")
     plan.refresh()
     outs = [torch.empty(nnz, dtype=torch.float32, device=P.device) for _ in channels]  # every entry is written
     arr = (C.c_void_p * len(outs))(*[o.data_ptr() for o in outs])
-    check(lib.thb_basis_tiled(C.byref(P.desc()), C.byref(plan.desc), ptr(plan.params), ptr(offsets), _chan_array(channels),
-                              len(channels), arr, stream_ptr(P.device)), "thb_basis_tiled")
+    with _on(P.device):
+        check(lib.thb_basis_tiled(C.byref(P.desc()), C.byref(plan.desc), ptr(plan.params), ptr(offsets), _chan_array(channels),
+                                  len(channels), arr, stream_ptr(P.device)), "thb_basis_tiled")
     return outs
 
 
 FORMULATIONS = {"local_net": 0, "tile_net": 1, "per_point": 2}
+
+
+def _check_rows(tensors, plan, cpd, name):
+    """Raw pointers go to the library: every per-point buffer must be a contiguous f32 [plan.n, cp_dim] tensor on the
+    hierarchy's device."""
+    for t in tensors:
+        require_cuda(t, name, torch.float32)
+        if t.device != plan.P.device or t.dim() != 2 or t.shape[0] < plan.n or t.shape[1] != cpd:
+            raise RuntimeError(f"{name} must be [{plan.n}, {cpd}] float32 on {plan.P.device}, got {tuple(t.shape)} on {t.device}")
 
 
 def net_workspace(P, with_derivatives=False):
@@ -166,8 +188,9 @@ def cell_nets(P, ctrl_pts, with_derivatives=False, plan=None, out=None):
     nets = out if out is not None else net_workspace(P, with_derivatives)
     if plan is not None:
         plan.refresh()
-    check(lib.thb_cell_nets(C.byref(P.desc()), C.byref(plan.desc) if plan is not None else None, ptr(ctrl_pts), ctrl_pts.shape[1],
-                            int(with_derivatives), ptr(nets), stream_ptr(P.device)), "thb_cell_nets")
+    with _on(P.device):
+        check(lib.thb_cell_nets(C.byref(P.desc()), C.byref(plan.desc) if plan is not None else None, ptr(ctrl_pts), ctrl_pts.shape[1],
+                                int(with_derivatives), ptr(nets), stream_ptr(P.device)), "thb_cell_nets")
     return nets
 
 
@@ -178,9 +201,13 @@ def eval_nets(P, plan, nets, cp_dim=3, channels=(CH_VALUE,), out=None, with_deri
     plan.refresh()
     if out is None:
         out = [torch.zeros((plan.n, cp_dim), dtype=torch.float32, device=P.device) for _ in channels]
+    if len(out) != len(channels):
+        raise RuntimeError("one output buffer per channel")
+    _check_rows(out, plan, cp_dim, "out")
     arr = (C.c_void_p * len(out))(*[o.data_ptr() for o in out])
-    check(lib.thb_eval_nets(C.byref(P.desc()), C.byref(plan.desc), ptr(nets), int(with_derivatives), cp_dim, _chan_array(channels),
-                            len(channels), arr, stream_ptr(P.device)), "thb_eval_nets")
+    with _on(P.device):
+        check(lib.thb_eval_nets(C.byref(P.desc()), C.byref(plan.desc), ptr(nets), int(with_derivatives), cp_dim, _chan_array(channels),
+                                len(channels), arr, stream_ptr(P.device)), "thb_eval_nets")
     return out
 
 
@@ -199,10 +226,14 @@ def eval_fused(P, plan, ctrl_pts, channels=(CH_VALUE,), cellnet=True, out=None, 
     plan.refresh()
     if out is None:
         out = [torch.zeros((plan.n, cpd), dtype=torch.float32, device=P.device) for _ in channels]
+    if len(out) != len(channels):
+        raise RuntimeError("one output buffer per channel")
+    _check_rows(out, plan, cpd, "out")
     arr = (C.c_void_p * len(out))(*[o.data_ptr() for o in out])
     ws = net_workspace(P, any(int(c) != 0 for c in channels)) if form == 0 else None
-    check(lib.thb_eval_fused(C.byref(P.desc()), C.byref(plan.desc), ptr(plan.params), ptr(ctrl_pts), cpd, _chan_array(channels),
-                             len(channels), arr, form, ptr(ws) if ws is not None else None, stream_ptr(P.device)), "thb_eval_fused")
+    with _on(P.device):
+        check(lib.thb_eval_fused(C.byref(P.desc()), C.byref(plan.desc), ptr(plan.params), ptr(ctrl_pts), cpd, _chan_array(channels),
+                                 len(channels), arr, form, ptr(ws) if ws is not None else None, stream_ptr(P.device)), "thb_eval_fused")
     return out
 
 
@@ -216,16 +247,73 @@ def eval_fused_backward(P, plan, grad_out, cp_dim=None, formulation="local_net")
     if not P.has_tiles:
         raise RuntimeError("the hierarchy has no coefficient tiles yet (PackedHierarchy.attach_tiles / from_space)")
     plan.refresh()
+    _check_rows([grad_out], plan, cpd, "grad_out")
     g = torch.empty((P.nCP, cpd), dtype=torch.float32, device=P.device)
-    ws = None
-    if formulation == "local_net":
-        ws = getattr(P, "_gnet_ws", None)
-        n = lib.thb_net_workspace_floats(C.byref(P.desc()), 0)
-        if ws is None or ws.numel() != n:
-            ws = P._gnet_ws = torch.empty(n, dtype=torch.float32, device=P.device)
-    check(lib.thb_eval_fused_backward(C.byref(P.desc()), C.byref(plan.desc), ptr(plan.params), ptr(grad_out), cpd, ptr(g), P.nCP,
-                                      ptr(ws) if ws is not None else None, stream_ptr(P.device)), "thb_eval_fused_backward")
+    ws = _gnet_workspace(P) if formulation == "local_net" else None
+    with _on(P.device):
+        check(lib.thb_eval_fused_backward(C.byref(P.desc()), C.byref(plan.desc), ptr(plan.params), ptr(grad_out), cpd, ptr(g), P.nCP,
+                                          ptr(ws) if ws is not None else None, stream_ptr(P.device)), "thb_eval_fused_backward")
     return g
+
+
+def _gnet_workspace(P):
+    ws = getattr(P, "_gnet_ws", None)
+    n = lib.thb_net_workspace_floats(C.byref(P.desc()), 0)
+    if ws is None or ws.numel() != n:
+        ws = P._gnet_ws = torch.empty(n, dtype=torch.float32, device=P.device)
+    return ws
+
+
+def eval_fused_backward_rows(P, plan, grad_out, out=None):
+    """The same gradient in COMPACT rows: [P.n_active, cp_dim], row i = flat function id P.active_rows()[0][i]
+    (thb_eval_fused_backward_rows).  Only active functions receive a gradient, so this is everything there is."""
+    require_cuda(grad_out, "grad_out", torch.float32)
+    cpd = grad_out.shape[1]
+    if cpd not in (3, 4):
+        raise RuntimeError("fused backward supports control points of width 3 or 4")
+    if not P.has_tiles:
+        raise RuntimeError("the hierarchy has no coefficient tiles yet (PackedHierarchy.attach_tiles / from_space)")
+    plan.refresh()
+    _check_rows([grad_out], plan, cpd, "grad_out")
+    ids, row_map = P.active_rows()
+    g = out if out is not None else torch.empty((ids.shape[0], cpd), dtype=torch.float32, device=P.device)
+    if g.shape != (ids.shape[0], cpd) or not g.is_contiguous() or g.device != P.device or g.dtype != torch.float32:
+        raise RuntimeError(f"out must be a contiguous float32 [{ids.shape[0]}, {cpd}] tensor on {P.device}")
+    with _on(P.device):
+        check(lib.thb_eval_fused_backward_rows(C.byref(P.desc()), C.byref(plan.desc), ptr(plan.params), ptr(grad_out), cpd, ptr(row_map),
+                                               ptr(g), ids.shape[0], ptr(_gnet_workspace(P)), stream_ptr(P.device)), "thb_eval_fused_backward_rows")
+    return g
+
+
+def mse_workspace(device):
+    return torch.zeros(int(lib.thb_mse_workspace_bytes()), dtype=torch.uint8, device=device)
+
+
+def mse_grad(out, target, scale, grad_out, loss, workspace):
+    """loss[0] = scale * sum (out - target)^2, grad_out = 2 scale (out - target) in one pass (thb_mse_grad)."""
+    for t, name in ((out, "out"), (target, "target"), (grad_out, "grad_out")):
+        require_cuda(t, name, torch.float32)
+    if out.shape != target.shape or out.shape != grad_out.shape:
+        raise RuntimeError("out, target and grad_out must have the same shape")
+    with _on(out.device):
+        check(lib.thb_mse_grad(ptr(out), ptr(target), out.numel(), float(scale), ptr(grad_out), ptr(loss), ptr(workspace),
+                               stream_ptr(out.device)), "thb_mse_grad")
+    return loss
+
+
+def adam_rows(params, row_ids, grad_rows, exp_avg, exp_avg_sq, lr, betas, eps, step=0, step_dev=None, grad_scale=1.0):
+    """torch.optim.Adam's update on the rows `row_ids` of the dense parameter `params` (thb_adam_rows)."""
+    require_cuda(params, "params", torch.float32)
+    require_cuda(row_ids, "row_ids", torch.int32)
+    for t, name in ((grad_rows, "grad_rows"), (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq")):
+        require_cuda(t, name, torch.float32)
+        if t.shape != (row_ids.shape[0], params.shape[1]):
+            raise RuntimeError(f"{name} must be [{row_ids.shape[0]}, {params.shape[1]}]")
+    with _on(params.device):
+        check(lib.thb_adam_rows(ptr(params), ptr(row_ids), ptr(grad_rows), ptr(exp_avg), ptr(exp_avg_sq), row_ids.shape[0], params.shape[1],
+                                float(lr), float(betas[0]), float(betas[1]), float(eps), float(grad_scale), int(step), ptr(step_dev),
+                                stream_ptr(params.device)), "thb_adam_rows")
+    return params
 
 
 def _idx(t, name):
@@ -246,8 +334,9 @@ def eval_forward(ctrl_pts, Jm, PHI, cumsum):
         raise RuntimeError("Jm_array and tensor_prod must have the same length")
     n = cumsum.shape[0]
     out = torch.zeros((n, ctrl_pts.shape[1]), dtype=torch.float32, device=ctrl_pts.device)
-    check(lib.thb_eval_forward(ptr(ctrl_pts), ptr(Jm), _idx(Jm, "Jm_array"), ptr(PHI), ptr(cumsum), _idx(cumsum, "cumsum"), ptr(out), n,
-                               ctrl_pts.shape[1], stream_ptr(ctrl_pts.device)), "thb_eval_forward")
+    with _on(ctrl_pts.device):
+        check(lib.thb_eval_forward(ptr(ctrl_pts), ptr(Jm), _idx(Jm, "Jm_array"), ptr(PHI), ptr(cumsum), _idx(cumsum, "cumsum"), ptr(out), n,
+                                   ctrl_pts.shape[1], stream_ptr(ctrl_pts.device)), "thb_eval_forward")
     return out
 
 
@@ -263,8 +352,9 @@ def eval_backward(grad_output, ctrl_pts, Jm, PHI, cumsum):
     if grad_output.shape != (n, ctrl_pts.shape[1]):
         raise RuntimeError("grad_output must be [N, cp_dim]")
     g = torch.empty_like(ctrl_pts)
-    check(lib.thb_eval_backward(ptr(grad_output), ptr(Jm), _idx(Jm, "Jm_array"), ptr(PHI), ptr(cumsum), _idx(cumsum, "cumsum"), ptr(g), n,
-                                ctrl_pts.shape[0], ctrl_pts.shape[1], stream_ptr(ctrl_pts.device)), "thb_eval_backward")
+    with _on(ctrl_pts.device):
+        check(lib.thb_eval_backward(ptr(grad_output), ptr(Jm), _idx(Jm, "Jm_array"), ptr(PHI), ptr(cumsum), _idx(cumsum, "cumsum"), ptr(g), n,
+                                    ctrl_pts.shape[0], ctrl_pts.shape[1], stream_ptr(ctrl_pts.device)), "thb_eval_backward")
     return g
 
 
@@ -273,7 +363,8 @@ def find_spans(params1d, knots, degree):
     require_cuda(knots, "knots", torch.float32)
     n = params1d.shape[0]
     out = torch.empty(n, dtype=torch.int32, device=params1d.device)
-    check(lib.thb_find_spans(ptr(params1d), 1, n, ptr(knots), knots.shape[0], int(degree), ptr(out), stream_ptr(params1d.device)), "thb_find_spans")
+    with _on(params1d.device):
+        check(lib.thb_find_spans(ptr(params1d), 1, n, ptr(knots), knots.shape[0], int(degree), ptr(out), stream_ptr(params1d.device)), "thb_find_spans")
     return out
 
 
@@ -283,7 +374,8 @@ def basis_1d(params1d, knots, degree, derivs=False):
     n = params1d.shape[0]
     v = torch.empty((n, degree + 1), dtype=torch.float32, device=params1d.device)
     dv = torch.empty_like(v) if derivs else None
-    check(lib.thb_basis_1d(ptr(params1d), 1, n, ptr(knots), knots.shape[0], int(degree), ptr(v), ptr(dv), stream_ptr(params1d.device)), "thb_basis_1d")
+    with _on(params1d.device):
+        check(lib.thb_basis_1d(ptr(params1d), 1, n, ptr(knots), knots.shape[0], int(degree), ptr(v), ptr(dv), stream_ptr(params1d.device)), "thb_basis_1d")
     return (v, dv) if derivs else v
 
 

@@ -426,6 +426,22 @@ class PackedHierarchy:
         return self
 
     # ------------------------------------------------------------------------------------------
+    def active_rows(self):
+        """(active_ids int32 [n_active], row_map int32 [nCP]): the flat ids of the functions that are a support of some
+        active cell -- the only rows of ctrl_pts the evaluation reads and the only ones that ever receive a gradient --
+        in ascending order, and the inverse map (-1 elsewhere).  Cached; device tensors."""
+        c = getattr(self, "_active_rows", None)
+        if c is None:
+            ids = torch.unique(self.supp_jm.to(torch.int64))
+            row_map = torch.full((self.nCP,), -1, dtype=torch.int32, device=self.device)
+            row_map[ids] = torch.arange(ids.shape[0], dtype=torch.int32, device=self.device)
+            c = self._active_rows = (ids.to(torch.int32), row_map)
+        return c
+
+    @property
+    def n_active(self):
+        return int(self.active_rows()[0].shape[0])
+
     def nbytes(self):
         ts = [self.knots, self.cell_slot, self.cellinfo, self.dmask, self.supp_jm, self.tiles] + [t for t in (getattr(self, 'sep_vec', None), getattr(self, 'full_tiles', None)) if t is not None] + ([self.finest_slot] if self.finest_slot is not None else [])
         return sum(t.numel() * t.element_size() for t in ts)

@@ -122,12 +122,22 @@ class THB_fused_module(torch.nn.Module):
         self.cellnet = cellnet
         self.perm = None
         if plan_order_rows:
-            if not cellnet:
-                raise RuntimeError("plan_order_rows needs the local-net formulation (cellnet=True)")
-            self.perm = self.plan.caller_index()
-            if self.perm.numel() != self.plan.n:
-                raise RuntimeError("plan_order_rows needs every point inside the domain")
-            self.plan.set_rows_in_plan_order(True)
+            self.use_plan_order_rows()
+
+    def points_inside(self):
+        """number of the plan's points that lie inside the domain (synchronises once)"""
+        return int(self.plan.counters[2])
+
+    def use_plan_order_rows(self):
+        """Switches the rows of the output / incoming gradient to the plan's cell order (see __init__)."""
+        if not self.cellnet:
+            raise RuntimeError("plan_order_rows needs the local-net formulation (cellnet=True)")
+        perm = self.plan.caller_index()
+        if perm.numel() != self.plan.n:
+            raise RuntimeError("plan_order_rows needs every point inside the domain")
+        self.perm = perm
+        self.plan.set_rows_in_plan_order(True)
+        return self
 
     def forward(self, ctrl_pts):
         return THBFusedEval.apply(ctrl_pts, self)
