@@ -137,6 +137,11 @@ THB_API int thb_find_spans(const float* params, int64_t stride, int64_t npoints,
 THB_API int thb_basis_1d(const float* params, int64_t stride, int64_t npoints, const float* knots, int nknots, int degree,
                  float* values, float* derivs, void* stream);
 
+/* compute_tensor_product (THB/bspline_funcs.py:54-59): outer product of 2 or 3 vectors, batched:
+ * out[q][i][j][k] = a[q][i] * b[q][j] * c[q][k] for q < batch (c == NULL and nc == 1: the 2-D form, out[q][i][j]). */
+THB_API int thb_tensor_product(const float* a, const float* b, const float* c, int64_t batch, int na, int nb, int nc, float* out,
+                       void* stream);
+
 /* ---- active-cell lookup: compute_active_span (THB/core.py:157-189) ----------------------------------------
  * For every point the finest-level span per dimension, then the finest level whose cell is active.
  * slot[i] = slot id of that cell (-1 for points outside the domain); num_supp[i] (nullable) = its number of

@@ -41,6 +41,15 @@ def num_threads():
     return int(lib().oracle_num_threads())
 
 
+def use_all_host_threads():
+    """OpenMP threads = the CPUs this process may run on, whatever OMP_NUM_THREADS a launcher exported (torchrun sets 1)."""
+    import os
+
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().oracle_set_threads(C.c_int(n))
+    return num_threads()
+
+
 def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
@@ -118,3 +127,70 @@ def eval_backward(go, cp_shape, Jm, phi, cumsum):
     g = np.zeros(cp_shape, dtype=np.float32)
     lib().oracle_eval_backward(_p(go), _p(Jm), _p(phi), _p(cumsum), _p(g), len(cumsum), cp_shape[0], cp_shape[1])
     return g
+
+
+class OracleDirect(C.Structure):
+    _fields_ = [
+        ("ndim", C.c_int32), ("nlevels", C.c_int32), ("degree", C.c_int32 * 3),
+        ("nfn", (C.c_int32 * 3) * MAXL), ("ncell", (C.c_int32 * 3) * MAXL), ("nk", (C.c_int32 * 3) * MAXL),
+        ("knots", (C.c_void_p * 3) * MAXL), ("cells", C.c_void_p * MAXL), ("fns", C.c_void_p * MAXL),
+        ("coeff", (C.c_void_p * 3) * MAXL), ("fn_off", C.c_int64 * MAXL),
+    ]
+
+
+class DirectTables:
+    """Table-free evaluator in C (oracle_direct_eval): same inputs and results as thb_oracle.DirectEvaluator.point,
+    for 1e4..1e6 points.  knotvectors / cells / fns: per-level dicts as in the reference's Space; Coeff[l][k] is the
+    level l -> l+1 matrix [nfn_l, nfn_{l+1}] of dimension k (thb_oracle.knot_insertion_matrix(...).T)."""
+
+    def __init__(self, knotvectors, degrees, cells, fns, Coeff, knots_as_f32=True):
+        L = max(knotvectors.keys())
+        d = len(degrees)
+        s = OracleDirect()
+        s.ndim, s.nlevels = d, L + 1
+        self.keep = []
+        off = 0
+        for k in range(3):
+            s.degree[k] = int(degrees[k]) if k < d else 0
+        for l in range(L + 1):
+            s.fn_off[l] = off
+            off += int(np.prod(fns[l].shape))
+            c8 = np.ascontiguousarray((np.asarray(cells[l]) == 1).astype(np.uint8))
+            f8 = np.ascontiguousarray((np.asarray(fns[l]) == 1).astype(np.uint8))
+            self.keep += [c8, f8]
+            s.cells[l], s.fns[l] = c8.ctypes.data, f8.ctypes.data
+            for k in range(d):
+                U = np.asarray(knotvectors[l][k])
+                # the product's canonical inputs are float32 (SURVEY Q11): spans are decided on the f32 knot values
+                U = np.ascontiguousarray(U.astype(np.float32).astype(np.float64) if knots_as_f32 else U.astype(np.float64))
+                self.keep.append(U)
+                s.knots[l][k], s.nk[l][k] = U.ctypes.data, len(U)
+                s.nfn[l][k], s.ncell[l][k] = fns[l].shape[k], cells[l].shape[k]
+                if l < L:
+                    M = np.ascontiguousarray(np.asarray(Coeff[l][k], dtype=np.float64))
+                    assert M.shape == (fns[l].shape[k], fns[l + 1].shape[k])
+                    self.keep.append(M)
+                    s.coeff[l][k] = M.ctypes.data
+        self.s, self.d = s, d
+        fn = lib().oracle_direct_eval
+        fn.restype = C.c_int64
+        fn.argtypes = [C.POINTER(OracleDirect), C.c_void_p, C.c_int64, C.c_int] + [C.c_void_p] * 6
+
+    def eval(self, x, max_supp=256, want_grad=False):
+        """-> dict(lev [n], cell [n,3], nsupp [n], jm [n,max_supp], phi [n,max_supp](, dphi [n,max_supp,3]))"""
+        x = np.ascontiguousarray(np.asarray(x, dtype=np.float64))
+        n = len(x)
+        lev = np.empty(n, np.int32)
+        cell = np.empty((n, 3), np.int32)
+        ns = np.empty(n, np.int32)
+        jm = np.zeros((n, max_supp), np.int64)
+        phi = np.zeros((n, max_supp), np.float64)
+        dphi = np.zeros((n, max_supp, 3), np.float64) if want_grad else None
+        worst = lib().oracle_direct_eval(C.byref(self.s), _p(x), n, max_supp, _p(lev), _p(cell), _p(ns), _p(jm), _p(phi),
+                                         _p(dphi) if dphi is not None else None)
+        if worst > max_supp:
+            raise RuntimeError(f"max_supp too small: {worst}")
+        r = dict(lev=lev, cell=cell, nsupp=ns, jm=jm, phi=phi)
+        if want_grad:
+            r["dphi"] = dphi
+        return r

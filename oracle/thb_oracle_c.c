@@ -25,6 +25,15 @@
 #define MAXL 8
 #define MAXD 6
 
+/* launchers such as torchrun export OMP_NUM_THREADS=1: the benchmark's CPU baseline asks for the host's cores explicitly */
+void oracle_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int oracle_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();
@@ -178,4 +187,139 @@ int64_t oracle_thb_eval(const oracle_space* sp, const float* params, int64_t n, 
         if (out) for (int k = 0; k < cpd; ++k) out[i * cpd + k] = acc[k];
     }
     return inside;
+}
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Table-free evaluator: the reference's (single-level-)truncated functions from their DEFINITION,
+ *     trunc(B^l_i)(x) = sum_{j child of i, fns[l+1][j] != 1}  prod_k Coeff[l][k][i_k, j_k] * B^{l+1}_j(x)
+ * (for l == L the function itself), i.e. compute_refinement_operators + finest-level evaluation in exact arithmetic
+ * [THB/core.py:43-114, 232-268] without the dense tables -- the C form of oracle/thb_oracle.py: DirectEvaluator.point,
+ * so that the packed tables of the product can be pinned at 1e4..1e5 points on the BASELINE spaces.
+ * Cell location: finest level downwards, first level whose cell is active [THB/core.py:165-187].
+ * Supports: own level first, then ancestors via cell // 2, window in C order, fns == 1 only [THB/core.py:424-449]. */
+typedef struct {
+    int32_t ndim, nlevels, degree[3];
+    int32_t nfn[MAXL][3], ncell[MAXL][3], nk[MAXL][3];
+    const double* knots[MAXL][3];
+    const uint8_t* cells[MAXL];  /* [ncell] C order, 1 = active */
+    const uint8_t* fns[MAXL];    /* [nfn] C order, 1 = active */
+    const double* coeff[MAXL][3]; /* level l -> l+1, [nfn[l][k]][nfn[l+1][k]] row major (l < L) */
+    int64_t fn_off[MAXL];
+} oracle_direct;
+
+static int span_right_d(const double* U, int nk, int p, double u) {
+    int lo = 0, hi = nk;
+    while (lo < hi) {
+        int mid = (lo + hi) / 2;
+        if (U[mid] <= u) lo = mid + 1; else hi = mid;
+    }
+    int n = nk - p - 1, idx = lo - 1;
+    if (idx > n) idx = n;
+    if (u == U[nk - 1]) idx = n - 1;
+    return idx;
+}
+
+/* x: [n][d] doubles.  Outputs per point: lev, cell[3], nsupp, jm[max_supp], phi[max_supp], dphi[max_supp][3] (may be NULL).
+ * Returns the largest support count met (> max_supp means the buffers were too small for some points: nsupp is still
+ * right, the lists are cut). */
+int64_t oracle_direct_eval(const oracle_direct* sp, const double* x, int64_t n, int max_supp, int32_t* lev_out, int32_t* cell_out,
+                           int32_t* nsupp, int64_t* jm, double* phi, double* dphi) {
+    const int d = sp->ndim, L = sp->nlevels - 1;
+    int64_t worst = 0;
+#pragma omp parallel for schedule(dynamic, 256) reduction(max : worst)
+    for (int64_t i = 0; i < n; ++i) {
+        const double* xi = x + i * d;
+        int lev = -1, c[3] = {0, 0, 0};
+        for (int l = L; l >= 0 && lev < 0; --l) {
+            int ok = 1, cc[3] = {0, 0, 0};
+            for (int k = 0; k < d; ++k) {
+                cc[k] = span_right_d(sp->knots[l][k], sp->nk[l][k], sp->degree[k], xi[k]) - sp->degree[k];
+                if (cc[k] < 0 || cc[k] >= sp->ncell[l][k]) ok = 0;
+            }
+            if (!ok) continue;
+            int64_t lin = cc[0];
+            for (int k = 1; k < d; ++k) lin = lin * sp->ncell[l][k] + cc[k];
+            if (sp->cells[l][lin] == 1) { lev = l; c[0] = cc[0]; c[1] = cc[1]; c[2] = cc[2]; }
+        }
+        lev_out[i] = lev;
+        for (int k = 0; k < 3; ++k) cell_out[i * 3 + k] = c[k];
+        nsupp[i] = 0;
+        if (lev < 0) continue;
+        /* 1-D values / derivatives at every level that is needed (levels lev+1 .. 1 for truncated functions, L for own) */
+        int start[MAXL][3];
+        double N[MAXL][3][MAXD + 1], dN[MAXL][3][MAXD + 1];
+        int have[MAXL];
+        for (int l = 0; l <= L; ++l) have[l] = 0;
+        int s = 0, cw[3] = {c[0], c[1], c[2]};
+        const int w0 = sp->degree[0] + 1, w1 = sp->degree[1] + 1, w2 = d == 3 ? sp->degree[2] + 1 : 1;
+        for (int fl = lev; fl >= 0; --fl) {
+            const int el = fl == L ? fl : fl + 1;
+            if (!have[el]) {
+                for (int k = 0; k < d; ++k) {
+                    const int p = sp->degree[k];
+                    const int sp_ = span_right_d(sp->knots[el][k], sp->nk[el][k], p, xi[k]);
+                    start[el][k] = sp_ - p;
+                    oracle_basis_funs(sp_, xi[k], p, sp->knots[el][k], N[el][k], dN[el][k]);
+                }
+                have[el] = 1;
+            }
+            for (int a = 0; a < w0; ++a)
+                for (int b = 0; b < w1; ++b)
+                    for (int e = 0; e < w2; ++e) {
+                        int fn[3] = {cw[0] + a, cw[1] + b, cw[2] + e};
+                        int64_t lin = fn[0];
+                        for (int k = 1; k < d; ++k) lin = lin * sp->nfn[fl][k] + fn[k];
+                        if (sp->fns[fl][lin] != 1) continue;
+                        double v = 0.0, g[3] = {0.0, 0.0, 0.0};
+                        if (fl == L) {
+                            int ok = 1, idx[3] = {0, 0, 0};
+                            for (int k = 0; k < d; ++k) {
+                                idx[k] = fn[k] - start[el][k];
+                                if (idx[k] < 0 || idx[k] > sp->degree[k]) ok = 0;
+                            }
+                            if (ok) {
+                                v = 1.0;
+                                for (int k = 0; k < d; ++k) v *= N[el][k][idx[k]];
+                                for (int j = 0; j < d; ++j) {
+                                    double t = 1.0;
+                                    for (int k = 0; k < d; ++k) t *= (k == j ? dN[el][k][idx[k]] : N[el][k][idx[k]]);
+                                    g[j] = t;
+                                }
+                            }
+                        } else {
+                            for (int ta = 0; ta < w0; ++ta)
+                                for (int tb = 0; tb < w1; ++tb)
+                                    for (int te = 0; te < w2; ++te) {
+                                        const int t[3] = {ta, tb, te};
+                                        int64_t cl = start[el][0] + ta;
+                                        double cwt = 1.0;
+                                        for (int k = 0; k < d; ++k) {
+                                            const int child = start[el][k] + t[k];
+                                            if (k) cl = cl * sp->nfn[el][k] + child;
+                                            cwt *= sp->coeff[fl][k][(int64_t)fn[k] * sp->nfn[el][k] + child];
+                                        }
+                                        if (sp->fns[el][cl] == 1 || cwt == 0.0) continue;
+                                        double tv = cwt;
+                                        for (int k = 0; k < d; ++k) tv *= N[el][k][t[k]];
+                                        v += tv;
+                                        for (int j = 0; j < d; ++j) {
+                                            double tg = cwt;
+                                            for (int k = 0; k < d; ++k) tg *= (k == j ? dN[el][k][t[k]] : N[el][k][t[k]]);
+                                            g[j] += tg;
+                                        }
+                                    }
+                        }
+                        if (s < max_supp) {
+                            jm[i * max_supp + s] = sp->fn_off[fl] + lin;
+                            phi[i * max_supp + s] = v;
+                            if (dphi) for (int j = 0; j < 3; ++j) dphi[(i * max_supp + s) * 3 + j] = g[j];
+                        }
+                        ++s;
+                    }
+            for (int k = 0; k < 3; ++k) cw[k] /= 2;
+        }
+        nsupp[i] = s;
+        if (s > worst) worst = s;
+    }
+    return worst;
 }

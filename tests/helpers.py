@@ -103,3 +103,51 @@ def host_tables_from_packed(P):
                                [list(P.sh_cells[l]) for l in range(P.nlevels)], P.cell_slot_off,
                                P.knots.cpu().numpy(), P.cell_slot.cpu().numpy(), P.cellinfo.cpu().numpy(),
                                P.dmask.cpu().numpy().view(np.uint64), P.supp_jm.cpu().numpy(), P.tiles.cpu().numpy())
+
+
+def direct_tables(sp):
+    """The table-free C evaluator (oracle_direct_eval) of a product / oracle Space: truncated functions from their
+    definition, refinement matrices by knot insertion -- nothing of the product's packed tables is used."""
+    from oracle import c_oracle
+
+    L = max(sp.knotvectors.keys())
+    d = len(sp.degrees)
+    Coeff = {l: {k: O.knot_insertion_matrix(sp.knotvectors[l][k], sp.knotvectors[l + 1][k], sp.degrees[k]).T for k in range(d)} for l in range(L)}
+    return c_oracle.DirectTables(sp.knotvectors, sp.degrees, sp.cells, sp.fns, Coeff)
+
+
+def interface_points(n, ndim, seed, lo=0.12, hi=0.88):
+    """Random float32 points, half of them within a few finest cells of the faces of the nested refinement boxes of
+    configs.cubic3d_space (where truncation and full tiles live), the rest uniform in [lo, hi]^d."""
+    rng = np.random.default_rng(seed)
+    pts = lo + (hi - lo) * rng.random((n, ndim))
+    faces = np.array([3, 13]) / 16.0, np.array([10, 22]) / 32.0, np.array([24, 40]) / 64.0, np.array([54, 74]) / 128.0
+    m = n // 2
+    for i in range(m):
+        f = faces[rng.integers(len(faces))]
+        k = rng.integers(ndim)
+        pts[i, k] = f[rng.integers(2)] + rng.normal() * 0.01
+    return np.clip(pts, 1e-4, 1 - 1e-4).astype(np.float32)
+
+
+def compare_with_direct(dt, prm, slot_info, Jm, PHI, offsets, tol, dPHI=None):
+    """Levels / cells / support ids bit-exact and PHI (and gradient channels) within tol against the table-free evaluator.
+    slot_info: cellinfo rows of the points [n, >=6]; Jm/PHI flat at offsets."""
+    r = dt.eval(prm.astype(np.float64), max_supp=int(slot_info[:, 5].max()), want_grad=dPHI is not None)
+    d = dt.d
+    assert np.array_equal(r["lev"], slot_info[:, 0])
+    assert np.array_equal(r["cell"][:, :d], slot_info[:, 1:1 + d])
+    assert np.array_equal(r["nsupp"], slot_info[:, 5])
+    n, ms = r["jm"].shape
+    col = np.arange(ms)[None, :]
+    valid = col < r["nsupp"][:, None]
+    flat = (offsets[:, None] + col)[valid]
+    assert np.array_equal(Jm[flat], r["jm"][valid])
+    err = rel_err(PHI[flat], r["phi"][valid]).max()
+    assert err <= tol, err
+    if dPHI is not None:
+        for k in range(d):
+            ref = r["dphi"][..., k][valid]
+            e = np.abs(dPHI[k][flat] - ref).max() / np.abs(ref).max()
+            assert e <= tol, (k, e)
+    return r

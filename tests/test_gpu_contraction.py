@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import GOLDEN
+from helpers import GOLDEN, rel_err
 from oracle import thb_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -87,3 +87,67 @@ def test_autograd_module_and_cpp_names():
     b2 = THB_eval.cpp_backward(torch.from_numpy(c["a_grad_out"]), torch.from_numpy(c["a_cp"]), torch.from_numpy(c["a_Jm"]), torch.from_numpy(c["a_phi"]),
                                torch.from_numpy(c["a_cumsum"]))
     assert _close(b2.numpy(), c["a_bwd"])
+
+
+def test_evaluate_and_prepare_data_for_evaluation_match_the_golden_contraction():
+    """a16: prepare_data_for_evaluation + Evaluate [THB/torch_funcs.py:83-128] on the golden block3d space against the
+    oracle contraction (values, gradient w.r.t. ctrl_pts and -- like the reference's pure-torch Evaluate -- w.r.t. PHI);
+    CUDA tensors directly and CPU tensors staged through the GPU."""
+    from helpers import load_golden, product_space_from_golden
+    from oracle import thb_oracle as O
+    from thb_diff_b200 import core
+    from thb_diff_b200.torch_funcs import Evaluate, prepare_data_for_evaluation
+
+    g = load_golden("block3d")
+    h = product_space_from_golden(g)
+    ac = core.compute_active_cells_active_supp(h.cells, h.fns, h.degrees)
+    supp, ns = core.compute_active_span(g["params"], h.knotvectors, h.cells, h.degrees, ac)
+    rng = np.random.default_rng(3)
+    L = max(h.sh_fns.keys())
+    cp_dict = {lev: rng.standard_normal(tuple(h.sh_fns[lev]) + (3,)).astype(np.float32) for lev in range(L + 1)}
+    cp_flat = np.concatenate([cp_dict[lev].reshape(-1, 3) for lev in range(L + 1)])
+    cs = np.cumsum(g["num_supp"])
+    ref = O.eval_forward(cp_flat, g["Jm"], g["PHI"], cs)
+    go = rng.standard_normal(ref.shape).astype(np.float32)
+    refg = O.eval_backward(go, cp_flat.shape, g["Jm"], g["PHI"], cs)
+    seg_np = np.repeat(np.arange(len(cs)), g["num_supp"])
+    ref_gphi = (go[seg_np] * cp_flat[g["Jm"]]).sum(1)
+    # the reference's list-of-spans form and the PointSupports form give the same packing
+    spans_list = [(int(l), tuple(int(v) for v in c)) for l, c in zip(g["span_level"], g["span_cell"])]
+    for spans in (supp, spans_list):
+        for device in ("cuda", "cpu"):
+            cp, Jm, PHI, seg, n = prepare_data_for_evaluation(g["PHI"], spans, g["num_supp"], cp_dict, ac, h.sh_fns, device)
+            assert n == len(cs) and PHI.shape == (len(g["PHI"]), 1) and seg.shape == (len(g["PHI"]), 3)
+            assert np.array_equal(Jm.cpu().numpy(), g["Jm"]) and np.array_equal(seg[:, 0].cpu().numpy(), seg_np)
+            assert cp.device.type == device and Jm.device.type == device
+            a = cp.clone().requires_grad_(True)
+            phi = PHI.clone().requires_grad_(True)
+            out = Evaluate(a, Jm, phi, seg, n, device)
+            assert out.device.type == device
+            assert rel_err(out.detach().cpu().numpy(), ref, scale=np.abs(ref).max()).max() <= TOL
+            (out * torch.from_numpy(go).to(device)).sum().backward()
+            assert rel_err(a.grad.cpu().numpy(), refg, scale=np.abs(refg).max()).max() <= TOL
+            assert rel_err(phi.grad.cpu().numpy()[:, 0], ref_gphi, scale=np.abs(ref_gphi).max()).max() <= TOL
+
+
+def test_compute_tensor_product_kernel():
+    """a7: compute_tensor_product [THB/bspline_funcs.py:54-59] = einsum('i,j->ij') / einsum('i,j,k->ijk'), single and batched."""
+    from thb_diff_b200 import bspline_funcs as B
+
+    rng = np.random.default_rng(0)
+    a, b, c = rng.standard_normal(3).astype(np.float32), rng.standard_normal(4).astype(np.float32), rng.standard_normal(5).astype(np.float32)
+    r2 = B.compute_tensor_product([a, b])
+    r3 = B.compute_tensor_product([torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda(), torch.from_numpy(c).cuda()])
+    assert r2.device.type == "cpu" and r3.is_cuda
+    assert np.array_equal(r2.numpy(), np.einsum("i,j->ij", a, b))
+    assert np.allclose(r3.cpu().numpy(), np.einsum("i,j,k->ijk", a, b, c), rtol=1e-6, atol=0)
+    A, Bm, Cm = (torch.from_numpy(rng.standard_normal((1000, n)).astype(np.float32)).cuda() for n in (4, 3, 4))
+    rb = B.compute_tensor_product([A, Bm, Cm])
+    assert rb.shape == (1000, 4, 3, 4)
+    assert torch.allclose(rb, torch.einsum("qi,qj,qk->qijk", A, Bm, Cm), rtol=1e-6, atol=0)
+    # the per-point tensor product of the path: basis values of a point in each direction (THB/core.py:652-677)
+    U = np.array([0, 0, 0, 0, 0.25, 0.5, 0.75, 1, 1, 1, 1.0], dtype=np.float32)
+    u = np.array([0.3, 0.6, 0.9], dtype=np.float32)
+    N = [B.basis_fns_vmap(u[k:k + 1], U, 3)[0] for k in range(3)]
+    tp = B.compute_tensor_product(N)
+    assert abs(float(tp.sum()) - 1.0) < 1e-6

@@ -111,3 +111,76 @@ def test_recursive_truncation_option():
             assert res["single"][1] > 0.3   # the reference's behaviour on this non-graded space
     with pytest.raises(ValueError):
         PackedHierarchy.from_space(h, device="cpu", truncation="both")
+
+
+@pytest.mark.parametrize("name", IDENTITY_OK)
+def test_direct_c_evaluator_reproduces_reference_goldens(name):
+    """oracle_direct_eval (table-free, C) against the outputs of the reference itself: levels, cells, Jm bit-exact, PHI."""
+    from helpers import direct_tables
+
+    g = load_golden(name)
+    sp = oracle_space_from_golden_(g)
+    dt = direct_tables(sp)
+    dt_exact = c_oracle.DirectTables(sp.knotvectors, sp.degrees, sp.cells, sp.fns, dt_coeff(sp), knots_as_f32=False)
+    r = dt_exact.eval(g["params"].astype(np.float64), max_supp=int(g["num_supp"].max()))
+    assert np.array_equal(r["lev"], g["span_level"]) and np.array_equal(r["cell"][:, :sp.ndim], g["span_cell"])
+    assert np.array_equal(r["nsupp"], g["num_supp"])
+    valid = np.arange(r["jm"].shape[1])[None, :] < r["nsupp"][:, None]
+    assert np.array_equal(r["jm"][valid], g["Jm"])
+    assert np.abs(r["phi"][valid] - g["PHI"]).max() < 1e-13
+    # f32-rounded knots (what the product sees) move PHI by f32 rounding only
+    r32 = dt.eval(g["params"].astype(np.float64), max_supp=int(g["num_supp"].max()))
+    assert np.array_equal(r32["jm"][valid], g["Jm"]) and np.abs(r32["phi"][valid] - g["PHI"]).max() < 5e-6
+
+
+def oracle_space_from_golden_(g):
+    from helpers import oracle_space_from_golden
+
+    return oracle_space_from_golden(g)
+
+
+def dt_coeff(sp):
+    L = max(sp.knotvectors.keys())
+    return {l: {k: O.knot_insertion_matrix(sp.knotvectors[l][k], sp.knotvectors[l + 1][k], sp.degrees[k]).T for k in range(sp.ndim)}
+            for l in range(L)}
+
+
+def test_direct_c_evaluator_equals_the_python_one_with_gradients():
+    g = load_golden("block3d")
+    sp = oracle_space_from_golden_(g)
+    Coeff = dt_coeff(sp)
+    de = O.DirectEvaluator(sp.knotvectors, sp.degrees, sp.cells, sp.fns, Coeff)
+    dt = c_oracle.DirectTables(sp.knotvectors, sp.degrees, sp.cells, sp.fns, Coeff, knots_as_f32=False)
+    x = np.random.default_rng(7).random((40, 3))
+    r = dt.eval(x, max_supp=256, want_grad=True)
+    for i in range(len(x)):
+        lev, c, jm, phi, dphi = de.point(x[i], want_grad=True)
+        n = len(jm)
+        assert r["lev"][i] == lev and tuple(r["cell"][i]) == tuple(c) and r["nsupp"][i] == n
+        assert np.array_equal(r["jm"][i, :n], jm)
+        assert np.abs(r["phi"][i, :n] - phi).max() < 1e-14 and np.abs(r["dphi"][i, :n] - dphi).max() < 1e-11
+
+
+@pytest.mark.parametrize("levels", [4, 5])
+def test_packed_tables_of_the_bench_spaces_against_the_table_free_evaluator(levels):
+    """BASELINE config 3 (4 levels) and config 5 (5 levels): the product's packed tables (host builder, evaluated by the C
+    oracle) against the definition of the truncated functions at 2e4 points concentrated on the level interfaces --
+    cells / support ids bit-exact, PHI and the three gradient channels within 1e-5."""
+    from helpers import compare_with_direct, direct_tables, interface_points
+    from thb_diff_b200 import configs
+    from thb_diff_b200.packed import PackedHierarchy
+
+    sp = configs.cubic3d_space(active_levels=levels)
+    P = PackedHierarchy.from_space(sp, device="cpu")
+    ht = host_tables_from_packed(P)
+    prm = interface_points(20000, 3, seed=levels)
+    r0 = ht.eval(prm, None)
+    info = P.cellinfo_host[r0["slot"]]
+    S = info[:, 5].astype(np.int64)
+    off = np.cumsum(S) - S
+    nnz = int(S.sum())
+    phi = ht.eval(prm, None, want_phi=True, offsets=off, nnz=nnz)["phi"]
+    dphi = [ht.eval(prm, None, mode=1 << k, want_phi=True, offsets=off, nnz=nnz)["phi"] for k in range(3)]
+    Jm = np.concatenate([P.supp_jm.numpy()[info[i, 4]: info[i, 4] + info[i, 5]] for i in range(len(prm))]).astype(np.int64)
+    r = compare_with_direct(direct_tables(sp), prm, info, Jm, phi, off, 1e-5, dPHI=dphi)
+    assert set(r["lev"].tolist()) == set(range(levels))

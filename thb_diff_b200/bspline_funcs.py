@@ -82,11 +82,13 @@ def basisFun(i, u, p, U):
 
 
 def compute_tensor_product(args):
-    """[THB/bspline_funcs.py:54-59] outer product of 2 or 3 vectors (torch)."""
-    a = [torch.as_tensor(x) for x in args]
-    if len(a) == 2:
-        return torch.einsum("i,j->ij", *a)
-    return torch.einsum("i,j,k->ijk", *a)
+    """[THB/bspline_funcs.py:54-59] outer product of 2 or 3 vectors ("i,j->ij" / "i,j,k->ijk"), on the GPU
+    (thb_tensor_product); [B, n] batches of vectors give [B, ...] batches of products.  numpy / CPU inputs are staged
+    through the device and come back on the CPU."""
+    a = [torch.as_tensor(np.asarray(x)) if not isinstance(x, torch.Tensor) else x for x in args]
+    src = a[0].device
+    out = engine.tensor_product([x.to(device="cuda", dtype=torch.float32) for x in a])
+    return out if src.type == "cuda" else out.to(src)
 
 
 def basisFun_jax(param, knotvector, degree):

@@ -599,6 +599,21 @@ __global__ void __launch_bounds__(256) k_plan_scatter(const int32_t* __restrict_
     }
 }
 
+// compute_tensor_product (THB/bspline_funcs.py:54-59): out[b][i][j][k] = a[b][i] * bb[b][j] * c[b][k] for a batch of vector
+// triples (nc == 1 and c == nullptr for the 2-D form); one thread per output entry, coalesced stores
+__global__ void __launch_bounds__(256) k_tensor_product(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
+                                                        int64_t batch, int na, int nb, int nc, float* __restrict__ out) {
+    const int64_t per = (int64_t)na * nb * nc, tot = batch * per;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t q = e / per;
+        const int r = (int)(e - q * per);
+        const int k = r % nc, j = (r / nc) % nb, i = r / (nc * nb);
+        float v = __ldg(a + q * na + i) * __ldg(b + q * nb + j);
+        if (c) v *= __ldg(c + q * nc + k);
+        out[e] = v;
+    }
+}
+
 int grid_for(int64_t n, int block, int per_sm) {
     int64_t want = (n + block - 1) / block;
     int64_t cap = (int64_t)thb_num_sms() * per_sm;
@@ -633,6 +648,17 @@ extern "C" int thb_basis_1d(const float* params, int64_t stride, int64_t npoints
     if (npoints == 0) return THB_OK;
     THB_REQUIRE(params && knots && values && stride >= 1, "thb_basis_1d: null pointer");
     k_basis_1d<<<grid_for(npoints, 256, 16), 256, 0, (cudaStream_t)stream>>>(params, stride, npoints, knots, nknots, degree, values, derivs);
+    THB_LAUNCHED();
+    return THB_OK;
+}
+
+extern "C" int thb_tensor_product(const float* a, const float* b, const float* c, int64_t batch, int na, int nb, int nc, float* out,
+                                  void* stream) {
+    THB_REQUIRE(batch >= 0 && na >= 1 && nb >= 1 && nc >= 1, "thb_tensor_product: bad sizes");
+    THB_REQUIRE(c || nc == 1, "thb_tensor_product: nc > 1 needs the third factor");
+    if (batch == 0) return THB_OK;
+    THB_REQUIRE(a && b && out, "thb_tensor_product: null pointer");
+    k_tensor_product<<<grid_for(batch * na * nb * nc, 256, 16), 256, 0, (cudaStream_t)stream>>>(a, b, c, batch, na, nb, nc, out);
     THB_LAUNCHED();
     return THB_OK;
 }

@@ -379,6 +379,23 @@ def basis_1d(params1d, knots, degree, derivs=False):
     return (v, dv) if derivs else v
 
 
+def tensor_product(vectors):
+    """Outer product of 2 or 3 vectors, or of batches of them ([B, n_k] each): thb_tensor_product."""
+    v = [require_cuda(x.contiguous(), "factor", torch.float32) for x in vectors]
+    if len(v) not in (2, 3) or any(x.dim() != v[0].dim() or x.dim() not in (1, 2) for x in v):
+        raise RuntimeError("compute_tensor_product takes 2 or 3 vectors (or [B, n] batches of vectors)")
+    batched = v[0].dim() == 2
+    B = v[0].shape[0] if batched else 1
+    if batched and any(x.shape[0] != B for x in v):
+        raise RuntimeError("batch sizes differ")
+    n = [x.shape[-1] for x in v]
+    out = torch.empty(([B] if batched else []) + n, dtype=torch.float32, device=v[0].device)
+    with _on(v[0].device):
+        check(lib.thb_tensor_product(ptr(v[0]), ptr(v[1]), ptr(v[2]) if len(v) == 3 else None, B, n[0], n[1], n[2] if len(v) == 3 else 1,
+                                     ptr(out), stream_ptr(v[0].device)), "thb_tensor_product")
+    return out
+
+
 def fma_peak(variant, iters=4096, repeats=5):
     """Measured FP32 FMA throughput (TFLOP/s) of the running GPU -- the FP32 roofline denominator."""
     sink = torch.zeros(4, dtype=torch.float32, device="cuda")

@@ -18,7 +18,7 @@ class THBEval(torch.autograd.Function):
     def forward(ctx, ctrl_pts, Jm_array, tensor_prod, num_supp_bs_cumsum, device):
         ctx.save_for_backward(ctrl_pts, Jm_array, tensor_prod, num_supp_bs_cumsum)
         ctx.device = device
-        if device == "cuda" or (isinstance(device, torch.device) and device.type == "cuda"):
+        if _is_cuda(device):
             return THB_eval.forward(ctrl_pts, Jm_array, tensor_prod, num_supp_bs_cumsum)
         return THB_eval.cpp_forward(ctrl_pts, Jm_array, tensor_prod, num_supp_bs_cumsum)
 
@@ -26,11 +26,25 @@ class THBEval(torch.autograd.Function):
     def backward(ctx, grad_output):
         ctrl_pts, Jm_array, tensor_prod, num_supp_bs_cumsum = ctx.saved_tensors
         device = ctx.device
-        if device == "cuda" or (isinstance(device, torch.device) and device.type == "cuda"):
-            g = THB_eval.backward(grad_output, ctrl_pts, Jm_array, tensor_prod, num_supp_bs_cumsum)
-        else:
-            g = THB_eval.cpp_backward(grad_output, ctrl_pts, Jm_array, tensor_prod, num_supp_bs_cumsum)
-        return g, None, None, None, None
+        g = None
+        if ctx.needs_input_grad[0]:
+            if _is_cuda(device):
+                g = THB_eval.backward(grad_output, ctrl_pts, Jm_array, tensor_prod, num_supp_bs_cumsum)
+            else:
+                g = THB_eval.cpp_backward(grad_output, ctrl_pts, Jm_array, tensor_prod, num_supp_bs_cumsum)
+        g_phi = None
+        if ctx.needs_input_grad[2]:
+            # the reference's THBEval has no such gradient; its pure-torch Evaluate does (autograd through
+            # ctrl_pts[Jm] * PHI): d out / d PHI_j = <grad_out[point of j], ctrl_pts[Jm_j]>
+            n = num_supp_bs_cumsum.shape[0]
+            lengths = torch.diff(num_supp_bs_cumsum, prepend=num_supp_bs_cumsum.new_zeros(1))
+            seg = torch.repeat_interleave(torch.arange(n, device=lengths.device), lengths)
+            g_phi = (grad_output[seg.to(grad_output.device)] * ctrl_pts[Jm_array.long()]).sum(1).to(tensor_prod.dtype)
+        return g, None, g_phi, None, None
+
+
+def _is_cuda(device):
+    return device == "cuda" or (isinstance(device, str) and device.startswith("cuda")) or (isinstance(device, torch.device) and device.type == "cuda")
 
 
 class THB_nn_module(torch.nn.Module):
@@ -59,9 +73,9 @@ def prepare_data_for_CUDA_evaluation(PHI, ac_spans, num_supp, ctrl_pts, ac_cells
     cp = _stack_ctrl_pts(ctrl_pts, device)
     phi = PHI.float().to(device) if isinstance(PHI, torch.Tensor) else torch.from_numpy(np.asarray(PHI)).float().to(device)
     if isinstance(ac_spans, PointSupports):
-        Jm = ac_spans.Jm(torch.int64)
+        Jm = ac_spans.Jm(torch.int64).to(device)
         ac_spans.offsets()
-        cumsum = ac_spans._cumsum
+        cumsum = ac_spans._cumsum.to(device)
     else:
         L = max(fn_sh.keys())
         nCP = np.zeros(L + 2, dtype=np.int64)
@@ -83,10 +97,13 @@ def prepare_data_for_evaluation(PHI, ac_spans, num_supp, ctrl_pts, ac_cells_ac_s
 
 
 def Evaluate(ctrl_pts, Jm, PHI, segment_ids, num_pts, device):
-    """[THB/torch_funcs.py:122-128] the same contraction; here it runs through the CSR kernel."""
+    """[THB/torch_funcs.py:122-128] out = zeros(num_pts, cp_dim).scatter_add_(0, segment_ids, ctrl_pts[Jm] * PHI): the same
+    contraction, here through the CSR kernel.  segment_ids are the non-decreasing point ids prepare_data_for_evaluation
+    produces.  Differentiable with respect to ctrl_pts and PHI like the reference's torch expression; tensors that live on
+    the CPU (device not "cuda") are staged through the GPU -- there is no CPU arithmetic."""
     seg = segment_ids[:, 0].contiguous()
     counts = torch.bincount(seg, minlength=num_pts)
-    return THBEval.apply(ctrl_pts, Jm, PHI.reshape(-1).contiguous(), torch.cumsum(counts, 0), "cuda")
+    return THBEval.apply(ctrl_pts, Jm, PHI.reshape(-1).contiguous(), torch.cumsum(counts, 0), "cuda" if _is_cuda(device) else "cpu")
 
 
 # ---- fused path -----------------------------------------------------------------------------------------
