@@ -73,7 +73,9 @@ typedef struct thb_space_desc {
     int32_t lut_off[3];
     int32_t lut_n[3];
     float lut_scale[3];                     /* bins per unit parameter: bin = (u - U[p]) * lut_scale */
-    int32_t pad_;
+    int32_t lut_exact;                      /* 1: the producer proved, with the same float32 bin formula evaluated at every
+                                               breakpoint, that the cell of any u of a bin is span_lut[bin] or the next one
+                                               (the plan then skips the verification and the fix-up pass) */
     const int32_t* finest_slot;             /* optional (may be NULL): per FINEST-level cell the slot of the active cell
                                                that contains it (-1 if none) -- one lookup instead of one per level */
     const int32_t* tiled_ref;               /* optional (NULL without the split tables): for tiled support j of the global

@@ -137,3 +137,42 @@ def test_update_cp_preserves_the_geometry():
         CP = np.concatenate([c[l].reshape(-1, 2) for l in range(4)])
         assert np.abs(evaluate(CP) - ref).max() < 5e-6
     assert {l: int(h.fns[l].sum()) for l in h.fns} == {0: 60, 1: 220, 2: 126, 3: 0}
+
+
+def test_exact_span_lut_decides_every_float_with_one_comparison():
+    """packed.py proves the span lookup table: with the device's float32 bin formula, the finest cell of EVERY float32 u
+    of the domain is lut[bin(u)] or the next one, decided by one comparison with the breakpoint in between
+    (k_plan_count_fast<.., EXACT>).  Emulated here in numpy float32 on the adversarial inputs: every breakpoint, its
+    float neighbours on both sides, and the first / last float of every bin."""
+    import numpy as np
+
+    from thb_diff_b200 import configs
+    from thb_diff_b200.packed import PackedHierarchy
+
+    for sp in (configs.cubic3d_space(4), configs.config2_space(), configs.cubic3d_space(5)):
+        P = PackedHierarchy.from_space(sp, device="cpu")
+        assert P.lut_exact
+        lut, off, nbs, scs = P._lut
+        L = P.nlevels - 1
+        for k in range(P.ndim):
+            p = P.degrees[k]
+            U = sp.knotvectors[L][k].astype(np.float32)
+            B = U[p:len(U) - p]
+            nc = len(B) - 1
+            nb, sc = nbs[k], np.float32(scs[k])
+            # adversarial inputs
+            xs = [B, np.nextafter(B, np.float32(-np.inf)), np.nextafter(B, np.float32(np.inf))]
+            edges = (B[0].astype(np.float64) + np.arange(nb + 1) / float(sc)).astype(np.float32)
+            for j in range(-3, 4):
+                e = edges.copy()
+                for _ in range(abs(j)):
+                    e = np.nextafter(e, np.float32(np.inf if j > 0 else -np.inf))
+                xs.append(e)
+            xs.append(np.random.default_rng(k).uniform(B[0], B[-1], 200000).astype(np.float32))
+            x = np.concatenate(xs)
+            x = x[(x >= B[0]) & (x <= B[-1])]
+            bins = np.minimum(((x - B[0]) * sc).astype(np.int32), nb - 1)
+            c0 = lut[off[k] + bins]
+            cell = np.minimum(c0 + (x >= B[np.minimum(c0 + 1, nc)]).astype(np.int32), nc - 1)
+            want = np.clip(np.searchsorted(B, x, side="right") - 1, 0, nc - 1)   # find_span_array_jax rule, u == U[-1] -> last cell
+            assert np.array_equal(cell, want)

@@ -244,7 +244,7 @@ constexpr int kPlanSmemLut = 3 * 1024;  // span lookup tables staged in shared m
 #endif
 constexpr int kCountPts = THB_COUNT_PTS;  // points per thread and iteration of the count pass
 
-template <int D, bool SLUT>
+template <int D, bool SLUT, bool EXACT>
 __global__ void __launch_bounds__(256) k_plan_count_fast(const __grid_constant__ thb_space_desc sp, const float* __restrict__ params,
                                                          unsigned n, int32_t* __restrict__ slot_out, int32_t* __restrict__ count,
                                                          int32_t* __restrict__ fail_list, int32_t* __restrict__ counters) {
@@ -300,13 +300,21 @@ __global__ void __launch_bounds__(256) k_plan_count_fast(const __grid_constant__
                 int bin = min((int)((x - u0[k]) * ls[k]), nbm1[k]);
                 bin = in ? bin : 0;
                 const int c0 = (SLUT ? s_lut[loff[k] + bin] : __ldg(glut + loff[k] + bin)) + off[k];
-                const float b0 = sk[c0], b1 = sk[c0 + 1], b2 = sk[c0 + 2];   // the p repeated end knots pad the last read
-                const bool inc = x >= b1;
-                const float lo = inc ? b1 : b0, hi = inc ? b2 : b1;
-                const int cc = min(c0 + (inc ? 1 : 0), last[k]);
-                ok &= (x >= lo) & ((x < hi) | (cc == last[k]));
-                inside &= in;
-                c[k] = cc - off[k];
+                if (EXACT) {
+                    // the host PROVED (packed.py: same float32 bin formula evaluated at every breakpoint, at most one
+                    // breakpoint per bin) that the cell of any x of this bin is lut[bin] or the next one: one comparison
+                    const int cc = min(c0 + (int)(x >= sk[c0 + 1]), last[k]);
+                    inside &= in;
+                    c[k] = cc - off[k];
+                } else {
+                    const float b0 = sk[c0], b1 = sk[c0 + 1], b2 = sk[c0 + 2];   // the p repeated end knots pad the last read
+                    const bool inc = x >= b1;
+                    const float lo = inc ? b1 : b0, hi = inc ? b2 : b1;
+                    const int cc = min(c0 + (inc ? 1 : 0), last[k]);
+                    ok &= (x >= lo) & ((x < hi) | (cc == last[k]));
+                    inside &= in;
+                    c[k] = cc - off[k];
+                }
             }
             int sl = -1;
             if (i < n) {
@@ -621,6 +629,18 @@ int grid_for(int64_t n, int block, int per_sm) {
     return (int)(want < cap ? want : cap);
 }
 
+// CTAs per SM of the two passes over the points (grid-stride loops).  Fewer than the 8 that fit leave room for a
+// concurrent kernel on another stream (the local control nets do not depend on the plan): THB_PLAN_CTAS_PER_SM.
+int plan_ctas_per_sm() {
+    static int v = 0;
+    if (v == 0) {
+        const char* e = getenv("THB_PLAN_CTAS_PER_SM");
+        v = e ? atoi(e) : 16;
+        if (v < 1 || v > 32) v = 16;
+    }
+    return v;
+}
+
 }  // namespace
 
 int thb_check_space(const thb_space_desc* sp, const char* who) {
@@ -712,14 +732,21 @@ extern "C" int thb_plan_build(const thb_space_desc* space, const float* params, 
             THB_CUDA(cudaMemsetAsync(plan->counters + 3, 0, sizeof(int32_t), st));
             // plan->scratch holds the (normally empty) list of unverified points
             const int lut_tot = space->lut_off[space->ndim - 1] + space->lut_n[space->ndim - 1];
-            const int g = grid_for(n, 256, 16);
-#define THB_COUNT(D_, S_) k_plan_count_fast<D_, S_><<<g, 256, 0, st>>>(*space, params, (unsigned)n, plan->slot, plan->cell_count, plan->scratch, plan->counters)
+            const int g = grid_for(n, 256, plan_ctas_per_sm());
+            const bool exact = space->lut_exact != 0;   // spans proven by the host: no verification, no fix-up pass
+#define THB_COUNT(D_, S_)                                                                                                        \
+    do {                                                                                                                        \
+        if (exact) k_plan_count_fast<D_, S_, true><<<g, 256, 0, st>>>(*space, params, (unsigned)n, plan->slot, plan->cell_count, plan->scratch, plan->counters); \
+        else k_plan_count_fast<D_, S_, false><<<g, 256, 0, st>>>(*space, params, (unsigned)n, plan->slot, plan->cell_count, plan->scratch, plan->counters); \
+    } while (0)
             if (space->ndim == 3) { if (lut_tot <= kPlanSmemLut) THB_COUNT(3, true); else THB_COUNT(3, false); }
             else { if (lut_tot <= kPlanSmemLut) THB_COUNT(2, true); else THB_COUNT(2, false); }
 #undef THB_COUNT
             THB_LAUNCHED();
-            k_plan_fixup<<<thb_num_sms(), 256, 0, st>>>(*space, params, plan->scratch, plan->counters, plan->slot, plan->cell_count);
-            THB_LAUNCHED();
+            if (!exact) {
+                k_plan_fixup<<<thb_num_sms(), 256, 0, st>>>(*space, params, plan->scratch, plan->counters, plan->slot, plan->cell_count);
+                THB_LAUNCHED();
+            }
         } else {
             k_plan_count<<<grid_for(n, 256, 16), 256, 0, st>>>(*space, params, n, plan->slot, plan->cell_count);
             THB_LAUNCHED();
@@ -741,7 +768,7 @@ extern "C" int thb_plan_build(const thb_space_desc* space, const float* params, 
                                                    plan->max_items, (int4*)plan->items);
     THB_LAUNCHED();
     if (n > 0) {
-        k_plan_scatter<<<grid_for(n, 256, 16), 256, 0, st>>>(plan->slot, params, space->ndim, n, plan->cell_cursor,
+        k_plan_scatter<<<grid_for(n, 256, plan_ctas_per_sm()), 256, 0, st>>>(plan->slot, params, space->ndim, n, plan->cell_cursor,
                                                              (float4*)plan->sorted_params);
         THB_LAUNCHED();
     }

@@ -157,12 +157,21 @@ def basis_tiled(P, plan, offsets, nnz, channels=(CH_VALUE,)):
 FORMULATIONS = {"local_net": 0, "tile_net": 1, "per_point": 2}
 
 
+def _same_device(a, b):
+    a, b = torch.device(a), torch.device(b)
+    if a.type != b.type:
+        return False
+    ia = a.index if a.index is not None else torch.cuda.current_device()
+    ib = b.index if b.index is not None else torch.cuda.current_device()
+    return ia == ib
+
+
 def _check_rows(tensors, plan, cpd, name):
     """Raw pointers go to the library: every per-point buffer must be a contiguous f32 [plan.n, cp_dim] tensor on the
     hierarchy's device."""
     for t in tensors:
         require_cuda(t, name, torch.float32)
-        if t.device != plan.P.device or t.dim() != 2 or t.shape[0] < plan.n or t.shape[1] != cpd:
+        if not _same_device(t.device, plan.P.device) or t.dim() != 2 or t.shape[0] < plan.n or t.shape[1] != cpd:
             raise RuntimeError(f"{name} must be [{plan.n}, {cpd}] float32 on {plan.P.device}, got {tuple(t.shape)} on {t.device}")
 
 
@@ -191,6 +200,26 @@ def cell_nets(P, ctrl_pts, with_derivatives=False, plan=None, out=None):
     with _on(P.device):
         check(lib.thb_cell_nets(C.byref(P.desc()), C.byref(plan.desc) if plan is not None else None, ptr(ctrl_pts), ctrl_pts.shape[1],
                                 int(with_derivatives), ptr(nets), stream_ptr(P.device)), "thb_cell_nets")
+    return nets
+
+
+def plan_and_nets(P, plan, ctrl_pts, with_derivatives=False, overlap=True):
+    """plan.build() and the local control nets of ctrl_pts, enqueued so that they run CONCURRENTLY: the nets depend on the
+    hierarchy and the control points only, not on the points, so they are built on a side stream (for every cell) while the
+    plan kernels sort the batch on the current stream; the current stream then waits for the nets.  Returns the nets.
+    overlap=False: plan first, then the nets of the cells that hold points, on one stream."""
+    if not overlap:
+        plan.build()
+        return cell_nets(P, ctrl_pts, with_derivatives, plan=plan)
+    cur = torch.cuda.current_stream(P.device)
+    side = getattr(P, "_side_stream", None)
+    if side is None:
+        side = P._side_stream = torch.cuda.Stream(device=P.device)
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        nets = cell_nets(P, ctrl_pts, with_derivatives)
+    plan.build()
+    cur.wait_stream(side)
     return nets
 
 
@@ -277,7 +306,7 @@ def eval_fused_backward_rows(P, plan, grad_out, out=None):
     _check_rows([grad_out], plan, cpd, "grad_out")
     ids, row_map = P.active_rows()
     g = out if out is not None else torch.empty((ids.shape[0], cpd), dtype=torch.float32, device=P.device)
-    if g.shape != (ids.shape[0], cpd) or not g.is_contiguous() or g.device != P.device or g.dtype != torch.float32:
+    if g.shape != (ids.shape[0], cpd) or not g.is_contiguous() or not _same_device(g.device, P.device) or g.dtype != torch.float32:
         raise RuntimeError(f"out must be a contiguous float32 [{ids.shape[0]}, {cpd}] tensor on {P.device}")
     with _on(P.device):
         check(lib.thb_eval_fused_backward_rows(C.byref(P.desc()), C.byref(plan.desc), ptr(plan.params), ptr(grad_out), cpd, ptr(row_map),

@@ -22,6 +22,8 @@ gather-multiply operation count).
 Semantics follow the reference: single-level truncation (core.py:98-111); the finest level
 uses the identity (the correct reading of core.py:113); no fp16 quantisation.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -127,9 +129,11 @@ class PackedHierarchy:
         # span lookup tables of the finest level: uniform bins at most 0.4 cells wide; entry = cell of the bin's left
         # edge, so the true cell of a point is that cell or the next one (the kernel compares once and verifies)
         lut_parts, lut_off, lut_n, lut_scale = [], [0, 0, 0], [0, 0, 0], [0.0, 0.0, 0.0]
+        lut_exact_parts = []
         lpos = 0
         for k in range(d):
-            Bk = kv[L - 1][k].astype(np.float32).astype(np.float64)[p[k]:len(kv[L - 1][k]) - p[k]]
+            B32 = kv[L - 1][k].astype(np.float32)[p[k]:len(kv[L - 1][k]) - p[k]]
+            Bk = B32.astype(np.float64)
             nb = int(np.ceil(2.5 * (Bk[-1] - Bk[0]) / np.min(np.diff(Bk))))
             if nb > 8192:
                 lut_parts = None
@@ -137,8 +141,22 @@ class PackedHierarchy:
             sc = np.float32(nb / (Bk[-1] - Bk[0]))
             left = Bk[0] + (np.arange(nb) - 0.05) / float(sc)
             lut_parts.append(np.clip(np.searchsorted(Bk, left, side="right") - 1, 0, len(Bk) - 2).astype(np.int32))
+            # PROVABLE form.  bin(x) = min(int((x - u0) * sc), nb - 1) in float32 is monotone in x, so with
+            # bin_c = bin(B[c]) of the interior breakpoints:  bin(x) > bin_c => x >= B[c],  bin(x) < bin_c => x < B[c].
+            # If no two breakpoints share a bin, the cell of every x of bin b is lut[b] = #{c : bin_c < b} or the next one,
+            # and one comparison with B[lut[b] + 1] decides -- no verification needed on the device.
+            if lut_exact_parts is not None and len(B32) >= 2:
+                with np.errstate(all="ignore"):
+                    bin_c = np.minimum(((B32[1:-1] - B32[0]) * sc).astype(np.int32), nb - 1)   # float32 arithmetic, as on the device
+                if len(bin_c) == 0 or (np.all(np.diff(bin_c) > 0) and bin_c[0] >= 0):
+                    lut_exact_parts.append(np.searchsorted(bin_c, np.arange(nb), side="left").astype(np.int32))
+                else:
+                    lut_exact_parts = None
             lut_off[k], lut_n[k], lut_scale[k] = lpos, nb, float(sc)
             lpos += nb
+        self.lut_exact = bool(lut_parts) and lut_exact_parts is not None and os.environ.get("THB_LUT_EXACT", "1") != "0"
+        if self.lut_exact:
+            lut_parts = lut_exact_parts   # also valid for the verifying kernels: the cell is lut[bin] or lut[bin] + 1
         self._lut = (np.concatenate(lut_parts), lut_off, lut_n, lut_scale) if lut_parts else None
         # finest-cell -> active-slot map (every finest cell lies in exactly one active cell): lets the kernels
         # find a point's cell with ONE lookup instead of one per level.  Skipped for very deep hierarchies.
@@ -483,6 +501,7 @@ def _desc(self):
         d.full_tiles, d.full_jm = self.full_tiles.data_ptr(), self.full_jm.data_ptr()
     d.tiled_ref = self.tiled_ref.data_ptr() if getattr(self, "tiled_ref", None) is not None and getattr(self, "sep_vec", None) is not None else None
     d.span_lut = self.span_lut.data_ptr() if self.span_lut is not None else None
+    d.lut_exact = 1 if (self.span_lut is not None and getattr(self, "lut_exact", False)) else 0
     if self.span_lut is not None:
         for k in range(self.ndim):
             d.lut_off[k], d.lut_n[k], d.lut_scale[k] = self._lut[1][k], self._lut[2][k], self._lut[3][k]
