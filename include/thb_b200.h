@@ -81,6 +81,11 @@ typedef struct thb_space_desc {
     const int32_t* tiled_ref;               /* optional (NULL without the split tables): for tiled support j of the global
                                                tile order (tile_off + position in the cell's reference-ordered list):
                                                (row of sep_vec << 1) or (row of full_tiles << 1) | 1 */
+    const float* poly;                      /* optional (may be NULL): per level, dimension and 1-D cell a row of 20 floats --
+                                               the p+1 B-splines of the cell as polynomials in s = (u - lo) / half - 1,
+                                               N_r(u) = sum_m C[m][r] s^m, C as [m][r] padded to 4 x 4, then (lo, 1/half, 0, 0).
+                                               Used by the monomial form of the local control nets (thb_cell_nets with THB_NETS_MONOMIAL) */
+    int32_t poly_off[THB_MAX_LEVELS][3];    /* first row of each (level, dimension) */
 } thb_space_desc;
 
 /* A plan = the points of one batch grouped by active cell. All arrays are caller-allocated device memory:
@@ -195,17 +200,26 @@ THB_API int thb_eval_fused(const thb_space_desc* space, const thb_plan_desc* pla
  * the cell's own-level B-splines and  W[t] = [t active] CP_own[t] + sum_{coarser s} tile_s[t] CP_s : W depends on the
  * hierarchy and the control points only, so it is built once per cell (and may be kept across batches of points for as
  * long as ctrl_pts do not change) and a point costs Cox-de Boor plus one sum-factorised contraction with W.
- * nets: [nslots][planes][tile_stride] f32, planes = 4 (value channel only) or 8 (with_derivatives: planes 4..7 are W
+ * nets: [nslots][planes][tile_stride] f32, planes = 4 (value channel only) or 8 (THB_NETS_DERIVATIVES: planes 4..7 are W
  * built from control points relative to the cell's first support, used by the derivative channels).
+ * flags (the same value goes to thb_net_workspace_floats, thb_cell_nets and thb_eval_nets):
+ *   THB_NETS_DERIVATIVES (1)  eight planes, derivative channels allowed
+ *   THB_NETS_MONOMIAL    (2)  the nets are stored in MONOMIAL form: with the cell's B-splines written as polynomials in the
+ *                             cell-local coordinate s_k = (u_k - lo_k) / half_k - 1 (thb_space_desc::poly, required),
+ *                             <tp(u), W> = sum M[m0][m1][m2] s0^m0 s1^m1 s2^m2 and a point costs three subtractions plus a
+ *                             nested Horner scheme (30 packed FMAs per output component for cubic 3-D) -- no Cox-de Boor.
+ *                             thb_eval_fused uses this form whenever `poly` is present.
  * thb_cell_nets: plan == NULL builds every active cell, otherwise only the cells that hold points of the plan.
  * Together the two calls replace THB_basis_fns (THB/core.py:604-701) + prepare_data_for_CUDA_evaluation
  * (THB/torch_funcs.py:50-80) + THBEval.forward / THB_eval.forward (THB/torch_funcs.py:22-33,
  * THB_extensions/compute_pts_cuda_kernels.cu:3-26); thb_cell_nets alone takes the place of the dense coefficient tables
  * of compute_refinement_operators (THB/core.py:43-114) on the evaluation side. */
-THB_API int64_t thb_net_workspace_floats(const thb_space_desc* space, int with_derivatives);
+#define THB_NETS_DERIVATIVES 1
+#define THB_NETS_MONOMIAL 2
+THB_API int64_t thb_net_workspace_floats(const thb_space_desc* space, int flags);
 THB_API int thb_cell_nets(const thb_space_desc* space, const thb_plan_desc* plan, const float* ctrl_pts, int cp_dim,
-                  int with_derivatives, float* nets, void* stream);
-THB_API int thb_eval_nets(const thb_space_desc* space, const thb_plan_desc* plan, const float* nets, int with_derivatives,
+                  int flags, float* nets, void* stream);
+THB_API int thb_eval_nets(const thb_space_desc* space, const thb_plan_desc* plan, const float* nets, int flags,
                   int cp_dim, const int32_t* channels, int nchannels, float* const* out_host, void* stream);
 /* grad_ctrl_pts[nctrl, cp_dim] (zeroed by the callee) = A^T grad_out, A = value-channel basis matrix.
  * Replaces THBEval.backward (THB/torch_funcs.py:35-47) for the fused path.  workspace: thb_net_workspace_floats(space, 0)

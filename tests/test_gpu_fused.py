@@ -259,3 +259,35 @@ def test_rows_in_plan_order():
         engine.eval_fused(P, plan, cp, formulation="per_point")      # only the nets path knows the row order
     plan.set_rows_in_plan_order(False)
     assert torch.equal(engine.eval_fused(P, plan, cp)[0], ref)
+
+
+@pytest.mark.parametrize("cp_dim", [3, 4])
+@pytest.mark.parametrize("name", IDENTITY_OK)
+def test_monomial_nets_and_control_point_nets_against_the_oracle(name, cp_dim):
+    """Both layouts of the local control nets -- control points evaluated with Cox-de Boor, and the monomial form evaluated
+    by nested Horner (the default) -- value and every first-derivative channel against the oracle contraction."""
+    from thb_diff_b200 import engine
+
+    g, h, P, plan, cp, cs = _setup(name, cp_dim=cp_dim)
+    d = h.ndim
+    cpt = torch.from_numpy(cp).cuda()
+    ref = O.eval_forward(cp, g["Jm"], g["PHI"], cs)
+    chans = [engine.CH_VALUE] + engine.grad_channels(d)
+    outs = {}
+    for mono in (False, True):
+        nets = engine.cell_nets(P, cpt, with_derivatives=True, monomial=mono)
+        assert bool(nets._thb_flags & engine.NETS_MONOMIAL) == mono
+        outs[mono] = [o.cpu().numpy() for o in engine.eval_nets(P, plan, nets, cp_dim, chans)]
+        assert rel_err(outs[mono][0], ref, scale=np.abs(ref).max()).max() <= TOL
+        nets4 = engine.cell_nets(P, cpt, with_derivatives=False, monomial=mono).clone()
+        v = engine.eval_nets(P, plan, nets4, cp_dim, monomial=mono)[0].cpu().numpy()
+        assert rel_err(v, ref, scale=np.abs(ref).max()).max() <= TOL
+    # derivative channels: the two layouts against each other and against the oracle's derivative PHI (golden spaces carry
+    # the mixed partial only, so the per-direction reference comes from the C oracle on the packed tables)
+    from helpers import host_tables_from_packed
+
+    ht = host_tables_from_packed(P)
+    for k in range(d):
+        r = ht.eval(g["params"], cp, mode=1 << k)["out"]
+        for mono in (False, True):
+            assert rel_err(outs[mono][1 + k], r, scale=max(np.abs(r).max(), 1.0)).max() <= 2 * TOL, (k, mono)

@@ -25,6 +25,7 @@ class SpaceDesc(C.Structure):
         ("sep_vec", C.c_void_p), ("sep_jm", C.c_void_p), ("full_tiles", C.c_void_p), ("full_jm", C.c_void_p),
         ("span_lut", C.c_void_p), ("lut_off", C.c_int32 * 3), ("lut_n", C.c_int32 * 3), ("lut_scale", C.c_float * 3), ("lut_exact", C.c_int32),
         ("finest_slot", C.c_void_p), ("tiled_ref", C.c_void_p),
+        ("poly", C.c_void_p), ("poly_off", (C.c_int32 * 3) * MAX_LEVELS),
     ]
 
 

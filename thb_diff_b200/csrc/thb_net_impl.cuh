@@ -37,6 +37,7 @@ struct NetArgs {
     float* nets;                // [nslots][planes][TS]
     int32_t planes;             // 4, or 8 with the relative planes
     const int32_t* row_map;     // k_cell_unfold: flat function id -> row of the (compact) gradient buffer; nullptr = identity
+    int32_t mono;               // k_cell_nets: 1 = store the nets in MONOMIAL form (see net_to_monomial), 0 = control points
 };
 
 template <int CPD>
@@ -65,6 +66,55 @@ THB_DEV void fold2(f32x2 (*w2)[4], f32x2 (*wr2)[4], f32x2 x01, f32x2 x23, const 
     }
 }
 
+// Control net -> monomial form of one cell, in place in a per-warp shared-memory buffer [planes][TS].
+// Over a cell the geometry is <tp(u), W> with tp the tensor product of the cell's p+1 B-splines per dimension; with
+// N_r(u_k) = sum_m C_k[m][r] s_k^m (sp.poly: s_k = (u_k - lo_k) / half_k - 1 in [-1, 1], float64 on the host)
+//     <tp(u), W> = sum_{m0,m1,m2} M[m0][m1][m2] s0^m0 s1^m1 s2^m2,   M = (C_0 x C_1 x C_2) W
+// so a point costs three subtractions and a nested Horner scheme (k_net_eval, MONO) instead of Cox-de Boor plus the
+// contraction with tp(u).  Three separable passes, one per dimension; every lane owns the entries t = lane (+ 32).
+template <int N0, int N1, int N2, int planes>
+THB_DEV void net_to_monomial(const thb_space_desc& sp, int lev, int c0, int c1, int c2, float* buf, int TS) {
+    constexpr int T = N0 * N1 * N2;
+    constexpr int NT = (T + 31) / 32;
+    const int lane = threadIdx.x & 31;
+    const int cell[3] = {c0, c1, c2};
+    constexpr int NN[3] = {N0, N1, N2};
+    constexpr int STR[3] = {N1 * N2, N2, 1};
+#pragma unroll
+    for (int dim = 2; dim >= 0; --dim) {
+        if (NN[dim] == 1) continue;
+        const float* row = sp.poly + (int64_t)(sp.poly_off[lev][dim] + cell[dim]) * 20;
+        float o[NT][planes];
+#pragma unroll
+        for (int h = 0; h < NT; ++h) {
+            const int t = lane + 32 * h;
+            if (t < T) {
+                const int m = (t / STR[dim]) % NN[dim];
+                const int base = t - m * STR[dim];
+                const float4 cm = __ldg(reinterpret_cast<const float4*>(row) + m);   // C[m][0..3]
+                const float cr[4] = {cm.x, cm.y, cm.z, cm.w};
+#pragma unroll
+                for (int k = 0; k < planes; ++k) {
+                    float acc = 0.f;
+#pragma unroll
+                    for (int r = 0; r < NN[dim]; ++r) acc = fmaf(cr[r], buf[k * TS + base + r * STR[dim]], acc);
+                    o[h][k] = acc;
+                }
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int h = 0; h < NT; ++h) {
+            const int t = lane + 32 * h;
+            if (t < T) {
+#pragma unroll
+                for (int k = 0; k < planes; ++k) buf[k * TS + t] = o[h][k];
+            }
+        }
+        __syncwarp();
+    }
+}
+
 template <int N0, int N1, int N2, int CPD, bool REL>
 __global__ void __launch_bounds__(32 * kNetWarps, (REL || CPD == 4) ? 6 : THB_NETS_MINB) k_cell_nets(const __grid_constant__ thb_space_desc sp, const __grid_constant__ NetArgs na) {
     using SH = Shp<N0, N1, N2>;
@@ -73,6 +123,7 @@ __global__ void __launch_bounds__(32 * kNetWarps, (REL || CPD == 4) ? 6 : THB_NE
     constexpr bool kSameBC = (32 % (N1 * N2)) == 0;  // t and t + 32 differ in the first index only
     __shared__ __align__(16) float4 s_sepv[kNetWarps][kNetChunk][3];
     __shared__ __align__(16) float4 s_cc[kNetWarps][kNetChunk];
+    __shared__ __align__(16) float s_conv[kNetWarps][REL ? 8 : 4][TS];   // control net -> monomial form (na.mono)
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     float4(*sepv)[3] = s_sepv[wid];
     float4* cc = s_cc[wid];
@@ -165,8 +216,10 @@ __global__ void __launch_bounds__(32 * kNetWarps, (REL || CPD == 4) ? 6 : THB_NE
                     fold2<CPD, REL>(w2, wr2, x01, x23, c, ref);
                 }
             }
-            // sum the two halves; half h then writes the entries a = 2h, 2h+1
-            float* dst = na.nets + (int64_t)slot * na.planes * TS;
+            // sum the two halves; half h then writes the entries a = 2h, 2h+1 (to the workspace, or to shared memory on
+            // the way to the monomial form)
+            float* const gdst = na.nets + (int64_t)slot * na.planes * TS;
+            float* dst = na.mono ? &s_conv[wid][0][0] : gdst;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 float o[2][2], orr[2][2];
@@ -188,6 +241,14 @@ __global__ void __launch_bounds__(32 * kNetWarps, (REL || CPD == 4) ? 6 : THB_NE
                     dst[(4 + k) * TS + tb] = half ? orr[1][0] : orr[0][0];
                     dst[(4 + k) * TS + tb + 16] = half ? orr[1][1] : orr[0][1];
                 }
+            }
+            if (na.mono) {
+                __syncwarp();
+                net_to_monomial<N0, N1, N2, (REL ? 8 : 4)>(sp, lev, a.y, a.z, a.w, dst, TS);
+                const float4* b4 = reinterpret_cast<const float4*>(dst);
+                float4* d4 = reinterpret_cast<float4*>(gdst);
+                for (int i = lane; i < (REL ? 8 : 4) * TS / 4; i += 32) d4[i] = b4[i];
+                __syncwarp();
             }
             continue;
         }
@@ -311,6 +372,27 @@ __global__ void __launch_bounds__(32 * kNetWarps, (REL || CPD == 4) ? 6 : THB_NE
             }
         }
         float* dst = na.nets + (int64_t)slot * na.planes * TS;
+        if (na.mono) {
+            float* buf = &s_conv[wid][0][0];
+#pragma unroll
+            for (int h = 0; h < NT; ++h) {
+                const int t = lane + 32 * h;
+                if (t < TS) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        buf[k * TS + t] = w[h][k];
+                        if (REL) buf[(4 + k) * TS + t] = wr[h][k];
+                    }
+                }
+            }
+            __syncwarp();
+            net_to_monomial<N0, N1, N2, (REL ? 8 : 4)>(sp, lev, a.y, a.z, a.w, buf, TS);
+            const float4* b4 = reinterpret_cast<const float4*>(buf);
+            float4* d4 = reinterpret_cast<float4*>(dst);
+            for (int i = lane; i < (REL ? 8 : 4) * TS / 4; i += 32) d4[i] = b4[i];
+            __syncwarp();
+            continue;
+        }
 #pragma unroll
         for (int h = 0; h < NT; ++h) {
             const int t = lane + 32 * h;
@@ -336,12 +418,18 @@ struct NetSmem {
     float4 prec[2][64];              // point records of a sub-batch: (u0, u1, u2, caller-order index as bits)
 };
 
-template <class SH, bool DER>
+template <class SH, bool DER, bool MONO>
 THB_DEV void prefetch_net(const thb_space_desc& sp, const float* __restrict__ nets, const Item& it, float (*knots)[8],
                           float (*net)[SH::TS]) {
     constexpr int NPL = DER ? 8 : 4;
     const int lane = threadIdx.x;
-    if (lane < 24) {
+    if (MONO) {   // (lo, 1 / half) of the cell in every dimension: floats 16, 17 of its row of sp.poly
+        if (lane < 6) {
+            const int dim = lane >> 1, m = lane & 1;
+            const int c = dim == 0 ? it.c0 : (dim == 1 ? it.c1 : it.c2);
+            if (dim < sp.ndim) cp_async4(&knots[dim][m], sp.poly + (int64_t)(sp.poly_off[it.lev][dim] + c) * 20 + 16 + m);
+        }
+    } else if (lane < 24) {
         const int dim = lane >> 3, m = lane & 7;
         const int P = dim == 0 ? SH::P0 : (dim == 1 ? SH::P1 : SH::P2);
         const int c = dim == 0 ? it.c0 : (dim == 1 ? it.c1 : it.c2);
@@ -353,6 +441,143 @@ THB_DEV void prefetch_net(const thb_space_desc& sp, const float* __restrict__ ne
     for (int i = 0; i < (NPL * SH::TS / 4 + 31) / 32; ++i) {
         const int j = lane + 32 * i;
         if (j < NPL * SH::TS / 4) cp_async16(dst + j, src + j);
+    }
+}
+
+// One-dimensional Horner step helpers of the monomial evaluation.  A polynomial c0 + c1 s + ... + c_{N-1} s^{N-1}: value by
+// the usual scheme; first derivative with respect to s as ((N-1) c_{N-1} s + (N-2) c_{N-2}) s + ... + c1, written with
+// the per-step multipliers mult[j] so that value and derivative share the code: r = c_{top}; r = r * mult[j] + c_j.
+//   value      : top = N-1, steps j = N-2 .. 0, mult = s
+//   derivative : top = N-1, steps j = N-2 .. 1, mult_j = s * (j+1)/j ... (see horner_mults)
+template <int N>
+THB_DEV void horner_mults(float s, bool der, float* mult) {
+    // der: d/ds sum c_m s^m = sum_{m>=1} m c_m s^{m-1}; nested: r_{N-1} = c_{N-1}; r_j = r_{j+1} * (s * (j+1)/j) + c_j for j >= 1
+    // gives r_1 = sum_m (m/1) c_m s^{m-1}: exactly the derivative.
+#pragma unroll
+    for (int j = 0; j < N - 1; ++j) mult[j] = der ? (j >= 1 ? s * (float(j + 1) / float(j)) : 0.f) : s;
+}
+
+// PPT*32 points of an item against the MONOMIAL net M (k_cell_nets with na.mono):
+//     out_k = sum_{m0,m1,m2} M[k][m0][m1][m2] s0^m0 s1^m1 s2^m2,  s = (u - lo) / half - 1
+// Nested Horner: over m1 on pairs of m2 (FFMA2 with a scalar multiplier), over m0 on the same pairs, then over m2.
+// 30 FFMA2 + 3 FFMA per output component for cubic 3-D against 45 FFMA2 for the B-spline form -- and no Cox-de Boor.
+// Derivative channels use the derivative polynomial in the flagged dimensions (times 1 / half of that dimension).
+template <class SH, int PPT, int CPD, bool DER>
+THB_DEV void net_points_mono(const Args& ar, const Item& it, int base, NetSmem<SH, DER>& sm, int tb, int pb) {
+    constexpr int N0 = SH::N0, N1 = SH::N1, N2 = SH::N2;
+    const int lane = threadIdx.x;
+    int idx[PPT];
+    bool valid[PPT];
+    float s[PPT][3];
+    float ih[3];
+#pragma unroll
+    for (int dim = 0; dim < 3; ++dim) ih[dim] = sm.knots[tb][dim][1];
+#pragma unroll
+    for (int q = 0; q < PPT; ++q) {
+        valid[q] = base + q * 32 + lane < it.count;
+        const float4 rec = sm.prec[pb][q * 32 + lane];
+        idx[q] = ar.rows_sorted ? it.begin + base + q * 32 + lane : __float_as_int(rec.w);
+        s[q][0] = fmaf(rec.x - sm.knots[tb][0][0], ih[0], -1.0f);
+        s[q][1] = fmaf(rec.y - sm.knots[tb][1][0], ih[1], -1.0f);
+        s[q][2] = N2 > 1 ? fmaf(rec.z - sm.knots[tb][2][0], ih[2], -1.0f) : 0.0f;
+    }
+    for (int chi = 0; chi < ar.nch; ++chi) {
+        const int ch = ar.channels[chi];
+        const int pl = (DER && ch != 0) ? 4 : 0;  // derivative channels use the relative planes
+        const bool d0 = DER && (ch & 1), d1 = DER && (ch & 2), d2 = DER && (ch & 4);
+        const float scale = (d0 ? ih[0] : 1.0f) * (d1 ? ih[1] : 1.0f) * (d2 ? ih[2] : 1.0f);
+        float m0[PPT][N0 > 1 ? N0 - 1 : 1], m1[PPT][N1 > 1 ? N1 - 1 : 1], m2[PPT][N2 > 1 ? N2 - 1 : 1];
+#pragma unroll
+        for (int q = 0; q < PPT; ++q) {
+            horner_mults<N0>(s[q][0], d0, m0[q]);
+            horner_mults<N1>(s[q][1], d1, m1[q]);
+            horner_mults<N2>(s[q][2], d2, m2[q]);
+        }
+        // lowest index reached by the Horner scheme of each dimension: 0 (value) or 1 (derivative)
+        const int e0 = d0 ? 1 : 0, e1 = d1 ? 1 : 0, e2 = d2 ? 1 : 0;
+        float acc[PPT][4];
+        if constexpr (N2 == 4) {
+#pragma unroll
+            for (int k = 0; k < CPD; ++k) {
+                const ulonglong2* col = reinterpret_cast<const ulonglong2*>(sm.net[tb][pl + k]);   // col[m0 * N1 + m1] = M[m0][m1][0..3]
+                f32x2 Q[PPT][2];
+#pragma unroll
+                for (int a = N0 - 1; a >= 0; --a) {
+                    if (a < e0) break;
+                    ulonglong2 cv[N1];
+#pragma unroll
+                    for (int b = 0; b < N1; ++b) cv[b] = col[a * N1 + b];
+#pragma unroll
+                    for (int q = 0; q < PPT; ++q) {
+                        f32x2 E0 = cv[N1 - 1].x, E1 = cv[N1 - 1].y;
+#pragma unroll
+                        for (int b = N1 - 2; b >= 0; --b) {
+                            if (b < e1) break;
+                            const f32x2 x = pack2(m1[q][b], m1[q][b]);
+                            f32x2 t0 = cv[b].x, t1 = cv[b].y;
+                            ffma2(t0, E0, x);
+                            ffma2(t1, E1, x);
+                            E0 = t0; E1 = t1;
+                        }
+                        if (a == N0 - 1) {
+                            Q[q][0] = E0; Q[q][1] = E1;
+                        } else {
+                            const f32x2 x = pack2(m0[q][a], m0[q][a]);
+                            ffma2(E0, Q[q][0], x);
+                            ffma2(E1, Q[q][1], x);
+                            Q[q][0] = E0; Q[q][1] = E1;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < PPT; ++q) {
+                    float c0, c1, c2, c3;
+                    unpack2(Q[q][0], c0, c1);
+                    unpack2(Q[q][1], c2, c3);
+                    float r = c3;
+                    r = fmaf(r, m2[q][2], c2);
+                    r = fmaf(r, m2[q][1], c1);
+                    if (!d2) r = fmaf(r, m2[q][0], c0);
+                    acc[q][k] = DER ? r * scale : r;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < CPD; ++k) {
+                const float* col = sm.net[tb][pl + k];
+#pragma unroll
+                for (int q = 0; q < PPT; ++q) {
+                    float ra = 0.0f;
+#pragma unroll
+                    for (int a = N0 - 1; a >= 0; --a) {
+                        if (a < e0) break;
+                        float rb = 0.0f;
+#pragma unroll
+                        for (int b = N1 - 1; b >= 0; --b) {
+                            if (b < e1) break;
+                            float rc = col[(a * N1 + b) * N2 + N2 - 1];
+#pragma unroll
+                            for (int c = N2 - 2; c >= 0; --c) {
+                                if (c < e2) break;
+                                rc = fmaf(rc, m2[q][c], col[(a * N1 + b) * N2 + c]);
+                            }
+                            if (N2 == 1 && d2) rc = 0.0f;
+                            rb = b == N1 - 1 ? rc : fmaf(rb, m1[q][b], rc);
+                        }
+                        ra = a == N0 - 1 ? rb : fmaf(ra, m0[q][a], rb);
+                    }
+                    acc[q][k] = DER ? ra * scale : ra;
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < PPT; ++q) {
+            if (valid[q]) {
+                float* o = ar.out[chi] + (int64_t)idx[q] * CPD;
+#pragma unroll
+                for (int k = 0; k < CPD; ++k) o[k] = acc[q][k];
+            }
+        }
     }
 }
 
@@ -481,7 +706,7 @@ THB_DEV void net_points(const Args& ar, const Item& it, int base, NetSmem<SH, DE
 // Persistent, warp-autonomous (one warp per CTA, no CTA barrier): work items from an atomic cursor; while item i is
 // computed the records of items i+1, i+2 are in flight, and the points of the next sub-batch plus the knots / net of
 // item i+1 stream into the other half of the shared-memory buffers (cp.async).
-template <int N0, int N1, int N2, int PPT, int CPD, bool DER>
+template <int N0, int N1, int N2, int PPT, int CPD, bool DER, bool MONO>
 __global__ void __launch_bounds__(kThreads, DER ? THB_NET_MINB_DER : THB_NET_MINB) k_net_eval(const __grid_constant__ thb_space_desc sp, const __grid_constant__ Args ar,
                                                                     const float* __restrict__ nets) {
     using SH = Shp<N0, N1, N2>;
@@ -500,7 +725,7 @@ __global__ void __launch_bounds__(kThreads, DER ? THB_NET_MINB_DER : THB_NET_MIN
     Item it = load_item(sp, ar.items, id0);
     if (lane < 4 && id1 < nitems) cp_async16(&sm.rec[1][lane], ar.items + (int64_t)id1 * 4 + lane);
     if (lane < 4 && id2 < nitems) cp_async16(&sm.rec[2][lane], ar.items + (int64_t)id2 * 4 + lane);
-    prefetch_net<SH, DER>(sp, nets, it, sm.knots[0], sm.net[0]);
+    prefetch_net<SH, DER, MONO>(sp, nets, it, sm.knots[0], sm.net[0]);
     prefetch_points<PPT>(ar, it.begin, it.count, 0, sm.prec[0]);
     cp_async_commit();
     int nn_id = 0;
@@ -510,7 +735,7 @@ __global__ void __launch_bounds__(kThreads, DER ? THB_NET_MINB_DER : THB_NET_MIN
     __syncwarp();
 
     for (;;) {
-        if (lane < 24) {  // reciprocal knot differences of this cell (from the staged knots)
+        if (!MONO && lane < 24) {  // reciprocal knot differences of this cell (from the staged knots)
             const int dim = lane >> 3, m = lane & 7;
             const int P = dim == 0 ? SH::P0 : (dim == 1 ? SH::P1 : SH::P2);
             if (dim < d && m < P * (P + 1) / 2) {
@@ -528,11 +753,16 @@ __global__ void __launch_bounds__(kThreads, DER ? THB_NET_MINB_DER : THB_NET_MIN
                 const int4* r = sm.rec[(ring + 1) % 3];
                 const Item nx = unpack_item(r[0], r[1], r[2], r[3]);
                 prefetch_points<PPT>(ar, nx.begin, nx.count, 0, sm.prec[pb ^ 1]);
-                prefetch_net<SH, DER>(sp, nets, nx, sm.knots[tb ^ 1], sm.net[tb ^ 1]);
+                prefetch_net<SH, DER, MONO>(sp, nets, nx, sm.knots[tb ^ 1], sm.net[tb ^ 1]);
             }
             cp_async_commit();
-            if (PPT == 2 && it.count - base <= 32) net_points<SH, 1, CPD, DER>(ar, it, base, sm, tb, pb);
-            else net_points<SH, PPT, CPD, DER>(ar, it, base, sm, tb, pb);
+            if constexpr (MONO) {
+                if (PPT >= 2 && it.count - base <= 32) net_points_mono<SH, 1, CPD, DER>(ar, it, base, sm, tb, pb);
+                else net_points_mono<SH, PPT, CPD, DER>(ar, it, base, sm, tb, pb);
+            } else {
+                if (PPT == 2 && it.count - base <= 32) net_points<SH, 1, CPD, DER>(ar, it, base, sm, tb, pb);
+                else net_points<SH, PPT, CPD, DER>(ar, it, base, sm, tb, pb);
+            }
             cp_async_wait<0>();
             __syncwarp();
             pb ^= 1;
@@ -845,26 +1075,31 @@ int launch_nets(const thb_space_desc* sp, const NetArgs* na, int cpd, cudaStream
 }
 
 template <int N0, int N1, int N2>
-int launch_net_eval(const thb_space_desc* sp, const Args* ar, const float* nets, int ppt, int cpd, int der, cudaStream_t st) {
-#define THB_NET_EVAL(PPT_, CPD_, DER_)                                                        \
+int launch_net_eval(const thb_space_desc* sp, const Args* ar, const float* nets, int ppt, int cpd, int der, int mono, cudaStream_t st) {
+#define THB_NET_EVAL(PPT_, CPD_, DER_, MONO_)                                                 \
     do {                                                                                      \
         static int grid_[THB_MAX_DEVICES] = {};                                               \
         int& grid = grid_[thb_device()];                                                      \
-        if (grid == 0) grid = persistent_grid(k_net_eval<N0, N1, N2, PPT_, CPD_, DER_>, kThreads); \
-        k_net_eval<N0, N1, N2, PPT_, CPD_, DER_><<<grid, kThreads, 0, st>>>(*sp, *ar, nets);   \
+        if (grid == 0) grid = persistent_grid(k_net_eval<N0, N1, N2, PPT_, CPD_, DER_, MONO_>, kThreads); \
+        k_net_eval<N0, N1, N2, PPT_, CPD_, DER_, MONO_><<<grid, kThreads, 0, st>>>(*sp, *ar, nets); \
         THB_LAUNCHED();                                                                       \
         return THB_OK;                                                                        \
     } while (0)
-    if (ppt == 2) {
-        if (cpd == 3 && !der) THB_NET_EVAL(2, 3, false);
-        if (cpd == 3 && der) THB_NET_EVAL(2, 3, true);
-        if (cpd == 4 && !der) THB_NET_EVAL(2, 4, false);
-        if (cpd == 4 && der) THB_NET_EVAL(2, 4, true);
+    if (mono) {   // monomial nets: two points per lane (one for tails)
+        if (cpd == 3 && !der) THB_NET_EVAL(2, 3, false, true);
+        if (cpd == 3 && der) THB_NET_EVAL(2, 3, true, true);
+        if (cpd == 4 && !der) THB_NET_EVAL(2, 4, false, true);
+        if (cpd == 4 && der) THB_NET_EVAL(2, 4, true, true);
+    } else if (ppt == 2) {
+        if (cpd == 3 && !der) THB_NET_EVAL(2, 3, false, false);
+        if (cpd == 3 && der) THB_NET_EVAL(2, 3, true, false);
+        if (cpd == 4 && !der) THB_NET_EVAL(2, 4, false, false);
+        if (cpd == 4 && der) THB_NET_EVAL(2, 4, true, false);
     } else {
-        if (cpd == 3 && !der) THB_NET_EVAL(1, 3, false);
-        if (cpd == 3 && der) THB_NET_EVAL(1, 3, true);
-        if (cpd == 4 && !der) THB_NET_EVAL(1, 4, false);
-        if (cpd == 4 && der) THB_NET_EVAL(1, 4, true);
+        if (cpd == 3 && !der) THB_NET_EVAL(1, 3, false, false);
+        if (cpd == 3 && der) THB_NET_EVAL(1, 3, true, false);
+        if (cpd == 4 && !der) THB_NET_EVAL(1, 4, false, false);
+        if (cpd == 4 && der) THB_NET_EVAL(1, 4, true, false);
     }
 #undef THB_NET_EVAL
     return thb_set_error(THB_E_UNSUPPORTED, "net evaluation: unsupported variant");
@@ -1109,7 +1344,7 @@ struct ShapeOps {
     // ppt in {1,2}; cpd in {3,4}; der in {0,1}
     int (*fused)(const thb_space_desc*, const Args*, int ppt, int cpd, int der, cudaStream_t);
     int (*nets)(const thb_space_desc*, const NetArgs*, int cpd, cudaStream_t);
-    int (*net_eval)(const thb_space_desc*, const Args*, const float* nets, int ppt, int cpd, int der, cudaStream_t);
+    int (*net_eval)(const thb_space_desc*, const Args*, const float* nets, int ppt, int cpd, int der, int mono, cudaStream_t);
     int (*net_backward)(const thb_space_desc*, const Args*, const NetArgs*, float* grad_cp, int cpd, cudaStream_t);
     int (*basis)(const thb_space_desc*, const Args*, int ppt, int der, cudaStream_t);
     int (*basis_rows)(const thb_space_desc*, const Args*, int der, cudaStream_t);

@@ -94,8 +94,10 @@ extern "C" int thb_eval_fused(const thb_space_desc* space, const thb_plan_desc* 
     THB_REQUIRE(formulation >= 0 && formulation <= 2, "thb_eval_fused: unknown formulation");
     if (formulation == THB_EVAL_LOCAL_NET) {
         THB_REQUIRE(workspace, "thb_eval_fused: the local-net formulation needs a workspace (thb_net_workspace_floats)");
-        if ((rc = thb_cell_nets(space, plan, ctrl_pts, cp_dim, der ? 1 : 0, workspace, stream))) return rc;
-        return thb_eval_nets(space, plan, workspace, der ? 1 : 0, cp_dim, channels, nchannels, out_host, stream);
+        // monomial nets (THB_NETS_MONOMIAL) whenever the hierarchy carries the span polynomials: no per-point Cox-de Boor
+        const int flags = (der ? THB_NETS_DERIVATIVES : 0) | ((space->poly && env_int("THB_NET_MONO", 1)) ? THB_NETS_MONOMIAL : 0);
+        if ((rc = thb_cell_nets(space, plan, ctrl_pts, cp_dim, flags, workspace, stream))) return rc;
+        return thb_eval_nets(space, plan, workspace, flags, cp_dim, channels, nchannels, out_host, stream);
     }
     THB_REQUIRE(!plan->rows_in_plan_order, "thb_eval_fused: rows_in_plan_order is only supported by the local-net formulation");
     for (int c = 0; c < nchannels; ++c) {
@@ -109,13 +111,13 @@ extern "C" int thb_eval_fused(const thb_space_desc* space, const thb_plan_desc* 
     return ops->fused(space, &ar, env_int("THB_FUSED_PPT", 2), cp_dim, der ? 1 : 0, st);
 }
 
-extern "C" int64_t thb_net_workspace_floats(const thb_space_desc* space, int with_derivatives) {
+extern "C" int64_t thb_net_workspace_floats(const thb_space_desc* space, int flags) {
     if (!space) return 0;
-    return (int64_t)space->nslots * (with_derivatives ? 8 : 4) * space->tile_stride;
+    return (int64_t)space->nslots * ((flags & THB_NETS_DERIVATIVES) ? 8 : 4) * space->tile_stride;
 }
 
 extern "C" int thb_cell_nets(const thb_space_desc* space, const thb_plan_desc* plan, const float* ctrl_pts, int cp_dim,
-                             int with_derivatives, float* nets, void* stream) {
+                             int flags, float* nets, void* stream) {
     int rc = thb_check_space(space, "thb_cell_nets");
     if (rc) return rc;
     THB_REQUIRE(ctrl_pts && nets, "thb_cell_nets: null pointer");
@@ -124,11 +126,14 @@ extern "C" int thb_cell_nets(const thb_space_desc* space, const thb_plan_desc* p
     const ShapeOps* ops = find_shape(space);
     if (!ops) return thb_set_error(THB_E_UNSUPPORTED, "thb_cell_nets: no kernel for degrees (%d,%d,%d)", space->degree[0], space->degree[1], space->degree[2]);
     NetArgs na = {};
-    na.ctrl_pts = ctrl_pts; na.cell_count = plan ? plan->cell_count : nullptr; na.nets = nets; na.planes = with_derivatives ? 8 : 4;
+    THB_REQUIRE(!(flags & THB_NETS_MONOMIAL) || space->poly, "thb_cell_nets: the monomial form needs the span polynomials (thb_space_desc::poly)");
+    na.ctrl_pts = ctrl_pts; na.cell_count = plan ? plan->cell_count : nullptr; na.nets = nets;
+    na.planes = (flags & THB_NETS_DERIVATIVES) ? 8 : 4;
+    na.mono = (flags & THB_NETS_MONOMIAL) ? 1 : 0;
     return ops->nets(space, &na, cp_dim, (cudaStream_t)stream);
 }
 
-extern "C" int thb_eval_nets(const thb_space_desc* space, const thb_plan_desc* plan, const float* nets, int with_derivatives,
+extern "C" int thb_eval_nets(const thb_space_desc* space, const thb_plan_desc* plan, const float* nets, int flags,
                              int cp_dim, const int32_t* channels, int nchannels, float* const* out_host, void* stream) {
     int rc = thb_check_space(space, "thb_eval_nets");
     if (rc) return rc;
@@ -141,7 +146,9 @@ extern "C" int thb_eval_nets(const thb_space_desc* space, const thb_plan_desc* p
     Args ar = {};
     bool der;
     if ((rc = fill_channels(ar, channels, nchannels, space->ndim, &der, "thb_eval_nets"))) return rc;
-    THB_REQUIRE(!der || with_derivatives, "thb_eval_nets: derivative channels need nets built with_derivatives");
+    const int with_derivatives = (flags & THB_NETS_DERIVATIVES) ? 1 : 0, mono = (flags & THB_NETS_MONOMIAL) ? 1 : 0;
+    THB_REQUIRE(!der || with_derivatives, "thb_eval_nets: derivative channels need nets built with THB_NETS_DERIVATIVES");
+    THB_REQUIRE(!mono || space->poly, "thb_eval_nets: the monomial form needs the span polynomials (thb_space_desc::poly)");
     for (int c = 0; c < nchannels; ++c) {
         THB_REQUIRE(out_host[c], "thb_eval_nets: null output");
         ar.out[c] = out_host[c];
@@ -150,7 +157,7 @@ extern "C" int thb_eval_nets(const thb_space_desc* space, const thb_plan_desc* p
     ar.rows_sorted = plan->rows_in_plan_order ? 1 : 0;
     cudaStream_t st = (cudaStream_t)stream;
     THB_CUDA(cudaMemsetAsync(plan->counters + 1, 0, sizeof(int32_t), st));
-    return ops->net_eval(space, &ar, nets, env_int("THB_NET_PPT", 2), cp_dim, with_derivatives ? 1 : 0, st);
+    return ops->net_eval(space, &ar, nets, env_int("THB_NET_PPT", 2), cp_dim, with_derivatives, mono, st);
 }
 
 static int fused_backward_impl(const thb_space_desc* space, const thb_plan_desc* plan, const float* params, const float* grad_out,

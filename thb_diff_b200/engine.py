@@ -175,31 +175,45 @@ def _check_rows(tensors, plan, cpd, name):
             raise RuntimeError(f"{name} must be [{plan.n}, {cpd}] float32 on {plan.P.device}, got {tuple(t.shape)} on {t.device}")
 
 
+NETS_DERIVATIVES, NETS_MONOMIAL = 1, 2
+
+
+def _net_flags(P, with_derivatives, monomial=None):
+    """flags of thb_cell_nets / thb_eval_nets: monomial nets by default whenever the hierarchy carries the span
+    polynomials (THB_NET_MONO=0 switches back to control-point nets evaluated with Cox-de Boor)."""
+    if monomial is None:
+        monomial = getattr(P, "poly", None) is not None and _os.environ.get("THB_NET_MONO", "1") != "0"
+    return (NETS_DERIVATIVES if with_derivatives else 0) | (NETS_MONOMIAL if monomial else 0)
+
+
 def net_workspace(P, with_derivatives=False):
     """Device buffer for the local control nets of P ([nslots][4 or 8][TS] f32), allocated once per hierarchy."""
     key = "_net_ws8" if with_derivatives else "_net_ws4"
     ws = getattr(P, key, None)
-    n = lib.thb_net_workspace_floats(C.byref(P.desc()), int(with_derivatives))
+    n = lib.thb_net_workspace_floats(C.byref(P.desc()), NETS_DERIVATIVES if with_derivatives else 0)
     if ws is None or ws.numel() != n:
         ws = torch.empty(n, dtype=torch.float32, device=P.device)
         setattr(P, key, ws)
     return ws
 
 
-def cell_nets(P, ctrl_pts, with_derivatives=False, plan=None, out=None):
+def cell_nets(P, ctrl_pts, with_derivatives=False, plan=None, out=None, monomial=None):
     """Local control nets W of the active cells (thb_cell_nets): every cell, or only those holding points of `plan`.
-    They stay valid for as long as ctrl_pts (and the hierarchy) do not change."""
+    They stay valid for as long as ctrl_pts (and the hierarchy) do not change.  monomial (default: yes when available):
+    the nets are stored as the coefficients of the cell's polynomial in cell-local coordinates, evaluated by Horner."""
     require_cuda(ctrl_pts, "ctrl_pts", torch.float32)
     if ctrl_pts.shape[1] not in (3, 4) or ctrl_pts.shape[0] != P.nCP:
         raise RuntimeError(f"ctrl_pts must be [{P.nCP}, 3 or 4]")
     if not P.has_tiles:
         raise RuntimeError("the hierarchy has no coefficient tiles yet (PackedHierarchy.attach_tiles / from_space)")
     nets = out if out is not None else net_workspace(P, with_derivatives)
+    flags = _net_flags(P, with_derivatives, monomial)
     if plan is not None:
         plan.refresh()
     with _on(P.device):
         check(lib.thb_cell_nets(C.byref(P.desc()), C.byref(plan.desc) if plan is not None else None, ptr(ctrl_pts), ctrl_pts.shape[1],
-                                int(with_derivatives), ptr(nets), stream_ptr(P.device)), "thb_cell_nets")
+                                flags, ptr(nets), stream_ptr(P.device)), "thb_cell_nets")
+    nets._thb_flags = flags
     return nets
 
 
@@ -223,10 +237,17 @@ def plan_and_nets(P, plan, ctrl_pts, with_derivatives=False, overlap=True):
     return nets
 
 
-def eval_nets(P, plan, nets, cp_dim=3, channels=(CH_VALUE,), out=None, with_derivatives=None):
-    """Evaluates the plan's points against prebuilt nets (thb_eval_nets)."""
-    if with_derivatives is None:
-        with_derivatives = nets.numel() == lib.thb_net_workspace_floats(C.byref(P.desc()), 1)
+def eval_nets(P, plan, nets, cp_dim=3, channels=(CH_VALUE,), out=None, with_derivatives=None, monomial=None):
+    """Evaluates the plan's points against prebuilt nets (thb_eval_nets).  The layout of `nets` (derivative planes,
+    monomial form) is the one cell_nets recorded on the tensor; pass with_derivatives / monomial for foreign buffers."""
+    flags = getattr(nets, "_thb_flags", None)
+    if flags is None or with_derivatives is not None or monomial is not None:
+        if with_derivatives is None:
+            with_derivatives = bool(flags & NETS_DERIVATIVES) if flags is not None else \
+                nets.numel() == lib.thb_net_workspace_floats(C.byref(P.desc()), NETS_DERIVATIVES)
+        if monomial is None:
+            monomial = bool(flags & NETS_MONOMIAL) if flags is not None else False
+        flags = (NETS_DERIVATIVES if with_derivatives else 0) | (NETS_MONOMIAL if monomial else 0)
     plan.refresh()
     if out is None:
         out = [torch.zeros((plan.n, cp_dim), dtype=torch.float32, device=P.device) for _ in channels]
@@ -235,7 +256,7 @@ def eval_nets(P, plan, nets, cp_dim=3, channels=(CH_VALUE,), out=None, with_deri
     _check_rows(out, plan, cp_dim, "out")
     arr = (C.c_void_p * len(out))(*[o.data_ptr() for o in out])
     with _on(P.device):
-        check(lib.thb_eval_nets(C.byref(P.desc()), C.byref(plan.desc), ptr(nets), int(with_derivatives), cp_dim, _chan_array(channels),
+        check(lib.thb_eval_nets(C.byref(P.desc()), C.byref(plan.desc), ptr(nets), flags, cp_dim, _chan_array(channels),
                                 len(channels), arr, stream_ptr(P.device)), "thb_eval_nets")
     return out
 
@@ -287,7 +308,7 @@ def eval_fused_backward(P, plan, grad_out, cp_dim=None, formulation="local_net")
 
 def _gnet_workspace(P):
     ws = getattr(P, "_gnet_ws", None)
-    n = lib.thb_net_workspace_floats(C.byref(P.desc()), 0)
+    n = lib.thb_net_workspace_floats(C.byref(P.desc()), 0)   # net GRADIENTS: always the control-point form, four planes
     if ws is None or ws.numel() != n:
         ws = P._gnet_ws = torch.empty(n, dtype=torch.float32, device=P.device)
     return ws
