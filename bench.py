@@ -53,21 +53,28 @@ def flop_model(degrees, cpd, n_in, nnz, nnz_tiled, nnz_sep=0):
     return float(executed), float(dense)
 
 
-def flop_model_local_net(P, plan, cpd, n_in):
-    """(FLOPs of k_net_eval, FLOPs of k_cell_nets), thb_net_impl.cuh.  Evaluation: per point Cox-de Boor and the
-    sum-factorised contraction with the cell's net (T + N0*N2 + N0 FMAs per output component, 3-D).  Nets: per cell
-    that holds points, per rank-one support 1.5 multiplications + cp_dim FMAs for each of the TS window entries, per
-    full tile cp_dim FMAs per entry."""
+def flop_model_local_net(P, plan, cpd, n_in, mono=False):
+    """(FLOPs of k_net_eval, FLOPs of k_cell_nets), thb_net_impl.cuh.
+    Evaluation, control-point nets: per point Cox-de Boor and the sum-factorised contraction with the cell's net
+    (T + N0*N2 + N0 FMAs per output component, 3-D).  Monomial nets: per point three (subtract, FMA) pairs for the local
+    coordinates and a nested Horner scheme, (N1-1)*N0*N2 + (N0-1)*N2 + (N2-1) FMAs per output component.
+    Nets: per cell that holds points, per rank-one support 1.5 multiplications + cp_dim FMAs for each of the TS window
+    entries, per full tile cp_dim FMAs per entry; monomial form: + three passes of N_k FMAs per entry and component."""
 
     deg = P.degrees
     d = len(deg)
     N = [p + 1 for p in deg] + ([1] if d == 2 else [])
     T = N[0] * N[1] * N[2]
-    per_pt = sum(cdb_flops(p) for p in deg) + cpd * 2 * (T + N[0] * N[2] + N[0])
+    if mono:
+        per_pt = 3 * d + cpd * 2 * ((N[1] - 1) * N[0] * N[2] + (N[0] - 1) * N[2] + (N[2] - 1))
+    else:
+        per_pt = sum(cdb_flops(p) for p in deg) + cpd * 2 * (T + N[0] * N[2] + N[0])
     used = (plan.cell_count[: P.nslots] > 0).long()
     info = P.cellinfo.long()
     nt, nsep = info[:, 5] - info[:, 7], info[:, 9]
     fold = (used * nsep).sum() * P.TS * (1.5 + 2 * cpd) + (used * (nt - nsep)).sum() * P.TS * 2 * cpd
+    if mono:
+        fold = fold + used.sum() * T * cpd * 2 * sum(N[:d])
     return float(n_in * per_pt), float(fold)
 
 
@@ -492,6 +499,7 @@ def main():
     ap.add_argument("--no-variants", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--inner", type=int, default=100, help="identical passes of the hot path per timed step (timed region of about a second)")
+    ap.add_argument("--no-overlap", action="store_true", help="plan, nets and evaluation one after the other on one stream")
     ap.add_argument("--no-blocks", action="store_true", help="skip the strong-scaling / config 4 / config 5 blocks")
     ap.add_argument("--cell-cost", type=float, default=100.0, help="cost of a touched cell in point evaluations (slab / cell balancing)")
     ap.add_argument("--e2e-chunks", type=int, default=8)
@@ -526,23 +534,34 @@ def main():
     out = [torch.zeros((n, 3), dtype=torch.float32, device=device)]
     st = torch.cuda.current_stream()
 
+    mono = engine._net_flags(P, False) & engine.NETS_MONOMIAL != 0
+
     def step(timers=None):
-        if timers is not None:
-            timers[0].record()
-        plan.build()
-        if timers is not None:
-            timers[1].record()
-        if args.formulation == "local_net":   # = engine.eval_fused(..., formulation="local_net"), its two launches timed apart
-            nets = engine.cell_nets(P, cp, plan=plan)
+        """One pass.  Timed region: the plan on the current stream and, beside it on a second stream, the local control nets
+        (they depend on the control points only), then the evaluation kernel -- engine.plan_and_nets(overlap=True).
+        With timers: the same three pieces one after the other on one stream, each between two events (breakdown pass)."""
+        if args.formulation != "local_net":
             if timers is not None:
-                timers[3].record()
-            engine.eval_nets(P, plan, nets, 3, out=out, with_derivatives=False)
-        else:
+                timers[0].record()
+            plan.build()
             if timers is not None:
+                timers[1].record()
                 timers[3].record()
             engine.eval_fused(P, plan, cp, formulation=args.formulation, out=out)
-        if timers is not None:
-            timers[2].record()
+            if timers is not None:
+                timers[2].record()
+            return
+        if timers is None:
+            nets = engine.plan_and_nets(P, plan, cp, overlap=not args.no_overlap)
+            engine.eval_nets(P, plan, nets, 3, out=out, with_derivatives=False)
+            return
+        timers[0].record()
+        plan.build()
+        timers[1].record()
+        nets = engine.cell_nets(P, cp, plan=plan)
+        timers[3].record()
+        engine.eval_nets(P, plan, nets, 3, out=out, with_derivatives=False)
+        timers[2].record()
 
     def barrier():
         torch.cuda.synchronize()
@@ -557,22 +576,26 @@ def main():
         step()
     clk = ClockSampler(local)
     clk.__enter__()  # samples during the timed region only (steps x inner passes, about a second)
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps * inner)]
     barrier()
     launches0 = _lib.launch_count()
     t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_beg.record()
     for k in range(args.steps * inner):
-        step(ev[k])
+        step()
     t_end.record()
     barrier()
     clk.__exit__()
     launches = _lib.launch_count() - launches0
     total_ms = t_beg.elapsed_time(t_end)
-    npass = args.steps * inner
-    plan_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / npass
-    nets_ms = sum(e[1].elapsed_time(e[3]) for e in ev) / npass   # local control nets of the cells that hold points
-    kern_ms = sum(e[3].elapsed_time(e[2]) for e in ev) / npass   # the evaluation kernel
+    # breakdown pass (not the headline): the three pieces serialised on one stream, CUDA events around each
+    nb = max(20, min(100, args.steps * inner // 10))
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(nb)]
+    for k in range(nb):
+        step(ev[k])
+    torch.cuda.synchronize()
+    plan_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / nb
+    nets_ms = sum(e[1].elapsed_time(e[3]) for e in ev) / nb   # local control nets of the cells that hold points
+    kern_ms = sum(e[3].elapsed_time(e[2]) for e in ev) / nb   # the evaluation kernel
     del ev
     tmax = torch.tensor([total_ms], device=device)
     if world > 1:
@@ -649,7 +672,7 @@ def main():
     f_exec, f_dense = flop_model(P.degrees, 3, n_in, nnz, nnz_tiled, nnz_sep)
     f_nets = 0.0
     if args.formulation == "local_net":
-        f_exec, f_nets = flop_model_local_net(P, plan, 3, n_in)
+        f_exec, f_nets = flop_model_local_net(P, plan, 3, n_in, mono=mono)
     elif args.formulation == "tile_net":  # per point the tensor product and the window dot products; all tiles folded per item
         cnt = plan.cell_count[: P.nslots].long()
         nt = (P.cellinfo[:, 5] - P.cellinfo[:, 7]).long()
@@ -670,7 +693,7 @@ def main():
     except Exception:
         pass
     roofline = {
-        "bound": bound, "kernel": "thb_tile::k_net_eval<4,4,4,2,3,0>" if args.formulation == "local_net" else "thb_tile::k_tile<4,4,4,2,3,FUSED>",
+        "bound": bound, "kernel": ("thb_tile::k_net_eval<4,4,4,4,3,0,MONO>" if mono else "thb_tile::k_net_eval<4,4,4,2,3,0>") if args.formulation == "local_net" else "thb_tile::k_tile<4,4,4,2,3,FUSED>",
         "achieved": (f_exec / (kern_ms * 1e-3) / 1e12) if bound == "fp32" else (alg_bytes / (kern_ms * 1e-3) / 1e9),
         "peak": fp32_peak if bound == "fp32" else hbm_peak, "unit": "TFLOP/s" if bound == "fp32" else "GB/s",
         "frac": t_roof / (kern_ms * 1e-3), "traffic": traffic,
@@ -702,6 +725,8 @@ def main():
                    "table_bytes": P.nbytes(), "l2": "inputs (201 MB params + 201 MB output per pass) exceed the 126 MB L2",
                    "passes_per_step": inner, "ms_per_pass": ms_per_pass,
                    "tables": "dense one-hot tiles" if args.dense else "own-level supports direct, rank-one tiles as 3 factor vectors, full tiles otherwise", "formulation": args.formulation,
+                   "nets": ("monomial form, nested Horner evaluation" if mono else "control points, Cox-de Boor + sum factorisation") if args.formulation == "local_net" else None,
+                   "step": "plan || nets (second stream), then evaluation" if (args.formulation == "local_net" and not args.no_overlap) else "plan, nets, evaluation on one stream",
                    "sharding": f"y planes round-robin over {world} rank(s), no collective"},
         "clocks": clk.summary(), "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": n * P.ndim * 4, "d2h_bytes_per_step": n * 3 * 4,

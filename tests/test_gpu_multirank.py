@@ -1,0 +1,102 @@
+"""Two ranks over NCCL (needs two GPUs; skipped otherwise): the fit step of BASELINE config 4 with the points moved to the rank
+that owns their cell (all-to-all) and the compact active-row gradient all-reduced gives the same losses and control points as
+one rank; sharded evaluation of a grid in cost-balanced slabs reproduces the unsharded result."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _fit_worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from thb_diff_b200 import configs, engine
+    from thb_diff_b200.distributed import FitEngine, grid_slab_bounds, partition_by_cell, shard_bounds
+    from thb_diff_b200.packed import PackedHierarchy
+
+    sp = configs.cubic3d_space(active_levels=3, base_cells=8)
+    P = PackedHierarchy.from_space(sp, device=dev)
+    n_total = 200_003
+    gen = torch.Generator(device=dev).manual_seed(0)
+    prm_all = torch.rand((n_total, 3), device=dev, generator=gen)
+    tgt_all = torch.stack([prm_all[:, 0], prm_all[:, 1], prm_all[:, 2] + 0.1 * torch.sin(6.2831853 * prm_all[:, 0])], 1).contiguous()
+    x0 = torch.from_numpy(configs.greville_ctrl_pts(sp, bump=0.0)).to(dev)
+
+    def run(prm, tgt, use_graph):
+        x = x0.clone()
+        eng = FitEngine(P, prm, tgt, n_total, lr=1e-2, use_graph=use_graph)
+        losses = []
+        for _ in range(6):
+            l = eng.step(x).clone()
+            dist.all_reduce(l)
+            losses.append(float(l))
+        return x, losses
+
+    lo, hi = shard_bounds(n_total, rank, world)
+    slot, _ = engine.active_span(P, prm_all[lo:hi], want_num_supp=False)
+    rows, bounds = partition_by_cell(slot, P.nslots, torch.cat([prm_all[lo:hi], tgt_all[lo:hi]], 1).contiguous())
+    res = {}
+    for use_graph in (False, True):
+        x, losses = run(rows[:, :3].contiguous(), rows[:, 3:].contiguous(), use_graph)
+        res[use_graph] = (x.cpu().numpy(), losses)
+    # sharded evaluation of a grid
+    ax = [torch.from_numpy(np.linspace(1e-5, 1.0, 40, endpoint=False)).float().to(dev) for _ in range(3)]
+    b = grid_slab_bounds(P, ax, world).tolist()
+    pts = torch.stack(torch.meshgrid(ax[0][b[rank]:b[rank + 1]], ax[1], ax[2], indexing="ij"), -1).reshape(-1, 3).contiguous()
+    out = engine.eval_fused(P, engine.Plan(P, pts), x0 + 0.01)[0]
+    ret[rank] = dict(fit=res, n_mine=int(rows.shape[0]), bounds=bounds.tolist(), slab=b, out=out.cpu().numpy(), pts=pts.cpu().numpy())
+    dist.destroy_process_group()
+
+
+def test_two_rank_fit_and_sharded_evaluation_over_nccl():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+
+    sys.path.insert(0, ROOT)
+    from thb_diff_b200 import configs, engine
+    from thb_diff_b200.distributed import FitEngine
+    from thb_diff_b200.packed import PackedHierarchy
+
+    world = 2
+    port = 32500 + (os.getpid() % 2000)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_fit_worker, args=(world, port, ret), nprocs=world, join=True)
+    # single-rank reference in this process
+    dev = torch.device("cuda", 0)
+    sp = configs.cubic3d_space(active_levels=3, base_cells=8)
+    P = PackedHierarchy.from_space(sp, device=dev)
+    n_total = 200_003
+    gen = torch.Generator(device=dev).manual_seed(0)
+    prm = torch.rand((n_total, 3), device=dev, generator=gen)
+    tgt = torch.stack([prm[:, 0], prm[:, 1], prm[:, 2] + 0.1 * torch.sin(6.2831853 * prm[:, 0])], 1).contiguous()
+    x = torch.from_numpy(configs.greville_ctrl_pts(sp, bump=0.0)).to(dev)
+    x0 = x.clone()
+    eng = FitEngine(P, prm, tgt, n_total, lr=1e-2)
+    ref_losses = [float(eng.step(x)) for _ in range(6)]
+    assert ret[0]["n_mine"] + ret[1]["n_mine"] == n_total and min(ret[0]["n_mine"], ret[1]["n_mine"]) > 0.3 * n_total
+    for r in range(world):
+        for use_graph in (False, True):
+            xr, losses = ret[r]["fit"][use_graph]
+            assert np.allclose(losses, ref_losses, rtol=1e-5, atol=1e-10), (r, use_graph, losses, ref_losses)
+            assert np.abs(xr - x.cpu().numpy()).max() <= 5e-5
+    assert np.array_equal(ret[0]["fit"][False][0], ret[1]["fit"][False][0])   # replicated parameters stay bit-identical
+    # sharded evaluation == unsharded
+    ax = np.linspace(1e-5, 1.0, 40, endpoint=False).astype(np.float32)
+    pts = np.concatenate([ret[r]["pts"] for r in range(world)])
+    full = np.stack(np.meshgrid(ax, ax, ax, indexing="ij"), -1).reshape(-1, 3)
+    assert np.array_equal(pts, full) and ret[0]["slab"][0] == 0 and ret[1]["slab"][-1] == 40
+    out = engine.eval_fused(P, engine.Plan(P, torch.from_numpy(full).to(dev)), x0 + 0.01)[0].cpu().numpy()
+    assert np.abs(np.concatenate([ret[r]["out"] for r in range(world)]) - out).max() <= 1e-6

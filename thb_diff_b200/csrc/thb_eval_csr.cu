@@ -18,170 +18,343 @@ constexpr int kWarpsPerCta = 8;
 
 constexpr int kFwdStrips = 5;   // support lists up to 160 entries live in registers (one entry per lane and strip)
 #ifndef THB_FWD_POINTS
-#define THB_FWD_POINTS 16
+#define THB_FWD_POINTS 32
 #endif
-constexpr int kFwdPoints = THB_FWD_POINTS;  // consecutive points per warp
+constexpr int kFwdPoints = THB_FWD_POINTS;  // consecutive points per warp (a multiple of kFwdBatch)
+constexpr int kFwdBatch = 8;                // points whose per-lane partial sums are reduced together
+
+// Sum over the 32 lanes of NB = 8 values per lane at once: three exchange steps halve the number of values a lane holds
+// (lanes that differ in bit 4, 3, 2 split the values between them), two butterfly steps finish.  9 shuffles per 8 points
+// and component instead of 40 for eight separate butterflies.  Afterwards lane l with (l & 3) == 0 holds the total of value
+// index ((l >> 4) & 1) * 4 + ((l >> 3) & 1) * 2 + ((l >> 2) & 1).
+THB_DEV float reduce8(float (&v)[8], int lane) {
+    float w4[4], w2[2];
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float send = b4 ? v[j] : v[j + 4];
+        const float keep = b4 ? v[j + 4] : v[j];
+        w4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const float send = b3 ? w4[j] : w4[j + 2];
+        const float keep = b3 ? w4[j + 2] : w4[j];
+        w2[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    const float send = b2 ? w2[0] : w2[1];
+    const float keep = b2 ? w2[1] : w2[0];
+    float r = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    r += __shfl_xor_sync(0xffffffffu, r, 2);
+    r += __shfl_xor_sync(0xffffffffu, r, 1);
+    return r;
+}
 
 // A warp owns kFwdPoints consecutive points.  Per point the lanes read the segment coalesced (one entry per lane and
-// strip).  The gathered control points stay in registers for as long as consecutive points have the same support
-// list (points of one cell do), so the dependent second round trip of a point -- the gather through Jm -- disappears
-// inside a run.  (A variant that streams the warp's contiguous PHI / Jm run through a shared-memory ring with
-// 16-byte cp.async was measured at 4.4 ms int64 / 3.2 ms int32 against 3.7 / 3.7 ms for this one on config 3: its
-// per-point bookkeeping executes 3.2 G warp-instructions, so it is issue-bound before it is bandwidth-bound.)
+// strip).  The gathered control points stay in registers for as long as consecutive points have the same support list
+// (points of one cell do), so the dependent second round trip of a point -- the gather through Jm -- disappears inside a
+// run.  Points are taken NPT at a time: the loads of all of them are issued before any is used (bytes in flight per warp),
+// and the body is specialised for the number of strips NS the longest of them needs (no per-strip branches); per-lane
+// partial sums are reduced eight points at a time (reduce8).  Segment ends travel as 32-bit offsets from the warp's first
+// entry.  History on config 3 (16.8 M points, 1.16 G pairs): one point at a time with five fixed strips and a butterfly
+// per point and component 3.66 ms int64 / 3.71 ms int32 (2.4 G warp-instructions, issue-bound); a variant that streams
+// PHI / Jm through a shared-memory ring with 16-byte cp.async 4.4 / 3.2 ms (3.2 G warp-instructions).
+template <typename JT, int CPD>
+struct FwdCache {
+    JT key[kFwdStrips];
+    float cpv[kFwdStrips][CPD];
+    int runS;
+};
+
+// NPT points starting at entry offsets ob[h] (relative to base), lengths S[h] <= 32 * NS; a[h][k] = per-lane partial sums
+template <typename JT, int CPD, int NS, int NPT>
+THB_DEV void fwd_points(const float* __restrict__ cp, const JT* __restrict__ jm, const float* __restrict__ phi, int64_t base,
+                        const int (&ob)[NPT], const int (&S)[NPT], FwdCache<JT, CPD>& c, float (&a)[NPT][CPD], int lane) {
+    JT cj[NPT][NS];
+    float cw[NPT][NS];
+#pragma unroll
+    for (int h = 0; h < NPT; ++h) {
+        const JT* pj = jm + base + ob[h] + lane;
+        const float* pw = phi + base + ob[h] + lane;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            const bool ok = s * 32 + lane < S[h];
+            cj[h][s] = ok ? __ldg(pj + s * 32) : (JT)-1;
+            cw[h][s] = ok ? __ldg(pw + s * 32) : 0.0f;
+        }
+    }
+#pragma unroll
+    for (int h = 0; h < NPT; ++h) {
+        bool same = S[h] == c.runS;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) same = same && (cj[h][s] == c.key[s]);
+        if (!__all_sync(0xffffffffu, same)) {
+#pragma unroll
+            for (int s = 0; s < kFwdStrips; ++s) c.key[s] = s < NS ? cj[h][s < NS ? s : 0] : (JT)-1;
+#pragma unroll
+            for (int s = 0; s < kFwdStrips; ++s) {   // strips beyond NS hold zeros: a later, wider body multiplies them by 0
+#pragma unroll
+                for (int k = 0; k < CPD; ++k)
+                    c.cpv[s][k] = (s < NS && cj[h][s < NS ? s : 0] >= 0) ? __ldg(cp + (int64_t)cj[h][s < NS ? s : 0] * CPD + k) : 0.0f;
+            }
+            c.runS = S[h];
+        }
+#pragma unroll
+        for (int k = 0; k < CPD; ++k) a[h][k] = 0.0f;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+#pragma unroll
+            for (int k = 0; k < CPD; ++k) a[h][k] = fmaf(cw[h][s], c.cpv[s][k], a[h][k]);
+        }
+    }
+}
+
 template <typename JT, typename CT, int CPD>
 __global__ void __launch_bounds__(kWarpsPerCta * 32) k_csr_forward(const float* __restrict__ cp, const JT* __restrict__ jm,
                                                                      const float* __restrict__ phi,
                                                                      const CT* __restrict__ cumsum, float* __restrict__ out,
                                                                      int64_t npoints) {
+    constexpr int NPT = 4;
+    static_assert(kFwdBatch % NPT == 0 && kFwdPoints % kFwdBatch == 0 && kFwdPoints <= 32, "point grouping");
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
     const int64_t p0 = warp * kFwdPoints;
     if (p0 >= npoints) return;
     const int np = (int)min((int64_t)kFwdPoints, npoints - p0);
-    // segment bounds of the warp's points: lane l holds the END of point p0 + l
-    const int64_t my_end = lane < np ? (int64_t)cumsum[p0 + lane] : 0;
-    int64_t beg = p0 ? (int64_t)cumsum[p0 - 1] : 0;
+    const int64_t base = p0 ? (int64_t)cumsum[p0 - 1] : 0;
+    // segment ends of the warp's points as offsets from `base`: lane l holds the END of point p0 + l.  A warp whose
+    // points hold more than 2^31 - 1 pairs together cannot occur with lists that fit the register path; longer lists take
+    // the streamed path below, which works on 64-bit positions.
+    const int64_t end64 = lane < np ? (int64_t)cumsum[p0 + lane] : 0;
+    const int64_t span = __shfl_sync(0xffffffffu, end64, np - 1) - base;
+    const bool small = span < (int64_t)0x7fffffff;
+    const int my_end = small ? (int)(end64 - base) : 0;
 
-    JT key[kFwdStrips];
-    float cpv[kFwdStrips][CPD];
-    int runS = -1;
+    FwdCache<JT, CPD> c;
+    c.runS = -1;
 #pragma unroll
-    for (int s = 0; s < kFwdStrips; ++s) key[s] = (JT)-2;
+    for (int s = 0; s < kFwdStrips; ++s) c.key[s] = (JT)-2;
 
-    for (int i = 0; i < np; ++i) {
-        const int64_t end = __shfl_sync(0xffffffffu, my_end, i);
-        const int64_t S64 = end - beg;
-        float acc[CPD];
+    int beg = 0;
+    for (int i0 = 0; i0 < np; i0 += kFwdBatch) {
+        float acc[CPD][kFwdBatch];
 #pragma unroll
-        for (int k = 0; k < CPD; ++k) acc[k] = 0.0f;
-        if (S64 <= 32 * kFwdStrips) {
-            const int S = (int)S64;
-            JT cj[kFwdStrips];
-            float cw[kFwdStrips];
-            bool same = S == runS;
+        for (int j0 = 0; j0 < kFwdBatch; j0 += NPT) {
+            float a[NPT][CPD];
 #pragma unroll
-            for (int s = 0; s < kFwdStrips; ++s) {
-                const int o = s * 32 + lane;
-                const bool ok = o < S;
-                cj[s] = ok ? __ldg(jm + beg + o) : (JT)-1;
-                cw[s] = ok ? __ldg(phi + beg + o) : 0.0f;
-            }
+            for (int h = 0; h < NPT; ++h)
 #pragma unroll
-            for (int s = 0; s < kFwdStrips; ++s) same = same && (cj[s] == key[s]);
-            if (!__all_sync(0xffffffffu, same)) {
+                for (int k = 0; k < CPD; ++k) a[h][k] = 0.0f;
+            if (i0 + j0 < np) {   // warp-uniform
+                int ob[NPT], S[NPT], smax = 0;
 #pragma unroll
-                for (int s = 0; s < kFwdStrips; ++s) {
-                    key[s] = cj[s];
-#pragma unroll
-                    for (int k = 0; k < CPD; ++k) cpv[s][k] = cj[s] >= 0 ? __ldg(cp + (int64_t)cj[s] * CPD + k) : 0.0f;
+                for (int h = 0; h < NPT; ++h) {
+                    const int i = i0 + j0 + h;
+                    const int e = (small && i < np) ? __shfl_sync(0xffffffffu, my_end, i & 31) : beg;
+                    ob[h] = beg;
+                    S[h] = e - beg;
+                    beg = e;
+                    smax = max(smax, S[h]);
                 }
-                runS = S;
+                if (small && smax <= 64) fwd_points<JT, CPD, 2, NPT>(cp, jm, phi, base, ob, S, c, a, lane);
+                else if (small && smax <= 96) fwd_points<JT, CPD, 3, NPT>(cp, jm, phi, base, ob, S, c, a, lane);
+                else if (small && smax <= 32 * kFwdStrips) fwd_points<JT, CPD, kFwdStrips, NPT>(cp, jm, phi, base, ob, S, c, a, lane);
+                else {  // very long lists (or a warp spanning > 2^31 pairs): streamed on 64-bit positions, nothing cached
+#pragma unroll
+                    for (int h = 0; h < NPT; ++h) {
+                        const int i = i0 + j0 + h;
+                        if (i >= np) break;
+                        const int64_t pb = i ? __shfl_sync(0xffffffffu, end64, (i - 1) & 31) : base;
+                        const int64_t pe = __shfl_sync(0xffffffffu, end64, i & 31);
+                        for (int64_t j = pb + lane; j < pe; j += 32) {
+                            const float w = __ldg(phi + j);
+                            const int64_t r = (int64_t)__ldg(jm + j);
+#pragma unroll
+                            for (int k = 0; k < CPD; ++k) a[h][k] = fmaf(w, __ldg(cp + r * CPD + k), a[h][k]);
+                        }
+                    }
+                    c.runS = -1;
+                }
             }
 #pragma unroll
-            for (int s = 0; s < kFwdStrips; ++s)
+            for (int h = 0; h < NPT; ++h)
 #pragma unroll
-                for (int k = 0; k < CPD; ++k) acc[k] = fmaf(cw[s], cpv[s][k], acc[k]);
-        } else {  // very long list: streamed, nothing cached
-            for (int64_t j = beg + lane; j < end; j += 32) {
-                const float w = __ldg(phi + j);
-                const int64_t r = (int64_t)__ldg(jm + j);
-#pragma unroll
-                for (int k = 0; k < CPD; ++k) acc[k] = fmaf(w, __ldg(cp + r * CPD + k), acc[k]);
-            }
+                for (int k = 0; k < CPD; ++k) acc[k][j0 + h] = a[h][k];
         }
+        // ---- eight points reduced together; lane l with (l & 3) == 0 holds point ((l>>4)&1)*4 + ((l>>3)&1)*2 + ((l>>2)&1)
+        const int mine = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
 #pragma unroll
         for (int k = 0; k < CPD; ++k) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+            const float r = reduce8(acc[k], lane);
+            if ((lane & 3) == 0 && i0 + mine < np) out[(p0 + i0 + mine) * CPD + k] = r;
         }
-        if (lane == 0) {
-#pragma unroll
-            for (int k = 0; k < CPD; ++k) out[(p0 + i) * CPD + k] = acc[k];
-        }
-        beg = end;
     }
 }
 
-constexpr int kStrips = 6;  // support lists up to 192 entries are aggregated across points
+constexpr int kStrips = kFwdStrips;  // support lists up to 160 entries are aggregated across points
+
+// grad_ctrl_pts[Jm[j]] += PHI[j] * grad_out[i].  A warp owns a run of consecutive points; per point the lanes read the
+// segment coalesced, NPT points at a time (all loads first), body specialised for the number of strips.  While consecutive
+// points have the same support list the products are accumulated in registers; the atomics are issued only when the list
+// changes (or the warp's run ends): cp_dim * S atomics per RUN of points instead of per point -- the warp-aggregated
+// scatter-add.
+template <typename JT, int CPD>
+struct BwdCache {
+    JT key[kStrips];
+    float acc[kStrips][CPD];
+    int runS;
+};
+
+// One row of the gradient: cp_dim reductions, issued as vector reductions (red.global.add.v2 / .v4.f32, sm_90+) where the
+// address allows -- rows of three floats start on an 8-byte boundary when the row index is even and 4 bytes after one when
+// it is odd, so a row is always one 8-byte pair plus one scalar: two L2 atomic operations instead of three (the backward is
+// bound by the L2 atomic units, not by HBM: 270 M row flushes on config 3).  vec: the buffer itself is 16-byte aligned.
+THB_DEV void red_v2(float* p, float a, float b) { asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory"); }
+THB_DEV void red_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+template <int CPD>
+THB_DEV void red_row(float* __restrict__ gcp, int64_t row, const float (&v)[CPD], bool vec) {
+    float* p = gcp + row * CPD;
+    if (!vec || CPD == 1) {
+#pragma unroll
+        for (int k = 0; k < CPD; ++k) atomicAdd(p + k, v[k]);
+    } else if constexpr (CPD == 2) {
+        red_v2(p, v[0], v[1]);
+    } else if constexpr (CPD == 3) {
+        if (row & 1) { atomicAdd(p, v[0]); red_v2(p + 1, v[1], v[2]); }
+        else { red_v2(p, v[0], v[1]); atomicAdd(p + 2, v[2]); }
+    } else if constexpr (CPD == 4) {
+        red_v4(p, v[0], v[1], v[2], v[3]);
+    }
+}
+
+template <typename JT, int CPD>
+THB_DEV void bwd_flush(BwdCache<JT, CPD>& c, float* __restrict__ gcp, bool vec) {
+#pragma unroll
+    for (int s = 0; s < kStrips; ++s) {
+        if (s * 32 < c.runS) {   // warp-uniform
+            if (c.key[s] >= 0) red_row<CPD>(gcp, (int64_t)c.key[s], c.acc[s], vec);
+#pragma unroll
+            for (int k = 0; k < CPD; ++k) c.acc[s][k] = 0.0f;
+        }
+        c.key[s] = (JT)-1;
+    }
+    c.runS = -1;
+}
+
+template <typename JT, int CPD, int NS, int NPT>
+THB_DEV void bwd_points(const float* __restrict__ gout, const JT* __restrict__ jm, const float* __restrict__ phi, int64_t base,
+                        int64_t row0, int nvalid, const int (&ob)[NPT], const int (&S)[NPT], BwdCache<JT, CPD>& c,
+                        float* __restrict__ gcp, int lane, bool vec) {
+    JT cj[NPT][NS];
+    float cw[NPT][NS], g[NPT][CPD];
+#pragma unroll
+    for (int h = 0; h < NPT; ++h) {
+        const JT* pj = jm + base + ob[h] + lane;
+        const float* pw = phi + base + ob[h] + lane;
+        const int64_t row = row0 + (h < nvalid ? h : 0);
+#pragma unroll
+        for (int k = 0; k < CPD; ++k) g[h][k] = __ldg(gout + row * CPD + k);
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            const bool ok = s * 32 + lane < S[h];
+            cj[h][s] = ok ? __ldg(pj + s * 32) : (JT)-1;
+            cw[h][s] = ok ? __ldg(pw + s * 32) : 0.0f;
+        }
+    }
+#pragma unroll
+    for (int h = 0; h < NPT; ++h) {
+        if (h >= nvalid) break;   // warp-uniform
+        bool same = S[h] == c.runS;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) same = same && (cj[h][s] == c.key[s]);
+        if (!__all_sync(0xffffffffu, same)) {
+            bwd_flush<JT, CPD>(c, gcp, vec);
+#pragma unroll
+            for (int s = 0; s < NS; ++s) c.key[s] = cj[h][s];
+            c.runS = S[h];
+        }
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+#pragma unroll
+            for (int k = 0; k < CPD; ++k) c.acc[s][k] = fmaf(cw[h][s], g[h][k], c.acc[s][k]);
+        }
+    }
+}
 
 template <typename JT, typename CT, int CPD>
 __global__ void __launch_bounds__(kWarpsPerCta * 32) k_csr_backward(const float* __restrict__ gout, const JT* __restrict__ jm,
                                                                       const float* __restrict__ phi,
                                                                       const CT* __restrict__ cumsum, float* __restrict__ gcp,
-                                                                      int64_t npoints, int pts_per_warp) {
+                                                                      int64_t npoints, int pts_per_warp, int64_t perm_stride) {
+    constexpr int NPT = 4;
     const int lane = threadIdx.x & 31;
-    const int64_t warp = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+    int64_t warp = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+    {   // Warps that run at the same time take point blocks far apart (block index times a stride coprime to the block
+        // count): neighbouring points add into the same control points, and atomics on one address serialise in L2 --
+        // with the blocks dealt in order the config-3 backward took 5.5 ms, spread out 3.0 ms (int32 indices).
+        const int64_t nw = (npoints + pts_per_warp - 1) / pts_per_warp;
+        if (warp >= nw) return;
+        warp = (warp * perm_stride) % nw;
+    }
+    const bool vec = (reinterpret_cast<uintptr_t>(gcp) & 15) == 0;
     const int64_t p0 = warp * pts_per_warp;
     if (p0 >= npoints) return;
     const int64_t p1 = (p0 + pts_per_warp < npoints) ? p0 + pts_per_warp : npoints;
 
-    float acc[kStrips][CPD];
-    long long key[kStrips];
+    BwdCache<JT, CPD> c;
 #pragma unroll
     for (int s = 0; s < kStrips; ++s) {
-        key[s] = -1;
+        c.key[s] = (JT)-1;
 #pragma unroll
-        for (int k = 0; k < CPD; ++k) acc[s][k] = 0.0f;
+        for (int k = 0; k < CPD; ++k) c.acc[s][k] = 0.0f;
     }
-    int runS = -1;
+    c.runS = -1;
 
-    auto flush = [&]() {
+    int64_t base = p0 ? (int64_t)cumsum[p0 - 1] : 0;
+    for (int64_t c0 = p0; c0 < p1; c0 += 32) {
+        // ends of up to 32 points at once (one coalesced load) as 32-bit offsets from the first entry of the group
+        const int nc = (int)min((int64_t)32, p1 - c0);
+        const int64_t end64 = lane < nc ? (int64_t)cumsum[c0 + lane] : 0;
+        const int64_t last = __shfl_sync(0xffffffffu, end64, nc - 1);
+        const bool small = last - base < (int64_t)0x7fffffff;
+        const int my_end = small ? (int)(end64 - base) : 0;
+        int beg = 0;
+        for (int i = 0; i < nc; i += NPT) {
+            int ob[NPT], S[NPT], smax = 0;
 #pragma unroll
-        for (int s = 0; s < kStrips; ++s) {
-            if (key[s] >= 0) {
-#pragma unroll
-                for (int k = 0; k < CPD; ++k) atomicAdd(gcp + key[s] * CPD + k, acc[s][k]);
+            for (int h = 0; h < NPT; ++h) {
+                const int e = (small && i + h < nc) ? __shfl_sync(0xffffffffu, my_end, (i + h) & 31) : beg;
+                ob[h] = beg;
+                S[h] = e - beg;
+                beg = e;
+                smax = max(smax, S[h]);
             }
-            key[s] = -1;
+            const int nvalid = min(NPT, nc - i);
+            if (small && smax <= 64) bwd_points<JT, CPD, 2, NPT>(gout, jm, phi, base, c0 + i, nvalid, ob, S, c, gcp, lane, vec);
+            else if (small && smax <= 96) bwd_points<JT, CPD, 3, NPT>(gout, jm, phi, base, c0 + i, nvalid, ob, S, c, gcp, lane, vec);
+            else if (small && smax <= 32 * kStrips) bwd_points<JT, CPD, kStrips, NPT>(gout, jm, phi, base, c0 + i, nvalid, ob, S, c, gcp, lane, vec);
+            else {  // very long lists: no aggregation, 64-bit positions
+                bwd_flush<JT, CPD>(c, gcp, vec);
+                for (int h = 0; h < nvalid; ++h) {
+                    const int64_t pb = (i + h) ? __shfl_sync(0xffffffffu, end64, (i + h - 1) & 31) : base;
+                    const int64_t pe = __shfl_sync(0xffffffffu, end64, (i + h) & 31);
+                    float g[CPD];
 #pragma unroll
-            for (int k = 0; k < CPD; ++k) acc[s][k] = 0.0f;
-        }
-        runS = -1;
-    };
-
-    for (int64_t i = p0; i < p1; ++i) {
-        const int64_t beg = i ? (int64_t)cumsum[i - 1] : 0;
-        const int64_t end = (int64_t)cumsum[i];
-        const int64_t S64 = end - beg;
-        float g[CPD];
+                    for (int k = 0; k < CPD; ++k) g[k] = __ldg(gout + (c0 + i + h) * CPD + k);
+                    for (int64_t j = pb + lane; j < pe; j += 32) {
+                        const float w = __ldg(phi + j);
+                        const int64_t r = (int64_t)__ldg(jm + j);
 #pragma unroll
-        for (int k = 0; k < CPD; ++k) g[k] = __ldg(gout + i * CPD + k);
-        if (S64 > 32 * kStrips) {  // very long list: no aggregation
-            flush();
-            for (int64_t j = beg + lane; j < end; j += 32) {
-                const float w = __ldg(phi + j);
-                const int64_t r = (int64_t)__ldg(jm + j);
-#pragma unroll
-                for (int k = 0; k < CPD; ++k) atomicAdd(gcp + r * CPD + k, w * g[k]);
+                        for (int k = 0; k < CPD; ++k) atomicAdd(gcp + r * CPD + k, w * g[k]);
+                    }
+                }
             }
-            continue;
         }
-        const int S = (int)S64;
-        long long myj[kStrips];
-        float myw[kStrips];
-        bool same = (S == runS);
-#pragma unroll
-        for (int s = 0; s < kStrips; ++s) {
-            const int o = s * 32 + lane;
-            const bool valid = o < S;
-            myj[s] = valid ? (long long)__ldg(jm + beg + o) : -1;
-            myw[s] = valid ? __ldg(phi + beg + o) : 0.0f;
-            same = same && (myj[s] == key[s]);
-        }
-        same = __all_sync(0xffffffffu, same);
-        if (!same) {
-            flush();
-#pragma unroll
-            for (int s = 0; s < kStrips; ++s) key[s] = myj[s];
-            runS = S;
-        }
-#pragma unroll
-        for (int s = 0; s < kStrips; ++s) {
-#pragma unroll
-            for (int k = 0; k < CPD; ++k) acc[s][k] = fmaf(myw[s], g[k], acc[s][k]);
-        }
+        base = last;
     }
-    flush();
+    bwd_flush<JT, CPD>(c, gcp, vec);
 }
 
 template <typename JT, typename CT>
@@ -212,9 +385,19 @@ int launch_bwd(const float* go, const void* jm, const float* phi, const void* cs
     if (ppw > 64) ppw = 64;
     const int64_t warps = (n + ppw - 1) / ppw;
     const int grid = (int)((warps + kWarpsPerCta - 1) / kWarpsPerCta);
+    // stride of the block permutation: about 0.618 of the block count, made coprime to it (1 = blocks in order: THB_BWD_PERM=0)
+    int64_t stride = 1;
+    {
+        const char* e = getenv("THB_BWD_PERM");
+        if (!(e && atoi(e) == 0) && warps > 8) {
+            stride = (int64_t)((double)warps * 0.6180339887) | 1;
+            auto gcd = [](int64_t a, int64_t b) { while (b) { const int64_t t = a % b; a = b; b = t; } return a; };
+            while (gcd(stride, warps) != 1) stride += 2;
+        }
+    }
 #define THB_BWD(C)                                                                                              \
     k_csr_backward<JT, CT, C><<<grid, kWarpsPerCta * 32, 0, st>>>(go, (const JT*)jm, phi, (const CT*)cs, gcp, n, \
-                                                                  (int)ppw)
+                                                                  (int)ppw, stride)
     switch (cpd) {
         case 1: THB_BWD(1); break;
         case 2: THB_BWD(2); break;

@@ -72,18 +72,30 @@ THB_DEV void fold2(f32x2 (*w2)[4], f32x2 (*wr2)[4], f32x2 x01, f32x2 x23, const 
 //     <tp(u), W> = sum_{m0,m1,m2} M[m0][m1][m2] s0^m0 s1^m1 s2^m2,   M = (C_0 x C_1 x C_2) W
 // so a point costs three subtractions and a nested Horner scheme (k_net_eval, MONO) instead of Cox-de Boor plus the
 // contraction with tp(u).  Three separable passes, one per dimension; every lane owns the entries t = lane (+ 32).
-template <int N0, int N1, int N2, int planes>
-THB_DEV void net_to_monomial(const thb_space_desc& sp, int lev, int c0, int c1, int c2, float* buf, int TS) {
+// cmat: the three 4 x 4 matrices C_k[m][r] of the cell, staged in shared memory by stage_span_polys (cp.async issued when
+// the cell is picked up, so their latency is hidden behind the fold of the supports).
+THB_DEV void stage_span_polys(const thb_space_desc& sp, int lev, int c0, int c1, int c2, float4 (*cmat)[4]) {
+    const int lane = threadIdx.x & 31;
+    if (lane < 12) {
+        const int dim = lane >> 2, m = lane & 3;
+        const int c = dim == 0 ? c0 : (dim == 1 ? c1 : c2);
+        if (dim < sp.ndim) cp_async16(&cmat[dim][m], sp.poly + (int64_t)(sp.poly_off[lev][dim] + c) * 20 + 4 * m);
+    }
+    cp_async_commit();
+}
+
+template <int N0, int N1, int N2, int CPD, bool REL>
+THB_DEV void net_to_monomial(const float4 (*cmat)[4], float* buf, int TS) {
+    constexpr int planes = REL ? 2 * CPD : CPD;   // plane index k -> buffer plane k (value) or 4 + k - CPD (relative)
+    auto plane_of = [](int k) { return k < CPD ? k : 4 + (k - CPD); };
     constexpr int T = N0 * N1 * N2;
     constexpr int NT = (T + 31) / 32;
     const int lane = threadIdx.x & 31;
-    const int cell[3] = {c0, c1, c2};
     constexpr int NN[3] = {N0, N1, N2};
     constexpr int STR[3] = {N1 * N2, N2, 1};
 #pragma unroll
     for (int dim = 2; dim >= 0; --dim) {
         if (NN[dim] == 1) continue;
-        const float* row = sp.poly + (int64_t)(sp.poly_off[lev][dim] + cell[dim]) * 20;
         float o[NT][planes];
 #pragma unroll
         for (int h = 0; h < NT; ++h) {
@@ -91,13 +103,13 @@ THB_DEV void net_to_monomial(const thb_space_desc& sp, int lev, int c0, int c1, 
             if (t < T) {
                 const int m = (t / STR[dim]) % NN[dim];
                 const int base = t - m * STR[dim];
-                const float4 cm = __ldg(reinterpret_cast<const float4*>(row) + m);   // C[m][0..3]
+                const float4 cm = cmat[dim][m];   // C[m][0..3]
                 const float cr[4] = {cm.x, cm.y, cm.z, cm.w};
 #pragma unroll
                 for (int k = 0; k < planes; ++k) {
                     float acc = 0.f;
 #pragma unroll
-                    for (int r = 0; r < NN[dim]; ++r) acc = fmaf(cr[r], buf[k * TS + base + r * STR[dim]], acc);
+                    for (int r = 0; r < NN[dim]; ++r) acc = fmaf(cr[r], buf[plane_of(k) * TS + base + r * STR[dim]], acc);
                     o[h][k] = acc;
                 }
             }
@@ -108,7 +120,7 @@ THB_DEV void net_to_monomial(const thb_space_desc& sp, int lev, int c0, int c1, 
             const int t = lane + 32 * h;
             if (t < T) {
 #pragma unroll
-                for (int k = 0; k < planes; ++k) buf[k * TS + t] = o[h][k];
+                for (int k = 0; k < planes; ++k) buf[plane_of(k) * TS + t] = o[h][k];
             }
         }
         __syncwarp();
@@ -124,6 +136,7 @@ __global__ void __launch_bounds__(32 * kNetWarps, (REL || CPD == 4) ? 6 : THB_NE
     __shared__ __align__(16) float4 s_sepv[kNetWarps][kNetChunk][3];
     __shared__ __align__(16) float4 s_cc[kNetWarps][kNetChunk];
     __shared__ __align__(16) float s_conv[kNetWarps][REL ? 8 : 4][TS];   // control net -> monomial form (na.mono)
+    __shared__ __align__(16) float4 s_cmat[kNetWarps][3][4];              // the cell's span polynomials C_k[m][r]
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     float4(*sepv)[3] = s_sepv[wid];
     float4* cc = s_cc[wid];
@@ -138,6 +151,7 @@ __global__ void __launch_bounds__(32 * kNetWarps, (REL || CPD == 4) ? 6 : THB_NE
         const int lev = a.x, soff = e.x, S = e.y, ndir = e.w;
         const int ntile = S - ndir;
         const int nsep = split ? f.y : 0;
+        if (na.mono) stage_span_polys(sp, lev, a.y, a.z, a.w, s_cmat[wid]);
         float ref[4] = {0.f, 0.f, 0.f, 0.f};
         if (REL && S > 0) {
             const float4 r = load_cp<CPD>(na.ctrl_pts, __ldg(sp.supp_jm + soff));
@@ -243,8 +257,9 @@ __global__ void __launch_bounds__(32 * kNetWarps, (REL || CPD == 4) ? 6 : THB_NE
                 }
             }
             if (na.mono) {
+                cp_async_wait<0>();
                 __syncwarp();
-                net_to_monomial<N0, N1, N2, (REL ? 8 : 4)>(sp, lev, a.y, a.z, a.w, dst, TS);
+                net_to_monomial<N0, N1, N2, CPD, REL>(s_cmat[wid], dst, TS);
                 const float4* b4 = reinterpret_cast<const float4*>(dst);
                 float4* d4 = reinterpret_cast<float4*>(gdst);
                 for (int i = lane; i < (REL ? 8 : 4) * TS / 4; i += 32) d4[i] = b4[i];
@@ -385,8 +400,9 @@ __global__ void __launch_bounds__(32 * kNetWarps, (REL || CPD == 4) ? 6 : THB_NE
                     }
                 }
             }
+            cp_async_wait<0>();
             __syncwarp();
-            net_to_monomial<N0, N1, N2, (REL ? 8 : 4)>(sp, lev, a.y, a.z, a.w, buf, TS);
+            net_to_monomial<N0, N1, N2, CPD, REL>(s_cmat[wid], buf, TS);
             const float4* b4 = reinterpret_cast<const float4*>(buf);
             float4* d4 = reinterpret_cast<float4*>(dst);
             for (int i = lane; i < (REL ? 8 : 4) * TS / 4; i += 32) d4[i] = b4[i];
@@ -415,7 +431,7 @@ struct NetSmem {
     float knots[2][3][8];            // local knots of the item's cell, per dimension
     float rk[3][8];                  // reciprocal knot differences of the current item
     float net[2][NPL][SH::TS];       // the item's local control net (planes 4..7: relative), double buffered
-    float4 prec[2][64];              // point records of a sub-batch: (u0, u1, u2, caller-order index as bits)
+    float4 prec[2][128];             // point records of a sub-batch (up to 4 per lane): (u0, u1, u2, caller-order index as bits)
 };
 
 template <class SH, bool DER, bool MONO>
@@ -706,8 +722,11 @@ THB_DEV void net_points(const Args& ar, const Item& it, int base, NetSmem<SH, DE
 // Persistent, warp-autonomous (one warp per CTA, no CTA barrier): work items from an atomic cursor; while item i is
 // computed the records of items i+1, i+2 are in flight, and the points of the next sub-batch plus the knots / net of
 // item i+1 stream into the other half of the shared-memory buffers (cp.async).
+#ifndef THB_NET_MINB_P4
+#define THB_NET_MINB_P4 16  // four points per lane still fit 128 registers (106 used)
+#endif
 template <int N0, int N1, int N2, int PPT, int CPD, bool DER, bool MONO>
-__global__ void __launch_bounds__(kThreads, DER ? THB_NET_MINB_DER : THB_NET_MINB) k_net_eval(const __grid_constant__ thb_space_desc sp, const __grid_constant__ Args ar,
+__global__ void __launch_bounds__(kThreads, PPT >= 4 ? THB_NET_MINB_P4 : (DER ? THB_NET_MINB_DER : THB_NET_MINB)) k_net_eval(const __grid_constant__ thb_space_desc sp, const __grid_constant__ Args ar,
                                                                     const float* __restrict__ nets) {
     using SH = Shp<N0, N1, N2>;
     constexpr int SB = 32 * PPT;
@@ -757,7 +776,10 @@ __global__ void __launch_bounds__(kThreads, DER ? THB_NET_MINB_DER : THB_NET_MIN
             }
             cp_async_commit();
             if constexpr (MONO) {
+                // four (or two) points per lane amortise the broadcast LDS.128 of the net: with two the shared-memory pipe
+                // (two wavefronts per broadcast LDS.128, one pipe per SM) is as busy as the FMA pipes
                 if (PPT >= 2 && it.count - base <= 32) net_points_mono<SH, 1, CPD, DER>(ar, it, base, sm, tb, pb);
+                else if (PPT >= 4 && it.count - base <= 64) net_points_mono<SH, 2, CPD, DER>(ar, it, base, sm, tb, pb);
                 else net_points_mono<SH, PPT, CPD, DER>(ar, it, base, sm, tb, pb);
             } else {
                 if (PPT == 2 && it.count - base <= 32) net_points<SH, 1, CPD, DER>(ar, it, base, sm, tb, pb);
@@ -1085,7 +1107,9 @@ int launch_net_eval(const thb_space_desc* sp, const Args* ar, const float* nets,
         THB_LAUNCHED();                                                                       \
         return THB_OK;                                                                        \
     } while (0)
-    if (mono) {   // monomial nets: two points per lane (one for tails)
+    if (mono) {   // monomial nets: four or two points per lane (fewer for tails)
+        if (cpd == 3 && !der && ppt == 4) THB_NET_EVAL(4, 3, false, true);
+        if (cpd == 4 && !der && ppt == 4) THB_NET_EVAL(4, 4, false, true);
         if (cpd == 3 && !der) THB_NET_EVAL(2, 3, false, true);
         if (cpd == 3 && der) THB_NET_EVAL(2, 3, true, true);
         if (cpd == 4 && !der) THB_NET_EVAL(2, 4, false, true);

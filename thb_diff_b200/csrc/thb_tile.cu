@@ -157,7 +157,7 @@ extern "C" int thb_eval_nets(const thb_space_desc* space, const thb_plan_desc* p
     ar.rows_sorted = plan->rows_in_plan_order ? 1 : 0;
     cudaStream_t st = (cudaStream_t)stream;
     THB_CUDA(cudaMemsetAsync(plan->counters + 1, 0, sizeof(int32_t), st));
-    return ops->net_eval(space, &ar, nets, env_int("THB_NET_PPT", 2), cp_dim, with_derivatives, mono, st);
+    return ops->net_eval(space, &ar, nets, env_int("THB_NET_PPT", mono ? 4 : 2), cp_dim, with_derivatives, mono, st);
 }
 
 static int fused_backward_impl(const thb_space_desc* space, const thb_plan_desc* plan, const float* params, const float* grad_out,

@@ -239,7 +239,8 @@ THB_DEV void prefetch_points(const Args& ar, int begin, int count, int base, flo
 #pragma unroll
     for (int q = 0; q < PPT; ++q) {
         const int li = base + q * 32 + lane;
-        cp_async16(prec + q * 32 + lane, src + begin + (li < count ? li : 0));
+        if (q == 0 || base + q * 32 < count)   // warp-uniform: blocks beyond the item are not fetched
+            cp_async16(prec + q * 32 + lane, src + begin + (li < count ? li : 0));
     }
 }
 
