@@ -66,6 +66,11 @@ struct FwdCache {
     int runS;
 };
 
+#ifndef THB_FWD_PF_DIST
+#define THB_FWD_PF_DIST 1   // groups of NPT points between the L2 prefetch and the loads (1: 2.40 ms, 2: 2.40, 3: 2.44, 4: 2.48, none: 2.50 -- config 3, int32)
+#endif
+THB_DEV void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // NPT points starting at entry offsets ob[h] (relative to base), lengths S[h] <= 32 * NS; a[h][k] = per-lane partial sums
 template <typename JT, int CPD, int NS, int NPT>
 THB_DEV void fwd_points(const float* __restrict__ cp, const JT* __restrict__ jm, const float* __restrict__ phi, int64_t base,
@@ -79,8 +84,8 @@ THB_DEV void fwd_points(const float* __restrict__ cp, const JT* __restrict__ jm,
 #pragma unroll
         for (int s = 0; s < NS; ++s) {
             const bool ok = s * 32 + lane < S[h];
-            cj[h][s] = ok ? __ldg(pj + s * 32) : (JT)-1;
-            cw[h][s] = ok ? __ldg(pw + s * 32) : 0.0f;
+            cj[h][s] = ok ? __ldcs(pj + s * 32) : (JT)-1;   // read once: streaming (evict-first) loads keep the control
+            cw[h][s] = ok ? __ldcs(pw + s * 32) : 0.0f;    // points / the gradient rows resident in L2
         }
     }
 #pragma unroll
@@ -146,6 +151,21 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_csr_forward(const float* 
 #pragma unroll
                 for (int k = 0; k < CPD; ++k) a[h][k] = 0.0f;
             if (i0 + j0 < np) {   // warp-uniform
+#ifndef THB_FWD_NO_PREFETCH
+                {   // the lines of the group two ahead -> L2 (one prefetch per lane and array): the loads of that group then
+                    // see L2 latency instead of HBM latency; bytes in flight per warp no longer limited by its registers
+                    const int gi = i0 + j0 + THB_FWD_PF_DIST * NPT;
+                    if (small && gi < np) {
+                        const int e0 = __shfl_sync(0xffffffffu, my_end, (gi - 1) & 31);
+                        const int e1 = __shfl_sync(0xffffffffu, my_end, (min(gi + NPT, np) - 1) & 31);
+                        const char* pa = reinterpret_cast<const char*>(phi + base + e0);
+                        const char* ja = reinterpret_cast<const char*>(jm + base + e0);
+                        const int nb_p = (e1 - e0) * 4, nb_j = (e1 - e0) * (int)sizeof(JT);
+                        if (lane * 128 < nb_p) prefetch_l2(pa + lane * 128);
+                        if (lane * 128 < nb_j) prefetch_l2(ja + lane * 128);
+                    }
+                }
+#endif
                 int ob[NPT], S[NPT], smax = 0;
 #pragma unroll
                 for (int h = 0; h < NPT; ++h) {
@@ -205,36 +225,18 @@ struct BwdCache {
     int runS;
 };
 
-// One row of the gradient: cp_dim reductions, issued as vector reductions (red.global.add.v2 / .v4.f32, sm_90+) where the
-// address allows -- rows of three floats start on an 8-byte boundary when the row index is even and 4 bytes after one when
-// it is odd, so a row is always one 8-byte pair plus one scalar: two L2 atomic operations instead of three (the backward is
-// bound by the L2 atomic units, not by HBM: 270 M row flushes on config 3).  vec: the buffer itself is 16-byte aligned.
-THB_DEV void red_v2(float* p, float a, float b) { asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory"); }
-THB_DEV void red_v4(float* p, float a, float b, float c, float d) {
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-template <int CPD>
-THB_DEV void red_row(float* __restrict__ gcp, int64_t row, const float (&v)[CPD], bool vec) {
-    float* p = gcp + row * CPD;
-    if (!vec || CPD == 1) {
-#pragma unroll
-        for (int k = 0; k < CPD; ++k) atomicAdd(p + k, v[k]);
-    } else if constexpr (CPD == 2) {
-        red_v2(p, v[0], v[1]);
-    } else if constexpr (CPD == 3) {
-        if (row & 1) { atomicAdd(p, v[0]); red_v2(p + 1, v[1], v[2]); }
-        else { red_v2(p, v[0], v[1]); atomicAdd(p + 2, v[2]); }
-    } else if constexpr (CPD == 4) {
-        red_v4(p, v[0], v[1], v[2], v[3]);
-    }
-}
-
+// (Vector reductions -- red.global.add.v2 / .v4.f32, a row of three floats as one 8-byte pair plus one scalar -- were
+// measured slower than three scalar reductions here, and the second code path made the kernel miss in the instruction
+// cache: 4.1 instead of 3.0 ms on config 3.  The kernel is kept small on purpose.)
 template <typename JT, int CPD>
-THB_DEV void bwd_flush(BwdCache<JT, CPD>& c, float* __restrict__ gcp, bool vec) {
+THB_DEV void bwd_flush(BwdCache<JT, CPD>& c, float* __restrict__ gcp) {
 #pragma unroll
     for (int s = 0; s < kStrips; ++s) {
         if (s * 32 < c.runS) {   // warp-uniform
-            if (c.key[s] >= 0) red_row<CPD>(gcp, (int64_t)c.key[s], c.acc[s], vec);
+            if (c.key[s] >= 0) {
+#pragma unroll
+                for (int k = 0; k < CPD; ++k) atomicAdd(gcp + (int64_t)c.key[s] * CPD + k, c.acc[s][k]);
+            }
 #pragma unroll
             for (int k = 0; k < CPD; ++k) c.acc[s][k] = 0.0f;
         }
@@ -243,10 +245,13 @@ THB_DEV void bwd_flush(BwdCache<JT, CPD>& c, float* __restrict__ gcp, bool vec) 
     c.runS = -1;
 }
 
+#ifndef THB_BWD_LD
+#define THB_BWD_LD __ldg   // (streaming __ldcs loads measured slower here: 4.1 vs 3.0 ms on config 3, int32)
+#endif
 template <typename JT, int CPD, int NS, int NPT>
 THB_DEV void bwd_points(const float* __restrict__ gout, const JT* __restrict__ jm, const float* __restrict__ phi, int64_t base,
                         int64_t row0, int nvalid, const int (&ob)[NPT], const int (&S)[NPT], BwdCache<JT, CPD>& c,
-                        float* __restrict__ gcp, int lane, bool vec) {
+                        float* __restrict__ gcp, int lane) {
     JT cj[NPT][NS];
     float cw[NPT][NS], g[NPT][CPD];
 #pragma unroll
@@ -259,8 +264,8 @@ THB_DEV void bwd_points(const float* __restrict__ gout, const JT* __restrict__ j
 #pragma unroll
         for (int s = 0; s < NS; ++s) {
             const bool ok = s * 32 + lane < S[h];
-            cj[h][s] = ok ? __ldg(pj + s * 32) : (JT)-1;
-            cw[h][s] = ok ? __ldg(pw + s * 32) : 0.0f;
+            cj[h][s] = ok ? THB_BWD_LD(pj + s * 32) : (JT)-1;
+            cw[h][s] = ok ? THB_BWD_LD(pw + s * 32) : 0.0f;
         }
     }
 #pragma unroll
@@ -270,7 +275,7 @@ THB_DEV void bwd_points(const float* __restrict__ gout, const JT* __restrict__ j
 #pragma unroll
         for (int s = 0; s < NS; ++s) same = same && (cj[h][s] == c.key[s]);
         if (!__all_sync(0xffffffffu, same)) {
-            bwd_flush<JT, CPD>(c, gcp, vec);
+            bwd_flush<JT, CPD>(c, gcp);
 #pragma unroll
             for (int s = 0; s < NS; ++s) c.key[s] = cj[h][s];
             c.runS = S[h];
@@ -288,7 +293,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_csr_backward(const float*
                                                                       const float* __restrict__ phi,
                                                                       const CT* __restrict__ cumsum, float* __restrict__ gcp,
                                                                       int64_t npoints, int pts_per_warp, int64_t perm_stride) {
-    constexpr int NPT = 4;
+    // points in flight per warp: four with 32-bit indices; two with 64-bit ones, whose bodies are twice as large -- the
+    // kernel is sensitive to its code size (instruction-cache misses): 5.2 vs 4.0 ms int64, 3.0 vs 3.7 ms int32 on config 3
+#ifdef THB_BWD_NPT
+    constexpr int NPT = THB_BWD_NPT;
+#else
+    constexpr int NPT = sizeof(JT) == 8 ? 2 : 4;
+#endif
     const int lane = threadIdx.x & 31;
     int64_t warp = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
     {   // Warps that run at the same time take point blocks far apart (block index times a stride coprime to the block
@@ -298,7 +309,6 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_csr_backward(const float*
         if (warp >= nw) return;
         warp = (warp * perm_stride) % nw;
     }
-    const bool vec = (reinterpret_cast<uintptr_t>(gcp) & 15) == 0;
     const int64_t p0 = warp * pts_per_warp;
     if (p0 >= npoints) return;
     const int64_t p1 = (p0 + pts_per_warp < npoints) ? p0 + pts_per_warp : npoints;
@@ -322,6 +332,21 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_csr_backward(const float*
         const int my_end = small ? (int)(end64 - base) : 0;
         int beg = 0;
         for (int i = 0; i < nc; i += NPT) {
+#ifndef THB_BWD_PREFETCH
+#define THB_BWD_PREFETCH 2   // as in the forward kernel (3.96 -> 3.75 ms int64, flat with int32 indices: that one waits on L2 atomics)
+#endif
+            {
+                const int gi = i + THB_BWD_PREFETCH * NPT;
+                if (small && gi < nc) {
+                    const int e0 = __shfl_sync(0xffffffffu, my_end, (gi - 1) & 31);
+                    const int e1 = __shfl_sync(0xffffffffu, my_end, (min(gi + NPT, nc) - 1) & 31);
+                    const char* pa = reinterpret_cast<const char*>(phi + base + e0);
+                    const char* ja = reinterpret_cast<const char*>(jm + base + e0);
+                    const int nb_p = (e1 - e0) * 4, nb_j = (e1 - e0) * (int)sizeof(JT);
+                    if (lane * 128 < nb_p) prefetch_l2(pa + lane * 128);
+                    if (lane * 128 < nb_j) prefetch_l2(ja + lane * 128);
+                }
+            }
             int ob[NPT], S[NPT], smax = 0;
 #pragma unroll
             for (int h = 0; h < NPT; ++h) {
@@ -332,11 +357,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_csr_backward(const float*
                 smax = max(smax, S[h]);
             }
             const int nvalid = min(NPT, nc - i);
-            if (small && smax <= 64) bwd_points<JT, CPD, 2, NPT>(gout, jm, phi, base, c0 + i, nvalid, ob, S, c, gcp, lane, vec);
-            else if (small && smax <= 96) bwd_points<JT, CPD, 3, NPT>(gout, jm, phi, base, c0 + i, nvalid, ob, S, c, gcp, lane, vec);
-            else if (small && smax <= 32 * kStrips) bwd_points<JT, CPD, kStrips, NPT>(gout, jm, phi, base, c0 + i, nvalid, ob, S, c, gcp, lane, vec);
+#ifndef THB_BWD_SPEC2
+            if (small && smax <= 64) bwd_points<JT, CPD, 2, NPT>(gout, jm, phi, base, c0 + i, nvalid, ob, S, c, gcp, lane);
+            else
+#endif
+            if (small && smax <= 96) bwd_points<JT, CPD, 3, NPT>(gout, jm, phi, base, c0 + i, nvalid, ob, S, c, gcp, lane);
+            else if (small && smax <= 32 * kStrips) bwd_points<JT, CPD, kStrips, NPT>(gout, jm, phi, base, c0 + i, nvalid, ob, S, c, gcp, lane);
             else {  // very long lists: no aggregation, 64-bit positions
-                bwd_flush<JT, CPD>(c, gcp, vec);
+                bwd_flush<JT, CPD>(c, gcp);
                 for (int h = 0; h < nvalid; ++h) {
                     const int64_t pb = (i + h) ? __shfl_sync(0xffffffffu, end64, (i + h - 1) & 31) : base;
                     const int64_t pe = __shfl_sync(0xffffffffu, end64, (i + h) & 31);
@@ -354,7 +382,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_csr_backward(const float*
         }
         base = last;
     }
-    bwd_flush<JT, CPD>(c, gcp, vec);
+    bwd_flush<JT, CPD>(c, gcp);
 }
 
 template <typename JT, typename CT>
@@ -385,14 +413,16 @@ int launch_bwd(const float* go, const void* jm, const float* phi, const void* cs
     if (ppw > 64) ppw = 64;
     const int64_t warps = (n + ppw - 1) / ppw;
     const int grid = (int)((warps + kWarpsPerCta - 1) / kWarpsPerCta);
-    // stride of the block permutation: about 0.618 of the block count, made coprime to it (1 = blocks in order: THB_BWD_PERM=0)
+    // stride of the block permutation: about 0.618 of the block count, made coprime to it (THB_BWD_PERM=0: blocks in
+    // order; any other value: that stride)
     int64_t stride = 1;
     {
         const char* e = getenv("THB_BWD_PERM");
-        if (!(e && atoi(e) == 0) && warps > 8) {
-            stride = (int64_t)((double)warps * 0.6180339887) | 1;
+        const long long want = e ? atoll(e) : -1;
+        if (want != 0 && warps > 8) {
+            stride = want > 0 ? (int64_t)want : ((int64_t)((double)warps * 0.6180339887) | 1);
             auto gcd = [](int64_t a, int64_t b) { while (b) { const int64_t t = a % b; a = b; b = t; } return a; };
-            while (gcd(stride, warps) != 1) stride += 2;
+            while (gcd(stride, warps) != 1) stride += 1;
         }
     }
 #define THB_BWD(C)                                                                                              \
