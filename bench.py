@@ -373,7 +373,7 @@ def fit_block(sp, P, rank, world, device, cell_cost, n_total=10_000_000):
     import torch.distributed as dist
 
     from thb_diff_b200 import configs, engine
-    from thb_diff_b200.distributed import FitEngine, partition_by_cell, shard_bounds
+    from thb_diff_b200.distributed import FitEngine, estimate_cell_cost, partition_by_cell, shard_bounds
 
     gen = torch.Generator(device=device).manual_seed(0)
     prm = torch.rand((n_total, 3), device=device, generator=gen)          # the same 10M points whatever the world size
@@ -381,12 +381,35 @@ def fit_block(sp, P, rank, world, device, cell_cost, n_total=10_000_000):
     prm = prm[lo:hi].contiguous()                                         # this rank's arbitrary share ...
     tgt = torch.stack([prm[:, 0], prm[:, 1], prm[:, 2] + 0.1 * torch.sin(6.2831853 * prm[:, 0]) * torch.sin(6.2831853 * prm[:, 1])
                        * torch.sin(6.2831853 * prm[:, 2])], dim=1)
+    payload = torch.cat([prm, tgt], dim=1)
     slot, _ = engine.active_span(P, prm, want_num_supp=False)
-    rows, bounds = partition_by_cell(slot, P.nslots, torch.cat([prm, tgt], dim=1), cell_cost=cell_cost)   # ... moved to the owner of its cell
-    prm, tgt = rows[:, :3].contiguous(), rows[:, 3:].contiguous()
-    del rows, slot
     x = torch.from_numpy(configs.greville_ctrl_pts(sp, bump=0.0)).to(device)
-    res = {}
+    balance = {"cell_cost_first": cell_cost}
+    for attempt in range(2):
+        rows, bounds = partition_by_cell(slot, P.nslots, payload, cell_cost=cell_cost)   # ... moved to the owner of its cell
+        prm, tgt = rows[:, :3].contiguous(), rows[:, 3:].contiguous()
+        if world == 1 or attempt == 1:
+            break
+        # measured re-balancing: a few steps with the guessed cell cost, per-rank compute time, least squares t = a points + b cells
+        eng = FitEngine(P, prm, tgt, n_total, lr=1e-2)
+        xx = x.clone()
+        for _ in range(3):
+            eng.step(xx)
+        t_c = eng.time_phases(xx, iters=10)[0]
+        ncell = int((eng.plan.cell_count[: P.nslots] > 0).sum())
+        mine = torch.tensor([float(prm.shape[0]), float(ncell), t_c], device=device)
+        allv = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allv, mine)
+        pts_r, cells_r, t_r = ([float(v[k]) for v in allv] for k in range(3))
+        est = estimate_cell_cost(pts_r, cells_r, t_r)
+        balance.update({"first_points": pts_r, "first_cells": cells_r, "first_compute_ms": t_r, "cell_cost_estimated": est})
+        del eng, xx
+        if est is None or max(t_r) <= 1.1 * (sum(t_r) / world):
+            break
+        cell_cost = est
+    balance["cell_cost_used"] = cell_cost
+    del rows, slot, payload
+    res = {"balance": balance}
     for name, use_graph in (("eager", False), ("graph", True)):
         xx = x.clone()
         eng = FitEngine(P, prm, tgt, n_total, lr=1e-2, use_graph=use_graph)

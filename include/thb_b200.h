@@ -239,6 +239,33 @@ THB_API int thb_eval_fused_backward_rows(const thb_space_desc* space, const thb_
                                  const float* grad_out, int cp_dim, const int32_t* row_map, float* grad_rows,
                                  int64_t nrows, float* workspace, void* stream);
 
+/* ORDERED (deterministic) form of the same gradient.  The reference's backward adds with one atomicAdd per (point,
+ * support) (THB/THB_extensions/compute_pts_cuda_kernels.cu:43): the result depends on the arrival order of the threads, and
+ * so does the default path above (atomics per work item and per cell).  Here every sum runs in a fixed order: per-item net
+ * gradients are stored, added per cell in item order, the per-(cell, support) contributions are stored and added per
+ * function in the order of a transposed support list.  Bit-identical results from run to run need, in addition, the points
+ * of every cell in a canonical order inside the plan (thb_diff_b200.engine.Plan.canonicalize sorts them by caller index).
+ * Buffers (device): item_ws [max_items][4][tile_stride] f32, item0 [nslots] i32, contrib [nsupp][cp_dim] f32 (nsupp = total
+ * length of the cells' support lists); tr_ptr [nrows + 1], tr_idx [nsupp] i32: for compact row r the slots of `contrib`
+ * that belong to its function, slot = supp_off(cell) + position with the cell's supports in the order own-level (window
+ * order) | rank-one tiled | full-tile (PackedHierarchy.ordered_scatter_tables); active_ids [nrows] i32 or NULL: NULL writes
+ * the compact rows grad[nrows, cp_dim], otherwise grad is the dense [nctrl, cp_dim] tensor (zeroed by the callee) and row
+ * active_ids[r] receives the sum.  workspace: thb_net_workspace_floats(space, 0) floats, required. */
+typedef struct thb_ordered_desc {
+    float* item_ws;
+    int32_t* item0;
+    float* contrib;
+    const int32_t* tr_ptr;
+    const int32_t* tr_idx;
+    const int32_t* active_ids;
+    int64_t nsupp;
+    int32_t nrows;
+    int32_t pad_;
+} thb_ordered_desc;
+THB_API int thb_eval_fused_backward_ordered(const thb_space_desc* space, const thb_plan_desc* plan, const float* params,
+                                    const float* grad_out, int cp_dim, const thb_ordered_desc* ordered, float* grad,
+                                    int64_t grad_rows, float* workspace, void* stream);
+
 /* ---- fit loop helpers (BASELINE config 4; the reference composes these from torch ops around THBEval,
  * THB/torch_funcs.py:8-47) ----------------------------------------------------------------------------------
  * thb_mse_grad: loss[0] = scale * sum_i (out[i] - target[i])^2 and grad_out[i] = 2 scale (out[i] - target[i]) over

@@ -177,3 +177,57 @@ def test_tensors_on_a_non_current_device():
     out = engine.eval_fused(P, plan, torch.from_numpy(cp).to("cuda:1"))[0]
     assert out.device.index == 1
     assert rel_err(out.cpu().numpy(), ref, scale=np.abs(ref).max()).max() <= TOL
+
+
+@pytest.mark.parametrize("cp_dim", [3, 4])
+@pytest.mark.parametrize("name", ["block3d", "readme3d", "graded2d"])
+def test_ordered_backward_matches_the_oracle_and_is_bit_reproducible(name, cp_dim):
+    """deterministic=True: no atomics, every sum in a fixed order.  Two plans built independently (their scatter order
+    differs from run to run) and made canonical give BIT-IDENTICAL gradients; the values match the oracle."""
+    from thb_diff_b200 import engine
+    from thb_diff_b200.packed import PackedHierarchy
+
+    g = load_golden(name)
+    h = product_space_from_golden(g)
+    P = PackedHierarchy.from_space(h, device="cuda")
+    d = h.ndim
+    rng = np.random.default_rng(9)
+    prm = np.concatenate([g["params"], rng.random((150_000, d)).astype(np.float32)])   # cells with several work items
+    go = torch.from_numpy(rng.standard_normal((len(prm), cp_dim)).astype(np.float32)).cuda()
+    grads, rows = [], []
+    for _ in range(3):
+        plan = engine.Plan(P, prm).canonicalize()
+        grads.append(engine.eval_fused_backward(P, plan, go, deterministic=True))
+        rows.append(engine.eval_fused_backward_rows(P, plan, go, deterministic=True))
+    assert torch.equal(grads[0], grads[1]) and torch.equal(grads[0], grads[2])
+    assert torch.equal(rows[0], rows[1])
+    ids = P.active_rows()[0].long()
+    assert torch.equal(grads[0][ids], rows[0])
+    fast = engine.eval_fused_backward(P, engine.Plan(P, prm), go, deterministic=False)
+    scale = float(fast.abs().max())
+    assert float((fast - grads[0]).abs().max()) <= 1e-5 * scale
+    # against the oracle on the golden points alone
+    cs = np.cumsum(g["num_supp"])
+    cp_shape = (P.nCP, cp_dim)
+    go_s = go[: len(cs)].cpu().numpy()
+    ref = O.eval_backward(go_s, cp_shape, g["Jm"], g["PHI"], cs)
+    got = engine.eval_fused_backward(P, engine.Plan(P, g["params"]).canonicalize(), torch.from_numpy(go_s).cuda(), deterministic=True).cpu().numpy()
+    assert rel_err(got, ref, scale=np.abs(ref).max()).max() <= TOL
+
+
+def test_deterministic_fit_is_bit_reproducible():
+    from thb_diff_b200 import configs
+    from thb_diff_b200.distributed import FitEngine
+
+    g, h, P, plan, _ = _setup("block3d")
+    prm = torch.rand((100_003, 3), device="cuda", generator=torch.Generator(device="cuda").manual_seed(3))
+    tgt = torch.stack([prm[:, 0], prm[:, 1], prm[:, 2] + 0.05 * torch.sin(9.0 * prm[:, 0])], 1).contiguous()
+    x0 = torch.from_numpy(configs.greville_ctrl_pts(h, bump=0.0)).cuda()
+    runs = []
+    for _ in range(2):
+        x = x0.clone()
+        eng = FitEngine(P, prm, tgt, prm.shape[0], lr=1e-2, deterministic=True)
+        losses = [float(eng.step(x)) for _ in range(5)]
+        runs.append((x.clone(), losses))
+    assert runs[0][1] == runs[1][1] and torch.equal(runs[0][0], runs[1][0])
+    assert runs[0][1][-1] < runs[0][1][0]

@@ -86,7 +86,7 @@ def test_two_rank_fit_and_sharded_evaluation_over_nccl():
     x0 = x.clone()
     eng = FitEngine(P, prm, tgt, n_total, lr=1e-2)
     ref_losses = [float(eng.step(x)) for _ in range(6)]
-    assert ret[0]["n_mine"] + ret[1]["n_mine"] == n_total and min(ret[0]["n_mine"], ret[1]["n_mine"]) > 0.3 * n_total
+    assert ret[0]["n_mine"] + ret[1]["n_mine"] == n_total and min(ret[0]["n_mine"], ret[1]["n_mine"]) > 0   # balanced by points + cells, not by points
     for r in range(world):
         for use_graph in (False, True):
             xr, losses = ret[r]["fit"][use_graph]

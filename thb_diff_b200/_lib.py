@@ -37,6 +37,13 @@ class PlanDesc(C.Structure):
     ]
 
 
+class OrderedDesc(C.Structure):
+    _fields_ = [
+        ("item_ws", C.c_void_p), ("item0", C.c_void_p), ("contrib", C.c_void_p), ("tr_ptr", C.c_void_p), ("tr_idx", C.c_void_p),
+        ("active_ids", C.c_void_p), ("nsupp", C.c_int64), ("nrows", C.c_int32), ("pad_", C.c_int32),
+    ]
+
+
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
@@ -65,6 +72,7 @@ def _load():
         "thb_eval_nets": (i32, [C.POINTER(SpaceDesc), C.POINTER(PlanDesc), vp, i32, i32, C.POINTER(C.c_int32), i32, C.POINTER(vp), vp]),
         "thb_eval_fused_backward": (i32, [C.POINTER(SpaceDesc), C.POINTER(PlanDesc), vp, vp, i32, vp, i64, vp, vp]),
         "thb_eval_fused_backward_rows": (i32, [C.POINTER(SpaceDesc), C.POINTER(PlanDesc), vp, vp, i32, vp, vp, i64, vp, vp]),
+        "thb_eval_fused_backward_ordered": (i32, [C.POINTER(SpaceDesc), C.POINTER(PlanDesc), vp, vp, i32, C.POINTER(OrderedDesc), vp, i64, vp, vp]),
         "thb_mse_workspace_bytes": (i64, []),
         "thb_mse_grad": (i32, [vp, vp, i64, C.c_float, vp, vp, vp, vp]),
         "thb_adam_rows": (i32, [vp, vp, vp, vp, vp, i64, i32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, i32, vp, vp]),

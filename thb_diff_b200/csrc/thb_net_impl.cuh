@@ -38,6 +38,7 @@ struct NetArgs {
     int32_t planes;             // 4, or 8 with the relative planes
     const int32_t* row_map;     // k_cell_unfold: flat function id -> row of the (compact) gradient buffer; nullptr = identity
     int32_t mono;               // k_cell_nets: 1 = store the nets in MONOMIAL form (see net_to_monomial), 0 = control points
+    float* contrib;             // k_cell_unfold, ordered mode: [nsupp][cp_dim] one slot per (cell, support), plain stores
 };
 
 template <int CPD>
@@ -839,7 +840,7 @@ __global__ void __launch_bounds__(kThreads, 16) k_net_backward(const __grid_cons
     if (lane == 0) c3 = atomicAdd(cursor, 3);
     const int id0 = __shfl_sync(0xffffffffu, c3, 0);
     if (id0 >= nitems) return;
-    int id1 = id0 + 1, id2 = id0 + 2;
+    int id1 = id0 + 1, id2 = id0 + 2, cur_id = id0;
     Item it = load_item(sp, ar.items, id0);
     if (lane < 4 && id1 < nitems) cp_async16(&sm.rec[1][lane], ar.items + (int64_t)id1 * 4 + lane);
     if (lane < 4 && id2 < nitems) cp_async16(&sm.rec[2][lane], ar.items + (int64_t)id2 * 4 + lane);
@@ -937,7 +938,8 @@ __global__ void __launch_bounds__(kThreads, 16) k_net_backward(const __grid_cons
         }
         // the item's contribution to its cell's net gradient: halves summed, half h adds the entries a = 2h, 2h+1
         {
-            float* dst = gnets + (int64_t)it.slot * 4 * TS;
+            // ordered mode: the item's own slot of item_ws (plain stores; k_sum_items adds the items of a cell in order)
+            float* dst = ar.item_ws ? ar.item_ws + (int64_t)cur_id * 4 * TS : gnets + (int64_t)it.slot * 4 * TS;
 #pragma unroll
             for (int k = 0; k < CPD; ++k) {
                 float o[2][2];
@@ -951,7 +953,10 @@ __global__ void __launch_bounds__(kThreads, 16) k_net_backward(const __grid_cons
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
                         const int a = 2 * half + q;
-                        if (a < N0) atomicAdd(dst + k * TS + a * BC + l16, half ? o[1][q] : o[0][q]);
+                        if (a < N0) {
+                            if (ar.item_ws) dst[k * TS + a * BC + l16] = half ? o[1][q] : o[0][q];
+                            else atomicAdd(dst + k * TS + a * BC + l16, half ? o[1][q] : o[0][q]);
+                        }
                     }
                 }
             }
@@ -964,11 +969,78 @@ __global__ void __launch_bounds__(kThreads, 16) k_net_backward(const __grid_cons
         }
         tb ^= 1;
         const int id3 = __shfl_sync(0xffffffffu, nn_id, 0);
+        cur_id = id1;
         id1 = id2;
         id2 = id3;
         if (lane < 4 && id3 < nitems) cp_async16(&sm.rec[(ring + 2) % 3][lane], ar.items + (int64_t)id3 * 4 + lane);
         cp_async_commit();
         if (lane == 0) nn_id = atomicAdd(cursor, 1);
+    }
+}
+
+// ---- ordered (deterministic) variant of the two reductions that use atomics above -----------------------------------
+// The reference's backward is an atomicAdd per (point, support) (compute_pts_cuda_kernels.cu:43): its result depends on the
+// order in which threads arrive.  Ordered mode makes every sum of the fused backward run in a fixed order:
+//   k_net_backward  stores each item's net gradient in its own slot (Args::item_ws)            -- no atomics
+//   k_item_first    first item id of every cell (the items of a cell are consecutive)
+//   k_sum_items     per cell: the items' net gradients added in item order                     -> the per-cell workspace
+//   k_cell_unfold   writes <tile_s, gW> of every (cell, support) to its own slot (NetArgs::contrib) -- no atomics
+//   k_fn_gather     per active function: its slots added in a fixed order (transposed support lists built by the host,
+//                   PackedHierarchy.ordered_scatter_tables) -> the gradient row
+// With the points of every cell in a canonical order (engine.Plan.canonicalize) two runs give bit-identical gradients.
+static __global__ void __launch_bounds__(256) k_item_first(const int4* __restrict__ items, const int32_t* __restrict__ counters,
+                                                    int32_t* __restrict__ item0) {
+    const int n = counters[0];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int slot = __ldg(&items[(int64_t)i * 4].x);
+        if (i == 0 || __ldg(&items[(int64_t)(i - 1) * 4].x) != slot) item0[slot] = i;
+    }
+}
+
+static __global__ void __launch_bounds__(256) k_sum_items(const float* __restrict__ item_ws, const int32_t* __restrict__ item0,
+                                                   const int32_t* __restrict__ cell_count, int nslots, int ppi, int TS, int T, int cpd,
+                                                   float* __restrict__ gnets) {
+    const int row = 4 * TS;
+    // one thread per (cell, entry): the items of the cell in increasing item id
+    const int64_t tot = (int64_t)nslots * row;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (int64_t)gridDim.x * blockDim.x) {
+        const int slot = (int)(e / row), j = (int)(e - (int64_t)slot * row);
+        const int c = __ldg(cell_count + slot);
+        if (c == 0) continue;
+        const int m = (c + ppi - 1) / ppi, i0 = __ldg(item0 + slot);
+        float acc = 0.0f;
+        if (j / TS < cpd && j % TS < T)   // the other entries of an item's slot are never written
+            for (int i = 0; i < m; ++i) acc += item_ws[(int64_t)(i0 + i) * row + j];
+        gnets[e] = acc;
+    }
+}
+
+// one warp per active function (compact row r): contributions tr_idx[tr_ptr[r] .. tr_ptr[r+1]) in order -- lane l takes the
+// entries l, l + 32, ... and the 32 partial sums are combined by a fixed butterfly
+template <int CPD>
+__global__ void __launch_bounds__(256) k_fn_gather(const float* __restrict__ contrib, const int32_t* __restrict__ tr_ptr,
+                                                   const int32_t* __restrict__ tr_idx, const int32_t* __restrict__ active_ids,
+                                                   int nrows, float* __restrict__ grad) {
+    const int lane = threadIdx.x & 31;
+    for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < nrows; r += (gridDim.x * blockDim.x) >> 5) {
+        const int b = __ldg(tr_ptr + r), e = __ldg(tr_ptr + r + 1);
+        float acc[CPD];
+#pragma unroll
+        for (int k = 0; k < CPD; ++k) acc[k] = 0.0f;
+        for (int j = b + lane; j < e; j += 32) {
+            const int64_t s = __ldg(tr_idx + j);
+#pragma unroll
+            for (int k = 0; k < CPD; ++k) acc[k] += contrib[s * CPD + k];
+        }
+#pragma unroll
+        for (int k = 0; k < CPD; ++k)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+        if (lane == 0) {
+            const int64_t row = active_ids ? (int64_t)__ldg(active_ids + r) : (int64_t)r;
+#pragma unroll
+            for (int k = 0; k < CPD; ++k) grad[row * CPD + k] = acc[k];
+        }
     }
 }
 
@@ -1000,9 +1072,17 @@ __global__ void __launch_bounds__(32 * kNetWarps) k_cell_unfold(const __grid_con
             for (int t = lane; t < T; t += 32) {
                 if ((dm >> t) & 1ull) {
                     const int t2 = t % N2, t1 = (t / N2) % N1, t0 = t / (N2 * N1);
+                    const float4 v = gw[t];
+                    if (na.contrib) {   // ordered mode: slot (cell, rank of t among the cell's own-level supports)
+                        float* o = na.contrib + (int64_t)(soff + __popcll(dm & ((1ull << t) - 1ull))) * CPD;
+                        o[0] = v.x;
+                        if (CPD > 1) o[1] = v.y;
+                        if (CPD > 2) o[2] = v.z;
+                        if (CPD > 3) o[3] = v.w;
+                        continue;
+                    }
                     int64_t r = f0 + ((int64_t)(a.y + t0) * n1 + (a.z + t1)) * n2 + (a.w + t2);
                     if (na.row_map) r = __ldg(na.row_map + r);   // compact rows: active functions only
-                    const float4 v = gw[t];
                     atomicAdd(grad_cp + r * CPD, v.x);
                     if (CPD > 1) atomicAdd(grad_cp + r * CPD + 1, v.y);
                     if (CPD > 2) atomicAdd(grad_cp + r * CPD + 2, v.z);
@@ -1049,6 +1129,12 @@ __global__ void __launch_bounds__(32 * kNetWarps) k_cell_unfold(const __grid_con
                     }
                 }
             }
+            if (na.contrib) {   // ordered mode: slot (cell, n_direct + position among the tiled supports: rank-one ones first)
+                float* o = na.contrib + (int64_t)(soff + ndir + sidx) * CPD;
+#pragma unroll
+                for (int k = 0; k < CPD; ++k) o[k] = acc[k];
+                continue;
+            }
             if (na.row_map) r = __ldg(na.row_map + r);
 #pragma unroll
             for (int k = 0; k < CPD; ++k) atomicAdd(grad_cp + r * CPD + k, acc[k]);
@@ -1074,6 +1160,36 @@ int launch_net_backward(const thb_space_desc* sp, const Args* ar, const NetArgs*
     if (cpd == 4) THB_NET_BWD(4);
 #undef THB_NET_BWD
     return thb_set_error(THB_E_UNSUPPORTED, "net backward: unsupported cp_dim");
+}
+
+// ordered backward: see the comment above k_item_first.  od: the buffers of thb_ordered_desc (thb_b200.h)
+template <int N0, int N1, int N2>
+int launch_net_backward_ordered(const thb_space_desc* sp, const Args* ar, const NetArgs* na, const thb_ordered_desc* od,
+                                const int32_t* cell_count, int ppi, int max_items, float* grad, int cpd, cudaStream_t st) {
+    using SH = Shp<N0, N1, N2>;
+#define THB_NET_BWD_ORD(CPD_)                                                                          \
+    do {                                                                                               \
+        static int g1_[THB_MAX_DEVICES] = {}, g2_[THB_MAX_DEVICES] = {};                               \
+        int &g1 = g1_[thb_device()], &g2 = g2_[thb_device()];                                          \
+        if (g1 == 0) g1 = persistent_grid(k_net_backward<N0, N1, N2, CPD_>, kThreads);                  \
+        if (g2 == 0) g2 = persistent_grid(k_cell_unfold<N0, N1, N2, CPD_>, 32 * kNetWarps);             \
+        k_net_backward<N0, N1, N2, CPD_><<<g1, kThreads, 0, st>>>(*sp, *ar, na->nets);                  \
+        THB_LAUNCHED();                                                                                \
+        k_item_first<<<min((max_items + 255) / 256, thb_num_sms() * 8), 256, 0, st>>>(ar->items, ar->counters, od->item0); \
+        THB_LAUNCHED();                                                                                \
+        k_sum_items<<<thb_num_sms() * 8, 256, 0, st>>>(od->item_ws, od->item0, cell_count, sp->nslots, ppi, SH::TS, SH::T, CPD_, na->nets); \
+        THB_LAUNCHED();                                                                                \
+        k_cell_unfold<N0, N1, N2, CPD_><<<min((sp->nslots + kNetWarps - 1) / kNetWarps, g2), 32 * kNetWarps, 0, st>>>(*sp, *na, grad); \
+        THB_LAUNCHED();                                                                                \
+        k_fn_gather<CPD_><<<min((od->nrows * 32 + 255) / 256, thb_num_sms() * 8), 256, 0, st>>>(od->contrib, od->tr_ptr, od->tr_idx, \
+                                                                                              od->active_ids, od->nrows, grad);  \
+        THB_LAUNCHED();                                                                                \
+        return THB_OK;                                                                                 \
+    } while (0)
+    if (cpd == 3) THB_NET_BWD_ORD(3);
+    if (cpd == 4) THB_NET_BWD_ORD(4);
+#undef THB_NET_BWD_ORD
+    return thb_set_error(THB_E_UNSUPPORTED, "ordered net backward: unsupported cp_dim");
 }
 
 template <int N0, int N1, int N2>
@@ -1166,7 +1282,7 @@ __global__ void __launch_bounds__(kThreads, 16) k_basis_rows(const __grid_consta
     if (lane == 0) c3 = atomicAdd(cursor, 3);
     const int id0 = __shfl_sync(0xffffffffu, c3, 0);
     if (id0 >= nitems) return;
-    int id1 = id0 + 1, id2 = id0 + 2;
+    int id1 = id0 + 1, id2 = id0 + 2, cur_id = id0;
     Item it = load_item(sp, ar.items, id0);
     if (lane < 4 && id1 < nitems) cp_async16(&sm.rec[1][lane], ar.items + (int64_t)id1 * 4 + lane);
     if (lane < 4 && id2 < nitems) cp_async16(&sm.rec[2][lane], ar.items + (int64_t)id2 * 4 + lane);
@@ -1370,6 +1486,8 @@ struct ShapeOps {
     int (*nets)(const thb_space_desc*, const NetArgs*, int cpd, cudaStream_t);
     int (*net_eval)(const thb_space_desc*, const Args*, const float* nets, int ppt, int cpd, int der, int mono, cudaStream_t);
     int (*net_backward)(const thb_space_desc*, const Args*, const NetArgs*, float* grad_cp, int cpd, cudaStream_t);
+    int (*net_backward_ordered)(const thb_space_desc*, const Args*, const NetArgs*, const thb_ordered_desc*, const int32_t* cell_count,
+                                int ppi, int max_items, float* grad, int cpd, cudaStream_t);
     int (*basis)(const thb_space_desc*, const Args*, int ppt, int der, cudaStream_t);
     int (*basis_rows)(const thb_space_desc*, const Args*, int der, cudaStream_t);
     int (*backward)(const thb_space_desc*, const Args*, int cpd, cudaStream_t);
@@ -1378,7 +1496,8 @@ struct ShapeOps {
 #define THB_DEFINE_SHAPE(A, B, C)                                                                                    \
     namespace thb_tile {                                                                                             \
     extern const ShapeOps shape_ops_##A##B##C = {A, B, C, &launch_fused<A, B, C>, &launch_nets<A, B, C>,              \
-                                                 &launch_net_eval<A, B, C>, &launch_net_backward<A, B, C>, &launch_basis<A, B, C>, \
+                                                 &launch_net_eval<A, B, C>, &launch_net_backward<A, B, C>,               \
+                                                 &launch_net_backward_ordered<A, B, C>, &launch_basis<A, B, C>,          \
                                                  &launch_basis_rows<A, B, C>,                                          \
                                                  &launch_backward<A, B, C>};                                         \
     }

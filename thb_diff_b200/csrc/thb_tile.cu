@@ -205,3 +205,33 @@ extern "C" int thb_eval_fused_backward_rows(const thb_space_desc* space, const t
     return fused_backward_impl(space, plan, params, grad_out, cp_dim, row_map, grad_rows, nrows, workspace, stream,
                                "thb_eval_fused_backward_rows");
 }
+
+extern "C" int thb_eval_fused_backward_ordered(const thb_space_desc* space, const thb_plan_desc* plan, const float* params,
+                                               const float* grad_out, int cp_dim, const thb_ordered_desc* od, float* grad,
+                                               int64_t grad_rows, float* workspace, void* stream) {
+    const char* who = "thb_eval_fused_backward_ordered";
+    int rc = thb_check_space(space, who);
+    if (rc) return rc;
+    if ((rc = check_plan(plan, who))) return rc;
+    THB_REQUIRE(cp_dim == 3 || cp_dim == 4, "%s: cp_dim must be 3 or 4", who);
+    THB_REQUIRE(od && od->item_ws && od->item0 && od->contrib && od->tr_ptr && od->tr_idx && od->nrows > 0 && od->nsupp > 0, "%s: incomplete ordered descriptor", who);
+    THB_REQUIRE(grad && grad_rows >= (od->active_ids ? 1 : od->nrows), "%s: gradient buffer too small", who);
+    THB_REQUIRE(workspace && plan->cell_count, "%s: needs the net-gradient workspace and a plan with cell_count", who);
+    cudaStream_t st = (cudaStream_t)stream;
+    THB_CUDA(cudaMemsetAsync(grad, 0, sizeof(float) * grad_rows * cp_dim, st));
+    if (plan->npoints == 0) return THB_OK;
+    THB_REQUIRE(params && grad_out, "%s: null pointer", who);
+    const ShapeOps* ops = find_shape(space);
+    if (!ops) return thb_set_error(THB_E_UNSUPPORTED, "%s: no kernel for degrees (%d,%d,%d)", who, space->degree[0], space->degree[1], space->degree[2]);
+    Args ar = {};
+    ar.items = (const int4*)plan->items; ar.counters = plan->counters;
+    ar.params = params; ar.sorted = plan->sorted_params; ar.grad_out = grad_out; ar.grad_cp = grad;
+    ar.rows_sorted = plan->rows_in_plan_order ? 1 : 0;
+    ar.item_ws = od->item_ws;
+    THB_CUDA(cudaMemsetAsync(plan->counters + 1, 0, sizeof(int32_t), st));
+    THB_CUDA(cudaMemsetAsync(workspace, 0, sizeof(float) * (size_t)thb_net_workspace_floats(space, 0), st));
+    THB_CUDA(cudaMemsetAsync(od->contrib, 0, sizeof(float) * (size_t)od->nsupp * cp_dim, st));   // cells without points contribute zero
+    NetArgs na = {};
+    na.cell_count = plan->cell_count; na.nets = workspace; na.planes = 4; na.contrib = od->contrib;
+    return ops->net_backward_ordered(space, &ar, &na, od, plan->cell_count, plan->points_per_item, plan->max_items, grad, cp_dim, st);
+}

@@ -50,6 +50,7 @@ struct Args {
     // backward
     const float* grad_out;
     float* grad_cp;
+    float* item_ws;          // ordered (deterministic) backward: per-ITEM net gradients [nitems][4][TS], plain stores
 };
 
 template <int N0_, int N1_, int N2_>

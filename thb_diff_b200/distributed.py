@@ -109,6 +109,23 @@ def grid_slab_bounds(P, axes, world, cell_cost=100.0, axis=0):
     return balanced_bounds(plane, world)
 
 
+def estimate_cell_cost(points, cells, times):
+    """Cost of a cell in point-equivalents from measured per-rank step times: least squares of t_r = a * points_r + b * cells_r
+    over the ranks, returns b / a (None when the fit is degenerate).  points / cells / times: sequences, one entry per rank.
+    A fit measures its first steps with a guessed cost, calls this and re-partitions once (cells of a finer level cost more
+    than the guess, coarse cells with thousands of points less)."""
+    import numpy as np
+
+    A = np.stack([np.asarray(points, dtype=np.float64), np.asarray(cells, dtype=np.float64)], axis=1)
+    t = np.asarray(times, dtype=np.float64)
+    if len(t) < 2 or np.linalg.matrix_rank(A) < 2:
+        return None
+    (a, b), *_ = np.linalg.lstsq(A, t, rcond=None)
+    if not (a > 0 and b > 0):
+        return None
+    return float(b / a)
+
+
 def partition_by_cell(slot, nslots, payload, group=None, cell_cost=100.0):
     """Moves every point to the rank that owns its active cell.
 
@@ -200,10 +217,12 @@ class FitEngine:
     Adam never moves a row whose gradient has always been zero, so updating the active rows only is the dense
     torch.optim.Adam step (tests compare the two).  `loss` is this rank's share of the global mean squared error
     (device tensor, no synchronisation); sum it over ranks for the global value.
-    use_graph: the whole step, all-reduce included, is captured into one CUDA graph after the first eager step."""
+    use_graph: the whole step, all-reduce included, is captured into one CUDA graph after the first eager step.
+    deterministic (default: THB_DETERMINISTIC): canonical point order inside the plan and the ordered backward -- the loss
+    (thb_mse_grad is ordered already) and the control points are then bit-identical from run to run on one rank."""
 
     def __init__(self, packed, params, targets, n_total, lr=1e-2, betas=(0.9, 0.999), eps=1e-8, group=None, use_graph=False,
-                 comm_stream=False):
+                 deterministic=None):
         from . import engine
 
         self.E, self.P, self.group = engine, packed, group
@@ -211,6 +230,9 @@ class FitEngine:
         n_in = int(self.plan.counters[2])
         if n_in != self.plan.n:
             raise RuntimeError("FitEngine needs every point inside the domain")
+        self.deterministic = engine.deterministic_default() if deterministic is None else bool(deterministic)
+        if self.deterministic:
+            self.plan.canonicalize()   # the points of every cell in caller order: sums over them no longer depend on the run
         perm = self.plan.caller_index()
         self.plan.set_rows_in_plan_order(True)
         dev = packed.device
@@ -240,7 +262,7 @@ class FitEngine:
         nets = E.cell_nets(P, x, plan=self.plan)
         E.eval_nets(P, self.plan, nets, self.cpd, out=[self.out], with_derivatives=False)
         E.mse_grad(self.out, self.targets, 1.0 / (self.n_total * self.cpd), self.gout, self.loss, self.mse_ws)
-        E.eval_fused_backward_rows(P, self.plan, self.gout, out=self.grad)
+        E.eval_fused_backward_rows(P, self.plan, self.gout, out=self.grad, deterministic=self.deterministic)
         if t:
             t[1].record()
         allreduce_grad_(self.grad, self.group)

@@ -6,7 +6,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import PlanDesc, check, lib, ptr, require_cuda, stream_ptr
+from ._lib import OrderedDesc, PlanDesc, check, lib, ptr, require_cuda, stream_ptr
 
 import os as _os
 
@@ -95,6 +95,22 @@ class Plan:
         """int64 [n_inside]: caller-order index of the point in row j of the plan order (synchronises once)."""
         n_in = int(self.counters[2])
         return self.sorted_params[:n_in, 3].contiguous().view(torch.int32).long()
+
+    def canonicalize(self):
+        """Puts the points of every cell in a CANONICAL order (increasing caller index).  thb_plan_build places the points
+        of a cell in the order its scatter atomics happen to arrive, which differs from run to run; sums over the points
+        of a work item (the fused backward) inherit that order.  After this call two plans of the same batch are
+        bit-identical, and with the ordered backward (deterministic=True) so are the gradients.  One device sort of the
+        batch (torch.sort, stable radix sort); call it once for a fit, whose plan is built once."""
+        n_in = int(self.counters[2])
+        if n_in == 0:
+            return self
+        rec = self.sorted_params[:n_in]
+        idx = rec[:, 3].contiguous().view(torch.int32).long()
+        key = (self.slot[: self.n].long()[idx] << 32) | idx          # records are already grouped by cell: the cell order is kept
+        order = torch.argsort(key, stable=True)
+        self.sorted_params[:n_in] = rec[order]
+        return self
 
     def refresh(self):
         """Work items embed per-cell table offsets: rebuild if the hierarchy's tables changed since build()."""
@@ -287,9 +303,11 @@ def eval_fused(P, plan, ctrl_pts, channels=(CH_VALUE,), cellnet=True, out=None, 
     return out
 
 
-def eval_fused_backward(P, plan, grad_out, cp_dim=None, formulation="local_net"):
+def eval_fused_backward(P, plan, grad_out, cp_dim=None, formulation="local_net", deterministic=None):
     """grad_ctrl_pts = A^T grad_out for the plan's points.  "local_net" (default): per-item reduction into per-cell net
-    gradients + one transposed fold per cell; "per_point": the per-item tile kernel."""
+    gradients + one transposed fold per cell; "per_point": the per-item tile kernel.  deterministic=True (default from
+    THB_DETERMINISTIC): the ordered form of "local_net" -- no atomics, every sum in a fixed order; with a canonical plan
+    (Plan.canonicalize) the result is bit-identical from run to run."""
     require_cuda(grad_out, "grad_out", torch.float32)
     cpd = grad_out.shape[1]
     if cpd not in (3, 4):
@@ -298,11 +316,46 @@ def eval_fused_backward(P, plan, grad_out, cp_dim=None, formulation="local_net")
         raise RuntimeError("the hierarchy has no coefficient tiles yet (PackedHierarchy.attach_tiles / from_space)")
     plan.refresh()
     _check_rows([grad_out], plan, cpd, "grad_out")
+    if deterministic is None:
+        deterministic = deterministic_default()
+    if deterministic:
+        if formulation != "local_net":
+            raise RuntimeError("the ordered (deterministic) backward exists for the local-net formulation only")
+        return _ordered_backward(P, plan, grad_out, cpd, dense=True)
     g = torch.empty((P.nCP, cpd), dtype=torch.float32, device=P.device)
     ws = _gnet_workspace(P) if formulation == "local_net" else None
     with _on(P.device):
         check(lib.thb_eval_fused_backward(C.byref(P.desc()), C.byref(plan.desc), ptr(plan.params), ptr(grad_out), cpd, ptr(g), P.nCP,
                                           ptr(ws) if ws is not None else None, stream_ptr(P.device)), "thb_eval_fused_backward")
+    return g
+
+
+def deterministic_default():
+    """THB_DETERMINISTIC=1 makes the ordered backward the default of eval_fused_backward / eval_fused_backward_rows."""
+    return _os.environ.get("THB_DETERMINISTIC", "0") not in ("0", "")
+
+
+def _ordered_backward(P, plan, grad_out, cpd, dense):
+    """thb_eval_fused_backward_ordered: every sum in a fixed order (no atomics).  dense: [nCP, cpd], else compact rows."""
+    tr_ptr, tr_idx = P.ordered_scatter_tables()
+    ids, _ = P.active_rows()
+    ws = getattr(P, "_ordered_ws", None)
+    key = (plan.max_items, cpd)
+    if ws is None or ws[0] != key:
+        ws = P._ordered_ws = (key,
+                              torch.empty((plan.max_items, 4, P.TS), dtype=torch.float32, device=P.device),
+                              torch.zeros(P.nslots, dtype=torch.int32, device=P.device),
+                              torch.empty((P.supp_jm.shape[0], cpd), dtype=torch.float32, device=P.device))
+    od = OrderedDesc()
+    od.item_ws, od.item0, od.contrib = ws[1].data_ptr(), ws[2].data_ptr(), ws[3].data_ptr()
+    od.tr_ptr, od.tr_idx = tr_ptr.data_ptr(), tr_idx.data_ptr()
+    od.active_ids = ids.data_ptr() if dense else None
+    od.nsupp, od.nrows = int(P.supp_jm.shape[0]), int(ids.shape[0])
+    g = torch.empty((P.nCP if dense else ids.shape[0], cpd), dtype=torch.float32, device=P.device)
+    with _on(P.device):
+        check(lib.thb_eval_fused_backward_ordered(C.byref(P.desc()), C.byref(plan.desc), ptr(plan.params), ptr(grad_out), cpd, C.byref(od),
+                                                  ptr(g), g.shape[0], ptr(_gnet_workspace(P)), stream_ptr(P.device)),
+              "thb_eval_fused_backward_ordered")
     return g
 
 
@@ -314,7 +367,7 @@ def _gnet_workspace(P):
     return ws
 
 
-def eval_fused_backward_rows(P, plan, grad_out, out=None):
+def eval_fused_backward_rows(P, plan, grad_out, out=None, deterministic=None):
     """The same gradient in COMPACT rows: [P.n_active, cp_dim], row i = flat function id P.active_rows()[0][i]
     (thb_eval_fused_backward_rows).  Only active functions receive a gradient, so this is everything there is."""
     require_cuda(grad_out, "grad_out", torch.float32)
@@ -326,6 +379,14 @@ def eval_fused_backward_rows(P, plan, grad_out, out=None):
     plan.refresh()
     _check_rows([grad_out], plan, cpd, "grad_out")
     ids, row_map = P.active_rows()
+    if deterministic is None:
+        deterministic = deterministic_default()
+    if deterministic:
+        g = _ordered_backward(P, plan, grad_out, cpd, dense=False)
+        if out is not None:
+            out.copy_(g)
+            return out
+        return g
     g = out if out is not None else torch.empty((ids.shape[0], cpd), dtype=torch.float32, device=P.device)
     if g.shape != (ids.shape[0], cpd) or not g.is_contiguous() or not _same_device(g.device, P.device) or g.dtype != torch.float32:
         raise RuntimeError(f"out must be a contiguous float32 [{ids.shape[0]}, {cpd}] tensor on {P.device}")
@@ -390,8 +451,11 @@ def eval_forward(ctrl_pts, Jm, PHI, cumsum):
     return out
 
 
-def eval_backward(grad_output, ctrl_pts, Jm, PHI, cumsum):
-    """THB_eval.backward: grad_ctrl_pts[nCP, cp_dim]."""
+def eval_backward(grad_output, ctrl_pts, Jm, PHI, cumsum, deterministic=None):
+    """THB_eval.backward: grad_ctrl_pts[nCP, cp_dim].  deterministic=True (default from THB_DETERMINISTIC): instead of the
+    warp-aggregated atomics, the (point, support) products are sorted by support id (stable radix sort) and summed per
+    control point in that order -- bit-identical from run to run, at the price of materialising the nnz x cp_dim products
+    (the reference itself is order-dependent: one atomicAdd per pair, compute_pts_cuda_kernels.cu:43)."""
     require_cuda(ctrl_pts, "ctrl_pts", torch.float32)
     grad_output = grad_output.contiguous()
     require_cuda(grad_output, "grad_output", torch.float32)
@@ -401,6 +465,15 @@ def eval_backward(grad_output, ctrl_pts, Jm, PHI, cumsum):
     n = cumsum.shape[0]
     if grad_output.shape != (n, ctrl_pts.shape[1]):
         raise RuntimeError("grad_output must be [N, cp_dim]")
+    if deterministic is None:
+        deterministic = deterministic_default()
+    if deterministic:
+        lengths = torch.diff(cumsum.long(), prepend=cumsum.new_zeros(1).long())
+        seg = torch.repeat_interleave(torch.arange(n, device=cumsum.device), lengths)
+        order = torch.argsort(Jm.long(), stable=True)
+        vals = (PHI[order].unsqueeze(1) * grad_output[seg[order]]).contiguous()
+        counts = torch.bincount(Jm.long(), minlength=ctrl_pts.shape[0])
+        return torch.segment_reduce(vals, "sum", lengths=counts, axis=0, unsafe=True).to(torch.float32).contiguous()
     g = torch.empty_like(ctrl_pts)
     with _on(ctrl_pts.device):
         check(lib.thb_eval_backward(ptr(grad_output), ptr(Jm), _idx(Jm, "Jm_array"), ptr(PHI), ptr(cumsum), _idx(cumsum, "cumsum"), ptr(g), n,

@@ -503,6 +503,40 @@ class PackedHierarchy:
             c = self._active_rows = (ids.to(torch.int32), row_map)
         return c
 
+    def ordered_scatter_tables(self):
+        """(tr_ptr int32 [n_active + 1], tr_idx int32 [nsupp]) for the ORDERED backward (thb_eval_fused_backward_ordered):
+        every (cell, support) pair owns one slot of a contribution buffer, slot = supp_off(cell) + position with the cell's
+        supports in the order  own-level (window order) | rank-one tiled | full-tile;  tr_idx lists, for every active
+        function (compact row of active_rows()), its slots in increasing slot number.  Cached; device tensors."""
+        c = getattr(self, "_ordered_tables", None)
+        if c is None:
+            info = self.cellinfo.long()
+            soff, S, ndir = info[:, 4], info[:, 5], info[:, 7]
+            nsupp = int(self.supp_jm.shape[0])
+            fn = torch.empty(nsupp, dtype=torch.int64, device=self.device)
+            pos = torch.arange(nsupp, device=self.device)
+            cell = torch.repeat_interleave(torch.arange(self.nslots, device=self.device), S)   # slots are laid out cell by cell
+            local = pos - soff[cell]
+            direct = local < ndir[cell]
+            fn[direct] = self.supp_jm.long()[pos[direct]]
+            if getattr(self, "sep_vec", None) is not None:
+                sep_off, nsep, full_off = info[:, 8], info[:, 9], info[:, 10]
+                t = local - ndir[cell]
+                is_sep = (~direct) & (t < nsep[cell])
+                is_full = (~direct) & (~is_sep)
+                fn[is_sep] = self.sep_jm.long()[(sep_off[cell] + t)[is_sep]]
+                fn[is_full] = self.full_jm.long()[(full_off[cell] + t - nsep[cell])[is_full]]
+            else:
+                fn[~direct] = self.supp_jm.long()[pos[~direct]]
+            ids, row_map = self.active_rows()
+            rows = row_map.long()[fn]
+            order = torch.argsort(rows, stable=True)
+            cnt = torch.bincount(rows, minlength=ids.shape[0])
+            tr_ptr = torch.zeros(ids.shape[0] + 1, dtype=torch.int64, device=self.device)
+            tr_ptr[1:] = torch.cumsum(cnt, 0)
+            c = self._ordered_tables = (tr_ptr.to(torch.int32), order.to(torch.int32))
+        return c
+
     @property
     def n_active(self):
         return int(self.active_rows()[0].shape[0])
