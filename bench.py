@@ -410,9 +410,10 @@ def fit_block(sp, P, rank, world, device, cell_cost, n_total=10_000_000):
     balance["cell_cost_used"] = cell_cost
     del rows, slot, payload
     res = {"balance": balance}
-    for name, use_graph in (("eager", False), ("graph", True)):
+    variants = [("eager", False, None), ("graph", True, None)] + ([("graph_nccl", True, False)] if world > 1 else [])
+    for name, use_graph, peer in variants:
         xx = x.clone()
-        eng = FitEngine(P, prm, tgt, n_total, lr=1e-2, use_graph=use_graph)
+        eng = FitEngine(P, prm, tgt, n_total, lr=1e-2, use_graph=use_graph, peer=peer)
         losses = []
         for _ in range(3):
             l = eng.step(xx).clone()
@@ -424,13 +425,21 @@ def fit_block(sp, P, rank, world, device, cell_cost, n_total=10_000_000):
         if world > 1:
             dist.all_reduce(l)
         res[name] = {"ms_per_step": ms, "adam_steps_per_s": 1e3 / ms, "loss_first": losses[0], "loss_third": losses[2], "loss_last": float(l),
-                     "cuda_graph": eng._graph is not None}
+                     "cuda_graph": bool(eng._graph),
+                     "exchange": "none (1 rank)" if world == 1 else ("NVLink peer memory, fused into the optimiser kernel (thb_adam_rows_peer)"
+                                                                     if eng.peer is not None else "NCCL all-reduce of the compact rows")}
+        if eng.peer is not None:
+            res[name]["peer_wait_timeouts"] = int(eng.peer.err.item())
+        elif world > 1 and peer is None:
+            res[name]["peer_unavailable"] = getattr(eng, "peer_error", None)
         if not use_graph:
             c, a, o = eng.time_phases(xx, iters=20)
             t = torch.tensor([c, a, o], device=device)
             if world > 1:
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            res["phases_ms"] = {"compute": float(t[0]), "allreduce": float(t[1]), "adam": float(t[2])}
+            res["phases_ms"] = {"compute": float(t[0]), "allreduce": float(t[1]), "adam": float(t[2]),
+                                "note": "eager launches; with peer memory the exchange is inside the `adam` kernel pair (flag wait + peer reads + Adam); "
+                                        "times include waiting for the slowest rank"}
             cnt = torch.tensor([float(prm.shape[0])], device=device)
             allc = [torch.zeros_like(cnt) for _ in range(world)]
             if world > 1:
@@ -439,7 +448,7 @@ def fit_block(sp, P, rank, world, device, cell_cost, n_total=10_000_000):
                 allc = [cnt]
             res["points_per_rank"] = [int(v) for v in allc]
         del eng
-    best = min(res["eager"]["ms_per_step"], res["graph"]["ms_per_step"])
+    best = min(res[k]["ms_per_step"] for k, _, _ in variants)
     res.update({"adam_steps_per_s": 1e3 / best, "ms_per_step": best, "points": n_total, "n_active_rows": P.n_active,
                 "allreduce_bytes": P.n_active * 3 * 4, "dense_gradient_bytes": P.nCP * 3 * 4,
                 "what": "10M random points moved once to the rank owning their cell (all-to-all), plan built once; step = nets + evaluation + "
@@ -850,7 +859,9 @@ def main():
             c["fit_c4_adam_steps_per_s"], c["fit_c4_ms_per_step"] = b["adam_steps_per_s"], b["ms_per_step"]
             c["fit_c4_allreduce_ms"], c["fit_c4_compute_ms"], c["fit_c4_adam_ms"] = (b["phases_ms"][k] for k in ("allreduce", "compute", "adam"))
             c["fit_c4_allreduce_bytes"], c["fit_c4_loss_first"], c["fit_c4_loss_last"] = b["allreduce_bytes"], b["eager"]["loss_first"], b["eager"]["loss_last"]
-            c["fit_c4_collective"] = "none (1 rank)" if world == 1 else "NCCL all-reduce of the compact active-row gradient"
+            c["fit_c4_collective"] = b["graph"]["exchange"]
+            if "graph_nccl" in b:
+                c["fit_c4_ms_per_step_nccl"] = b["graph_nccl"]["ms_per_step"]
         b = blocks.get("c5", {})
         if "points_per_s" in b:
             c["c5_points_per_s"], c["c5_ms_per_step"], c["c5_jacobian_max_abs_err"] = b["points_per_s"], b["ms_per_step"], b["jacobian_max_abs_err"]

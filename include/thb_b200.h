@@ -275,13 +275,25 @@ THB_API int thb_eval_fused_backward_ordered(const thb_space_desc* space, const t
  *     dense parameter params[nctrl, cp_dim] with gradient grad_rows[r, :] * grad_scale and state exp_avg / exp_avg_sq
  *     [nrows, cp_dim].  Rows outside row_ids keep a zero gradient for ever, and Adam never moves such a row, so this is
  *     the dense optimiser restricted to the rows it can change.  step: 1-based step number; when step_dev (device i32)
- *     is non-null the number is step_dev[0] + 1 and the call increments it (CUDA-graph replay). */
+ *     is non-null the number is step_dev[0] + 1 and the call increments it (CUDA-graph replay).
+ * thb_adam_rows_peer: the all-reduce of the gradient rows and the Adam step as ONE enqueue over NVLink peer memory, no
+ *     collective library call.  peer_grads[r] / peer_flags[r] (host arrays of `world` DEVICE pointers): rank r's gradient
+ *     rows [nrows, cp_dim] f32 and flag array (>= world u32, zero-initialised) as mapped into THIS process (symmetric /
+ *     peer memory); entry `rank` is this rank's own buffer.  Every rank stores the step number (step_dev[0] + 1) into
+ *     its slot of every peer's flags, waits for all of them, then adds the peers' rows in rank order -- bitwise the same
+ *     sum on every rank -- and applies Adam; step_dev is incremented.  The caller alternates between TWO gradient buffers
+ *     per rank from step to step (a rank running ahead must not overwrite rows a slow peer still reads).  err[0] is set
+ *     to 1 when a peer does not arrive within ~4 s (the call never hangs the GPU). */
 THB_API int64_t thb_mse_workspace_bytes(void);
 THB_API int thb_mse_grad(const float* out, const float* target, int64_t nvalues, float scale, float* grad_out, float* loss,
                  void* workspace, void* stream);
 THB_API int thb_adam_rows(float* params, const int32_t* row_ids, const float* grad_rows, float* exp_avg, float* exp_avg_sq,
                   int64_t nrows, int cp_dim, float lr, float beta1, float beta2, float eps, float grad_scale, int step,
                   int32_t* step_dev, void* stream);
+
+THB_API int thb_adam_rows_peer(float* params, const int32_t* row_ids, const void* const* peer_grads, void* const* peer_flags,
+                       int world, int rank, float* exp_avg, float* exp_avg_sq, int64_t nrows, int cp_dim, float lr, float beta1,
+                       float beta2, float eps, float grad_scale, int32_t* step_dev, int32_t* err, void* stream);
 
 /* ---- measurement helpers -----------------------------------------------------------------------------------
  * Dependent-chain FP32 FMA micro-kernel used by bench.py to measure the FP32 roofline denominator.

@@ -33,9 +33,9 @@ def _fit_worker(rank, world, port, ret):
     tgt_all = torch.stack([prm_all[:, 0], prm_all[:, 1], prm_all[:, 2] + 0.1 * torch.sin(6.2831853 * prm_all[:, 0])], 1).contiguous()
     x0 = torch.from_numpy(configs.greville_ctrl_pts(sp, bump=0.0)).to(dev)
 
-    def run(prm, tgt, use_graph):
+    def run(prm, tgt, use_graph, peer=None):
         x = x0.clone()
-        eng = FitEngine(P, prm, tgt, n_total, lr=1e-2, use_graph=use_graph)
+        eng = FitEngine(P, prm, tgt, n_total, lr=1e-2, use_graph=use_graph, peer=peer)
         losses = []
         for _ in range(6):
             l = eng.step(x).clone()
@@ -50,6 +50,12 @@ def _fit_worker(rank, world, port, ret):
     for use_graph in (False, True):
         x, losses = run(rows[:, :3].contiguous(), rows[:, 3:].contiguous(), use_graph)
         res[use_graph] = (x.cpu().numpy(), losses)
+    x, losses = run(rows[:, :3].contiguous(), rows[:, 3:].contiguous(), True, peer=False)   # NCCL all-reduce instead of peer memory
+    res["nccl"] = (x.cpu().numpy(), losses)
+    probe = FitEngine(P, rows[:, :3].contiguous(), rows[:, 3:].contiguous(), n_total)
+    res["peer_active"] = probe.peer is not None
+    res["peer_error"] = getattr(probe, "peer_error", None)
+    res["peer_timeouts"] = int(probe.peer.err.item()) if probe.peer is not None else 0
     # sharded evaluation of a grid
     ax = [torch.from_numpy(np.linspace(1e-5, 1.0, 40, endpoint=False)).float().to(dev) for _ in range(3)]
     b = grid_slab_bounds(P, ax, world).tolist()
@@ -87,8 +93,10 @@ def test_two_rank_fit_and_sharded_evaluation_over_nccl():
     eng = FitEngine(P, prm, tgt, n_total, lr=1e-2)
     ref_losses = [float(eng.step(x)) for _ in range(6)]
     assert ret[0]["n_mine"] + ret[1]["n_mine"] == n_total and min(ret[0]["n_mine"], ret[1]["n_mine"]) > 0   # balanced by points + cells, not by points
+    print("peer memory active:", ret[0]["fit"]["peer_active"], ret[0]["fit"]["peer_error"])
+    assert ret[0]["fit"]["peer_timeouts"] == 0
     for r in range(world):
-        for use_graph in (False, True):
+        for use_graph in (False, True, "nccl"):
             xr, losses = ret[r]["fit"][use_graph]
             assert np.allclose(losses, ref_losses, rtol=1e-5, atol=1e-10), (r, use_graph, losses, ref_losses)
             assert np.abs(xr - x.cpu().numpy()).max() <= 5e-5

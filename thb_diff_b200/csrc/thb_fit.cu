@@ -91,6 +91,68 @@ __global__ void __launch_bounds__(256) k_adam_rows(float* __restrict__ params, c
 
 __global__ void k_step_inc(int32_t* step_dev) { step_dev[0] += 1; }
 
+// ---- gradient all-reduce over NVLink peer memory, fused with the optimiser ----------------------------------------------
+// Every rank keeps its compact gradient rows in a buffer its peers can read (symmetric memory: the same allocation made on
+// every GPU and mapped into every process).  One step of a fit then needs no collective library call:
+//   k_peer_arrive_wait : rank r stores the step number into slot r of every peer's flag array (st.release.sys) and waits
+//                        until its own array holds that number from every peer (ld.acquire.sys): all gradients are written
+//   k_adam_rows_peer   : g = sum over ranks of peer_grad[rank][e], read straight from the peers' memory in rank order (so
+//                        every rank forms the same sum bit for bit and the replicated parameters stay identical), then Adam
+// The gradient buffers alternate between two allocations by step parity, so a rank that runs ahead writes the other buffer
+// while a slow peer still reads this one; by the time a buffer is written again every peer has passed the arrive-wait of
+// the step in between, i.e. finished reading it.  A wait that lasts longer than ~4 s sets err[0] = 1 and gives up (a dead
+// peer must not hang the GPU).
+constexpr int kMaxPeers = 16;
+struct PeerPtrs {
+    const float* grad[kMaxPeers];
+    unsigned* flags[kMaxPeers];
+};
+
+__global__ void __launch_bounds__(32) k_peer_arrive_wait(PeerPtrs pp, int world, int rank, const int32_t* __restrict__ step_dev,
+                                                         int32_t* __restrict__ err) {
+    const int r = threadIdx.x;
+    const unsigned seq = (unsigned)(step_dev[0] + 1);
+    if (r < world) {
+        __threadfence_system();   // this rank's gradient (written by the kernels before this one) is visible to the peers
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pp.flags[r] + rank), "r"(seq) : "memory");
+        const unsigned* mine = pp.flags[rank] + r;
+        const long long t0 = clock64();
+        unsigned v;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+            if ((int)(v - seq) >= 0) break;
+            if (clock64() - t0 > 8000000000ll) { err[0] = 1; break; }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_adam_rows_peer(float* __restrict__ params, const int32_t* __restrict__ row_ids, PeerPtrs pp,
+                                                        int world, float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq,
+                                                        int64_t nrows, int cpd, AdamArgs a, const int32_t* __restrict__ step_dev) {
+    const int64_t tot = nrows * cpd;
+    const int t = step_dev ? step_dev[0] + 1 : a.step;
+    const double bc1 = 1.0 - pow((double)a.beta1, (double)t), bc2 = 1.0 - pow((double)a.beta2, (double)t);
+    const float step_size = (float)((double)a.lr / bc1), bc2_sqrt = (float)sqrt(bc2);
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (int64_t)gridDim.x * blockDim.x) {
+        float g = 0.0f;
+        for (int r = 0; r < world; ++r) {   // rank order: the same sum on every rank
+            float v;
+            asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(pp.grad[r] + e) : "memory");   // never from a stale L1 line
+            g += v;
+        }
+        g *= a.grad_scale;
+        const int64_t row = e / cpd;
+        const int k = (int)(e - row * cpd);
+        const float m = a.beta1 * exp_avg[e] + (1.0f - a.beta1) * g;
+        const float v = a.beta2 * exp_avg_sq[e] + (1.0f - a.beta2) * g * g;
+        exp_avg[e] = m;
+        exp_avg_sq[e] = v;
+        const float denom = sqrtf(v) / bc2_sqrt + a.eps;
+        float* p = params + (int64_t)__ldg(row_ids + row) * cpd + k;
+        *p = *p - step_size * (m / denom);
+    }
+}
+
 }  // namespace
 
 extern "C" int64_t thb_mse_workspace_bytes(void) { return (int64_t)(1024 * sizeof(double) + 16); }
@@ -131,5 +193,33 @@ extern "C" int thb_adam_rows(float* params, const int32_t* row_ids, const float*
         k_step_inc<<<1, 1, 0, st>>>(step_dev);
         THB_LAUNCHED();
     }
+    return THB_OK;
+}
+
+extern "C" int thb_adam_rows_peer(float* params, const int32_t* row_ids, const void* const* peer_grads, void* const* peer_flags,
+                                  int world, int rank, float* exp_avg, float* exp_avg_sq, int64_t nrows, int cp_dim, float lr,
+                                  float beta1, float beta2, float eps, float grad_scale, int32_t* step_dev, int32_t* err,
+                                  void* stream) {
+    THB_REQUIRE(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, "thb_adam_rows_peer: bad world / rank");
+    THB_REQUIRE(nrows >= 0 && cp_dim >= 1 && cp_dim <= 4, "thb_adam_rows_peer: bad sizes");
+    THB_REQUIRE(params && row_ids && peer_grads && peer_flags && exp_avg && exp_avg_sq && step_dev && err, "thb_adam_rows_peer: null pointer");
+    PeerPtrs pp = {};
+    for (int r = 0; r < world; ++r) {
+        THB_REQUIRE(peer_grads[r] && peer_flags[r], "thb_adam_rows_peer: null peer pointer");
+        pp.grad[r] = (const float*)peer_grads[r];
+        pp.flags[r] = (unsigned*)peer_flags[r];
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    k_peer_arrive_wait<<<1, 32, 0, st>>>(pp, world, rank, step_dev, err);
+    THB_LAUNCHED();
+    if (nrows > 0) {
+        AdamArgs a = {lr, beta1, beta2, eps, grad_scale, 0};
+        const int64_t tot = nrows * cp_dim;
+        const int64_t want = (tot + 255) / 256, cap = (int64_t)thb_num_sms() * 8;
+        k_adam_rows_peer<<<(int)(want < cap ? want : cap), 256, 0, st>>>(params, row_ids, pp, world, exp_avg, exp_avg_sq, nrows, cp_dim, a, step_dev);
+        THB_LAUNCHED();
+    }
+    k_step_inc<<<1, 1, 0, st>>>(step_dev);
+    THB_LAUNCHED();
     return THB_OK;
 }

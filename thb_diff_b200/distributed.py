@@ -11,6 +11,8 @@ Sharding a FIT (fixed points, many steps) by cells: the per-cell work of a step 
 fold of the net gradients) is as large as the per-point work, so ranks must own disjoint sets of CELLS, not arbitrary
 subsets of the points -- `partition_by_cell` moves every point to the rank that owns its cell once, at set-up
 (all-to-all), balanced by points + per-cell cost ("sort by active cell then split evenly")."""
+import os as _os
+
 import torch
 import torch.distributed as dist
 
@@ -205,6 +207,37 @@ class ShardedFit:
         return loss.detach()
 
 
+class PeerRows:
+    """The compact gradient rows of every rank in memory all ranks of the node can read (torch symmetric memory: the same
+    allocation on every GPU, mapped into every process over NVLink), twice -- steps alternate between the two buffers --
+    plus one flag array per rank.  With it the gradient all-reduce is part of the optimiser kernel (thb_adam_rows_peer)
+    instead of a collective-library call."""
+
+    def __init__(self, n_rows, cp_dim, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+
+        group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > 16:
+            raise RuntimeError("PeerRows: at most 16 ranks")
+        self.grads, self.grad_ptrs, self._handles = [], [], []
+        for _ in range(2):
+            t = symm.empty((n_rows, cp_dim), dtype=torch.float32, device=device)
+            t.zero_()
+            h = symm.rendezvous(t, group=group)
+            self.grads.append(t)
+            self.grad_ptrs.append([int(p) for p in h.buffer_ptrs])
+            self._handles.append(h)
+        self.flags = symm.empty(64, dtype=torch.int32, device=device)
+        self.flags.zero_()
+        hf = symm.rendezvous(self.flags, group=group)
+        self._handles.append(hf)
+        self.flag_ptrs = [int(p) for p in hf.buffer_ptrs]
+        self.err = torch.zeros(1, dtype=torch.int32, device=device)
+        torch.cuda.synchronize(device)
+        dist.barrier(group)   # every rank's buffers and flags are zero before anyone signals
+
+
 class FitEngine:
     """The fit step of BASELINE config 4 with everything compact and nothing through autograd:
 
@@ -222,7 +255,7 @@ class FitEngine:
     (thb_mse_grad is ordered already) and the control points are then bit-identical from run to run on one rank."""
 
     def __init__(self, packed, params, targets, n_total, lr=1e-2, betas=(0.9, 0.999), eps=1e-8, group=None, use_graph=False,
-                 deterministic=None):
+                 deterministic=None, peer=None):
         from . import engine
 
         self.E, self.P, self.group = engine, packed, group
@@ -251,24 +284,42 @@ class FitEngine:
         self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
         self.mse_ws = engine.mse_workspace(dev)
         self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
-        self.use_graph, self._graph, self._graph_x = bool(use_graph), None, None
+        self.use_graph, self._graph, self._graph_x = bool(use_graph), {}, None
         self.timers = None
+        # gradient exchange: NVLink peer memory fused into the optimiser kernel when the ranks can map each other's memory
+        # (peer=None: try it, fall back to the NCCL all-reduce; peer=True: required; peer=False: NCCL)
+        self.peer, self._parity, self._nsteps = None, 0, 0
+        if _world(group) > 1 and peer is not False and _os.environ.get("THB_PEER_ROWS", "1") != "0":
+            try:
+                self.peer = PeerRows(na, cpd, dev, group)
+            except Exception as e:
+                if peer:
+                    raise
+                self.peer_error = repr(e)
 
-    def _enqueue(self, x):
+    def _enqueue(self, x, parity=0):
         E, P = self.E, self.P
         t = self.timers
+        grad = self.peer.grads[parity] if self.peer is not None else self.grad
         if t:
             t[0].record()
         nets = E.cell_nets(P, x, plan=self.plan)
         E.eval_nets(P, self.plan, nets, self.cpd, out=[self.out], with_derivatives=False)
         E.mse_grad(self.out, self.targets, 1.0 / (self.n_total * self.cpd), self.gout, self.loss, self.mse_ws)
-        E.eval_fused_backward_rows(P, self.plan, self.gout, out=self.grad, deterministic=self.deterministic)
+        E.eval_fused_backward_rows(P, self.plan, self.gout, out=grad, deterministic=self.deterministic)
         if t:
             t[1].record()
-        allreduce_grad_(self.grad, self.group)
-        if t:
-            t[2].record()
-        E.adam_rows(x, self.ids, self.grad, self.m, self.v, self.lr, self.betas, self.eps, step_dev=self.step_dev)
+        if self.peer is not None:
+            # arrive + wait on the peers' flags, sum of the peers' rows in rank order, Adam: one enqueue, no collective call
+            if t:
+                t[2].record()
+            E.adam_rows_peer(x, self.ids, self.peer.grad_ptrs[parity], self.peer.flag_ptrs, self.peer.rank, self.m, self.v, self.lr,
+                             self.betas, self.eps, self.step_dev, self.peer.err)
+        else:
+            allreduce_grad_(grad, self.group)
+            if t:
+                t[2].record()
+            E.adam_rows(x, self.ids, grad, self.m, self.v, self.lr, self.betas, self.eps, step_dev=self.step_dev)
         if t:
             t[3].record()
 
@@ -276,23 +327,30 @@ class FitEngine:
         x = ctrl_pts
         if x.requires_grad:
             x = x.detach()
+        parity = self._parity if self.peer is not None else 0
+        self._parity ^= 1
+        self._nsteps += 1
         if not self.use_graph:
-            self._enqueue(x)
+            self._enqueue(x, parity)
             return self.loss
-        if self._graph is None or self._graph_x != x.data_ptr():
-            self._enqueue(x)   # eager once (allocations, NCCL warm-up)
-            torch.cuda.synchronize(self.P.device)
-            try:
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    self._enqueue(x)
-                self._graph, self._graph_x = g, x.data_ptr()
-                # the capture itself does not run the step
-            except Exception:
-                self.use_graph, self._graph = False, None
+        if self._graph_x != x.data_ptr():
+            self._graph, self._graph_x, self._eager_left = {}, x.data_ptr(), 2   # two eager steps (one per buffer), then capture
+        if self._eager_left > 0:
+            self._enqueue(x, parity)   # eager: allocations, NCCL warm-up
+            self._eager_left -= 1
+            if self._eager_left == 0:
                 torch.cuda.synchronize(self.P.device)
+                try:
+                    for par in ((0, 1) if self.peer is not None else (0,)):
+                        g = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g):
+                            self._enqueue(x, par)   # the capture itself does not run the step
+                        self._graph[par] = g
+                except Exception:
+                    self.use_graph, self._graph = False, {}
+                    torch.cuda.synchronize(self.P.device)
             return self.loss
-        self._graph.replay()
+        self._graph[parity].replay()
         return self.loss
 
     def time_phases(self, ctrl_pts, iters=10):
@@ -307,4 +365,5 @@ class FitEngine:
         self.use_graph = keep
         torch.cuda.synchronize(self.P.device)
         f = lambda a, b: sum(e[a].elapsed_time(e[b]) for e in ev) / iters
+        # NCCL: compute | all-reduce | Adam.  Peer memory: compute | 0 | fused (flags + peer reads + Adam)
         return f(0, 1), f(1, 2), f(2, 3)

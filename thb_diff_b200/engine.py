@@ -427,6 +427,21 @@ def adam_rows(params, row_ids, grad_rows, exp_avg, exp_avg_sq, lr, betas, eps, s
     return params
 
 
+def adam_rows_peer(params, row_ids, peer_grads, peer_flags, rank, exp_avg, exp_avg_sq, lr, betas, eps, step_dev, err, grad_scale=1.0):
+    """All-reduce of the gradient rows over NVLink peer memory fused with the Adam step (thb_adam_rows_peer).
+    peer_grads / peer_flags: lists of device pointers (ints), one per rank, as mapped into this process."""
+    require_cuda(params, "params", torch.float32)
+    require_cuda(row_ids, "row_ids", torch.int32)
+    world = len(peer_grads)
+    ga = (C.c_void_p * world)(*[int(p) for p in peer_grads])
+    fa = (C.c_void_p * world)(*[int(p) for p in peer_flags])
+    with _on(params.device):
+        check(lib.thb_adam_rows_peer(ptr(params), ptr(row_ids), ga, fa, world, int(rank), ptr(exp_avg), ptr(exp_avg_sq), row_ids.shape[0],
+                                     params.shape[1], float(lr), float(betas[0]), float(betas[1]), float(eps), float(grad_scale),
+                                     ptr(step_dev), ptr(err), stream_ptr(params.device)), "thb_adam_rows_peer")
+    return params
+
+
 def _idx(t, name):
     if t.dtype not in (torch.int64, torch.int32):
         raise RuntimeError(f"{name} must be int64 or int32")
