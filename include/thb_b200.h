@@ -208,6 +208,9 @@ THB_API int thb_eval_fused(const thb_space_desc* space, const thb_plan_desc* pla
  *                             cell-local coordinate s_k = (u_k - lo_k) / half_k - 1 (thb_space_desc::poly, required),
  *                             <tp(u), W> = sum M[m0][m1][m2] s0^m0 s1^m1 s2^m2 and a point costs three subtractions plus a
  *                             nested Horner scheme (30 packed FMAs per output component for cubic 3-D) -- no Cox-de Boor.
+ *                             Monomial nets are built from control points relative to the cell's first support with that
+ *                             point added back to the constant term, so ONE set of four planes serves the value and every
+ *                             derivative channel (THB_NETS_DERIVATIVES changes nothing for them).
  *                             thb_eval_fused uses this form whenever `poly` is present.
  * thb_cell_nets: plan == NULL builds every active cell, otherwise only the cells that hold points of the plan.
  * Together the two calls replace THB_basis_fns (THB/core.py:604-701) + prepare_data_for_CUDA_evaluation

@@ -229,8 +229,16 @@ def test_local_net_needs_a_workspace_and_nets_are_reusable():
     half = engine.Plan(P, g["params"][: len(cs) // 2])               # another batch, same nets
     b = engine.eval_nets(P, half, nets, 3)[0].cpu().numpy()
     assert rel_err(b, ref[: len(cs) // 2], scale=np.abs(ref).max()).max() <= TOL
-    with pytest.raises(RuntimeError):                                # derivative channels need nets built with them
-        engine.eval_nets(P, plan, nets, 3, channels=engine.grad_channels(3), with_derivatives=False)
+    # control-point nets: derivative channels need the relative planes; monomial nets serve them from the same four planes
+    assert _lib.lib.thb_net_workspace_floats(C.byref(P.desc()), 3) == P.nslots * 4 * P.TS
+    nets_cp = engine.cell_nets(P, cpt, monomial=False)
+    with pytest.raises(RuntimeError):
+        engine.eval_nets(P, plan, nets_cp, 3, channels=engine.grad_channels(3), with_derivatives=False)
+    if nets._thb_flags & engine.NETS_MONOMIAL:
+        d_mono = engine.eval_nets(P, plan, engine.cell_nets(P, cpt), 3, channels=engine.grad_channels(3))
+        d_cp = engine.eval_nets(P, plan, engine.cell_nets(P, cpt, with_derivatives=True, monomial=False).clone(), 3, channels=engine.grad_channels(3))
+        for x, y in zip(d_mono, d_cp):
+            assert float((x - y).abs().max()) <= 2e-5 * max(float(y.abs().max()), 1.0)
 
 
 def test_rows_in_plan_order():

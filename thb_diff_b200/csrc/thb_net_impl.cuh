@@ -49,6 +49,16 @@ THB_DEV float4 load_cp(const float* __restrict__ cp, int64_t r) {
     return make_float4(v[0], v[1], v[2], v[3]);
 }
 
+// control point minus the cell's reference point (monomial nets are built from RELATIVE control points: every polynomial
+// coefficient but the constant one is a difference of control points, and forming it from small numbers keeps the
+// first-derivative channels free of float32 cancellation; the reference point is added back to the constant term)
+template <int CPD>
+THB_DEV float4 load_cp_sub(const float* __restrict__ cp, int64_t r, const float* ref, bool sub) {
+    float4 v = load_cp<CPD>(cp, r);
+    if (sub) { v.x -= ref[0]; v.y -= ref[1]; v.z -= ref[2]; v.w -= ref[3]; }
+    return v;
+}
+
 // (w01, w23)[k] += (x01, x23) * c[k]   (and the relative planes with c - ref)
 template <int CPD, bool REL>
 THB_DEV void fold2(f32x2 (*w2)[4], f32x2 (*wr2)[4], f32x2 x01, f32x2 x23, const float4& c, const float* ref) {
@@ -154,7 +164,8 @@ __global__ void __launch_bounds__(32 * kNetWarps, (REL || CPD == 4) ? 6 : THB_NE
         const int nsep = split ? f.y : 0;
         if (na.mono) stage_span_polys(sp, lev, a.y, a.z, a.w, s_cmat[wid]);
         float ref[4] = {0.f, 0.f, 0.f, 0.f};
-        if (REL && S > 0) {
+        const bool sub = na.mono != 0;   // monomial form: W is built from control points relative to `ref`
+        if ((REL || sub) && S > 0) {
             const float4 r = load_cp<CPD>(na.ctrl_pts, __ldg(sp.supp_jm + soff));
             ref[0] = r.x; ref[1] = r.y; ref[2] = r.z; ref[3] = r.w;
         }
@@ -179,7 +190,7 @@ __global__ void __launch_bounds__(32 * kNetWarps, (REL || CPD == 4) ? 6 : THB_NE
                         const int t0 = 2 * p + q, t = t0 * 16 + l16;
                         on[q] = ndir > 0 && p == half && ((dm >> t) & 1ull);  // half h loads the entries a = 2h, 2h+1
                         v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (on[q]) v[q] = load_cp<CPD>(na.ctrl_pts, f0 + ((int64_t)(a.y + t0) * n1 + (a.z + t1)) * n2 + (a.w + t2));
+                        if (on[q]) v[q] = load_cp_sub<CPD>(na.ctrl_pts, f0 + ((int64_t)(a.y + t0) * n1 + (a.z + t1)) * n2 + (a.w + t2), ref, sub);
                     }
                     w2[p][0] = pack2(v[0].x, v[1].x); w2[p][1] = pack2(v[0].y, v[1].y); w2[p][2] = pack2(v[0].z, v[1].z);
                     w2[p][3] = pack2(v[0].w, v[1].w);
@@ -208,7 +219,7 @@ __global__ void __launch_bounds__(32 * kNetWarps, (REL || CPD == 4) ? 6 : THB_NE
                 }
                 {   // control point of tiled support c0 + lane (rank-one ones first)
                     const int g = c0 + lane;
-                    if (g < ntile) cc[lane] = load_cp<CPD>(na.ctrl_pts, __ldg(g < nsep ? sp.sep_jm + f.x + g : full_jm + (g - nsep)));
+                    if (g < ntile) cc[lane] = load_cp_sub<CPD>(na.ctrl_pts, __ldg(g < nsep ? sp.sep_jm + f.x + g : full_jm + (g - nsep)), ref, sub);
                 }
                 cp_async_wait<0>();
                 __syncwarp();
@@ -261,6 +272,8 @@ __global__ void __launch_bounds__(32 * kNetWarps, (REL || CPD == 4) ? 6 : THB_NE
                 cp_async_wait<0>();
                 __syncwarp();
                 net_to_monomial<N0, N1, N2, CPD, REL>(s_cmat[wid], dst, TS);
+                if (lane < CPD) dst[lane * TS] += ref[lane];   // the reference point goes back into the constant term
+                __syncwarp();
                 const float4* b4 = reinterpret_cast<const float4*>(dst);
                 float4* d4 = reinterpret_cast<float4*>(gdst);
                 for (int i = lane; i < (REL ? 8 : 4) * TS / 4; i += 32) d4[i] = b4[i];
@@ -282,7 +295,7 @@ __global__ void __launch_bounds__(32 * kNetWarps, (REL || CPD == 4) ? 6 : THB_NE
                 ia[h] = tv[h] ? t0 : 0;
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                 const bool on = ndir > 0 && tv[h] && ((dm >> t) & 1ull);
-                if (on) v = load_cp<CPD>(na.ctrl_pts, f0 + ((int64_t)(a.y + t0) * n1 + (a.z + t1)) * n2 + (a.w + t2));
+                if (on) v = load_cp_sub<CPD>(na.ctrl_pts, f0 + ((int64_t)(a.y + t0) * n1 + (a.z + t1)) * n2 + (a.w + t2), ref, sub);
                 w[h][0] = v.x; w[h][1] = v.y; w[h][2] = v.z; w[h][3] = v.w;
                 if (REL) {
                     wr[h][0] = on ? v.x - ref[0] : 0.f; wr[h][1] = on ? v.y - ref[1] : 0.f;
@@ -308,9 +321,9 @@ __global__ void __launch_bounds__(32 * kNetWarps, (REL || CPD == 4) ? 6 : THB_NE
                 const float4* src = reinterpret_cast<const float4*>(sp.sep_vec + (int64_t)(f.x + s_lo) * 12);
                 for (int i = lane; i < s_n * 3; i += 32) cp_async16(&sepv[0][0] + i, src + i);
                 cp_async_commit();
-                for (int i = lane; i < s_n; i += 32) cc[i] = load_cp<CPD>(na.ctrl_pts, __ldg(sp.sep_jm + f.x + s_lo + i));
+                for (int i = lane; i < s_n; i += 32) cc[i] = load_cp_sub<CPD>(na.ctrl_pts, __ldg(sp.sep_jm + f.x + s_lo + i), ref, sub);
             }
-            for (int i = lane; i < f_n; i += 32) cc[s_n + i] = load_cp<CPD>(na.ctrl_pts, __ldg(full_jm + f_lo + i));
+            for (int i = lane; i < f_n; i += 32) cc[s_n + i] = load_cp_sub<CPD>(na.ctrl_pts, __ldg(full_jm + f_lo + i), ref, sub);
             cp_async_wait<0>();
             __syncwarp();
             if constexpr (NT == 2 && kSameBC && T == TS) {
@@ -404,6 +417,8 @@ __global__ void __launch_bounds__(32 * kNetWarps, (REL || CPD == 4) ? 6 : THB_NE
             cp_async_wait<0>();
             __syncwarp();
             net_to_monomial<N0, N1, N2, CPD, REL>(s_cmat[wid], buf, TS);
+            if (lane < CPD) buf[lane * TS] += ref[lane];   // the reference point goes back into the constant term
+            __syncwarp();
             const float4* b4 = reinterpret_cast<const float4*>(buf);
             float4* d4 = reinterpret_cast<float4*>(dst);
             for (int i = lane; i < (REL ? 8 : 4) * TS / 4; i += 32) d4[i] = b4[i];
@@ -425,9 +440,9 @@ __global__ void __launch_bounds__(32 * kNetWarps, (REL || CPD == 4) ? 6 : THB_NE
 }
 
 // ---- evaluation against the nets --------------------------------------------------------------------------------
-template <class SH, bool DER>
+template <class SH, bool DER, bool MONO = false>
 struct NetSmem {
-    static constexpr int NPL = DER ? 8 : 4;
+    static constexpr int NPL = (DER && !MONO) ? 8 : 4;   // monomial nets: one set of planes serves every channel
     int4 rec[3][4];                  // ring of work-item records (lookahead 2)
     float knots[2][3][8];            // local knots of the item's cell, per dimension
     float rk[3][8];                  // reciprocal knot differences of the current item
@@ -438,7 +453,7 @@ struct NetSmem {
 template <class SH, bool DER, bool MONO>
 THB_DEV void prefetch_net(const thb_space_desc& sp, const float* __restrict__ nets, const Item& it, float (*knots)[8],
                           float (*net)[SH::TS]) {
-    constexpr int NPL = DER ? 8 : 4;
+    constexpr int NPL = (DER && !MONO) ? 8 : 4;
     const int lane = threadIdx.x;
     if (MONO) {   // (lo, 1 / half) of the cell in every dimension: floats 16, 17 of its row of sp.poly
         if (lane < 6) {
@@ -480,7 +495,7 @@ THB_DEV void horner_mults(float s, bool der, float* mult) {
 // 30 FFMA2 + 3 FFMA per output component for cubic 3-D against 45 FFMA2 for the B-spline form -- and no Cox-de Boor.
 // Derivative channels use the derivative polynomial in the flagged dimensions (times 1 / half of that dimension).
 template <class SH, int PPT, int CPD, bool DER>
-THB_DEV void net_points_mono(const Args& ar, const Item& it, int base, NetSmem<SH, DER>& sm, int tb, int pb) {
+THB_DEV void net_points_mono(const Args& ar, const Item& it, int base, NetSmem<SH, DER, true>& sm, int tb, int pb) {
     constexpr int N0 = SH::N0, N1 = SH::N1, N2 = SH::N2;
     const int lane = threadIdx.x;
     int idx[PPT];
@@ -500,7 +515,7 @@ THB_DEV void net_points_mono(const Args& ar, const Item& it, int base, NetSmem<S
     }
     for (int chi = 0; chi < ar.nch; ++chi) {
         const int ch = ar.channels[chi];
-        const int pl = (DER && ch != 0) ? 4 : 0;  // derivative channels use the relative planes
+        constexpr int pl = 0;  // one set of planes: built from relative control points, reference point in the constant term
         const bool d0 = DER && (ch & 1), d1 = DER && (ch & 2), d2 = DER && (ch & 4);
         const float scale = (d0 ? ih[0] : 1.0f) * (d1 ? ih[1] : 1.0f) * (d2 ? ih[2] : 1.0f);
         float m0[PPT][N0 > 1 ? N0 - 1 : 1], m1[PPT][N1 > 1 ? N1 - 1 : 1], m2[PPT][N2 > 1 ? N2 - 1 : 1];
@@ -720,18 +735,124 @@ THB_DEV void net_points(const Args& ar, const Item& it, int base, NetSmem<SH, DE
     }
 }
 
+// Value + the three first derivatives in ONE pass over the monomial net (channels 0, 1, 2, 4 in this order: the outputs of
+// BASELINE config 5).  The four polynomials share their Horner stages:
+//   stage 1 over m1:  E  (value in s1)            -> recurrences over m0:  Qv (value in s0), Q0 (derivative in s0)
+//                     E' (derivative in s1)       -> recurrence  over m0:  Q1 (value in s0)
+//   finals over m2 :  value = H(Qv), d/du2 = H'(Qv), d/du0 = H(Q0) / half0, d/du1 = H(Q1) / half1
+// 56 FFMA2 + 11 FFMA per output component for cubic 3-D instead of 4 x 33 when the channels are evaluated one by one.
+template <class SH, int PPT, int CPD>
+THB_DEV void net_points_mono_grad4(const Args& ar, const Item& it, int base, NetSmem<SH, true, true>& sm, int tb, int pb) {
+    constexpr int N0 = SH::N0, N1 = SH::N1;
+    static_assert(SH::N2 == 4 && N0 >= 2 && N1 >= 2, "cubic last dimension");
+    const int lane = threadIdx.x;
+    int idx[PPT];
+    bool valid[PPT];
+    float s[PPT][3], ih[3];
+#pragma unroll
+    for (int dim = 0; dim < 3; ++dim) ih[dim] = sm.knots[tb][dim][1];
+#pragma unroll
+    for (int q = 0; q < PPT; ++q) {
+        valid[q] = base + q * 32 + lane < it.count;
+        const float4 rec = sm.prec[pb][q * 32 + lane];
+        idx[q] = ar.rows_sorted ? it.begin + base + q * 32 + lane : __float_as_int(rec.w);
+        s[q][0] = fmaf(rec.x - sm.knots[tb][0][0], ih[0], -1.0f);
+        s[q][1] = fmaf(rec.y - sm.knots[tb][1][0], ih[1], -1.0f);
+        s[q][2] = fmaf(rec.z - sm.knots[tb][2][0], ih[2], -1.0f);
+    }
+    float m0v[PPT][N0 - 1], m0d[PPT][N0 - 1], m1v[PPT][N1 - 1], m1d[PPT][N1 - 1], m2v[PPT][3], m2d[PPT][3];
+#pragma unroll
+    for (int q = 0; q < PPT; ++q) {
+        horner_mults<N0>(s[q][0], false, m0v[q]); horner_mults<N0>(s[q][0], true, m0d[q]);
+        horner_mults<N1>(s[q][1], false, m1v[q]); horner_mults<N1>(s[q][1], true, m1d[q]);
+        horner_mults<4>(s[q][2], false, m2v[q]);  horner_mults<4>(s[q][2], true, m2d[q]);
+    }
+    float acc[4][PPT][4];
+#pragma unroll
+    for (int k = 0; k < CPD; ++k) {
+        const ulonglong2* col = reinterpret_cast<const ulonglong2*>(sm.net[tb][k]);
+        f32x2 Qv[PPT][2], Q0[PPT][2], Q1[PPT][2];
+#pragma unroll
+        for (int a = N0 - 1; a >= 0; --a) {
+            ulonglong2 cv[N1];
+#pragma unroll
+            for (int b = 0; b < N1; ++b) cv[b] = col[a * N1 + b];
+#pragma unroll
+            for (int q = 0; q < PPT; ++q) {
+                f32x2 E0 = cv[N1 - 1].x, E1 = cv[N1 - 1].y, D0 = cv[N1 - 1].x, D1 = cv[N1 - 1].y;
+#pragma unroll
+                for (int b = N1 - 2; b >= 0; --b) {
+                    const f32x2 x = pack2(m1v[q][b], m1v[q][b]);
+                    f32x2 t0 = cv[b].x, t1 = cv[b].y;
+                    ffma2(t0, E0, x); ffma2(t1, E1, x);
+                    E0 = t0; E1 = t1;
+                    if (b >= 1) {
+                        const f32x2 y = pack2(m1d[q][b], m1d[q][b]);
+                        f32x2 u0 = cv[b].x, u1 = cv[b].y;
+                        ffma2(u0, D0, y); ffma2(u1, D1, y);
+                        D0 = u0; D1 = u1;
+                    }
+                }
+                if (a == N0 - 1) {
+                    Qv[q][0] = E0; Qv[q][1] = E1; Q0[q][0] = E0; Q0[q][1] = E1; Q1[q][0] = D0; Q1[q][1] = D1;
+                } else {
+                    const f32x2 x = pack2(m0v[q][a], m0v[q][a]);
+                    f32x2 t0 = E0, t1 = E1, u0 = D0, u1 = D1;
+                    ffma2(t0, Qv[q][0], x); ffma2(t1, Qv[q][1], x);
+                    ffma2(u0, Q1[q][0], x); ffma2(u1, Q1[q][1], x);
+                    Qv[q][0] = t0; Qv[q][1] = t1; Q1[q][0] = u0; Q1[q][1] = u1;
+                    if (a >= 1) {
+                        const f32x2 y = pack2(m0d[q][a], m0d[q][a]);
+                        f32x2 w0 = E0, w1 = E1;
+                        ffma2(w0, Q0[q][0], y); ffma2(w1, Q0[q][1], y);
+                        Q0[q][0] = w0; Q0[q][1] = w1;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < PPT; ++q) {
+            auto hv = [&](const f32x2 (&Q)[2]) {
+                float c0, c1, c2, c3;
+                unpack2(Q[0], c0, c1); unpack2(Q[1], c2, c3);
+                float r = fmaf(c3, m2v[q][2], c2);
+                r = fmaf(r, m2v[q][1], c1);
+                return fmaf(r, m2v[q][0], c0);
+            };
+            float c0, c1, c2, c3;
+            unpack2(Qv[q][0], c0, c1); unpack2(Qv[q][1], c2, c3);
+            float rd = fmaf(c3, m2d[q][2], c2);
+            rd = fmaf(rd, m2d[q][1], c1);
+            acc[0][q][k] = hv(Qv[q]);
+            acc[1][q][k] = hv(Q0[q]) * ih[0];
+            acc[2][q][k] = hv(Q1[q]) * ih[1];
+            acc[3][q][k] = rd * ih[2];
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int q = 0; q < PPT; ++q) {
+            if (valid[q]) {
+                float* o = ar.out[c] + (int64_t)idx[q] * CPD;
+#pragma unroll
+                for (int k = 0; k < CPD; ++k) o[k] = acc[c][q][k];
+            }
+        }
+}
+
 // Persistent, warp-autonomous (one warp per CTA, no CTA barrier): work items from an atomic cursor; while item i is
 // computed the records of items i+1, i+2 are in flight, and the points of the next sub-batch plus the knots / net of
 // item i+1 stream into the other half of the shared-memory buffers (cp.async).
 #ifndef THB_NET_MINB_P4
 #define THB_NET_MINB_P4 16  // four points per lane still fit 128 registers (106 used)
 #endif
-template <int N0, int N1, int N2, int PPT, int CPD, bool DER, bool MONO>
-__global__ void __launch_bounds__(kThreads, PPT >= 4 ? THB_NET_MINB_P4 : (DER ? THB_NET_MINB_DER : THB_NET_MINB)) k_net_eval(const __grid_constant__ thb_space_desc sp, const __grid_constant__ Args ar,
+template <int N0, int N1, int N2, int PPT, int CPD, bool DER, bool MONO, bool GRAD4 = false>
+__global__ void __launch_bounds__(kThreads, GRAD4 ? 12 : (PPT >= 4 ? (DER ? 12 : THB_NET_MINB_P4) : (DER ? THB_NET_MINB_DER : THB_NET_MINB))) k_net_eval(const __grid_constant__ thb_space_desc sp, const __grid_constant__ Args ar,
                                                                     const float* __restrict__ nets) {
     using SH = Shp<N0, N1, N2>;
     constexpr int SB = 32 * PPT;
-    __shared__ __align__(16) NetSmem<SH, DER> sm;
+    __shared__ __align__(16) NetSmem<SH, DER, MONO> sm;
     const int lane = threadIdx.x;
     const int nitems = ar.counters[0];
     int32_t* const cursor = ar.counters + 1;
@@ -776,7 +897,10 @@ __global__ void __launch_bounds__(kThreads, PPT >= 4 ? THB_NET_MINB_P4 : (DER ? 
                 prefetch_net<SH, DER, MONO>(sp, nets, nx, sm.knots[tb ^ 1], sm.net[tb ^ 1]);
             }
             cp_async_commit();
-            if constexpr (MONO) {
+            if constexpr (GRAD4) {
+                if (it.count - base <= 32) net_points_mono_grad4<SH, 1, CPD>(ar, it, base, sm, tb, pb);
+                else net_points_mono_grad4<SH, PPT, CPD>(ar, it, base, sm, tb, pb);
+            } else if constexpr (MONO) {
                 // four (or two) points per lane amortise the broadcast LDS.128 of the net: with two the shared-memory pipe
                 // (two wavefronts per broadcast LDS.128, one pipe per SM) is as busy as the FMA pipes
                 if (PPT >= 2 && it.count - base <= 32) net_points_mono<SH, 1, CPD, DER>(ar, it, base, sm, tb, pb);
@@ -1214,18 +1338,28 @@ int launch_nets(const thb_space_desc* sp, const NetArgs* na, int cpd, cudaStream
 
 template <int N0, int N1, int N2>
 int launch_net_eval(const thb_space_desc* sp, const Args* ar, const float* nets, int ppt, int cpd, int der, int mono, cudaStream_t st) {
-#define THB_NET_EVAL(PPT_, CPD_, DER_, MONO_)                                                 \
+#define THB_NET_EVAL(PPT_, CPD_, DER_, MONO_, ...)                                            \
     do {                                                                                      \
         static int grid_[THB_MAX_DEVICES] = {};                                               \
         int& grid = grid_[thb_device()];                                                      \
-        if (grid == 0) grid = persistent_grid(k_net_eval<N0, N1, N2, PPT_, CPD_, DER_, MONO_>, kThreads); \
-        k_net_eval<N0, N1, N2, PPT_, CPD_, DER_, MONO_><<<grid, kThreads, 0, st>>>(*sp, *ar, nets); \
+        if (grid == 0) grid = persistent_grid(k_net_eval<N0, N1, N2, PPT_, CPD_, DER_, MONO_, ##__VA_ARGS__>, kThreads); \
+        k_net_eval<N0, N1, N2, PPT_, CPD_, DER_, MONO_, ##__VA_ARGS__><<<grid, kThreads, 0, st>>>(*sp, *ar, nets); \
         THB_LAUNCHED();                                                                       \
         return THB_OK;                                                                        \
     } while (0)
+    if constexpr (N2 == 4 && N0 >= 2 && N1 >= 2) {
+        // value + the three first derivatives (channels 0, 1, 2, 4): one fused pass over the monomial net
+        if (mono && der && ar->nch == 4 && ar->channels[0] == 0 && ar->channels[1] == 1 && ar->channels[2] == 2 && ar->channels[3] == 4 &&
+            !getenv("THB_NET_NO_GRAD4")) {
+            if (cpd == 3) THB_NET_EVAL(2, 3, true, true, true);
+            if (cpd == 4) THB_NET_EVAL(2, 4, true, true, true);
+        }
+    }
     if (mono) {   // monomial nets: four or two points per lane (fewer for tails)
         if (cpd == 3 && !der && ppt == 4) THB_NET_EVAL(4, 3, false, true);
         if (cpd == 4 && !der && ppt == 4) THB_NET_EVAL(4, 4, false, true);
+        if (cpd == 3 && der && ppt == 4) THB_NET_EVAL(4, 3, true, true);
+        if (cpd == 4 && der && ppt == 4) THB_NET_EVAL(4, 4, true, true);
         if (cpd == 3 && !der) THB_NET_EVAL(2, 3, false, true);
         if (cpd == 3 && der) THB_NET_EVAL(2, 3, true, true);
         if (cpd == 4 && !der) THB_NET_EVAL(2, 4, false, true);

@@ -113,7 +113,8 @@ extern "C" int thb_eval_fused(const thb_space_desc* space, const thb_plan_desc* 
 
 extern "C" int64_t thb_net_workspace_floats(const thb_space_desc* space, int flags) {
     if (!space) return 0;
-    return (int64_t)space->nslots * ((flags & THB_NETS_DERIVATIVES) ? 8 : 4) * space->tile_stride;
+    // monomial nets serve every channel from one set of planes (see thb_b200.h)
+    return (int64_t)space->nslots * (((flags & THB_NETS_DERIVATIVES) && !(flags & THB_NETS_MONOMIAL)) ? 8 : 4) * space->tile_stride;
 }
 
 extern "C" int thb_cell_nets(const thb_space_desc* space, const thb_plan_desc* plan, const float* ctrl_pts, int cp_dim,
@@ -128,8 +129,8 @@ extern "C" int thb_cell_nets(const thb_space_desc* space, const thb_plan_desc* p
     NetArgs na = {};
     THB_REQUIRE(!(flags & THB_NETS_MONOMIAL) || space->poly, "thb_cell_nets: the monomial form needs the span polynomials (thb_space_desc::poly)");
     na.ctrl_pts = ctrl_pts; na.cell_count = plan ? plan->cell_count : nullptr; na.nets = nets;
-    na.planes = (flags & THB_NETS_DERIVATIVES) ? 8 : 4;
     na.mono = (flags & THB_NETS_MONOMIAL) ? 1 : 0;
+    na.planes = ((flags & THB_NETS_DERIVATIVES) && !na.mono) ? 8 : 4;
     return ops->nets(space, &na, cp_dim, (cudaStream_t)stream);
 }
 
@@ -147,7 +148,7 @@ extern "C" int thb_eval_nets(const thb_space_desc* space, const thb_plan_desc* p
     bool der;
     if ((rc = fill_channels(ar, channels, nchannels, space->ndim, &der, "thb_eval_nets"))) return rc;
     const int with_derivatives = (flags & THB_NETS_DERIVATIVES) ? 1 : 0, mono = (flags & THB_NETS_MONOMIAL) ? 1 : 0;
-    THB_REQUIRE(!der || with_derivatives, "thb_eval_nets: derivative channels need nets built with THB_NETS_DERIVATIVES");
+    THB_REQUIRE(!der || with_derivatives || mono, "thb_eval_nets: derivative channels need nets built with THB_NETS_DERIVATIVES (or monomial nets)");
     THB_REQUIRE(!mono || space->poly, "thb_eval_nets: the monomial form needs the span polynomials (thb_space_desc::poly)");
     for (int c = 0; c < nchannels; ++c) {
         THB_REQUIRE(out_host[c], "thb_eval_nets: null output");
@@ -157,7 +158,7 @@ extern "C" int thb_eval_nets(const thb_space_desc* space, const thb_plan_desc* p
     ar.rows_sorted = plan->rows_in_plan_order ? 1 : 0;
     cudaStream_t st = (cudaStream_t)stream;
     THB_CUDA(cudaMemsetAsync(plan->counters + 1, 0, sizeof(int32_t), st));
-    return ops->net_eval(space, &ar, nets, env_int("THB_NET_PPT", mono ? 4 : 2), cp_dim, with_derivatives, mono, st);
+    return ops->net_eval(space, &ar, nets, env_int("THB_NET_PPT", mono ? 4 : 2), cp_dim, mono ? (der ? 1 : 0) : with_derivatives, mono, st);
 }
 
 static int fused_backward_impl(const thb_space_desc* space, const thb_plan_desc* plan, const float* params, const float* grad_out,

@@ -206,7 +206,7 @@ def net_workspace(P, with_derivatives=False):
     """Device buffer for the local control nets of P ([nslots][4 or 8][TS] f32), allocated once per hierarchy."""
     key = "_net_ws8" if with_derivatives else "_net_ws4"
     ws = getattr(P, key, None)
-    n = lib.thb_net_workspace_floats(C.byref(P.desc()), NETS_DERIVATIVES if with_derivatives else 0)
+    n = lib.thb_net_workspace_floats(C.byref(P.desc()), NETS_DERIVATIVES if with_derivatives else 0)   # control-point form: the larger
     if ws is None or ws.numel() != n:
         ws = torch.empty(n, dtype=torch.float32, device=P.device)
         setattr(P, key, ws)
