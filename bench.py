@@ -334,6 +334,36 @@ def strong_block(P, cp, rank, world, device, cell_cost):
             "what": "fixed 256^3 grid, x-plane slabs balanced by points + cell_cost per touched cell; plan + nets + evaluation per step"}
 
 
+def grid_block(P, cp, rank, world, device):
+    """The tensor-product-grid path (thb_eval_grid): same 256^3 grid per GPU as the headline, but evaluated as a GRID -- no
+    plan (the points of a cell are an index box; engine.GridPlan lists the boxes on the host once per grid) and sum
+    factorisation at the cell level.  Step = local control nets (monomial) + grid evaluation.  Reported next to the
+    headline, which treats the same points as an arbitrary batch."""
+    import time as _t
+
+    import torch
+
+    from thb_diff_b200 import engine
+
+    ax = [np.linspace(1e-5, 1.0, GRID, endpoint=False).astype(np.float32), np.linspace(1e-5, 1.0, GRID * world, endpoint=False).astype(np.float32)[rank::world],
+          np.linspace(1e-5, 1.0, GRID, endpoint=False).astype(np.float32)]
+    t0 = _t.perf_counter()
+    gp = engine.GridPlan(P, ax)
+    t_plan = _t.perf_counter() - t0
+    out = torch.empty((gp.n_points, 3), dtype=torch.float32, device=device)
+
+    def step():
+        engine.eval_grid(P, gp, cp, out=out)
+
+    ms = timed_max_over_ranks(step, 200, 20, world, device)
+    nets = engine.cell_nets(P, cp, monomial=True)
+    ms_eval = timed_max_over_ranks(lambda: engine.eval_grid(P, gp, cp, nets=nets, out=out), 200, 10, world, device)
+    return {"points_per_s": gp.n_points * world / (ms * 1e-3), "ms_per_step": ms, "grid_kernel_ms": ms_eval, "boxes": gp.nitems,
+            "grid_plan_host_ms_once": t_plan * 1e3,
+            "hbm_frac_of_output_write": (gp.n_points * 12 / (ms_eval * 1e-3) / 1e9) / 6538.9,
+            "what": "nets (monomial, every cell) + thb_eval_grid on the 256^3 grid of this rank; GridPlan built once per grid on the host"}
+
+
 def c5_block(rank, world, device, cell_cost):
     """BASELINE config 5: 5 active levels, value + the three first-derivative vectors on the 512^3 grid cut into slabs."""
     import torch
@@ -837,7 +867,8 @@ def main():
         # every N: strong scaling of the fixed grid, config 4 (fit with the gradient all-reduce), config 5 (5 levels, derivatives)
         blocks = {}
         torch.cuda.empty_cache()
-        for name, fn in (("strong", lambda: strong_block(P, cp, rank, world, device, args.cell_cost)),
+        for name, fn in (("grid", lambda: grid_block(P, cp, rank, world, device)),
+                         ("strong", lambda: strong_block(P, cp, rank, world, device, args.cell_cost)),
                          ("fit_c4", lambda: fit_block(sp, P, rank, world, device, args.cell_cost)),
                          ("c5", lambda: c5_block(rank, world, device, args.cell_cost))):
             try:
@@ -850,6 +881,10 @@ def main():
             torch.cuda.empty_cache()
         line["blocks"] = blocks
         c = line["config"]
+        b = blocks.get("grid", {})
+        if "points_per_s" in b:
+            c["grid_points_per_s"], c["grid_ms_per_step"] = b["points_per_s"], b["ms_per_step"]
+            c["grid_what"] = "same points evaluated as a tensor-product grid (thb_eval_grid): no plan, cell-level sum factorisation"
         b = blocks.get("strong", {})
         if "points_per_s" in b:
             c["strong_points_per_s"], c["strong_ms_per_step"] = b["points_per_s"], b["ms_per_step"]

@@ -224,6 +224,19 @@ THB_API int thb_cell_nets(const thb_space_desc* space, const thb_plan_desc* plan
                   int flags, float* nets, void* stream);
 THB_API int thb_eval_nets(const thb_space_desc* space, const thb_plan_desc* plan, const float* nets, int flags,
                   int cp_dim, const int32_t* channels, int nchannels, float* const* out_host, void* stream);
+/* Evaluation on a TENSOR-PRODUCT GRID of parameters u0[i0] x u1[i1] (x u2[i2]) -- the point sets the reference generates with
+ * generate_parametric_coordinates (THB/bspline_funcs.py:20-35) and every BASELINE configuration uses.  No plan is built: the
+ * points of an active cell are one index range per axis, so the host lists work items once per grid
+ * (thb_diff_b200.engine.GridPlan): items [nitems][8] i32 = slot, i0, n0, i1, n1, i2, n2, level (index box of at most 16 values per
+ * axis inside ONE active cell; n2 = 1 in 2-D), item_cells [nitems][4] i32 = the cell's 1-D cell indices.  nets: MONOMIAL nets
+ * of thb_cell_nets (THB_NETS_MONOMIAL, four planes).  The geometry of point (i0, i1, i2) is written to row
+ * i0 * row_stride[0] + i1 * row_stride[1] + i2 * row_stride[2] of out [*, cp_dim]; rows of points outside the domain are not
+ * written.  cursor: one device i32 of scratch.  Cost per point: (p0) FMAs per component plus O(n1 n2 + n2) per box (sum
+ * factorisation at the cell level) -- against (p+1)^d-many per point on the general path. */
+THB_API int thb_eval_grid(const thb_space_desc* space, const float* nets, const int32_t* items, const int32_t* item_cells, int nitems,
+                  const float* axis0, const float* axis1, const float* axis2, const int64_t* row_stride, int cp_dim, float* out,
+                  int32_t* cursor, void* stream);
+
 /* grad_ctrl_pts[nctrl, cp_dim] (zeroed by the callee) = A^T grad_out, A = value-channel basis matrix.
  * Replaces THBEval.backward (THB/torch_funcs.py:35-47) for the fused path.  workspace: thb_net_workspace_floats(space, 0)
  * floats (overwritten) -> the gradient goes through per-cell net gradients (one reduction per work item, one transposed

@@ -77,6 +77,7 @@ def _load():
         "thb_mse_grad": (i32, [vp, vp, i64, C.c_float, vp, vp, vp, vp]),
         "thb_adam_rows": (i32, [vp, vp, vp, vp, vp, i64, i32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, i32, vp, vp]),
         "thb_adam_rows_peer": (i32, [vp, vp, vp, vp, i32, i32, vp, vp, i64, i32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, vp, vp, vp]),
+        "thb_eval_grid": (i32, [C.POINTER(SpaceDesc), vp, vp, vp, i32, vp, vp, vp, C.POINTER(C.c_int64), i32, vp, vp, vp]),
         "thb_tensor_product": (i32, [vp, vp, vp, i64, i32, i32, i32, vp, vp]),
         "thb_fma_peak": (i32, [i32, i32, vp, C.POINTER(C.c_double), vp]),
     }

@@ -534,6 +534,107 @@ def tensor_product(vectors):
     return out
 
 
+class GridPlan:
+    """Work items of a TENSOR-PRODUCT GRID of parameters (axes[k]: the non-decreasing values of parameter k) for
+    thb_eval_grid: per active cell the index box of the grid points it holds, cut into boxes of at most 16 values per axis.
+    Built on the host with numpy from the hierarchy's knots, once per grid -- there is no per-point sort.
+
+    order: row of point (i0, i1[, i2]) in the output.  "xy" (default) is the reference's generate_parametric_coordinates
+    order (numpy meshgrid 'xy': i1 slowest, then i0, i2 fastest; 2-D: i1 slowest); "ij" is C order."""
+
+    BOX = 16
+
+    def __init__(self, P, axes, order="xy"):
+        import numpy as np
+
+        d = P.ndim
+        if len(axes) != d:
+            raise RuntimeError(f"GridPlan needs {d} axes")
+        ax = [np.ascontiguousarray((a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)), dtype=np.float32).reshape(-1) for a in axes]
+        if any(len(a) == 0 or np.any(np.diff(a) < 0) for a in ax):
+            raise RuntimeError("GridPlan: every axis must be a non-empty, non-decreasing sequence")
+        n = [len(a) for a in ax]
+        info = P.cellinfo_host
+        knots = P.knots.detach().cpu().numpy()
+        lo = np.zeros((P.nslots, 3), dtype=np.int64)
+        cnt = np.ones((P.nslots, 3), dtype=np.int64)
+        inside = 1
+        for k in range(d):
+            p = P.degrees[k]
+            for l in range(P.nlevels):
+                U = knots[P.knot_off[l, k]: P.knot_off[l, k] + P.knot_len[l, k]]
+                nc = int(P.sh_cells[l][k])
+                B = U[p: p + nc + 1]
+                first = np.searchsorted(ax[k], B, side="left").astype(np.int64)    # first grid value >= breakpoint
+                first[-1] = np.searchsorted(ax[k], B[-1], side="right")             # u == U[-1] belongs to the last cell
+                sel = info[:, 0] == l
+                c = info[sel, 1 + k]
+                lo[sel, k] = first[c]
+                cnt[sel, k] = first[c + 1] - first[c]
+                if l == 0:
+                    inside *= int(first[-1] - first[0])
+        npts = cnt.prod(axis=1)
+        if int(npts.sum()) != inside:
+            raise RuntimeError("GridPlan: the active cells do not partition the domain (overlapping active cells of different "
+                               "levels); use the general path (engine.Plan)")
+        slots = np.nonzero(npts > 0)[0]
+        m = (cnt[slots] + self.BOX - 1) // self.BOX                                # boxes per axis
+        per = m.prod(axis=1)
+        rep = np.repeat(np.arange(len(slots)), per)
+        t = np.arange(int(per.sum())) - np.repeat(np.cumsum(per) - per, per)
+        mm = m[rep]
+        b2 = t % mm[:, 2]
+        b1 = (t // mm[:, 2]) % mm[:, 1]
+        b0 = t // (mm[:, 2] * mm[:, 1])
+        bidx = np.stack([b0, b1, b2], axis=1)
+        start = lo[slots][rep] + bidx * self.BOX
+        size = np.minimum(self.BOX, cnt[slots][rep] - bidx * self.BOX)
+        items = np.zeros((len(rep), 8), dtype=np.int32)
+        items[:, 0] = slots[rep]
+        items[:, 1], items[:, 2], items[:, 3], items[:, 4], items[:, 5], items[:, 6] = start[:, 0], size[:, 0], start[:, 1], size[:, 1], start[:, 2], size[:, 2]
+        items[:, 7] = info[slots[rep], 0]
+        cells = np.zeros((len(rep), 4), dtype=np.int32)
+        cells[:, :d] = info[slots[rep], 1:1 + d]
+        big_first = np.argsort(-(size.prod(axis=1)), kind="stable")               # dynamic scheduler: large boxes first
+        self.P, self.n, self.order = P, n, order
+        self.n_points, self.n_inside, self.nitems = int(np.prod(n)), inside, len(rep)
+        self.items = torch.from_numpy(items[big_first]).to(P.device)
+        self.cells = torch.from_numpy(cells[big_first]).to(P.device)
+        self.axes = [torch.from_numpy(a).to(P.device) for a in ax]
+        if order == "xy":
+            st = [n[2], n[0] * n[2], 1] if d == 3 else [1, n[0], 0]
+        elif order == "ij":
+            st = [n[1] * n[2], n[2], 1] if d == 3 else [n[1], 1, 0]
+        else:
+            raise RuntimeError("order must be 'xy' or 'ij'")
+        self.strides = (C.c_int64 * 3)(*st)
+        self.cursor = torch.zeros(1, dtype=torch.int32, device=P.device)
+        self.version = P.version
+
+
+def eval_grid(P, gplan, ctrl_pts=None, nets=None, out=None):
+    """Geometry on the tensor-product grid of `gplan` (thb_eval_grid): [prod(n), cp_dim] in the plan's row order.  Pass
+    ctrl_pts (the monomial nets are built here, for every cell) or prebuilt monomial nets."""
+    if gplan.version != P.version:
+        raise RuntimeError("the hierarchy changed since the GridPlan was built")
+    if nets is None:
+        nets = cell_nets(P, ctrl_pts, monomial=True)
+    if not getattr(nets, "_thb_flags", NETS_MONOMIAL) & NETS_MONOMIAL:
+        raise RuntimeError("eval_grid needs monomial nets (cell_nets(..., monomial=True))")
+    cpd = ctrl_pts.shape[1] if ctrl_pts is not None else 3
+    if out is None:
+        alloc = torch.empty if gplan.n_inside == gplan.n_points else torch.zeros
+        out = alloc((gplan.n_points, cpd), dtype=torch.float32, device=P.device)
+    require_cuda(out, "out", torch.float32)
+    if out.shape != (gplan.n_points, cpd):
+        raise RuntimeError(f"out must be [{gplan.n_points}, {cpd}]")
+    with _on(P.device):
+        check(lib.thb_eval_grid(C.byref(P.desc()), ptr(nets), ptr(gplan.items), ptr(gplan.cells), gplan.nitems, ptr(gplan.axes[0]),
+                                ptr(gplan.axes[1]), ptr(gplan.axes[2]) if P.ndim == 3 else None, gplan.strides, cpd, ptr(out),
+                                ptr(gplan.cursor), stream_ptr(P.device)), "thb_eval_grid")
+    return out
+
+
 def fma_peak(variant, iters=4096, repeats=5):
     """Measured FP32 FMA throughput (TFLOP/s) of the running GPU -- the FP32 roofline denominator."""
     sink = torch.zeros(4, dtype=torch.float32, device="cuda")
