@@ -43,6 +43,8 @@ def _span_poly_tables(kv, degrees, nlevels):
     Cox-de Boor); the centred, scaled variable keeps the coefficients O(1): float32 Horner stays ~1e-6 of max|geometry|
     (measured 1.6e-6 worst over random nets)."""
     d = len(degrees)
+    if any(int(p) > 3 for p in degrees):
+        return None, None   # rows hold 4 x 4 coefficients: degrees above three have no monomial tables (and no fused kernels)
     rows, off = [], np.zeros((nlevels, 3), dtype=np.int64)
     pos = 0
     for l in range(nlevels):
@@ -297,7 +299,7 @@ class PackedHierarchy:
         self.cellinfo_host = info
         self.knots = torch.from_numpy(knots).to(dev)
         poly, self.poly_off = _span_poly_tables(kv, p, L)
-        self.poly = torch.from_numpy(poly).to(dev)
+        self.poly = torch.from_numpy(poly).to(dev) if poly is not None else None
         self.cell_slot = torch.from_numpy(cell_slot).to(dev)
         self.finest_slot = torch.from_numpy(finest_map.reshape(-1)).to(dev) if finest_map is not None else None
         self.span_lut = torch.from_numpy(self._lut[0]).to(dev) if self._lut is not None else None
@@ -581,10 +583,11 @@ def _desc(self):
         d.sep_vec, d.sep_jm = self.sep_vec.data_ptr(), self.sep_jm.data_ptr()
         d.full_tiles, d.full_jm = self.full_tiles.data_ptr(), self.full_jm.data_ptr()
     d.tiled_ref = self.tiled_ref.data_ptr() if getattr(self, "tiled_ref", None) is not None and getattr(self, "sep_vec", None) is not None else None
-    d.poly = self.poly.data_ptr()
-    for l in range(self.nlevels):
-        for k in range(self.ndim):
-            d.poly_off[l][k] = int(self.poly_off[l, k])
+    d.poly = self.poly.data_ptr() if self.poly is not None else None
+    if self.poly is not None:
+        for l in range(self.nlevels):
+            for k in range(self.ndim):
+                d.poly_off[l][k] = int(self.poly_off[l, k])
     d.span_lut = self.span_lut.data_ptr() if self.span_lut is not None else None
     d.lut_exact = 1 if (self.span_lut is not None and getattr(self, "lut_exact", False)) else 0
     if self.span_lut is not None:
