@@ -7,7 +7,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from thb_diff_b200 import configs, core, engine, bspline_funcs as B
 from thb_diff_b200.packed import PackedHierarchy
 
-what = set(sys.argv[1:]) or {"plan", "nets", "eval", "bwd", "basis", "csr32", "csr64"}
+what = set(sys.argv[1:]) or {"plan", "nets", "eval", "bwd", "basis", "csr32", "csr64", "grid", "fit"}
 under_ncu = "NV_NSIGHT_INJECTION_PORT_BASE" in os.environ or os.environ.get("THB_PROFILING") == "1"
 
 def t(fn, it=10, warm=3):
@@ -45,6 +45,24 @@ if what & {"basis", "csr32", "csr64"}:
                 Jm = supp.Jm(dt); cs = supp._cumsum.to(dt)
                 calls[name + "_fwd"] = (lambda Jm=Jm, cs=cs: engine.eval_forward(cp, Jm, PHI, cs))
                 calls[name + "_bwd"] = (lambda Jm=Jm, cs=cs: engine.eval_backward(g, cp, Jm, PHI, cs))
+if "grid" in what:
+    import numpy as np
+    ax = [np.linspace(1e-5, 1.0, 256, endpoint=False).astype(np.float32)] * 3
+    gp = engine.GridPlan(P, ax)
+    gnets = engine.cell_nets(P, cp, monomial=True).clone()
+    gnets._thb_flags = engine.NETS_MONOMIAL
+    gout = torch.empty((256 ** 3, 3), device="cuda")
+    calls["grid"] = lambda: engine.eval_grid(P, gp, cp, nets=gnets, out=gout)
+if "fit" in what:
+    from thb_diff_b200.distributed import FitEngine
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    fp = torch.rand((10_000_000, 3), device="cuda", generator=gen)
+    ft = fp.clone()
+    fx = torch.from_numpy(configs.greville_ctrl_pts(sp, bump=0.0)).cuda()
+    feng = FitEngine(P, fp, ft, fp.shape[0])
+    calls["fit_step"] = lambda: feng.step(fx)
+    feng_d = FitEngine(P, fp, ft, fp.shape[0], deterministic=True)
+    calls["fit_step_ordered"] = lambda: feng_d.step(fx)
 res = {}
 if not under_ncu:
     for k, fn in calls.items(): res[k] = t(fn)
