@@ -326,10 +326,22 @@ def strong_block(P, cp, rank, world, device, cell_cost):
         dist.all_gather(all_ms, mine)
     else:
         all_ms = [mine]
+    # where the step goes on this rank (eager launches, CUDA events): the parts that do not shrink with the slab explain
+    # the distance from linear scaling
+    ph = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(20)]
+    for e in ph:
+        e[0].record(); plan.build(); e[1].record()
+        nets = engine.cell_nets(P, cp, plan=plan); e[2].record()
+        engine.eval_nets(P, plan, nets, 3, out=out, with_derivatives=False); e[3].record()
+    torch.cuda.synchronize()
+    phases = torch.tensor([sum(e[k].elapsed_time(e[k + 1]) for e in ph) / len(ph) for k in range(3)], device=device)
+    if world > 1:
+        dist.all_reduce(phases, op=dist.ReduceOp.MAX)
     # Greville control points reproduce the parameters: the slab's geometry must equal its own points
     err = float((out[0][:, :2] - pts[:, :2]).abs().max())
     return {"points_per_s": GRID ** 3 / (ms * 1e-3), "ms_per_step": ms, "planes": [bnd[r + 1] - bnd[r] for r in range(world)],
             "rank_ms": [float(x) for x in all_ms], "cuda_graph": is_graph, "greville_max_abs_err_xy": err,
+            "eager_phase_ms_max_over_ranks": {"plan": float(phases[0]), "nets": float(phases[1]), "eval": float(phases[2])},
             "cells_with_points": int((plan.cell_count[: P.nslots] > 0).sum()),
             "what": "fixed 256^3 grid, x-plane slabs balanced by points + cell_cost per touched cell; plan + nets + evaluation per step"}
 

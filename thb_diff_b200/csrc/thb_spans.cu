@@ -549,16 +549,18 @@ __global__ void __launch_bounds__(256) k_plan_items(const __grid_constant__ thb_
     const int sh = (ppi & (ppi - 1)) == 0 ? 31 - __clz(ppi) : -1;
     int c = 0, b = 0, it0 = 0, m = 0;
     if (s < nslots) {
+        c = count[s]; b = start[s]; it0 = item_start_then_cursor[s];
+        item_start_then_cursor[s] = b;  // from here on the scatter cursor of the cell: next free place
+    }
+    if (c > 0) {   // cells without points (most cells, on a rank that holds a slab of the domain) read no descriptor
         const int4* ci = reinterpret_cast<const int4*>(sp.cellinfo + (int64_t)s * THB_INFO_W);
         const int4 a = __ldg(ci), e = __ldg(ci + 1), f = __ldg(ci + 2);  // level c0 c1 c2 | supp_off S tile_off n_direct | sep_off n_sep full_off 0
         const unsigned long long dm = __ldg(sp.dmask + s);
-        c = count[s]; b = start[s]; it0 = item_start_then_cursor[s];
         m = sh >= 0 ? (c + ppi - 1) >> sh : (c + ppi - 1) / ppi;
         s_rec[wid][lane][0] = make_int4(s, b, min(ppi, c), a.x);
         s_rec[wid][lane][1] = make_int4(a.y, a.z, a.w, e.x);
         s_rec[wid][lane][2] = make_int4(e.y, e.z, e.w, f.y);
         s_rec[wid][lane][3] = make_int4((int)(unsigned)(dm & 0xffffffffull), (int)(unsigned)(dm >> 32), f.x, f.z);
-        item_start_then_cursor[s] = b;  // from here on the scatter cursor of the cell: next free place
     }
     __syncwarp();
     const int part = lane & 3, grp = lane >> 2;

@@ -183,6 +183,8 @@ static int fused_backward_impl(const thb_space_desc* space, const thb_plan_desc*
     THB_REQUIRE(workspace || !row_map, "%s: compact gradient rows need the workspace (local nets) path", who);
     if (workspace) {  // through the per-cell net gradients (thb_net_impl.cuh); workspace: thb_net_workspace_floats(space, 0)
         THB_REQUIRE(plan->cell_count, "%s: plan without cell_count", who);
+        // (a self-cleaning workspace -- k_cell_unfold zeroing the cells it consumes instead of this memset -- was measured:
+        // the fused backward went from 0.55 to 0.81 ms on config 3)
         THB_CUDA(cudaMemsetAsync(workspace, 0, sizeof(float) * (size_t)thb_net_workspace_floats(space, 0), st));
         NetArgs na = {};
         na.cell_count = plan->cell_count; na.nets = workspace; na.planes = 4; na.row_map = row_map;

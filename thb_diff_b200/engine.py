@@ -363,7 +363,7 @@ def _gnet_workspace(P):
     ws = getattr(P, "_gnet_ws", None)
     n = lib.thb_net_workspace_floats(C.byref(P.desc()), 0)   # net GRADIENTS: always the control-point form, four planes
     if ws is None or ws.numel() != n:
-        ws = P._gnet_ws = torch.empty(n, dtype=torch.float32, device=P.device)
+        ws = P._gnet_ws = torch.zeros(n, dtype=torch.float32, device=P.device)   # zero before the first call; self-cleaning after
     return ws
 
 
