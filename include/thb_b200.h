@@ -219,6 +219,8 @@ THB_API int thb_eval_fused(const thb_space_desc* space, const thb_plan_desc* pla
  * of compute_refinement_operators (THB/core.py:43-114) on the evaluation side. */
 #define THB_NETS_DERIVATIVES 1
 #define THB_NETS_MONOMIAL 2
+#define THB_NETS_CTAS(k) (((k) & 0xff) << 8) /* thb_cell_nets only: at most k resident CTAs per SM, so that a kernel on
+                                                another stream (the plan of the batch) finds room beside it */
 THB_API int64_t thb_net_workspace_floats(const thb_space_desc* space, int flags);
 THB_API int thb_cell_nets(const thb_space_desc* space, const thb_plan_desc* plan, const float* ctrl_pts, int cp_dim,
                   int flags, float* nets, void* stream);

@@ -39,6 +39,7 @@ struct NetArgs {
     const int32_t* row_map;     // k_cell_unfold: flat function id -> row of the (compact) gradient buffer; nullptr = identity
     int32_t mono;               // k_cell_nets: 1 = store the nets in MONOMIAL form (see net_to_monomial), 0 = control points
     float* contrib;             // k_cell_unfold, ordered mode: [nsupp][cp_dim] one slot per (cell, support), plain stores
+    int32_t ctas_per_sm;        // k_cell_nets: > 0 caps the resident CTAs per SM (room for a kernel on another stream)
 };
 
 template <int CPD>
@@ -1323,7 +1324,9 @@ int launch_nets(const thb_space_desc* sp, const NetArgs* na, int cpd, cudaStream
         static int full_[THB_MAX_DEVICES] = {}; /* one resident wave: no partial second wave */ \
         int& full = full_[thb_device()];                                                      \
         if (full == 0) full = persistent_grid(k_cell_nets<N0, N1, N2, CPD_, REL_>, 32 * kNetWarps); \
-        const int grid = min((sp->nslots + kNetWarps - 1) / kNetWarps, full);                  \
+        int cap = full;                                                                       \
+        if (na->ctas_per_sm > 0) cap = min(full, thb_num_sms() * na->ctas_per_sm);             \
+        const int grid = min((sp->nslots + kNetWarps - 1) / kNetWarps, cap);                   \
         k_cell_nets<N0, N1, N2, CPD_, REL_><<<grid, 32 * kNetWarps, 0, st>>>(*sp, *na);        \
         THB_LAUNCHED();                                                                       \
         return THB_OK;                                                                        \

@@ -131,6 +131,7 @@ extern "C" int thb_cell_nets(const thb_space_desc* space, const thb_plan_desc* p
     na.ctrl_pts = ctrl_pts; na.cell_count = plan ? plan->cell_count : nullptr; na.nets = nets;
     na.mono = (flags & THB_NETS_MONOMIAL) ? 1 : 0;
     na.planes = ((flags & THB_NETS_DERIVATIVES) && !na.mono) ? 8 : 4;
+    na.ctas_per_sm = (flags >> 8) & 0xff;   // THB_NETS_CTAS(k): leave room for a concurrent kernel
     return ops->nets(space, &na, cp_dim, (cudaStream_t)stream);
 }
 

@@ -213,7 +213,7 @@ def net_workspace(P, with_derivatives=False):
     return ws
 
 
-def cell_nets(P, ctrl_pts, with_derivatives=False, plan=None, out=None, monomial=None):
+def cell_nets(P, ctrl_pts, with_derivatives=False, plan=None, out=None, monomial=None, ctas_per_sm=0):
     """Local control nets W of the active cells (thb_cell_nets): every cell, or only those holding points of `plan`.
     They stay valid for as long as ctrl_pts (and the hierarchy) do not change.  monomial (default: yes when available):
     the nets are stored as the coefficients of the cell's polynomial in cell-local coordinates, evaluated by Horner."""
@@ -228,7 +228,7 @@ def cell_nets(P, ctrl_pts, with_derivatives=False, plan=None, out=None, monomial
         plan.refresh()
     with _on(P.device):
         check(lib.thb_cell_nets(C.byref(P.desc()), C.byref(plan.desc) if plan is not None else None, ptr(ctrl_pts), ctrl_pts.shape[1],
-                                flags, ptr(nets), stream_ptr(P.device)), "thb_cell_nets")
+                                flags | ((int(ctas_per_sm) & 0xff) << 8), ptr(nets), stream_ptr(P.device)), "thb_cell_nets")
     nets._thb_flags = flags
     return nets
 
@@ -247,7 +247,9 @@ def plan_and_nets(P, plan, ctrl_pts, with_derivatives=False, overlap=True):
         side = P._side_stream = torch.cuda.Stream(device=P.device)
     side.wait_stream(cur)
     with torch.cuda.stream(side):
-        nets = cell_nets(P, ctrl_pts, with_derivatives)
+        # (capping the resident CTAs of the nets kernel -- THB_NETS_CTAS -- so that the plan kernels find registers beside
+        # it was measured on config 3: 0 = uncapped 0.467 ms per pass, 3: 0.461, 4-6: 0.468, 2: 0.559)
+        nets = cell_nets(P, ctrl_pts, with_derivatives, ctas_per_sm=int(_os.environ.get("THB_OVERLAP_NETS_CTAS", "0")))
     plan.build()
     cur.wait_stream(side)
     return nets
