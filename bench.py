@@ -775,6 +775,7 @@ def main():
         "nets_flops": f_nets,
         "flops_executed": f_exec, "flops_dense_model_8d": f_dense, "algorithmic_bytes": alg_bytes,
         "frac_vs_dense_model_8d": (f_dense / (fp32_peak * 1e12)) / (kern_ms * 1e-3),
+        "frac_fp32": t_fp32 / (kern_ms * 1e-3), "frac_hbm": t_hbm / (kern_ms * 1e-3),
         "peak_source": "FP32: thb_fma_peak micro-kernel measured in this run (MEASURED_PEAKS.json has no FP32 entry); "
                        f"HBM: {'MEASURED_PEAKS.json' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s'}",
     }
@@ -784,6 +785,12 @@ def main():
     n_items = int(plan.counters[0].item())
     n_cells_used = int((plan.cell_count[: P.nslots] > 0).sum())
     step_bytes = n * ((4 * P.ndim + 4) + (4 * P.ndim + 4 + 16) + (16 + 4 * 3)) + (n_cells_used + n_items) * 4 * P.TS * 4
+    if args.formulation == "local_net" and mono:
+        # the same kernel time against the FLOPs of the control-point form it replaces (Cox-de Boor + sum-factorised
+        # contraction with tp(u), 612 per point for cubic 3-D: round 1's kernel): what the monomial form saves is work, not speed
+        f_cp = flop_model_local_net(P, plan, 3, n_in, mono=False)[0]
+        roofline["frac_fp32_vs_control_point_form_flops"] = (f_cp / (fp32_peak * 1e12)) / (kern_ms * 1e-3)
+        roofline["note"] = "monomial nets: FP32 and HBM roofs of this kernel coincide (0.088 ms each on C3); frac = the slower roof / measured time"
     roofline["step_flops"] = f_exec + f_nets
     roofline["step_bytes"] = step_bytes
     roofline["step_frac"] = ((f_exec + f_nets) / (fp32_peak * 1e12)) / (ms_per_pass * 1e-3)
