@@ -112,7 +112,14 @@ typedef struct thb_plan_desc {
                                     that keep their per-point data in plan order (a fit loop permutes its targets once);
                                     honoured by thb_eval_nets / thb_eval_fused (local nets) / thb_eval_fused_backward with
                                     a workspace, an error elsewhere */
-    int32_t pad_;
+    int32_t light;               /* 0: thb_plan_build writes the 16-byte records (sorted_params).
+                                    1: LIGHT plan -- thb_plan_build writes only the permutation (scratch[j] = caller index of the
+                                       point in place j of the cell order, 4 bytes per point instead of 16 written and 12 read);
+                                       thb_eval_nets gathers the parameters through it (needs `params` below); every other
+                                       consumer of a plan needs thb_plan_records first.
+                                    2: light plan whose records have been materialised by thb_plan_records (set by the caller) */
+    const float* params;         /* the batch the plan was built from (same pointer as passed to thb_plan_build); read by
+                                    thb_eval_nets when light == 1 */
 } thb_plan_desc;
 
 THB_API int thb_version(void);
@@ -179,6 +186,10 @@ THB_API int thb_basis_dense(const float* params, int64_t npoints, int ndim, cons
                     const int32_t* knot_off, const int32_t* knot_len, const int32_t* nfns_finest,
                     const float* coeffs, const void* jm, int jm_is_i64, const int64_t* cumsum, int channel,
                     float* phi_out, void* stream);
+
+/* Materialises the 16-byte records of a LIGHT plan (light == 1) from its permutation: sorted_params[j] = (params[perm[j]],
+ * perm[j]).  The caller then sets plan->light = 2. */
+THB_API int thb_plan_records(const thb_space_desc* space, const float* params, const thb_plan_desc* plan, void* stream);
 
 /* ---- fused basis + evaluation (PHI never leaves the SM) ----------------------------------------------------
  * out_host[c] is a device buffer [N, cp_dim] per channel; rows of points outside the domain (slot -1) are NOT written,

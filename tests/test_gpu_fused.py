@@ -299,3 +299,34 @@ def test_monomial_nets_and_control_point_nets_against_the_oracle(name, cp_dim):
         r = ht.eval(g["params"], cp, mode=1 << k)["out"]
         for mono in (False, True):
             assert rel_err(outs[mono][1 + k], r, scale=max(np.abs(r).max(), 1.0)).max() <= 2 * TOL, (k, mono)
+
+
+@pytest.mark.parametrize("name", ["block3d", "graded2d"])
+def test_light_plan_and_record_plan_give_the_same_results(name):
+    """Plan(light=True): only the permutation is built and k_net_eval gathers the parameters through it; Plan(light=False):
+    16-byte records.  Same geometry bit for bit (the arithmetic per point is identical), work items of many sizes."""
+    from thb_diff_b200 import engine
+    from thb_diff_b200.packed import PackedHierarchy
+
+    g = load_golden(name)
+    h = product_space_from_golden(g)
+    P = PackedHierarchy.from_space(h, device="cuda")
+    rng = np.random.default_rng(4)
+    prm = np.concatenate([g["params"], rng.random((70_001, h.ndim)).astype(np.float32), np.full((3, h.ndim), 2.0, np.float32)])
+    cp = torch.from_numpy(rng.standard_normal((P.nCP, 3)).astype(np.float32)).cuda()
+    a_plan, b_plan = engine.Plan(P, prm, light=True), engine.Plan(P, prm, light=False)
+    assert a_plan.light and not b_plan.light
+    chans = [engine.CH_VALUE] + engine.grad_channels(h.ndim)
+    for ch in ([engine.CH_VALUE], chans):
+        a = engine.eval_fused(P, a_plan, cp, ch)
+        assert a_plan.desc.light == 1            # still light: no records were needed
+        b = engine.eval_fused(P, b_plan, cp, ch)
+        for x, y in zip(a, b):
+            assert torch.equal(x, y)
+    # consumers that need records materialise them
+    go = torch.randn((len(prm), 3), device="cuda")
+    ga = engine.eval_fused_backward(P, a_plan, go)
+    assert a_plan.desc.light == 2
+    gb = engine.eval_fused_backward(P, b_plan, go)
+    assert float((ga - gb).abs().max()) <= 1e-5 * float(gb.abs().max())
+    assert torch.equal(engine.eval_fused(P, a_plan, cp)[0], engine.eval_fused(P, b_plan, cp)[0])

@@ -61,8 +61,13 @@ def test_compute_active_span_bit_exact(name):
     for i in (0, len(supp) // 2, len(supp) - 1):
         lev, c = cells[i]
         assert supp[i] == [(fl, tuple(fn)) for fl, fn in oa[lev][c]]
-    # plan is a permutation grouped by cell
+    # plan is a permutation grouped by cell (a light plan holds the permutation only until its records are asked for)
+    if supp.plan.light:
+        perm_light = supp.plan.scratch[: supp.plan.n].cpu().numpy().copy()
+    supp.plan.ensure_records()
     rec = supp.plan.sorted_params[: supp.plan.n].cpu().numpy()
+    if supp.plan.light:
+        assert np.array_equal(perm_light, np.ascontiguousarray(rec[:, 3]).view(np.int32))
     perm = np.ascontiguousarray(rec[:, 3]).view(np.int32)
     assert np.array_equal(np.sort(perm), np.arange(len(perm)))
     slot_sorted = supp.slot.cpu().numpy()[perm]

@@ -33,7 +33,8 @@ class PlanDesc(C.Structure):
     _fields_ = [
         ("npoints", C.c_int64), ("points_per_item", C.c_int32), ("max_items", C.c_int32),
         ("slot", C.c_void_p), ("scratch", C.c_void_p), ("sorted_params", C.c_void_p), ("cell_count", C.c_void_p), ("cell_start", C.c_void_p),
-        ("cell_cursor", C.c_void_p), ("items", C.c_void_p), ("counters", C.c_void_p), ("rows_in_plan_order", C.c_int32), ("pad_", C.c_int32),
+        ("cell_cursor", C.c_void_p), ("items", C.c_void_p), ("counters", C.c_void_p), ("rows_in_plan_order", C.c_int32), ("light", C.c_int32),
+        ("params", C.c_void_p),
     ]
 
 
@@ -77,6 +78,7 @@ def _load():
         "thb_mse_grad": (i32, [vp, vp, i64, C.c_float, vp, vp, vp, vp]),
         "thb_adam_rows": (i32, [vp, vp, vp, vp, vp, i64, i32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, i32, vp, vp]),
         "thb_adam_rows_peer": (i32, [vp, vp, vp, vp, i32, i32, vp, vp, i64, i32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, vp, vp, vp]),
+        "thb_plan_records": (i32, [C.POINTER(SpaceDesc), vp, C.POINTER(PlanDesc), vp]),
         "thb_eval_grid": (i32, [C.POINTER(SpaceDesc), vp, vp, vp, i32, vp, vp, vp, C.POINTER(C.c_int64), i32, vp, vp, vp]),
         "thb_tensor_product": (i32, [vp, vp, vp, i64, i32, i32, i32, vp, vp]),
         "thb_fma_peak": (i32, [i32, i32, vp, C.POINTER(C.c_double), vp]),

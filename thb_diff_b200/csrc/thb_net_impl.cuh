@@ -444,11 +444,12 @@ __global__ void __launch_bounds__(32 * kNetWarps, (REL || CPD == 4) ? 6 : THB_NE
 template <class SH, bool DER, bool MONO = false>
 struct NetSmem {
     static constexpr int NPL = (DER && !MONO) ? 8 : 4;   // monomial nets: one set of planes serves every channel
-    int4 rec[3][4];                  // ring of work-item records (lookahead 2)
+    int4 rec[4][4];                  // ring of work-item records (lookahead 3)
     float knots[2][3][8];            // local knots of the item's cell, per dimension
     float rk[3][8];                  // reciprocal knot differences of the current item
     float net[2][NPL][SH::TS];       // the item's local control net (planes 4..7: relative), double buffered
     float4 prec[2][128];             // point records of a sub-batch (up to 4 per lane): (u0, u1, u2, caller-order index as bits)
+    int pidx[3][256];                // light plan: caller indices of the points of the current item and the two after it (<= 256 each)
 };
 
 template <class SH, bool DER, bool MONO>
@@ -859,22 +860,44 @@ __global__ void __launch_bounds__(kThreads, GRAD4 ? 12 : (PPT >= 4 ? (DER ? 12 :
     int32_t* const cursor = ar.counters + 1;
     const int d = sp.ndim;
 
-    int c3 = 0;
-    if (lane == 0) c3 = atomicAdd(cursor, 3);
-    const int id0 = __shfl_sync(0xffffffffu, c3, 0);
+    // item records run three ahead (ring of four), the permutation of a light plan two items ahead (ring of three): the
+    // indices of an item are in shared memory a whole item before its first points are gathered
+    int c4 = 0;
+    if (lane == 0) c4 = atomicAdd(cursor, 4);
+    const int id0 = __shfl_sync(0xffffffffu, c4, 0);
     if (id0 >= nitems) return;
-    int id1 = id0 + 1, id2 = id0 + 2;
+    int id1 = id0 + 1, id2 = id0 + 2, id3 = id0 + 3;
     Item it = load_item(sp, ar.items, id0);
     if (lane < 4 && id1 < nitems) cp_async16(&sm.rec[1][lane], ar.items + (int64_t)id1 * 4 + lane);
     if (lane < 4 && id2 < nitems) cp_async16(&sm.rec[2][lane], ar.items + (int64_t)id2 * 4 + lane);
+    if (lane < 4 && id3 < nitems) cp_async16(&sm.rec[3][lane], ar.items + (int64_t)id3 * 4 + lane);
     prefetch_net<SH, DER, MONO>(sp, nets, it, sm.knots[0], sm.net[0]);
-    prefetch_points<PPT>(ar, it.begin, it.count, 0, sm.prec[0]);
+    const bool light = ar.perm != nullptr;   // light plan: parameters gathered through the permutation
+    auto fetch_perm = [&](const Item& x, int* dst) {   // caller indices of an item's points (at most 256)
+        for (int i = lane; i < x.count; i += 32) cp_async4(dst + i, ar.perm + x.begin + i);
+    };
+    if (light) fetch_perm(it, sm.pidx[0]);
+    else prefetch_points<PPT>(ar, it.begin, it.count, 0, sm.prec[0]);
     cp_async_commit();
     int nn_id = 0;
     if (lane == 0) nn_id = atomicAdd(cursor, 1);
-    int ring = 0, tb = 0, pb = 0;
+    int ring = 0, tb = 0, pb = 0, pi = 0;   // pi: buffer of sm.pidx that holds the current item's indices
     cp_async_wait<0>();
     __syncwarp();
+    if (light) {
+        prefetch_points_gather<PPT>(ar, sm.pidx[0], it.count, 0, sm.prec[0]);
+        if (id1 < nitems) {
+            const int4* r = sm.rec[1];
+            fetch_perm(unpack_item(r[0], r[1], r[2], r[3]), sm.pidx[1]);
+        }
+        if (id2 < nitems) {
+            const int4* r = sm.rec[2];
+            fetch_perm(unpack_item(r[0], r[1], r[2], r[3]), sm.pidx[2]);
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncwarp();
+    }
 
     for (;;) {
         if (!MONO && lane < 24) {  // reciprocal knot differences of this cell (from the staged knots)
@@ -890,11 +913,13 @@ __global__ void __launch_bounds__(kThreads, GRAD4 ? 12 : (PPT >= 4 ? (DER ? 12 :
         const bool nx_valid = id1 < nitems;
         for (int base = 0; base < it.count; base += SB) {
             if (base + SB < it.count) {
-                prefetch_points<PPT>(ar, it.begin, it.count, base + SB, sm.prec[pb ^ 1]);
+                if (light) prefetch_points_gather<PPT>(ar, sm.pidx[pi], it.count, base + SB, sm.prec[pb ^ 1]);
+                else prefetch_points<PPT>(ar, it.begin, it.count, base + SB, sm.prec[pb ^ 1]);
             } else if (nx_valid) {
-                const int4* r = sm.rec[(ring + 1) % 3];
+                const int4* r = sm.rec[(ring + 1) & 3];
                 const Item nx = unpack_item(r[0], r[1], r[2], r[3]);
-                prefetch_points<PPT>(ar, nx.begin, nx.count, 0, sm.prec[pb ^ 1]);
+                if (light) prefetch_points_gather<PPT>(ar, sm.pidx[pi == 2 ? 0 : pi + 1], nx.count, 0, sm.prec[pb ^ 1]);   // its indices arrived an item ago
+                else prefetch_points<PPT>(ar, nx.begin, nx.count, 0, sm.prec[pb ^ 1]);
                 prefetch_net<SH, DER, MONO>(sp, nets, nx, sm.knots[tb ^ 1], sm.net[tb ^ 1]);
             }
             cp_async_commit();
@@ -916,16 +941,22 @@ __global__ void __launch_bounds__(kThreads, GRAD4 ? 12 : (PPT >= 4 ? (DER ? 12 :
             pb ^= 1;
         }
         if (!nx_valid) break;
-        ring = (ring + 1) % 3;
+        ring = (ring + 1) & 3;
         {
             const int4* r = sm.rec[ring];
             it = unpack_item(r[0], r[1], r[2], r[3]);
         }
         tb ^= 1;
-        const int id3 = __shfl_sync(0xffffffffu, nn_id, 0);
+        pi = pi == 2 ? 0 : pi + 1;
+        const int id4 = __shfl_sync(0xffffffffu, nn_id, 0);
         id1 = id2;
         id2 = id3;
-        if (lane < 4 && id3 < nitems) cp_async16(&sm.rec[(ring + 2) % 3][lane], ar.items + (int64_t)id3 * 4 + lane);
+        id3 = id4;
+        if (lane < 4 && id3 < nitems) cp_async16(&sm.rec[(ring + 3) & 3][lane], ar.items + (int64_t)id3 * 4 + lane);
+        if (light && id2 < nitems) {   // indices of the item two ahead (its record arrived an item ago) into the buffer the
+            const int4* r = sm.rec[(ring + 2) & 3];   // item just finished used; they are gathered from at the end of the next item
+            fetch_perm(unpack_item(r[0], r[1], r[2], r[3]), sm.pidx[pi == 0 ? 2 : pi - 1]);
+        }
         cp_async_commit();
         if (lane == 0) nn_id = atomicAdd(cursor, 1);
     }

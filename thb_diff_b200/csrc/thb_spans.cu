@@ -629,6 +629,47 @@ __global__ void __launch_bounds__(256) k_plan_scatter(const int32_t* __restrict_
     }
 }
 
+// pass 4, LIGHT plan: the same placement, but only the caller index travels (4 bytes written and the slot read per point,
+// instead of 16 written and slot + parameters read): the evaluation kernel gathers the parameters through the permutation.
+__global__ void __launch_bounds__(256) k_plan_scatter_light(const int32_t* __restrict__ slot, int64_t n, int32_t* __restrict__ cursor,
+                                                            int32_t* __restrict__ perm) {
+    constexpr int H = 4;
+    const int lane = threadIdx.x & 31;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t nround = (n + H * stride - 1) / (H * stride) * (H * stride);
+    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < nround; i0 += H * stride) {
+        int s[H], base[H], leader[H];
+        unsigned peers[H];
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+            const int64_t i = i0 + h * stride;
+            s[h] = i < n ? slot[i] : -1;
+        }
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+            peers[h] = __match_any_sync(0xffffffffu, s[h]);
+            leader[h] = __ffs(peers[h]) - 1;
+            base[h] = 0;
+            if (s[h] >= 0 && lane == leader[h]) base[h] = atomicAdd(cursor + s[h], __popc(peers[h]));
+        }
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+            base[h] = __shfl_sync(0xffffffffu, base[h], leader[h]);
+            if (s[h] >= 0) perm[(int64_t)base[h] + __popc(peers[h] & ((1u << lane) - 1u))] = (int32_t)(i0 + h * stride);
+        }
+    }
+}
+
+// records of a light plan: sorted[j] = (params[perm[j]], perm[j]) for the in-domain points (counters[2] of them)
+__global__ void __launch_bounds__(256) k_plan_records(const int32_t* __restrict__ perm, const float* __restrict__ params, int ndim,
+                                                      const int32_t* __restrict__ counters, float4* __restrict__ sorted) {
+    const int64_t n_in = counters[2];
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n_in; j += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = perm[j];
+        sorted[j] = make_float4(params[i * ndim], params[i * ndim + 1], ndim == 3 ? params[i * ndim + 2] : 0.f, __int_as_float((int32_t)i));
+    }
+}
+
 // compute_tensor_product (THB/bspline_funcs.py:54-59): out[b][i][j][k] = a[b][i] * bb[b][j] * c[b][k] for a batch of vector
 // triples (nc == 1 and c == nullptr for the 2-D form); one thread per output entry, coalesced stores
 __global__ void __launch_bounds__(256) k_tensor_product(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
@@ -790,9 +831,26 @@ extern "C" int thb_plan_build(const thb_space_desc* space, const float* params, 
                                                    plan->max_items, (int4*)plan->items);
     THB_LAUNCHED();
     if (n > 0) {
-        k_plan_scatter<<<grid_for(n, 256, plan_ctas_per_sm()), 256, 0, st>>>(plan->slot, params, space->ndim, n, plan->cell_cursor,
-                                                             (float4*)plan->sorted_params);
+        if (plan->light) {   // permutation only; plan->scratch is free from here on
+            k_plan_scatter_light<<<grid_for(n, 256, plan_ctas_per_sm()), 256, 0, st>>>(plan->slot, n, plan->cell_cursor, plan->scratch);
+        } else {
+            k_plan_scatter<<<grid_for(n, 256, plan_ctas_per_sm()), 256, 0, st>>>(plan->slot, params, space->ndim, n, plan->cell_cursor,
+                                                                 (float4*)plan->sorted_params);
+        }
         THB_LAUNCHED();
     }
+    return THB_OK;
+}
+
+extern "C" int thb_plan_records(const thb_space_desc* space, const float* params, const thb_plan_desc* plan, void* stream) {
+    int rc = thb_check_space(space, "thb_plan_records");
+    if (rc) return rc;
+    THB_REQUIRE(plan && plan->scratch && plan->sorted_params && plan->counters, "thb_plan_records: null plan buffer");
+    THB_REQUIRE(plan->light, "thb_plan_records: the plan already holds its records");
+    if (plan->npoints == 0) return THB_OK;
+    THB_REQUIRE(params, "thb_plan_records: null params");
+    k_plan_records<<<grid_for(plan->npoints, 256, 16), 256, 0, (cudaStream_t)stream>>>(plan->scratch, params, space->ndim, plan->counters,
+                                                                                       (float4*)plan->sorted_params);
+    THB_LAUNCHED();
     return THB_OK;
 }

@@ -34,8 +34,9 @@ static int env_int(const char* name, int dflt) {
 
 using namespace thb_tile;
 
-static int check_plan(const thb_plan_desc* plan, const char* who) {
+static int check_plan(const thb_plan_desc* plan, const char* who, bool light_ok = false) {
     THB_REQUIRE(plan && plan->sorted_params && plan->items && plan->counters, "%s: null plan buffer", who);
+    THB_REQUIRE(light_ok || plan->light != 1, "%s: light plan without records (thb_plan_records first)", who);
     return THB_OK;
 }
 
@@ -82,7 +83,7 @@ extern "C" int thb_eval_fused(const thb_space_desc* space, const thb_plan_desc* 
                               int formulation, float* workspace, void* stream) {
     int rc = thb_check_space(space, "thb_eval_fused");
     if (rc) return rc;
-    if ((rc = check_plan(plan, "thb_eval_fused"))) return rc;
+    if ((rc = check_plan(plan, "thb_eval_fused", formulation == THB_EVAL_LOCAL_NET))) return rc;
     if (plan->npoints == 0) return THB_OK;
     THB_REQUIRE(params && ctrl_pts && out_host, "thb_eval_fused: null pointer");
     THB_REQUIRE(cp_dim == 3 || cp_dim == 4, "thb_eval_fused: cp_dim must be 3 or 4 (pad other widths to 4)");
@@ -139,7 +140,7 @@ extern "C" int thb_eval_nets(const thb_space_desc* space, const thb_plan_desc* p
                              int cp_dim, const int32_t* channels, int nchannels, float* const* out_host, void* stream) {
     int rc = thb_check_space(space, "thb_eval_nets");
     if (rc) return rc;
-    if ((rc = check_plan(plan, "thb_eval_nets"))) return rc;
+    if ((rc = check_plan(plan, "thb_eval_nets", true))) return rc;
     if (plan->npoints == 0) return THB_OK;
     THB_REQUIRE(nets && out_host, "thb_eval_nets: null pointer");
     THB_REQUIRE(cp_dim == 3 || cp_dim == 4, "thb_eval_nets: cp_dim must be 3 or 4 (pad other widths to 4)");
@@ -157,6 +158,12 @@ extern "C" int thb_eval_nets(const thb_space_desc* space, const thb_plan_desc* p
     }
     ar.items = (const int4*)plan->items; ar.counters = plan->counters; ar.sorted = plan->sorted_params;
     ar.rows_sorted = plan->rows_in_plan_order ? 1 : 0;
+    if (plan->light == 1) {   // light plan: the kernel gathers the parameters through the permutation (plan->scratch)
+        THB_REQUIRE(plan->params && plan->scratch, "thb_eval_nets: a light plan needs thb_plan_desc::params");
+        THB_REQUIRE(plan->points_per_item <= 256, "thb_eval_nets: light plans need points_per_item <= 256");
+        THB_REQUIRE(mono, "thb_eval_nets: light plans are evaluated against monomial nets");
+        ar.perm = plan->scratch; ar.params = plan->params; ar.ndim = space->ndim;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     THB_CUDA(cudaMemsetAsync(plan->counters + 1, 0, sizeof(int32_t), st));
     return ops->net_eval(space, &ar, nets, env_int("THB_NET_PPT", mono ? 4 : 2), cp_dim, mono ? (der ? 1 : 0) : with_derivatives, mono, st);

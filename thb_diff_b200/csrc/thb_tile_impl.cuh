@@ -51,6 +51,8 @@ struct Args {
     const float* grad_out;
     float* grad_cp;
     float* item_ws;          // ordered (deterministic) backward: per-ITEM net gradients [nitems][4][TS], plain stores
+    const int32_t* perm;     // LIGHT plan (k_net_eval): perm[j] = caller index of the point in place j; nullptr = records in `sorted`
+    int32_t ndim;            // ... and the width of `params` the points are gathered from
 };
 
 template <int N0_, int N1_, int N2_>
@@ -242,6 +244,27 @@ THB_DEV void prefetch_points(const Args& ar, int begin, int count, int base, flo
         const int li = base + q * 32 + lane;
         if (q == 0 || base + q * 32 < count)   // warp-uniform: blocks beyond the item are not fetched
             cp_async16(prec + q * 32 + lane, src + begin + (li < count ? li : 0));
+    }
+}
+
+// The same for a LIGHT plan: the caller indices of the item's points are already in shared memory (pidx, one item ahead);
+// the parameters are gathered from the caller's array (three 4-byte cp.async per point), the index goes into .w.
+template <int PPT>
+THB_DEV void prefetch_points_gather(const Args& ar, const int* pidx, int count, int base, float4* prec) {
+    const int lane = threadIdx.x;
+#pragma unroll
+    for (int q = 0; q < PPT; ++q) {
+        const int li = base + q * 32 + lane;
+        if (q == 0 || base + q * 32 < count) {
+            const int idx = pidx[li < count ? li : 0];
+            const float* src = ar.params + (int64_t)idx * ar.ndim;
+            float* dst = reinterpret_cast<float*>(prec + q * 32 + lane);
+            cp_async4(dst, src);
+            cp_async4(dst + 1, src + 1);
+            if (ar.ndim == 3) cp_async4(dst + 2, src + 2);
+            else dst[2] = 0.0f;
+            dst[3] = __int_as_float(idx);
+        }
     }
 }
 

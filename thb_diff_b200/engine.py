@@ -44,8 +44,16 @@ def _as_params(params, ndim, device):
 class Plan:
     """The points of one batch grouped by active cell (device resident)."""
 
-    def __init__(self, P, params, points_per_item=POINTS_PER_ITEM, capacity=None):
+    def __init__(self, P, params, points_per_item=POINTS_PER_ITEM, capacity=None, light=None):
+        """light (default off; THB_PLAN_LIGHT=1): thb_plan_build writes only the permutation of the points (4 bytes per
+        point instead of a 16-byte record, and it does not re-read the parameters); eval_nets gathers the parameters
+        through it.  Every other consumer (PHI rows, the per-point formulations, the backward, caller_index) materialises
+        the records on first use (ensure_records).  Measured on config 3: plan 0.207 -> 0.154 ms, evaluation kernel 0.176
+        -> 0.207 ms (three 4-byte gathers per point instead of one 16-byte record), pass 0.467 -> 0.443 ms."""
         self.P = P
+        if light is None:
+            light = _os.environ.get("THB_PLAN_LIGHT", "0") not in ("0", "")
+        self.light = bool(light) and points_per_item <= 256 and getattr(P, "poly", None) is not None
         self.params = _as_params(params, P.ndim, P.device)
         n = self.params.shape[0]
         dev = P.device
@@ -71,8 +79,18 @@ class Plan:
 
     def build(self):
         self.version = self.P.version
+        self.desc.light = 1 if self.light else 0
+        self.desc.params = self.params.data_ptr()
         with _on(self.P.device):
             check(lib.thb_plan_build(C.byref(self.P.desc()), ptr(self.params), C.byref(self.desc), stream_ptr(self.P.device)), "thb_plan_build")
+
+    def ensure_records(self):
+        """The 16-byte point records of a light plan (thb_plan_records), built once per plan build."""
+        if self.desc.light == 1:
+            with _on(self.P.device):
+                check(lib.thb_plan_records(C.byref(self.P.desc()), ptr(self.params), C.byref(self.desc), stream_ptr(self.P.device)), "thb_plan_records")
+            self.desc.light = 2
+        return self
 
     def rebind(self, params):
         """Plans another batch (at most `capacity` points) in the same buffers."""
@@ -93,6 +111,7 @@ class Plan:
 
     def caller_index(self):
         """int64 [n_inside]: caller-order index of the point in row j of the plan order (synchronises once)."""
+        self.ensure_records()
         n_in = int(self.counters[2])
         return self.sorted_params[:n_in, 3].contiguous().view(torch.int32).long()
 
@@ -102,6 +121,7 @@ class Plan:
         of a work item (the fused backward) inherit that order.  After this call two plans of the same batch are
         bit-identical, and with the ordered backward (deterministic=True) so are the gradients.  One device sort of the
         batch (torch.sort, stable radix sort); call it once for a fit, whose plan is built once."""
+        self.ensure_records()
         n_in = int(self.counters[2])
         if n_in == 0:
             return self
@@ -110,6 +130,8 @@ class Plan:
         key = (self.slot[: self.n].long()[idx] << 32) | idx          # records are already grouped by cell: the cell order is kept
         order = torch.argsort(key, stable=True)
         self.sorted_params[:n_in] = rec[order]
+        if self.light:   # keep the permutation of a light plan in step with its records
+            self.scratch[:n_in] = self.sorted_params[:n_in, 3].contiguous().view(torch.int32)
         return self
 
     def refresh(self):
@@ -161,7 +183,7 @@ def basis_tiled(P, plan, offsets, nnz, channels=(CH_VALUE,)):
     """PHI for each channel, flat [nnz] in the reference's (point-major) pair order."""
     if not P.has_tiles:
         raise RuntimeError("the hierarchy has no coefficient tiles yet (PackedHierarchy.attach_tiles / from_space)")
-    plan.refresh()
+    plan.refresh().ensure_records()
     outs = [torch.empty(nnz, dtype=torch.float32, device=P.device) for _ in channels]  # every entry is written
     arr = (C.c_void_p * len(outs))(*[o.data_ptr() for o in outs])
     with _on(P.device):
@@ -267,6 +289,8 @@ def eval_nets(P, plan, nets, cp_dim=3, channels=(CH_VALUE,), out=None, with_deri
             monomial = bool(flags & NETS_MONOMIAL) if flags is not None else False
         flags = (NETS_DERIVATIVES if with_derivatives else 0) | (NETS_MONOMIAL if monomial else 0)
     plan.refresh()
+    if not flags & NETS_MONOMIAL:
+        plan.ensure_records()   # a light plan is gathered through its permutation by the monomial kernels only
     if out is None:
         out = [torch.zeros((plan.n, cp_dim), dtype=torch.float32, device=P.device) for _ in channels]
     if len(out) != len(channels):
@@ -292,6 +316,8 @@ def eval_fused(P, plan, ctrl_pts, channels=(CH_VALUE,), cellnet=True, out=None, 
     if not P.has_tiles:
         raise RuntimeError("the hierarchy has no coefficient tiles yet (PackedHierarchy.attach_tiles / from_space)")
     plan.refresh()
+    if form != 0 or not (_net_flags(P, False) & NETS_MONOMIAL):
+        plan.ensure_records()
     if out is None:
         out = [torch.zeros((plan.n, cpd), dtype=torch.float32, device=P.device) for _ in channels]
     if len(out) != len(channels):
@@ -316,7 +342,7 @@ def eval_fused_backward(P, plan, grad_out, cp_dim=None, formulation="local_net",
         raise RuntimeError("fused backward supports control points of width 3 or 4")
     if not P.has_tiles:
         raise RuntimeError("the hierarchy has no coefficient tiles yet (PackedHierarchy.attach_tiles / from_space)")
-    plan.refresh()
+    plan.refresh().ensure_records()
     _check_rows([grad_out], plan, cpd, "grad_out")
     if deterministic is None:
         deterministic = deterministic_default()
@@ -378,7 +404,7 @@ def eval_fused_backward_rows(P, plan, grad_out, out=None, deterministic=None):
         raise RuntimeError("fused backward supports control points of width 3 or 4")
     if not P.has_tiles:
         raise RuntimeError("the hierarchy has no coefficient tiles yet (PackedHierarchy.attach_tiles / from_space)")
-    plan.refresh()
+    plan.refresh().ensure_records()
     _check_rows([grad_out], plan, cpd, "grad_out")
     ids, row_map = P.active_rows()
     if deterministic is None:
