@@ -479,6 +479,11 @@ def fit_block(sp, P, rank, world, device, cell_cost, n_total=10_000_000):
             t = torch.tensor([c, a, o], device=device)
             if world > 1:
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            tmin = torch.tensor([c, a, o], device=device)
+            if world > 1:
+                dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+            # the rank that arrives last does not wait for anyone: its exchange phase is the cost of the exchange itself
+            res["exchange_ms_min_over_ranks"] = float(tmin[2]) if eng.peer is not None else float(tmin[1])
             res["phases_ms"] = {"compute": float(t[0]), "allreduce": float(t[1]), "adam": float(t[2]),
                                 "note": "eager launches; with peer memory the exchange is inside the `adam` kernel pair (flag wait + peer reads + Adam); "
                                         "times include waiting for the slowest rank"}
@@ -489,6 +494,11 @@ def fit_block(sp, P, rank, world, device, cell_cost, n_total=10_000_000):
             else:
                 allc = [cnt]
             res["points_per_rank"] = [int(v) for v in allc]
+        if name == "graph_nccl":
+            c, a, o = eng.time_phases(xx, iters=20)
+            tmin = torch.tensor([a], device=device)
+            dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+            res["nccl_allreduce_ms_min_over_ranks"] = float(tmin[0])
         del eng
     best = min(res[k]["ms_per_step"] for k, _, _ in variants)
     res.update({"adam_steps_per_s": 1e3 / best, "ms_per_step": best, "points": n_total, "n_active_rows": P.n_active,
@@ -916,6 +926,7 @@ def main():
             c["fit_c4_collective"] = b["graph"]["exchange"]
             if "graph_nccl" in b:
                 c["fit_c4_ms_per_step_nccl"] = b["graph_nccl"]["ms_per_step"]
+                c["fit_c4_exchange_ms"], c["fit_c4_nccl_allreduce_ms"] = b.get("exchange_ms_min_over_ranks"), b.get("nccl_allreduce_ms_min_over_ranks")
         b = blocks.get("c5", {})
         if "points_per_s" in b:
             c["c5_points_per_s"], c["c5_ms_per_step"], c["c5_jacobian_max_abs_err"] = b["points_per_s"], b["ms_per_step"], b["jacobian_max_abs_err"]

@@ -196,6 +196,7 @@ static int fused_backward_impl(const thb_space_desc* space, const thb_plan_desc*
         THB_CUDA(cudaMemsetAsync(workspace, 0, sizeof(float) * (size_t)thb_net_workspace_floats(space, 0), st));
         NetArgs na = {};
         na.cell_count = plan->cell_count; na.nets = workspace; na.planes = 4; na.row_map = row_map;
+        na.mono = (space->poly && env_int("THB_NET_MONO", 1)) ? 1 : 0;   // per-item sums in the monomial basis of the cell
         ar.rows_sorted = plan->rows_in_plan_order ? 1 : 0;
         return ops->net_backward(space, &ar, &na, grad, cp_dim, st);
     }
@@ -244,5 +245,6 @@ extern "C" int thb_eval_fused_backward_ordered(const thb_space_desc* space, cons
     THB_CUDA(cudaMemsetAsync(od->contrib, 0, sizeof(float) * (size_t)od->nsupp * cp_dim, st));   // cells without points contribute zero
     NetArgs na = {};
     na.cell_count = plan->cell_count; na.nets = workspace; na.planes = 4; na.contrib = od->contrib;
+    na.mono = (space->poly && env_int("THB_NET_MONO", 1)) ? 1 : 0;
     return ops->net_backward_ordered(space, &ar, &na, od, plan->cell_count, plan->points_per_item, plan->max_items, grad, cp_dim, st);
 }
