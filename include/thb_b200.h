@@ -172,6 +172,12 @@ THB_API int thb_expand_supports(const thb_space_desc* space, const int32_t* slot
  * Computes plan->slot itself (same result as thb_active_span). */
 THB_API int thb_plan_build(const thb_space_desc* space, const float* params, const thb_plan_desc* plan, void* stream);
 
+/* The same in two calls, so that a caller can put other work between them or beside the second:
+ * phase 1 = histogram (plan->slot, cell_count), scan and work items -- everything thb_cell_nets needs to know which cells hold
+ * points; phase 2 = the scatter of the points into cell order (HBM-bound; engine.plan_and_nets runs the nets kernel beside it). */
+THB_API int thb_plan_build_phase(const thb_space_desc* space, const float* params, const thb_plan_desc* plan, int phase,
+                         void* stream);
+
 /* ---- THB_basis_fns (THB/core.py:604-701; float64 statement: compute_THB_fns_tp, core.py:203-268) -----------
  * phi_out[c][offsets[i] + s] for every channel c < nchannels, point i and support s of the point's cell. */
 THB_API int thb_basis_tiled(const thb_space_desc* space, const thb_plan_desc* plan, const float* params,

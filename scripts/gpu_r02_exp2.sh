@@ -1,0 +1,11 @@
+#!/bin/bash
+# bulk-staged CSR forward: parity + timing against the register-path kernel
+cd "${GRAFT_REPO_ROOT:-/root/repo}"
+mkdir -p gpurun_out
+L=gpurun_out/exp2.log; : > $L
+timeout 600 python -m pytest tests/test_gpu_contraction.py -q -m gpu -x --tb=short >> $L 2>&1; echo "tests rc=$?" >> $L
+echo "== bulk" >> $L
+timeout 600 python scripts/exp_csr.py >> $L 2>&1
+echo "== register path" >> $L
+THB_CSR_BULK=0 timeout 600 python scripts/exp_csr.py >> $L 2>&1
+tail -n 30 $L

@@ -36,8 +36,9 @@ def test_golden_compute_pts(tag, idx_dtype):
     assert _close(gcp.cpu().numpy(), c[f"{tag}_bwd"])
 
 
+@pytest.mark.parametrize("idx_dtype", [torch.int64, torch.int32])
 @pytest.mark.parametrize("cp_dim", [1, 2, 3, 4])
-def test_random_csr_vs_oracle(cp_dim):
+def test_random_csr_vs_oracle(cp_dim, idx_dtype):
     from thb_diff_b200 import THB_eval
 
     rng = np.random.default_rng(11 + cp_dim)
@@ -51,11 +52,58 @@ def test_random_csr_vs_oracle(cp_dim):
     cs = np.cumsum(ns).astype(np.int64)
     cp = rng.standard_normal((nCP, cp_dim)).astype(np.float32)
     g = rng.standard_normal((N, cp_dim)).astype(np.float32)
-    out = THB_eval.forward(torch.from_numpy(cp).cuda(), torch.from_numpy(Jm).cuda(), torch.from_numpy(phi).cuda(), torch.from_numpy(cs).cuda())
+    Jd, cd = torch.from_numpy(Jm).to(idx_dtype).cuda(), torch.from_numpy(cs).to(idx_dtype).cuda()
+    out = THB_eval.forward(torch.from_numpy(cp).cuda(), Jd, torch.from_numpy(phi).cuda(), cd)
     assert _close(out.cpu().numpy(), O.eval_forward(cp, Jm, phi, cs))
-    gcp = THB_eval.backward(torch.from_numpy(g).cuda(), torch.from_numpy(cp).cuda(), torch.from_numpy(Jm).cuda(), torch.from_numpy(phi).cuda(),
-                            torch.from_numpy(cs).cuda())
+    gcp = THB_eval.backward(torch.from_numpy(g).cuda(), torch.from_numpy(cp).cuda(), Jd, torch.from_numpy(phi).cuda(), cd)
     assert _close(gcp.cpu().numpy(), O.eval_backward(g, cp.shape, Jm, phi, cs))
+
+
+@pytest.mark.parametrize("idx_dtype", [torch.int64, torch.int32])
+def test_long_segments_and_misaligned_views(idx_dtype):
+    """Segments longer than one shared-memory stage of the bulk-staged forward (walked from global memory), chunks that end
+    at the end of the arrays, and PHI / Jm views that are not 16-byte aligned (register-path kernels)."""
+    from thb_diff_b200 import THB_eval
+
+    rng = np.random.default_rng(5)
+    nCP = 300
+    ns = np.concatenate([rng.integers(0, 90, size=70), [5000, 0, 2304, 2305, 17], rng.integers(60, 130, size=100), [3]])
+    Jm = rng.integers(0, nCP, size=int(ns.sum())).astype(np.int64)
+    phi = rng.random(len(Jm)).astype(np.float32)
+    cs = np.cumsum(ns).astype(np.int64)
+    cp = rng.standard_normal((nCP, 3)).astype(np.float32)
+    ref = O.eval_forward(cp, Jm, phi, cs)
+    cpd = torch.from_numpy(cp).cuda()
+    Jd, pd, cd = torch.from_numpy(Jm).to(idx_dtype).cuda(), torch.from_numpy(phi).cuda(), torch.from_numpy(cs).to(idx_dtype).cuda()
+    assert _close(THB_eval.forward(cpd, Jd, pd, cd).cpu().numpy(), ref)
+    # the same data one element into a larger buffer: base pointers 4 bytes off a 16-byte boundary
+    Jo = torch.zeros(len(Jm) + 1, dtype=idx_dtype, device="cuda"); Jo[1:] = Jd
+    po = torch.zeros(len(Jm) + 1, device="cuda"); po[1:] = pd
+    assert _close(THB_eval.forward(cpd, Jo[1:], po[1:], cd).cpu().numpy(), ref)
+
+
+def test_staged_forward_with_int64_indices():
+    """THB_CSR_BULK=2 routes 64-bit indices through the bulk-staged kernel too (read once per process: own process)."""
+    import os, subprocess, sys
+
+    code = (
+        "import numpy as np, torch, sys\n"
+        "sys.path.insert(0, 'tests'); sys.path.insert(0, '.')\n"
+        "from oracle import thb_oracle as O\n"
+        "from thb_diff_b200 import THB_eval\n"
+        "rng = np.random.default_rng(3)\n"
+        "ns = np.concatenate([rng.integers(0, 140, size=400), [3000, 0, 1152, 1153], rng.integers(60, 70, size=300)])\n"
+        "Jm = rng.integers(0, 500, size=int(ns.sum())).astype(np.int64); phi = rng.random(len(Jm)).astype(np.float32)\n"
+        "cs = np.cumsum(ns).astype(np.int64); cp = rng.standard_normal((500, 3)).astype(np.float32)\n"
+        "out = THB_eval.forward(torch.from_numpy(cp).cuda(), torch.from_numpy(Jm).cuda(), torch.from_numpy(phi).cuda(), torch.from_numpy(cs).cuda())\n"
+        "ref = O.eval_forward(cp, Jm, phi, cs)\n"
+        "err = np.abs(out.cpu().numpy() - ref).max() / np.abs(ref).max()\n"
+        "assert err <= 1e-5, err\n"
+        "print('ok')\n"
+    )
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ, THB_CSR_BULK="2"), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
 
 
 def test_empty_and_errors():

@@ -64,6 +64,7 @@ def _load():
         "thb_active_span": (i32, [C.POINTER(SpaceDesc), vp, i64, vp, vp, vp]),
         "thb_expand_supports": (i32, [C.POINTER(SpaceDesc), vp, vp, i64, vp, i32, vp]),
         "thb_plan_build": (i32, [C.POINTER(SpaceDesc), vp, C.POINTER(PlanDesc), vp]),
+        "thb_plan_build_phase": (i32, [C.POINTER(SpaceDesc), vp, C.POINTER(PlanDesc), C.c_int, vp]),
         "thb_basis_tiled": (i32, [C.POINTER(SpaceDesc), C.POINTER(PlanDesc), vp, vp, C.POINTER(C.c_int32), i32, C.POINTER(vp), vp]),
         "thb_basis_dense": (i32, [vp, i64, i32, C.POINTER(C.c_int32), vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                   C.POINTER(C.c_int32), vp, vp, i32, vp, i32, vp, vp]),

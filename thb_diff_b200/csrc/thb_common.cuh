@@ -166,3 +166,42 @@ THB_DEV void cp_async16_cg(void* smem, const void* gmem) {  // streaming data: b
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
 }
+
+// ---- bulk asynchronous copies (TMA, 1-D: cp.async.bulk global -> shared, SASS UBLKCP) completing on an mbarrier ---------
+// One lane arms the barrier with the byte count and issues the copies; every lane of the consumer waits on the phase
+// parity.  Source and destination 16-byte aligned, size a multiple of 16.
+THB_DEV void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+THB_DEV void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+THB_DEV void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+THB_DEV void bulk_g2s(void* smem, const void* gmem, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(smem)),
+                 "l"(gmem), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+THB_DEV bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+THB_DEV void mbar_wait(unsigned long long* bar, unsigned parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+
+// CSR contraction from bulk-staged segments (thb_eval_bulk.cu); returns THB_OK, an error, or 1 = "not applicable here"
+// (misaligned arrays, switched off): the caller then runs the register-path kernels of thb_eval_csr.cu
+int thb_csr_forward_bulk(const float* cp, const void* jm, int jm_is_i64, const float* phi, const void* cumsum, int cumsum_is_i64,
+                         float* out, int64_t npoints, int cp_dim, cudaStream_t st);

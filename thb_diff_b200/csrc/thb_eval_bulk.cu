@@ -1,0 +1,276 @@
+// THB_eval.forward (compute_pts_cuda_kernels.cu:3-26) from BULK-STAGED segments.
+//
+// The register-path kernel of thb_eval_csr.cu (lane = entry, coalesced loads, control points cached in registers while
+// consecutive points share a support list) is limited by the bytes a warp can keep in flight: its loads live in registers
+// (four points at a time) and it waits for them at ~50 % issue, 0.6 of HBM on config 3.  Here the memory side is the TMA:
+// a warp's next chunk of up to 16 consecutive points is ONE contiguous range of PHI and one of Jm, fetched by two
+// cp.async.bulk copies (one lane issues them, completion on an mbarrier) into a two-stage shared-memory ring -- the whole
+// next chunk in flight per warp, no registers, no address arithmetic, no prefetch instructions.  The compute side is the
+// same point body (thb_csr_impl.cuh) reading shared memory.
+//
+// Measured and dropped on the way (config 3, int32 indices, register path 2.40 ms): the reference's own loop, one LANE per
+// point walking its staged segment (no reductions, no run detection: 9.5 instructions per entry) -- lanes of one cell sit
+// S words apart, S = 64 is the common case, so either all lanes hit one bank or, staggered, every gather touches up to 32
+// control-point rows: 2.48 ms at best (4-way conflicts, 8 rows).
+#include <cstdint>
+#include <cstdlib>
+
+#include "thb_common.cuh"
+#include "thb_csr_impl.cuh"
+
+namespace {
+
+using namespace thb_csr;
+
+#ifndef THB_BULK_CAP
+#define THB_BULK_CAP 1152   // entries per stage: 16 points x 72 supports
+#endif
+constexpr int kCap = THB_BULK_CAP;
+constexpr int kSlack = 8;   // alignment shift (<= 3) + rounding up to 16 bytes (<= 3)
+
+template <typename JT>
+struct BulkStage {
+    float phi[kCap + kSlack];
+    JT jm[kCap + kSlack];   // (the kernel addresses jm as phi + (kCap + kSlack) * 4 bytes when sizeof(JT) == 4)
+};
+template <typename JT>
+struct BulkWarp {
+    BulkStage<JT> st[2];
+    unsigned long long bar[2];
+};
+#ifndef THB_BULK_WARPS32
+#define THB_BULK_WARPS32 12
+#endif
+#ifndef THB_BULK_WARPS64
+#define THB_BULK_WARPS64 8
+#endif
+template <typename JT>
+struct BulkCfg {
+    static constexpr int kWarps = sizeof(JT) == 8 ? THB_BULK_WARPS64 : THB_BULK_WARPS32;   // autonomous warps per CTA (one CTA per SM: ~220 KB of stages)
+};
+
+constexpr int kChunkPts = 16;   // points per chunk at most (two reduce8 batches)
+
+struct Chunk {
+    int64_t p;       // first point
+    int64_t base;    // first entry
+    int m;           // points (0: none left)
+    int npairs;
+    int my_beg, my_end;   // this lane's segment relative to base (lane < m)
+    bool bulk;
+};
+
+// cumsum[p + lane] (the end of the lane's segment) or -1 past the warp's range.  Loaded one chunk AHEAD of its use: the
+// chain p -> cumsum -> number of points that fit -> next p is serial, and a load per chunk on the critical path cost a
+// third of the kernel (measured)
+template <typename CT>
+THB_DEV int64_t load_end(const CT* __restrict__ cumsum, int64_t p, int64_t p1, int lane) {
+    return p + lane < p1 ? (int64_t)__ldg(cumsum + p + lane) : (int64_t)-1;
+}
+
+// up to 32 points from p (< p1) whose entries fit one stage; `end` = load_end(p)
+THB_DEV Chunk describe(int64_t end, int64_t p, int64_t p1, int64_t base, int64_t nnz, int esz_jm, int lane) {
+    Chunk c;
+    c.p = p; c.base = base; c.m = 0; c.npairs = 0; c.my_beg = 0; c.my_end = 0; c.bulk = false;
+    if (p >= p1) return c;
+    const bool in = end >= 0 && lane < kChunkPts;
+    const int64_t rel = in ? end - base : 0;
+    const bool fits = in && rel <= (int64_t)kCap;
+    const unsigned mask = __ballot_sync(0xffffffffu, fits);   // cumsum is non-decreasing: a prefix of the lanes
+    int m = __popc(mask);
+    c.bulk = m > 0;
+    if (m == 0) m = 1;   // one over-long segment: walked from global memory by lane 0
+    c.m = m;
+    c.my_end = (int)min(rel, (int64_t)0x7fffffff);
+    const int64_t tot = __shfl_sync(0xffffffffu, rel, m - 1);
+    c.npairs = (int)min(tot, (int64_t)0x7fffffff);
+    const int up = __shfl_up_sync(0xffffffffu, c.my_end, 1);
+    c.my_beg = lane == 0 ? 0 : up;
+    if (c.bulk) {   // the copies are rounded out to 16 bytes: they must stay inside the arrays
+        const int64_t a0 = base & ~(int64_t)3, end4 = (base + tot + 3) & ~(int64_t)3;
+        const int per16 = 16 / esz_jm;
+        const int64_t endj = (base + tot + per16 - 1) / per16 * per16;
+        if (end4 > nnz || endj > nnz || tot == 0) c.bulk = false;   // (nothing to copy: the points have no supports)
+        (void)a0;
+    }
+    return c;
+}
+
+template <typename JT>
+THB_DEV void issue(const Chunk& c, BulkStage<JT>& st, unsigned long long* bar, const float* __restrict__ phi, const JT* __restrict__ jm,
+                   int lane) {
+    if (lane == 0) {
+        constexpr int per16 = 16 / (int)sizeof(JT);
+        const int64_t a0 = c.base & ~(int64_t)3, a1 = (c.base + c.npairs + 3) & ~(int64_t)3;
+        const int64_t j0 = c.base / per16 * per16, j1 = (c.base + c.npairs + per16 - 1) / per16 * per16;
+        const unsigned bp = (unsigned)(a1 - a0) * 4u, bj = (unsigned)(j1 - j0) * (unsigned)sizeof(JT);
+        mbar_expect_tx(bar, bp + bj);
+        bulk_g2s(st.phi, phi + a0, bp, bar);
+        bulk_g2s(st.jm, jm + j0, bj, bar);
+    }
+}
+
+template <typename JT, typename CT, int CPD>
+__global__ void __launch_bounds__(32 * BulkCfg<JT>::kWarps, 1) k_csr_forward_bulk(const float* __restrict__ cp, const JT* __restrict__ jm,
+                                                                                const float* __restrict__ phi,
+                                                                                const CT* __restrict__ cumsum, float* __restrict__ out,
+                                                                                int64_t npoints, int pts_per_warp) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    BulkWarp<JT>& sw = reinterpret_cast<BulkWarp<JT>*>(smem_raw)[wid];
+    const int64_t warp = (int64_t)blockIdx.x * BulkCfg<JT>::kWarps + wid;
+    const int64_t p0 = warp * pts_per_warp;
+    if (p0 >= npoints) return;
+    const int64_t p1 = min(p0 + pts_per_warp, npoints);
+    if (lane == 0) {
+        mbar_init(&sw.bar[0], 1);
+        mbar_init(&sw.bar[1], 1);
+        mbar_init_fence();
+    }
+    __syncwarp();
+    const int64_t nnz = (int64_t)cumsum[npoints - 1];
+    constexpr int per16 = 16 / (int)sizeof(JT);
+    constexpr int ej = (int)sizeof(JT);
+    Chunk cur = describe(load_end<CT>(cumsum, p0, p1, lane), p0, p1, p0 ? (int64_t)cumsum[p0 - 1] : 0, nnz, ej, lane);
+    if (cur.bulk) issue<JT>(cur, sw.st[0], &sw.bar[0], phi, jm, lane);
+    Chunk nxt = describe(load_end<CT>(cumsum, cur.p + cur.m, p1, lane), cur.p + cur.m, p1, cur.base + cur.npairs, nnz, ej, lane);
+    if (nxt.m > 0 && nxt.bulk) issue<JT>(nxt, sw.st[1], &sw.bar[1], phi, jm, lane);
+    int64_t p_after = nxt.p + nxt.m;
+    int64_t end_after = load_end<CT>(cumsum, p_after, p1, lane);   // consumed after the next compute phase
+    int s = 0;
+    unsigned parity = 0u;   // bit s: phase of stage s
+    constexpr int NPT = 4;
+    FwdCache<JT, CPD> c;
+    c.runS = -1;
+#pragma unroll
+    for (int q = 0; q < kFwdStrips; ++q) c.key[q] = (JT)-2;
+    while (cur.m > 0) {
+        if (cur.bulk) {
+            mbar_wait(&sw.bar[s], (parity >> s) & 1u);
+            parity ^= 1u << s;
+        }
+        // staged chunk: pointers into the stage, entry 0 = the chunk's first entry; otherwise (ends of the arrays, over-long
+        // segments) the same bodies on global memory
+        const float* cphi = cur.bulk ? sw.st[s].phi + (int)(cur.base & 3) : phi + cur.base;
+        const JT* cjm = cur.bulk ? sw.st[s].jm + (int)(cur.base % per16) : jm + cur.base;
+        const int np = cur.m;
+        int beg = 0;
+        for (int i0 = 0; i0 < np; i0 += kFwdBatch) {
+            float acc[CPD][kFwdBatch];
+#pragma unroll
+            for (int j0 = 0; j0 < kFwdBatch; j0 += NPT) {
+                float a[NPT][CPD];
+#pragma unroll
+                for (int h = 0; h < NPT; ++h)
+#pragma unroll
+                    for (int k = 0; k < CPD; ++k) a[h][k] = 0.0f;
+                if (i0 + j0 < np) {   // warp-uniform
+                    int ob[NPT], S[NPT], smax = 0;
+#pragma unroll
+                    for (int h = 0; h < NPT; ++h) {
+                        const int i = i0 + j0 + h;
+                        const int e = i < np ? __shfl_sync(0xffffffffu, cur.my_end, i & 31) : beg;
+                        ob[h] = beg;
+                        S[h] = e - beg;
+                        beg = e;
+                        smax = max(smax, S[h]);
+                    }
+                    if (cur.bulk && smax <= 64) fwd_points<JT, CPD, 2, NPT, true>(cp, cjm, cphi, 0, ob, S, c, a, lane);
+                    else if (cur.bulk && smax <= 96) fwd_points<JT, CPD, 3, NPT, true>(cp, cjm, cphi, 0, ob, S, c, a, lane);
+                    else if (cur.bulk && smax <= 32 * kFwdStrips) fwd_points<JT, CPD, kFwdStrips, NPT, true>(cp, cjm, cphi, 0, ob, S, c, a, lane);
+                    else {   // long lists, or a chunk that was not staged: streamed from global memory, nothing cached
+#pragma unroll
+                        for (int h = 0; h < NPT; ++h) {
+                            for (int64_t j = cur.base + ob[h] + lane; j < cur.base + ob[h] + S[h]; j += 32) {
+                                const float w = __ldg(phi + j);
+                                const int64_t r = (int64_t)__ldg(jm + j);
+#pragma unroll
+                                for (int k = 0; k < CPD; ++k) a[h][k] = fmaf(w, __ldg(cp + r * CPD + k), a[h][k]);
+                            }
+                        }
+                        c.runS = -1;
+                    }
+                }
+#pragma unroll
+                for (int h = 0; h < NPT; ++h)
+#pragma unroll
+                    for (int k = 0; k < CPD; ++k) acc[k][j0 + h] = a[h][k];
+            }
+            const int mine = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+#pragma unroll
+            for (int k = 0; k < CPD; ++k) {
+                const float r = reduce8(acc[k], lane);
+                if ((lane & 3) == 0 && i0 + mine < np) out[(cur.p + i0 + mine) * CPD + k] = r;
+            }
+        }
+        (void)cphi; (void)cjm;
+        __syncwarp();
+        // the stage just read is free: the chunk after next goes there
+        Chunk nn = describe(end_after, p_after, p1, nxt.base + nxt.npairs, nnz, ej, lane);
+        if (nn.m > 0 && nn.bulk) issue<JT>(nn, sw.st[s], &sw.bar[s], phi, jm, lane);
+        p_after = nn.p + nn.m;
+        end_after = load_end<CT>(cumsum, p_after, p1, lane);
+        cur = nxt;
+        nxt = nn;
+        s ^= 1;
+    }
+}
+
+// THB_CSR_BULK: 0 = register-path kernels only, 1 (default) = staged kernel for 32-bit indices, 2 = for 64-bit ones too
+int bulk_mode() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("THB_CSR_BULK");
+        v = e ? atoi(e) : 1;
+        if (v < 0 || v > 2) v = 1;
+    }
+    return v;
+}
+bool bulk_enabled() { return bulk_mode() != 0; }
+
+template <typename JT, typename CT>
+int launch_fwd_bulk(const float* cp, const void* jm, const float* phi, const void* cs, float* out, int64_t n, int cpd, cudaStream_t st) {
+    constexpr int W = BulkCfg<JT>::kWarps;
+    const size_t smem = sizeof(BulkWarp<JT>) * W;
+    // ranges of 2048 points per warp: many more CTAs than fit at once, dealt by the hardware as CTAs retire
+    int ppw = 2048;
+    while (ppw > 64 && (n + ppw - 1) / ppw < (int64_t)thb_num_sms() * W * 8) ppw >>= 1;
+    const int64_t warps = (n + ppw - 1) / ppw;
+    const int grid = (int)((warps + W - 1) / W);
+#define THB_FWDB(C)                                                                                                        \
+    do {                                                                                                                   \
+        static bool attr_set[THB_MAX_DEVICES] = {};                                                                        \
+        const int dev = thb_device();                                                                                      \
+        if (!attr_set[dev]) {                                                                                              \
+            THB_CUDA(cudaFuncSetAttribute(k_csr_forward_bulk<JT, CT, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            attr_set[dev] = true;                                                                                          \
+        }                                                                                                                  \
+        k_csr_forward_bulk<JT, CT, C><<<grid, 32 * W, smem, st>>>(cp, (const JT*)jm, phi, (const CT*)cs, out, n, ppw);      \
+    } while (0)
+    switch (cpd) {
+        case 1: THB_FWDB(1); break;
+        case 2: THB_FWDB(2); break;
+        case 3: THB_FWDB(3); break;
+        case 4: THB_FWDB(4); break;
+        default: return thb_set_error(THB_E_INVALID, "cp_dim must be 1..4");
+    }
+#undef THB_FWDB
+    THB_LAUNCHED();
+    return THB_OK;
+}
+
+}  // namespace
+
+int thb_csr_forward_bulk(const float* cp, const void* jm, int jm_is_i64, const float* phi, const void* cumsum, int cumsum_is_i64,
+                         float* out, int64_t npoints, int cp_dim, cudaStream_t st) {
+    if (!bulk_enabled() || ((((uintptr_t)phi) | ((uintptr_t)jm)) & 15) != 0) return 1;
+    // Measured on config 3 (16.8 M points, 1.16 G pairs): int32 indices 2.29 ms staged against 2.40 ms on the register path
+    // (instruction-bound now: 1.37 G warp-instructions at 56 % issue, the loads no longer wait); int64 indices 3.24 against
+    // 2.75 ms -- the larger stages leave 8 warps per SM for a body with 64-bit key compares -- so those keep the register
+    // path unless THB_CSR_BULK=2 asks for the staged kernel.
+    if (jm_is_i64 && bulk_mode() != 2) return 1;
+    if (jm_is_i64 && cumsum_is_i64) return launch_fwd_bulk<long long, long long>(cp, jm, phi, cumsum, out, npoints, cp_dim, st);
+    if (jm_is_i64) return launch_fwd_bulk<long long, int>(cp, jm, phi, cumsum, out, npoints, cp_dim, st);
+    if (cumsum_is_i64) return launch_fwd_bulk<int, long long>(cp, jm, phi, cumsum, out, npoints, cp_dim, st);
+    return launch_fwd_bulk<int, int>(cp, jm, phi, cumsum, out, npoints, cp_dim, st);
+}

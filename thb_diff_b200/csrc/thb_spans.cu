@@ -339,6 +339,117 @@ __global__ void __launch_bounds__(256) k_plan_count_fast(const __grid_constant__
     }
 }
 
+// pass 1, vector form of the EXACT case (host-proven span table in shared memory, one finest-cell -> slot lookup):
+// a thread owns FOUR CONSECUTIVE points -- 3 (2-D: 2) LDG.128 and one STG.128 instead of 12 scalar loads and 4 stores --
+// and 113 instructions per point become ~70:
+//   * the staged table holds indices into the staged knots, and the breakpoint after the last cell is replaced by +inf
+//     in the staged copy, so the candidate needs no clamp: cell = lut[bin] + (x >= knot[lut[bin] + 1]);
+//   * bin = umin(float2uint_rz((x - u0) * scale), nb - 1): the same value as the proven formula for every x of the
+//     domain, and a valid index for anything else (NaN / negative -> 0);
+//   * the histogram adds one RED per RUN of equal slots among the thread's four points (neighbouring points share cells;
+//     no __match_any_sync -- a warp-wide match costs more issue slots than the REDs it saves).
+#ifndef THB_COUNT_VEC_GROUPS
+#define THB_COUNT_VEC_GROUPS 2
+#endif
+template <int D>
+__global__ void __launch_bounds__(256) k_plan_count_vec(const __grid_constant__ thb_space_desc sp, const float* __restrict__ params,
+                                                        unsigned n, int32_t* __restrict__ slot_out, int32_t* __restrict__ count) {
+    constexpr int G = THB_COUNT_VEC_GROUPS;   // groups of four points per thread and iteration (independent loads in flight)
+    constexpr int NV = D == 3 ? 3 : 2;        // float4 per group
+    __shared__ float sk[kPlanSmemKnots];
+    __shared__ unsigned s_lut[kPlanSmemLut];  // BYTE offset into sk of the candidate cell's left breakpoint
+    PlanKnots pk;
+    stage_finest_knots(sp, sk, pk);
+    const int L = sp.nlevels - 1;
+    unsigned nbm1[D];
+    const unsigned* lutk[D];
+    float ls[D], u0[D], u1[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        nbm1[k] = (unsigned)(sp.lut_n[k] - 1);
+        lutk[k] = s_lut + sp.lut_off[k];
+        ls[k] = sp.lut_scale[k];
+        u0[k] = pk.u0[k];
+        u1[k] = pk.u1[k];
+        for (int i = threadIdx.x; i < sp.lut_n[k]; i += blockDim.x)
+            s_lut[sp.lut_off[k] + i] = 4u * (unsigned)(sp.span_lut[sp.lut_off[k] + i] + pk.off[k]);
+        if (threadIdx.x == 0) sk[pk.off[k] + sp.ncells[L][k]] = __int_as_float(0x7f800000);
+    }
+    __syncthreads();
+    // 4 * lin = sum_k 4 * (i_k - off_k) * m_k with i_k the index into sk: everything stays in byte offsets
+    const unsigned n1 = sp.ncells[L][1], n2 = D == 3 ? sp.ncells[L][2] : 1;
+    const unsigned m0 = D == 3 ? n1 * n2 : n1, m1 = D == 3 ? n2 : 1;
+    const unsigned lin_base = 0u - 4u * (D == 3 ? ((unsigned)pk.off[0] * n1 + (unsigned)pk.off[1]) * n2 + (unsigned)pk.off[2]
+                                                : (unsigned)pk.off[0] * n1 + (unsigned)pk.off[1]);
+    const char* const skb = reinterpret_cast<const char*>(sk);
+    const char* const fslot = reinterpret_cast<const char*>(sp.finest_slot);
+    // byte offset of the point's finest cell in finest_slot, or 0xffffffff outside the domain (NaN included)
+    auto locate = [&](const float* x) -> unsigned {
+        bool inside = true;
+        unsigned lin = lin_base;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            inside &= (x[k] >= u0[k]) & (x[k] <= u1[k]);
+            const unsigned bin = min(__float2uint_rz((x[k] - u0[k]) * ls[k]), nbm1[k]);
+            const unsigned c0 = lutk[k][bin];
+            const unsigned cc = c0 + ((x[k] >= *reinterpret_cast<const float*>(skb + c0 + 4)) ? 4u : 0u);
+            lin += cc * (k == 0 ? m0 : (k == 1 ? m1 : 1u));
+        }
+        return inside ? lin : 0xffffffffu;
+    };
+    const unsigned nfull = n >> 2;   // groups with four points
+    const unsigned stride = gridDim.x * blockDim.x;
+    const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const float4* __restrict__ p4 = reinterpret_cast<const float4*>(params);
+    for (unsigned g0 = tid; g0 < nfull; g0 += G * stride) {
+        float u[G][4 * D];
+#pragma unroll
+        for (int h = 0; h < G; ++h) {
+            const unsigned g = min(g0 + h * stride, nfull - 1);
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                const float4 q = __ldg(p4 + (size_t)g * NV + v);
+                u[h][4 * v] = q.x; u[h][4 * v + 1] = q.y; u[h][4 * v + 2] = q.z; u[h][4 * v + 3] = q.w;
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < G; ++h) {
+            const unsigned g = g0 + h * stride;
+            if (g >= nfull) break;
+            unsigned lin[4];
+            int sl[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) lin[q] = locate(&u[h][q * D]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) sl[q] = lin[q] != 0xffffffffu ? __ldg(reinterpret_cast<const int32_t*>(fslot + lin[q])) : -1;
+            reinterpret_cast<int4*>(slot_out)[g] = make_int4(sl[0], sl[1], sl[2], sl[3]);
+            int cur = sl[0], cnt = 1;
+#pragma unroll
+            for (int q = 1; q < 4; ++q) {
+                if (sl[q] == cur) {
+                    ++cnt;
+                } else {
+                    if (cur >= 0) atomicAdd(count + cur, cnt);
+                    cur = sl[q];
+                    cnt = 1;
+                }
+            }
+            if (cur >= 0) atomicAdd(count + cur, cnt);
+        }
+    }
+    // the last one to three points
+    const unsigned i = 4u * nfull + tid;
+    if (i < n) {
+        float x[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) x[k] = __ldg(params + (size_t)i * D + k);
+        const unsigned lin = locate(x);
+        const int sl = lin != 0xffffffffu ? __ldg(reinterpret_cast<const int32_t*>(fslot + lin)) : -1;
+        slot_out[i] = sl;
+        if (sl >= 0) atomicAdd(count + sl, 1);
+    }
+}
+
 __global__ void __launch_bounds__(256) k_plan_fixup(const __grid_constant__ thb_space_desc sp, const float* __restrict__ params,
                                                     const int32_t* __restrict__ fail_list, const int32_t* __restrict__ counters,
                                                     int32_t* __restrict__ slot_out, int32_t* __restrict__ count) {
@@ -704,6 +815,27 @@ int plan_ctas_per_sm() {
     return v;
 }
 
+// THB_COUNT_VEC=0 selects the scalar histogram kernel (k_plan_count_fast) where the vector form would run
+bool count_vec_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("THB_COUNT_VEC");
+        v = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    return v != 0;
+}
+
+// the scatter pass alone (the nets can run beside it on another stream: it is HBM-bound, they are issue / latency-bound)
+int scatter_ctas_per_sm() {
+    static int v = 0;
+    if (v == 0) {
+        const char* e = getenv("THB_SCATTER_CTAS_PER_SM");
+        v = e ? atoi(e) : plan_ctas_per_sm();
+        if (v < 1 || v > 32) v = plan_ctas_per_sm();
+    }
+    return v;
+}
+
 }  // namespace
 
 int thb_check_space(const thb_space_desc* sp, const char* who) {
@@ -773,7 +905,9 @@ extern "C" int thb_expand_supports(const thb_space_desc* space, const int32_t* s
     return THB_OK;
 }
 
-extern "C" int thb_plan_build(const thb_space_desc* space, const float* params, const thb_plan_desc* plan, void* stream) {
+// phases: bit 0 = histogram + scan + work items (everything the nets of the touched cells and the item list need),
+// bit 1 = scatter of the points into cell order
+static int plan_build_impl(const thb_space_desc* space, const float* params, const thb_plan_desc* plan, void* stream, int phases) {
     int rc = thb_check_space(space, "thb_plan_build");
     if (rc) return rc;
     THB_REQUIRE(plan && plan->npoints >= 0 && plan->npoints < (int64_t)2147483647, "thb_plan_build: bad point count");
@@ -786,9 +920,10 @@ extern "C" int thb_plan_build(const thb_space_desc* space, const float* params, 
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t n = plan->npoints;
     const int ns = space->nslots;
+    THB_REQUIRE(n == 0 || params, "thb_plan_build: null params");
+    if (phases & 1) {
     THB_CUDA(cudaMemsetAsync(plan->cell_count, 0, sizeof(int32_t) * (ns + 1), st));
     if (n > 0) {
-        THB_REQUIRE(params, "thb_plan_build: null params");
         int finest_knots = 0;
         for (int k = 0; k < space->ndim; ++k) finest_knots += space->knot_len[space->nlevels - 1][k];
         if (space->span_lut && space->finest_slot && finest_knots <= kPlanSmemKnots) {
@@ -797,6 +932,12 @@ extern "C" int thb_plan_build(const thb_space_desc* space, const float* params, 
             const int lut_tot = space->lut_off[space->ndim - 1] + space->lut_n[space->ndim - 1];
             const int g = grid_for(n, 256, plan_ctas_per_sm());
             const bool exact = space->lut_exact != 0;   // spans proven by the host: no verification, no fix-up pass
+            if (exact && lut_tot <= kPlanSmemLut && count_vec_enabled() && ((((uintptr_t)params) | ((uintptr_t)plan->slot)) & 15) == 0) {
+                const int gv = grid_for((n + 3) / 4, 256, plan_ctas_per_sm());   // >= 1 CTA: the tail runs on the first threads
+                if (space->ndim == 3) k_plan_count_vec<3><<<gv, 256, 0, st>>>(*space, params, (unsigned)n, plan->slot, plan->cell_count);
+                else k_plan_count_vec<2><<<gv, 256, 0, st>>>(*space, params, (unsigned)n, plan->slot, plan->cell_count);
+                THB_LAUNCHED();
+            } else {
 #define THB_COUNT(D_, S_)                                                                                                        \
     do {                                                                                                                        \
         if (exact) k_plan_count_fast<D_, S_, true><<<g, 256, 0, st>>>(*space, params, (unsigned)n, plan->slot, plan->cell_count, plan->scratch, plan->counters); \
@@ -809,6 +950,7 @@ extern "C" int thb_plan_build(const thb_space_desc* space, const float* params, 
             if (!exact) {
                 k_plan_fixup<<<thb_num_sms(), 256, 0, st>>>(*space, params, plan->scratch, plan->counters, plan->slot, plan->cell_count);
                 THB_LAUNCHED();
+            }
             }
         } else {
             k_plan_count<<<grid_for(n, 256, 16), 256, 0, st>>>(*space, params, n, plan->slot, plan->cell_count);
@@ -830,16 +972,27 @@ extern "C" int thb_plan_build(const thb_space_desc* space, const float* params, 
     k_plan_items<<<(ns + 255) / 256, 256, 0, st>>>(*space, plan->cell_count, plan->cell_start, plan->cell_cursor, ns, plan->points_per_item,
                                                    plan->max_items, (int4*)plan->items);
     THB_LAUNCHED();
-    if (n > 0) {
+    }
+    if ((phases & 2) && n > 0) {
         if (plan->light) {   // permutation only; plan->scratch is free from here on
-            k_plan_scatter_light<<<grid_for(n, 256, plan_ctas_per_sm()), 256, 0, st>>>(plan->slot, n, plan->cell_cursor, plan->scratch);
+            k_plan_scatter_light<<<grid_for(n, 256, scatter_ctas_per_sm()), 256, 0, st>>>(plan->slot, n, plan->cell_cursor, plan->scratch);
         } else {
-            k_plan_scatter<<<grid_for(n, 256, plan_ctas_per_sm()), 256, 0, st>>>(plan->slot, params, space->ndim, n, plan->cell_cursor,
+            k_plan_scatter<<<grid_for(n, 256, scatter_ctas_per_sm()), 256, 0, st>>>(plan->slot, params, space->ndim, n, plan->cell_cursor,
                                                                  (float4*)plan->sorted_params);
         }
         THB_LAUNCHED();
     }
     return THB_OK;
+}
+
+extern "C" int thb_plan_build(const thb_space_desc* space, const float* params, const thb_plan_desc* plan, void* stream) {
+    return plan_build_impl(space, params, plan, stream, 3);
+}
+
+extern "C" int thb_plan_build_phase(const thb_space_desc* space, const float* params, const thb_plan_desc* plan, int phase,
+                                    void* stream) {
+    THB_REQUIRE(phase == 1 || phase == 2, "thb_plan_build_phase: phase must be 1 (histogram, scan, work items) or 2 (scatter)");
+    return plan_build_impl(space, params, plan, stream, phase);
 }
 
 extern "C" int thb_plan_records(const thb_space_desc* space, const float* params, const thb_plan_desc* plan, void* stream) {

@@ -77,12 +77,17 @@ class Plan:
         self.desc = d
         self.build()
 
-    def build(self):
+    def build(self, phase=None):
+        """phase None: the whole plan.  1: histogram + scan + work items, 2: the scatter (thb_plan_build_phase)."""
         self.version = self.P.version
         self.desc.light = 1 if self.light else 0
         self.desc.params = self.params.data_ptr()
         with _on(self.P.device):
-            check(lib.thb_plan_build(C.byref(self.P.desc()), ptr(self.params), C.byref(self.desc), stream_ptr(self.P.device)), "thb_plan_build")
+            if phase is None:
+                check(lib.thb_plan_build(C.byref(self.P.desc()), ptr(self.params), C.byref(self.desc), stream_ptr(self.P.device)), "thb_plan_build")
+            else:
+                check(lib.thb_plan_build_phase(C.byref(self.P.desc()), ptr(self.params), C.byref(self.desc), int(phase),
+                                               stream_ptr(self.P.device)), "thb_plan_build_phase")
 
     def ensure_records(self):
         """The 16-byte point records of a light plan (thb_plan_records), built once per plan build."""
@@ -267,6 +272,16 @@ def plan_and_nets(P, plan, ctrl_pts, with_derivatives=False, overlap=True):
     side = getattr(P, "_side_stream", None)
     if side is None:
         side = P._side_stream = torch.cuda.Stream(device=P.device)
+    if overlap == "scatter":
+        # the nets (issue / latency-bound) beside the SCATTER pass alone (HBM-bound): the histogram pass is issue-bound
+        # itself and gains nothing from company; the nets are built for the cells that hold points
+        plan.build(phase=1)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            nets = cell_nets(P, ctrl_pts, with_derivatives, plan=plan, ctas_per_sm=int(_os.environ.get("THB_OVERLAP_NETS_CTAS", "0")))
+        plan.build(phase=2)
+        cur.wait_stream(side)
+        return nets
     side.wait_stream(cur)
     with torch.cuda.stream(side):
         # (capping the resident CTAs of the nets kernel -- THB_NETS_CTAS -- so that the plan kernels find registers beside
