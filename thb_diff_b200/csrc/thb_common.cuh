@@ -205,3 +205,5 @@ THB_DEV void mbar_wait(unsigned long long* bar, unsigned parity) {
 // (misaligned arrays, switched off): the caller then runs the register-path kernels of thb_eval_csr.cu
 int thb_csr_forward_bulk(const float* cp, const void* jm, int jm_is_i64, const float* phi, const void* cumsum, int cumsum_is_i64,
                          float* out, int64_t npoints, int cp_dim, cudaStream_t st);
+int thb_csr_backward_bulk(const float* grad_out, const void* jm, int jm_is_i64, const float* phi, const void* cumsum, int cumsum_is_i64,
+                          float* grad_ctrl_pts, int64_t npoints, int cp_dim, cudaStream_t st);

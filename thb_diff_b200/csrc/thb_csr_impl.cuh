@@ -136,4 +136,92 @@ THB_DEV void fwd_points(const float* __restrict__ cp, const JT* __restrict__ jm,
 }
 
 
+constexpr int kStrips = kFwdStrips;  // support lists up to 160 entries are aggregated across points
+
+// grad_ctrl_pts[Jm[j]] += PHI[j] * grad_out[i].  A warp owns a run of consecutive points; per point the lanes read the
+// segment coalesced, NPT points at a time (all loads first), body specialised for the number of strips.  While consecutive
+// points have the same support list the products are accumulated in registers; the atomics are issued only when the list
+// changes (or the warp's run ends): cp_dim * S atomics per RUN of points instead of per point -- the warp-aggregated
+// scatter-add.
+template <typename JT, int CPD>
+struct BwdCache {
+    JT key[kStrips];
+    float acc[kStrips][CPD];
+    int runS;
+};
+
+// (Vector reductions -- red.global.add.v2 / .v4.f32, a row of three floats as one 8-byte pair plus one scalar -- were
+// measured slower than three scalar reductions here, and the second code path made the kernel miss in the instruction
+// cache: 4.1 instead of 3.0 ms on config 3.  The kernel is kept small on purpose.)
+template <typename JT, int CPD>
+THB_DEV void bwd_flush(BwdCache<JT, CPD>& c, float* __restrict__ gcp) {
+#pragma unroll
+    for (int s = 0; s < kStrips; ++s) {
+        if (s * 32 < c.runS) {   // warp-uniform
+            if (c.key[s] >= 0) {
+#pragma unroll
+                for (int k = 0; k < CPD; ++k) atomicAdd(gcp + (int64_t)c.key[s] * CPD + k, c.acc[s][k]);
+            }
+#pragma unroll
+            for (int k = 0; k < CPD; ++k) c.acc[s][k] = 0.0f;
+        }
+        c.key[s] = (JT)-1;
+    }
+    c.runS = -1;
+}
+
+#ifndef THB_BWD_LD
+#define THB_BWD_LD __ldg   // (streaming __ldcs loads measured slower here: 4.1 vs 3.0 ms on config 3, int32)
+#endif
+// STAGED: gout / jm / phi point into shared memory (gout: the rows of the chunk, row0 relative to it)
+template <typename JT, int CPD, int NS, int NPT, bool STAGED = false>
+THB_DEV void bwd_points(const float* __restrict__ gout, const JT* __restrict__ jm, const float* __restrict__ phi, int64_t base,
+                        int64_t row0, int nvalid, const int (&ob)[NPT], const int (&S)[NPT], BwdCache<JT, CPD>& c,
+                        float* __restrict__ gcp, int lane) {
+    JT cj[NPT][NS];
+    float cw[NPT][NS], g[NPT][CPD];
+#pragma unroll
+    for (int h = 0; h < NPT; ++h) {
+        const JT* pj = jm + base + ob[h] + lane;
+        const float* pw = phi + base + ob[h] + lane;
+        const int64_t row = row0 + (h < nvalid ? h : 0);
+#pragma unroll
+        for (int k = 0; k < CPD; ++k) g[h][k] = STAGED ? lds_f32(gout + row * CPD + k) : __ldg(gout + row * CPD + k);
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            const bool ok = s * 32 + lane < S[h];
+            if (STAGED) {
+                cj[h][s] = (JT)-1;
+                cw[h][s] = 0.0f;
+                if (ok) {
+                    cj[h][s] = lds_index<JT>(pj + s * 32);
+                    cw[h][s] = lds_f32(pw + s * 32);
+                }
+            } else {
+                cj[h][s] = ok ? THB_BWD_LD(pj + s * 32) : (JT)-1;
+                cw[h][s] = ok ? THB_BWD_LD(pw + s * 32) : 0.0f;
+            }
+        }
+    }
+#pragma unroll
+    for (int h = 0; h < NPT; ++h) {
+        if (h >= nvalid) break;   // warp-uniform
+        bool same = S[h] == c.runS;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) same = same && (cj[h][s] == c.key[s]);
+        if (!__all_sync(0xffffffffu, same)) {
+            bwd_flush<JT, CPD>(c, gcp);
+#pragma unroll
+            for (int s = 0; s < NS; ++s) c.key[s] = cj[h][s];
+            c.runS = S[h];
+        }
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+#pragma unroll
+            for (int k = 0; k < CPD; ++k) c.acc[s][k] = fmaf(cw[h][s], g[h][k], c.acc[s][k]);
+        }
+    }
+}
+
+
 }  // namespace thb_csr

@@ -116,83 +116,6 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_csr_forward(const float* 
     }
 }
 
-constexpr int kStrips = kFwdStrips;  // support lists up to 160 entries are aggregated across points
-
-// grad_ctrl_pts[Jm[j]] += PHI[j] * grad_out[i].  A warp owns a run of consecutive points; per point the lanes read the
-// segment coalesced, NPT points at a time (all loads first), body specialised for the number of strips.  While consecutive
-// points have the same support list the products are accumulated in registers; the atomics are issued only when the list
-// changes (or the warp's run ends): cp_dim * S atomics per RUN of points instead of per point -- the warp-aggregated
-// scatter-add.
-template <typename JT, int CPD>
-struct BwdCache {
-    JT key[kStrips];
-    float acc[kStrips][CPD];
-    int runS;
-};
-
-// (Vector reductions -- red.global.add.v2 / .v4.f32, a row of three floats as one 8-byte pair plus one scalar -- were
-// measured slower than three scalar reductions here, and the second code path made the kernel miss in the instruction
-// cache: 4.1 instead of 3.0 ms on config 3.  The kernel is kept small on purpose.)
-template <typename JT, int CPD>
-THB_DEV void bwd_flush(BwdCache<JT, CPD>& c, float* __restrict__ gcp) {
-#pragma unroll
-    for (int s = 0; s < kStrips; ++s) {
-        if (s * 32 < c.runS) {   // warp-uniform
-            if (c.key[s] >= 0) {
-#pragma unroll
-                for (int k = 0; k < CPD; ++k) atomicAdd(gcp + (int64_t)c.key[s] * CPD + k, c.acc[s][k]);
-            }
-#pragma unroll
-            for (int k = 0; k < CPD; ++k) c.acc[s][k] = 0.0f;
-        }
-        c.key[s] = (JT)-1;
-    }
-    c.runS = -1;
-}
-
-#ifndef THB_BWD_LD
-#define THB_BWD_LD __ldg   // (streaming __ldcs loads measured slower here: 4.1 vs 3.0 ms on config 3, int32)
-#endif
-template <typename JT, int CPD, int NS, int NPT>
-THB_DEV void bwd_points(const float* __restrict__ gout, const JT* __restrict__ jm, const float* __restrict__ phi, int64_t base,
-                        int64_t row0, int nvalid, const int (&ob)[NPT], const int (&S)[NPT], BwdCache<JT, CPD>& c,
-                        float* __restrict__ gcp, int lane) {
-    JT cj[NPT][NS];
-    float cw[NPT][NS], g[NPT][CPD];
-#pragma unroll
-    for (int h = 0; h < NPT; ++h) {
-        const JT* pj = jm + base + ob[h] + lane;
-        const float* pw = phi + base + ob[h] + lane;
-        const int64_t row = row0 + (h < nvalid ? h : 0);
-#pragma unroll
-        for (int k = 0; k < CPD; ++k) g[h][k] = __ldg(gout + row * CPD + k);
-#pragma unroll
-        for (int s = 0; s < NS; ++s) {
-            const bool ok = s * 32 + lane < S[h];
-            cj[h][s] = ok ? THB_BWD_LD(pj + s * 32) : (JT)-1;
-            cw[h][s] = ok ? THB_BWD_LD(pw + s * 32) : 0.0f;
-        }
-    }
-#pragma unroll
-    for (int h = 0; h < NPT; ++h) {
-        if (h >= nvalid) break;   // warp-uniform
-        bool same = S[h] == c.runS;
-#pragma unroll
-        for (int s = 0; s < NS; ++s) same = same && (cj[h][s] == c.key[s]);
-        if (!__all_sync(0xffffffffu, same)) {
-            bwd_flush<JT, CPD>(c, gcp);
-#pragma unroll
-            for (int s = 0; s < NS; ++s) c.key[s] = cj[h][s];
-            c.runS = S[h];
-        }
-#pragma unroll
-        for (int s = 0; s < NS; ++s) {
-#pragma unroll
-            for (int k = 0; k < CPD; ++k) c.acc[s][k] = fmaf(cw[h][s], g[h][k], c.acc[s][k]);
-        }
-    }
-}
-
 template <typename JT, typename CT, int CPD>
 __global__ void __launch_bounds__(kWarpsPerCta * 32) k_csr_backward(const float* __restrict__ gout, const JT* __restrict__ jm,
                                                                       const float* __restrict__ phi,
@@ -376,6 +299,10 @@ extern "C" int thb_eval_backward(const float* grad_out, const void* jm, int jm_i
     }
     if (npoints == 0) return THB_OK;
     THB_REQUIRE(grad_out && jm && phi && cumsum, "thb_eval_backward: null pointer");
+    {   // bulk-staged kernel (thb_eval_bulk.cu) whenever the arrays allow 16-byte copies
+        const int rc = thb_csr_backward_bulk(grad_out, jm, jm_is_i64, phi, cumsum, cumsum_is_i64, grad_ctrl_pts, npoints, cp_dim, st);
+        if (rc != 1) return rc;
+    }
     if (jm_is_i64 && cumsum_is_i64) return launch_bwd<long long, long long>(grad_out, jm, phi, cumsum, grad_ctrl_pts, npoints, cp_dim, st);
     if (jm_is_i64) return launch_bwd<long long, int>(grad_out, jm, phi, cumsum, grad_ctrl_pts, npoints, cp_dim, st);
     if (cumsum_is_i64) return launch_bwd<int, long long>(grad_out, jm, phi, cumsum, grad_ctrl_pts, npoints, cp_dim, st);

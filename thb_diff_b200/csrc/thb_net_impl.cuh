@@ -1490,15 +1490,18 @@ struct BasisSmem {
     float rk[3][8];
     float4 prec[2][32];
     float4 fac[6][32];        // [2 * dim + derivative][point] -> the (up to) four 1-D values of that point
-    long long poff[32];       // row offset of the point in PHI
+    long long poff[32];       // BYTE offset of the point's row in PHI (a store address is one IMAD.WIDE: index * 4 + row)
     float stage[32][33];      // [point][support of the chunk]
     float4 vec[32][3];        // factor vectors of the chunk's rank-one supports (lane = support on the way in)
     float tile[64];           // one full tile at a time
     int ref[32];              // tiled_ref of the chunk
 };
 
+#ifndef THB_BASIS_MINB
+#define THB_BASIS_MINB 16   // one-warp CTAs per SM of k_basis_rows (11 KB of shared memory each: 20 fit)
+#endif
 template <int N0, int N1, int N2, bool DER>
-__global__ void __launch_bounds__(kThreads, 16) k_basis_rows(const __grid_constant__ thb_space_desc sp, const __grid_constant__ Args ar) {
+__global__ void __launch_bounds__(kThreads, THB_BASIS_MINB) k_basis_rows(const __grid_constant__ thb_space_desc sp, const __grid_constant__ Args ar) {
     using SH = Shp<N0, N1, N2>;
     constexpr int T = SH::T, TS = SH::TS;
     constexpr int NT = (T + 31) / 32;
@@ -1578,7 +1581,7 @@ __global__ void __launch_bounds__(kThreads, 16) k_basis_rows(const __grid_consta
                 const float4 rec = sm.prec[pb][lane];
                 const float u[3] = {rec.x, rec.y, rec.z};
                 bs.eval(u, sm.knots[tb], sm.rk);
-                sm.poff[lane] = lane < nval ? (long long)__ldg(ar.offsets + __float_as_int(rec.w)) : 0;
+                sm.poff[lane] = lane < nval ? 4ll * (long long)__ldg(ar.offsets + __float_as_int(rec.w)) : 0;
                 float v[6][4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -1596,7 +1599,7 @@ __global__ void __launch_bounds__(kThreads, 16) k_basis_rows(const __grid_consta
             __syncwarp();
             for (int chi = 0; chi < ar.nch; ++chi) {
                 const int ch = ar.channels[chi];
-                float* const outp = ar.out[chi];
+                char* const outp = reinterpret_cast<char*>(ar.out[chi]);
                 const int q0 = (DER && (ch & 1)) ? 1 : 0, q1 = (DER && (ch & 2)) ? 3 : 2, q2 = (DER && (ch & 4)) ? 5 : 4;
                 if (it.ndir > 0) {
                     // own-level supports: lane = window entry
@@ -1609,20 +1612,20 @@ __global__ void __launch_bounds__(kThreads, 16) k_basis_rows(const __grid_consta
                         const float* fcp = fc + tc[0];
 #pragma unroll 4
                         for (int pt = 0; pt < nval; ++pt) {
-                            float* dst = outp + sm.poff[pt];
+                            float* dst = reinterpret_cast<float*>(outp + sm.poff[pt]);
                             const float2 aa = fa2[pt * 2];
                             const float bc = fbp[pt * 4] * fcp[pt * 4];
-                            if (dpos[0] >= 0) dst[dpos[0]] = aa.x * bc;
-                            if (dpos[1] >= 0) dst[dpos[1]] = aa.y * bc;
+                            if (dpos[0] >= 0) dst[(unsigned)dpos[0]] = aa.x * bc;
+                            if (dpos[1] >= 0) dst[(unsigned)dpos[1]] = aa.y * bc;
                         }
                     } else {
 #pragma unroll 4
                         for (int pt = 0; pt < nval; ++pt) {
-                            float* dst = outp + sm.poff[pt];
+                            float* dst = reinterpret_cast<float*>(outp + sm.poff[pt]);
 #pragma unroll
                             for (int h = 0; h < NT; ++h) {
                                 const float val = fa[pt * 4 + ta[h]] * fb[pt * 4 + tb_[h]] * fc[pt * 4 + tc[h]];
-                                if (dpos[h] >= 0) dst[dpos[h]] = val;
+                                if (dpos[h] >= 0) dst[(unsigned)dpos[h]] = val;
                             }
                         }
                     }
@@ -1679,7 +1682,7 @@ __global__ void __launch_bounds__(kThreads, 16) k_basis_rows(const __grid_consta
                     __syncwarp();
                     if (lane < ns) {
 #pragma unroll 4
-                        for (int pt = 0; pt < nval; ++pt) outp[sm.poff[pt] + it.ndir + c0 + lane] = sm.stage[pt][lane];
+                        for (int pt = 0; pt < nval; ++pt) reinterpret_cast<float*>(outp + sm.poff[pt])[(unsigned)(it.ndir + c0 + lane)] = sm.stage[pt][lane];
                     }
                 }
             }
