@@ -235,6 +235,9 @@ def extras(sp, P, params, cp, hbm_peak):
                     "speedup_forward": rf / tf, "speedup_backward": rb / tb,
                     "what": "THB/THB_extensions/compute_pts_cuda_kernels.cu compiled unmodified (oracle/_ref/cuda), same tensors"}
                 del o_ref, o_our
+        elif "reference_cuda_kernels_sm100a" in out:   # the same work with the 32-bit indices this library also accepts
+            rc = out["reference_cuda_kernels_sm100a"]
+            rc["speedup_forward_int32_indices"], rc["speedup_backward_int32_indices"] = rc["forward_ms"] / tf, rc["backward_ms"] / tb
         del Jm
     tfb = time_cuda(lambda: engine.eval_fused_backward(P, supp.plan, g))
     tfb_pp = time_cuda(lambda: engine.eval_fused_backward(P, supp.plan, g, formulation="per_point"))
@@ -886,6 +889,8 @@ def main():
                 rc = ex["reference_cuda_kernels_sm100a"]
                 r["ref_cuda_fwd_ms"], r["ref_cuda_bwd_ms"] = rc["forward_ms"], rc["backward_ms"]
                 r["speedup_vs_ref_cuda_fwd"], r["speedup_vs_ref_cuda_bwd"] = rc["speedup_forward"], rc["speedup_backward"]
+                if "speedup_forward_int32_indices" in rc:
+                    r["speedup_vs_ref_cuda_fwd_i32"], r["speedup_vs_ref_cuda_bwd_i32"] = rc["speedup_forward_int32_indices"], rc["speedup_backward_int32_indices"]
             r["fused_backward_ms"] = ex["fused_backward"]["ms"]
         except Exception as e:  # secondary numbers must never take the headline down -- but they must be seen
             import traceback

@@ -67,7 +67,7 @@ def test_long_segments_and_misaligned_views(idx_dtype):
 
     rng = np.random.default_rng(5)
     nCP = 300
-    ns = np.concatenate([rng.integers(0, 90, size=70), [5000, 0, 2304, 2305, 17], rng.integers(60, 130, size=100), [3]])
+    ns = np.concatenate([rng.integers(0, 90, size=70), [5000, 0, 2304, 2305, 17, 768, 769, 767], rng.integers(60, 130, size=100), [3]])
     Jm = rng.integers(0, nCP, size=int(ns.sum())).astype(np.int64)
     phi = rng.random(len(Jm)).astype(np.float32)
     cs = np.cumsum(ns).astype(np.int64)
@@ -92,7 +92,7 @@ def test_staged_forward_with_int64_indices():
         "from oracle import thb_oracle as O\n"
         "from thb_diff_b200 import THB_eval\n"
         "rng = np.random.default_rng(3)\n"
-        "ns = np.concatenate([rng.integers(0, 140, size=400), [3000, 0, 1152, 1153], rng.integers(60, 70, size=300)])\n"
+        "ns = np.concatenate([rng.integers(0, 140, size=400), [3000, 0, 1152, 1153, 768, 769], rng.integers(60, 70, size=300)])\n"
         "Jm = rng.integers(0, 500, size=int(ns.sum())).astype(np.int64); phi = rng.random(len(Jm)).astype(np.float32)\n"
         "cs = np.cumsum(ns).astype(np.int64); cp = rng.standard_normal((500, 3)).astype(np.float32)\n"
         "out = THB_eval.forward(torch.from_numpy(cp).cuda(), torch.from_numpy(Jm).cuda(), torch.from_numpy(phi).cuda(), torch.from_numpy(cs).cuda())\n"

@@ -65,20 +65,22 @@ THB_DEV void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];
 
 // NPT points starting at entry offsets ob[h] (relative to base), lengths S[h] <= 32 * NS; a[h][k] = per-lane partial sums
 // explicit shared-memory loads (volatile: they stay behind the mbarrier wait that makes the staged data visible)
-THB_DEV float lds_f32(const float* p) {
+// (32-bit shared-window addresses: one conversion per point, the strips are immediates)
+THB_DEV unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+THB_DEV float lds_f32(unsigned a) {
     float v;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"((unsigned)__cvta_generic_to_shared(p)));
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
     return v;
 }
 template <typename JT>
-THB_DEV JT lds_index(const JT* p) {
+THB_DEV JT lds_index(unsigned a) {
     if (sizeof(JT) == 8) {
         long long v;
-        asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"((unsigned)__cvta_generic_to_shared(p)));
+        asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(a));
         return (JT)v;
     } else {
         int v;
-        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(p)));
+        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a));
         return (JT)v;
     }
 }
@@ -93,6 +95,7 @@ THB_DEV void fwd_points(const float* __restrict__ cp, const JT* __restrict__ jm,
     for (int h = 0; h < NPT; ++h) {
         const JT* pj = jm + base + ob[h] + lane;
         const float* pw = phi + base + ob[h] + lane;
+        const unsigned aj = STAGED ? smem_addr(pj) : 0u, aw = STAGED ? smem_addr(pw) : 0u;
 #pragma unroll
         for (int s = 0; s < NS; ++s) {
             const bool ok = s * 32 + lane < S[h];
@@ -100,8 +103,8 @@ THB_DEV void fwd_points(const float* __restrict__ cp, const JT* __restrict__ jm,
                 cj[h][s] = (JT)-1;
                 cw[h][s] = 0.0f;
                 if (ok) {
-                    cj[h][s] = lds_index<JT>(pj + s * 32);
-                    cw[h][s] = lds_f32(pw + s * 32);
+                    cj[h][s] = lds_index<JT>(aj + s * 32 * (unsigned)sizeof(JT));
+                    cw[h][s] = lds_f32(aw + s * 128u);
                 }
             } else {
                 cj[h][s] = ok ? __ldcs(pj + s * 32) : (JT)-1;   // read once: streaming (evict-first) loads keep the control
@@ -186,7 +189,7 @@ THB_DEV void bwd_points(const float* __restrict__ gout, const JT* __restrict__ j
         const float* pw = phi + base + ob[h] + lane;
         const int64_t row = row0 + (h < nvalid ? h : 0);
 #pragma unroll
-        for (int k = 0; k < CPD; ++k) g[h][k] = STAGED ? lds_f32(gout + row * CPD + k) : __ldg(gout + row * CPD + k);
+        for (int k = 0; k < CPD; ++k) g[h][k] = STAGED ? lds_f32(smem_addr(gout + row * CPD) + 4u * k) : __ldg(gout + row * CPD + k);
 #pragma unroll
         for (int s = 0; s < NS; ++s) {
             const bool ok = s * 32 + lane < S[h];
@@ -194,8 +197,8 @@ THB_DEV void bwd_points(const float* __restrict__ gout, const JT* __restrict__ j
                 cj[h][s] = (JT)-1;
                 cw[h][s] = 0.0f;
                 if (ok) {
-                    cj[h][s] = lds_index<JT>(pj + s * 32);
-                    cw[h][s] = lds_f32(pw + s * 32);
+                    cj[h][s] = lds_index<JT>(smem_addr(pj) + s * 32 * (unsigned)sizeof(JT));
+                    cw[h][s] = lds_f32(smem_addr(pw) + s * 128u);
                 }
             } else {
                 cj[h][s] = ok ? THB_BWD_LD(pj + s * 32) : (JT)-1;

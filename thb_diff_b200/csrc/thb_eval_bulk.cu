@@ -23,7 +23,9 @@ namespace {
 using namespace thb_csr;
 
 #ifndef THB_BULK_CAP
-#define THB_BULK_CAP 1152   // entries per stage: 16 points x 72 supports
+#define THB_BULK_CAP 768   // entries per stage (~11 points of config 3).  Measured on config 3, forward / backward ms with int32 indices:
+                           // 2304 entries, 6 warps per SM: 2.48 / -; 1152, 12 warps: 2.28 / 2.68; 768, 16 warps: 2.10 / 2.56; 640, 20 warps
+                           // and two points in flight: 2.17 / 2.60 -- registers (128 at 16 warps) bound the number of warps
 #endif
 constexpr int kCap = THB_BULK_CAP;
 constexpr int kSlack = 8;   // alignment shift (<= 3) + rounding up to 16 bytes (<= 3)
@@ -47,10 +49,10 @@ struct BulkWarpBwd {
     unsigned long long bar[2];
 };
 #ifndef THB_BULK_WARPS32
-#define THB_BULK_WARPS32 12
+#define THB_BULK_WARPS32 16
 #endif
 #ifndef THB_BULK_WARPS64
-#define THB_BULK_WARPS64 8
+#define THB_BULK_WARPS64 12
 #endif
 template <typename JT>
 struct BulkCfg {
@@ -92,6 +94,8 @@ THB_DEV Chunk describe(int64_t end, int64_t p, int64_t p1, int64_t base, int64_t
     c.my_end = (int)min(rel, (int64_t)0x7fffffff);
     const int64_t tot = __shfl_sync(0xffffffffu, rel, m - 1);
     c.npairs = (int)min(tot, (int64_t)0x7fffffff);
+    if (lane >= m) c.my_end = c.npairs;   // lanes past the chunk describe empty segments at its end: no range checks when the
+                                          // kernels walk the points
     const int up = __shfl_up_sync(0xffffffffu, c.my_end, 1);
     c.my_beg = lane == 0 ? 0 : up;
     if (c.bulk) {   // the copies are rounded out to 16 bytes: they must stay inside the arrays
@@ -155,7 +159,11 @@ __global__ void __launch_bounds__(32 * BulkCfg<JT>::kWarps, 1) k_csr_forward_bul
     int64_t end_after = load_end<CT>(cumsum, p_after, p1, lane);   // consumed after the next compute phase
     int s = 0;
     unsigned parity = 0u;   // bit s: phase of stage s
+#ifdef THB_BULK_NPT
+    constexpr int NPT = THB_BULK_NPT;
+#else
     constexpr int NPT = 4;
+#endif
     FwdCache<JT, CPD> c;
     c.runS = -1;
 #pragma unroll
@@ -185,7 +193,7 @@ __global__ void __launch_bounds__(32 * BulkCfg<JT>::kWarps, 1) k_csr_forward_bul
 #pragma unroll
                     for (int h = 0; h < NPT; ++h) {
                         const int i = i0 + j0 + h;
-                        const int e = i < np ? __shfl_sync(0xffffffffu, cur.my_end, i & 31) : beg;
+                        const int e = __shfl_sync(0xffffffffu, cur.my_end, i);   // i < 32; lanes >= np hold the chunk's end
                         ob[h] = beg;
                         S[h] = e - beg;
                         beg = e;
@@ -263,7 +271,11 @@ __global__ void __launch_bounds__(32 * BulkCfg<JT>::kWarps, 1) k_csr_backward_bu
     const int64_t gtot = npoints * CPD;
     constexpr int per16 = 16 / (int)sizeof(JT);
     constexpr int ej = (int)sizeof(JT);
+#ifdef THB_BULK_NPT
+    constexpr int NPT = sizeof(JT) == 8 ? 2 : THB_BULK_NPT;
+#else
     constexpr int NPT = sizeof(JT) == 8 ? 2 : 4;
+#endif
     Chunk cur = describe(load_end<CT>(cumsum, p0, p1, lane), p0, p1, p0 ? (int64_t)cumsum[p0 - 1] : 0, nnz, ej, lane, gtot, CPD);
     if (cur.bulk) issue<JT>(cur, sw.st[0], &sw.bar[0], phi, jm, lane, sw.g[0], gout, CPD);
     Chunk nxt = describe(load_end<CT>(cumsum, cur.p + cur.m, p1, lane), cur.p + cur.m, p1, cur.base + cur.npairs, nnz, ej, lane, gtot, CPD);
@@ -294,7 +306,7 @@ __global__ void __launch_bounds__(32 * BulkCfg<JT>::kWarps, 1) k_csr_backward_bu
             int ob[NPT], S[NPT], smax = 0;
 #pragma unroll
             for (int h = 0; h < NPT; ++h) {
-                const int e = i + h < np ? __shfl_sync(0xffffffffu, cur.my_end, (i + h) & 31) : beg;
+                const int e = __shfl_sync(0xffffffffu, cur.my_end, i + h);   // < 32; lanes >= np hold the chunk's end
                 ob[h] = beg;
                 S[h] = e - beg;
                 beg = e;
@@ -437,9 +449,9 @@ int thb_csr_backward_bulk(const float* grad_out, const void* jm, int jm_is_i64, 
 int thb_csr_forward_bulk(const float* cp, const void* jm, int jm_is_i64, const float* phi, const void* cumsum, int cumsum_is_i64,
                          float* out, int64_t npoints, int cp_dim, cudaStream_t st) {
     if (!bulk_enabled() || ((((uintptr_t)phi) | ((uintptr_t)jm)) & 15) != 0) return 1;
-    // Measured on config 3 (16.8 M points, 1.16 G pairs): int32 indices 2.29 ms staged against 2.40 ms on the register path
-    // (instruction-bound now: 1.37 G warp-instructions at 56 % issue, the loads no longer wait); int64 indices 3.24 against
-    // 2.75 ms -- the larger stages leave 8 warps per SM for a body with 64-bit key compares -- so those keep the register
+    // Measured on config 3 (16.8 M points, 1.16 G pairs): int32 indices 2.10 ms staged against 2.40 ms on the register path
+    // (instruction-bound now: 1.37 G warp-instructions at 56 % issue, the loads no longer wait); int64 indices 2.91 against
+    // 2.75 ms -- the larger stages leave 12 warps per SM for a body with 64-bit key compares -- so those keep the register
     // path unless THB_CSR_BULK=2 asks for the staged kernel.
     if (jm_is_i64 && bulk_mode() != 2) return 1;
     if (jm_is_i64 && cumsum_is_i64) return launch_fwd_bulk<long long, long long>(cp, jm, phi, cumsum, out, npoints, cp_dim, st);
