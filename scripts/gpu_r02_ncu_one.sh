@@ -8,3 +8,6 @@ echo "ncu rc=$?"; tail -n 2 gpurun_out/ncu_$TAG.log
 python scripts/ncu_raw_summary.py /tmp/prof/$TAG.ncu-rep > gpurun_out/ncu_raw_$TAG.txt
 python scripts/ncu_line_summary.py /tmp/prof/$TAG.ncu-rep $K 24 > gpurun_out/ncu_lines_$TAG.txt 2>&1
 cat gpurun_out/ncu_raw_$TAG.txt gpurun_out/ncu_lines_$TAG.txt
+ncu -i /tmp/prof/$TAG.ncu-rep --page source --csv --kernel-name regex:$K > /tmp/prof/$TAG.src.csv 2>/dev/null
+python scripts/ncu_src_summary.py /tmp/prof/$TAG.src.csv > gpurun_out/ncu_sass_mix_$TAG.txt 2>&1
+cat gpurun_out/ncu_sass_mix_$TAG.txt

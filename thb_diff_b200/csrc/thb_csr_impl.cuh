@@ -156,18 +156,20 @@ struct BwdCache {
 // (Vector reductions -- red.global.add.v2 / .v4.f32, a row of three floats as one 8-byte pair plus one scalar -- were
 // measured slower than three scalar reductions here, and the second code path made the kernel miss in the instruction
 // cache: 4.1 instead of 3.0 ms on config 3.  The kernel is kept small on purpose.)
+// Straight-line: every strip tests its own key (strips past the run hold -1) and the reductions are predicated -- the
+// flush is inlined at every point of every specialised body, and a branch per strip made it ~150 instructions with the
+// register moves at the joins (a quarter of the kernel's instructions on config 3, where a run is ~7 points).
 template <typename JT, int CPD>
 THB_DEV void bwd_flush(BwdCache<JT, CPD>& c, float* __restrict__ gcp) {
 #pragma unroll
     for (int s = 0; s < kStrips; ++s) {
-        if (s * 32 < c.runS) {   // warp-uniform
-            if (c.key[s] >= 0) {
+        if (c.key[s] >= 0) {
+            float* d = gcp + (int64_t)c.key[s] * CPD;
 #pragma unroll
-                for (int k = 0; k < CPD; ++k) atomicAdd(gcp + (int64_t)c.key[s] * CPD + k, c.acc[s][k]);
-            }
-#pragma unroll
-            for (int k = 0; k < CPD; ++k) c.acc[s][k] = 0.0f;
+            for (int k = 0; k < CPD; ++k) atomicAdd(d + k, c.acc[s][k]);
         }
+#pragma unroll
+        for (int k = 0; k < CPD; ++k) c.acc[s][k] = 0.0f;
         c.key[s] = (JT)-1;
     }
     c.runS = -1;
