@@ -121,6 +121,35 @@ def test_c3_full_size_properties(c3):
     assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), float(Ax.double().norm() * g.double().norm()))
 
 
+def test_plan_slots_at_full_size_match_the_span_kernel(c3):
+    """Batches of >= 4 M points take the vector histogram kernel (four points per thread, proven span table): its slots
+    must equal those of thb_active_span (binary search + level walk, an independent kernel) bit for bit -- grid points,
+    random points, points on breakpoints and the domain ends, outside points, NaN, and a tail that is not a multiple of 4."""
+    from thb_diff_b200 import bspline_funcs as B
+    from thb_diff_b200 import engine
+
+    sp, P, cp = c3
+    g = torch.Generator(device="cuda").manual_seed(7)
+    grid = B.grid_parametric_coordinates_device((256, 256, 256))
+    rnd = torch.rand((4_200_003, 3), device="cuda", generator=g)
+    kn = torch.from_numpy(np.unique(np.asarray(sp.knotvectors[len(sp.knotvectors) - 1][0], dtype=np.float32))).cuda()
+    idx = torch.randint(0, len(kn), (300_000, 3), device="cuda", generator=g)
+    onk = kn[idx]
+    onk[::3] = torch.nextafter(onk[::3], torch.zeros_like(onk[::3]))
+    onk[1::3] = torch.nextafter(onk[1::3], torch.ones_like(onk[1::3]) * 2)
+    special = torch.tensor([[0.0, 0.0, 0.0], [1.0, 1.0, 1.0], [1.0, 0.5, 0.0], [-1e-7, 0.5, 0.5], [0.5, 1.0000001, 0.5],
+                            [float("nan"), 0.5, 0.5], [0.5, 0.5, float("inf")]], device="cuda")
+    for prm in (grid, torch.cat([rnd, onk, special]).contiguous()):
+        plan = engine.Plan(P, prm)
+        ref, _ = engine.active_span(P, prm)
+        assert torch.equal(plan.slot[: prm.shape[0]], ref)
+        n_in = int((ref >= 0).sum())
+        assert int(plan.counters[2]) == n_in
+        cnt = torch.bincount(ref[ref >= 0].long(), minlength=P.nslots)
+        assert torch.equal(plan.cell_count[: P.nslots].long(), cnt)
+        del plan
+
+
 def test_sharded_fit_reduces_loss(c3):
     from thb_diff_b200 import configs
     from thb_diff_b200.distributed import ShardedFit

@@ -348,6 +348,10 @@ __global__ void __launch_bounds__(256) k_plan_count_fast(const __grid_constant__
 //     domain, and a valid index for anything else (NaN / negative -> 0);
 //   * the histogram adds one RED per RUN of equal slots among the thread's four points (neighbouring points share cells;
 //     no __match_any_sync -- a warp-wide match costs more issue slots than the REDs it saves).
+#ifndef THB_COUNT_VEC_MIN
+#define THB_COUNT_VEC_MIN 4000000   // points from which the vector histogram kernel is used
+#endif
+constexpr long long kCountVecMin = THB_COUNT_VEC_MIN;
 #ifndef THB_COUNT_VEC_GROUPS
 #define THB_COUNT_VEC_GROUPS 2
 #endif
@@ -932,7 +936,11 @@ static int plan_build_impl(const thb_space_desc* space, const float* params, con
             const int lut_tot = space->lut_off[space->ndim - 1] + space->lut_n[space->ndim - 1];
             const int g = grid_for(n, 256, plan_ctas_per_sm());
             const bool exact = space->lut_exact != 0;   // spans proven by the host: no verification, no fix-up pass
-            if (exact && lut_tot <= kPlanSmemLut && count_vec_enabled() && ((((uintptr_t)params) | ((uintptr_t)plan->slot)) & 15) == 0) {
+            // (small batches -- a rank's slab, a chunk of the host pipeline -- keep the scalar kernel, whose twice as many
+            // threads hide the latency of a single iteration better: 19 against 25 us for 1.4 M points, with or without the
+            // staging prologue of the vector kernel)
+            if (exact && lut_tot <= kPlanSmemLut && count_vec_enabled() && n >= kCountVecMin &&
+                ((((uintptr_t)params) | ((uintptr_t)plan->slot)) & 15) == 0) {
                 const int gv = grid_for((n + 3) / 4, 256, plan_ctas_per_sm());   // >= 1 CTA: the tail runs on the first threads
                 if (space->ndim == 3) k_plan_count_vec<3><<<gv, 256, 0, st>>>(*space, params, (unsigned)n, plan->slot, plan->cell_count);
                 else k_plan_count_vec<2><<<gv, 256, 0, st>>>(*space, params, (unsigned)n, plan->slot, plan->cell_count);
