@@ -660,7 +660,12 @@ __global__ void __launch_bounds__(256) k_plan_items(const __grid_constant__ thb_
                                                     int nslots, int ppi, int max_items, int4* __restrict__ items) {
     __shared__ int4 s_rec[8][32][4];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    // The 32 cells of a warp lie nslots / 32 apart: cells with many work items (the coarse ones: 16 items each on config 3)
+    // sit next to each other in slot order, and a warp that owned 32 of them ran 3x longer than the kernel needs (the items
+    // of a cell beyond its first are written one cell after the other).
+    const int per_lane = (nslots + 31) >> 5;
+    const int gw = blockIdx.x * (blockDim.x >> 5) + wid;
+    const int s = gw < per_lane ? lane * per_lane + gw : nslots;
     const int sh = (ppi & (ppi - 1)) == 0 ? 31 - __clz(ppi) : -1;
     int c = 0, b = 0, it0 = 0, m = 0;
     if (s < nslots) {
