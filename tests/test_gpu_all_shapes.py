@@ -82,3 +82,30 @@ def test_shape_against_c_oracle(degrees):
     grev = torch.from_numpy(configs.greville_ctrl_pts(sp, bump=0.0)).cuda()
     rep = engine.eval_fused(P, supp.plan, grev)[0][:, :d].cpu().numpy()
     assert np.abs(rep - prm).max() <= TOL
+
+
+@pytest.mark.parametrize("degrees", [(2, 3), (3, 3), (3, 2, 3)], ids=lambda s: "p" + "".join(map(str, s)))
+def test_large_batches_take_the_vector_histogram_kernel(degrees):
+    """From 4 M points up thb_plan_build runs k_plan_count_vec (2-D and 3-D instantiations, four points per thread): slots
+    and histogram bit-identical to thb_active_span on a non-uniform three-level hierarchy, incl. breakpoints, the domain
+    ends, outside points, NaN and a tail that is not a multiple of four."""
+    from thb_diff_b200 import engine
+    from thb_diff_b200.packed import PackedHierarchy
+
+    d = len(degrees)
+    sp = _space(degrees, seed=3)
+    P = PackedHierarchy.from_space(sp, device="cuda")
+    g = torch.Generator(device="cuda").manual_seed(11)
+    rnd = torch.rand((4_100_001, d), device="cuda", generator=g)
+    kn = [torch.from_numpy(np.unique(np.asarray(sp.knotvectors[len(sp.knotvectors) - 1][k], dtype=np.float32))).cuda() for k in range(d)]
+    onk = torch.stack([kn[k][torch.randint(0, len(kn[k]), (60_000,), device="cuda", generator=g)] for k in range(d)], dim=1)
+    onk[::3] = torch.nextafter(onk[::3], torch.zeros_like(onk[::3]))
+    onk[1::3] = torch.nextafter(onk[1::3], torch.full_like(onk[1::3], 2.0))
+    special = torch.tensor([[0.0] * d, [1.0] * d, [-1e-7] + [0.5] * (d - 1), [0.5] * (d - 1) + [1.0000001],
+                            [float("nan")] + [0.5] * (d - 1), [0.5] * (d - 1) + [float("inf")]], device="cuda")
+    prm = torch.cat([rnd, onk, special]).contiguous()
+    plan = engine.Plan(P, prm)
+    ref, _ = engine.active_span(P, prm)
+    assert torch.equal(plan.slot[: prm.shape[0]], ref)
+    assert torch.equal(plan.cell_count[: P.nslots].long(), torch.bincount(ref[ref >= 0].long(), minlength=P.nslots))
+    assert int(plan.counters[2]) == int((ref >= 0).sum())

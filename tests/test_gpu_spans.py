@@ -75,6 +75,38 @@ def test_compute_active_span_bit_exact(name):
     assert np.array_equal(rec[:, : h.ndim], np.asarray(g["params"], dtype=np.float32)[perm])
 
 
+def test_plan_build_in_two_phases_equals_the_whole(tmp_path):
+    """thb_plan_build_phase 1 (histogram, scan, work items) + 2 (scatter) = thb_plan_build; plan_and_nets(overlap="scatter")
+    -- the nets beside the scatter pass -- evaluates to the same bits as the serial order."""
+    from thb_diff_b200 import configs, engine
+    from thb_diff_b200.packed import PackedHierarchy
+
+    sp = configs.cubic3d_space(active_levels=3)
+    P = PackedHierarchy.from_space(sp, device="cuda")
+    g = torch.Generator(device="cuda").manual_seed(1)
+    prm = torch.rand((200_000, 3), device="cuda", generator=g)
+    whole = engine.Plan(P, prm).canonicalize()
+    split = engine.Plan(P, prm)
+    split.sorted_params.zero_(); split.items.zero_(); split.cell_count.zero_(); split.slot.fill_(-7)
+    split.build(phase=1)
+    assert torch.equal(split.slot, whole.slot) and torch.equal(split.cell_count[: P.nslots], whole.cell_count[: P.nslots])
+    assert torch.equal(split.cell_start[: P.nslots + 1], whole.cell_start[: P.nslots + 1])
+    nit = int(whole.counters[0])
+    assert int(split.counters[0]) == nit and torch.equal(split.items[:nit], whole.items[:nit])
+    split.build(phase=2)
+    split.canonicalize()
+    n_in = int(whole.counters[2])
+    assert int(split.counters[2]) == n_in and torch.equal(split.sorted_params[:n_in], whole.sorted_params[:n_in])
+    cp = torch.from_numpy(configs.greville_ctrl_pts(sp)).cuda()
+    outs = []
+    for mode in (False, True, "scatter"):
+        nets = engine.plan_and_nets(P, split, cp, overlap=mode)
+        outs.append(engine.eval_nets(P, split, nets, 3, with_derivatives=False)[0].clone())
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    with pytest.raises(RuntimeError):
+        split.build(phase=3)
+
+
 def test_out_of_domain_points_are_flagged():
     from thb_diff_b200 import core
 
