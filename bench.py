@@ -317,8 +317,9 @@ def strong_block(P, cp, rank, world, device, cell_cost):
     out = [torch.zeros((pts.shape[0], 3), dtype=torch.float32, device=device)]
 
     def step():
-        plan.build()
-        nets = engine.cell_nets(P, cp, plan=plan)
+        # a slab is a small batch: the histogram pass first, then the nets of the touched cells on a second stream beside the
+        # rest of the plan (plan_and_nets picks that below 12 M points; the full batch keeps the nets beside the whole plan)
+        nets = engine.plan_and_nets(P, plan, cp, overlap="auto")
         engine.eval_nets(P, plan, nets, 3, out=out, with_derivatives=False)
 
     run, is_graph = graphed(step, device)

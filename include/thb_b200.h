@@ -172,10 +172,14 @@ THB_API int thb_expand_supports(const thb_space_desc* space, const int32_t* slot
  * Computes plan->slot itself (same result as thb_active_span). */
 THB_API int thb_plan_build(const thb_space_desc* space, const float* params, const thb_plan_desc* plan, void* stream);
 
-/* The same in two calls, so that a caller can put other work between them or beside the second:
- * phase 1 = histogram (plan->slot, cell_count), scan and work items -- everything thb_cell_nets needs to know which cells hold
- * points; phase 2 = the scatter of the points into cell order (HBM-bound; engine.plan_and_nets runs the nets kernel beside it). */
-THB_API int thb_plan_build_phase(const thb_space_desc* space, const float* params, const thb_plan_desc* plan, int phase,
+/* The same in up to three calls, so that a caller can put other work between or beside them.  `phases` is a combination of
+ * THB_PLAN_HISTOGRAM (plan->slot and cell_count -- everything thb_cell_nets needs to know which cells hold points),
+ * THB_PLAN_ITEMS (scan + work items) and THB_PLAN_SCATTER (the points into cell order), issued in that order over the calls.
+ * engine.plan_and_nets runs the nets kernel on a second stream beside the phases after the histogram. */
+#define THB_PLAN_HISTOGRAM 1
+#define THB_PLAN_ITEMS 2
+#define THB_PLAN_SCATTER 4
+THB_API int thb_plan_build_phase(const thb_space_desc* space, const float* params, const thb_plan_desc* plan, int phases,
                          void* stream);
 
 /* ---- THB_basis_fns (THB/core.py:604-701; float64 statement: compute_THB_fns_tp, core.py:203-268) -----------

@@ -17,9 +17,9 @@ bnd = grid_slab_bounds(P, axes, world, cell_cost=100.0).tolist()
 pts = bench.grid_slab(axes, bnd[rank], bnd[rank + 1])
 plan = engine.Plan(P, pts)
 out = [torch.zeros((pts.shape[0], 3), device=dev)]
+MODE = {"serial": False, "all": True}.get(os.environ.get("SLAB_OVERLAP", "serial"), os.environ.get("SLAB_OVERLAP", "serial"))
 def step():
-    plan.build()
-    nets = engine.cell_nets(P, cp, plan=plan)
+    nets = engine.plan_and_nets(P, plan, cp, overlap=MODE)
     engine.eval_nets(P, plan, nets, 3, out=out, with_derivatives=False)
 def t(fn, it=200, warm=20):
     for _ in range(warm): fn()
@@ -28,7 +28,7 @@ def t(fn, it=200, warm=20):
     for _ in range(it): fn()
     b.record(); torch.cuda.synchronize()
     return round(a.elapsed_time(b) / it, 4)
-res = {"world": world, "rank": rank, "planes": bnd[rank + 1] - bnd[rank], "points": pts.shape[0], "eager": t(step)}
+res = {"mode": str(MODE), "world": world, "rank": rank, "planes": bnd[rank + 1] - bnd[rank], "points": pts.shape[0], "eager": t(step)}
 run, isg = bench.graphed(step, dev)
 res["graph"] = t(run)
 ph = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(50)]

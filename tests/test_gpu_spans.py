@@ -76,8 +76,8 @@ def test_compute_active_span_bit_exact(name):
 
 
 def test_plan_build_in_two_phases_equals_the_whole(tmp_path):
-    """thb_plan_build_phase 1 (histogram, scan, work items) + 2 (scatter) = thb_plan_build; plan_and_nets(overlap="scatter")
-    -- the nets beside the scatter pass -- evaluates to the same bits as the serial order."""
+    """thb_plan_build_phase: histogram, then scan + work items, then scatter = thb_plan_build; every overlap mode of
+    plan_and_nets (the nets beside different parts of the plan, on a second stream) evaluates to the same bits."""
     from thb_diff_b200 import configs, engine
     from thb_diff_b200.packed import PackedHierarchy
 
@@ -88,23 +88,24 @@ def test_plan_build_in_two_phases_equals_the_whole(tmp_path):
     whole = engine.Plan(P, prm).canonicalize()
     split = engine.Plan(P, prm)
     split.sorted_params.zero_(); split.items.zero_(); split.cell_count.zero_(); split.slot.fill_(-7)
-    split.build(phase=1)
+    split.build(phase=engine.PLAN_HISTOGRAM)
     assert torch.equal(split.slot, whole.slot) and torch.equal(split.cell_count[: P.nslots], whole.cell_count[: P.nslots])
+    split.build(phase=engine.PLAN_ITEMS)
     assert torch.equal(split.cell_start[: P.nslots + 1], whole.cell_start[: P.nslots + 1])
     nit = int(whole.counters[0])
     assert int(split.counters[0]) == nit and torch.equal(split.items[:nit], whole.items[:nit])
-    split.build(phase=2)
+    split.build(phase=engine.PLAN_SCATTER)
     split.canonicalize()
     n_in = int(whole.counters[2])
     assert int(split.counters[2]) == n_in and torch.equal(split.sorted_params[:n_in], whole.sorted_params[:n_in])
     cp = torch.from_numpy(configs.greville_ctrl_pts(sp)).cuda()
     outs = []
-    for mode in (False, True, "scatter"):
+    for mode in (False, True, "scatter", "after_histogram", "auto"):
         nets = engine.plan_and_nets(P, split, cp, overlap=mode)
         outs.append(engine.eval_nets(P, split, nets, 3, with_derivatives=False)[0].clone())
-    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    assert all(torch.equal(outs[0], o) for o in outs[1:])
     with pytest.raises(RuntimeError):
-        split.build(phase=3)
+        split.build(phase=8)
 
 
 def test_out_of_domain_points_are_flagged():

@@ -914,8 +914,8 @@ extern "C" int thb_expand_supports(const thb_space_desc* space, const int32_t* s
     return THB_OK;
 }
 
-// phases: bit 0 = histogram + scan + work items (everything the nets of the touched cells and the item list need),
-// bit 1 = scatter of the points into cell order
+// phases (THB_PLAN_*): histogram (slot per point + points per cell: all the nets of the touched cells need), scan + work
+// items, scatter of the points into cell order
 static int plan_build_impl(const thb_space_desc* space, const float* params, const thb_plan_desc* plan, void* stream, int phases) {
     int rc = thb_check_space(space, "thb_plan_build");
     if (rc) return rc;
@@ -930,68 +930,71 @@ static int plan_build_impl(const thb_space_desc* space, const float* params, con
     const int64_t n = plan->npoints;
     const int ns = space->nslots;
     THB_REQUIRE(n == 0 || params, "thb_plan_build: null params");
-    if (phases & 1) {
-    THB_CUDA(cudaMemsetAsync(plan->cell_count, 0, sizeof(int32_t) * (ns + 1), st));
-    if (n > 0) {
-        int finest_knots = 0;
-        for (int k = 0; k < space->ndim; ++k) finest_knots += space->knot_len[space->nlevels - 1][k];
-        if (space->span_lut && space->finest_slot && finest_knots <= kPlanSmemKnots) {
-            THB_CUDA(cudaMemsetAsync(plan->counters + 3, 0, sizeof(int32_t), st));
-            // plan->scratch holds the (normally empty) list of unverified points
-            const int lut_tot = space->lut_off[space->ndim - 1] + space->lut_n[space->ndim - 1];
-            const int g = grid_for(n, 256, plan_ctas_per_sm());
-            const bool exact = space->lut_exact != 0;   // spans proven by the host: no verification, no fix-up pass
-            // (small batches -- a rank's slab, a chunk of the host pipeline -- keep the scalar kernel, whose twice as many
-            // threads hide the latency of a single iteration better: 19 against 25 us for 1.4 M points, with or without the
-            // staging prologue of the vector kernel)
-            if (exact && lut_tot <= kPlanSmemLut && count_vec_enabled() && n >= kCountVecMin &&
-                ((((uintptr_t)params) | ((uintptr_t)plan->slot)) & 15) == 0) {
-                const int gv = grid_for((n + 3) / 4, 256, plan_ctas_per_sm());   // >= 1 CTA: the tail runs on the first threads
-                if (space->ndim == 3) k_plan_count_vec<3><<<gv, 256, 0, st>>>(*space, params, (unsigned)n, plan->slot, plan->cell_count);
-                else k_plan_count_vec<2><<<gv, 256, 0, st>>>(*space, params, (unsigned)n, plan->slot, plan->cell_count);
-                THB_LAUNCHED();
-            } else {
+    if (phases & THB_PLAN_HISTOGRAM) {
+        THB_CUDA(cudaMemsetAsync(plan->cell_count, 0, sizeof(int32_t) * (ns + 1), st));
+        if (n > 0) {
+            int finest_knots = 0;
+            for (int k = 0; k < space->ndim; ++k) finest_knots += space->knot_len[space->nlevels - 1][k];
+            if (space->span_lut && space->finest_slot && finest_knots <= kPlanSmemKnots) {
+                THB_CUDA(cudaMemsetAsync(plan->counters + 3, 0, sizeof(int32_t), st));
+                // plan->scratch holds the (normally empty) list of unverified points
+                const int lut_tot = space->lut_off[space->ndim - 1] + space->lut_n[space->ndim - 1];
+                const int g = grid_for(n, 256, plan_ctas_per_sm());
+                const bool exact = space->lut_exact != 0;   // spans proven by the host: no verification, no fix-up pass
+                // (small batches -- a rank's slab, a chunk of the host pipeline -- keep the scalar kernel, whose twice as many
+                // threads hide the latency of a single iteration better: 19 against 25 us for 1.4 M points, with or without
+                // the staging prologue of the vector kernel; one wave of 6 resident CTAs per SM for the vector kernel was
+                // measured too: 0.220 instead of 0.204 ms for the plan of config 3)
+                if (exact && lut_tot <= kPlanSmemLut && count_vec_enabled() && n >= kCountVecMin &&
+                    ((((uintptr_t)params) | ((uintptr_t)plan->slot)) & 15) == 0) {
+                    const int gv = grid_for((n + 3) / 4, 256, plan_ctas_per_sm());   // >= 1 CTA: the tail runs on the first threads
+                    if (space->ndim == 3) k_plan_count_vec<3><<<gv, 256, 0, st>>>(*space, params, (unsigned)n, plan->slot, plan->cell_count);
+                    else k_plan_count_vec<2><<<gv, 256, 0, st>>>(*space, params, (unsigned)n, plan->slot, plan->cell_count);
+                    THB_LAUNCHED();
+                } else {
 #define THB_COUNT(D_, S_)                                                                                                        \
     do {                                                                                                                        \
         if (exact) k_plan_count_fast<D_, S_, true><<<g, 256, 0, st>>>(*space, params, (unsigned)n, plan->slot, plan->cell_count, plan->scratch, plan->counters); \
         else k_plan_count_fast<D_, S_, false><<<g, 256, 0, st>>>(*space, params, (unsigned)n, plan->slot, plan->cell_count, plan->scratch, plan->counters); \
     } while (0)
-            if (space->ndim == 3) { if (lut_tot <= kPlanSmemLut) THB_COUNT(3, true); else THB_COUNT(3, false); }
-            else { if (lut_tot <= kPlanSmemLut) THB_COUNT(2, true); else THB_COUNT(2, false); }
+                    if (space->ndim == 3) { if (lut_tot <= kPlanSmemLut) THB_COUNT(3, true); else THB_COUNT(3, false); }
+                    else { if (lut_tot <= kPlanSmemLut) THB_COUNT(2, true); else THB_COUNT(2, false); }
 #undef THB_COUNT
-            THB_LAUNCHED();
-            if (!exact) {
-                k_plan_fixup<<<thb_num_sms(), 256, 0, st>>>(*space, params, plan->scratch, plan->counters, plan->slot, plan->cell_count);
+                    THB_LAUNCHED();
+                    if (!exact) {
+                        k_plan_fixup<<<thb_num_sms(), 256, 0, st>>>(*space, params, plan->scratch, plan->counters, plan->slot, plan->cell_count);
+                        THB_LAUNCHED();
+                    }
+                }
+            } else {
+                k_plan_count<<<grid_for(n, 256, 16), 256, 0, st>>>(*space, params, n, plan->slot, plan->cell_count);
                 THB_LAUNCHED();
             }
-            }
-        } else {
-            k_plan_count<<<grid_for(n, 256, 16), 256, 0, st>>>(*space, params, n, plan->slot, plan->cell_count);
-            THB_LAUNCHED();
         }
     }
-    const int ntile = (ns + kScanTile - 1) / kScanTile;
-    if (ntile >= 4 && n >= 2 * (int64_t)ntile && (((uintptr_t)plan->scratch) & 3) == 0) {
-        // plan->scratch is free between the fix-up pass and the end of the plan: it holds the per-tile totals
-        k_plan_scan_sums<<<ntile, 1024, 0, st>>>(plan->cell_count, ns, plan->points_per_item, plan->scratch);
-        THB_LAUNCHED();
-        k_plan_scan_write<<<ntile, 1024, 0, st>>>(plan->cell_count, plan->cell_start, plan->cell_cursor, ns, plan->points_per_item,
-                                                  plan->scratch, plan->counters);
-        THB_LAUNCHED();
-    } else {
-        k_plan_scan<<<1, 1024, 0, st>>>(plan->cell_count, plan->cell_start, plan->cell_cursor, ns, plan->points_per_item, plan->counters);
+    if (phases & THB_PLAN_ITEMS) {
+        const int ntile = (ns + kScanTile - 1) / kScanTile;
+        if (ntile >= 4 && n >= 2 * (int64_t)ntile && (((uintptr_t)plan->scratch) & 3) == 0) {
+            // plan->scratch is free between the fix-up pass and the end of the plan: it holds the per-tile totals
+            k_plan_scan_sums<<<ntile, 1024, 0, st>>>(plan->cell_count, ns, plan->points_per_item, plan->scratch);
+            THB_LAUNCHED();
+            k_plan_scan_write<<<ntile, 1024, 0, st>>>(plan->cell_count, plan->cell_start, plan->cell_cursor, ns, plan->points_per_item,
+                                                      plan->scratch, plan->counters);
+            THB_LAUNCHED();
+        } else {
+            k_plan_scan<<<1, 1024, 0, st>>>(plan->cell_count, plan->cell_start, plan->cell_cursor, ns, plan->points_per_item, plan->counters);
+            THB_LAUNCHED();
+        }
+        k_plan_items<<<(ns + 255) / 256, 256, 0, st>>>(*space, plan->cell_count, plan->cell_start, plan->cell_cursor, ns, plan->points_per_item,
+                                                       plan->max_items, (int4*)plan->items);
         THB_LAUNCHED();
     }
-    k_plan_items<<<(ns + 255) / 256, 256, 0, st>>>(*space, plan->cell_count, plan->cell_start, plan->cell_cursor, ns, plan->points_per_item,
-                                                   plan->max_items, (int4*)plan->items);
-    THB_LAUNCHED();
-    }
-    if ((phases & 2) && n > 0) {
+    if ((phases & THB_PLAN_SCATTER) && n > 0) {
         if (plan->light) {   // permutation only; plan->scratch is free from here on
             k_plan_scatter_light<<<grid_for(n, 256, scatter_ctas_per_sm()), 256, 0, st>>>(plan->slot, n, plan->cell_cursor, plan->scratch);
         } else {
             k_plan_scatter<<<grid_for(n, 256, scatter_ctas_per_sm()), 256, 0, st>>>(plan->slot, params, space->ndim, n, plan->cell_cursor,
-                                                                 (float4*)plan->sorted_params);
+                                                                                     (float4*)plan->sorted_params);
         }
         THB_LAUNCHED();
     }
@@ -999,13 +1002,14 @@ static int plan_build_impl(const thb_space_desc* space, const float* params, con
 }
 
 extern "C" int thb_plan_build(const thb_space_desc* space, const float* params, const thb_plan_desc* plan, void* stream) {
-    return plan_build_impl(space, params, plan, stream, 3);
+    return plan_build_impl(space, params, plan, stream, THB_PLAN_HISTOGRAM | THB_PLAN_ITEMS | THB_PLAN_SCATTER);
 }
 
-extern "C" int thb_plan_build_phase(const thb_space_desc* space, const float* params, const thb_plan_desc* plan, int phase,
+extern "C" int thb_plan_build_phase(const thb_space_desc* space, const float* params, const thb_plan_desc* plan, int phases,
                                     void* stream) {
-    THB_REQUIRE(phase == 1 || phase == 2, "thb_plan_build_phase: phase must be 1 (histogram, scan, work items) or 2 (scatter)");
-    return plan_build_impl(space, params, plan, stream, phase);
+    THB_REQUIRE(phases >= 1 && phases <= (THB_PLAN_HISTOGRAM | THB_PLAN_ITEMS | THB_PLAN_SCATTER),
+                "thb_plan_build_phase: phases must be a combination of THB_PLAN_HISTOGRAM, THB_PLAN_ITEMS, THB_PLAN_SCATTER");
+    return plan_build_impl(space, params, plan, stream, phases);
 }
 
 extern "C" int thb_plan_records(const thb_space_desc* space, const float* params, const thb_plan_desc* plan, void* stream) {

@@ -13,6 +13,7 @@ import os as _os
 POINTS_PER_ITEM = int(_os.environ.get("THB_POINTS_PER_ITEM", "256"))  # points per work item (multiple of 64)
 
 CH_VALUE = 0
+PLAN_HISTOGRAM, PLAN_ITEMS, PLAN_SCATTER = 1, 2, 4   # thb_plan_build_phase
 
 
 def grad_channels(ndim):
@@ -78,7 +79,8 @@ class Plan:
         self.build()
 
     def build(self, phase=None):
-        """phase None: the whole plan.  1: histogram + scan + work items, 2: the scatter (thb_plan_build_phase)."""
+        """phase None: the whole plan; else a combination of PLAN_HISTOGRAM, PLAN_ITEMS, PLAN_SCATTER (thb_plan_build_phase),
+        issued in that order over the calls."""
         self.version = self.P.version
         self.desc.light = 1 if self.light else 0
         self.desc.params = self.params.data_ptr()
@@ -260,11 +262,26 @@ def cell_nets(P, ctrl_pts, with_derivatives=False, plan=None, out=None, monomial
     return nets
 
 
-def plan_and_nets(P, plan, ctrl_pts, with_derivatives=False, overlap=True):
-    """plan.build() and the local control nets of ctrl_pts, enqueued so that they run CONCURRENTLY: the nets depend on the
-    hierarchy and the control points only, not on the points, so they are built on a side stream (for every cell) while the
-    plan kernels sort the batch on the current stream; the current stream then waits for the nets.  Returns the nets.
-    overlap=False: plan first, then the nets of the cells that hold points, on one stream."""
+SMALL_BATCH = int(_os.environ.get("THB_SMALL_BATCH", "12000000"))   # plan_and_nets(overlap="auto"): below this many points the
+                                                                    # nets go beside the plan's later phases
+
+
+def plan_and_nets(P, plan, ctrl_pts, with_derivatives=False, overlap="auto"):
+    """plan.build() and the local control nets of ctrl_pts, enqueued so that they run CONCURRENTLY on two streams; the current
+    stream then waits for the nets.  Returns the nets.  overlap:
+      True               the nets of EVERY cell beside the whole plan (they depend on the hierarchy and the control points only).
+                         Best for large batches: 0.443 against 0.477 ms serial on config 3 (16.8 M points); both kernels fill the
+                         SMs, so in effect the nets run first and their tail shares the machine with the histogram pass.
+      "after_histogram"  histogram pass first, then the nets of the cells that HOLD POINTS beside scan + work items + scatter.
+                         Best below the full batch (a rank's slab, a chunk), whose kernels run at their latency and leave the SMs
+                         half empty -- measured on slabs of the config-3 grid, serial / this / True: 1/8 (1.4 M points, 14 k of
+                         52 k cells) 0.114 / 0.103 / 0.160 ms, 1/4 0.172 / 0.163 / 0.192, 1/2 0.284 / 0.279 / 0.297; for the full
+                         batch it equals the serial order (0.485 against 0.450 ms).
+      "scatter"          the nets beside the scatter pass alone (measured: never better than the other two).
+      "auto" (default)   True from SMALL_BATCH (12 M) points up, "after_histogram" below.
+      False              plan first, then the nets of the cells that hold points, on one stream."""
+    if overlap == "auto":
+        overlap = True if plan.n >= SMALL_BATCH else "after_histogram"
     if not overlap:
         plan.build()
         return cell_nets(P, ctrl_pts, with_derivatives, plan=plan)
@@ -272,14 +289,13 @@ def plan_and_nets(P, plan, ctrl_pts, with_derivatives=False, overlap=True):
     side = getattr(P, "_side_stream", None)
     if side is None:
         side = P._side_stream = torch.cuda.Stream(device=P.device)
-    if overlap == "scatter":
-        # the nets (issue / latency-bound) beside the SCATTER pass alone (HBM-bound): the histogram pass is issue-bound
-        # itself and gains nothing from company; the nets are built for the cells that hold points
-        plan.build(phase=1)
+    if overlap in ("after_histogram", "scatter"):
+        first = PLAN_HISTOGRAM if overlap == "after_histogram" else PLAN_HISTOGRAM | PLAN_ITEMS
+        plan.build(phase=first)
         side.wait_stream(cur)
         with torch.cuda.stream(side):
             nets = cell_nets(P, ctrl_pts, with_derivatives, plan=plan, ctas_per_sm=int(_os.environ.get("THB_OVERLAP_NETS_CTAS", "0")))
-        plan.build(phase=2)
+        plan.build(phase=(PLAN_HISTOGRAM | PLAN_ITEMS | PLAN_SCATTER) & ~first)
         cur.wait_stream(side)
         return nets
     side.wait_stream(cur)
