@@ -1,4 +1,4 @@
-// THB_eval.forward (compute_pts_cuda_kernels.cu:3-26) from BULK-STAGED segments.
+// THB_eval.forward / backward (compute_pts_cuda_kernels.cu:3-26, 28-47) from BULK-STAGED segments.
 //
 // The register-path kernel of thb_eval_csr.cu (lane = entry, coalesced loads, control points cached in registers while
 // consecutive points share a support list) is limited by the bytes a warp can keep in flight: its loads live in registers
@@ -56,7 +56,8 @@ struct BulkWarpBwd {
 #endif
 template <typename JT>
 struct BulkCfg {
-    static constexpr int kWarps = sizeof(JT) == 8 ? THB_BULK_WARPS64 : THB_BULK_WARPS32;   // autonomous warps per CTA (one CTA per SM: ~220 KB of stages)
+    // autonomous warps per CTA (one CTA per SM: 200-225 KB of stages; 128 registers per thread at 16 warps)
+    static constexpr int kWarps = sizeof(JT) == 8 ? THB_BULK_WARPS64 : THB_BULK_WARPS32;
 };
 
 constexpr int kChunkPts = kChunkPtsMax;   // points per chunk at most (two reduce8 batches)
@@ -78,7 +79,8 @@ THB_DEV int64_t load_end(const CT* __restrict__ cumsum, int64_t p, int64_t p1, i
     return p + lane < p1 ? (int64_t)__ldg(cumsum + p + lane) : (int64_t)-1;
 }
 
-// up to 32 points from p (< p1) whose entries fit one stage; `end` = load_end(p)
+// up to kChunkPts points from p (< p1) whose entries fit one stage; `end` = load_end(p).  gtot / cpd (backward): the number
+// of floats of grad_out, whose rows [p, p + m) are staged too
 THB_DEV Chunk describe(int64_t end, int64_t p, int64_t p1, int64_t base, int64_t nnz, int esz_jm, int lane, int64_t gtot = 0, int cpd = 0) {
     Chunk c;
     c.p = p; c.base = base; c.m = 0; c.npairs = 0; c.my_beg = 0; c.my_end = 0; c.bulk = false;
@@ -99,12 +101,11 @@ THB_DEV Chunk describe(int64_t end, int64_t p, int64_t p1, int64_t base, int64_t
     const int up = __shfl_up_sync(0xffffffffu, c.my_end, 1);
     c.my_beg = lane == 0 ? 0 : up;
     if (c.bulk) {   // the copies are rounded out to 16 bytes: they must stay inside the arrays
-        const int64_t a0 = base & ~(int64_t)3, end4 = (base + tot + 3) & ~(int64_t)3;
+        const int64_t end4 = (base + tot + 3) & ~(int64_t)3;
         const int per16 = 16 / esz_jm;
         const int64_t endj = (base + tot + per16 - 1) / per16 * per16;
         if (end4 > nnz || endj > nnz || tot == 0) c.bulk = false;   // (nothing to copy: the points have no supports)
         if (gtot > 0 && (((p + m) * cpd + 3) & ~(int64_t)3) > gtot) c.bulk = false;
-        (void)a0;
     }
     return c;
 }
@@ -227,7 +228,6 @@ __global__ void __launch_bounds__(32 * BulkCfg<JT>::kWarps, 1) k_csr_forward_bul
                 if ((lane & 3) == 0 && i0 + mine < np) out[(cur.p + i0 + mine) * CPD + k] = r;
             }
         }
-        (void)cphi; (void)cjm;
         __syncwarp();
         // the stage just read is free: the chunk after next goes there
         Chunk nn = describe(end_after, p_after, p1, nxt.base + nxt.npairs, nnz, ej, lane);
