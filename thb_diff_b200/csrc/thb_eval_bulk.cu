@@ -87,9 +87,9 @@ THB_DEV Chunk describe(int64_t end, int64_t p, int64_t p1, int64_t base, int64_t
     if (p >= p1) return c;
     const bool in = end >= 0 && lane < kChunkPts;
     const int64_t rel = in ? end - base : 0;
-    const bool fits = in && rel <= (int64_t)kCap;
-    const unsigned mask = __ballot_sync(0xffffffffu, fits);   // cumsum is non-decreasing: a prefix of the lanes
-    int m = __popc(mask);
+    const bool fits = in && rel >= 0 && rel <= (int64_t)kCap;
+    const unsigned mask = __ballot_sync(0xffffffffu, fits);   // cumsum is non-decreasing: a prefix of the lanes ...
+    int m = __ffs(~mask) - 1;                                 // ... and if it is not (invalid input), the copies stay bounded
     c.bulk = m > 0;
     if (m == 0) m = 1;   // one over-long segment: walked from global memory by lane 0
     c.m = m;

@@ -936,8 +936,6 @@ static int plan_build_impl(const thb_space_desc* space, const float* params, con
             int finest_knots = 0;
             for (int k = 0; k < space->ndim; ++k) finest_knots += space->knot_len[space->nlevels - 1][k];
             if (space->span_lut && space->finest_slot && finest_knots <= kPlanSmemKnots) {
-                THB_CUDA(cudaMemsetAsync(plan->counters + 3, 0, sizeof(int32_t), st));
-                // plan->scratch holds the (normally empty) list of unverified points
                 const int lut_tot = space->lut_off[space->ndim - 1] + space->lut_n[space->ndim - 1];
                 const int g = grid_for(n, 256, plan_ctas_per_sm());
                 const bool exact = space->lut_exact != 0;   // spans proven by the host: no verification, no fix-up pass
@@ -952,6 +950,8 @@ static int plan_build_impl(const thb_space_desc* space, const float* params, con
                     else k_plan_count_vec<2><<<gv, 256, 0, st>>>(*space, params, (unsigned)n, plan->slot, plan->cell_count);
                     THB_LAUNCHED();
                 } else {
+                    // plan->scratch holds the (normally empty) list of unverified points, counters[3] their number
+                    THB_CUDA(cudaMemsetAsync(plan->counters + 3, 0, sizeof(int32_t), st));
 #define THB_COUNT(D_, S_)                                                                                                        \
     do {                                                                                                                        \
         if (exact) k_plan_count_fast<D_, S_, true><<<g, 256, 0, st>>>(*space, params, (unsigned)n, plan->slot, plan->cell_count, plan->scratch, plan->counters); \
