@@ -10,7 +10,10 @@ from ._lib import OrderedDesc, PlanDesc, check, lib, ptr, require_cuda, stream_p
 
 import os as _os
 
-POINTS_PER_ITEM = int(_os.environ.get("THB_POINTS_PER_ITEM", "256"))  # points per work item (multiple of 64)
+# points per work item (multiple of 64).  Measured on config 3, 128 / 256 / 512 / 1024: evaluation kernel 0.188 / 0.176 / 0.171 /
+# 0.174 ms, fused backward 0.556 / 0.541 / 0.528 / 0.529 ms, pass 0.454 / 0.442 / 0.436 / 0.438 ms (an item switch costs a net
+# load and a pipeline refill; beyond 512 the tail of the persistent kernels grows)
+POINTS_PER_ITEM = int(_os.environ.get("THB_POINTS_PER_ITEM", "512"))
 
 CH_VALUE = 0
 PLAN_HISTOGRAM, PLAN_ITEMS, PLAN_SCATTER = 1, 2, 4   # thb_plan_build_phase
@@ -54,6 +57,8 @@ class Plan:
         self.P = P
         if light is None:
             light = _os.environ.get("THB_PLAN_LIGHT", "0") not in ("0", "")
+        if light and points_per_item > 256 and getattr(P, "poly", None) is not None:
+            points_per_item = 256   # a light plan's items are gathered through index buffers of 256 entries
         self.light = bool(light) and points_per_item <= 256 and getattr(P, "poly", None) is not None
         self.params = _as_params(params, P.ndim, P.device)
         n = self.params.shape[0]
