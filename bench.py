@@ -764,7 +764,8 @@ def main():
     elif args.formulation == "tile_net":  # per point the tensor product and the window dot products; all tiles folded per item
         cnt = plan.cell_count[: P.nslots].long()
         nt = (P.cellinfo[:, 5] - P.cellinfo[:, 7]).long()
-        items = (cnt + engine.POINTS_PER_ITEM - 1) // engine.POINTS_PER_ITEM
+        ppi = int(plan.desc.points_per_item)
+        items = (cnt + ppi - 1) // ppi
         f_exec = flop_model(P.degrees, 3, n_in, 0, 0)[0] + float((items * nt).sum()) * P.T * 2 * 4
     tile_bytes = (P.sep_vec.numel() + P.full_tiles.numel()) * 4 if (getattr(P, "sep_vec", None) is not None and args.formulation != "tile_net") else P.tiles.numel() * 4
     if args.formulation == "local_net":  # evaluation kernel: 16-byte point records in, geometry out, one net per work item

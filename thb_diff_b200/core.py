@@ -235,7 +235,7 @@ def compute_active_span(params, knotvectors, cells, degrees, ac_cells_ac_supp, d
         P = _packed_from_dict(knotvectors, cells, degrees, ac_cells_ac_supp, device)
     # this plan feeds THB_basis_fns (k_basis_rows), which is fastest with 256 points per work item (1.72 against 2.13 ms at
     # 512 on config 3); the fused path plans its own batches with engine.POINTS_PER_ITEM
-    plan = engine.Plan(P, params, points_per_item=min(256, engine.POINTS_PER_ITEM))
+    plan = engine.Plan(P, params, points_per_item=min(256, engine.POINTS_PER_ITEM or 256))
     ns = plan.num_supp()
     supp = PointSupports(P, plan, ns)
     return supp, NumSupp(ns)

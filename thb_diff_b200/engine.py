@@ -10,10 +10,19 @@ from ._lib import OrderedDesc, PlanDesc, check, lib, ptr, require_cuda, stream_p
 
 import os as _os
 
-# points per work item (multiple of 64).  Measured on config 3, 128 / 256 / 512 / 1024: evaluation kernel 0.188 / 0.176 / 0.171 /
-# 0.174 ms, fused backward 0.556 / 0.541 / 0.528 / 0.529 ms, pass 0.454 / 0.442 / 0.436 / 0.438 ms (an item switch costs a net
-# load and a pipeline refill; beyond 512 the tail of the persistent kernels grows)
-POINTS_PER_ITEM = int(_os.environ.get("THB_POINTS_PER_ITEM", "512"))
+# Points per work item (multiple of 64).  Measured on config 3 (16.8 M points), 128 / 256 / 512 / 1024: evaluation kernel 0.188 /
+# 0.176 / 0.171 / 0.174 ms, fused backward 0.556 / 0.541 / 0.528 / 0.529 ms, pass 0.454 / 0.442 / 0.436 / 0.438 ms (an item
+# switch costs a net load and a pipeline refill).  Small batches want more, smaller items for the ~2400 resident warps of the
+# persistent kernels: with 512 the strong-scaling step of a 1/8 slab went from 0.117 to 0.132 ms and the 8-GPU fit from 5 045 to
+# 4 564 steps/s.  THB_POINTS_PER_ITEM overrides the choice.
+POINTS_PER_ITEM = int(_os.environ.get("THB_POINTS_PER_ITEM", "0"))   # 0: by batch size
+LARGE_BATCH_ITEMS = 8_000_000
+
+
+def points_per_item_for(n):
+    if POINTS_PER_ITEM:
+        return POINTS_PER_ITEM
+    return 512 if n >= LARGE_BATCH_ITEMS else 256
 
 CH_VALUE = 0
 PLAN_HISTOGRAM, PLAN_ITEMS, PLAN_SCATTER = 1, 2, 4   # thb_plan_build_phase
@@ -48,19 +57,21 @@ def _as_params(params, ndim, device):
 class Plan:
     """The points of one batch grouped by active cell (device resident)."""
 
-    def __init__(self, P, params, points_per_item=POINTS_PER_ITEM, capacity=None, light=None):
+    def __init__(self, P, params, points_per_item=None, capacity=None, light=None):
         """light (default off; THB_PLAN_LIGHT=1): thb_plan_build writes only the permutation of the points (4 bytes per
         point instead of a 16-byte record, and it does not re-read the parameters); eval_nets gathers the parameters
         through it.  Every other consumer (PHI rows, the per-point formulations, the backward, caller_index) materialises
         the records on first use (ensure_records).  Measured on config 3: plan 0.207 -> 0.154 ms, evaluation kernel 0.176
         -> 0.207 ms (three 4-byte gathers per point instead of one 16-byte record), pass 0.467 -> 0.443 ms."""
         self.P = P
+        self.params = _as_params(params, P.ndim, P.device)
+        if points_per_item is None:
+            points_per_item = points_per_item_for(max(int(self.params.shape[0]), int(capacity or 0)))
         if light is None:
             light = _os.environ.get("THB_PLAN_LIGHT", "0") not in ("0", "")
         if light and points_per_item > 256 and getattr(P, "poly", None) is not None:
             points_per_item = 256   # a light plan's items are gathered through index buffers of 256 entries
         self.light = bool(light) and points_per_item <= 256 and getattr(P, "poly", None) is not None
-        self.params = _as_params(params, P.ndim, P.device)
         n = self.params.shape[0]
         dev = P.device
         i32 = dict(dtype=torch.int32, device=dev)
