@@ -47,6 +47,22 @@ def test_descriptor_layout_matches_header(tmp_path):
             assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, f"{cname}.{fname}"
 
 
+def test_plan_phase_constants_and_item_size_policy():
+    """The Python mirror of the THB_PLAN_* phase bits equals the header's; work items hold 512 points in large batches and
+    256 in small ones unless THB_POINTS_PER_ITEM fixes the size."""
+    from thb_diff_b200 import engine
+
+    hdr = open(os.path.join(ROOT, "include", "thb_b200.h")).read()
+    consts = dict(re.findall(r"#define\s+(THB_PLAN_\w+)\s+(\d+)", hdr))
+    assert (int(consts["THB_PLAN_HISTOGRAM"]), int(consts["THB_PLAN_ITEMS"]), int(consts["THB_PLAN_SCATTER"])) == (
+        engine.PLAN_HISTOGRAM, engine.PLAN_ITEMS, engine.PLAN_SCATTER) == (1, 2, 4)
+    if engine.POINTS_PER_ITEM == 0:
+        assert engine.points_per_item_for(16_777_216) == 512 and engine.points_per_item_for(2_000_000) == 256
+        assert engine.points_per_item_for(engine.LARGE_BATCH_ITEMS) == 512
+    else:
+        assert engine.points_per_item_for(1) == engine.POINTS_PER_ITEM
+
+
 def test_no_cpu_fallback():
     import torch
 
